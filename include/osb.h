@@ -1,0 +1,185 @@
+/*
+ * osb.h -- C ABI of the B200-native Orr-Sommerfeld engine (libosb.so).
+ *
+ * This is the drop-in boundary for the one data-parallel hot path of
+ * sscollis/os-stab: the per-point eigenvalue solves behind the reference's
+ * Fortran-77 operator interfaces.  Each entry point below names the reference
+ * interface it replaces (file:line into the reference tree).  The reference has
+ * no FFI of its own; INTEGRATION.md shows the ISO_C_BINDING interface block and
+ * the one-line change in each driver that binds these symbols.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only; complex data is interleaved
+ *     (re, im) double pairs == Fortran complex(c_double_complex) == CUDA double2.
+ *   - All physical quantities are in the SOLVER's units, i.e. what the reference
+ *     passes to CONTE/CONTE_IC after its driver-side rescale (contebl.f:181-182,
+ *     orrspace.f:160-168).
+ *   - Every function returns 0 on success, a negative OSB_E_* code otherwise;
+ *     osb_last_error() returns the message.  Per-point outcomes travel in the
+ *     `status` arrays (OSB_ST_*).  Nothing here falls back to a CPU path: with
+ *     no usable CUDA device every call fails with OSB_E_CUDA.
+ *   - `*_dev` variants take DEVICE pointers (inputs already resident in HBM);
+ *     the plain variants take HOST pointers and do the copies themselves.
+ *   - A context owns one CUDA device (one process per GPU is the intended
+ *     deployment; osb_create_multi() drives several devices from one host
+ *     thread for the single-process Fortran hosts).
+ */
+#ifndef OSB_H
+#define OSB_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OSB_VERSION 1
+
+/* error codes */
+#define OSB_OK 0
+#define OSB_E_ARG (-1)   /* bad argument                                     */
+#define OSB_E_CUDA (-2)  /* CUDA runtime error / no device                   */
+#define OSB_E_ALLOC (-3) /* out of memory                                    */
+#define OSB_E_STATE (-4) /* object used before it is ready                   */
+
+/* per-point status */
+#define OSB_ST_CONVERGED 0 /* eigenvalue loop left by tolerance               */
+#define OSB_ST_MAXCOUNT 1  /* left by the pass limit (shoot.f:478-479)        */
+#define OSB_ST_NONFINITE 2 /* NaN/Inf met (the reference would SIGFPE)        */
+
+/* flows: which reference driver's iteration is reproduced */
+#define OSB_FLOW_CONTEBL 0  /* CONTE_IC via contebl.f:205   (shoot.f:391-813) */
+#define OSB_FLOW_CONTE 1    /* CONTE via conte.f:131        (shoot.f:26-388)  */
+#define OSB_FLOW_ORRSOM 2   /* private CONTE orrsom.f:165-506                 */
+#define OSB_FLOW_ORRSPACE 3 /* private CONTE orrspace.f:209-582 (spatial)     */
+
+/* integrators (gcc.mak:46-48: USE_RKCK45 or the default RK4) */
+#define OSB_INT_RK4 0
+#define OSB_INT_CK45 1
+
+typedef struct osb_ctx osb_ctx;
+typedef struct osb_profile osb_profile;
+
+/* ---- context ---------------------------------------------------------- */
+int osb_version(void);
+/* one context bound to CUDA device `device` */
+int osb_create(osb_ctx **ctx, int device);
+/* one context driving `ndev` devices (ndev = 0: all visible) from one thread */
+int osb_create_multi(osb_ctx **ctx, int ndev, const int *devices);
+int osb_destroy(osb_ctx *ctx);
+int osb_device_count(const osb_ctx *ctx);
+const char *osb_last_error(const osb_ctx *ctx);
+/* the stream the context launches on (as a cudaStream_t cast to void*) for
+ * device 0 of the context; lets a caller time the kernels with CUDA events */
+void *osb_stream(osb_ctx *ctx);
+/* number of kernels launched by this context so far */
+int64_t osb_launch_count(const osb_ctx *ctx);
+
+/* ---- mean profile (replaces SOLVE_BL: contebl.f:386-533, orrsom.f:687-804,
+ *      orrspace.f:697-817; and the analytic CHANNEL conte.f:311-323) -------- */
+/* Solve the Blasius / Falkner-Skan similarity equation on the device and keep
+ * the tables resident.  variant = OSB_FLOW_CONTEBL | _ORRSOM | _ORRSPACE picks
+ * which copy of SOLVE_BL is reproduced (integrator is honoured by CONTEBL only,
+ * the other two are RK4 as in the reference). */
+int osb_profile_blasius(osb_ctx *ctx, int variant, int integrator, int nbl,
+                        double ymin, double ymax, double f2p, double beta,
+                        osb_profile **prof);
+/* Batched form: nprof independent (beta, f2p) pairs, same grid; tables land in
+ * caller (host) arrays of shape [nprof][nbl+1] each; any pointer may be NULL. */
+int osb_profile_blasius_batch(osb_ctx *ctx, int variant, int integrator, int nbl,
+                              double ymin, double ymax, int64_t nprof,
+                              const double *f2p, const double *beta, double *U,
+                              double *Uspl, double *d2U, double *d2Uspl,
+                              double *f2p_out, int32_t *npass);
+/* Upload tables computed elsewhere (e.g. by an unmodified host SOLVE_BL). */
+int osb_profile_upload(osb_ctx *ctx, int variant, int nbl, double ymin, double ymax,
+                       const double *U, const double *Uspl, const double *d2U,
+                       const double *d2Uspl, osb_profile **prof);
+/* The channel profile U = 1 - y^2 (no tables). */
+int osb_profile_channel(osb_ctx *ctx, osb_profile **prof);
+/* Copy the tables back ([nbl+1] each; any pointer may be NULL). */
+int osb_profile_get(osb_ctx *ctx, const osb_profile *prof, double *ydat, double *U,
+                    double *Uspl, double *d2U, double *d2Uspl, int32_t *npass,
+                    double *f2p_last);
+int osb_profile_nbl(const osb_profile *prof);
+int osb_profile_free(osb_ctx *ctx, osb_profile *prof);
+
+/* ---- shooting (replaces CONTE_IC shoot.f:391-392, CONTE shoot.f:26-27,
+ *      and the private CONTEs orrsom.f:165, orrspace.f:209) ----------------- */
+typedef struct {
+  int32_t flow;       /* OSB_FLOW_*                                          */
+  int32_t integrator; /* OSB_INT_*                                           */
+  int32_t nstep;      /* integration steps (CONTE's nstep)                   */
+  int32_t maxcount;   /* 0 = the flow's own limit (20; orrspace 50)          */
+  double testalpha;   /* contebl/orrsom: degrees; orrspace: cosine bound;
+                         conte: ignored (hard-wired 10 deg, shoot.f:64-65)   */
+  double ymin, ymax;  /* CONTE's to, tf                                      */
+  double errtol;      /* 0 = the flow's own (1e-14 / 1e-15 / 1e-8 / 1e-8)    */
+  double eigtol;      /* 0 = the flow's own (1e-14 / 1e-15 / 1e-12 / 1e-12)  */
+} osb_shoot_opts;
+
+/* Fill opts with what the named reference driver uses. */
+int osb_shoot_defaults(int flow, osb_shoot_opts *opts);
+
+/*
+ * Batched temporal eigenvalue solve: npts independent points, each exactly the
+ * iteration of CONTE_IC / CONTE (secant then Muller on c).
+ *   alpha  [2*npts]  complex wavenumber           (in)
+ *   Re     [npts]                                  (in)
+ *   c      [2*npts]  guess (in) -> ctemp, the last value integrated (out)
+ *   passes [npts]    integrations performed ("Eigenvalue iterations")
+ *   qend   [npts]    normalisations in the last pass
+ *   status [npts]    OSB_ST_*
+ *   resid  [2*npts]  optional: |err|, |c-cm1| at exit (shoot.f:756-758)
+ *   history[npts*hist_cap*4] optional: per pass ctemp (conte: updated c), err
+ *                    -- the rows of the reference's stdout table
+ */
+int osb_shoot_temporal(osb_ctx *ctx, const osb_shoot_opts *opts,
+                       const osb_profile *prof, int64_t npts, const double *alpha,
+                       const double *Re, double *c, int32_t *passes, int32_t *qend,
+                       int32_t *status, double *resid, double *history,
+                       int32_t hist_cap);
+int osb_shoot_temporal_dev(osb_ctx *ctx, const osb_shoot_opts *opts,
+                           const osb_profile *prof, int64_t npts,
+                           const double *d_alpha, const double *d_Re, double *d_c,
+                           int32_t *d_passes, int32_t *d_qend, int32_t *d_status,
+                           double *d_resid, double *d_history, int32_t hist_cap);
+
+/*
+ * Batched spatial continuation lines (the omega sweep of orrspace.f:186-195):
+ * nlines independent lines, each niter points; point i of a line starts from
+ * the converged alpha of point i-1 (sequential inside a line, parallel across).
+ *   Re     [nlines]
+ *   omega0 [2*nlines], domega [nlines]   omega_i = omega0 + i*domega (real part)
+ *   alpha0 [2*nlines]  guess for the first point
+ *   alpha_out [nlines*niter*2], passes/qend/status [nlines*niter]
+ */
+int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts,
+                            const osb_profile *prof, int64_t nlines, int32_t niter,
+                            const double *Re, const double *omega0,
+                            const double *domega, const double *alpha0,
+                            double *alpha_out, int32_t *passes, int32_t *qend,
+                            int32_t *status);
+
+/*
+ * Eigenfunction pass (the "second pass" shoot.f:762-810 / 338-385): for each
+ * point re-integrates at eig (the ctemp returned above), back-substitutes and
+ * returns y(i,k), i=1..4, k=0..nstep UN-normalised plus the reference's vmax
+ * (divide to obtain the fort.11-14 columns).
+ *   y    [npts*(nstep+1)*4*2], vmax [npts*2]
+ */
+int osb_eigfun(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof,
+               int64_t npts, const double *alpha, const double *Re,
+               const double *eig, const double *omega, double *y, double *vmax,
+               int32_t *qend);
+
+/* ---- measurement helpers ---------------------------------------------- */
+/* Device FP64 peak micro-benchmark: runs a dependent-chain-free DFMA kernel for
+ * ~ms_target milliseconds on the context's device; returns TFLOP/s (2 flops
+ * per DFMA).  Used as the roofline denominator of the shooting kernel. */
+int osb_measure_fp64_peak(osb_ctx *ctx, double ms_target, double *tflops,
+                          double *sm_clock_mhz_est);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSB_H */

@@ -316,9 +316,9 @@ static void osr_rhs(const osr_state *s, const zc *yo, double t, zc *yf) {
   } else if (s->flow == OSR_FLOW_ORRSOM) {
     /* orrsom.f:637-639, literally (Appendix D-14) */
     zc c = s->c;
-    yf[3] = (1.0 / (alpha * Re) * (2.0 * a2 * yo[2] - a4 * yo[0]) +
+    yf[3] = (1.0 / alpha / Re * (2.0 * a2 * yo[2] - a4 * yo[0]) +
              I1 * ((UU - c) * (yo[2] - a2 * yo[0]) - d2UU * yo[0])) *
-            (alpha * Re);
+            alpha * Re;
   } else {
     /* orrspace.f:645-647: c = omega/alpha */
     zc c = s->omega / alpha;
@@ -424,8 +424,8 @@ int osr_shoot(osr_state *s, osr_result *res, double *history, int history_cap,
     case OSR_FLOW_ORRSOM: errtol = 1.0e-8; eigtol = 1.0e-12; maxcount = 20; break;   /* orrsom.f:203-204 */
     default: errtol = 1.0e-8; eigtol = 1.0e-12; maxcount = 50; break;                /* orrspace.f:277-278 */
   }
-  if (flow == OSR_FLOW_CONTEBL || flow == OSR_FLOW_CONTE) pi = acos(-1.0);
-  else pi = 3.14159265358979323846; /* orrsom.f:194, orrspace.f:267 */
+  if (flow == OSR_FLOW_ORRSPACE) pi = 3.14159265358979323846; /* orrspace.f:267 */
+  else pi = acos(-1.0);                                        /* shoot.f:467, orrsom.f:194 */
   const double h = (tf - to) / nstep;
 
   /* trajectory storage (the reference keeps it even when eigfun is false) */
@@ -511,8 +511,8 @@ int osr_shoot(osr_state *s, osr_result *res, double *history, int history_cap,
         double x1 = cc12 / sqrt(aa * bb), x2 = cc21 / sqrt(bb * aa);
         if (x1 > 1.0) x1 = 1.0;
         if (x2 > 1.0) x2 = 1.0;
-        if (180.0 / pi * acos(x1) <= s->testalpha) norm = 1;
-        if (180.0 / pi * acos(x2) <= s->testalpha) norm = 1;
+        if (180.0 * acos(x1) / pi <= s->testalpha) norm = 1;
+        if (180.0 * acos(x2) / pi <= s->testalpha) norm = 1;
       } else { /* orrspace.f:350-358 */
         if (cc12 / sqrt(aa * bb) > s->testalpha) norm = 1;
         if (cc21 / sqrt(bb * aa) > s->testalpha) norm = 1;

@@ -1,0 +1,322 @@
+"""Host-side mirror of the reference's operator interface over libosb.so.
+
+The reference (sscollis/os-stab) is compiled Fortran: its operators are
+``SOLVE_BL`` (contebl.f:386), ``CONTE_IC`` (shoot.f:391), ``CONTE`` (shoot.f:26)
+and the private ``CONTE`` copies of orrsom.f:165 / orrspace.f:209.  The product
+boundary is the C ABI in ``include/osb.h``; the C++ twin drivers under
+``host/`` and the Fortran ``bind(C)`` module in INTEGRATION.md sit directly on
+it.  This module is a thin ctypes binding of the same ABI, used by ``tests/``
+and ``bench.py`` (which need Python for pytest / torch.distributed plumbing).
+It contains no numerics: every call goes to the CUDA library, and importing it
+on a machine where ``libosb.so`` has not been built raises immediately.
+
+Argument names follow the reference: ``nstep, testalpha, ymin(to), ymax(tf),
+alpha, Re, c`` for the shooter; ``nbl, f2p, beta`` for the profile.  As in the
+reference, ``alpha``/``Re`` passed to the shooter are in the solver's units
+(after the driver's sqrt(2) rescale, contebl.f:181-182); :func:`contebl_units`
+applies that rescale.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+LIB_PATH = _HERE / "libosb.so"
+
+FLOW_CONTEBL, FLOW_CONTE, FLOW_ORRSOM, FLOW_ORRSPACE = 0, 1, 2, 3
+INT_RK4, INT_CK45 = 0, 1
+ST_CONVERGED, ST_MAXCOUNT, ST_NONFINITE = 0, 1, 2
+E_ARG, E_CUDA, E_ALLOC, E_STATE = -1, -2, -3, -4
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class OsbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libosb error {code}: {msg}")
+        self.code = code
+
+
+class ShootOpts(C.Structure):
+    """``osb_shoot_opts`` (include/osb.h)."""
+
+    _fields_ = [
+        ("flow", C.c_int32),
+        ("integrator", C.c_int32),
+        ("nstep", C.c_int32),
+        ("maxcount", C.c_int32),
+        ("testalpha", C.c_double),
+        ("ymin", C.c_double),
+        ("ymax", C.c_double),
+        ("errtol", C.c_double),
+        ("eigtol", C.c_double),
+    ]
+
+
+def load_library(path: os.PathLike | None = None) -> C.CDLL:
+    p = Path(path) if path else LIB_PATH
+    if not p.exists():
+        raise ImportError(
+            f"{p} not found: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()' "
+            "or make -C os-stab_b200). There is no CPU fallback."
+        )
+    lib = C.CDLL(str(p))
+    vp = C.c_void_p
+    i32, i64, dbl = C.c_int32, C.c_int64, C.c_double
+    sig = {
+        "osb_version": (C.c_int, []),
+        "osb_create": (C.c_int, [C.POINTER(vp), C.c_int]),
+        "osb_create_multi": (C.c_int, [C.POINTER(vp), C.c_int, C.POINTER(C.c_int)]),
+        "osb_destroy": (C.c_int, [vp]),
+        "osb_device_count": (C.c_int, [vp]),
+        "osb_last_error": (C.c_char_p, [vp]),
+        "osb_stream": (vp, [vp]),
+        "osb_launch_count": (i64, [vp]),
+        "osb_profile_blasius": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, dbl, dbl, dbl, dbl, C.POINTER(vp)]),
+        "osb_profile_blasius_batch": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, dbl, dbl, i64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip]),
+        "osb_profile_upload": (C.c_int, [vp, C.c_int, C.c_int, dbl, dbl, _dp, _dp, _dp, _dp, C.POINTER(vp)]),
+        "osb_profile_channel": (C.c_int, [vp, C.POINTER(vp)]),
+        "osb_profile_get": (C.c_int, [vp, vp, _dp, _dp, _dp, _dp, _dp, _ip, _dp]),
+        "osb_profile_nbl": (C.c_int, [vp]),
+        "osb_profile_free": (C.c_int, [vp, vp]),
+        "osb_shoot_defaults": (C.c_int, [C.c_int, C.POINTER(ShootOpts)]),
+        "osb_shoot_temporal": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, _dp, _dp, _dp, _ip, _ip, _ip, _dp, _dp, i32]),
+        "osb_shoot_temporal_dev": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
+        "osb_shoot_spatial_lines": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, i32, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _ip]),
+        "osb_eigfun": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, _dp, _dp, _dp, _dp, _dp, _dp, _ip]),
+        "osb_measure_fp64_peak": (C.c_int, [vp, dbl, _dp, _dp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+EXPORTED_SYMBOLS = (
+    "osb_version osb_create osb_create_multi osb_destroy osb_device_count osb_last_error osb_stream "
+    "osb_launch_count osb_profile_blasius osb_profile_blasius_batch osb_profile_upload "
+    "osb_profile_channel osb_profile_get osb_profile_nbl osb_profile_free osb_shoot_defaults "
+    "osb_shoot_temporal osb_shoot_temporal_dev osb_shoot_spatial_lines osb_eigfun osb_measure_fp64_peak"
+).split()
+
+
+def contebl_units(alpha, Re):
+    """The driver-side rescale of contebl.f:181-182 / orrsom.f:129-130."""
+    s2 = math.sqrt(2.0)
+    return np.asarray(alpha) * s2, np.asarray(Re) * s2
+
+
+def shoot_defaults(flow: int, lib: C.CDLL | None = None) -> ShootOpts:
+    lib = lib or load_library()
+    o = ShootOpts()
+    rc = lib.osb_shoot_defaults(flow, C.byref(o))
+    if rc:
+        raise OsbError(rc, "osb_shoot_defaults")
+    return o
+
+
+def _f64(a, n=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} doubles, got {a.size}")
+    return a
+
+
+def _cplx_pairs(a, n):
+    """complex or (n,2) float array -> contiguous float64 view of 2n doubles."""
+    a = np.asarray(a)
+    if np.iscomplexobj(a):
+        a = np.ascontiguousarray(a, dtype=np.complex128).view(np.float64)
+    return _f64(a.reshape(-1), 2 * n)
+
+
+class Profile:
+    """Device-resident mean profile (the reference's COMMON tables U, Uspl, d2U, d2Uspl)."""
+
+    def __init__(self, engine, handle):
+        self.engine = engine
+        self.handle = handle
+
+    @property
+    def nbl(self):
+        return self.engine.lib.osb_profile_nbl(self.handle)
+
+    def tables(self):
+        n = self.nbl + 1
+        out = {k: np.zeros(n) for k in ("ydat", "U", "Uspl", "d2U", "d2Uspl")}
+        npass = C.c_int32()
+        f2p = C.c_double()
+        self.engine._check(
+            self.engine.lib.osb_profile_get(
+                self.engine.ctx, self.handle, *[out[k].ctypes.data_as(_dp) for k in ("ydat", "U", "Uspl", "d2U", "d2Uspl")],
+                C.byref(npass), C.byref(f2p)))
+        out["npass"] = npass.value
+        out["f2p"] = f2p.value
+        return out
+
+    def free(self):
+        if self.handle:
+            self.engine.lib.osb_profile_free(self.engine.ctx, self.handle)
+            self.handle = None
+
+
+class Engine:
+    """One ``osb_ctx``: a CUDA device (or several) plus its stream(s)."""
+
+    def __init__(self, device: int | None = 0, devices=None, lib: C.CDLL | None = None):
+        self.lib = lib or load_library()
+        self.ctx = C.c_void_p()
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            rc = self.lib.osb_create_multi(C.byref(self.ctx), len(devices), arr)
+        else:
+            rc = self.lib.osb_create(C.byref(self.ctx), int(device))
+        if rc:
+            raise OsbError(rc, "osb_create failed (no usable CUDA device? there is no CPU fallback)")
+
+    def _check(self, rc):
+        if rc:
+            raise OsbError(rc, self.lib.osb_last_error(self.ctx).decode())
+
+    def close(self):
+        if self.ctx:
+            self.lib.osb_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.osb_launch_count(self.ctx))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.osb_stream(self.ctx) or 0)
+
+    # ---- SOLVE_BL -----------------------------------------------------
+    def solve_bl(self, variant=FLOW_CONTEBL, integrator=INT_CK45, nbl=1000, ymin=0.0, ymax=17.0, f2p=0.5, beta=0.0) -> Profile:
+        h = C.c_void_p()
+        self._check(self.lib.osb_profile_blasius(self.ctx, variant, integrator, nbl, ymin, ymax, f2p, beta, C.byref(h)))
+        return Profile(self, h)
+
+    def solve_bl_batch(self, f2p, beta, variant=FLOW_CONTEBL, integrator=INT_CK45, nbl=1000, ymin=0.0, ymax=17.0):
+        f2p = _f64(f2p)
+        beta = _f64(beta, f2p.size)
+        n = f2p.size
+        out = {k: np.zeros((n, nbl + 1)) for k in ("U", "Uspl", "d2U", "d2Uspl")}
+        f2o = np.zeros(n)
+        npass = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.osb_profile_blasius_batch(
+            self.ctx, variant, integrator, nbl, ymin, ymax, n, f2p.ctypes.data_as(_dp), beta.ctypes.data_as(_dp),
+            *[out[k].ctypes.data_as(_dp) for k in ("U", "Uspl", "d2U", "d2Uspl")], f2o.ctypes.data_as(_dp), npass.ctypes.data_as(_ip)))
+        out["f2p"] = f2o
+        out["npass"] = npass
+        return out
+
+    def upload_profile(self, variant, nbl, ymin, ymax, U, Uspl, d2U=None, d2Uspl=None) -> Profile:
+        h = C.c_void_p()
+        U = _f64(U, nbl + 1)
+        Uspl = _f64(Uspl, nbl + 1)
+        d2U = _f64(d2U, nbl + 1) if d2U is not None else None
+        d2Uspl = _f64(d2Uspl, nbl + 1) if d2Uspl is not None else None
+        self._check(self.lib.osb_profile_upload(
+            self.ctx, variant, nbl, ymin, ymax, U.ctypes.data_as(_dp), Uspl.ctypes.data_as(_dp),
+            d2U.ctypes.data_as(_dp) if d2U is not None else None,
+            d2Uspl.ctypes.data_as(_dp) if d2Uspl is not None else None, C.byref(h)))
+        return Profile(self, h)
+
+    def channel_profile(self) -> Profile:
+        h = C.c_void_p()
+        self._check(self.lib.osb_profile_channel(self.ctx, C.byref(h)))
+        return Profile(self, h)
+
+    # ---- CONTE / CONTE_IC ---------------------------------------------
+    def shoot_temporal(self, opts: ShootOpts, prof: Profile, alpha, Re, c, want_resid=False, hist_cap=0):
+        """Batched CONTE_IC/CONTE.  alpha, c: complex arrays [npts]; Re: [npts].
+        Returns dict(c, passes, qend, status[, resid, history])."""
+        Re = _f64(Re)
+        n = Re.size
+        al = _cplx_pairs(alpha, n)
+        cc = _cplx_pairs(c, n).copy()
+        passes = np.zeros(n, dtype=np.int32)
+        qend = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        resid = np.zeros(2 * n) if want_resid else None
+        hist = np.zeros(n * hist_cap * 4) if hist_cap else None
+        self._check(self.lib.osb_shoot_temporal(
+            self.ctx, C.byref(opts), prof.handle, n, al.ctypes.data_as(_dp), Re.ctypes.data_as(_dp),
+            cc.ctypes.data_as(_dp), passes.ctypes.data_as(_ip), qend.ctypes.data_as(_ip), status.ctypes.data_as(_ip),
+            resid.ctypes.data_as(_dp) if want_resid else None, hist.ctypes.data_as(_dp) if hist_cap else None, hist_cap))
+        out = dict(c=cc.view(np.complex128), passes=passes, qend=qend, status=status)
+        if want_resid:
+            out["resid"] = resid.reshape(n, 2)
+        if hist_cap:
+            out["history"] = hist.reshape(n, hist_cap, 4)
+        return out
+
+    def shoot_temporal_dev(self, opts: ShootOpts, prof: Profile, npts, d_alpha, d_Re, d_c, d_passes, d_qend, d_status,
+                           d_resid=0, d_history=0, hist_cap=0):
+        """Device-pointer form (ints are raw device addresses, e.g. torch ``data_ptr()``).
+        Asynchronous on ``self.stream``."""
+        self._check(self.lib.osb_shoot_temporal_dev(
+            self.ctx, C.byref(opts), prof.handle, int(npts), d_alpha, d_Re, d_c, d_passes, d_qend, d_status,
+            d_resid or None, d_history or None, hist_cap))
+
+    def shoot_spatial_lines(self, opts: ShootOpts, prof: Profile, Re, omega0, domega, alpha0, niter):
+        Re = _f64(Re)
+        n = Re.size
+        om = _cplx_pairs(omega0, n)
+        dom = _f64(domega, n)
+        a0 = _cplx_pairs(alpha0, n)
+        out = np.zeros(n * niter * 2)
+        passes = np.zeros(n * niter, dtype=np.int32)
+        qend = np.zeros(n * niter, dtype=np.int32)
+        status = np.zeros(n * niter, dtype=np.int32)
+        self._check(self.lib.osb_shoot_spatial_lines(
+            self.ctx, C.byref(opts), prof.handle, n, niter, Re.ctypes.data_as(_dp), om.ctypes.data_as(_dp),
+            dom.ctypes.data_as(_dp), a0.ctypes.data_as(_dp), out.ctypes.data_as(_dp), passes.ctypes.data_as(_ip),
+            qend.ctypes.data_as(_ip), status.ctypes.data_as(_ip)))
+        return dict(alpha=out.view(np.complex128).reshape(n, niter), passes=passes.reshape(n, niter),
+                    qend=qend.reshape(n, niter), status=status.reshape(n, niter))
+
+    def eigfun(self, opts: ShootOpts, prof: Profile, Re, eig, alpha=None, omega=None):
+        Re = _f64(Re)
+        n = Re.size
+        ev = _cplx_pairs(eig, n)
+        al = _cplx_pairs(alpha, n) if alpha is not None else None
+        om = _cplx_pairs(omega, n) if omega is not None else None
+        y = np.zeros(n * (opts.nstep + 1) * 8)
+        vmax = np.zeros(2 * n)
+        qend = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.osb_eigfun(
+            self.ctx, C.byref(opts), prof.handle, n, al.ctypes.data_as(_dp) if al is not None else None,
+            Re.ctypes.data_as(_dp), ev.ctypes.data_as(_dp), om.ctypes.data_as(_dp) if om is not None else None,
+            y.ctypes.data_as(_dp), vmax.ctypes.data_as(_dp), qend.ctypes.data_as(_ip)))
+        return dict(y=y.view(np.complex128).reshape(n, opts.nstep + 1, 4), vmax=vmax.view(np.complex128), qend=qend)
+
+    def measure_fp64_peak(self, ms_target=200.0):
+        tf = C.c_double()
+        mhz = C.c_double()
+        self._check(self.lib.osb_measure_fp64_peak(self.ctx, ms_target, C.byref(tf), C.byref(mhz)))
+        return tf.value, mhz.value
+
+
+# ---- sharding of a sweep over ranks: host logic, no numerics ----
+def shard_bounds(npts: int, world: int, rank: int, tile: int = 4096):
+    """Cyclic-by-tile partition of the flattened point index: tile t goes to rank
+    t % world.  Returns the index array owned by ``rank`` (sorted)."""
+    ntile = (npts + tile - 1) // tile
+    mine = np.arange(rank, ntile, world, dtype=np.int64)
+    idx = (mine[:, None] * tile + np.arange(tile, dtype=np.int64)[None, :]).reshape(-1)
+    return idx[idx < npts]

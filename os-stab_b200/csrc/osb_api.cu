@@ -1,0 +1,666 @@
+// osb_api.cu -- the C ABI of libosb.so (declared in include/osb.h).
+//
+// Host-side glue only: argument checking, device buffers, stream-ordered copies
+// and kernel launches.  There is deliberately no CPU implementation of any
+// solver here: with no CUDA device every entry point fails with OSB_E_CUDA.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+
+#include "osb_internal.h"
+
+using namespace osb;
+
+struct osb_ctx {
+  std::vector<int> devices;
+  std::vector<cudaStream_t> streams;
+  std::string err;
+  int64_t launches = 0;
+};
+
+struct osb_profile {
+  std::vector<ProfileDev> dev;  // one per context device
+};
+
+namespace {
+
+int fail(osb_ctx *ctx, int code, const std::string &msg) {
+  if (ctx) ctx->err = msg;
+  return code;
+}
+
+#define OSB_CUDA(ctx, call)                                                              \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return fail((ctx), OSB_E_CUDA,                                                     \
+                  std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
+                      std::to_string(__LINE__) + ")");                                   \
+  } while (0)
+
+// Cash-Karp tableau as typed in the reference (shoot.f:1381-1391)
+const double kCKb[15] = {0.2,
+                         0.075, 0.225,
+                         0.3, -0.9, 1.2,
+                         -0.2037037037037037, 2.5, -2.5925925925925926, 1.2962962962962963,
+                         0.029495804398148147, 0.341796875, 0.041594328703703706,
+                         0.40034541377314814, 0.061767578125};
+const double kCKc[6] = {0.09788359788359788, 0.0, 0.4025764895330113,
+                        0.21043771043771045, 0.0, 0.2891022021456804};
+
+struct FlowRules {
+  int maxcount;
+  double errtol, eigtol;
+  int loop_rule, cm1_defined, strict, first_perturb, show_updated, bl_ic, spatial, analytic;
+};
+
+bool flow_rules(int flow, FlowRules *r) {
+  switch (flow) {
+    case OSB_FLOW_CONTEBL:  // shoot.f:461-463,478-479,602,718
+      *r = FlowRules{20, 1.0e-14, 1.0e-14, 0, 1, 1, 0, 0, 1, 0, 0};
+      return true;
+    case OSB_FLOW_CONTE:  // shoot.f:53-55,76-77,144,294,322
+      *r = FlowRules{20, 1.0e-15, 1.0e-15, 1, 1, 0, 0, 1, 0, 0, 0};
+      return true;
+    case OSB_FLOW_ORRSOM:  // orrsom.f:203-204,302,422
+      *r = FlowRules{20, 1.0e-8, 1.0e-12, 1, 0, 0, 0, 0, 1, 0, 0};
+      return true;
+    case OSB_FLOW_ORRSPACE:  // orrspace.f:277-278,357-358,459
+      *r = FlowRules{50, 1.0e-8, 1.0e-12, 1, 0, 1, 1, 0, 1, 1, 1};
+      return true;
+  }
+  return false;
+}
+
+// threshold of the orthonormality test in the form the kernel evaluates it
+double norm_threshold(int flow, double testalpha) {
+  const double pi = acos(-1.0);
+  switch (flow) {
+    case OSB_FLOW_CONTEBL: { double c = cos(pi * testalpha / 180.0); return c * c; }  // shoot.f:594
+    case OSB_FLOW_CONTE: { double c = cos(10.0 * pi / 180.0); return c * c; }          // shoot.f:64-65
+    case OSB_FLOW_ORRSOM: { double c = cos(testalpha * pi / 180.0); return c * c; }    // orrsom.f:292
+    default: return testalpha * testalpha;                                             // orrspace.f:357
+  }
+}
+
+int fill_args(osb_ctx *ctx, const osb_shoot_opts *o, ShootArgs *a, int *analytic) {
+  FlowRules r;
+  if (!o || !flow_rules(o->flow, &r)) return fail(ctx, OSB_E_ARG, "unknown flow");
+  if (o->integrator != OSB_INT_RK4 && o->integrator != OSB_INT_CK45)
+    return fail(ctx, OSB_E_ARG, "unknown integrator");
+  if (o->nstep < 1) return fail(ctx, OSB_E_ARG, "nstep < 1");
+  if (!(o->ymax > o->ymin)) return fail(ctx, OSB_E_ARG, "ymax <= ymin");
+  memset(a, 0, sizeof(*a));
+  a->nstep = o->nstep;
+  a->maxcount = o->maxcount > 0 ? o->maxcount : r.maxcount;
+  a->errtol = o->errtol > 0 ? o->errtol : r.errtol;
+  a->eigtol = o->eigtol > 0 ? o->eigtol : r.eigtol;
+  a->niter = 1;
+  a->spatial = r.spatial;
+  a->bl_ic = r.bl_ic;
+  a->loop_rule = r.loop_rule;
+  a->cm1_defined = r.cm1_defined;
+  a->strict = r.strict;
+  a->first_perturb = r.first_perturb;
+  a->show_updated = r.show_updated;
+  a->thr = norm_threshold(o->flow, o->testalpha);
+  const double h = (o->ymax - o->ymin) / (double)o->nstep;  // shoot.f:471
+  a->hs = (o->flow == OSB_FLOW_CONTE) ? h : -h;
+  a->tf = o->ymax;
+  for (int i = 0; i < 15; ++i) a->bh[i] = kCKb[i] * a->hs;
+  for (int i = 0; i < 6; ++i) a->ch[i] = kCKc[i] * a->hs;
+  *analytic = r.analytic;
+  return OSB_OK;
+}
+
+int check_profile(osb_ctx *ctx, const osb_shoot_opts *o, const osb_profile *prof) {
+  if (!prof || prof->dev.size() != ctx->devices.size())
+    return fail(ctx, OSB_E_ARG, "profile does not belong to this context");
+  const ProfileDev &p = prof->dev[0];
+  if (o->flow == OSB_FLOW_CONTE) {
+    if (p.variant != OSB_FLOW_CONTE) return fail(ctx, OSB_E_ARG, "conte flow needs the channel profile");
+  } else {
+    if (p.variant == OSB_FLOW_CONTE || !p.tables) return fail(ctx, OSB_E_ARG, "BL flow needs Blasius tables");
+  }
+  return OSB_OK;
+}
+
+// split [0,n) into ndev contiguous chunks
+void chunk(int64_t n, int ndev, int d, int64_t *lo, int64_t *hi) {
+  int64_t per = (n + ndev - 1) / ndev;
+  *lo = std::min<int64_t>(n, per * d);
+  *hi = std::min<int64_t>(n, per * (d + 1));
+}
+
+}  // namespace
+
+extern "C" {
+
+int osb_version(void) { return OSB_VERSION; }
+
+int osb_create_multi(osb_ctx **out, int ndev, const int *devices) {
+  if (!out) return OSB_E_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return OSB_E_CUDA;
+  std::unique_ptr<osb_ctx> c(new osb_ctx);
+  if (ndev <= 0) {
+    for (int d = 0; d < count; ++d) c->devices.push_back(d);
+  } else {
+    for (int i = 0; i < ndev; ++i) {
+      int d = devices ? devices[i] : i;
+      if (d < 0 || d >= count) return OSB_E_ARG;
+      c->devices.push_back(d);
+    }
+  }
+  for (int d : c->devices) {
+    if (cudaSetDevice(d) != cudaSuccess) return OSB_E_CUDA;
+    cudaStream_t s;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return OSB_E_CUDA;
+    c->streams.push_back(s);
+  }
+  *out = c.release();
+  return OSB_OK;
+}
+
+int osb_create(osb_ctx **out, int device) { return osb_create_multi(out, 1, &device); }
+
+int osb_destroy(osb_ctx *ctx) {
+  if (!ctx) return OSB_E_ARG;
+  for (size_t i = 0; i < ctx->devices.size(); ++i) {
+    cudaSetDevice(ctx->devices[i]);
+    cudaStreamSynchronize(ctx->streams[i]);
+    cudaStreamDestroy(ctx->streams[i]);
+  }
+  delete ctx;
+  return OSB_OK;
+}
+
+int osb_device_count(const osb_ctx *ctx) { return ctx ? (int)ctx->devices.size() : 0; }
+const char *osb_last_error(const osb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void *osb_stream(osb_ctx *ctx) { return ctx && !ctx->streams.empty() ? (void *)ctx->streams[0] : nullptr; }
+int64_t osb_launch_count(const osb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int osb_shoot_defaults(int flow, osb_shoot_opts *o) {
+  FlowRules r;
+  if (!o || !flow_rules(flow, &r)) return OSB_E_ARG;
+  memset(o, 0, sizeof(*o));
+  o->flow = flow;
+  o->maxcount = r.maxcount;
+  o->errtol = r.errtol;
+  o->eigtol = r.eigtol;
+  switch (flow) {
+    case OSB_FLOW_CONTEBL:  // contebl.f:64-83, built with USE_RKCK45 (README.md:60-62)
+      o->integrator = OSB_INT_CK45; o->nstep = 1000; o->testalpha = 10.0; o->ymin = 0.0; o->ymax = 17.0;
+      break;
+    case OSB_FLOW_CONTE:  // conte.f:61-68
+      o->integrator = OSB_INT_CK45; o->nstep = 2000; o->testalpha = 10.0; o->ymin = -1.0; o->ymax = 1.0;
+      break;
+    case OSB_FLOW_ORRSOM:  // test.inp
+      o->integrator = OSB_INT_RK4; o->nstep = 2000; o->testalpha = 10.0; o->ymin = 0.0; o->ymax = 17.0;
+      break;
+    default:  // sweep.inp (ymax is rescaled by the driver, orrspace.f:160-167)
+      o->integrator = OSB_INT_RK4; o->nstep = 1000; o->testalpha = 0.9; o->ymin = 0.0; o->ymax = 17.0;
+      break;
+  }
+  return OSB_OK;
+}
+
+// ---------------------------------------------------------------- profiles
+static int profile_alloc(osb_ctx *ctx, int variant, int nbl, double ymin, double ymax,
+                         osb_profile **out) {
+  std::unique_ptr<osb_profile> p(new osb_profile);
+  p->dev.resize(ctx->devices.size());
+  for (size_t i = 0; i < ctx->devices.size(); ++i) {
+    ProfileDev &d = p->dev[i];
+    d.variant = variant; d.nbl = nbl; d.ymin = ymin; d.ymax = ymax; d.device = ctx->devices[i];
+    if (variant != OSB_FLOW_CONTE) {
+      OSB_CUDA(ctx, cudaSetDevice(d.device));
+      OSB_CUDA(ctx, cudaMalloc(&d.tables, 5 * ((size_t)nbl + 2) * sizeof(double)));
+    }
+  }
+  *out = p.release();
+  return OSB_OK;
+}
+
+int osb_profile_blasius(osb_ctx *ctx, int variant, int integrator, int nbl, double ymin,
+                        double ymax, double f2p, double beta, osb_profile **out) {
+  if (!ctx || !out) return OSB_E_ARG;
+  if (variant != OSB_FLOW_CONTEBL && variant != OSB_FLOW_ORRSOM && variant != OSB_FLOW_ORRSPACE)
+    return fail(ctx, OSB_E_ARG, "variant must be CONTEBL, ORRSOM or ORRSPACE");
+  if (nbl < 8) return fail(ctx, OSB_E_ARG, "nbl < 8");
+  osb_profile *p = nullptr;
+  int rc = profile_alloc(ctx, variant, nbl, ymin, ymax, &p);
+  if (rc) return rc;
+  for (size_t i = 0; i < ctx->devices.size(); ++i) {
+    ProfileDev &d = p->dev[i];
+    cudaStream_t st = ctx->streams[i];
+    OSB_CUDA(ctx, cudaSetDevice(d.device));
+    double *scr = nullptr, *par = nullptr;
+    int32_t *np = nullptr;
+    OSB_CUDA(ctx, cudaMallocAsync(&scr, blasius_scratch_doubles(nbl, 1) * sizeof(double), st));
+    OSB_CUDA(ctx, cudaMallocAsync(&par, 3 * sizeof(double), st));
+    OSB_CUDA(ctx, cudaMallocAsync(&np, sizeof(int32_t), st));
+    double hp[2] = {f2p, beta};
+    OSB_CUDA(ctx, cudaMemcpyAsync(par, hp, sizeof(hp), cudaMemcpyHostToDevice, st));
+    OSB_CUDA(ctx, launch_blasius(variant, integrator, nbl, ymin, ymax, 1, par, par + 1, d.tables, scr,
+                                 par + 2, np, st));
+    ctx->launches++;
+    int32_t hnp = 0;
+    double hf2 = 0;
+    OSB_CUDA(ctx, cudaMemcpyAsync(&hnp, np, sizeof(hnp), cudaMemcpyDeviceToHost, st));
+    OSB_CUDA(ctx, cudaMemcpyAsync(&hf2, par + 2, sizeof(hf2), cudaMemcpyDeviceToHost, st));
+    OSB_CUDA(ctx, cudaFreeAsync(scr, st));
+    OSB_CUDA(ctx, cudaFreeAsync(par, st));
+    OSB_CUDA(ctx, cudaFreeAsync(np, st));
+    OSB_CUDA(ctx, cudaStreamSynchronize(st));
+    d.npass = hnp; d.f2p_last = hf2;
+  }
+  *out = p;
+  return OSB_OK;
+}
+
+int osb_profile_blasius_batch(osb_ctx *ctx, int variant, int integrator, int nbl, double ymin,
+                              double ymax, int64_t nprof, const double *f2p, const double *beta,
+                              double *U, double *Uspl, double *d2U, double *d2Uspl,
+                              double *f2p_out, int32_t *npass) {
+  if (!ctx || nprof < 1 || !f2p || !beta) return OSB_E_ARG;
+  if (variant != OSB_FLOW_CONTEBL && variant != OSB_FLOW_ORRSOM && variant != OSB_FLOW_ORRSPACE)
+    return fail(ctx, OSB_E_ARG, "variant must be CONTEBL, ORRSOM or ORRSPACE");
+  if (nbl < 8) return fail(ctx, OSB_E_ARG, "nbl < 8");
+  cudaStream_t st = ctx->streams[0];
+  OSB_CUDA(ctx, cudaSetDevice(ctx->devices[0]));
+  const size_t n2 = (size_t)nbl + 2;
+  double *tab = nullptr, *scr = nullptr, *par = nullptr;
+  int32_t *np = nullptr;
+  OSB_CUDA(ctx, cudaMallocAsync(&tab, 5 * n2 * nprof * sizeof(double), st));
+  OSB_CUDA(ctx, cudaMallocAsync(&scr, blasius_scratch_doubles(nbl, nprof) * sizeof(double), st));
+  OSB_CUDA(ctx, cudaMallocAsync(&par, 3 * nprof * sizeof(double), st));
+  OSB_CUDA(ctx, cudaMallocAsync(&np, nprof * sizeof(int32_t), st));
+  OSB_CUDA(ctx, cudaMemcpyAsync(par, f2p, nprof * sizeof(double), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(ctx, cudaMemcpyAsync(par + nprof, beta, nprof * sizeof(double), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(ctx, launch_blasius(variant, integrator, nbl, ymin, ymax, nprof, par, par + nprof, tab, scr,
+                               par + 2 * nprof, np, st));
+  ctx->launches++;
+  // device layout is [array][i][p]; the caller wants [p][i]: strided 2-D copies
+  double *outs[4] = {U, Uspl, d2U, d2Uspl};
+  for (int a = 0; a < 4; ++a) {
+    if (!outs[a]) continue;
+    // source: rows i (pitch nprof doubles), columns p -> transpose on the host side
+    std::vector<double> tmp((size_t)(nbl + 1) * nprof);
+    OSB_CUDA(ctx, cudaMemcpyAsync(tmp.data(), tab + (size_t)(a + 1) * n2 * nprof,
+                                  tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OSB_CUDA(ctx, cudaStreamSynchronize(st));
+    for (int64_t p = 0; p < nprof; ++p)
+      for (int i = 0; i <= nbl; ++i) outs[a][p * (nbl + 1) + i] = tmp[(size_t)i * nprof + p];
+  }
+  if (f2p_out) OSB_CUDA(ctx, cudaMemcpyAsync(f2p_out, par + 2 * nprof, nprof * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (npass) OSB_CUDA(ctx, cudaMemcpyAsync(npass, np, nprof * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(ctx, cudaFreeAsync(tab, st));
+  OSB_CUDA(ctx, cudaFreeAsync(scr, st));
+  OSB_CUDA(ctx, cudaFreeAsync(par, st));
+  OSB_CUDA(ctx, cudaFreeAsync(np, st));
+  OSB_CUDA(ctx, cudaStreamSynchronize(st));
+  return OSB_OK;
+}
+
+int osb_profile_upload(osb_ctx *ctx, int variant, int nbl, double ymin, double ymax,
+                       const double *U, const double *Uspl, const double *d2U,
+                       const double *d2Uspl, osb_profile **out) {
+  if (!ctx || !out || !U || !Uspl) return OSB_E_ARG;
+  if (variant != OSB_FLOW_CONTEBL && variant != OSB_FLOW_ORRSOM && variant != OSB_FLOW_ORRSPACE)
+    return fail(ctx, OSB_E_ARG, "variant must be CONTEBL, ORRSOM or ORRSPACE");
+  if (variant != OSB_FLOW_CONTEBL && (!d2U || !d2Uspl))
+    return fail(ctx, OSB_E_ARG, "orrsom/orrspace need d2U and d2Uspl");
+  const size_t n2 = (size_t)nbl + 2;
+  std::vector<double> h(5 * n2, 0.0);
+  const double hh = (ymax - ymin) / (double)nbl;
+  for (int i = 0; i <= nbl; ++i) {
+    h[i] = ymin + i * hh;  // ydat(i) = ymin + i*h  contebl.f:499
+    h[n2 + i] = U[i];
+    h[2 * n2 + i] = Uspl[i];
+    h[3 * n2 + i] = d2U ? d2U[i] : Uspl[i];
+    h[4 * n2 + i] = d2Uspl ? d2Uspl[i] : 0.0;
+  }
+  osb_profile *p = nullptr;
+  int rc = profile_alloc(ctx, variant, nbl, ymin, ymax, &p);
+  if (rc) return rc;
+  for (size_t i = 0; i < ctx->devices.size(); ++i) {
+    OSB_CUDA(ctx, cudaSetDevice(p->dev[i].device));
+    OSB_CUDA(ctx, cudaMemcpy(p->dev[i].tables, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  *out = p;
+  return OSB_OK;
+}
+
+int osb_profile_channel(osb_ctx *ctx, osb_profile **out) {
+  if (!ctx || !out) return OSB_E_ARG;
+  return profile_alloc(ctx, OSB_FLOW_CONTE, 0, -1.0, 1.0, out);
+}
+
+int osb_profile_get(osb_ctx *ctx, const osb_profile *prof, double *ydat, double *U, double *Uspl,
+                    double *d2U, double *d2Uspl, int32_t *npass, double *f2p_last) {
+  if (!ctx || !prof || prof->dev.empty()) return OSB_E_ARG;
+  const ProfileDev &d = prof->dev[0];
+  if (!d.tables) return fail(ctx, OSB_E_STATE, "profile has no tables");
+  const size_t n2 = (size_t)d.nbl + 2;
+  double *outs[5] = {ydat, U, Uspl, d2U, d2Uspl};
+  OSB_CUDA(ctx, cudaSetDevice(d.device));
+  for (int a = 0; a < 5; ++a)
+    if (outs[a])
+      OSB_CUDA(ctx, cudaMemcpy(outs[a], d.tables + a * n2, ((size_t)d.nbl + 1) * sizeof(double), cudaMemcpyDeviceToHost));
+  if (npass) *npass = d.npass;
+  if (f2p_last) *f2p_last = d.f2p_last;
+  return OSB_OK;
+}
+
+int osb_profile_nbl(const osb_profile *prof) { return prof && !prof->dev.empty() ? prof->dev[0].nbl : -1; }
+
+int osb_profile_free(osb_ctx *ctx, osb_profile *prof) {
+  if (!prof) return OSB_E_ARG;
+  for (auto &d : prof->dev)
+    if (d.tables) {
+      cudaSetDevice(d.device);
+      cudaFree(d.tables);
+    }
+  delete prof;
+  (void)ctx;
+  return OSB_OK;
+}
+
+// ---------------------------------------------------------------- shooting
+// build the stage table for device slot i; returns a stream-ordered allocation
+static int make_stage_table(osb_ctx *ctx, size_t i, const osb_shoot_opts *o, const osb_profile *prof,
+                            double2 **tab) {
+  cudaStream_t st = ctx->streams[i];
+  size_t n = (size_t)o->nstep * stages_per_step(o->integrator);
+  OSB_CUDA(ctx, cudaMallocAsync(tab, n * sizeof(double2), st));
+  OSB_CUDA(ctx, launch_stage_table(prof->dev[i], o->flow, o->integrator, o->nstep, o->ymin, o->ymax, *tab, st));
+  ctx->launches++;
+  return OSB_OK;
+}
+
+int osb_shoot_temporal_dev(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof,
+                           int64_t npts, const double *d_alpha, const double *d_Re, double *d_c,
+                           int32_t *d_passes, int32_t *d_qend, int32_t *d_status, double *d_resid,
+                           double *d_history, int32_t hist_cap) {
+  if (!ctx || npts < 0 || !d_alpha || !d_Re || !d_c || !d_passes || !d_qend || !d_status)
+    return fail(ctx, OSB_E_ARG, "null argument");
+  if (opts && opts->flow == OSB_FLOW_ORRSPACE) return fail(ctx, OSB_E_ARG, "orrspace is spatial: use osb_shoot_spatial_lines");
+  ShootArgs a;
+  int analytic = 0;
+  int rc = fill_args(ctx, opts, &a, &analytic);
+  if (rc) return rc;
+  rc = check_profile(ctx, opts, prof);
+  if (rc) return rc;
+  if (npts == 0) return OSB_OK;
+  OSB_CUDA(ctx, cudaSetDevice(ctx->devices[0]));
+  cudaStream_t st = ctx->streams[0];
+  double2 *tab = nullptr;
+  rc = make_stage_table(ctx, 0, opts, prof, &tab);
+  if (rc) return rc;
+  a.tab = tab;
+  a.nlines = npts;
+  a.alpha = (const double2 *)d_alpha;
+  a.Re = d_Re;
+  a.ev = (double2 *)d_c;
+  a.passes = d_passes; a.qend = d_qend; a.status = d_status;
+  a.resid = (double2 *)d_resid;
+  a.history = (double4 *)d_history;
+  a.hist_cap = d_history ? hist_cap : 0;
+  int nl = 0;
+  OSB_CUDA(ctx, launch_shoot(a, opts->integrator, analytic, st, &nl));
+  ctx->launches += nl;
+  OSB_CUDA(ctx, cudaFreeAsync(tab, st));
+  return OSB_OK;
+}
+
+int osb_shoot_temporal(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof,
+                       int64_t npts, const double *alpha, const double *Re, double *c,
+                       int32_t *passes, int32_t *qend, int32_t *status, double *resid,
+                       double *history, int32_t hist_cap) {
+  if (!ctx || npts < 0 || !alpha || !Re || !c || !passes || !qend || !status)
+    return fail(ctx, OSB_E_ARG, "null argument");
+  if (opts && opts->flow == OSB_FLOW_ORRSPACE) return fail(ctx, OSB_E_ARG, "orrspace is spatial: use osb_shoot_spatial_lines");
+  ShootArgs base;
+  int analytic = 0;
+  int rc = fill_args(ctx, opts, &base, &analytic);
+  if (rc) return rc;
+  rc = check_profile(ctx, opts, prof);
+  if (rc) return rc;
+  if (npts == 0) return OSB_OK;
+  if (history && hist_cap < 1) return fail(ctx, OSB_E_ARG, "hist_cap < 1");
+  const int ndev = (int)ctx->devices.size();
+  struct Buf { double *alpha = 0, *Re = 0, *c = 0, *resid = 0, *hist = 0; int32_t *ip = 0; double2 *tab = 0; int64_t lo = 0, hi = 0; };
+  std::vector<Buf> bufs(ndev);
+  // phase 1: per device H2D + launch (kernels of different devices overlap)
+  for (int d = 0; d < ndev; ++d) {
+    Buf &b = bufs[d];
+    chunk(npts, ndev, d, &b.lo, &b.hi);
+    const int64_t n = b.hi - b.lo;
+    if (n <= 0) continue;
+    cudaStream_t st = ctx->streams[d];
+    OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
+    OSB_CUDA(ctx, cudaMallocAsync(&b.alpha, n * 2 * sizeof(double), st));
+    OSB_CUDA(ctx, cudaMallocAsync(&b.Re, n * sizeof(double), st));
+    OSB_CUDA(ctx, cudaMallocAsync(&b.c, n * 2 * sizeof(double), st));
+    OSB_CUDA(ctx, cudaMallocAsync(&b.ip, n * 3 * sizeof(int32_t), st));
+    if (resid) OSB_CUDA(ctx, cudaMallocAsync(&b.resid, n * 2 * sizeof(double), st));
+    if (history) OSB_CUDA(ctx, cudaMallocAsync(&b.hist, n * hist_cap * 4 * sizeof(double), st));
+    OSB_CUDA(ctx, cudaMemcpyAsync(b.alpha, alpha + 2 * b.lo, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    OSB_CUDA(ctx, cudaMemcpyAsync(b.Re, Re + b.lo, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    OSB_CUDA(ctx, cudaMemcpyAsync(b.c, c + 2 * b.lo, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (history) OSB_CUDA(ctx, cudaMemsetAsync(b.hist, 0, n * hist_cap * 4 * sizeof(double), st));
+    rc = make_stage_table(ctx, d, opts, prof, &b.tab);
+    if (rc) return rc;
+    ShootArgs a = base;
+    a.tab = b.tab;
+    a.nlines = n;
+    a.alpha = (const double2 *)b.alpha; a.Re = b.Re; a.ev = (double2 *)b.c;
+    a.passes = b.ip; a.qend = b.ip + n; a.status = b.ip + 2 * n;
+    a.resid = (double2 *)b.resid;
+    a.history = (double4 *)b.hist;
+    a.hist_cap = history ? hist_cap : 0;
+    int nl = 0;
+    OSB_CUDA(ctx, launch_shoot(a, opts->integrator, analytic, st, &nl));
+    ctx->launches += nl;
+  }
+  // phase 2: D2H + free
+  for (int d = 0; d < ndev; ++d) {
+    Buf &b = bufs[d];
+    const int64_t n = b.hi - b.lo;
+    if (n <= 0) continue;
+    cudaStream_t st = ctx->streams[d];
+    OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
+    OSB_CUDA(ctx, cudaMemcpyAsync(c + 2 * b.lo, b.c, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OSB_CUDA(ctx, cudaMemcpyAsync(passes + b.lo, b.ip, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    OSB_CUDA(ctx, cudaMemcpyAsync(qend + b.lo, b.ip + n, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    OSB_CUDA(ctx, cudaMemcpyAsync(status + b.lo, b.ip + 2 * n, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (resid) OSB_CUDA(ctx, cudaMemcpyAsync(resid + 2 * b.lo, b.resid, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (history) OSB_CUDA(ctx, cudaMemcpyAsync(history + b.lo * hist_cap * 4, b.hist, n * hist_cap * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OSB_CUDA(ctx, cudaFreeAsync(b.alpha, st));
+    OSB_CUDA(ctx, cudaFreeAsync(b.Re, st));
+    OSB_CUDA(ctx, cudaFreeAsync(b.c, st));
+    OSB_CUDA(ctx, cudaFreeAsync(b.ip, st));
+    if (b.resid) OSB_CUDA(ctx, cudaFreeAsync(b.resid, st));
+    if (b.hist) OSB_CUDA(ctx, cudaFreeAsync(b.hist, st));
+    OSB_CUDA(ctx, cudaFreeAsync(b.tab, st));
+  }
+  for (int d = 0; d < ndev; ++d) {
+    OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
+    OSB_CUDA(ctx, cudaStreamSynchronize(ctx->streams[d]));
+  }
+  return OSB_OK;
+}
+
+int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof,
+                            int64_t nlines, int32_t niter, const double *Re, const double *omega0,
+                            const double *domega, const double *alpha0, double *alpha_out,
+                            int32_t *passes, int32_t *qend, int32_t *status) {
+  if (!ctx || nlines < 0 || niter < 1 || !Re || !omega0 || !domega || !alpha0 || !alpha_out ||
+      !passes || !qend || !status)
+    return fail(ctx, OSB_E_ARG, "null argument");
+  if (!opts || opts->flow != OSB_FLOW_ORRSPACE) return fail(ctx, OSB_E_ARG, "spatial lines need the ORRSPACE flow");
+  ShootArgs base;
+  int analytic = 0;
+  int rc = fill_args(ctx, opts, &base, &analytic);
+  if (rc) return rc;
+  rc = check_profile(ctx, opts, prof);
+  if (rc) return rc;
+  if (nlines == 0) return OSB_OK;
+  const int ndev = (int)ctx->devices.size();
+  struct Buf { double *in = 0, *out = 0; int32_t *ip = 0; double2 *tab = 0; int64_t lo = 0, hi = 0; };
+  std::vector<Buf> bufs(ndev);
+  for (int d = 0; d < ndev; ++d) {
+    Buf &b = bufs[d];
+    chunk(nlines, ndev, d, &b.lo, &b.hi);
+    const int64_t n = b.hi - b.lo;
+    if (n <= 0) continue;
+    cudaStream_t st = ctx->streams[d];
+    OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
+    // in: Re[n], domega[n], omega0[2n], alpha0[2n]
+    OSB_CUDA(ctx, cudaMallocAsync(&b.in, n * 6 * sizeof(double), st));
+    OSB_CUDA(ctx, cudaMallocAsync(&b.out, n * niter * 2 * sizeof(double), st));
+    OSB_CUDA(ctx, cudaMallocAsync(&b.ip, n * niter * 3 * sizeof(int32_t), st));
+    OSB_CUDA(ctx, cudaMemcpyAsync(b.in, Re + b.lo, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    OSB_CUDA(ctx, cudaMemcpyAsync(b.in + n, domega + b.lo, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    OSB_CUDA(ctx, cudaMemcpyAsync(b.in + 2 * n, omega0 + 2 * b.lo, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    OSB_CUDA(ctx, cudaMemcpyAsync(b.in + 4 * n, alpha0 + 2 * b.lo, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    rc = make_stage_table(ctx, d, opts, prof, &b.tab);
+    if (rc) return rc;
+    ShootArgs a = base;
+    a.tab = b.tab;
+    a.nlines = n;
+    a.niter = niter;
+    a.Re = b.in; a.domega = b.in + n;
+    a.omega0 = (const double2 *)(b.in + 2 * n);
+    a.alpha = (const double2 *)(b.in + 4 * n);
+    a.ev = (double2 *)b.out;
+    a.passes = b.ip; a.qend = b.ip + n * niter; a.status = b.ip + 2 * n * niter;
+    int nl = 0;
+    OSB_CUDA(ctx, launch_shoot(a, opts->integrator, analytic, st, &nl));
+    ctx->launches += nl;
+  }
+  for (int d = 0; d < ndev; ++d) {
+    Buf &b = bufs[d];
+    const int64_t n = b.hi - b.lo;
+    if (n <= 0) continue;
+    cudaStream_t st = ctx->streams[d];
+    const int64_t m = n * niter;
+    OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
+    OSB_CUDA(ctx, cudaMemcpyAsync(alpha_out + 2 * b.lo * niter, b.out, m * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OSB_CUDA(ctx, cudaMemcpyAsync(passes + b.lo * niter, b.ip, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    OSB_CUDA(ctx, cudaMemcpyAsync(qend + b.lo * niter, b.ip + m, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    OSB_CUDA(ctx, cudaMemcpyAsync(status + b.lo * niter, b.ip + 2 * m, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    OSB_CUDA(ctx, cudaFreeAsync(b.in, st));
+    OSB_CUDA(ctx, cudaFreeAsync(b.out, st));
+    OSB_CUDA(ctx, cudaFreeAsync(b.ip, st));
+    OSB_CUDA(ctx, cudaFreeAsync(b.tab, st));
+  }
+  for (int d = 0; d < ndev; ++d) {
+    OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
+    OSB_CUDA(ctx, cudaStreamSynchronize(ctx->streams[d]));
+  }
+  return OSB_OK;
+}
+
+int osb_eigfun(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof, int64_t npts,
+               const double *alpha, const double *Re, const double *eig, const double *omega,
+               double *y, double *vmax, int32_t *qend) {
+  if (!ctx || npts < 0 || !Re || !eig || !y || !vmax) return fail(ctx, OSB_E_ARG, "null argument");
+  ShootArgs a;
+  int analytic = 0;
+  int rc = fill_args(ctx, opts, &a, &analytic);
+  if (rc) return rc;
+  rc = check_profile(ctx, opts, prof);
+  if (rc) return rc;
+  if (a.spatial ? !omega : !alpha) return fail(ctx, OSB_E_ARG, "alpha (temporal) / omega (spatial) required");
+  if (npts == 0) return OSB_OK;
+  OSB_CUDA(ctx, cudaSetDevice(ctx->devices[0]));
+  cudaStream_t st = ctx->streams[0];
+  const size_t n1 = (size_t)opts->nstep + 1;
+  double *d_in = nullptr, *d_tq = nullptr;
+  double2 *d_U = nullptr, *d_P = nullptr, *d_y = nullptr, *d_vmax = nullptr, *tab = nullptr;
+  int32_t *d_q = nullptr;
+  OSB_CUDA(ctx, cudaMallocAsync(&d_in, npts * 5 * sizeof(double), st));  // Re, eig(2), alpha|omega(2)
+  OSB_CUDA(ctx, cudaMallocAsync(&d_U, npts * n1 * 8 * sizeof(double2), st));
+  OSB_CUDA(ctx, cudaMallocAsync(&d_P, npts * n1 * 4 * sizeof(double2), st));
+  OSB_CUDA(ctx, cudaMallocAsync(&d_tq, npts * n1 * sizeof(double), st));
+  OSB_CUDA(ctx, cudaMallocAsync(&d_y, npts * n1 * 4 * sizeof(double2), st));
+  OSB_CUDA(ctx, cudaMallocAsync(&d_vmax, npts * sizeof(double2), st));
+  OSB_CUDA(ctx, cudaMallocAsync(&d_q, npts * sizeof(int32_t), st));
+  OSB_CUDA(ctx, cudaMemcpyAsync(d_in, Re, npts * sizeof(double), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(ctx, cudaMemcpyAsync(d_in + npts, eig, npts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(ctx, cudaMemcpyAsync(d_in + 3 * npts, a.spatial ? omega : alpha, npts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  rc = make_stage_table(ctx, 0, opts, prof, &tab);
+  if (rc) return rc;
+  EigfunArgs e;
+  memset(&e, 0, sizeof(e));
+  a.tab = tab;
+  a.Re = d_in;
+  a.alpha = (const double2 *)(d_in + 3 * npts);
+  e.s = a;
+  e.eig = (const double2 *)(d_in + npts);
+  e.omega = (const double2 *)(d_in + 3 * npts);
+  e.U = d_U; e.P = d_P; e.tq = d_tq; e.y = d_y; e.vmax = d_vmax; e.qend = d_q;
+  e.t0 = opts->ymin;
+  e.habs = fabs(a.hs);
+  OSB_CUDA(ctx, launch_eigfun(e, opts->integrator, analytic, npts, st));
+  ctx->launches++;
+  OSB_CUDA(ctx, cudaMemcpyAsync(y, d_y, npts * n1 * 4 * sizeof(double2), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(ctx, cudaMemcpyAsync(vmax, d_vmax, npts * sizeof(double2), cudaMemcpyDeviceToHost, st));
+  if (qend) OSB_CUDA(ctx, cudaMemcpyAsync(qend, d_q, npts * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  OSB_CUDA(ctx, cudaFreeAsync(d_in, st));
+  OSB_CUDA(ctx, cudaFreeAsync(d_U, st));
+  OSB_CUDA(ctx, cudaFreeAsync(d_P, st));
+  OSB_CUDA(ctx, cudaFreeAsync(d_tq, st));
+  OSB_CUDA(ctx, cudaFreeAsync(d_y, st));
+  OSB_CUDA(ctx, cudaFreeAsync(d_vmax, st));
+  OSB_CUDA(ctx, cudaFreeAsync(d_q, st));
+  OSB_CUDA(ctx, cudaFreeAsync(tab, st));
+  OSB_CUDA(ctx, cudaStreamSynchronize(st));
+  return OSB_OK;
+}
+
+// ---------------------------------------------------------------- measurement
+int osb_measure_fp64_peak(osb_ctx *ctx, double ms_target, double *tflops, double *sm_clock_mhz_est) {
+  if (!ctx || !tflops) return OSB_E_ARG;
+  OSB_CUDA(ctx, cudaSetDevice(ctx->devices[0]));
+  cudaStream_t st = ctx->streams[0];
+  cudaDeviceProp prop;
+  OSB_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->devices[0]));
+  const int threads = 256, blocks = prop.multiProcessorCount * 8;
+  double *d_out = nullptr;
+  OSB_CUDA(ctx, cudaMallocAsync(&d_out, sizeof(double), st));
+  cudaEvent_t e0, e1;
+  OSB_CUDA(ctx, cudaEventCreate(&e0));
+  OSB_CUDA(ctx, cudaEventCreate(&e1));
+  int iters = 2000;
+  double best = 0.0;
+  float ms = 0.f;
+  for (int rep = 0; rep < 6; ++rep) {
+    OSB_CUDA(ctx, cudaEventRecord(e0, st));
+    OSB_CUDA(ctx, launch_fp64_peak(d_out, iters, blocks, threads, st));
+    ctx->launches++;
+    OSB_CUDA(ctx, cudaEventRecord(e1, st));
+    OSB_CUDA(ctx, cudaEventSynchronize(e1));
+    OSB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+    double flops = 2.0 * 8.0 * 16.0 * (double)iters * threads * (double)blocks;
+    double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0) best = std::max(best, tf);
+    if (ms < ms_target && iters < (1 << 24)) iters = (int)std::min<double>(1 << 24, iters * std::max(1.5, ms_target / std::max(ms, 1e-3f)));
+  }
+  *tflops = best;
+  if (sm_clock_mhz_est)  // 64 DFMA / clk / SM on B200
+    *sm_clock_mhz_est = best * 1e12 / (2.0 * 64.0 * prop.multiProcessorCount) / 1e6;
+  OSB_CUDA(ctx, cudaFreeAsync(d_out, st));
+  OSB_CUDA(ctx, cudaStreamSynchronize(st));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return OSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,669 @@
+// shoot_kernels.cu -- K1b (stage table) and K2 (Godunov-Conte shooting) for sm_100a.
+//
+// K2 replaces the reference's CONTE_IC / CONTE eigenvalue iteration
+// (shoot.f:391-813, shoot.f:26-388, orrsom.f:165-506, orrspace.f:209-582) for a
+// whole batch of independent sweep points: one thread owns one point (or one
+// continuation line), keeps both solution vectors (2 x 4 complex) and all
+// Runge-Kutta stage derivatives in registers, and runs the secant/Muller update
+// on the eigenvalue inside the kernel.  The work is bound by the FP64 pipe;
+// HBM traffic is ~60 B per point.
+//
+// Design notes:
+//  * The mean flow enters the RHS only through U(t), U''(t) at the integrator's
+//    stage abscissae, and those abscissae are the same for every point of the
+//    batch.  K1b evaluates the reference's spline (SPDER/SPEVAL, shoot.f:960-1101)
+//    once per abscissa -- in the reference's own operation order, without FMA
+//    contraction -- into a [nstep][stages] table.  K2 then reads one warp-uniform
+//    row (96 B for Cash-Karp) per step instead of bisecting + evaluating a cubic
+//    12 times per step per point as the reference does.
+//  * RHS row 4 is regrouped as A(t)*y1 + B(t)*y3 with
+//      B = 2a^2 + ik(U-c),  A = -a^2 (a^2 + ik(U-c)) - ik U'',  k = alpha*Re
+//    (contebl.f:335-337); A, B are computed once per stage and shared by both
+//    solution vectors.
+//  * The step size is folded into the tableau on the host (bh = b*h, ch = c*h).
+//  * The orthonormality test acos(cc/sqrt(aa*bb)) < ta (shoot.f:593-606) is
+//    evaluated as cc^2 > cos^2(ta)*aa*bb (acos is monotone): no sqrt/div/acos on
+//    the per-step path.
+#include "osb_cplx.cuh"
+#include "osb_internal.h"
+
+namespace osb {
+
+// ---------------------------------------------------------------------------
+// K1b: stage table
+// ---------------------------------------------------------------------------
+#define OSB_MUL(a, b) __dmul_rn((a), (b))
+#define OSB_ADD(a, b) __dadd_rn((a), (b))
+#define OSB_SUB(a, b) __dsub_rn((a), (b))
+#define OSB_DIV(a, b) __ddiv_rn((a), (b))
+
+// BISECT (shoot.f:1018-1034) with the exact-knot shortcuts of SPDER
+// (shoot.f:1070-1076); returns the 1-based interval index.
+__device__ static int find_bisect(const double *X0, int N, double xx) {
+  if (xx == X0[0]) return 1;
+  if (xx == X0[N - 1]) return N;
+  int il = 0, ir = N - 1;
+  while (ir - il > 1) {
+    int im = (ir + il) >> 1;
+    if (X0[im] > xx) ir = im; else il = im;
+  }
+  return il + 1;
+}
+
+// linear search of orrsom.f:885-908 / orrspace.f:906-929: first I with xx <= X(I+1).
+// X is ascending, so a binary search for the same predicate gives the same I.
+__device__ static int find_linear(const double *X0, int N, double xx) {
+  int lo = 1, hi = N;  // answer in [1, N]; N means "fell through"
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;  // candidate I = mid (<= N-1 here)
+    if (xx <= X0[mid]) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// the cubic of SPEVAL/SPDER (shoot.f:1008-1013, 1090-1095), reference operation order
+__device__ static double spline_value(const double *X0, const double *Y0, const double *F0,
+                                      int I, double XX) {
+  const double *X = X0 - 1, *Y = Y0 - 1, *FDP = F0 - 1;
+  double DXM = OSB_SUB(XX, X[I]);
+  double DXP = OSB_SUB(X[I + 1], XX);
+  double DEL = OSB_SUB(X[I + 1], X[I]);
+  double t1 = OSB_DIV(OSB_MUL(OSB_MUL(FDP[I], DXP), OSB_SUB(OSB_DIV(OSB_MUL(DXP, DXP), DEL), DEL)), 6.0);
+  double t2 = OSB_DIV(OSB_MUL(OSB_MUL(FDP[I + 1], DXM), OSB_SUB(OSB_DIV(OSB_MUL(DXM, DXM), DEL), DEL)), 6.0);
+  double t3 = OSB_DIV(OSB_MUL(Y[I], DXP), DEL);
+  double t4 = OSB_DIV(OSB_MUL(Y[I + 1], DXM), DEL);
+  return OSB_ADD(OSB_ADD(OSB_ADD(t1, t2), t3), t4);
+}
+// FPP of SPDER (shoot.f:1099)
+__device__ static double spline_fpp(const double *X0, const double *F0, int I, double XX) {
+  const double *X = X0 - 1, *FDP = F0 - 1;
+  double DXM = OSB_SUB(XX, X[I]);
+  double DXP = OSB_SUB(X[I + 1], XX);
+  double DEL = OSB_SUB(X[I + 1], X[I]);
+  return OSB_ADD(OSB_DIV(OSB_MUL(FDP[I], DXP), DEL), OSB_DIV(OSB_MUL(FDP[I + 1], DXM), DEL));
+}
+
+int stages_per_step(int integrator) { return integrator == OSB_INT_CK45 ? 6 : 3; }
+
+__global__ void stage_table_kernel(const double *__restrict__ tables, int nbl, int flow,
+                                   int integrator, int nstep, double to, double tf,
+                                   double2 *__restrict__ tab) {
+  const int NS = (integrator == OSB_INT_CK45) ? 6 : 3;
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nstep * NS) return;
+  int k = idx / NS + 1;
+  int s = idx % NS;
+  const double h = OSB_DIV(OSB_SUB(tf, to), (double)nstep);  // shoot.f:471
+  double t0, hs;
+  if (flow == OSB_FLOW_CONTE) {  // t = to + h*k; STEP(.., t-h, +h)   shoot.f:110,116
+    double t = OSB_ADD(to, OSB_MUL(h, (double)k));
+    t0 = OSB_SUB(t, h);
+    hs = h;
+  } else {  // t = tf - h*k; STEP(.., t+h, -h)   shoot.f:527,563
+    double t = OSB_SUB(tf, OSB_MUL(h, (double)k));
+    t0 = OSB_ADD(t, h);
+    hs = -h;
+  }
+  double ts;
+  if (integrator == OSB_INT_CK45) {  // t = to + a(m)*h   shoot.f:1410
+    const double a[6] = {0.0, 0.2, 0.3, 0.6, 1.0, 0.875};
+    ts = OSB_ADD(t0, OSB_MUL(a[s], hs));
+  } else {  // to, to+0.5*h, to+h   shoot.f:881-896
+    ts = (s == 0) ? t0 : (s == 1 ? OSB_ADD(t0, OSB_MUL(0.5, hs)) : OSB_ADD(t0, hs));
+  }
+  double UU, d2UU;
+  if (flow == OSB_FLOW_CONTE) {  // CHANNEL conte.f:319-321
+    UU = OSB_SUB(1.0, OSB_MUL(ts, ts));
+    d2UU = -2.0;
+  } else {
+    const size_t n = (size_t)nbl + 2;
+    const double *ydat = tables, *U = tables + n, *Uspl = tables + 2 * n,
+                 *d2U = tables + 3 * n, *d2Uspl = tables + 4 * n;
+    if (flow == OSB_FLOW_CONTEBL) {  // SPDER contebl.f:330
+      int I = find_bisect(ydat, nbl + 1, ts);
+      UU = spline_value(ydat, U, Uspl, I, ts);
+      d2UU = spline_fpp(ydat, Uspl, I, ts);
+    } else {  // two SPEVALs orrsom.f:627-628, orrspace.f:634-635
+      int I = find_linear(ydat, nbl + 1, ts);
+      UU = spline_value(ydat, U, Uspl, I, ts);
+      d2UU = spline_value(ydat, d2U, d2Uspl, I, ts);
+    }
+  }
+  tab[idx] = make_double2(UU, d2UU);
+}
+
+cudaError_t launch_stage_table(const ProfileDev &p, int flow, int integrator, int nstep,
+                               double to, double tf, double2 *tab, cudaStream_t st) {
+  int n = nstep * stages_per_step(integrator);
+  int threads = 128, blocks = (n + threads - 1) / threads;
+  stage_table_kernel<<<blocks, threads, 0, st>>>(p.tables, p.nbl, flow, integrator, nstep, to, tf, tab);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// K2: shooting
+// ---------------------------------------------------------------------------
+struct PassConst {
+  double a2r, a2i;  // alpha^2
+  double kr, ki;    // i*alpha*Re
+  double g0r, g0i;  // alpha^2 - i*alpha*Re*c
+};
+
+struct StageCoef {
+  double Ar, Ai, Br, Bi;
+};
+
+__device__ __forceinline__ StageCoef stage_coef(const PassConst &pc, double2 uu) {
+  // G = a^2 + ik(U - c);  B = G + a^2;  A = -a^2 G - ik U''
+  double Gr = fma(pc.kr, uu.x, pc.g0r);
+  double Gi = fma(pc.ki, uu.x, pc.g0i);
+  StageCoef s;
+  s.Br = Gr + pc.a2r;
+  s.Bi = Gi + pc.a2i;
+  s.Ar = fma(-pc.a2r, Gr, fma(pc.a2i, Gi, -pc.kr * uu.y));
+  s.Ai = fma(-pc.a2r, Gi, fma(-pc.a2i, Gr, -pc.ki * uu.y));
+  return s;
+}
+
+// r = A*y1 + B*y3   (y laid out re,im interleaved: y1 = y[0..1], y3 = y[4..5])
+__device__ __forceinline__ void rhs4(const StageCoef &s, const double *y, double &rr, double &ri) {
+  rr = fma(s.Ar, y[0], fma(-s.Ai, y[1], fma(s.Br, y[4], -s.Bi * y[5])));
+  ri = fma(s.Ar, y[1], fma(s.Ai, y[0], fma(s.Br, y[5], s.Bi * y[4])));
+}
+
+// One fixed Cash-Karp step (CRKCK45, shoot.f:1367-1439) of BOTH solution vectors.
+// u[v][0..7] = (y1, y2, y3, y4) of vector v.  f[k] holds the stage derivative
+// (y2, y3, y4, r) WITHOUT the step size; bh/ch carry it.
+__device__ __forceinline__ void step_ck45(double (&u)[2][8], const double2 *__restrict__ trow,
+                                          const PassConst &pc, const ShootArgs &a) {
+  double f[2][6][8];
+#pragma unroll
+  for (int m = 0; m < 6; ++m) {
+    const StageCoef sc = stage_coef(pc, __ldg(&trow[m]));
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      double yt[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        double acc = u[v][n];
+#pragma unroll
+        for (int k = 0; k < m; ++k) acc = fma(a.bh[m * (m - 1) / 2 + k], f[v][k][n], acc);
+        yt[n] = acc;
+      }
+#pragma unroll
+      for (int n = 0; n < 6; ++n) f[v][m][n] = yt[n + 2];
+      rhs4(sc, yt, f[v][m][6], f[v][m][7]);
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < 2; ++v)
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      // c(2) = c(5) = 0 (shoot.f:1390-1391)
+      double acc = u[v][n];
+      acc = fma(a.ch[0], f[v][0][n], acc);
+      acc = fma(a.ch[2], f[v][2][n], acc);
+      acc = fma(a.ch[3], f[v][3][n], acc);
+      acc = fma(a.ch[5], f[v][5][n], acc);
+      u[v][n] = acc;
+    }
+}
+
+// One classical RK4 step (CRK4, shoot.f:869-903) of both vectors.  Table row:
+// (to, to+h/2, to+h).
+__device__ __forceinline__ void step_rk4(double (&u)[2][8], const double2 *__restrict__ trow,
+                                         const PassConst &pc, const ShootArgs &a) {
+  const double hs = a.hs, h2 = 0.5 * a.hs, h6 = a.hs / 6.0, h3 = a.hs / 3.0;
+  const StageCoef s0 = stage_coef(pc, __ldg(&trow[0]));
+  const StageCoef s1 = stage_coef(pc, __ldg(&trow[1]));
+  const StageCoef s2 = stage_coef(pc, __ldg(&trow[2]));
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    double f[8], q[8], acc[8];
+    // k1
+#pragma unroll
+    for (int n = 0; n < 6; ++n) f[n] = u[v][n + 2];
+    rhs4(s0, u[v], f[6], f[7]);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { acc[n] = fma(h6, f[n], u[v][n]); q[n] = fma(h2, f[n], u[v][n]); }
+    // k2
+#pragma unroll
+    for (int n = 0; n < 6; ++n) f[n] = q[n + 2];
+    rhs4(s1, q, f[6], f[7]);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) acc[n] = fma(h3, f[n], acc[n]);
+    {
+      double q2[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) q2[n] = fma(h2, f[n], u[v][n]);
+      // k3
+#pragma unroll
+      for (int n = 0; n < 6; ++n) f[n] = q2[n + 2];
+      rhs4(s1, q2, f[6], f[7]);
+    }
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { acc[n] = fma(h3, f[n], acc[n]); q[n] = fma(hs, f[n], u[v][n]); }
+    // k4
+#pragma unroll
+    for (int n = 0; n < 6; ++n) f[n] = q[n + 2];
+    rhs4(s2, q, f[6], f[7]);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) u[v][n] = fma(h6, f[n], acc[n]);
+  }
+}
+
+// <v1, v2>: Hermitian sum v1 conj(v2) (contebl.f:238-241) or analytic sum v1 v2
+// (orrspace.f:597-601)
+template <bool ANALYTIC>
+__device__ __forceinline__ zd inprod(const double *v1, const double *v2) {
+  double re = 0.0, im = 0.0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double ar = v1[2 * i], ai = v1[2 * i + 1], br = v2[2 * i], bi = v2[2 * i + 1];
+    if (ANALYTIC) {
+      re = fma(ar, br, fma(-ai, bi, re));
+      im = fma(ar, bi, fma(ai, br, im));
+    } else {
+      re = fma(ar, br, fma(ai, bi, re));
+      im = fma(ai, br, fma(-ar, bi, im));
+    }
+  }
+  return zd{re, im};
+}
+
+// Gram-Schmidt (shoot.f:621-639).  Returns w1, w2 and p = <U2, z1> for the P matrix.
+template <bool ANALYTIC>
+__device__ __forceinline__ void gram_schmidt(double (&u)[2][8], zd &w1, zd &w2, zd &p) {
+  if (ANALYTIC) {
+    w1 = zsqrt(inprod<true>(u[0], u[0]));
+    zd r1 = zdiv(zd{1.0, 0.0}, w1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      zd z = zmul(zd{u[0][2 * i], u[0][2 * i + 1]}, r1);
+      u[0][2 * i] = z.x; u[0][2 * i + 1] = z.y;
+    }
+    p = inprod<true>(u[1], u[0]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      zd pz = zmul(p, zd{u[0][2 * i], u[0][2 * i + 1]});
+      u[1][2 * i] -= pz.x; u[1][2 * i + 1] -= pz.y;
+    }
+    w2 = zsqrt(inprod<true>(u[1], u[1]));
+    zd r2 = zdiv(zd{1.0, 0.0}, w2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      zd z = zmul(zd{u[1][2 * i], u[1][2 * i + 1]}, r2);
+      u[1][2 * i] = z.x; u[1][2 * i + 1] = z.y;
+    }
+  } else {
+    double aa = inprod<false>(u[0], u[0]).x;
+    double s1 = sqrt(aa);
+    w1 = zd{s1, 0.0};
+    double r1 = 1.0 / s1;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) u[0][n] *= r1;
+    p = inprod<false>(u[1], u[0]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double zr = u[0][2 * i], zi = u[0][2 * i + 1];
+      u[1][2 * i] -= p.x * zr - p.y * zi;
+      u[1][2 * i + 1] -= p.x * zi + p.y * zr;
+    }
+    double ee = inprod<false>(u[1], u[1]).x;
+    double s2 = sqrt(ee);
+    w2 = zd{s2, 0.0};
+    double r2 = 1.0 / s2;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) u[1][n] *= r2;
+  }
+}
+
+// orthonormality test (shoot.f:593-606 and its three variants), see header note
+template <bool ANALYTIC>
+__device__ __forceinline__ bool need_norm(const double (&u)[2][8], double thr, int strict) {
+  double lhs, rhs;
+  if (ANALYTIC) {
+    zd a = inprod<true>(u[0], u[0]), b = inprod<true>(u[1], u[1]), c = inprod<true>(u[0], u[1]);
+    lhs = fma(c.x, c.x, c.y * c.y);
+    rhs = thr * (sqrt(fma(a.x, a.x, a.y * a.y)) * sqrt(fma(b.x, b.x, b.y * b.y)));
+  } else {
+    double aa = 0.0, bb = 0.0;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { aa = fma(u[0][n], u[0][n], aa); bb = fma(u[1][n], u[1][n], bb); }
+    zd c = inprod<false>(u[0], u[1]);
+    lhs = fma(c.x, c.x, c.y * c.y);
+    rhs = thr * (aa * bb);
+  }
+  return strict ? (lhs > rhs) : (lhs >= rhs);
+}
+
+__device__ __forceinline__ PassConst pass_const(zd alpha, double Re, zd cw) {
+  PassConst pc;
+  zd a2 = zmul(alpha, alpha);
+  zd k = zd{-alpha.y * Re, alpha.x * Re};  // (0,1)*alpha*Re
+  zd kc = zmul(k, cw);
+  pc.a2r = a2.x; pc.a2i = a2.y; pc.kr = k.x; pc.ki = k.y;
+  pc.g0r = a2.x - kc.x; pc.g0i = a2.y - kc.y;
+  return pc;
+}
+
+// initial vectors: free-stream asymptotes (BL_IC contebl.f:269-279) or e3, e4 (shoot.f:88-96)
+__device__ __forceinline__ void initial_vectors(double (&u)[2][8], const ShootArgs &a, zd alpha,
+                                                double Re, zd cw) {
+  if (a.bl_ic) {
+    zd a2 = zmul(alpha, alpha), a3 = zmul(a2, alpha);
+    zd ea = zexp(zd{-alpha.x * a.tf, -alpha.y * a.tf});
+    zd v;
+    u[0][0] = ea.x; u[0][1] = ea.y;
+    v = zmul(zneg(alpha), ea); u[0][2] = v.x; u[0][3] = v.y;
+    v = zmul(a2, ea); u[0][4] = v.x; u[0][5] = v.y;
+    v = zmul(zneg(a3), ea); u[0][6] = v.x; u[0][7] = v.y;
+    zd k = zd{-alpha.y * Re, alpha.x * Re};
+    zd g = zsqrt(zadd(a2, zmul(k, zd{1.0 - cw.x, -cw.y})));
+    zd g2 = zmul(g, g), g3 = zmul(g2, g);
+    zd eg = zexp(zd{-g.x * a.tf, -g.y * a.tf});
+    u[1][0] = eg.x; u[1][1] = eg.y;
+    v = zmul(zneg(g), eg); u[1][2] = v.x; u[1][3] = v.y;
+    v = zmul(g2, eg); u[1][4] = v.x; u[1][5] = v.y;
+    v = zmul(zneg(g3), eg); u[1][6] = v.x; u[1][7] = v.y;
+  } else {
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { u[0][n] = 0.0; u[1][n] = 0.0; }
+    u[0][4] = 1.0;  // e3
+    u[1][6] = 1.0;  // e4
+  }
+}
+
+// One integration across the layer at the current eigenvalue guess; returns the
+// wall residual err (shoot.f:699-700,716) and the normalisation count qend.
+template <int INTEG, bool ANALYTIC>
+__device__ __forceinline__ void integrate_pass(const ShootArgs &a, zd alpha, double Re, zd cw,
+                                               zd &err, int &qend) {
+  constexpr int NS = (INTEG == OSB_INT_CK45) ? 6 : 3;
+  const PassConst pc = pass_const(alpha, Re, cw);
+  double u[2][8];
+  initial_vectors(u, a, alpha, Re, cw);
+  int q = 0;
+  const double2 *__restrict__ trow = a.tab;
+  // k = 0 is the Gram-Schmidt of the initial vectors (shoot.f:490-515); k >= 1
+  // are the integration steps.  One Gram-Schmidt site keeps the code small.
+  for (int k = a.bl_ic ? 0 : 1; k <= a.nstep; ++k) {
+    bool norm;
+    if (k > 0) {
+      if (INTEG == OSB_INT_CK45) step_ck45(u, trow, pc, a);
+      else step_rk4(u, trow, pc, a);
+      trow += NS;
+      norm = need_norm<ANALYTIC>(u, a.thr, a.strict) || (k == a.nstep);
+      q += norm ? 1 : 0;
+    } else {
+      norm = true;
+    }
+    if (norm) {
+      zd w1, w2, p;
+      gram_schmidt<ANALYTIC>(u, w1, w2, p);
+    }
+  }
+  qend = q;
+  // B(1) = -U(1,2)/U(1,1), B(2) = 1; err = U(2,1) B(1) + U(2,2) B(2)
+  zd B1 = zneg(zdiv(zd{u[1][0], u[1][1]}, zd{u[0][0], u[0][1]}));
+  err = zadd(zmul(zd{u[0][2], u[0][3]}, B1), zd{u[1][2], u[1][3]});
+}
+
+// secant / Muller update of the eigenvalue, shoot.f:713-744
+struct IterState {
+  zd ev, cm1, cm2, errm1, errm2;
+  int icount;
+  int cm1_defined;
+};
+
+__device__ __forceinline__ void update_eigenvalue(IterState &s, zd err, zd ctemp, int first_perturb) {
+  if (s.icount == 1) {
+    s.cm2 = s.ev;
+    s.errm2 = err;
+    if (first_perturb) s.ev = zd{s.ev.x * 1.01, s.ev.y * 1.01};  // orrspace.f:459
+    else s.ev = zd{s.ev.x * .9999, s.ev.y};                       // shoot.f:718
+  } else if (s.icount == 2) {
+    s.cm1 = s.ev; s.cm1_defined = 1;
+    s.errm1 = err;
+    double den = s.ev.x - s.cm2.x;
+    zd fd = zd{(err.x - s.errm2.x) / den, (err.y - s.errm2.y) / den};
+    s.ev = zsub(s.ev, zdiv(err, fd));
+  } else {
+    zd c = s.ev;
+    zd qt = zdiv(zsub(c, s.cm1), zsub(s.cm1, s.cm2));
+    zd one_qt = zd{1.0 + qt.x, qt.y};
+    zd qt2 = zmul(qt, qt);
+    zd At = zadd(zsub(zmul(qt, err), zmul(zmul(qt, one_qt), s.errm1)), zmul(qt2, s.errm2));
+    zd Bt = zadd(zsub(zmul(zd{2.0 * qt.x + 1.0, 2.0 * qt.y}, err), zmul(zmul(one_qt, one_qt), s.errm1)),
+                 zmul(qt2, s.errm2));
+    zd Ct = zmul(one_qt, err);
+    zd D = zsqrt(zsub(zmul(Bt, Bt), zmul(zscale(4.0, At), Ct)));
+    zd dp = zadd(Bt, D), dm = zsub(Bt, D);
+    zd den = (zabs(dp) > zabs(dm)) ? dp : dm;
+    zd num = zmul(zscale(2.0, zsub(ctemp, s.cm1)), Ct);
+    s.ev = zsub(ctemp, zdiv(num, den));
+    s.cm2 = s.cm1;
+    s.cm1 = ctemp;
+    s.errm2 = s.errm1;
+    s.errm1 = err;
+  }
+}
+
+__device__ __forceinline__ bool keep_going(const ShootArgs &a, const IterState &s, zd err) {
+  double dc = s.cm1_defined ? zabs(zsub(s.ev, s.cm1)) : 1.0;
+  double ae = zabs(err);
+  if (a.loop_rule == 0) return ((ae >= a.errtol) || (dc >= a.eigtol)) && (s.icount <= a.maxcount);
+  return (ae >= a.errtol) && (s.icount <= a.maxcount) && (dc >= a.eigtol);
+}
+
+template <int INTEG, bool ANALYTIC>
+__global__ void __launch_bounds__(128) shoot_kernel(const __grid_constant__ ShootArgs a) {
+  const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= a.nlines) return;
+  const double Re = a.Re[line];
+  zd alpha, omega = zd{0.0, 0.0};
+  IterState s;
+  {
+    double2 al = a.alpha[line];
+    alpha = zd{al.x, al.y};
+    if (a.spatial) {
+      double2 om = a.omega0[line];
+      omega = zd{om.x, om.y};
+      s.ev = alpha;
+    } else {
+      double2 c0 = a.ev[line];
+      s.ev = zd{c0.x, c0.y};
+    }
+  }
+  for (int it = 0; it < a.niter; ++it) {
+    const int64_t out = line * a.niter + it;
+    s.icount = 1;
+    s.cm1_defined = a.cm1_defined;
+    s.cm1 = zd{s.ev.x + 1.0, s.ev.y};
+    s.cm2 = zd{0.0, 0.0}; s.errm1 = zd{0.0, 0.0}; s.errm2 = zd{0.0, 0.0};
+    zd err = zd{1.0, 0.0}, ctemp = s.ev;
+    int qend = 0, status = OSB_ST_MAXCOUNT;
+    while (true) {
+      if (!keep_going(a, s, err)) {
+        if (s.icount <= a.maxcount) status = OSB_ST_CONVERGED;
+        break;
+      }
+      ctemp = s.ev;
+      {
+        // spatial: the unknown is alpha and c = omega/alpha (orrspace.f:290,645)
+        const zd al = a.spatial ? s.ev : alpha;
+        const zd cw = a.spatial ? zdiv(omega, s.ev) : s.ev;
+        integrate_pass<INTEG, ANALYTIC>(a, al, Re, cw, err, qend);
+      }
+      update_eigenvalue(s, err, ctemp, a.first_perturb);
+      if (a.history && s.icount <= a.hist_cap) {
+        zd shown = a.show_updated ? s.ev : ctemp;
+        a.history[out * a.hist_cap + (s.icount - 1)] = make_double4(shown.x, shown.y, err.x, err.y);
+      }
+      s.icount += 1;
+      if (!(zfinite(s.ev) && zfinite(err))) { status = OSB_ST_NONFINITE; break; }
+    }
+    a.ev[out] = make_double2(ctemp.x, ctemp.y);
+    a.passes[out] = s.icount - 1;
+    a.qend[out] = qend;
+    a.status[out] = status;
+    if (a.resid)
+      a.resid[out] = make_double2(zabs(err), s.cm1_defined ? zabs(zsub(s.ev, s.cm1)) : 0.0);
+    if (a.spatial) {
+      s.ev = ctemp;  // orrspace.f:494: alpha = ctemp seeds the next omega
+      omega.x += a.domega[line];  // orrspace.f:192-194
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K2b: eigenfunction pass (shoot.f:762-810; conte shoot.f:338-385).  One thread
+// per requested point: re-integrates at the converged eigenvalue keeping the
+// (orthonormalised) trajectory, the P matrices and the normalisation abscissae,
+// then back-substitutes B and applies the reference's vmax scan (oracle D-2).
+// ---------------------------------------------------------------------------
+template <int INTEG, bool ANALYTIC>
+__global__ void __launch_bounds__(64) eigfun_kernel(const __grid_constant__ EigfunArgs e, int64_t npts) {
+  constexpr int NS = (INTEG == OSB_INT_CK45) ? 6 : 3;
+  const ShootArgs &a = e.s;
+  const int64_t pt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt >= npts) return;
+  const int nstep = a.nstep;
+  const size_t n1 = (size_t)nstep + 1;
+  double2 *Ut = e.U + pt * n1 * 8;
+  double2 *Pq = e.P + pt * n1 * 4;
+  double *tq = e.tq + pt * n1;
+  double2 *yo = e.y + pt * n1 * 4;
+  const double Re = a.Re[pt];
+  zd alpha, cw;
+  {
+    double2 ev = e.eig[pt];
+    if (a.spatial) {
+      double2 om = e.omega[pt];
+      alpha = zd{ev.x, ev.y};
+      cw = zdiv(zd{om.x, om.y}, alpha);
+    } else {
+      double2 al = a.alpha[pt];
+      alpha = zd{al.x, al.y};
+      cw = zd{ev.x, ev.y};
+    }
+  }
+  const PassConst pc = pass_const(alpha, Re, cw);
+  const bool bl = a.hs < 0.0;
+  double u[2][8];
+  initial_vectors(u, a, alpha, Re, cw);
+  int q = 0;
+  tq[0] = bl ? a.tf : e.t0;
+  const double2 *__restrict__ trow = a.tab;
+  for (int k = a.bl_ic ? 0 : 1; k <= nstep; ++k) {
+    bool norm;
+    double t = bl ? __dsub_rn(a.tf, __dmul_rn(e.habs, (double)k)) : __dadd_rn(e.t0, __dmul_rn(e.habs, (double)k));
+    if (k > 0) {
+      if (INTEG == OSB_INT_CK45) step_ck45(u, trow, pc, a);
+      else step_rk4(u, trow, pc, a);
+      trow += NS;
+      norm = need_norm<ANALYTIC>(u, a.thr, a.strict) || (k == nstep);
+    } else {
+      norm = true;
+    }
+    if (norm) {
+      zd w1, w2, p;
+      gram_schmidt<ANALYTIC>(u, w1, w2, p);
+      if (k > 0) {
+        q += 1;
+        tq[q] = t;
+        zd P11 = zdiv(zd{1.0, 0.0}, w1), P22 = zdiv(zd{1.0, 0.0}, w2);
+        zd P21 = zneg(zmul(zdiv(p, w2), P11));  // shoot.f:652-653
+        Pq[(size_t)q * 4 + 0] = make_double2(P11.x, P11.y);
+        Pq[(size_t)q * 4 + 1] = make_double2(P21.x, P21.y);
+        Pq[(size_t)q * 4 + 2] = make_double2(P22.x, P22.y);
+      }
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      Ut[(size_t)k * 8 + n] = make_double2(u[0][2 * n], u[0][2 * n + 1]);
+      Ut[(size_t)k * 8 + 4 + n] = make_double2(u[1][2 * n], u[1][2 * n + 1]);
+    }
+  }
+  if (!a.bl_ic) {  // k = 0 of the channel flow: the unit vectors themselves
+    double v[2][8];
+    initial_vectors(v, a, alpha, Re, cw);
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      Ut[n] = make_double2(v[0][2 * n], v[0][2 * n + 1]);
+      Ut[4 + n] = make_double2(v[1][2 * n], v[1][2 * n + 1]);
+    }
+  }
+  const int qend = q;
+  if (e.qend) e.qend[pt] = qend;
+  // B(:,qend): phi(wall) = 0 enforced (shoot.f:699-700)
+  zd Bq1 = zneg(zdiv(zd{u[1][0], u[1][1]}, zd{u[0][0], u[0][1]})), Bq2 = zd{1.0, 0.0};
+  auto apply_PT = [&](int qq, zd b1, zd b2, zd &o1, zd &o2) {
+    // B(m,q-1) = sum_j P(j,m,q) B(j,q)   (shoot.f:772-777)
+    double2 p11 = Pq[(size_t)qq * 4 + 0], p21 = Pq[(size_t)qq * 4 + 1], p22 = Pq[(size_t)qq * 4 + 2];
+    o1 = zadd(zmul(zd{p11.x, p11.y}, b1), zmul(zd{p21.x, p21.y}, b2));
+    o2 = zmul(zd{p22.x, p22.y}, b2);
+  };
+  auto combine = [&](int k, zd b1, zd b2) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      double2 u1 = Ut[(size_t)k * 8 + n], u2 = Ut[(size_t)k * 8 + 4 + n];
+      zd v = zadd(zmul(zd{u1.x, u1.y}, b1), zmul(zd{u2.x, u2.y}, b2));
+      yo[(size_t)k * 4 + n] = make_double2(v.x, v.y);
+    }
+  };
+  combine(nstep, Bq1, Bq2);
+  zd Bp1, Bp2;
+  apply_PT(q, Bq1, Bq2, Bp1, Bp2);
+  zd vmax = zd{0.0, 0.0};
+  for (int k = nstep - 1; k >= 0; --k) {
+    double t = bl ? __dsub_rn(a.tf, __dmul_rn(e.habs, (double)k)) : __dadd_rn(e.t0, __dmul_rn(e.habs, (double)k));
+    bool back = bl ? (t > tq[q - 1]) : (t < tq[q - 1]);
+    if (back) {
+      q -= 1;
+      Bq1 = Bp1; Bq2 = Bp2;
+      apply_PT(q, Bq1, Bq2, Bp1, Bp2);
+    }
+    combine(k, Bp1, Bp2);
+    // the reference's scan reads y(n+1,k) == y(1,k+1)  (shoot.f:795-797)
+    double2 y1 = yo[(size_t)(k + 1) * 4];
+    if (zabs(zd{y1.x, y1.y}) > zabs(vmax)) vmax = zd{y1.x, y1.y};
+  }
+  e.vmax[pt] = make_double2(vmax.x, vmax.y);
+}
+
+cudaError_t launch_eigfun(const EigfunArgs &e, int integrator, int analytic_inprod, int64_t npts,
+                          cudaStream_t st) {
+  if (npts <= 0) return cudaSuccess;
+  int threads = 32;
+  unsigned blocks = (unsigned)((npts + threads - 1) / threads);
+  if (integrator == OSB_INT_CK45) {
+    if (analytic_inprod) eigfun_kernel<OSB_INT_CK45, true><<<blocks, threads, 0, st>>>(e, npts);
+    else eigfun_kernel<OSB_INT_CK45, false><<<blocks, threads, 0, st>>>(e, npts);
+  } else {
+    if (analytic_inprod) eigfun_kernel<OSB_INT_RK4, true><<<blocks, threads, 0, st>>>(e, npts);
+    else eigfun_kernel<OSB_INT_RK4, false><<<blocks, threads, 0, st>>>(e, npts);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_shoot(const ShootArgs &a, int integrator, int analytic_inprod, cudaStream_t st,
+                         int *nlaunch) {
+  if (a.nlines <= 0) return cudaSuccess;
+  // small batches: narrow CTAs so the points spread over all 148 SMs
+  int threads = (a.nlines >= 148 * 4 * 128) ? 128 : (a.nlines >= 148 * 4 * 64 ? 64 : 32);
+  int64_t blocks = (a.nlines + threads - 1) / threads;
+  if (blocks > 0x7fffffff) return cudaErrorInvalidValue;
+  dim3 g((unsigned)blocks), b(threads);
+  if (integrator == OSB_INT_CK45) {
+    if (analytic_inprod) shoot_kernel<OSB_INT_CK45, true><<<g, b, 0, st>>>(a);
+    else shoot_kernel<OSB_INT_CK45, false><<<g, b, 0, st>>>(a);
+  } else {
+    if (analytic_inprod) shoot_kernel<OSB_INT_RK4, true><<<g, b, 0, st>>>(a);
+    else shoot_kernel<OSB_INT_RK4, false><<<g, b, 0, st>>>(a);
+  }
+  if (nlaunch) *nlaunch += 1;
+  return cudaGetLastError();
+}
+
+}  // namespace osb

@@ -1,0 +1,103 @@
+"""ctypes binding of oracle/_build/libos_oracle.so -- TEST INFRASTRUCTURE ONLY.
+
+Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs; never by the product package."""
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+LIB = ROOT / "oracle" / "_build" / "libos_oracle.so"
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+FLOW_CONTEBL, FLOW_CONTE, FLOW_ORRSOM, FLOW_ORRSPACE = 0, 1, 2, 3
+INT_RK4, INT_CK45 = 0, 1
+
+
+def build():
+    subprocess.run(["make", "-s", "-C", str(ROOT / "oracle")], check=True)
+
+
+class Oracle:
+    def __init__(self, lib):
+        self.lib = lib
+        i, d, i64 = C.c_int, C.c_double, C.c_int64
+        lib.osr_solve_bl.restype = i
+        lib.osr_solve_bl.argtypes = [i, i, i, d, d, d, d, _dp, _dp, _dp, _dp, _dp, _dp]
+        lib.osr_shoot_temporal.restype = i
+        lib.osr_shoot_temporal.argtypes = [i, i, i, d, d, d, i, _dp, d, d, d, d, d, _dp, _ip, _dp, i, _dp, _dp]
+        lib.osr_shoot_temporal_batch.restype = i
+        lib.osr_shoot_temporal_batch.argtypes = [i, i, i, d, d, d, i, _dp, i64, _dp, _dp, _dp, _ip, _ip, _ip]
+        lib.osr_shoot_spatial_line.restype = i
+        lib.osr_shoot_spatial_line.argtypes = [i, i, d, d, d, i, _dp, d, d, d, d, d, d, i, _dp, _ip, _ip, _ip]
+
+    def solve_bl(self, variant=FLOW_CONTEBL, integrator=INT_CK45, nbl=1000, ymin=0.0, ymax=17.0, f2p=0.5, beta=0.0):
+        """Returns (prof[5, nbl+2] = ydat,U,Uspl,d2U,d2Uspl zero padded, npass, f2p_last)."""
+        prof = np.zeros((5, nbl + 2))
+        f2 = C.c_double()
+        n = self.lib.osr_solve_bl(variant, integrator, nbl, ymin, ymax, f2p, beta,
+                                  *[prof[k].ctypes.data_as(_dp) for k in range(5)], C.byref(f2))
+        return prof, n, f2.value
+
+    def shoot_temporal(self, flow, integrator, nstep, testalpha, ymin, ymax, prof, alpha, Re, c,
+                       hist_cap=50, eigfun=False):
+        out = np.zeros(6)
+        iout = np.zeros(3, dtype=np.int32)
+        hist = np.zeros(4 * hist_cap)
+        nbl = prof.shape[1] - 2 if prof is not None else 0
+        y = np.zeros((nstep + 1) * 8) if eigfun else None
+        vmax = np.zeros(2) if eigfun else None
+        alpha = complex(alpha)
+        c = complex(c)
+        self.lib.osr_shoot_temporal(
+            flow, integrator, nstep, testalpha, ymin, ymax, nbl,
+            prof.ctypes.data_as(_dp) if prof is not None else None, alpha.real, alpha.imag, Re, c.real, c.imag,
+            out.ctypes.data_as(_dp), iout.ctypes.data_as(_ip), hist.ctypes.data_as(_dp), hist_cap,
+            y.ctypes.data_as(_dp) if eigfun else None, vmax.ctypes.data_as(_dp) if eigfun else None)
+        r = dict(c=complex(out[0], out[1]), next=complex(out[2], out[3]), abserr=out[4], absdc=out[5],
+                 passes=int(iout[0]), qend=int(iout[1]), status=int(iout[2]),
+                 history=hist.reshape(hist_cap, 4)[: int(iout[0])])
+        if eigfun:
+            r["y"] = y.view(np.complex128).reshape(nstep + 1, 4)
+            r["vmax"] = complex(vmax[0], vmax[1])
+        return r
+
+    def shoot_temporal_batch(self, flow, integrator, nstep, testalpha, ymin, ymax, prof, alpha, Re, c):
+        Re = np.ascontiguousarray(Re, dtype=np.float64)
+        n = Re.size
+        al = np.ascontiguousarray(alpha, dtype=np.complex128).view(np.float64)
+        cc = np.ascontiguousarray(c, dtype=np.complex128).copy().view(np.float64)
+        passes = np.zeros(n, dtype=np.int32)
+        qend = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        nbl = prof.shape[1] - 2 if prof is not None else 0
+        self.lib.osr_shoot_temporal_batch(
+            flow, integrator, nstep, testalpha, ymin, ymax, nbl,
+            prof.ctypes.data_as(_dp) if prof is not None else None, n, al.ctypes.data_as(_dp),
+            Re.ctypes.data_as(_dp), cc.ctypes.data_as(_dp), passes.ctypes.data_as(_ip), qend.ctypes.data_as(_ip),
+            status.ctypes.data_as(_ip))
+        return dict(c=cc.view(np.complex128), passes=passes, qend=qend, status=status)
+
+    def shoot_spatial_line(self, integrator, nstep, testalpha, ymin, ymax, prof, Re, omega, domega, alpha, niter):
+        rows = np.zeros(4 * niter)
+        ipass = np.zeros(niter, dtype=np.int32)
+        iq = np.zeros(niter, dtype=np.int32)
+        ist = np.zeros(niter, dtype=np.int32)
+        omega = complex(omega)
+        alpha = complex(alpha)
+        self.lib.osr_shoot_spatial_line(
+            integrator, nstep, testalpha, ymin, ymax, prof.shape[1] - 2, prof.ctypes.data_as(_dp), Re,
+            omega.real, omega.imag, domega, alpha.real, alpha.imag, niter, rows.ctypes.data_as(_dp),
+            ipass.ctypes.data_as(_ip), iq.ctypes.data_as(_ip), ist.ctypes.data_as(_ip))
+        rows = rows.reshape(niter, 4)
+        return dict(omega=rows[:, 0] + 1j * rows[:, 1], alpha=rows[:, 2] + 1j * rows[:, 3],
+                    passes=ipass, qend=iq, status=ist)
+
+
+def load(rebuild=True):
+    if rebuild or not LIB.exists():
+        build()
+    return Oracle(C.CDLL(str(LIB)))

@@ -1,0 +1,260 @@
+"""GPU parity: the CUDA shooting path (through the C ABI) against the CPU oracle
+on the same inputs.  Tolerances (BASELINE.json north_star): eigenvalues 1e-10
+relative, eigenfunctions 1e-8 after normalisation, fp64.  Integer outputs
+(passes, qend) are compared exactly where the decision margins allow it and as
+a mismatch fraction on grids (a normalisation decision sitting within rounding
+of its threshold may legitimately move by one step under FMA contraction)."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+S2 = math.sqrt(2.0)
+EIG_RTOL = 1e-10
+EIGFUN_TOL = 1e-8
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)) / np.abs(np.asarray(b))
+
+
+@pytest.fixture(scope="module")
+def bl(engine, osb):
+    p = engine.solve_bl(osb.FLOW_CONTEBL, osb.INT_CK45, 1000, 0.0, 17.0, 0.5, 0.0)
+    yield p
+    p.free()
+
+
+@pytest.fixture(scope="module")
+def bl_oracle(oracle):
+    return oracle.solve_bl(ob.FLOW_CONTEBL, ob.INT_CK45, 1000, 0.0, 17.0, 0.5, 0.0)
+
+
+# ---------------------------------------------------------------- K1 profile
+@pytest.mark.parametrize("variant,integ,nbl,ymax", [
+    (ob.FLOW_CONTEBL, ob.INT_CK45, 1000, 17.0),
+    (ob.FLOW_CONTEBL, ob.INT_RK4, 1000, 17.0),
+    (ob.FLOW_ORRSOM, ob.INT_RK4, 400, 30.0),
+    (ob.FLOW_ORRSPACE, ob.INT_RK4, 1000, 20.0 * math.sqrt(2.0) / 1.7207876),
+])
+def test_profile_tables_bit_exact(engine, oracle, variant, integ, nbl, ymax):
+    """K1 uses non-contracting arithmetic in the reference's order: bit-exact."""
+    p = engine.solve_bl(variant, integ, nbl, 0.0, ymax, 0.5, 0.0)
+    t = p.tables()
+    p.free()
+    prof, npass, f2p = oracle.solve_bl(variant, integ, nbl, 0.0, ymax, 0.5, 0.0)
+    assert t["npass"] == npass
+    assert t["f2p"] == f2p
+    for k, name in enumerate(("ydat", "U", "Uspl", "d2U", "d2Uspl")):
+        assert np.array_equal(t[name], prof[k][: nbl + 1]), name
+
+
+def test_profile_batch_falkner_skan(engine, oracle, osb):
+    beta = np.array([0.0, 0.1, -0.05, 0.3, 0.0, 0.5, 1.0])
+    f2p = np.array([0.5, 0.6, 0.4, 0.8, 0.45, 0.9, 1.2])
+    out = engine.solve_bl_batch(f2p, beta, osb.FLOW_CONTEBL, osb.INT_CK45, 600, 0.0, 12.0)
+    for i in range(beta.size):
+        prof, npass, f2 = oracle.solve_bl(ob.FLOW_CONTEBL, ob.INT_CK45, 600, 0.0, 12.0, f2p[i], beta[i])
+        assert out["npass"][i] == npass and out["f2p"][i] == f2
+        assert np.array_equal(out["U"][i], prof[1][:601])
+        assert np.array_equal(out["Uspl"][i], prof[2][:601])
+        assert np.array_equal(out["d2Uspl"][i], prof[4][:601])
+
+
+# ---------------------------------------------------------------- K2 shooting
+def test_contebl_default_point(engine, osb, oracle, bl, bl_oracle):
+    """Config 1: README.md:24-26."""
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    r = engine.shoot_temporal(opts, bl, [0.179 * S2], [580.0 * S2], [complex(0.36413124, 0.79527387e-2)],
+                              want_resid=True, hist_cap=20)
+    ref = oracle.shoot_temporal(ob.FLOW_CONTEBL, ob.INT_CK45, 1000, 10.0, 0.0, 17.0, bl_oracle[0],
+                                0.179 * S2, 580.0 * S2, complex(0.36413124, 0.79527387e-2))
+    assert r["status"][0] == 0
+    assert rel(r["c"][0], ref["c"]) < EIG_RTOL
+    assert abs(r["c"][0] - complex(0.36412287, 0.0079597206)) < 1e-8
+    assert r["passes"][0] == ref["passes"] == 5
+    assert r["qend"][0] == ref["qend"] == 21
+    # the stdout pass table (shoot.f:745-747): ctemp to 1e-10, err to ~1e-9 absolute
+    h = r["history"][0][:5]
+    assert np.max(np.abs(h[:, :2] - ref["history"][:, :2])) < 1e-11
+    assert np.max(np.abs(h[:3, 2:] - ref["history"][:3, 2:])) < 1e-9
+    assert r["resid"][0, 0] < 1e-14 and r["resid"][0, 1] < 1e-14
+
+
+def test_contebl_rk4_point(engine, osb, oracle):
+    p = engine.solve_bl(osb.FLOW_CONTEBL, osb.INT_RK4, 1000, 0.0, 17.0, 0.5, 0.0)
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    opts.integrator = osb.INT_RK4
+    r = engine.shoot_temporal(opts, p, [0.179 * S2], [580.0 * S2], [complex(0.36413124, 0.79527387e-2)])
+    p.free()
+    assert rel(r["c"][0], complex(0.36412271287, 0.0079597135036)) < 1e-10
+    assert (r["passes"][0], r["qend"][0], r["status"][0]) == (5, 21, 0)
+
+
+def test_conte_channel_point(engine, osb, oracle):
+    """Config 2: conte defaults (conte.f:61-68)."""
+    prof = engine.channel_profile()
+    for integ, expect in ((osb.INT_CK45, complex(0.23752648882047672, 0.00373967062299434)),
+                          (osb.INT_RK4, complex(0.23752648711564373, 0.0037396708967126395))):
+        opts = osb.shoot_defaults(osb.FLOW_CONTE)
+        opts.integrator = integ
+        r = engine.shoot_temporal(opts, prof, [1.0], [10000.0], [complex(0.23753, 0.00374)], hist_cap=20)
+        ref = oracle.shoot_temporal(ob.FLOW_CONTE, integ, 2000, 10.0, -1.0, 1.0, None, 1.0, 10000.0,
+                                    complex(0.23753, 0.00374))
+        assert rel(r["c"][0], ref["c"]) < EIG_RTOL
+        assert rel(r["c"][0], expect) < EIG_RTOL
+        assert r["qend"][0] == ref["qend"] == 115
+        assert r["status"][0] == 0
+        assert abs(r["passes"][0] - ref["passes"]) <= 1  # errtol 1e-15 sits at the rounding floor
+    prof.free()
+
+
+def test_contebl_grid_vs_oracle(engine, osb, oracle, bl, bl_oracle):
+    """24 x 24 patch of the config-5 grid around the anchor, seeded by continuation."""
+    na = nr = 24
+    alpha = 0.179 + 0.0008 * (np.arange(na) - na // 2)
+    Re = 580.0 * 1.004 ** (np.arange(nr) - nr // 2)
+    A, R = np.meshgrid(alpha, Re)
+    A, R = A.ravel() * S2, R.ravel() * S2
+    # seeds: oracle solution at the anchor, everything else starts from it (|dc| ~ 1e-3)
+    guess = np.full(A.size, complex(0.36412287, 0.0079597206))
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    r = engine.shoot_temporal(opts, bl, A, R, guess)
+    ref = oracle.shoot_temporal_batch(ob.FLOW_CONTEBL, ob.INT_CK45, 1000, 10.0, 0.0, 17.0, bl_oracle[0], A, R, guess)
+    ok = (ref["status"] == 0)
+    assert ok.mean() > 0.95
+    assert np.array_equal(r["status"][ok], ref["status"][ok])
+    err = rel(r["c"][ok], ref["c"][ok])
+    assert err.max() < EIG_RTOL, err.max()
+    # integer outputs: identical except where a decision sits on its threshold
+    assert (r["qend"][ok] != ref["qend"][ok]).mean() < 0.02
+    assert (np.abs(r["passes"][ok] - ref["passes"][ok]) > 1).mean() < 0.01
+    assert (r["passes"][ok] != ref["passes"][ok]).mean() < 0.15
+
+
+def test_complex_alpha_and_ragged_batches(engine, osb, oracle, bl, bl_oracle):
+    """alpha with an imaginary part (contebl accepts alphai, contebl.f:73-74,175) and
+    batch sizes that are not a multiple of the CTA size, including empty."""
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    empty = engine.shoot_temporal(opts, bl, np.zeros(0, complex), np.zeros(0), np.zeros(0, complex))
+    assert empty["c"].size == 0
+    for n in (1, 31, 33, 130):
+        al = (0.179 + 0.0003 * np.arange(n) + 1j * 0.0005 * (np.arange(n) % 3)) * S2
+        Re = np.full(n, 580.0 * S2)
+        guess = np.full(n, complex(0.36412287, 0.0079597206))
+        r = engine.shoot_temporal(opts, bl, al, Re, guess)
+        ref = oracle.shoot_temporal_batch(ob.FLOW_CONTEBL, ob.INT_CK45, 1000, 10.0, 0.0, 17.0, bl_oracle[0], al, Re, guess)
+        ok = ref["status"] == 0
+        assert ok.all()
+        assert rel(r["c"], ref["c"]).max() < EIG_RTOL
+
+
+def test_maxcount_and_nonfinite_are_reported(engine, osb, bl):
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    # far outside the basin of the iteration: must not claim convergence
+    r = engine.shoot_temporal(opts, bl, [0.179 * S2, 0.179 * S2], [580.0 * S2, 580.0 * S2],
+                              [complex(0.9, 0.3), complex(0.36413124, 0.0079527387)])
+    assert r["status"][1] == osb.ST_CONVERGED
+    assert r["status"][0] in (osb.ST_MAXCOUNT, osb.ST_NONFINITE) or abs(r["c"][0] - r["c"][1]) > 1e-3
+    # underflow domain: first Gram-Schmidt divides by zero (contebl.f:80) -> flagged, not silent
+    r = engine.shoot_temporal(opts, bl, [0.4 * S2], [3000.0 * S2], [complex(0.3, 0.0)])
+    assert r["status"][0] in (osb.ST_NONFINITE, osb.ST_MAXCOUNT)
+
+
+def test_orrsom_decks(engine, osb, oracle):
+    for nbl, nstep, ymax, al, Re, guess, expect, pq in (
+            (400, 4000, 30.0, 0.179, 580.0, complex(0.36413124, 0.0079527387),
+             complex(0.3640704766590239, 0.008003326110564948), (5, 39)),
+            (1000, 1000, 17.0, 0.1453, 581.1, complex(0.35, 0.01),
+             complex(0.3497873683492642, 0.01208610121615455), (7, 18))):
+        p = engine.solve_bl(osb.FLOW_ORRSOM, osb.INT_RK4, nbl, 0.0, ymax, 0.5, 0.0)
+        opts = osb.shoot_defaults(osb.FLOW_ORRSOM)
+        opts.nstep, opts.ymax = nstep, ymax
+        r = engine.shoot_temporal(opts, p, [al * S2], [Re * S2], [guess])
+        p.free()
+        assert rel(r["c"][0], expect) < EIG_RTOL
+        assert (r["passes"][0], r["qend"][0]) == pq
+        assert r["status"][0] == 0
+
+
+def test_orrspace_sweep_line(engine, osb, oracle):
+    """Config 3: sweep.inp, 50 omega steps with continuation inside the kernel.
+    Points whose Muller iteration wanders (17-32 passes) amplify rounding:
+    1e-10 is asserted where the oracle needed <= 10 passes, 5e-9 elsewhere."""
+    fact = math.sqrt(2.0) / 1.7207876
+    ymin, ymax = 0.0, 20.0 * fact
+    p = engine.solve_bl(osb.FLOW_ORRSPACE, osb.INT_RK4, 1000, ymin, ymax, 0.5, 0.0)
+    opts = osb.shoot_defaults(osb.FLOW_ORRSPACE)
+    opts.nstep, opts.ymin, opts.ymax, opts.testalpha = 1000, ymin, ymax, 0.9
+    nl = 3
+    Re = np.array([1000.0, 1000.0, 990.0]) * fact
+    om = np.full(nl, complex(0.042, 0.0)) * fact
+    dom = np.full(nl, 0.002) * fact
+    a0 = np.full(nl, complex(0.13809592, 0.0051958399)) * fact
+    r = engine.shoot_spatial_lines(opts, p, Re, om, dom, a0, 50)
+    p.free()
+    prof, _, _ = oracle.solve_bl(ob.FLOW_ORRSPACE, ob.INT_RK4, 1000, ymin, ymax, 0.5, 0.0)
+    for line in (0, 2):
+        ref = oracle.shoot_spatial_line(ob.INT_RK4, 1000, 0.9, ymin, ymax, prof, Re[line], om[line], dom[line], a0[line], 50)
+        assert np.all(r["status"][line] == 0)
+        e = rel(r["alpha"][line], ref["alpha"])
+        easy = ref["passes"] <= 10
+        assert e[easy].max() < EIG_RTOL, e[easy].max()
+        assert e.max() < 5e-9, e.max()
+    assert np.array_equal(r["alpha"][0], r["alpha"][1])  # identical lines -> identical bits
+
+
+# ---------------------------------------------------------------- K2b eigenfunction
+def test_eigenfunction_contebl(engine, osb, oracle, bl, bl_oracle):
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    r = engine.shoot_temporal(opts, bl, [0.179 * S2], [580.0 * S2], [complex(0.36413124, 0.79527387e-2)])
+    e = engine.eigfun(opts, bl, [580.0 * S2], r["c"], alpha=[0.179 * S2])
+    ref = oracle.shoot_temporal(ob.FLOW_CONTEBL, ob.INT_CK45, 1000, 10.0, 0.0, 17.0, bl_oracle[0],
+                                0.179 * S2, 580.0 * S2, complex(0.36413124, 0.79527387e-2), eigfun=True)
+    y = e["y"][0] / e["vmax"][0]
+    yr = ref["y"] / ref["vmax"]
+    assert e["qend"][0] == ref["qend"]
+    for i in range(4):
+        scale = np.max(np.abs(yr[:, i]))
+        assert np.max(np.abs(y[:, i] - yr[:, i])) / scale < EIGFUN_TOL
+
+
+def test_eigenfunction_conte(engine, osb, oracle):
+    prof = engine.channel_profile()
+    opts = osb.shoot_defaults(osb.FLOW_CONTE)
+    r = engine.shoot_temporal(opts, prof, [1.0], [10000.0], [complex(0.23753, 0.00374)])
+    e = engine.eigfun(opts, prof, [10000.0], r["c"], alpha=[1.0])
+    prof.free()
+    ref = oracle.shoot_temporal(ob.FLOW_CONTE, ob.INT_CK45, 2000, 10.0, -1.0, 1.0, None, 1.0, 10000.0,
+                                complex(0.23753, 0.00374), eigfun=True)
+    y = e["y"][0] / e["vmax"][0]
+    yr = ref["y"] / ref["vmax"]
+    for i in range(4):
+        scale = np.max(np.abs(yr[:, i]))
+        assert np.max(np.abs(y[:, i] - yr[:, i])) / scale < EIGFUN_TOL
+
+
+# ---------------------------------------------------------------- full-size property
+def test_full_size_properties(engine, osb, bl):
+    """At bench sizes the oracle is too slow; use size-independent properties:
+    (i) results do not depend on batch composition/order (points are independent),
+    (ii) a converged c fed back as the guess stays put (idempotence) to 1e-12."""
+    n = 200_000
+    rng = np.random.default_rng(7)
+    al = (0.179 + 0.004 * (rng.random(n) - 0.5)) * S2
+    Re = 580.0 * (1 + 0.02 * (rng.random(n) - 0.5)) * S2
+    guess = np.full(n, complex(0.36412287, 0.0079597206))
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    r = engine.shoot_temporal(opts, bl, al, Re, guess)
+    assert (r["status"] == 0).mean() > 0.999
+    perm = rng.permutation(n)
+    r2 = engine.shoot_temporal(opts, bl, al[perm], Re[perm], guess[perm])
+    assert np.array_equal(r2["c"], r["c"][perm])
+    assert np.array_equal(r2["passes"], r["passes"][perm])
+    sub = slice(0, 20_000)
+    r3 = engine.shoot_temporal(opts, bl, al[sub], Re[sub], r["c"][sub])
+    ok = (r["status"][sub] == 0) & (r3["status"] == 0)
+    assert rel(r3["c"][ok], r["c"][sub][ok]).max() < 1e-11
