@@ -152,8 +152,10 @@ def cpu_run(npts_sample, cores, world=1):
 
     ob.build()
     idx, nre = workload_indices(world, 0)
-    stride = max(1, idx.size // npts_sample)
-    sub = idx[::stride][:npts_sample]
+    # evenly spread over the flattened batch; the positions are deliberately not a
+    # multiple of the row length so that both alpha and Re are sampled
+    pos = np.unique(np.floor(np.arange(npts_sample) * ((idx.size - 1) / max(npts_sample - 1, 1))).astype(np.int64))
+    sub = idx[pos]
     alpha, Re, c = build_inputs(sub, nre)
     parts = [(alpha[k::cores], Re[k::cores], c[k::cores]) for k in range(cores)]
     with ProcessPoolExecutor(cores) as ex:
@@ -180,7 +182,7 @@ def run_reference(args, rank, world):
         if s >= args.warmup:
             vals.append(v); ms.append(dt * 1e3)
     value = float(np.mean(vals)) if vals else 0.0
-    sample_txt = f"{n} points strided evenly over rank 0's 4096x4096 batch of config 5, same seeds; {conv} converged, {passes / max(n, 1):.2f} passes/point"
+    sample_txt = f"{n} points spread evenly over rank 0's 4096x4096 batch of config 5, same seeds; {conv} converged, {passes / max(n, 1):.2f} passes/point"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(ms)) if ms else None,
@@ -353,7 +355,7 @@ def main():
         cores = os.cpu_count() or 1
         v, conv, cpasses, dt, ns = cpu_run(256 * cores, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{ns} points strided evenly over the same 4096x4096 batch, same seeds, one process per core; "
+               "sample": f"{ns} points spread evenly over the same 4096x4096 batch, same seeds, one process per core; "
                          f"{conv} converged, {cpasses / max(ns, 1):.2f} passes/point, {dt:.1f} s wall",
                "per_core": v / cores}
 
@@ -392,6 +394,12 @@ def main():
         }
         print(json.dumps(line), flush=True)
     barrier()
+    # torch frees pinned/device buffers by recording events on the library's stream:
+    # release them before the stream goes away with the context
+    del h_alpha, h_Re, h_guess, h_c, h_int, d_alpha, d_Re, d_guess, d_c, d_int, gather_c, gather_i
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
     prof.free()
     eng.close()
     if world > 1:

@@ -132,7 +132,7 @@ def _f64(a, n=None):
 def _cplx_pairs(a, n):
     """complex or (n,2) float array -> contiguous float64 view of 2n doubles."""
     a = np.asarray(a)
-    if np.iscomplexobj(a):
+    if np.iscomplexobj(a) or a.size == n:  # complex, or real values (imaginary part 0)
         a = np.ascontiguousarray(a, dtype=np.complex128).view(np.float64)
     return _f64(a.reshape(-1), 2 * n)
 

@@ -592,19 +592,20 @@ int osb_eigfun(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof
   OSB_CUDA(ctx, cudaMallocAsync(&d_y, npts * n1 * 4 * sizeof(double2), st));
   OSB_CUDA(ctx, cudaMallocAsync(&d_vmax, npts * sizeof(double2), st));
   OSB_CUDA(ctx, cudaMallocAsync(&d_q, npts * sizeof(int32_t), st));
-  OSB_CUDA(ctx, cudaMemcpyAsync(d_in, Re, npts * sizeof(double), cudaMemcpyHostToDevice, st));
-  OSB_CUDA(ctx, cudaMemcpyAsync(d_in + npts, eig, npts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-  OSB_CUDA(ctx, cudaMemcpyAsync(d_in + 3 * npts, a.spatial ? omega : alpha, npts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  // layout: eig(2n), alpha|omega(2n), Re(n)  -- the double2 arrays first (16-byte alignment)
+  OSB_CUDA(ctx, cudaMemcpyAsync(d_in, eig, npts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * npts, a.spatial ? omega : alpha, npts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(ctx, cudaMemcpyAsync(d_in + 4 * npts, Re, npts * sizeof(double), cudaMemcpyHostToDevice, st));
   rc = make_stage_table(ctx, 0, opts, prof, &tab);
   if (rc) return rc;
   EigfunArgs e;
   memset(&e, 0, sizeof(e));
   a.tab = tab;
-  a.Re = d_in;
-  a.alpha = (const double2 *)(d_in + 3 * npts);
+  a.Re = d_in + 4 * npts;
+  a.alpha = (const double2 *)(d_in + 2 * npts);
   e.s = a;
-  e.eig = (const double2 *)(d_in + npts);
-  e.omega = (const double2 *)(d_in + 3 * npts);
+  e.eig = (const double2 *)d_in;
+  e.omega = (const double2 *)(d_in + 2 * npts);
   e.U = d_U; e.P = d_P; e.tq = d_tq; e.y = d_y; e.vmax = d_vmax; e.qend = d_q;
   e.t0 = opts->ymin;
   e.habs = fabs(a.hs);

@@ -16,10 +16,10 @@
 //    contraction -- into a [nstep][stages] table.  K2 then reads one warp-uniform
 //    row (96 B for Cash-Karp) per step instead of bisecting + evaluating a cubic
 //    12 times per step per point as the reference does.
-//  * RHS row 4 is regrouped as A(t)*y1 + B(t)*y3 with
-//      B = 2a^2 + ik(U-c),  A = -a^2 (a^2 + ik(U-c)) - ik U'',  k = alpha*Re
-//    (contebl.f:335-337); A, B are computed once per stage and shared by both
-//    solution vectors.
+//  * RHS row 4 (contebl.f:335-337) is evaluated as G d + a^2 y3 - (ik U'') y1 with
+//    d = y3 - a^2 y1 and G = a^2 + ik(U - c), k = alpha*Re; G and ik U'' are computed
+//    once per stage and shared by both solution vectors (see rhs4 for why d must be
+//    kept as its own rounded quantity).
 //  * The step size is folded into the tableau on the host (bh = b*h, ch = c*h).
 //  * The orthonormality test acos(cc/sqrt(aa*bb)) < ta (shoot.f:593-606) is
 //    evaluated as cc^2 > cos^2(ta)*aa*bb (acos is monotone): no sqrt/div/acos on
@@ -150,36 +150,65 @@ struct PassConst {
 };
 
 struct StageCoef {
-  double Ar, Ai, Br, Bi;
+  double Gr, Gi;  // G = a^2 + ik(U - c)
+  double Kr, Ki;  // ik U''
 };
 
+// REAL_ALPHA: alpha is real, so a^2 is real and ik = i*alpha*Re is purely imaginary
+// (Gr is then constant over the pass and Kr = 0).  The general path with those zeros
+// produces the same bits, so mixing real and complex alpha in one batch is safe.
+template <bool REAL_ALPHA>
 __device__ __forceinline__ StageCoef stage_coef(const PassConst &pc, double2 uu) {
-  // G = a^2 + ik(U - c);  B = G + a^2;  A = -a^2 G - ik U''
-  double Gr = fma(pc.kr, uu.x, pc.g0r);
-  double Gi = fma(pc.ki, uu.x, pc.g0i);
   StageCoef s;
-  s.Br = Gr + pc.a2r;
-  s.Bi = Gi + pc.a2i;
-  s.Ar = fma(-pc.a2r, Gr, fma(pc.a2i, Gi, -pc.kr * uu.y));
-  s.Ai = fma(-pc.a2r, Gi, fma(-pc.a2i, Gr, -pc.ki * uu.y));
+  s.Gi = fma(pc.ki, uu.x, pc.g0i);
+  s.Ki = pc.ki * uu.y;
+  if (REAL_ALPHA) {
+    s.Gr = pc.g0r;
+    s.Kr = 0.0;
+  } else {
+    s.Gr = fma(pc.kr, uu.x, pc.g0r);
+    s.Kr = pc.kr * uu.y;
+  }
   return s;
 }
 
-// r = A*y1 + B*y3   (y laid out re,im interleaved: y1 = y[0..1], y3 = y[4..5])
-__device__ __forceinline__ void rhs4(const StageCoef &s, const double *y, double &rr, double &ri) {
-  rr = fma(s.Ar, y[0], fma(-s.Ai, y[1], fma(s.Br, y[4], -s.Bi * y[5])));
-  ri = fma(s.Ar, y[1], fma(s.Ai, y[0], fma(s.Br, y[5], s.Bi * y[4])));
+// Row 4 of OSHOMO (contebl.f:335-337), regrouped but keeping the reference's
+// d = y3 - a^2 y1 as a separately rounded quantity:
+//     r = G d + a^2 y3 - (ik U'') y1,      G = a^2 + ik (U - c)
+// (== 2a^2 y3 - a^4 y1 + ik[(U-c) d - U'' y1]).  This is not cosmetic.  In the
+// free stream d cancels to a rounding residue, and that residue is what seeds the
+// viscous content of the first solution vector -- which, after the Gram-Schmidt
+// steps, fixes the PHASE of the wall residual err(c).  With d formed first, the
+// eigenvalue guess multiplies a residue that does not itself depend on c, so
+// err(c) stays smooth and the secant/Muller update converges as in the reference.
+// Grouping the row as A(c) y1 + B(c) y3 makes the residue c-dependent noise and the
+// iteration stalls at |err| ~ 1e-5 (measured; see DESIGN.md "err(c) is rounding-phased").
+template <bool REAL_ALPHA>
+__device__ __forceinline__ void rhs4(const StageCoef &s, const PassConst &pc, const double *y,
+                                     double &rr, double &ri) {
+  if (REAL_ALPHA) {
+    const double dr = fma(-pc.a2r, y[0], y[4]);
+    const double di = fma(-pc.a2r, y[1], y[5]);
+    rr = fma(s.Gr, dr, fma(-s.Gi, di, fma(pc.a2r, y[4], s.Ki * y[1])));
+    ri = fma(s.Gr, di, fma(s.Gi, dr, fma(pc.a2r, y[5], -s.Ki * y[0])));
+  } else {
+    const double dr = fma(-pc.a2r, y[0], fma(pc.a2i, y[1], y[4]));
+    const double di = fma(-pc.a2r, y[1], fma(-pc.a2i, y[0], y[5]));
+    rr = fma(s.Gr, dr, fma(-s.Gi, di, fma(pc.a2r, y[4], fma(-pc.a2i, y[5], fma(-s.Kr, y[0], s.Ki * y[1])))));
+    ri = fma(s.Gr, di, fma(s.Gi, dr, fma(pc.a2r, y[5], fma(pc.a2i, y[4], fma(-s.Kr, y[1], -s.Ki * y[0])))));
+  }
 }
 
 // One fixed Cash-Karp step (CRKCK45, shoot.f:1367-1439) of BOTH solution vectors.
 // u[v][0..7] = (y1, y2, y3, y4) of vector v.  f[k] holds the stage derivative
 // (y2, y3, y4, r) WITHOUT the step size; bh/ch carry it.
+template <bool REAL_ALPHA>
 __device__ __forceinline__ void step_ck45(double (&u)[2][8], const double2 *__restrict__ trow,
                                           const PassConst &pc, const ShootArgs &a) {
   double f[2][6][8];
 #pragma unroll
   for (int m = 0; m < 6; ++m) {
-    const StageCoef sc = stage_coef(pc, __ldg(&trow[m]));
+    const StageCoef sc = stage_coef<REAL_ALPHA>(pc, __ldg(&trow[m]));
 #pragma unroll
     for (int v = 0; v < 2; ++v) {
       double yt[8];
@@ -192,7 +221,7 @@ __device__ __forceinline__ void step_ck45(double (&u)[2][8], const double2 *__re
       }
 #pragma unroll
       for (int n = 0; n < 6; ++n) f[v][m][n] = yt[n + 2];
-      rhs4(sc, yt, f[v][m][6], f[v][m][7]);
+      rhs4<REAL_ALPHA>(sc, pc, yt, f[v][m][6], f[v][m][7]);
     }
   }
 #pragma unroll
@@ -211,25 +240,26 @@ __device__ __forceinline__ void step_ck45(double (&u)[2][8], const double2 *__re
 
 // One classical RK4 step (CRK4, shoot.f:869-903) of both vectors.  Table row:
 // (to, to+h/2, to+h).
+template <bool REAL_ALPHA>
 __device__ __forceinline__ void step_rk4(double (&u)[2][8], const double2 *__restrict__ trow,
                                          const PassConst &pc, const ShootArgs &a) {
   const double hs = a.hs, h2 = 0.5 * a.hs, h6 = a.hs / 6.0, h3 = a.hs / 3.0;
-  const StageCoef s0 = stage_coef(pc, __ldg(&trow[0]));
-  const StageCoef s1 = stage_coef(pc, __ldg(&trow[1]));
-  const StageCoef s2 = stage_coef(pc, __ldg(&trow[2]));
+  const StageCoef s0 = stage_coef<REAL_ALPHA>(pc, __ldg(&trow[0]));
+  const StageCoef s1 = stage_coef<REAL_ALPHA>(pc, __ldg(&trow[1]));
+  const StageCoef s2 = stage_coef<REAL_ALPHA>(pc, __ldg(&trow[2]));
 #pragma unroll
   for (int v = 0; v < 2; ++v) {
     double f[8], q[8], acc[8];
     // k1
 #pragma unroll
     for (int n = 0; n < 6; ++n) f[n] = u[v][n + 2];
-    rhs4(s0, u[v], f[6], f[7]);
+    rhs4<REAL_ALPHA>(s0, pc, u[v], f[6], f[7]);
 #pragma unroll
     for (int n = 0; n < 8; ++n) { acc[n] = fma(h6, f[n], u[v][n]); q[n] = fma(h2, f[n], u[v][n]); }
     // k2
 #pragma unroll
     for (int n = 0; n < 6; ++n) f[n] = q[n + 2];
-    rhs4(s1, q, f[6], f[7]);
+    rhs4<REAL_ALPHA>(s1, pc, q, f[6], f[7]);
 #pragma unroll
     for (int n = 0; n < 8; ++n) acc[n] = fma(h3, f[n], acc[n]);
     {
@@ -239,14 +269,14 @@ __device__ __forceinline__ void step_rk4(double (&u)[2][8], const double2 *__res
       // k3
 #pragma unroll
       for (int n = 0; n < 6; ++n) f[n] = q2[n + 2];
-      rhs4(s1, q2, f[6], f[7]);
+      rhs4<REAL_ALPHA>(s1, pc, q2, f[6], f[7]);
     }
 #pragma unroll
     for (int n = 0; n < 8; ++n) { acc[n] = fma(h3, f[n], acc[n]); q[n] = fma(hs, f[n], u[v][n]); }
     // k4
 #pragma unroll
     for (int n = 0; n < 6; ++n) f[n] = q[n + 2];
-    rhs4(s2, q, f[6], f[7]);
+    rhs4<REAL_ALPHA>(s2, pc, q, f[6], f[7]);
 #pragma unroll
     for (int n = 0; n < 8; ++n) u[v][n] = fma(h6, f[n], acc[n]);
   }
@@ -376,7 +406,7 @@ __device__ __forceinline__ void initial_vectors(double (&u)[2][8], const ShootAr
 
 // One integration across the layer at the current eigenvalue guess; returns the
 // wall residual err (shoot.f:699-700,716) and the normalisation count qend.
-template <int INTEG, bool ANALYTIC>
+template <int INTEG, bool ANALYTIC, bool REAL_ALPHA>
 __device__ __forceinline__ void integrate_pass(const ShootArgs &a, zd alpha, double Re, zd cw,
                                                zd &err, int &qend) {
   constexpr int NS = (INTEG == OSB_INT_CK45) ? 6 : 3;
@@ -390,8 +420,8 @@ __device__ __forceinline__ void integrate_pass(const ShootArgs &a, zd alpha, dou
   for (int k = a.bl_ic ? 0 : 1; k <= a.nstep; ++k) {
     bool norm;
     if (k > 0) {
-      if (INTEG == OSB_INT_CK45) step_ck45(u, trow, pc, a);
-      else step_rk4(u, trow, pc, a);
+      if (INTEG == OSB_INT_CK45) step_ck45<REAL_ALPHA>(u, trow, pc, a);
+      else step_rk4<REAL_ALPHA>(u, trow, pc, a);
       trow += NS;
       norm = need_norm<ANALYTIC>(u, a.thr, a.strict) || (k == a.nstep);
       q += norm ? 1 : 0;
@@ -458,8 +488,11 @@ __device__ __forceinline__ bool keep_going(const ShootArgs &a, const IterState &
 
 template <int INTEG, bool ANALYTIC>
 __global__ void __launch_bounds__(128) shoot_kernel(const __grid_constant__ ShootArgs a) {
-  const int64_t line = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (line >= a.nlines) return;
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // lanes past the end shadow the last line (same work, no stores) so that every
+  // warp is full for the warp-wide vote below
+  const bool active = gid < a.nlines;
+  const int64_t line = active ? gid : a.nlines - 1;
   const double Re = a.Re[line];
   zd alpha, omega = zd{0.0, 0.0};
   IterState s;
@@ -475,6 +508,8 @@ __global__ void __launch_bounds__(128) shoot_kernel(const __grid_constant__ Shoo
       s.ev = zd{c0.x, c0.y};
     }
   }
+  // temporal sweeps normally have real alpha: take the cheaper RHS when the whole warp does
+  const bool real_alpha = !a.spatial && __all_sync(0xffffffffu, alpha.y == 0.0);
   for (int it = 0; it < a.niter; ++it) {
     const int64_t out = line * a.niter + it;
     s.icount = 1;
@@ -493,22 +528,25 @@ __global__ void __launch_bounds__(128) shoot_kernel(const __grid_constant__ Shoo
         // spatial: the unknown is alpha and c = omega/alpha (orrspace.f:290,645)
         const zd al = a.spatial ? s.ev : alpha;
         const zd cw = a.spatial ? zdiv(omega, s.ev) : s.ev;
-        integrate_pass<INTEG, ANALYTIC>(a, al, Re, cw, err, qend);
+        if (real_alpha) integrate_pass<INTEG, ANALYTIC, true>(a, al, Re, cw, err, qend);
+        else integrate_pass<INTEG, ANALYTIC, false>(a, al, Re, cw, err, qend);
       }
       update_eigenvalue(s, err, ctemp, a.first_perturb);
-      if (a.history && s.icount <= a.hist_cap) {
+      if (active && a.history && s.icount <= a.hist_cap) {
         zd shown = a.show_updated ? s.ev : ctemp;
         a.history[out * a.hist_cap + (s.icount - 1)] = make_double4(shown.x, shown.y, err.x, err.y);
       }
       s.icount += 1;
       if (!(zfinite(s.ev) && zfinite(err))) { status = OSB_ST_NONFINITE; break; }
     }
-    a.ev[out] = make_double2(ctemp.x, ctemp.y);
-    a.passes[out] = s.icount - 1;
-    a.qend[out] = qend;
-    a.status[out] = status;
-    if (a.resid)
-      a.resid[out] = make_double2(zabs(err), s.cm1_defined ? zabs(zsub(s.ev, s.cm1)) : 0.0);
+    if (active) {
+      a.ev[out] = make_double2(ctemp.x, ctemp.y);
+      a.passes[out] = s.icount - 1;
+      a.qend[out] = qend;
+      a.status[out] = status;
+      if (a.resid)
+        a.resid[out] = make_double2(zabs(err), s.cm1_defined ? zabs(zsub(s.ev, s.cm1)) : 0.0);
+    }
     if (a.spatial) {
       s.ev = ctemp;  // orrspace.f:494: alpha = ctemp seeds the next omega
       omega.x += a.domega[line];  // orrspace.f:192-194
@@ -559,8 +597,8 @@ __global__ void __launch_bounds__(64) eigfun_kernel(const __grid_constant__ Eigf
     bool norm;
     double t = bl ? __dsub_rn(a.tf, __dmul_rn(e.habs, (double)k)) : __dadd_rn(e.t0, __dmul_rn(e.habs, (double)k));
     if (k > 0) {
-      if (INTEG == OSB_INT_CK45) step_ck45(u, trow, pc, a);
-      else step_rk4(u, trow, pc, a);
+      if (INTEG == OSB_INT_CK45) step_ck45<false>(u, trow, pc, a);  // same bits as the real-alpha path
+      else step_rk4<false>(u, trow, pc, a);
       trow += NS;
       norm = need_norm<ANALYTIC>(u, a.thr, a.strict) || (k == nstep);
     } else {
