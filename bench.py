@@ -47,13 +47,15 @@ TILE = 4096
 # ----------------------------------------------------------------- workload
 def workload_indices(world, rank, points=None):
     """Flattened (i_Re, j_alpha) indices owned by `rank` (cyclic tiles)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("osb_sweep", ROOT / "os-stab_b200" / "sweep.py")
+    sweep = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sweep)  # pure host logic; does not need the CUDA library
     nre = NRE_PER_RANK * world
-    total = NA * nre
-    ntile = total // TILE
-    tiles = np.arange(rank, ntile, world, dtype=np.int64)
+    idx = sweep.shard_indices(NA * nre, world, rank, TILE)
     if points is not None:
-        tiles = tiles[: max(1, points // TILE)]
-    idx = (tiles[:, None] * TILE + np.arange(TILE, dtype=np.int64)[None, :]).reshape(-1)
+        idx = idx[: max(TILE, (points // TILE) * TILE)]
     return idx, nre
 
 
