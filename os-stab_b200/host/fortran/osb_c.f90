@@ -1,0 +1,116 @@
+!> osb_c -- ISO_C_BINDING interfaces to libosb.so (include/osb.h).
+!!
+!! SOURCE ONLY: no Fortran compiler exists in the build image (SURVEY H2), so this
+!! module is syntax-reviewed, not compiled; the C++ twin drivers in ../ exercise
+!! the same C entry points with the same argument order.
+!!
+!! The reference is compiled with -fdefault-integer-8 -fdefault-real-8
+!! (gcc.mak:78-79): every integer crossing the boundary is therefore declared with
+!! an explicit C kind, and default `real`/`complex` (promoted to 8/16 bytes) are
+!! passed as real(c_double)/complex(c_double_complex).
+module osb_c
+  use iso_c_binding
+  implicit none
+
+  integer(c_int), parameter :: OSB_FLOW_CONTEBL = 0, OSB_FLOW_CONTE = 1, &
+                               OSB_FLOW_ORRSOM = 2, OSB_FLOW_ORRSPACE = 3
+  integer(c_int), parameter :: OSB_INT_RK4 = 0, OSB_INT_CK45 = 1
+
+  type, bind(C) :: osb_shoot_opts
+    integer(c_int32_t) :: flow, integrator, nstep, maxcount
+    real(c_double)     :: testalpha, ymin, ymax, errtol, eigtol
+  end type osb_shoot_opts
+
+  interface
+    integer(c_int) function osb_create(ctx, device) bind(C, name="osb_create")
+      import :: c_int, c_ptr
+      type(c_ptr), intent(out) :: ctx
+      integer(c_int), value :: device
+    end function
+    integer(c_int) function osb_create_multi(ctx, ndev, devices) bind(C, name="osb_create_multi")
+      import :: c_int, c_ptr
+      type(c_ptr), intent(out) :: ctx
+      integer(c_int), value :: ndev
+      type(c_ptr), value :: devices          ! c_null_ptr: devices 0..ndev-1 (ndev=0: all)
+    end function
+    integer(c_int) function osb_destroy(ctx) bind(C, name="osb_destroy")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+    end function
+    integer(c_int) function osb_shoot_defaults(flow, opts) bind(C, name="osb_shoot_defaults")
+      import :: c_int, osb_shoot_opts
+      integer(c_int), value :: flow
+      type(osb_shoot_opts), intent(out) :: opts
+    end function
+    !> replaces `call SOLVE_BL` (contebl.f:196, orrsom.f:139, orrspace.f:177)
+    integer(c_int) function osb_profile_blasius(ctx, variant, integrator, nbl, ymin, ymax, &
+                                                f2p, beta, prof) bind(C, name="osb_profile_blasius")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: variant, integrator, nbl
+      real(c_double), value :: ymin, ymax, f2p, beta
+      type(c_ptr), intent(out) :: prof
+    end function
+    integer(c_int) function osb_profile_channel(ctx, prof) bind(C, name="osb_profile_channel")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      type(c_ptr), intent(out) :: prof
+    end function
+    !> copies the tables back so the host can write fort.10 exactly as before
+    integer(c_int) function osb_profile_get(ctx, prof, ydat, U, Uspl, d2U, d2Uspl, npass, f2p_last) &
+        bind(C, name="osb_profile_get")
+      import :: c_int, c_int32_t, c_ptr, c_double
+      type(c_ptr), value :: ctx, prof
+      real(c_double), intent(out) :: ydat(*), U(*), Uspl(*), d2U(*), d2Uspl(*)
+      integer(c_int32_t), intent(out) :: npass
+      real(c_double), intent(out) :: f2p_last
+    end function
+    integer(c_int) function osb_profile_free(ctx, prof) bind(C, name="osb_profile_free")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx, prof
+    end function
+    !> replaces `call CONTE_IC(...)` (contebl.f:205), `call CONTE(...)` (conte.f:131, orrsom.f:151)
+    integer(c_int) function osb_shoot_temporal(ctx, opts, prof, npts, alpha, Re, c, passes, qend, &
+                                               status, resid, history, hist_cap) &
+        bind(C, name="osb_shoot_temporal")
+      import :: c_int, c_int32_t, c_int64_t, c_ptr, c_double, c_double_complex, osb_shoot_opts
+      type(c_ptr), value :: ctx, prof
+      type(osb_shoot_opts), intent(in) :: opts
+      integer(c_int64_t), value :: npts
+      complex(c_double_complex), intent(in) :: alpha(*)
+      real(c_double), intent(in) :: Re(*)
+      complex(c_double_complex), intent(inout) :: c(*)
+      integer(c_int32_t), intent(out) :: passes(*), qend(*), status(*)
+      real(c_double), intent(out) :: resid(2, *)        ! |err|, |c-cm1|
+      real(c_double), intent(out) :: history(4, hist_cap, *)
+      integer(c_int32_t), value :: hist_cap
+    end function
+    !> replaces the omega loop around `call CONTE` (orrspace.f:186-195)
+    integer(c_int) function osb_shoot_spatial_lines(ctx, opts, prof, nlines, niter, Re, omega0, &
+                                                    domega, alpha0, alpha_out, passes, qend, status) &
+        bind(C, name="osb_shoot_spatial_lines")
+      import :: c_int, c_int32_t, c_int64_t, c_ptr, c_double, c_double_complex, osb_shoot_opts
+      type(c_ptr), value :: ctx, prof
+      type(osb_shoot_opts), intent(in) :: opts
+      integer(c_int64_t), value :: nlines
+      integer(c_int32_t), value :: niter
+      real(c_double), intent(in) :: Re(*), domega(*)
+      complex(c_double_complex), intent(in) :: omega0(*), alpha0(*)
+      complex(c_double_complex), intent(out) :: alpha_out(niter, *)
+      integer(c_int32_t), intent(out) :: passes(niter, *), qend(niter, *), status(niter, *)
+    end function
+    !> replaces the "second pass" (shoot.f:762-810): y(i,k) un-normalised + vmax
+    integer(c_int) function osb_eigfun(ctx, opts, prof, npts, alpha, Re, eig, omega, y, vmax, qend) &
+        bind(C, name="osb_eigfun")
+      import :: c_int, c_int32_t, c_int64_t, c_ptr, c_double, c_double_complex, osb_shoot_opts
+      type(c_ptr), value :: ctx, prof
+      type(osb_shoot_opts), intent(in) :: opts
+      integer(c_int64_t), value :: npts
+      complex(c_double_complex), intent(in) :: alpha(*), eig(*), omega(*)
+      real(c_double), intent(in) :: Re(*)
+      complex(c_double_complex), intent(out) :: y(4, *)   ! (4, 0:nstep) per point
+      complex(c_double_complex), intent(out) :: vmax(*)
+      integer(c_int32_t), intent(out) :: qend(*)
+    end function
+  end interface
+end module osb_c
