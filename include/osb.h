@@ -172,6 +172,48 @@ int osb_eigfun(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof
                const double *eig, const double *omega, double *y, double *vmax,
                int32_t *qend);
 
+/* ---- channel matrix path (replaces MAKE_DERIVATIVES + MAKE_MATRIX +
+ *      SOLVE_ORR_SOM of orrfdchan.f:273-350,553-659,688-823; orrcolchan.f:77-154,
+ *      272-513; orrncbl.f:122-202,553-695,758-981) ------------------------- */
+#define OSB_DISC_FD 0       /* orrfdchan: FiniteD1 (orrfdchan.f:1183), analytic U''   */
+#define OSB_DISC_CHEB 1     /* orrcolchan: CHEBYD (orrcolchan.f:904), analytic U''    */
+#define OSB_DISC_CHEB_NUM 2 /* orrncbl: CHEBYD, U'' by collocation (orrncbl.f:520-545) */
+
+typedef struct osb_chan osb_chan;
+
+/* Grid, profile and derivative tables for N mesh intervals (the reference's n):
+ * cosine grid, D1hat, D1 with rows 0,N zeroed, D2 = D1hat D1, D3, D4 formed with the
+ * reference's own triple loops on the host (once per N), interior blocks uploaded. */
+int osb_chan_create(osb_ctx *ctx, int disc, int N, osb_chan **chan);
+int osb_chan_free(osb_ctx *ctx, osb_chan *chan);
+/* eta, u, d2u: [N+1]; D2, D4: [(N+1)*(N+1)] row-major (i,j); any may be NULL */
+int osb_chan_tables(osb_ctx *ctx, const osb_chan *chan, double *eta, double *u, double *d2u,
+                    double *D2, double *D4);
+
+/*
+ * Batched SOLVE_ORR_SOM: for each alpha the eigenvalue the reference's driver keeps
+ * (the least stable mode: largest Im w, orrfdchan.f:815-823 / orrncbl.f:897-905) and,
+ * optionally, its eigenvector on the full grid normalised by the component of largest
+ * modulus (orrfdchan.f:849-857).  The interior (N-1)x(N-1) pencil is used (the BC rows
+ * of orrcolchan.f:424-435 only add infinite eigenvalues).
+ *   alpha  [2*npts]; sigma0 [2*npts] optional shift guesses (NULL: a 16-shift scan
+ *   over 0 < c_r < 1 per point picks the mode); omega [2*npts] out;
+ *   evec   [npts*(N+1)*2] optional; iters [npts] inverse iterations; status [npts].
+ */
+int osb_chan_eig(osb_ctx *ctx, const osb_chan *chan, double Re, int64_t npts, const double *alpha,
+                 const double *sigma0, double *omega, double *evec, int32_t *iters, int32_t *status);
+
+/*
+ * Batched neutral-point search, the Newton iteration on alpha of orrncbl.f:109-116
+ * (bug-compatible step: the adjoint is the left eigenvector of inv(B)A, D-7), one
+ * independent search per Re:  while |Im w| > tol: alpha += sfac * (-Im w / Im dw/da).
+ *   Re, alpha0 [nRe]; alpha_out, omega [nRe] / [2*nRe]; steps, status [nRe];
+ *   trace optional [nRe*maxit*7]: nalpha, w_r, w_i, dwda_r, dwda_i, dalpha, nw per step
+ */
+int osb_chan_neutral(osb_ctx *ctx, const osb_chan *chan, int64_t nRe, const double *Re,
+                     const double *alpha0, double sfac, double tol, int32_t maxit, double *alpha_out,
+                     double *omega, int32_t *steps, int32_t *status, double *trace);
+
 /* ---- measurement helpers ---------------------------------------------- */
 /* Device FP64 peak micro-benchmark: runs a dependent-chain-free DFMA kernel for
  * ~ms_target milliseconds on the context's device; returns TFLOP/s (2 flops

@@ -91,6 +91,11 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "osb_shoot_spatial_lines": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, i32, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _ip]),
         "osb_eigfun": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, _dp, _dp, _dp, _dp, _dp, _dp, _ip]),
         "osb_measure_fp64_peak": (C.c_int, [vp, dbl, _dp, _dp]),
+        "osb_chan_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+        "osb_chan_free": (C.c_int, [vp, vp]),
+        "osb_chan_tables": (C.c_int, [vp, vp, _dp, _dp, _dp, _dp, _dp]),
+        "osb_chan_eig": (C.c_int, [vp, vp, dbl, i64, _dp, _dp, _dp, _dp, _ip, _ip]),
+        "osb_chan_neutral": (C.c_int, [vp, vp, i64, _dp, _dp, dbl, dbl, i32, _dp, _dp, _ip, _ip, _dp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
@@ -103,8 +108,11 @@ EXPORTED_SYMBOLS = (
     "osb_version osb_create osb_create_multi osb_destroy osb_device_count osb_last_error osb_stream "
     "osb_launch_count osb_profile_blasius osb_profile_blasius_batch osb_profile_upload "
     "osb_profile_channel osb_profile_get osb_profile_nbl osb_profile_free osb_shoot_defaults "
-    "osb_shoot_temporal osb_shoot_temporal_dev osb_shoot_spatial_lines osb_eigfun osb_measure_fp64_peak"
+    "osb_shoot_temporal osb_shoot_temporal_dev osb_shoot_spatial_lines osb_eigfun osb_measure_fp64_peak "
+    "osb_chan_create osb_chan_free osb_chan_tables osb_chan_eig osb_chan_neutral"
 ).split()
+
+DISC_FD, DISC_CHEB, DISC_CHEB_NUM = 0, 1, 2
 
 
 def contebl_units(alpha, Re):
@@ -305,11 +313,75 @@ class Engine:
             y.ctypes.data_as(_dp), vmax.ctypes.data_as(_dp), qend.ctypes.data_as(_ip)))
         return dict(y=y.view(np.complex128).reshape(n, opts.nstep + 1, 4), vmax=vmax.view(np.complex128), qend=qend)
 
+    # ---- MAKE_MATRIX + SOLVE_ORR_SOM (channel matrix path) ---------------
+    def chan(self, disc, N) -> "Chan":
+        h = C.c_void_p()
+        self._check(self.lib.osb_chan_create(self.ctx, disc, N, C.byref(h)))
+        return Chan(self, h, N)
+
     def measure_fp64_peak(self, ms_target=200.0):
         tf = C.c_double()
         mhz = C.c_double()
         self._check(self.lib.osb_measure_fp64_peak(self.ctx, ms_target, C.byref(tf), C.byref(mhz)))
         return tf.value, mhz.value
+
+
+class Chan:
+    """Grid + derivative tables of one (discretisation, N): the reference's COMMON
+    /data/ /deriv/ after MAKE_CHANNEL_METRICS, MAKE_DERIVATIVES, INIT_CHANNEL_PROFILE."""
+
+    def __init__(self, engine, handle, N):
+        self.engine, self.handle, self.N = engine, handle, N
+
+    def tables(self):
+        n1 = self.N + 1
+        out = dict(eta=np.zeros(n1), u=np.zeros(n1), d2u=np.zeros(n1), D2=np.zeros((n1, n1)), D4=np.zeros((n1, n1)))
+        self.engine._check(self.engine.lib.osb_chan_tables(
+            self.engine.ctx, self.handle, *[out[k].ctypes.data_as(_dp) for k in ("eta", "u", "d2u", "D2", "D4")]))
+        return out
+
+    def solve(self, alpha, Re, sigma0=None, want_evec=False):
+        """SOLVE_ORR_SOM for a batch of alpha (orrfdchan.f:116-121 hoisted into one call)."""
+        alpha = np.atleast_1d(np.asarray(alpha, dtype=np.complex128))
+        n = alpha.size
+        al = _cplx_pairs(alpha, n)
+        sg = _cplx_pairs(np.atleast_1d(sigma0), n) if sigma0 is not None else None
+        om = np.zeros(2 * n)
+        ev = np.zeros(2 * n * (self.N + 1)) if want_evec else None
+        iters = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        self.engine._check(self.engine.lib.osb_chan_eig(
+            self.engine.ctx, self.handle, float(Re), n, al.ctypes.data_as(_dp),
+            sg.ctypes.data_as(_dp) if sg is not None else None, om.ctypes.data_as(_dp),
+            ev.ctypes.data_as(_dp) if want_evec else None, iters.ctypes.data_as(_ip), status.ctypes.data_as(_ip)))
+        r = dict(omega=om.view(np.complex128), iters=iters, status=status)
+        if want_evec:
+            r["evec"] = ev.view(np.complex128).reshape(n, self.N + 1)
+        return r
+
+    def neutral(self, Re, alpha0, sfac=0.01, tol=1.0e-8, maxit=200, want_trace=False):
+        """The Newton iteration on alpha of orrncbl.f:109-116, one search per Re."""
+        Re = _f64(np.atleast_1d(Re))
+        n = Re.size
+        a0 = _f64(np.broadcast_to(np.asarray(alpha0, dtype=np.float64), (n,)).copy(), n)
+        aout = np.zeros(n)
+        om = np.zeros(2 * n)
+        steps = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        tr = np.zeros(n * maxit * 7) if want_trace else None
+        self.engine._check(self.engine.lib.osb_chan_neutral(
+            self.engine.ctx, self.handle, n, Re.ctypes.data_as(_dp), a0.ctypes.data_as(_dp), sfac, tol, maxit,
+            aout.ctypes.data_as(_dp), om.ctypes.data_as(_dp), steps.ctypes.data_as(_ip), status.ctypes.data_as(_ip),
+            tr.ctypes.data_as(_dp) if want_trace else None))
+        r = dict(alpha=aout, omega=om.view(np.complex128), steps=steps, status=status)
+        if want_trace:
+            r["trace"] = tr.reshape(n, maxit, 7)
+        return r
+
+    def free(self):
+        if self.handle:
+            self.engine.lib.osb_chan_free(self.engine.ctx, self.handle)
+            self.handle = None
 
 
 # ---- sharding of a sweep over ranks (SURVEY 8e): host logic, no numerics ----

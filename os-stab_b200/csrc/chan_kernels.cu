@@ -1,0 +1,667 @@
+// chan_kernels.cu -- K3/K4: the channel MATRIX path (orrfdchan / orrcolchan / orrncbl).
+//
+// Replaces MAKE_MATRIX + SOLVE_ORR_SOM (orrfdchan.f:553-659,688-823; orrcolchan.f:272-513;
+// orrncbl.f:553-695,758-981) for a batch of independent (alpha, Re) points.  The
+// reference forms inv(B) A and calls ZGEEV for the FULL spectrum (25 n^3 flops) only
+// to keep one eigenvalue; here every point is a shift-invert inverse iteration
+//     (A - sigma B) y = B x,   omega = sigma + (y^H x)/(y^H y)
+// on the pencil itself:
+//   K3 (fused): M = A - sigma B is assembled straight into the LU workspace from the
+//       shared real tables D2, D4 (A3 = A1 = B1 = 0 for the channel metrics); A and B
+//       are never materialised -- B x and the d/dalpha products are applied from D2.
+//   K4: one CTA per instance: blocked right-looking complex LU with partial pivoting
+//       (IZAMAX's |re|+|im| rule, like ZGETRF), the 16-column panel factorised in
+//       shared memory, the trailing update A22 -= L21 U12 on the FP64 tensor path
+//       (mma.sync.m8n8k4.f64 -> DMMA; complex product as four real ones), then
+//       triangular solves + the D2 mat-vec per inverse iteration.  tcgen05 has no
+//       fp64 kind, so DMMA via mma.sync is the sm_100a FP64 tensor path.
+//   Newton on alpha (orrncbl) runs inside the kernel, one CTA per Re, including the
+//       reference's use of the LEFT eigenvector of inv(B)A (oracle D-7), obtained as
+//       vl = B^H u with u from inverse iteration on (A - sigma B)^H.
+#include "osb_cplx.cuh"
+#include "osb_internal.h"
+
+namespace osb {
+
+constexpr int CH_THREADS = 256;
+constexpr int CH_NB = 16;
+
+__device__ __forceinline__ double2 cmul2(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ double2 cmulc2(double2 a, double2 b) {  // conj(a) * b
+  return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ double2 csub2(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ double2 cadd2(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 cdiv2(double2 a, double2 b) {
+  zd r = zdiv(zd{a.x, a.y}, zd{b.x, b.y});
+  return make_double2(r.x, r.y);
+}
+
+__device__ __forceinline__ void dmma884(double &d0, double &d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// block-wide sum of a complex value; result valid in every thread.  red: >= 2*(CH_THREADS/32) doubles
+__device__ double2 block_sum(double2 v, double *red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+  }
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (l == 0) { red[2 * w] = v.x; red[2 * w + 1] = v.y; }
+  __syncthreads();
+  double2 s = make_double2(0.0, 0.0);
+  for (int i = 0; i < nw; ++i) { s.x += red[2 * i]; s.y += red[2 * i + 1]; }
+  return s;
+}
+
+// ---------------------------------------------------------------------------
+// per-instance coefficients of the pencil (MAKE_MATRIX with m1=1, m2=m3=m4=0)
+// ---------------------------------------------------------------------------
+struct PencilCoef {
+  double2 alpha, a2, a3, a4;
+  double Re;
+  double2 b2, b0;  // B = b2 D2 + b0 I          (orrfdchan.f:633-652)
+  double2 db0;     // dB/dalpha = db0 I          (orrncbl.f:686-691)
+};
+
+__device__ __forceinline__ PencilCoef pencil_coef(double2 alpha, double Re) {
+  PencilCoef p;
+  p.alpha = alpha; p.Re = Re;
+  p.a2 = cmul2(alpha, alpha); p.a3 = cmul2(p.a2, alpha); p.a4 = cmul2(p.a2, p.a2);
+  p.b2 = make_double2(0.0, -Re);                                  // -1.0*(0,1)*Re
+  p.b0 = make_double2(-p.a2.y * Re, p.a2.x * Re);                 // (0,1)*alpha^2*Re
+  p.db0 = make_double2(-2.0 * alpha.y * Re, 2.0 * alpha.x * Re);  // (0,1)*2*alpha*Re
+  return p;
+}
+// row coefficients: A = D4 + w2_i D2 + w0_i I ; dA = d2_i D2 + d0_i I
+__device__ __forceinline__ double2 coef_w2(const PencilCoef &p, double u) {
+  // -2 alpha^2 - (0,1) alpha Re U
+  return make_double2(-2.0 * p.a2.x + p.alpha.y * p.Re * u, -2.0 * p.a2.y - p.alpha.x * p.Re * u);
+}
+__device__ __forceinline__ double2 coef_w0(const PencilCoef &p, double u, double d2u) {
+  // alpha^4 + (0,1) alpha^3 Re U + (0,1) alpha Re U''
+  return make_double2(p.a4.x - p.a3.y * p.Re * u - p.alpha.y * p.Re * d2u,
+                      p.a4.y + p.a3.x * p.Re * u + p.alpha.x * p.Re * d2u);
+}
+__device__ __forceinline__ double2 coef_d2(const PencilCoef &p, double u) {
+  // -4 alpha - (0,1) Re U
+  return make_double2(-4.0 * p.alpha.x, -4.0 * p.alpha.y - p.Re * u);
+}
+__device__ __forceinline__ double2 coef_d0(const PencilCoef &p, double u, double d2u) {
+  // 4 alpha^3 + 3 (0,1) alpha^2 Re U + (0,1) Re U''
+  return make_double2(4.0 * p.a3.x - 3.0 * p.a2.y * p.Re * u, 4.0 * p.a3.y + 3.0 * p.a2.x * p.Re * u + p.Re * d2u);
+}
+
+// K3 (fused): M = A - sigma B, column-major n x n, ld = n
+__device__ void assemble_shifted(double2 *__restrict__ M, int n, const double *__restrict__ D2,
+                                 const double *__restrict__ D4, const double *__restrict__ u,
+                                 const double *__restrict__ d2u, const PencilCoef &p, double2 sigma) {
+  const double2 sb2 = cmul2(sigma, p.b2), sb0 = cmul2(sigma, p.b0);
+  for (size_t e = threadIdx.x; e < (size_t)n * n; e += blockDim.x) {
+    const int i = (int)(e % n), j = (int)(e / n);
+    const double2 w2 = csub2(coef_w2(p, u[i]), sb2);
+    const double d2 = D2[e], d4 = D4[e];
+    double2 v = make_double2(fma(w2.x, d2, d4), w2.y * d2);
+    if (i == j) v = cadd2(v, csub2(coef_w0(p, u[i], d2u[i]), sb0));
+    M[e] = v;
+  }
+  __syncthreads();
+}
+
+// ---------------------------------------------------------------------------
+// K4: blocked LU, P M = L U in place.  panel: shared, (n + 16) x CH_NB complex.
+// ---------------------------------------------------------------------------
+__device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel, double *red) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  const int ldp = n + 16;
+  int *red_i = (int *)(red + 2 * (CH_THREADS / 32));
+  for (int k0 = 0; k0 < n; k0 += CH_NB) {
+    const int nb = min(CH_NB, n - k0), mp = n - k0;
+    // ---- stage the panel
+    for (int e = tid; e < mp * nb; e += nt) {
+      const int r = e % mp, c = e / mp;
+      panel[c * ldp + r] = M[(size_t)(k0 + c) * n + k0 + r];
+    }
+    __syncthreads();
+    // ---- unblocked factorisation inside the panel (ZGETF2)
+    for (int j = 0; j < nb; ++j) {
+      double best = -1.0;
+      int bi = j;
+      for (int r = j + tid; r < mp; r += nt) {
+        const double2 v = panel[j * ldp + r];
+        const double a = fabs(v.x) + fabs(v.y);
+        if (a > best) { best = a; bi = r; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      if (lane == 0) { red[warp] = best; red_i[warp] = bi; }
+      __syncthreads();
+      if (tid == 0) {
+        double b = red[0];
+        int p = red_i[0];
+        for (int w = 1; w < nwarp; ++w)
+          if (red[w] > b || (red[w] == b && red_i[w] < p)) { b = red[w]; p = red_i[w]; }
+        ipiv[k0 + j] = k0 + p;
+        red_i[nwarp] = p;
+      }
+      __syncthreads();
+      const int p = red_i[nwarp];
+      if (p != j && tid < nb) {
+        const double2 t = panel[tid * ldp + j];
+        panel[tid * ldp + j] = panel[tid * ldp + p];
+        panel[tid * ldp + p] = t;
+      }
+      __syncthreads();
+      double2 piv = panel[j * ldp + j];
+      // an exactly singular pivot only happens when sigma hits an eigenvalue to the last
+      // bit; inverse iteration wants the huge solve, not a NaN
+      if (piv.x == 0.0 && piv.y == 0.0) piv = make_double2(1.0e-290, 0.0);
+      const double2 rinv = cdiv2(make_double2(1.0, 0.0), piv);
+      for (int r = j + 1 + tid; r < mp; r += nt) {
+        const double2 l = cmul2(panel[j * ldp + r], rinv);
+        panel[j * ldp + r] = l;
+        for (int c = j + 1; c < nb; ++c)
+          panel[c * ldp + r] = csub2(panel[c * ldp + r], cmul2(l, panel[c * ldp + j]));
+      }
+      __syncthreads();
+    }
+    // ---- row interchanges on the columns outside the panel; write the panel back
+    for (int c = tid; c < n; c += nt) {
+      if (c >= k0 && c < k0 + nb) continue;
+      double2 *col = M + (size_t)c * n;
+      for (int j = 0; j < nb; ++j) {
+        const int p = ipiv[k0 + j];
+        if (p != k0 + j) { const double2 t = col[k0 + j]; col[k0 + j] = col[p]; col[p] = t; }
+      }
+    }
+    for (int e = tid; e < mp * nb; e += nt) {
+      const int r = e % mp, c = e / mp;
+      M[(size_t)(k0 + c) * n + k0 + r] = panel[c * ldp + r];
+    }
+    __syncthreads();
+    const int mt = n - k0 - nb;  // trailing size
+    if (mt <= 0) break;
+    // ---- U12 = L11^{-1} A12  (unit lower L11 from the panel), one thread per column
+    for (int c = tid; c < mt; c += nt) {
+      double2 *col = M + (size_t)(k0 + nb + c) * n + k0;
+      double2 a[CH_NB];
+#pragma unroll
+      for (int i = 0; i < CH_NB; ++i) a[i] = (i < nb) ? col[i] : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int i = 1; i < CH_NB; ++i) {
+        if (i < nb) {
+          double2 s = a[i];
+#pragma unroll
+          for (int t = 0; t < i; ++t) s = csub2(s, cmul2(panel[t * ldp + i], a[t]));
+          a[i] = s;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < CH_NB; ++i) if (i < nb) col[i] = a[i];
+    }
+    __syncthreads();
+    // ---- trailing update A22 -= L21 U12 on the FP64 tensor path; a warp owns 16x16 blocks
+    if (nb == CH_NB) {
+      const int g = lane >> 2, t4 = lane & 3;
+      const int nblk = (mt + 15) >> 4;
+      for (int blk = warp; blk < nblk * nblk; blk += nwarp) {
+        const int R0 = (blk % nblk) << 4, C0 = (blk / nblk) << 4;
+        double cr[2][2][2], ci[2][2][2];
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+          for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = R0 + 8 * rt + g, j = C0 + 8 * ct + 2 * t4 + e;
+              double2 v = make_double2(0.0, 0.0);
+              if (i < mt && j < mt) v = M[(size_t)(k0 + nb + j) * n + k0 + nb + i];
+              cr[rt][ct][e] = v.x; ci[rt][ct][e] = v.y;
+            }
+#pragma unroll
+        for (int ks = 0; ks < CH_NB / 4; ++ks) {
+          const int k = 4 * ks + t4;
+          double lr[2], li[2], ur[2], ui[2];
+#pragma unroll
+          for (int rt = 0; rt < 2; ++rt) {  // rows past the end read the zero/garbage pad; their outputs are dropped
+            const double2 l = panel[k * ldp + nb + R0 + 8 * rt + g];
+            lr[rt] = l.x; li[rt] = l.y;
+          }
+#pragma unroll
+          for (int ct = 0; ct < 2; ++ct) {
+            const int j = min(C0 + 8 * ct + g, mt - 1);
+            const double2 uu = M[(size_t)(k0 + nb + j) * n + k0 + k];
+            ur[ct] = uu.x; ui[ct] = uu.y;
+          }
+#pragma unroll
+          for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) {
+              // C -= L U :  Cr += (-Lr) Ur + Li Ui ;  Ci += (-Lr) Ui + (-Li) Ur
+              dmma884(cr[rt][ct][0], cr[rt][ct][1], -lr[rt], ur[ct]);
+              dmma884(cr[rt][ct][0], cr[rt][ct][1], li[rt], ui[ct]);
+              dmma884(ci[rt][ct][0], ci[rt][ct][1], -lr[rt], ui[ct]);
+              dmma884(ci[rt][ct][0], ci[rt][ct][1], -li[rt], ur[ct]);
+            }
+        }
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+          for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = R0 + 8 * rt + g, j = C0 + 8 * ct + 2 * t4 + e;
+              if (i < mt && j < mt)
+                M[(size_t)(k0 + nb + j) * n + k0 + nb + i] = make_double2(cr[rt][ct][e], ci[rt][ct][e]);
+            }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// x <- M^{-1} x using P M = L U.  x: shared, n complex.
+__device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv, double2 *x) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0)
+    for (int k = 0; k < n; ++k) {
+      const int p = ipiv[k];
+      if (p != k) { const double2 t = x[k]; x[k] = x[p]; x[p] = t; }
+    }
+  __syncthreads();
+  for (int j = 0; j < n - 1; ++j) {  // L y = P b (unit lower)
+    const double2 xj = x[j];
+    const double2 *col = M + (size_t)j * n;
+    for (int r = j + 1 + tid; r < n; r += nt) x[r] = csub2(x[r], cmul2(col[r], xj));
+    __syncthreads();
+  }
+  for (int j = n - 1; j >= 0; --j) {  // U x = y
+    const double2 *col = M + (size_t)j * n;
+    if (tid == 0) {
+      double2 d = col[j];
+      if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
+      x[j] = cdiv2(x[j], d);
+    }
+    __syncthreads();
+    const double2 xj = x[j];
+    for (int r = tid; r < j; r += nt) x[r] = csub2(x[r], cmul2(col[r], xj));
+    __syncthreads();
+  }
+}
+
+// x <- M^{-H} x :  M^H = U^H L^H P
+__device__ void cta_solve_h(const double2 *__restrict__ M, int n, const int *ipiv, double2 *x) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int j = 0; j < n; ++j) {  // U^H a = r : lower triangular, row j of U^H = conj(column j of U)
+    const double2 *col = M + (size_t)j * n;
+    // a_j = (r_j - sum_{i<j} conj(U(i,j)) a_i) / conj(U(j,j)) : dot product over the column
+    double2 s = make_double2(0.0, 0.0);
+    for (int i = tid; i < j; i += nt) s = cadd2(s, cmulc2(col[i], x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+      s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+    }
+    __shared__ double2 part[CH_THREADS / 32];
+    if ((tid & 31) == 0) part[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+      double2 tot = make_double2(0.0, 0.0);
+      for (int w = 0; w < (nt >> 5); ++w) tot = cadd2(tot, part[w]);
+      const double2 d = make_double2(col[j].x, -col[j].y);
+      x[j] = cdiv2(csub2(x[j], tot), d);
+    }
+    __syncthreads();
+  }
+  for (int j = n - 1; j >= 0; --j) {  // L^H b = a : unit upper, row j of L^H = conj(column j of L)
+    const double2 *col = M + (size_t)j * n;
+    double2 s = make_double2(0.0, 0.0);
+    for (int i = j + 1 + tid; i < n; i += nt) s = cadd2(s, cmulc2(col[i], x[i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+      s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+    }
+    __shared__ double2 part2[CH_THREADS / 32];
+    if ((tid & 31) == 0) part2[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+      double2 tot = make_double2(0.0, 0.0);
+      for (int w = 0; w < (nt >> 5); ++w) tot = cadd2(tot, part2[w]);
+      x[j] = csub2(x[j], tot);
+    }
+    __syncthreads();
+  }
+  if (tid == 0)  // z = P^T b
+    for (int k = n - 1; k >= 0; --k) {
+      const int p = ipiv[k];
+      if (p != k) { const double2 t = x[k]; x[k] = x[p]; x[p] = t; }
+    }
+  __syncthreads();
+}
+
+// y = D2 x (or D2^T x); D2 real column-major n x n; x, y shared
+__device__ void cta_d2_matvec(const double *__restrict__ D2, int n, const double2 *x, double2 *y, bool transpose) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (!transpose) {
+    for (int i = tid; i < n; i += nt) {
+      double sr = 0.0, si = 0.0;
+      for (int j = 0; j < n; ++j) {
+        const double d = D2[(size_t)j * n + i];
+        sr = fma(d, x[j].x, sr); si = fma(d, x[j].y, si);
+      }
+      y[i] = make_double2(sr, si);
+    }
+  } else {
+    for (int j = tid; j < n; j += nt) {
+      const double *col = D2 + (size_t)j * n;
+      double sr = 0.0, si = 0.0;
+      for (int i = 0; i < n; ++i) { sr = fma(col[i], x[i].x, sr); si = fma(col[i], x[i].y, si); }
+      y[j] = make_double2(sr, si);
+    }
+  }
+  __syncthreads();
+}
+
+struct ChanShared {
+  double2 *panel, *x, *y, *t;
+  int *ipiv;
+  double *red;
+};
+
+__device__ ChanShared carve(unsigned char *smem, int n) {
+  ChanShared s;
+  size_t off = 0;
+  s.panel = (double2 *)(smem + off); off += sizeof(double2) * (size_t)(n + 16) * CH_NB;
+  s.x = (double2 *)(smem + off); off += sizeof(double2) * (size_t)n;
+  s.y = (double2 *)(smem + off); off += sizeof(double2) * (size_t)n;
+  s.t = (double2 *)(smem + off); off += sizeof(double2) * (size_t)n;
+  s.red = (double *)(smem + off); off += sizeof(double) * 64;
+  s.ipiv = (int *)(smem + off);
+  return s;
+}
+
+size_t chan_smem_bytes(int n) {
+  return sizeof(double2) * ((size_t)(n + 16) * CH_NB + 3 * (size_t)n) + sizeof(double) * 64 + sizeof(int) * (size_t)(n + 8);
+}
+
+// Right inverse iteration with the current LU: x (unit 2-norm, shared) in/out.
+// Returns the eigenvalue estimate after up to maxit iterations; *delta = last change.
+__device__ double2 inverse_iterate(const double2 *M, int n, const double *D2, const PencilCoef &p,
+                                   double2 sigma, ChanShared &s, int maxit, double tol, double *delta,
+                                   int *iters) {
+  double2 om = sigma;
+  double dl = 1.0e300;
+  int it = 0;
+  for (; it < maxit; ++it) {
+    // y = B x = b2 D2 x + b0 x
+    cta_d2_matvec(D2, n, s.x, s.y, false);
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      s.y[i] = cadd2(cmul2(p.b2, s.y[i]), cmul2(p.b0, s.x[i]));
+    __syncthreads();
+    cta_solve(M, n, s.ipiv, s.y);
+    double2 yx = make_double2(0.0, 0.0), yy = make_double2(0.0, 0.0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      yx = cadd2(yx, cmulc2(s.y[i], s.x[i]));
+      yy.x += s.y[i].x * s.y[i].x + s.y[i].y * s.y[i].y;
+    }
+    yx = block_sum(yx, s.red);
+    yy = block_sum(yy, s.red);
+    const double2 om_new = cadd2(sigma, make_double2(yx.x / yy.x, yx.y / yy.x));
+    const double rn = rsqrt(yy.x);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s.x[i] = make_double2(s.y[i].x * rn, s.y[i].y * rn);
+    __syncthreads();
+    dl = hypot(om_new.x - om.x, om_new.y - om.y);
+    om = om_new;
+    if (it > 0 && dl <= tol * hypot(om.x, om.y)) { ++it; break; }
+  }
+  *delta = dl;
+  *iters = it;
+  return om;
+}
+
+struct ChanArgs {
+  int n;                 // interior size N-1
+  const double *D2, *D4; // n x n column-major
+  const double *u, *d2u; // interior
+  double2 *work;         // gridDim.x * n*n
+  int64_t ninst;
+  const double2 *alpha;  // [ninst]
+  const double *Re;      // [ninst]
+  const double2 *sigma;  // [ninst] shifts
+  int outer, inner;      // re-shift rounds, iterations per round
+  double tol;
+  double2 *omega;        // [ninst]
+  double *delta;         // [ninst] last |d omega|
+  int32_t *iters;        // [ninst] total inverse iterations
+  double2 *evec;         // optional [ninst][n+2] (grid 0..N, zeros at the walls), max-modulus normalised
+};
+
+__device__ void start_vector(double2 *x, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double s = sin(3.0 * (i + 1.0) / (n + 1.0)) + 0.37 * cos(11.0 * (i + 1.0) / (n + 1.0));
+    x[i] = make_double2(s, 0.25 * s * s - 0.1);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(CH_THREADS) chan_eig_kernel(const __grid_constant__ ChanArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int n = a.n;
+  ChanShared s = carve(smem, n);
+  double2 *M = a.work + (size_t)blockIdx.x * n * n;
+  for (int64_t inst = blockIdx.x; inst < a.ninst; inst += gridDim.x) {
+    const PencilCoef p = pencil_coef(a.alpha[inst], a.Re[inst]);
+    double2 sigma = a.sigma[inst];
+    start_vector(s.x, n);
+    double2 om = sigma;
+    double dl = 1.0e300;
+    int total = 0;
+    for (int o = 0; o < a.outer; ++o) {
+      assemble_shifted(M, n, a.D2, a.D4, a.u, a.d2u, p, sigma);
+      cta_lu(M, n, s.ipiv, s.panel, s.red);
+      int it = 0;
+      om = inverse_iterate(M, n, a.D2, p, sigma, s, a.inner, a.tol, &dl, &it);
+      total += it;
+      if (dl <= a.tol * hypot(om.x, om.y)) break;
+      sigma = om;  // re-shift (Rayleigh-quotient style) and refactorise
+    }
+    if (threadIdx.x == 0) {
+      a.omega[inst] = om;
+      a.delta[inst] = dl;
+      a.iters[inst] = total;
+    }
+    if (a.evec) {
+      // normalise by the component of largest modulus (orrfdchan.f:849-857)
+      double best = -1.0;
+      int bi = 0;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double m2 = s.x[i].x * s.x[i].x + s.x[i].y * s.x[i].y;
+        if (m2 > best) { best = m2; bi = i; }
+      }
+      __shared__ double sb[CH_THREADS];
+      __shared__ int si[CH_THREADS];
+      sb[threadIdx.x] = best; si[threadIdx.x] = bi;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        for (int t = 1; t < blockDim.x; ++t)
+          if (sb[t] > sb[0] || (sb[t] == sb[0] && si[t] < si[0])) { sb[0] = sb[t]; si[0] = si[t]; }
+      }
+      __syncthreads();
+      const double2 esc = cdiv2(make_double2(1.0, 0.0), s.x[si[0]]);
+      double2 *ev = a.evec + (size_t)inst * (n + 2);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) ev[i + 1] = cmul2(esc, s.x[i]);
+      if (threadIdx.x == 0) { ev[0] = make_double2(0.0, 0.0); ev[n + 1] = make_double2(0.0, 0.0); }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Newton on alpha to Im(omega) = 0   (orrncbl.f:109-116, 962-981), one CTA per Re
+// ---------------------------------------------------------------------------
+struct NeutralArgs {
+  int n;
+  const double *D2, *D4, *u, *d2u;
+  double2 *work;
+  int64_t ninst;
+  const double *Re;       // [ninst]
+  const double *alpha0;   // [ninst] starting alpha_r
+  const double2 *sigma0;  // [ninst] eigenvalue at alpha0 (from the scan)
+  double sfac, tol;
+  int maxit;
+  double *alpha_out;      // [ninst] nalpha after the last step
+  double2 *omega_out;     // [ninst]
+  int32_t *steps;         // [ninst]
+  int32_t *status;        // [ninst]
+  double *trace;          // optional [ninst][maxit][7]
+};
+
+__global__ void __launch_bounds__(CH_THREADS) chan_neutral_kernel(const __grid_constant__ NeutralArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int n = a.n;
+  ChanShared s = carve(smem, n);
+  double2 *M = a.work + (size_t)blockIdx.x * n * n;
+  for (int64_t inst = blockIdx.x; inst < a.ninst; inst += gridDim.x) {
+    const double Re = a.Re[inst];
+    double nalpha = a.alpha0[inst];
+    double2 sigma = a.sigma0[inst];
+    double2 ev = make_double2(1.0, 1.0);
+    int it = 0, st = OSB_ST_MAXCOUNT;
+    while (fabs(ev.y) > a.tol && it < a.maxit) {
+      const PencilCoef p = pencil_coef(make_double2(nalpha, 0.0), Re);
+      // right eigenpair, up to 3 factorisations
+      start_vector(s.x, n);
+      double dl = 1.0e300;
+      for (int o = 0; o < 3; ++o) {
+        assemble_shifted(M, n, a.D2, a.D4, a.u, a.d2u, p, sigma);
+        cta_lu(M, n, s.ipiv, s.panel, s.red);
+        int k = 0;
+        ev = inverse_iterate(M, n, a.D2, p, sigma, s, 8, 1.0e-14, &dl, &k);
+        if (dl <= 1.0e-14 * hypot(ev.x, ev.y)) break;
+        sigma = ev;
+      }
+      // left vector of inv(B)A: vl = B^H u, (A - sigma B)^H u' = vl  (same LU)
+      for (int i = threadIdx.x; i < n; i += blockDim.x) s.t[i] = make_double2(s.x[i].x, -s.x[i].y + 0.3);
+      __syncthreads();
+      for (int k = 0; k < 6; ++k) {
+        cta_solve_h(M, n, s.ipiv, s.t);                     // u = M^{-H} vl
+        cta_d2_matvec(a.D2, n, s.t, s.y, true);             // D2^T u
+        double nn = 0.0;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+          // vl = conj(b2) D2^T u + conj(b0) u
+          const double2 v = cadd2(cmulc2(p.b2, s.y[i]), cmulc2(p.b0, s.t[i]));
+          s.t[i] = v;
+          nn += v.x * v.x + v.y * v.y;
+        }
+        const double2 tot = block_sum(make_double2(nn, 0.0), s.red);
+        const double rn = rsqrt(tot.x);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s.t[i] = make_double2(s.t[i].x * rn, s.t[i].y * rn);
+        __syncthreads();
+      }
+      // dw = vl^H (dB w - dA) x ; dalp = vl^H B x        (orrncbl.f:962-976)
+      cta_d2_matvec(a.D2, n, s.x, s.y, false);              // D2 x
+      double2 dw = make_double2(0.0, 0.0), dalp = make_double2(0.0, 0.0);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double2 d2x = s.y[i], xi = s.x[i];
+        const double2 tdw = csub2(csub2(cmul2(cmul2(p.db0, ev), xi), cmul2(coef_d2(p, a.u[i]), d2x)),
+                                  cmul2(coef_d0(p, a.u[i], a.d2u[i]), xi));
+        const double2 tbx = cadd2(cmul2(p.b2, d2x), cmul2(p.b0, xi));
+        dw = cadd2(dw, cmulc2(s.t[i], tdw));
+        dalp = cadd2(dalp, cmulc2(s.t[i], tbx));
+      }
+      dw = block_sum(dw, s.red);
+      dalp = block_sum(dalp, s.red);
+      const double2 q = cdiv2(dw, dalp);
+      const double2 dwda = make_double2(-q.x, -q.y);
+      const double dalpha = -ev.y / dwda.y;
+      const double alpha_now = nalpha;
+      nalpha = alpha_now + a.sfac * dalpha;
+      const double nw = ev.x + a.sfac * dalpha * dwda.x;
+      if (a.trace && threadIdx.x == 0) {
+        double *r = a.trace + ((size_t)inst * a.maxit + it) * 7;
+        r[0] = nalpha; r[1] = ev.x; r[2] = ev.y; r[3] = dwda.x; r[4] = dwda.y; r[5] = dalpha; r[6] = nw;
+      }
+      sigma = make_double2(nw, ev.y);  // next shift: predicted real part (orrncbl.f:907-914 selects near nw)
+      ++it;
+      if (!(isfinite(nalpha) && isfinite(ev.x) && isfinite(ev.y))) { st = OSB_ST_NONFINITE; break; }
+      __syncthreads();
+    }
+    if (fabs(ev.y) <= a.tol) st = OSB_ST_CONVERGED;
+    if (threadIdx.x == 0) {
+      a.alpha_out[inst] = nalpha;
+      a.omega_out[inst] = ev;
+      a.steps[inst] = it;
+      a.status[inst] = st;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------
+struct ChanLaunch {
+  int n;
+  const double *D2, *D4, *u, *d2u;
+};
+
+static cudaError_t chan_grid(int n, int64_t ninst, int *grid, size_t *smem, const void *func) {
+  *smem = chan_smem_bytes(n);
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 0, per = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, func, CH_THREADS, *smem);
+  if (e != cudaSuccess) return e;
+  if (per < 1) return cudaErrorInvalidConfiguration;
+  *grid = (int)std::min<int64_t>(ninst, (int64_t)sms * per);
+  return cudaSuccess;
+}
+
+cudaError_t chan_eig_grid(int n, int64_t ninst, int *grid, size_t *smem) {
+  return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel);
+}
+cudaError_t chan_neutral_grid(int n, int64_t ninst, int *grid, size_t *smem) {
+  return chan_grid(n, ninst, grid, smem, (const void *)chan_neutral_kernel);
+}
+
+cudaError_t launch_chan_eig(int n, const double *D2, const double *D4, const double *u, const double *d2u,
+                            double2 *work, int grid, size_t smem, int64_t ninst, const double2 *alpha,
+                            const double *Re, const double2 *sigma, int outer, int inner, double tol,
+                            double2 *omega, double *delta, int32_t *iters, double2 *evec, cudaStream_t st) {
+  ChanArgs a;
+  a.n = n; a.D2 = D2; a.D4 = D4; a.u = u; a.d2u = d2u; a.work = work; a.ninst = ninst;
+  a.alpha = alpha; a.Re = Re; a.sigma = sigma; a.outer = outer; a.inner = inner; a.tol = tol;
+  a.omega = omega; a.delta = delta; a.iters = iters; a.evec = evec;
+  chan_eig_kernel<<<grid, CH_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_chan_neutral(int n, const double *D2, const double *D4, const double *u, const double *d2u,
+                                double2 *work, int grid, size_t smem, int64_t ninst, const double *Re,
+                                const double *alpha0, const double2 *sigma0, double sfac, double tol, int maxit,
+                                double *alpha_out, double2 *omega_out, int32_t *steps, int32_t *status,
+                                double *trace, cudaStream_t st) {
+  NeutralArgs a;
+  a.n = n; a.D2 = D2; a.D4 = D4; a.u = u; a.d2u = d2u; a.work = work; a.ninst = ninst;
+  a.Re = Re; a.alpha0 = alpha0; a.sigma0 = sigma0; a.sfac = sfac; a.tol = tol; a.maxit = maxit;
+  a.alpha_out = alpha_out; a.omega_out = omega_out; a.steps = steps; a.status = status; a.trace = trace;
+  chan_neutral_kernel<<<grid, CH_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace osb

@@ -137,6 +137,13 @@ void chunk(int64_t n, int ndev, int d, int64_t *lo, int64_t *hi) {
 
 }  // namespace
 
+// accessors for the other translation units of the library
+namespace osb {
+int ctx_fail(osb_ctx *ctx, int code, const std::string &msg) { return fail(ctx, code, msg); }
+int ctx_device(const osb_ctx *ctx, int slot) { return ctx->devices[slot]; }
+void ctx_count_launch(osb_ctx *ctx, int n) { ctx->launches += n; }
+}  // namespace osb
+
 extern "C" {
 
 int osb_version(void) { return OSB_VERSION; }

@@ -1,0 +1,343 @@
+// osb_chan_api.cu -- C ABI of the channel matrix path (include/osb.h, "channel matrix path").
+//
+// Host side of MAKE_CHANNEL_METRICS / INIT_CHANNEL_PROFILE / MAKE_DERIVATIVES: the grid,
+// the profile and D1hat..D4 are formed once per (discretisation, N) with the reference's
+// own loops and summation order (orrfdchan.f:177-183, 235-239, 305-342, 1183-1215;
+// orrcolchan.f:904-944; orrncbl.f:520-545), then the interior blocks are uploaded.
+// Everything per alpha / per Re runs in chan_kernels.cu.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "osb_internal.h"
+
+using namespace osb;
+
+// the context is defined in osb_api.cu; only these accessors are needed here
+extern "C" {
+int osb_device_count(const osb_ctx *ctx);
+void *osb_stream(osb_ctx *ctx);
+}
+namespace osb {
+int ctx_fail(osb_ctx *ctx, int code, const std::string &msg);
+int ctx_device(const osb_ctx *ctx, int slot);
+void ctx_count_launch(osb_ctx *ctx, int n);
+}  // namespace osb
+
+struct osb_chan {
+  int disc = 0, N = 0, n = 0;
+  std::vector<double> eta, u, d1u, d2u, D2full, D4full;  // host copies, full (N+1) grid, row-major (i,j)
+  double *dD2 = nullptr, *dD4 = nullptr, *du = nullptr, *dd2u = nullptr;  // device, interior, column-major
+  int device = 0;
+};
+
+namespace {
+
+#define CH_CUDA(ctx, call)                                                                \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess)                                                               \
+      return ctx_fail((ctx), OSB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + \
+                                             " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+  } while (0)
+
+inline double &at(std::vector<double> &M, int N, int i, int j) { return M[(size_t)i * (N + 1) + j]; }
+inline double at(const std::vector<double> &M, int N, int i, int j) { return M[(size_t)i * (N + 1) + j]; }
+
+// FiniteD1, orrfdchan.f:1183-1215
+void finite_d1(std::vector<double> &D, int N, const std::vector<double> &eta) {
+  std::fill(D.begin(), D.end(), 0.0);
+  at(D, N, 0, 0) = 1. / (eta[0] - eta[1]);
+  at(D, N, 0, 1) = -1. / (eta[0] - eta[1]);
+  at(D, N, N, N - 1) = 1. / (eta[N - 1] - eta[N]);
+  at(D, N, N, N) = -1. / (eta[N - 1] - eta[N]);
+  for (int i = 1; i <= N - 1; ++i) {
+    at(D, N, i, i - 1) = 1. / (eta[i - 1] - eta[i + 1]);
+    at(D, N, i, i + 1) = -1. / (eta[i - 1] - eta[i + 1]);
+  }
+}
+
+// CHEBYD, orrcolchan.f:904-944
+void chebyd(std::vector<double> &D, int N) {
+  const double PI = acos(-1.0), fn = (double)N;
+  std::vector<double> C(N + 1, 1.0);
+  C[0] = 2.0; C[N] = 2.0;
+  for (int j = 0; j <= N; ++j)
+    for (int k = 0; k <= N; ++k) {
+      double v;
+      if (j == 0 && k == 0) v = (2.0 * (fn * fn) + 1.0) / 6.0;
+      else if (j == N && k == N) v = -1.0 * (2. * (fn * fn) + 1.0) / 6.0;
+      else if (j == k) {
+        const double cj = cos((double)j * PI / fn);
+        v = -1.0 * cj / (2. * (1. - cj * cj));
+      } else {
+        const double sgn = ((j + k) % 2 == 0) ? 1.0 : -1.0;
+        v = C[j] * sgn / (C[k] * (cos((double)j * PI / fn) - cos((double)k * PI / fn)));
+      }
+      at(D, N, j, k) = v;
+    }
+}
+
+// D(i,j) = sum_k A(i,k) B(k,j), k ascending (orrfdchan.f:318-342)
+void matmul_ref(std::vector<double> &Cm, const std::vector<double> &A, const std::vector<double> &B, int N) {
+  // B is traversed by column; transpose it once so that the k loop is contiguous
+  // (same products, same summation order as the reference's triple loop)
+  std::vector<double> Bt(B.size());
+  for (int k = 0; k <= N; ++k)
+    for (int j = 0; j <= N; ++j) Bt[(size_t)j * (N + 1) + k] = at(B, N, k, j);
+  for (int i = 0; i <= N; ++i)
+    for (int j = 0; j <= N; ++j) {
+      const double *a = &A[(size_t)i * (N + 1)], *b = &Bt[(size_t)j * (N + 1)];
+      double s = 0.0;
+      for (int k = 0; k <= N; ++k) s = s + a[k] * b[k];
+      at(Cm, N, i, j) = s;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int osb_chan_create(osb_ctx *ctx, int disc, int N, osb_chan **out) {
+  if (!ctx || !out) return OSB_E_ARG;
+  if (disc != OSB_DISC_FD && disc != OSB_DISC_CHEB && disc != OSB_DISC_CHEB_NUM)
+    return ctx_fail(ctx, OSB_E_ARG, "unknown discretisation");
+  if (N < 8 || N > 1024) return ctx_fail(ctx, OSB_E_ARG, "N out of range [8,1024]");
+  if (osb_device_count(ctx) != 1) return ctx_fail(ctx, OSB_E_ARG, "the matrix path takes a single-device context");
+  std::unique_ptr<osb_chan> c(new osb_chan);
+  c->disc = disc; c->N = N; c->n = N - 1; c->device = ctx_device(ctx, 0);
+  const size_t n1 = (size_t)N + 1, nn = n1 * n1;
+  c->eta.resize(n1); c->u.resize(n1); c->d1u.resize(n1); c->d2u.resize(n1);
+  std::vector<double> D1hat(nn), D1(nn), D3(nn);
+  c->D2full.resize(nn); c->D4full.resize(nn);
+  const double pi = acos(-1.0), dth = pi / (double)N;  // orrfdchan.f:177-183
+  for (int i = 0; i <= N; ++i) c->eta[i] = cos((double)i * dth);
+  if (disc == OSB_DISC_FD) { finite_d1(D1hat, N, c->eta); finite_d1(D1, N, c->eta); }
+  else { chebyd(D1hat, N); chebyd(D1, N); }
+  for (int i = 0; i <= N; ++i) { at(D1, N, 0, i) = 0.0; at(D1, N, N, i) = 0.0; }  // phi' = 0
+  matmul_ref(c->D2full, D1hat, D1, N);
+  matmul_ref(D3, D1hat, c->D2full, N);
+  matmul_ref(c->D4full, D1hat, D3, N);
+  for (int i = 0; i <= N; ++i) {  // INIT_CHANNEL_PROFILE
+    c->u[i] = (1. - c->eta[i] * c->eta[i]);
+    c->d1u[i] = -2.0 * c->eta[i];
+    c->d2u[i] = -2.0;
+  }
+  if (disc == OSB_DISC_CHEB_NUM) {  // orrncbl.f:520-545
+    std::vector<double> D2hat(nn);
+    matmul_ref(D2hat, D1hat, D1hat, N);
+    for (int i = 0; i <= N; ++i) {
+      double a = 0.0, b = 0.0;
+      for (int k = 0; k <= N; ++k) { a = a + at(D1hat, N, i, k) * c->u[k]; b = b + at(D2hat, N, i, k) * c->u[k]; }
+      c->d1u[i] = a; c->d2u[i] = b;
+    }
+  }
+  // interior blocks, column-major n x n
+  const int n = c->n;
+  std::vector<double> h2((size_t)n * n), h4((size_t)n * n), hu(n), hd(n);
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) {
+      h2[(size_t)j * n + i] = at(c->D2full, N, i + 1, j + 1);
+      h4[(size_t)j * n + i] = at(c->D4full, N, i + 1, j + 1);
+    }
+  for (int i = 0; i < n; ++i) { hu[i] = c->u[i + 1]; hd[i] = c->d2u[i + 1]; }
+  CH_CUDA(ctx, cudaSetDevice(c->device));
+  CH_CUDA(ctx, cudaMalloc(&c->dD2, h2.size() * sizeof(double)));
+  CH_CUDA(ctx, cudaMalloc(&c->dD4, h4.size() * sizeof(double)));
+  CH_CUDA(ctx, cudaMalloc(&c->du, n * sizeof(double)));
+  CH_CUDA(ctx, cudaMalloc(&c->dd2u, n * sizeof(double)));
+  CH_CUDA(ctx, cudaMemcpy(c->dD2, h2.data(), h2.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CH_CUDA(ctx, cudaMemcpy(c->dD4, h4.data(), h4.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CH_CUDA(ctx, cudaMemcpy(c->du, hu.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  CH_CUDA(ctx, cudaMemcpy(c->dd2u, hd.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  *out = c.release();
+  return OSB_OK;
+}
+
+int osb_chan_free(osb_ctx *ctx, osb_chan *c) {
+  if (!c) return OSB_E_ARG;
+  cudaSetDevice(c->device);
+  cudaFree(c->dD2); cudaFree(c->dD4); cudaFree(c->du); cudaFree(c->dd2u);
+  delete c;
+  (void)ctx;
+  return OSB_OK;
+}
+
+int osb_chan_tables(osb_ctx *ctx, const osb_chan *c, double *eta, double *u, double *d2u, double *D2, double *D4) {
+  if (!c) return OSB_E_ARG;
+  const size_t n1 = (size_t)c->N + 1;
+  if (eta) memcpy(eta, c->eta.data(), n1 * sizeof(double));
+  if (u) memcpy(u, c->u.data(), n1 * sizeof(double));
+  if (d2u) memcpy(d2u, c->d2u.data(), n1 * sizeof(double));
+  if (D2) memcpy(D2, c->D2full.data(), n1 * n1 * sizeof(double));
+  if (D4) memcpy(D4, c->D4full.data(), n1 * n1 * sizeof(double));
+  (void)ctx;
+  return OSB_OK;
+}
+
+// run one batch of instances (alpha, Re, sigma) -> (omega, delta, iters[, evec])
+static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::vector<double> &alpha,
+                   const std::vector<double> &Re, const std::vector<double> &sigma, int outer, int inner,
+                   double tol, std::vector<double> &omega, std::vector<double> &delta,
+                   std::vector<int32_t> &iters, double *evec_host) {
+  cudaStream_t st = (cudaStream_t)osb_stream(ctx);
+  const int n = c->n;
+  int grid = 0;
+  size_t smem = 0;
+  CH_CUDA(ctx, cudaSetDevice(c->device));
+  CH_CUDA(ctx, chan_eig_grid(n, ninst, &grid, &smem));
+  double *d_in = nullptr, *d_out = nullptr;
+  double2 *work = nullptr, *d_evec = nullptr;
+  int32_t *d_it = nullptr;
+  CH_CUDA(ctx, cudaMallocAsync(&d_in, ninst * 5 * sizeof(double), st));   // alpha(2), sigma(2), Re
+  CH_CUDA(ctx, cudaMallocAsync(&d_out, ninst * 3 * sizeof(double), st));  // omega(2), delta
+  CH_CUDA(ctx, cudaMallocAsync(&d_it, ninst * sizeof(int32_t), st));
+  CH_CUDA(ctx, cudaMallocAsync(&work, (size_t)grid * n * n * sizeof(double2), st));
+  if (evec_host) CH_CUDA(ctx, cudaMallocAsync(&d_evec, (size_t)ninst * (n + 2) * sizeof(double2), st));
+  CH_CUDA(ctx, cudaMemcpyAsync(d_in, alpha.data(), ninst * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CH_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * ninst, sigma.data(), ninst * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CH_CUDA(ctx, cudaMemcpyAsync(d_in + 4 * ninst, Re.data(), ninst * sizeof(double), cudaMemcpyHostToDevice, st));
+  CH_CUDA(ctx, launch_chan_eig(n, c->dD2, c->dD4, c->du, c->dd2u, work, grid, smem, ninst,
+                               (const double2 *)d_in, d_in + 4 * ninst, (const double2 *)(d_in + 2 * ninst), outer,
+                               inner, tol, (double2 *)d_out, d_out + 2 * ninst, d_it, d_evec, st));
+  ctx_count_launch(ctx, 1);
+  omega.resize(2 * ninst); delta.resize(ninst); iters.resize(ninst);
+  CH_CUDA(ctx, cudaMemcpyAsync(omega.data(), d_out, ninst * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CH_CUDA(ctx, cudaMemcpyAsync(delta.data(), d_out + 2 * ninst, ninst * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CH_CUDA(ctx, cudaMemcpyAsync(iters.data(), d_it, ninst * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (evec_host)
+    CH_CUDA(ctx, cudaMemcpyAsync(evec_host, d_evec, (size_t)ninst * (n + 2) * sizeof(double2), cudaMemcpyDeviceToHost, st));
+  CH_CUDA(ctx, cudaFreeAsync(d_in, st));
+  CH_CUDA(ctx, cudaFreeAsync(d_out, st));
+  CH_CUDA(ctx, cudaFreeAsync(d_it, st));
+  CH_CUDA(ctx, cudaFreeAsync(work, st));
+  if (d_evec) CH_CUDA(ctx, cudaFreeAsync(d_evec, st));
+  CH_CUDA(ctx, cudaStreamSynchronize(st));
+  return OSB_OK;
+}
+
+// The reference keeps, out of the full spectrum, the least stable mode.  Without the
+// spectrum: 16 shifts sigma = Re(alpha) * c, c = (k + 1/2)/16 on the real c axis, each
+// refined by re-shifted inverse iteration; the converged candidate with the largest
+// Im(omega) (|Im| < 10 as in orrfdchan.f:818; 0 < c_r < 1.1) is kept.
+static const int kScan = 16;
+
+static int scan_shifts(osb_ctx *ctx, const osb_chan *c, int64_t npts, const double *alpha, const double *Re,
+                       std::vector<double> &sigma_out, std::vector<int32_t> &ok) {
+  const int64_t ninst = npts * kScan;
+  std::vector<double> a(2 * ninst), r(ninst), s(2 * ninst), om, dl;
+  std::vector<int32_t> it;
+  for (int64_t p = 0; p < npts; ++p)
+    for (int k = 0; k < kScan; ++k) {
+      const int64_t e = p * kScan + k;
+      a[2 * e] = alpha[2 * p]; a[2 * e + 1] = alpha[2 * p + 1];
+      r[e] = Re[p];
+      s[2 * e] = alpha[2 * p] * ((k + 0.5) / kScan);
+      s[2 * e + 1] = 0.0;
+    }
+  int rc = run_eig(ctx, c, ninst, a, r, s, 3, 6, 1.0e-10, om, dl, it, nullptr);
+  if (rc) return rc;
+  sigma_out.assign(2 * npts, 0.0);
+  ok.assign(npts, 0);
+  for (int64_t p = 0; p < npts; ++p) {
+    double best = -1.0e300;
+    for (int k = 0; k < kScan; ++k) {
+      const int64_t e = p * kScan + k;
+      const double wr = om[2 * e], wi = om[2 * e + 1];
+      if (!(std::isfinite(wr) && std::isfinite(wi))) continue;
+      if (!(dl[e] <= 1.0e-8 * hypot(wr, wi))) continue;   // not settled on one mode
+      if (!(fabs(wi) < 10.0)) continue;
+      const double cr = wr / alpha[2 * p];
+      if (!(cr > 0.0 && cr < 1.1)) continue;
+      if (wi > best) { best = wi; sigma_out[2 * p] = wr; sigma_out[2 * p + 1] = wi; ok[p] = 1; }
+    }
+  }
+  return OSB_OK;
+}
+
+int osb_chan_eig(osb_ctx *ctx, const osb_chan *c, double Re, int64_t npts, const double *alpha,
+                 const double *sigma0, double *omega, double *evec, int32_t *iters, int32_t *status) {
+  if (!ctx || !c || npts < 0 || !alpha || !omega || !status) return ctx_fail(ctx, OSB_E_ARG, "null argument");
+  if (npts == 0) return OSB_OK;
+  std::vector<double> Rev(npts, Re), sig(2 * npts);
+  std::vector<int32_t> ok(npts, 1);
+  if (sigma0) memcpy(sig.data(), sigma0, 2 * npts * sizeof(double));
+  else {
+    int rc = scan_shifts(ctx, c, npts, alpha, Rev.data(), sig, ok);
+    if (rc) return rc;
+  }
+  std::vector<double> a(alpha, alpha + 2 * npts), om, dl;
+  std::vector<int32_t> it;
+  std::vector<double> ev;
+  if (evec) ev.resize((size_t)npts * (c->n + 2) * 2);
+  int rc = run_eig(ctx, c, npts, a, Rev, sig, 4, 8, 1.0e-14, om, dl, it, evec ? ev.data() : nullptr);
+  if (rc) return rc;
+  for (int64_t p = 0; p < npts; ++p) {
+    omega[2 * p] = om[2 * p]; omega[2 * p + 1] = om[2 * p + 1];
+    if (iters) iters[p] = it[p];
+    const bool fin = std::isfinite(om[2 * p]) && std::isfinite(om[2 * p + 1]);
+    const bool conv = fin && dl[p] <= 1.0e-12 * hypot(om[2 * p], om[2 * p + 1]);
+    status[p] = !fin ? OSB_ST_NONFINITE : ((conv && ok[p]) ? OSB_ST_CONVERGED : OSB_ST_MAXCOUNT);
+  }
+  if (evec) memcpy(evec, ev.data(), ev.size() * sizeof(double));
+  return OSB_OK;
+}
+
+int osb_chan_neutral(osb_ctx *ctx, const osb_chan *c, int64_t nRe, const double *Re, const double *alpha0,
+                     double sfac, double tol, int32_t maxit, double *alpha_out, double *omega, int32_t *steps,
+                     int32_t *status, double *trace) {
+  if (!ctx || !c || nRe < 0 || !Re || !alpha0 || !alpha_out || !omega || !steps || !status)
+    return ctx_fail(ctx, OSB_E_ARG, "null argument");
+  if (nRe == 0) return OSB_OK;
+  if (maxit < 1) return ctx_fail(ctx, OSB_E_ARG, "maxit < 1");
+  // first call of the reference: the topmost mode with |w_r| < 1 (orrncbl.f:897-905)
+  std::vector<double> a(2 * nRe), sig;
+  std::vector<int32_t> ok;
+  for (int64_t p = 0; p < nRe; ++p) { a[2 * p] = alpha0[p]; a[2 * p + 1] = 0.0; }
+  int rc = scan_shifts(ctx, c, nRe, a.data(), Re, sig, ok);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)osb_stream(ctx);
+  const int n = c->n;
+  int grid = 0;
+  size_t smem = 0;
+  CH_CUDA(ctx, cudaSetDevice(c->device));
+  CH_CUDA(ctx, chan_neutral_grid(n, nRe, &grid, &smem));
+  double *d_in = nullptr, *d_out = nullptr, *d_trace = nullptr;
+  double2 *work = nullptr;
+  int32_t *d_i = nullptr;
+  CH_CUDA(ctx, cudaMallocAsync(&d_in, nRe * 4 * sizeof(double), st));   // sigma0(2), Re, alpha0
+  CH_CUDA(ctx, cudaMallocAsync(&d_out, nRe * 3 * sizeof(double), st));  // omega(2), alpha
+  CH_CUDA(ctx, cudaMallocAsync(&d_i, nRe * 2 * sizeof(int32_t), st));
+  CH_CUDA(ctx, cudaMallocAsync(&work, (size_t)grid * n * n * sizeof(double2), st));
+  if (trace) {
+    CH_CUDA(ctx, cudaMallocAsync(&d_trace, (size_t)nRe * maxit * 7 * sizeof(double), st));
+    CH_CUDA(ctx, cudaMemsetAsync(d_trace, 0, (size_t)nRe * maxit * 7 * sizeof(double), st));
+  }
+  CH_CUDA(ctx, cudaMemcpyAsync(d_in, sig.data(), nRe * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  CH_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * nRe, Re, nRe * sizeof(double), cudaMemcpyHostToDevice, st));
+  CH_CUDA(ctx, cudaMemcpyAsync(d_in + 3 * nRe, alpha0, nRe * sizeof(double), cudaMemcpyHostToDevice, st));
+  CH_CUDA(ctx, launch_chan_neutral(n, c->dD2, c->dD4, c->du, c->dd2u, work, grid, smem, nRe, d_in + 2 * nRe,
+                                   d_in + 3 * nRe, (const double2 *)d_in, sfac, tol, maxit, d_out + 2 * nRe,
+                                   (double2 *)d_out, d_i, d_i + nRe, d_trace, st));
+  ctx_count_launch(ctx, 1);
+  CH_CUDA(ctx, cudaMemcpyAsync(omega, d_out, nRe * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CH_CUDA(ctx, cudaMemcpyAsync(alpha_out, d_out + 2 * nRe, nRe * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CH_CUDA(ctx, cudaMemcpyAsync(steps, d_i, nRe * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  CH_CUDA(ctx, cudaMemcpyAsync(status, d_i + nRe, nRe * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  if (trace) CH_CUDA(ctx, cudaMemcpyAsync(trace, d_trace, (size_t)nRe * maxit * 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CH_CUDA(ctx, cudaFreeAsync(d_in, st));
+  CH_CUDA(ctx, cudaFreeAsync(d_out, st));
+  CH_CUDA(ctx, cudaFreeAsync(d_i, st));
+  CH_CUDA(ctx, cudaFreeAsync(work, st));
+  if (d_trace) CH_CUDA(ctx, cudaFreeAsync(d_trace, st));
+  CH_CUDA(ctx, cudaStreamSynchronize(st));
+  for (int64_t p = 0; p < nRe; ++p)
+    if (!ok[p] && status[p] == OSB_ST_CONVERGED) status[p] = OSB_ST_MAXCOUNT;
+  return OSB_OK;
+}
+
+}  // extern "C"

@@ -83,6 +83,19 @@ cudaError_t launch_blasius(int variant, int integrator, int nbl, double ymin, do
                            double *d_tables /*[nprof][5][nbl+2]*/, double *d_scratch,
                            double *d_f2p_out, int32_t *d_npass, cudaStream_t st);
 size_t blasius_scratch_doubles(int nbl, int64_t nprof);
+// channel matrix path (chan_kernels.cu)
+size_t chan_smem_bytes(int n);
+cudaError_t chan_eig_grid(int n, int64_t ninst, int *grid, size_t *smem);
+cudaError_t chan_neutral_grid(int n, int64_t ninst, int *grid, size_t *smem);
+cudaError_t launch_chan_eig(int n, const double *D2, const double *D4, const double *u, const double *d2u,
+                            double2 *work, int grid, size_t smem, int64_t ninst, const double2 *alpha,
+                            const double *Re, const double2 *sigma, int outer, int inner, double tol,
+                            double2 *omega, double *delta, int32_t *iters, double2 *evec, cudaStream_t st);
+cudaError_t launch_chan_neutral(int n, const double *D2, const double *D4, const double *u, const double *d2u,
+                                double2 *work, int grid, size_t smem, int64_t ninst, const double *Re,
+                                const double *alpha0, const double2 *sigma0, double sfac, double tol, int maxit,
+                                double *alpha_out, double2 *omega_out, int32_t *steps, int32_t *status,
+                                double *trace, cudaStream_t st);
 cudaError_t launch_fp64_peak(double *d_out, int iters, int blocks, int threads, cudaStream_t st);
 
 }  // namespace osb

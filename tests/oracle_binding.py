@@ -101,3 +101,87 @@ def load(rebuild=True):
     if rebuild or not LIB.exists():
         build()
     return Oracle(C.CDLL(str(LIB)))
+
+
+# ---------------------------------------------------------------- matrix path
+DISC_FD, DISC_CHEB, DISC_CHEB_NUM = 0, 1, 2
+
+
+def _find_openblas():
+    import glob
+    import scipy
+
+    base = Path(scipy.__file__).resolve().parent.parent / "scipy.libs"
+    cands = sorted(glob.glob(str(base / "libscipy_openblas-*.so"))) or sorted(glob.glob(str(base / "libscipy_openblas*.so")))
+    if not cands:
+        raise RuntimeError("scipy's bundled OpenBLAS not found")
+    return cands[0]
+
+
+class ChanOracle:
+    """orrfdchan / orrcolchan / orrncbl restatement (oracle/os_chan_oracle.c)."""
+
+    def __init__(self, lib, disc, n):
+        self.lib = lib
+        self.n = n
+        i, d = C.c_int, C.c_double
+        lib.osr_lapack_open.argtypes = [C.c_char_p]
+        lib.osr_chan_create.restype = C.c_void_p
+        lib.osr_chan_create.argtypes = [i, i]
+        lib.osr_chan_destroy.argtypes = [C.c_void_p]
+        lib.osr_chan_get.argtypes = [C.c_void_p, i, _dp]
+        lib.osr_chan_solve_fdstyle.argtypes = [C.c_void_p, d, d, d, _dp, _dp, _dp]
+        lib.osr_chan_solve_col.argtypes = [C.c_void_p, d, d, d, _dp, i, _dp]
+        lib.osr_chan_neutral.restype = i
+        lib.osr_chan_neutral.argtypes = [C.c_void_p, d, d, d, d, i, _dp]
+        if lib.osr_lapack_open(_find_openblas().encode()) != 0:
+            raise RuntimeError("cannot open LAPACK")
+        self.h = lib.osr_chan_create(disc, n)
+
+    def close(self):
+        if self.h:
+            self.lib.osr_chan_destroy(self.h)
+            self.h = None
+
+    def table(self, which):
+        n1 = self.n + 1
+        out = np.zeros(n1 if which < 4 else n1 * n1)
+        self.lib.osr_chan_get(self.h, which, out.ctypes.data_as(_dp))
+        return out if which < 4 else out.reshape(n1, n1)
+
+    def solve_fd(self, alpha, Re, want_spectrum=False, want_evec=False):
+        alpha = complex(alpha)
+        om = np.zeros(2)
+        spec = np.zeros(2 * (self.n - 1)) if want_spectrum else None
+        ev = np.zeros(2 * (self.n + 1)) if want_evec else None
+        self.lib.osr_chan_solve_fdstyle(self.h, alpha.real, alpha.imag, Re, om.ctypes.data_as(_dp),
+                                        spec.ctypes.data_as(_dp) if want_spectrum else None,
+                                        ev.ctypes.data_as(_dp) if want_evec else None)
+        r = dict(omega=complex(om[0], om[1]))
+        if want_spectrum:
+            r["spectrum"] = spec.view(np.complex128)
+        if want_evec:
+            r["evec"] = ev.view(np.complex128)
+        return r
+
+    def solve_col(self, alpha, Re, which=-1):
+        alpha = complex(alpha)
+        spec = np.zeros(2 * (self.n + 1))
+        ev = np.zeros(2 * (self.n + 1)) if which >= 0 else None
+        self.lib.osr_chan_solve_col(self.h, alpha.real, alpha.imag, Re, spec.ctypes.data_as(_dp), which,
+                                    ev.ctypes.data_as(_dp) if which >= 0 else None)
+        r = dict(spectrum=spec.view(np.complex128))
+        if which >= 0:
+            r["evec"] = ev.view(np.complex128)
+        return r
+
+    def neutral(self, Re, sfac, alpha_r, tol=1.0e-8, maxit=200):
+        tr = np.zeros(7 * maxit)
+        it = self.lib.osr_chan_neutral(self.h, Re, sfac, alpha_r, tol, maxit, tr.ctypes.data_as(_dp))
+        return tr.reshape(maxit, 7)[:it]
+
+
+def chan(disc, n, rebuild=False):
+    if rebuild or not LIB.exists():
+        build()
+    return ChanOracle(C.CDLL(str(LIB)), disc, n)

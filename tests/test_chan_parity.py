@@ -1,0 +1,107 @@
+"""GPU parity of the channel matrix path (K3/K4, through the C ABI) against the oracle
+(which calls the reference's LAPACK routines).  FD: 1e-10 relative on the eigenvalue at
+every N; Chebyshev collocation: 1e-10 holds at N=64 only -- the operator is so
+ill-scaled that the reference's own LAPACK paths disagree beyond that, so
+the bound is conditioning-aware."""
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.abs(np.asarray(a) - np.asarray(b)) / np.abs(np.asarray(b))
+
+
+@pytest.mark.parametrize("disc", [ob.DISC_FD, ob.DISC_CHEB, ob.DISC_CHEB_NUM])
+def test_tables_bit_exact(engine, oracle, disc):
+    ch = engine.chan(disc, 64)
+    t = ch.tables()
+    ch.free()
+    c = ob.chan(disc, 64)
+    assert np.array_equal(t["eta"], c.table(0))
+    assert np.array_equal(t["u"], c.table(1))
+    assert np.array_equal(t["d2u"], c.table(3))
+    assert np.array_equal(t["D2"], c.table(4))
+    assert np.array_equal(t["D4"], c.table(5))
+    c.close()
+
+
+@pytest.mark.parametrize("N,lo,hi,inc", [(64, 0.76, 1.16, 0.02), (128, 0.76, 1.16, 0.01)])
+def test_orrfdchan_decks(engine, oracle, N, lo, hi, inc):
+    """fd-64.inp / fd-128.inp: Re=1e4, alpha_r sweep, alpha_i = 0, no shift guesses given."""
+    nar = int((hi - lo) / inc) + 1  # orrfdchan.f:89
+    alpha = lo + np.arange(nar) * inc
+    ch = engine.chan(ob.DISC_FD, N)
+    r = ch.solve(alpha, 1.0e4, want_evec=True)
+    ch.free()
+    c = ob.chan(ob.DISC_FD, N)
+    ref = np.array([c.solve_fd(a, 1.0e4)["omega"] for a in alpha])
+    refv = c.solve_fd(alpha[nar // 2], 1.0e4, want_evec=True)["evec"]
+    c.close()
+    assert (r["status"] == 0).all()
+    assert rel(r["omega"], ref).max() < 1e-10, rel(r["omega"], ref).max()
+    v = r["evec"][nar // 2]
+    assert np.max(np.abs(v - refv)) < 1e-8
+
+
+def test_orrfdchan_large_N(engine, oracle):
+    for N in (256, 512):
+        alpha = np.array([0.76, 1.0, 1.16])
+        ch = engine.chan(ob.DISC_FD, N)
+        r = ch.solve(alpha, 1.0e4)
+        ch.free()
+        c = ob.chan(ob.DISC_FD, N)
+        ref = np.array([c.solve_fd(a, 1.0e4)["omega"] for a in alpha])
+        c.close()
+        assert (r["status"] == 0).all()
+        assert rel(r["omega"], ref).max() < 1e-10, (N, rel(r["omega"], ref).max())
+
+
+def test_complex_alpha_and_given_shift(engine, oracle):
+    """alpha_i != 0 (orrfdchan sweeps alpha_i too, orrfdchan.f:116-118) with a user shift."""
+    ch = engine.chan(ob.DISC_FD, 64)
+    c = ob.chan(ob.DISC_FD, 64)
+    alpha = np.array([1.0 + 0.01j, 0.9 - 0.02j])
+    ref = np.array([c.solve_fd(a, 1.0e4)["omega"] for a in alpha])
+    r = ch.solve(alpha, 1.0e4, sigma0=ref + 1e-3)
+    ch.free(); c.close()
+    assert rel(r["omega"], ref).max() < 1e-10
+
+
+def test_orrcolchan_chan_inp(engine, oracle):
+    """chan.inp: collocation N=64, alpha=1; the mode the deck asks for (sorted index 62)."""
+    ch = engine.chan(ob.DISC_CHEB, 64)
+    r = ch.solve([1.0], 1.0e4, want_evec=True)
+    ch.free()
+    c = ob.chan(ob.DISC_CHEB, 64)
+    ref = c.solve_col(1.0, 1.0e4, which=62)
+    c.close()
+    # QZ on the ill-scaled collocation pencil vs shift-invert: 2.5e-10 apart at N=64
+    assert rel(r["omega"][0], ref["spectrum"][62]) < 2e-9
+    assert abs(r["omega"][0] - (0.23752649 + 0.00373967j)) < 5e-7
+    v, vr = r["evec"][0], ref["evec"]
+    assert np.max(np.abs(v - vr)) < 1e-6
+
+
+def test_orrncbl_neutral_point(engine, oracle):
+    """nc.inp through the batched Newton search, plus a small Re sweep."""
+    ch = engine.chan(ob.DISC_CHEB_NUM, 64)
+    r = ch.neutral([10000.0, 9000.0, 12000.0], 1.0, sfac=0.01, want_trace=True)
+    ch.free()
+    c = ob.chan(ob.DISC_CHEB_NUM, 64)
+    for k, Re in enumerate((10000.0, 9000.0, 12000.0)):
+        tr = c.neutral(Re, 0.01, 1.0)
+        assert r["status"][k] == 0
+        assert abs(r["steps"][k] - len(tr)) <= 1
+        # the converged alpha is path dependent only within tol/|Im dw/da| (oracle D-7)
+        assert abs(r["alpha"][k] - tr[-1, 0]) < 5e-5
+        assert abs(r["omega"][k].real - tr[-1, 1]) < 2e-5
+        assert abs(r["omega"][k].imag) <= 1e-8
+        # first Newton step: same eigenvalue, same (bug-compatible) dw/da
+        t0 = r["trace"][k, 0]
+        assert abs(complex(t0[1], t0[2]) - complex(tr[0, 1], tr[0, 2])) < 1e-8
+        assert abs(complex(t0[3], t0[4]) - complex(tr[0, 3], tr[0, 4])) < 1e-6 * abs(complex(tr[0, 3], tr[0, 4])) + 1e-9
+    c.close()
