@@ -220,39 +220,57 @@ static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::ve
   return OSB_OK;
 }
 
-// The reference keeps, out of the full spectrum, the least stable mode.  Without the
-// spectrum: 16 shifts sigma = Re(alpha) * c, c = (k + 1/2)/16 on the real c axis, each
-// refined by re-shifted inverse iteration; the converged candidate with the largest
-// Im(omega) (|Im| < 10 as in orrfdchan.f:818; 0 < c_r < 1.1) is kept.
-static const int kScan = 16;
+// The reference keeps ONE eigenvalue out of the full spectrum:
+//   orrfdchan.f:815-823   the largest Im(w) among |Im w| < 10 -- whatever its real part.
+//                         For the FD operator this is sometimes a spurious mode with
+//                         w_r < 0 (e.g. N=64, alpha=0.76: -2.144-0.0027i beats the TS
+//                         mode 0.156-0.0034i), and the drop-in must return the same one.
+//   orrncbl.f:897-905     the topmost mode with |w_r| < 1 (also what chan.inp's index 62
+//                         denotes for orrcolchan: the two Im~3 modes have |w_r| ~ 21).
+// Without the spectrum: a scan of shifts on the real w axis, each refined by re-shifted
+// inverse iteration to its nearest eigenvalue; the settled candidate that the
+// reference's rule would keep is the result.  16 shifts cover 0 < c_r < 1; the FD rule
+// adds 32 shifts over -4 < w_r < 0, the |w_r| < 1 rule adds 8 over -1 < w_r < 0.
+static std::vector<double> scan_list(int disc, double alpha_r) {
+  std::vector<double> s;
+  for (int k = 0; k < 16; ++k) s.push_back(alpha_r * ((k + 0.5) / 16.0));
+  if (disc == OSB_DISC_FD) for (int k = 0; k < 32; ++k) s.push_back(-(k + 0.5) * 0.125);
+  else for (int k = 0; k < 8; ++k) s.push_back(-(k + 0.5) * 0.125);
+  return s;
+}
 
 static int scan_shifts(osb_ctx *ctx, const osb_chan *c, int64_t npts, const double *alpha, const double *Re,
                        std::vector<double> &sigma_out, std::vector<int32_t> &ok) {
-  const int64_t ninst = npts * kScan;
+  const int ns = (int)scan_list(c->disc, 1.0).size();
+  const int64_t ninst = npts * ns;
   std::vector<double> a(2 * ninst), r(ninst), s(2 * ninst), om, dl;
   std::vector<int32_t> it;
-  for (int64_t p = 0; p < npts; ++p)
-    for (int k = 0; k < kScan; ++k) {
-      const int64_t e = p * kScan + k;
+  for (int64_t p = 0; p < npts; ++p) {
+    const std::vector<double> sh = scan_list(c->disc, alpha[2 * p]);
+    for (int k = 0; k < ns; ++k) {
+      const int64_t e = p * ns + k;
       a[2 * e] = alpha[2 * p]; a[2 * e + 1] = alpha[2 * p + 1];
       r[e] = Re[p];
-      s[2 * e] = alpha[2 * p] * ((k + 0.5) / kScan);
+      s[2 * e] = sh[k];
       s[2 * e + 1] = 0.0;
     }
+  }
   int rc = run_eig(ctx, c, ninst, a, r, s, 3, 6, 1.0e-10, om, dl, it, nullptr);
   if (rc) return rc;
   sigma_out.assign(2 * npts, 0.0);
   ok.assign(npts, 0);
   for (int64_t p = 0; p < npts; ++p) {
     double best = -1.0e300;
-    for (int k = 0; k < kScan; ++k) {
-      const int64_t e = p * kScan + k;
+    for (int k = 0; k < ns; ++k) {
+      const int64_t e = p * ns + k;
       const double wr = om[2 * e], wi = om[2 * e + 1];
       if (!(std::isfinite(wr) && std::isfinite(wi))) continue;
-      if (!(dl[e] <= 1.0e-8 * hypot(wr, wi))) continue;   // not settled on one mode
-      if (!(fabs(wi) < 10.0)) continue;
-      const double cr = wr / alpha[2 * p];
-      if (!(cr > 0.0 && cr < 1.1)) continue;
+      if (!(dl[e] <= 1.0e-8 * hypot(wr, wi))) continue;  // not settled on one mode
+      if (c->disc == OSB_DISC_FD) {
+        if (!(fabs(wi) < 10.0) || (int)wr == 999) continue;  // orrfdchan.f:818-819
+      } else {
+        if (!(fabs(wr) < 1.0)) continue;                      // orrncbl.f:898
+      }
       if (wi > best) { best = wi; sigma_out[2 * p] = wr; sigma_out[2 * p + 1] = wi; ok[p] = 1; }
     }
   }

@@ -42,7 +42,13 @@ def test_orrfdchan_decks(engine, oracle, N, lo, hi, inc):
     refv = c.solve_fd(alpha[nar // 2], 1.0e4, want_evec=True)["evec"]
     c.close()
     assert (r["status"] == 0).all()
-    assert rel(r["omega"], ref).max() < 1e-10, rel(r["omega"], ref).max()
+    e = rel(r["omega"], ref)
+    # the reference's rule (largest Im w, |Im w| < 10) sometimes keeps a spurious FD mode with
+    # w_r < 0 (N=64: alpha = 0.76 and 1.16); the GPU path must return the same mode.  Those modes
+    # are ill-conditioned: ZGEEV on inv(B)A and shift-invert on the pencil agree to ~1e-10 only.
+    phys = ref.real > 0
+    assert e[phys].max() < 1e-12, e[phys].max()
+    assert e.max() < 1e-9, e.max()
     v = r["evec"][nar // 2]
     assert np.max(np.abs(v - refv)) < 1e-8
 
@@ -68,7 +74,8 @@ def test_complex_alpha_and_given_shift(engine, oracle):
     ref = np.array([c.solve_fd(a, 1.0e4)["omega"] for a in alpha])
     r = ch.solve(alpha, 1.0e4, sigma0=ref + 1e-3)
     ch.free(); c.close()
-    assert rel(r["omega"], ref).max() < 1e-10
+    e = rel(r["omega"], ref)
+    assert e[ref.real > 0].max() < 1e-12 and e.max() < 1e-9  # ref[0] is the spurious w_r < 0 mode
 
 
 def test_orrcolchan_chan_inp(engine, oracle):
