@@ -18,6 +18,9 @@
 //   Newton on alpha (orrncbl) runs inside the kernel, one CTA per Re, including the
 //       reference's use of the LEFT eigenvector of inv(B)A (oracle D-7), obtained as
 //       vl = B^H u with u from inverse iteration on (A - sigma B)^H.
+#include <stdio.h>
+#include <string.h>
+
 #include "osb_cplx.cuh"
 #include "osb_internal.h"
 
@@ -25,6 +28,20 @@ namespace osb {
 
 constexpr int CH_THREADS = 256;
 constexpr int CH_NB = 16;
+
+// optional phase timers (cycles of block 0, thread 0); read back when OSB_CHAN_PROFILE is set
+__device__ long long g_chan_prof[8];
+#define PROF_T0() long long prof_t0 = clock64()
+#define PROF_ADD(slot)                                                        \
+  do {                                                                        \
+    if (blockIdx.x == 0 && threadIdx.x == 0) {                                \
+      long long t1 = clock64();                                               \
+      g_chan_prof[slot] += t1 - prof_t0;                                      \
+      prof_t0 = t1;                                                           \
+    } else {                                                                  \
+      prof_t0 = 0;                                                            \
+    }                                                                         \
+  } while (0)
 
 __device__ __forceinline__ double2 cmul2(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -125,6 +142,7 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
   int *red_i = (int *)(red + 2 * (CH_THREADS / 32));
   for (int k0 = 0; k0 < n; k0 += CH_NB) {
     const int nb = min(CH_NB, n - k0), mp = n - k0;
+    PROF_T0();
     // ---- stage the panel
     for (int e = tid; e < mp * nb; e += nt) {
       const int r = e % mp, c = e / mp;
@@ -177,6 +195,7 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
       }
       __syncthreads();
     }
+    PROF_ADD(1);
     // ---- row interchanges on the columns outside the panel; write the panel back
     for (int c = tid; c < n; c += nt) {
       if (c >= k0 && c < k0 + nb) continue;
@@ -191,6 +210,7 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
       M[(size_t)(k0 + c) * n + k0 + r] = panel[c * ldp + r];
     }
     __syncthreads();
+    PROF_ADD(2);
     const int mt = n - k0 - nb;  // trailing size
     if (mt <= 0) break;
     // ---- U12 = L11^{-1} A12  (unit lower L11 from the panel), one thread per column
@@ -212,6 +232,7 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
       for (int i = 0; i < CH_NB; ++i) if (i < nb) col[i] = a[i];
     }
     __syncthreads();
+    PROF_ADD(3);
     // ---- trailing update A22 -= L21 U12 on the FP64 tensor path; a warp owns 16x16 blocks
     if (nb == CH_NB) {
       const int g = lane >> 2, t4 = lane & 3;
@@ -269,6 +290,7 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
       }
     }
     __syncthreads();
+    PROF_ADD(4);
   }
 }
 
@@ -406,12 +428,15 @@ __device__ double2 inverse_iterate(const double2 *M, int n, const double *D2, co
   double dl = 1.0e300;
   int it = 0;
   for (; it < maxit; ++it) {
+    PROF_T0();
     // y = B x = b2 D2 x + b0 x
     cta_d2_matvec(D2, n, s.x, s.y, false);
     for (int i = threadIdx.x; i < n; i += blockDim.x)
       s.y[i] = cadd2(cmul2(p.b2, s.y[i]), cmul2(p.b0, s.x[i]));
     __syncthreads();
+    PROF_ADD(5);
     cta_solve(M, n, s.ipiv, s.y);
+    PROF_ADD(6);
     double2 yx = make_double2(0.0, 0.0), yy = make_double2(0.0, 0.0);
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
       yx = cadd2(yx, cmulc2(s.y[i], s.x[i]));
@@ -470,7 +495,9 @@ __global__ void __launch_bounds__(CH_THREADS) chan_eig_kernel(const __grid_const
     double dl = 1.0e300;
     int total = 0;
     for (int o = 0; o < a.outer; ++o) {
+      PROF_T0();
       assemble_shifted(M, n, a.D2, a.D4, a.u, a.d2u, p, sigma);
+      PROF_ADD(0);
       cta_lu(M, n, s.ipiv, s.panel, s.red);
       int it = 0;
       om = inverse_iterate(M, n, a.D2, p, sigma, s, a.inner, a.tol, &dl, &it);
@@ -630,6 +657,19 @@ static cudaError_t chan_grid(int n, int64_t ninst, int *grid, size_t *smem, cons
   if (per < 1) return cudaErrorInvalidConfiguration;
   *grid = (int)std::min<int64_t>(ninst, (int64_t)sms * per);
   return cudaSuccess;
+}
+
+void chan_profile_dump(const char *tag) {
+  long long h[8];
+  if (cudaMemcpyFromSymbol(h, g_chan_prof, sizeof(h)) != cudaSuccess) return;
+  const char *names[8] = {"assemble", "panel", "swap+writeback", "U12", "trailing(DMMA)", "B x", "solve", "-"};
+  double tot = 0;
+  for (int i = 0; i < 7; ++i) tot += (double)h[i];
+  fprintf(stderr, "[osb chan profile %s] block 0 cycles:", tag);
+  for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.1f%%", names[i], tot > 0 ? 100.0 * h[i] / tot : 0.0);
+  fprintf(stderr, " total=%.3g\n", tot);
+  memset(h, 0, sizeof(h));
+  cudaMemcpyToSymbol(g_chan_prof, h, sizeof(h));
 }
 
 cudaError_t chan_eig_grid(int n, int64_t ninst, int *grid, size_t *smem) {

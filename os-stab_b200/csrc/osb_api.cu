@@ -168,6 +168,13 @@ int osb_create_multi(osb_ctx **out, int ndev, const int *devices) {
     cudaStream_t s;
     if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return OSB_E_CUDA;
     c->streams.push_back(s);
+    // keep stream-ordered allocations cached between calls (the default pool hands
+    // memory back to the driver at every synchronisation)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) {
+      uint64_t keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
   }
   *out = c.release();
   return OSB_OK;

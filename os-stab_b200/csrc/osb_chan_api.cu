@@ -6,6 +6,7 @@
 // orrcolchan.f:904-944; orrncbl.f:520-545), then the interior blocks are uploaded.
 // Everything per alpha / per Re runs in chan_kernels.cu.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -217,6 +218,7 @@ static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::ve
   CH_CUDA(ctx, cudaFreeAsync(work, st));
   if (d_evec) CH_CUDA(ctx, cudaFreeAsync(d_evec, st));
   CH_CUDA(ctx, cudaStreamSynchronize(st));
+  if (getenv("OSB_CHAN_PROFILE")) chan_profile_dump("eig");
   return OSB_OK;
 }
 

@@ -85,6 +85,7 @@ cudaError_t launch_blasius(int variant, int integrator, int nbl, double ymin, do
 size_t blasius_scratch_doubles(int nbl, int64_t nprof);
 // channel matrix path (chan_kernels.cu)
 size_t chan_smem_bytes(int n);
+void chan_profile_dump(const char *tag);
 cudaError_t chan_eig_grid(int n, int64_t ninst, int *grid, size_t *smem);
 cudaError_t chan_neutral_grid(int n, int64_t ninst, int *grid, size_t *smem);
 cudaError_t launch_chan_eig(int n, const double *D2, const double *D4, const double *u, const double *d2u,
