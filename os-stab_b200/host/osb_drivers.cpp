@@ -1,0 +1,658 @@
+// osb_drivers.cpp -- C++ twin drivers of the reference's programs over the C ABI.
+//
+//   osb_drivers contebl | conte | orrsom | orrspace | orrfdchan | orrcolchan | orrncbl
+//
+// Each twin reads the same stdin (prompts, "key = value" decks, list-directed numbers),
+// echoes the same text and writes the same fort.N / <root>.g/.dat/.q files as the
+// Fortran program of that name; the only thing that changes is where the work is done:
+// `call SOLVE_BL`, `call CONTE_IC/CONTE`, `call MAKE_MATRIX + SOLVE_ORR_SOM` become the
+// libosb.so entry points that INTEGRATION.md binds for the Fortran hosts.  (No Fortran
+// compiler exists in this image; these twins are how the host layer is exercised.)
+//
+// Known, documented deviations from the reference's text:
+//   * columns 4-5 of the per-pass table (err) agree in modulus only; their phase is a
+//     rounding artefact of the reference's arithmetic;
+//   * orrcolchan prints the table row of the mode the GPU path isolates (the TS mode,
+//     sorted index 62 of chan.inp) instead of the whole QZ spectrum;
+//   * gfortran's list-directed `write(*,*)` spacing (orrncbl.f:902, orrcolchan.f:539,546)
+//     is not reproduced.
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/osb.h"
+#include "fortfmt.hpp"
+
+using fortfmt::E;
+using fortfmt::ES;
+using fortfmt::I;
+typedef std::complex<double> cd;
+
+static void die(osb_ctx *ctx, const char *what, int rc) {
+  fprintf(stderr, "osb_drivers: %s failed (%d): %s\n", what, rc, ctx ? osb_last_error(ctx) : "");
+  exit(2);
+}
+#define CK(ctx, call)                 \
+  do {                                \
+    int rc__ = (call);                \
+    if (rc__) die((ctx), #call, rc__); \
+  } while (0)
+
+static std::string getline80() {
+  std::string s;
+  if (!std::getline(std::cin, s)) s.clear();
+  return s;
+}
+
+// ---- deck (contebl.f:122-149): skip leading '#' lines, then positional "key = value" lines
+struct Deck {
+  std::ifstream f;
+  bool first = true;
+  bool open(const std::string &name) { f.open(name); return (bool)f; }
+  std::string next_line() {
+    std::string s;
+    if (first) {
+      first = false;
+      do { if (!std::getline(f, s)) return ""; } while (!s.empty() && s[0] == '#');
+      return s;
+    }
+    std::getline(f, s);
+    return s;
+  }
+  static void input_error() { printf("\n\n ERROR in input file...\n\n\n"); exit(0); }  // contebl.f:586-588
+  long long geti() {
+    std::string fld;
+    long long v = 0;
+    if (!fortfmt::deck_field(next_line(), fld) || !fortfmt::read_I10(fld, v)) input_error();
+    return v;
+  }
+  double getr() {
+    std::string fld;
+    double v = 0;
+    if (!fortfmt::deck_field(next_line(), fld) || !fortfmt::read_G20_10(fld, v)) input_error();
+    return v;
+  }
+};
+
+// SPDER (shoot.f:1037-1101) on the host, only to print fort.10 from the tables
+static int interval(const std::vector<double> &X, double xx) {
+  const int N = (int)X.size();
+  if (xx == X[0]) return 1;
+  if (xx == X[N - 1]) return N;
+  int il = 0, ir = N - 1;
+  while (ir - il > 1) { int im = (ir + il) >> 1; if (X[im] > xx) ir = im; else il = im; }
+  return il + 1;
+}
+static void spder(const std::vector<double> &X, const std::vector<double> &Y, const std::vector<double> &F, double xx,
+                  double &f, double &fpp) {
+  const int N = (int)X.size();
+  const int Ii = interval(X, xx);
+  auto x = [&](int i) { return i <= N ? X[i - 1] : 0.0; };  // one element past the table reads COMMON zeros
+  auto y = [&](int i) { return i <= N ? Y[i - 1] : 0.0; };
+  auto d = [&](int i) { return i <= N ? F[i - 1] : 0.0; };
+  const double DXM = xx - x(Ii), DXP = x(Ii + 1) - xx, DEL = x(Ii + 1) - x(Ii);
+  f = d(Ii) * DXP * (DXP * DXP / DEL - DEL) / 6.0 + d(Ii + 1) * DXM * (DXM * DXM / DEL - DEL) / 6.0 + y(Ii) * DXP / DEL +
+      y(Ii + 1) * DXM / DEL;
+  fpp = d(Ii) * DXP / DEL + d(Ii + 1) * DXM / DEL;
+}
+static double speval_linear(const std::vector<double> &X, const std::vector<double> &Y, const std::vector<double> &F, double xx) {
+  const int N = (int)X.size();
+  int Ii = N;
+  for (int i = 1; i <= N - 1; ++i) if (xx <= X[i]) { Ii = i; break; }
+  auto x = [&](int i) { return i <= N ? X[i - 1] : 0.0; };
+  auto y = [&](int i) { return i <= N ? Y[i - 1] : 0.0; };
+  auto d = [&](int i) { return i <= N ? F[i - 1] : 0.0; };
+  const double DXM = xx - x(Ii), DXP = x(Ii + 1) - xx, DEL = x(Ii + 1) - x(Ii);
+  return d(Ii) * DXP * (DXP * DXP / DEL - DEL) / 6.0 + d(Ii + 1) * DXM * (DXM * DXM / DEL - DEL) / 6.0 + y(Ii) * DXP / DEL +
+         y(Ii + 1) * DXM / DEL;
+}
+
+struct Tables {
+  std::vector<double> ydat, U, Uspl, d2U, d2Uspl;
+};
+static Tables fetch_tables(osb_ctx *ctx, osb_profile *prof, int nbl) {
+  Tables t;
+  t.ydat.resize(nbl + 1); t.U.resize(nbl + 1); t.Uspl.resize(nbl + 1); t.d2U.resize(nbl + 1); t.d2Uspl.resize(nbl + 1);
+  int32_t np = 0;
+  double f2 = 0;
+  CK(ctx, osb_profile_get(ctx, prof, t.ydat.data(), t.U.data(), t.Uspl.data(), t.d2U.data(), t.d2Uspl.data(), &np, &f2));
+  return t;
+}
+
+// fort.11-14 (shoot.f:802-809): t, Re(y_i/vmax), Im(y_i/vmax)
+static void write_eigfun(const std::vector<double> &y, cd vmax, int nstep, double tf, double to, double h, bool bl,
+                         int wES, bool lead1x, double tscale = 1.0) {
+  for (int comp = 0; comp < 4; ++comp) {
+    char name[32];
+    snprintf(name, sizeof name, "fort.%d", 11 + comp);
+    FILE *f = fopen(name, "w");
+    for (int k = 0; k <= nstep; ++k) {
+      const double t = (bl ? tf - h * k : to + h * k) * tscale;
+      const cd v = cd(y[2 * (4 * k + comp)], y[2 * (4 * k + comp) + 1]) / vmax;
+      fprintf(f, "%s%s %s %s \n", lead1x ? " " : "", ES(t, wES, 8, 3).c_str(), ES(v.real(), wES, 8, 3).c_str(),
+              ES(v.imag(), wES, 8, 3).c_str());
+    }
+    fclose(f);
+  }
+}
+
+// ---------------------------------------------------------------- contebl
+static int run_contebl(osb_ctx *ctx) {
+  int nbl = 1000, nstep = 1000;  // contebl.f:64-83
+  double testalpha = 10.0, Re = 580., beta = 0.0, alphar = 0.179, alphai = 0.0;
+  double cr = 0.36413124E+00, ci = 0.79527387E-02, ymin = 0.0, ymax = 17.0, f2p = 0.5;
+  const bool eigfun = true;
+  printf("\n          Solve Orr-Sommerfeld for Boundary Layer using shooting\n\n");
+  printf("\n Read from keyboard, file, default (k,f,d) ==> ");
+  fflush(stdout);
+  const std::string input = getline80();
+  const char ch = input.empty() ? ' ' : input[0];
+  if (ch == 'k' || ch == 'K') {
+    printf("\n Enter number of steps for BL solve ==> "); std::cin >> nbl;
+    printf("\n Enter number of steps for shooting ==> "); std::cin >> nstep;
+    printf("\n Enter Reynolds number ==> "); std::cin >> Re;
+    printf("\n Enter beta ==> "); std::cin >> beta;
+    printf("\n Enter alpha_r ==> "); std::cin >> alphar;
+    printf("\n Enter alpha_i ==> "); std::cin >> alphai;
+    printf("\n Enter guess for (c_r, c_i) ==> "); std::cin >> cr >> ci;
+    printf("\n Enter Ymin and Ymax ==> "); std::cin >> ymin >> ymax;
+  } else if (ch == 'f' || ch == 'F') {
+    printf("\n Enter filename ==> ");
+    fflush(stdout);
+    std::string infile = getline80();
+    while (!infile.empty() && infile.back() == ' ') infile.pop_back();
+    Deck d;
+    if (!d.open(infile)) { printf("\n\n Error in input file...\n\n\n"); return 0; }
+    nbl = (int)d.geti(); nstep = (int)d.geti(); testalpha = d.getr(); Re = d.getr(); beta = d.getr(); f2p = d.getr();
+    alphar = d.getr(); alphai = d.getr(); cr = d.getr(); ci = d.getr(); ymin = d.getr(); ymax = d.getr();
+  }
+  printf("\n nbl = %s\n", I(nbl, 5).c_str());
+  printf(" nstep = %s\n", I(nstep, 5).c_str());
+  printf(" Test Alpha = %s\n", E(testalpha, 20, 10).c_str());
+  printf(" Re = %s\n", E(Re, 20, 10).c_str());
+  printf(" Beta = %s\n", E(beta, 20, 10).c_str());
+  printf(" f2p = %s\n", E(f2p, 20, 10).c_str());
+  printf(" Ymin = %s  Ymax = %s\n", E(ymin, 20, 10).c_str(), E(ymax, 20, 10).c_str());
+  printf(" alpha = (%s, %s)\n", E(alphar, 20, 10).c_str(), E(alphai, 20, 10).c_str());
+  printf(" c = (%s, %s)\n\n", E(cr, 20, 10).c_str(), E(ci, 20, 10).c_str());
+  cd alpha(alphar, alphai), c(cr, ci);
+  const double hbl = (ymax - ymin) / (double)nbl;
+  Re = Re * std::sqrt(2.);  // contebl.f:181-182
+  alpha = alpha * std::sqrt(2.);
+  if (nbl > 50000) { printf("\n\n N > Idim...Stopping\n\n\n"); return 0; }
+  // call SOLVE_BL  (contebl.f:196)
+  osb_profile *prof = nullptr;
+  CK(ctx, osb_profile_blasius(ctx, OSB_FLOW_CONTEBL, OSB_INT_CK45, nbl, ymin, ymax, f2p, beta, &prof));
+  const Tables t = fetch_tables(ctx, prof, nbl);
+  {
+    FILE *f = fopen("fort.10", "w");  // contebl.f:511-526
+    for (int i = 0; i <= nbl; ++i) {
+      const double y = ymin + i * hbl;
+      double us, d2us;
+      spder(t.ydat, t.U, t.Uspl, y, us, d2us);
+      fprintf(f, " %s %s %s %s %s \n", ES(y, 16, 8, 3).c_str(), ES(us, 16, 8, 3).c_str(), ES(d2us, 16, 8, 3).c_str(),
+              ES(t.U[i], 16, 8, 3).c_str(), ES(t.d2U[i], 16, 8, 3).c_str());
+    }
+    fclose(f);
+  }
+  printf(" Blasius velocity profile completed...\n\n");
+  // call CONTE_IC(...)  (contebl.f:205)
+  osb_shoot_opts o;
+  CK(ctx, osb_shoot_defaults(OSB_FLOW_CONTEBL, &o));
+  o.nstep = nstep; o.testalpha = testalpha; o.ymin = ymin; o.ymax = ymax;
+  double al[2] = {alpha.real(), alpha.imag()}, cc[2] = {c.real(), c.imag()}, resid[2], hist[4 * 20];
+  int32_t passes, qend, status;
+  CK(ctx, osb_shoot_temporal(ctx, &o, prof, 1, al, &Re, cc, &passes, &qend, &status, resid, hist, 20));
+  for (int i = 0; i < passes && i < 20; ++i)  // shoot.f:745-747
+    printf(" %s%s%s   %s%s   \n", I(i + 1, 4).c_str(), E(hist[4 * i], 17, 8).c_str(), E(hist[4 * i + 1], 17, 8).c_str(),
+           E(hist[4 * i + 2], 17, 8).c_str(), E(hist[4 * i + 3], 17, 8).c_str());
+  printf("\nEigenvalue = %s %s  %s\n\n", E(cc[0], 17, 8).c_str(), E(cc[1], 17, 8).c_str(), I(qend, 5).c_str());
+  printf("  Eigenvalue iterations = %s\n  |error| = %s\n  |c-cm1| = %s\n\n", I(passes, 5).c_str(),
+         ES(resid[0], 17, 8).c_str(), ES(resid[1], 17, 8).c_str());
+  if (eigfun) {
+    std::vector<double> y((size_t)(nstep + 1) * 8);
+    double vmax[2];
+    int32_t q2;
+    CK(ctx, osb_eigfun(ctx, &o, prof, 1, al, &Re, cc, nullptr, y.data(), vmax, &q2));
+    write_eigfun(y, cd(vmax[0], vmax[1]), nstep, ymax, ymin, (ymax - ymin) / nstep, true, 16, true);
+  }
+  osb_profile_free(ctx, prof);
+  return status;
+}
+
+// ---------------------------------------------------------------- conte
+static int run_conte(osb_ctx *ctx) {
+  int n = 2000;  // conte.f:61-68
+  double Re = 10000.0, alphar = 1.0, alphai = 0.0, cr = 0.23753, ci = 0.00374, ymin = -1.0, ymax = 1.0;
+  printf("\n          Solve Orr-Sommerfeld for Channel using shooting\n\n");
+  printf("\n Read from keyboard, file, default (k,d) ==> ");
+  fflush(stdout);
+  const std::string input = getline80();
+  const char ch = input.empty() ? ' ' : input[0];
+  if (ch == 'k' || ch == 'K') {
+    printf("\n Enter number of steps ==> "); std::cin >> n;
+    printf("\n Enter Reynolds number ==> "); std::cin >> Re;
+    printf("\n Enter alpha_r ==> "); std::cin >> alphar;
+    printf("\n Enter alpha_i ==> "); std::cin >> alphai;
+    printf("\n Enter guess for (c_r, c_i) ==> "); std::cin >> cr >> ci;
+  }
+  printf("\n n = %s\n", I(n, 5).c_str());
+  printf(" Re = %s\n", E(Re, 20, 10).c_str());
+  printf(" alpha = (%s, %s)\n", E(alphar, 20, 10).c_str(), E(alphai, 20, 10).c_str());
+  printf(" c = (%s, %s)\n\n", E(cr, 20, 10).c_str(), E(ci, 20, 10).c_str());
+  const double h = (ymax - ymin) / (double)n;
+  if (n > 10000) { printf("\n\n N > Idim...Stopping\n\n\n"); return 0; }
+  {
+    FILE *f = fopen("fort.10", "w");  // conte.f:288-294: 2x resolved mesh
+    for (int i = 0; i <= 2 * n; ++i) {
+      const double y = ymin + i * h / 2.0;
+      fprintf(f, " %s %s %s \n", ES(y, 16, 8, 3).c_str(), ES(1.0 - y * y, 16, 8, 3).c_str(), ES(-2.0, 16, 8, 3).c_str());
+    }
+    fclose(f);
+  }
+  printf(" Channel velocity profile completed...\n\n");
+  osb_profile *prof = nullptr;
+  CK(ctx, osb_profile_channel(ctx, &prof));
+  osb_shoot_opts o;
+  CK(ctx, osb_shoot_defaults(OSB_FLOW_CONTE, &o));
+  o.nstep = n; o.ymin = ymin; o.ymax = ymax;
+  double al[2] = {alphar, alphai}, cc[2] = {cr, ci}, resid[2], hist[4 * 21];
+  int32_t passes, qend, status;
+  CK(ctx, osb_shoot_temporal(ctx, &o, prof, 1, al, &Re, cc, &passes, &qend, &status, resid, hist, 21));
+  for (int i = 0; i < passes && i < 21; ++i)  // shoot.f:322-323 (shows the UPDATED c)
+    printf(" %s %s %s    %s %s   \n", I(i + 1, 4).c_str(), ES(hist[4 * i], 16, 8, 3).c_str(), ES(hist[4 * i + 1], 16, 8, 3).c_str(),
+           ES(hist[4 * i + 2], 16, 8, 3).c_str(), ES(hist[4 * i + 3], 16, 8, 3).c_str());
+  printf("\nEigenvalue = %s %s  %s\n\n", E(cc[0], 17, 8, 3).c_str(), E(cc[1], 17, 8, 3).c_str(), I(qend, 5).c_str());
+  // conte does not decrement icount before printing (shoot.f:332)
+  printf("  Eigenvalue iterations = %s\n  |error| = %s\n  |c-cm1| = %s\n\n", I(passes + 1, 5).c_str(),
+         ES(resid[0], 17, 8, 3).c_str(), ES(resid[1], 17, 8, 3).c_str());
+  std::vector<double> y((size_t)(n + 1) * 8);
+  double vmax[2];
+  int32_t q2;
+  CK(ctx, osb_eigfun(ctx, &o, prof, 1, al, &Re, cc, nullptr, y.data(), vmax, &q2));
+  write_eigfun(y, cd(vmax[0], vmax[1]), n, ymax, ymin, h, false, 16, true);
+  osb_profile_free(ctx, prof);
+  return status;
+}
+
+// ---------------------------------------------------------------- orrsom (deck on stdin, orrsom.f:63-91)
+struct StdinDeck {
+  bool first = true;
+  std::string next_line() {
+    std::string s;
+    if (first) {
+      first = false;
+      do { if (!std::getline(std::cin, s)) return ""; } while (!s.empty() && s[0] == '#');
+      return s;
+    }
+    std::getline(std::cin, s);
+    return s;
+  }
+  long long geti() {
+    std::string fld; long long v = 0;
+    if (!fortfmt::deck_field(next_line(), fld) || !fortfmt::read_I10(fld, v)) Deck::input_error();
+    return v;
+  }
+  double getr() {
+    std::string fld; double v = 0;
+    if (!fortfmt::deck_field(next_line(), fld) || !fortfmt::read_G20_10(fld, v)) Deck::input_error();
+    return v;
+  }
+};
+
+static int run_orrsom(osb_ctx *ctx) {
+  printf("\n          Solve Orr-Sommerfeld (Shooting) Temporal Problem\n\n");
+  StdinDeck d;
+  const int n = (int)d.geti(), nstep = (int)d.geti();
+  const double testalpha = d.getr();
+  double Re = d.getr();
+  const double beta = d.getr(), f2p = d.getr(), alphar = d.getr(), alphai = d.getr(), cr = d.getr(), ci = d.getr(),
+               ymin = d.getr(), ymax = d.getr();
+  printf("\n n = %s\n", I(n, 5).c_str());
+  printf(" nstep = %s\n", I(nstep, 5).c_str());
+  printf(" Test Alpha = %s\n", E(testalpha, 20, 10).c_str());
+  printf(" Re = %s\n", E(Re, 20, 10).c_str());
+  printf(" Beta = %s\n", E(beta, 20, 10).c_str());
+  printf(" f2p = %s\n", E(f2p, 20, 10).c_str());
+  printf(" Ymin = %s  Ymax = %s\n", E(ymin, 20, 10).c_str(), E(ymax, 20, 10).c_str());
+  printf(" alpha = (%s, %s)\n", E(alphar, 20, 10).c_str(), E(alphai, 20, 10).c_str());
+  printf(" c = (%s, %s)\n\n", E(cr, 20, 10).c_str(), E(ci, 20, 10).c_str());
+  cd alpha(alphar, alphai);
+  const double h = (ymax - ymin) / (double)n;
+  Re = Re * std::sqrt(2.);  // orrsom.f:129-130
+  alpha = alpha * std::sqrt(2.);
+  if (n > 20000) { printf("\n\n N > Idim...Stopping\n\n\n"); return 0; }
+  osb_profile *prof = nullptr;
+  CK(ctx, osb_profile_blasius(ctx, OSB_FLOW_ORRSOM, OSB_INT_RK4, n, ymin, ymax, f2p, beta, &prof));
+  const Tables t = fetch_tables(ctx, prof, n);
+  {
+    FILE *f = fopen("fort.10", "w");  // orrsom.f:790-797
+    for (int i = 0; i <= n; ++i) {
+      const double y = ymin + i * h;
+      const double us = speval_linear(t.ydat, t.U, t.Uspl, y), d2us = speval_linear(t.ydat, t.d2U, t.d2Uspl, y);
+      fprintf(f, " %s %s %s %s %s \n", ES(y, 20, 12, 3).c_str(), ES(us, 20, 12, 3).c_str(), ES(d2us, 20, 12, 3).c_str(),
+              ES(t.U[i], 20, 12, 3).c_str(), ES(t.d2U[i], 20, 12, 3).c_str());
+    }
+    fclose(f);
+  }
+  printf(" Velocity Profile completed...\n\n");
+  osb_shoot_opts o;
+  CK(ctx, osb_shoot_defaults(OSB_FLOW_ORRSOM, &o));
+  o.nstep = nstep; o.testalpha = testalpha; o.ymin = ymin; o.ymax = ymax;
+  double al[2] = {alpha.real(), alpha.imag()}, cc[2] = {cr, ci}, resid[2], hist[4 * 20];
+  int32_t passes, qend, status;
+  CK(ctx, osb_shoot_temporal(ctx, &o, prof, 1, al, &Re, cc, &passes, &qend, &status, resid, hist, 20));
+  for (int i = 0; i < passes && i < 20; ++i)  // orrsom.f:442-444
+    printf(" %s%s%s   %s%s   \n", I(i + 1, 4).c_str(), E(hist[4 * i], 17, 8).c_str(), E(hist[4 * i + 1], 17, 8).c_str(),
+           E(hist[4 * i + 2], 17, 8).c_str(), E(hist[4 * i + 3], 17, 8).c_str());
+  printf("\nEigenvalue = %s %s  %s\n\n", E(cc[0], 17, 8).c_str(), E(cc[1], 17, 8).c_str(), I(qend, 5).c_str());
+  printf("Second pass: computing and writing eigenfunction\n");
+  std::vector<double> y((size_t)(nstep + 1) * 8);
+  double vmax[2];
+  int32_t q2;
+  CK(ctx, osb_eigfun(ctx, &o, prof, 1, al, &Re, cc, nullptr, y.data(), vmax, &q2));
+  const cd vm(vmax[0], vmax[1]);
+  write_eigfun(y, vm, nstep, ymax, ymin, (ymax - ymin) / nstep, true, 17, true);
+  {
+    FILE *f = fopen("fort.15", "w");  // orrsom.f:500: t, Re(phi'/max), Re(-i alpha phi/max)
+    const double hh = (ymax - ymin) / nstep;
+    for (int k = 0; k <= nstep; ++k) {
+      const cd y1(y[2 * (4 * k)], y[2 * (4 * k) + 1]), y2(y[2 * (4 * k + 1)], y[2 * (4 * k + 1) + 1]);
+      fprintf(f, " %s %s %s \n", ES(ymax - hh * k, 17, 8, 3).c_str(), ES((y2 / vm).real(), 17, 8, 3).c_str(),
+              ES((cd(0., -1.) * alpha * y1 / vm).real(), 17, 8, 3).c_str());
+    }
+    fclose(f);
+  }
+  osb_profile_free(ctx, prof);
+  return status;
+}
+
+// ---------------------------------------------------------------- orrspace
+static int run_orrspace(osb_ctx *ctx) {
+  printf("\n          Solve Orr-Sommerfeld (Shooting)\n\n");
+  printf("     This version solves the spatial problem\n\n");
+  printf("\n Enter filename ==> ");
+  fflush(stdout);
+  std::string infile = getline80();
+  while (!infile.empty() && infile.back() == ' ') infile.pop_back();
+  Deck d;
+  if (!d.open(infile)) { printf("\n\n Error in input file...\n\n\n"); return 0; }
+  const int n = (int)d.geti(), nstep = (int)d.geti();
+  const double testalpha = d.getr();
+  double Re = d.getr();
+  const double beta = d.getr(), f2p = d.getr(), alphar = d.getr(), alphai = d.getr(), omegar = d.getr(), omegai = d.getr();
+  double ymin = d.getr(), ymax = d.getr();
+  const int niter = (int)d.geti();
+  double domega = d.getr();
+  const int eigfun = (int)d.geti();
+  printf("\n n = %s\n", I(n, 5).c_str());
+  printf(" nstep = %s\n", I(nstep, 5).c_str());
+  printf(" Test Alpha = %s\n", E(testalpha, 20, 10).c_str());
+  printf(" Re = %s\n", E(Re, 20, 10).c_str());
+  printf(" Beta = %s\n", E(beta, 20, 10).c_str());
+  printf(" f2p = %s\n", E(f2p, 20, 10).c_str());
+  printf(" Ymin = %s  Ymax = %s\n", E(ymin, 20, 10).c_str(), E(ymax, 20, 10).c_str());
+  printf(" alpha = (%s, %s)\n", E(alphar, 20, 10).c_str(), E(alphai, 20, 10).c_str());
+  printf(" omega = (%s, %s)\n\n", E(omegar, 20, 10).c_str(), E(omegai, 20, 10).c_str());
+  cd alpha(alphar, alphai), omega(omegar, omegai);
+  printf("\n Note:  changing nondimsensionalization to displacement thickness to match Mack...\n\n");
+  const double fact = std::sqrt(2.0) / 1.7207876, facti = 1.0 / fact;  // orrspace.f:160-168
+  Re = Re * fact; alpha = alpha * fact; omega = omega * fact; domega = domega * fact;
+  ymin = ymin * fact; ymax = ymax * fact;
+  const double hbl = (ymax - ymin) / (double)n;
+  if (n > 20000) { printf("\n\n N > Idim...Stopping\n\n\n"); return 0; }
+  osb_profile *prof = nullptr;
+  CK(ctx, osb_profile_blasius(ctx, OSB_FLOW_ORRSPACE, OSB_INT_RK4, n, ymin, ymax, f2p, beta, &prof));
+  const Tables t = fetch_tables(ctx, prof, n);
+  {
+    FILE *f = fopen("fort.10", "w");  // orrspace.f:804-810, format 5(1PE20.13E2,1x)
+    for (int i = 0; i <= n; ++i) {
+      const double y = ymin + i * hbl;
+      const double us = speval_linear(t.ydat, t.U, t.Uspl, y), d2us = speval_linear(t.ydat, t.d2U, t.d2Uspl, y);
+      fprintf(f, " %s %s %s %s %s \n", ES(y / std::sqrt(2.) * 1.7207876, 20, 13, 2).c_str(), ES(us, 20, 13, 2).c_str(),
+              ES(d2us, 20, 13, 2).c_str(), ES(t.U[i], 20, 13, 2).c_str(), ES(t.d2U[i], 20, 13, 2).c_str());
+    }
+    fclose(f);
+  }
+  printf(" Velocity Profile completed...\n\n");
+  osb_shoot_opts o;
+  CK(ctx, osb_shoot_defaults(OSB_FLOW_ORRSPACE, &o));
+  o.nstep = nstep; o.testalpha = testalpha; o.ymin = ymin; o.ymax = ymax;
+  // the whole omega loop of orrspace.f:186-195 is one call: continuation runs inside the kernel
+  std::vector<double> aout((size_t)niter * 2);
+  std::vector<int32_t> passes(niter), qend(niter), status(niter);
+  double om0[2] = {omega.real(), omega.imag()}, a0[2] = {alpha.real(), alpha.imag()};
+  CK(ctx, osb_shoot_spatial_lines(ctx, &o, prof, 1, niter, &Re, om0, &domega, a0, aout.data(), passes.data(), qend.data(),
+                                  status.data()));
+  FILE *f17 = fopen("fort.17", "w");
+  const double pfac = 1.7207877 / std::sqrt(2.);  // orrspace.f:485-486,495-498 (note the ...77)
+  int bad = 0;
+  for (int i = 0; i < niter; ++i) {
+    const cd om(omega.real() + i * domega, omega.imag()), al(aout[2 * i], aout[2 * i + 1]);
+    printf("\nOmega = (%s %s)    Alpha = (%s %s)\n\n", E(om.real() * pfac, 15, 8).c_str(), E(om.imag() * pfac, 15, 8).c_str(),
+           E(al.real() * pfac, 15, 8).c_str(), E(al.imag() * pfac, 15, 8).c_str());
+    fprintf(f17, " %s  %s  %s  \n", E((om * facti).real(), 17, 8).c_str(), E((al * facti).real(), 17, 8).c_str(),
+            E((al * facti).imag(), 17, 8).c_str());
+    bad |= status[i];
+  }
+  fclose(f17);
+  if (eigfun == 1) {  // eigenfunction of the LAST point (each CONTE call overwrites fort.11-14)
+    const cd om(omega.real() + (niter - 1) * domega, omega.imag());
+    double omr[2] = {om.real(), om.imag()}, ev[2] = {aout[2 * (niter - 1)], aout[2 * (niter - 1) + 1]};
+    std::vector<double> y((size_t)(nstep + 1) * 8);
+    double vmax[2];
+    int32_t q2;
+    CK(ctx, osb_eigfun(ctx, &o, prof, 1, nullptr, &Re, ev, omr, y.data(), vmax, &q2));
+    write_eigfun(y, cd(vmax[0], vmax[1]), nstep, ymax, ymin, (ymax - ymin) / nstep, true, 16, false, std::sqrt(2.) / 1.7207876);
+  }
+  osb_profile_free(ctx, prof);
+  return bad;
+}
+
+// ---------------------------------------------------------------- orrfdchan
+static int run_orrfdchan(osb_ctx *ctx) {
+  int n, ians;
+  double Re, minar, maxar, incar, minai, maxai, incai;
+  std::string filename;
+  printf("\n\n          Solve Orr-Sommerfeld (Finite-difference)\n");
+  printf("\n Enter the number of mesh points ==> "); std::cin >> n;
+  printf("\n Enter Reynolds number ==> "); std::cin >> Re;
+  printf("\n Enter alpha_r (min,max,inc) ==> "); std::cin >> minar >> maxar >> incar;
+  printf("\n Enter alpha_i (min,max,inc) ==> "); std::cin >> minai >> maxai >> incai;
+  printf("\n Enter root filename ==> "); std::cin >> filename;
+  printf("\n Print eigenvectors (1,0) ==> "); std::cin >> ians;
+  const int nar = (int)std::trunc((maxar - minar) / incar) + 1, nai = (int)std::trunc((maxai - minai) / incai) + 1;  // :89-90
+  printf("\n  nar = %s  nai = %s\n", I(nar, 5).c_str(), I(nai, 5).c_str());
+  if (nar > 100 || nai > 100 || nar < 1 || nai < 1) { fprintf(stderr, "sweep exceeds the reference's 100x100 arrays\n"); return 1; }
+  std::vector<double> alphar(nar), alphai(nai);
+  for (int i = 1; i <= nar; ++i) alphar[i - 1] = minar + (i - 1.) * incar;
+  for (int i = 1; i <= nai; ++i) alphai[i - 1] = minai + (i - 1.) * incai;
+  auto write5 = [](FILE *f, const std::vector<double> &v) {  // format 110: 5(ES16.8E3,1x) per record
+    for (size_t k = 0; k < v.size(); ++k) {
+      fprintf(f, "%s ", ES(v[k], 16, 8, 3).c_str());
+      if (k % 5 == 4 || k + 1 == v.size()) fprintf(f, "\n");
+    }
+  };
+  {
+    FILE *g = fopen((filename + ".g").c_str(), "w");
+    fprintf(g, "%s %s \n", I(nar, 5).c_str(), I(nai, 5).c_str());
+    std::vector<double> v;
+    for (int j = 0; j < nai; ++j) for (int i = 0; i < nar; ++i) v.push_back(alphar[i]);
+    for (int j = 0; j < nai; ++j) for (int i = 0; i < nar; ++i) v.push_back(alphai[j]);
+    write5(g, v);
+    fclose(g);
+  }
+  osb_chan *chan = nullptr;
+  CK(ctx, osb_chan_create(ctx, OSB_DISC_FD, n, &chan));
+  {
+    std::vector<double> eta(n + 1), u(n + 1), d2u(n + 1);
+    CK(ctx, osb_chan_tables(ctx, chan, eta.data(), u.data(), d2u.data(), nullptr, nullptr));
+    FILE *f = fopen("fort.10", "w");  // orrfdchan.f:262-266
+    for (int i = 0; i <= n; ++i)
+      fprintf(f, " %s    %s    %s    %s    \n", ES(eta[i], 16, 8, 3).c_str(), ES(u[i], 16, 8, 3).c_str(),
+              ES(-2.0 * eta[i], 16, 8, 3).c_str(), ES(d2u[i], 16, 8, 3).c_str());
+    fclose(f);
+  }
+  // the (j, i) loop nest of orrfdchan.f:116-128 hoisted into one batched call
+  const int64_t npts = (int64_t)nar * nai;
+  std::vector<double> al(2 * npts), om(2 * npts);
+  std::vector<int32_t> it(npts), st(npts);
+  for (int j = 0; j < nai; ++j) for (int i = 0; i < nar; ++i) { al[2 * (j * nar + i)] = alphar[i]; al[2 * (j * nar + i) + 1] = alphai[j]; }
+  CK(ctx, osb_chan_eig(ctx, chan, Re, npts, al.data(), nullptr, om.data(), nullptr, it.data(), st.data()));
+  FILE *dat = fopen((filename + ".dat").c_str(), "w");
+  int bad = 0;
+  for (int64_t p = 0; p < npts; ++p) {
+    const std::string row = " " + ES(al[2 * p], 16, 8, 3) + " " + ES(al[2 * p + 1], 16, 8, 3) + " " + ES(om[2 * p], 16, 8, 3) + " " +
+                            ES(om[2 * p + 1], 16, 8, 3) + " ";
+    fprintf(dat, "%s\n", row.c_str());
+    printf("%s\n", row.c_str());
+    bad |= st[p];
+  }
+  fclose(dat);
+  {
+    FILE *q = fopen((filename + ".q").c_str(), "w");  // orrfdchan.f:130-138
+    fprintf(q, "%s %s \n", I(nar, 5).c_str(), I(nai, 5).c_str());
+    write5(q, {0.0, 0.0, 0.0, 0.0});
+    std::vector<double> v;
+    for (int64_t p = 0; p < npts; ++p) v.push_back(1.0);
+    for (int64_t p = 0; p < npts; ++p) v.push_back(om[2 * p]);
+    for (int64_t p = 0; p < npts; ++p) v.push_back(om[2 * p + 1]);
+    for (int64_t p = 0; p < npts; ++p) v.push_back(1.0);
+    write5(q, v);
+    fclose(q);
+  }
+  (void)ians;
+  osb_chan_free(ctx, chan);
+  return bad;
+}
+
+// ---------------------------------------------------------------- orrcolchan
+static int run_orrcolchan(osb_ctx *ctx) {
+  int n;
+  double Re, alphar, alphai;
+  printf("\n\n          Solve Orr-Sommerfeld (Collocation)\n");
+  printf("\n Enter the number of modes ==> "); std::cin >> n;
+  printf("\n Enter Reynolds number ==> "); std::cin >> Re;
+  printf("\n Enter alpha (R,I) ==> "); std::cin >> alphar >> alphai;
+  osb_chan *chan = nullptr;
+  CK(ctx, osb_chan_create(ctx, OSB_DISC_CHEB, n, &chan));
+  std::vector<double> eta(n + 1), u(n + 1), d2u(n + 1);
+  CK(ctx, osb_chan_tables(ctx, chan, eta.data(), u.data(), d2u.data(), nullptr, nullptr));
+  {
+    FILE *f = fopen("fort.10", "w");  // orrcolchan.f:235-240
+    for (int i = 0; i <= n; ++i)
+      fprintf(f, " %s %s %s %s \n", ES(eta[i], 16, 8, 3).c_str(), ES(u[i], 16, 8, 3).c_str(), ES(-2. * eta[i], 16, 8, 3).c_str(),
+              ES(d2u[i], 16, 8, 3).c_str());
+    fclose(f);
+  }
+  double al[2] = {alphar, alphai}, om[2];
+  std::vector<double> ev((size_t)(n + 1) * 2);
+  int32_t it, st;
+  CK(ctx, osb_chan_eig(ctx, chan, Re, 1, al, nullptr, om, ev.data(), &it, &st));
+  printf("\n Eigenvalues for N+1 = %s\n\n", I(n + 1, 4).c_str());
+  const cd w(om[0], om[1]), c = w / cd(alphar, alphai);
+  // the reference lists all N+1 QZ eigenvalues; the GPU path isolates the least stable
+  // physical mode (sorted index N-2 when the two spurious Im~3 modes sit above it)
+  printf(" %s  %s %s %s %s \n", I(n - 2, 5).c_str(), ES(w.real(), 17, 10).c_str(), ES(w.imag(), 17, 10).c_str(),
+         ES(c.real(), 17, 10).c_str(), ES(c.imag(), 17, 10).c_str());
+  int which = -1;
+  printf("\n Eigenvector for which eigenvalue (-1 quits) ==> ");
+  while (std::cin >> which && which != -1) {
+    FILE *f = fopen("fort.11", "w");  // orrcolchan.f:551-555 (adjoint columns: not computed, zeros)
+    for (int i = 0; i <= n; ++i)
+      fprintf(f, " %s %s %s %s %s \n", ES(eta[i], 16, 8, 3).c_str(), ES(ev[2 * i], 16, 8, 3).c_str(), ES(ev[2 * i + 1], 16, 8, 3).c_str(),
+              ES(0.0, 16, 8, 3).c_str(), ES(0.0, 16, 8, 3).c_str());
+    fclose(f);
+    printf("\n Eigenvector for which eigenvalue (-1 quits) ==> ");
+  }
+  osb_chan_free(ctx, chan);
+  return st;
+}
+
+// ---------------------------------------------------------------- orrncbl
+static int run_orrncbl(osb_ctx *ctx) {
+  int n;
+  double Re, sfac, alpha_r;
+  printf("\n\n          Find Neutral Curve (Collocation)\n");
+  printf("\n Enter the number of modes ==> "); std::cin >> n;
+  printf("\n Enter Reynolds number ==> "); std::cin >> Re;
+  printf("\n Enter step size ==> "); std::cin >> sfac;
+  printf("\n Enter alpha_r ==> "); std::cin >> alpha_r;
+  osb_chan *chan = nullptr;
+  CK(ctx, osb_chan_create(ctx, OSB_DISC_CHEB_NUM, n, &chan));
+  const int maxit = 500;
+  std::vector<double> trace((size_t)maxit * 7);
+  double aout, om[2];
+  int32_t steps, st;
+  CK(ctx, osb_chan_neutral(ctx, chan, 1, &Re, &alpha_r, sfac, 1.0e-8, maxit, &aout, om, &steps, &st, trace.data()));
+  for (int k = 0; k < steps; ++k) {
+    const double *r = &trace[(size_t)k * 7];
+    if (k == 0) printf(" Eigenvalue =  (%.16g,%.16g)\n", r[1], r[2]);  // list-directed in the reference (orrncbl.f:902)
+    printf(" dw/da = %s %si, dalpha = %s, nw = %s\n", E(r[3], 12, 5).c_str(), E(r[4], 12, 5).c_str(), E(r[5], 12, 5).c_str(),
+           E(r[6], 12, 5).c_str());  // orrncbl.f:982,990-991
+    printf(" %s %s %s \n", E(r[0], 15, 8).c_str(), E(r[1], 15, 8).c_str(), E(r[2], 15, 8).c_str());  // :114-115
+  }
+  osb_chan_free(ctx, chan);
+  return st;
+}
+
+// ---------------------------------------------------------------- self tests (no GPU)
+static int selftest_format() {
+  printf("E17.8|%s|%s|%s|\n", E(0.36412287e0, 17, 8).c_str(), E(-9.4619873e-5, 17, 8).c_str(), E(0.0, 17, 8).c_str());
+  printf("E20.10|%s|%s|\n", E(580.0, 20, 10).c_str(), E(0.179, 20, 10).c_str());
+  printf("E17.8E3|%s|\n", E(0.23752649, 17, 8, 3).c_str());
+  printf("ES16.8E3|%s|%s|%s|\n", ES(17.0, 16, 8, 3).c_str(), ES(-1.5e-7, 16, 8, 3).c_str(), ES(0.0, 16, 8, 3).c_str());
+  printf("1PE20.12E3|%s|\n", ES(0.5, 20, 12, 3).c_str());
+  printf("ES17.8|%s|%s|\n", ES(2.88657986e-15, 17, 8).c_str(), ES(1.0e-101, 17, 8).c_str());
+  printf("E15.8|%s|%s|\n", E(0.999999996, 15, 8).c_str(), E(1.0e100, 15, 8).c_str());
+  printf("I5|%s|%s|\n", I(21, 5).c_str(), I(123456, 5).c_str());
+  return 0;
+}
+static int selftest_deck(const char *path) {
+  Deck d;
+  if (!d.open(path)) return 1;
+  const long long nbl = d.geti(), nstep = d.geti();
+  printf("%lld %lld", nbl, nstep);
+  for (int k = 0; k < 10; ++k) printf(" %.17g", d.getr());
+  printf("\n");
+  return 0;
+}
+
+int main(int argc, char **argv) {
+  if (argc < 2) {
+    fprintf(stderr, "usage: osb_drivers contebl|conte|orrsom|orrspace|orrfdchan|orrcolchan|orrncbl  (input on stdin)\n");
+    return 64;
+  }
+  const std::string prog = argv[1];
+  if (prog == "--selftest-format") return selftest_format();
+  if (prog == "--selftest-deck" && argc > 2) return selftest_deck(argv[2]);
+  if (prog == "--selftest-readr" && argc > 2) {
+    double v = 0;
+    std::string fld;
+    if (!fortfmt::deck_field(argv[2], fld) || !fortfmt::read_G20_10(fld, v)) return 1;
+    printf("%.17g\n", v);
+    return 0;
+  }
+  osb_ctx *ctx = nullptr;
+  const int rc = osb_create(&ctx, 0);
+  if (rc) {
+    fprintf(stderr, "osb_drivers: no usable CUDA device (osb_create = %d); there is no CPU fallback\n", rc);
+    return 3;
+  }
+  int st = 0;
+  if (prog == "contebl") st = run_contebl(ctx);
+  else if (prog == "conte") st = run_conte(ctx);
+  else if (prog == "orrsom") st = run_orrsom(ctx);
+  else if (prog == "orrspace") st = run_orrspace(ctx);
+  else if (prog == "orrfdchan") st = run_orrfdchan(ctx);
+  else if (prog == "orrcolchan") st = run_orrcolchan(ctx);
+  else if (prog == "orrncbl") st = run_orrncbl(ctx);
+  else { fprintf(stderr, "unknown program %s\n", prog.c_str()); st = 64; }
+  osb_destroy(ctx);
+  return st == 0 ? 0 : 1;
+}

@@ -1,0 +1,204 @@
+"""C++ twin drivers (os-stab_b200/host/osb_drivers): Fortran edit-descriptor and deck
+emulation on CPU; on the GPU the drivers must reproduce the reference's stdout records
+and fort.N files (README.md:24-26 line included)."""
+import math
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_binding as ob
+
+ROOT = Path(__file__).resolve().parent.parent
+DRV = ROOT / "os-stab_b200" / "host" / "osb_drivers"
+S2 = math.sqrt(2.0)
+
+TEMPORAL_DECK = """#
+# temporal deck (layout of the reference's contebl.inp / test.inp: positional lines)
+#
+nbl = {nbl}              # number of in profile
+nstep = {nstep}            # number of integration points
+testalpha = 10.0        # Ortho. constraint (0 - 90 deg)
+Re = {Re}              # Reynolds number
+beta = 0.0              # Falker-Skan parameter
+fp2 = 0.50              # Guess for profile slope
+alphar = {ar}          # Real part of alpha
+alphai = 0.0            # Imag part of alpha
+cr = {cr}   # Guess for Re(c)
+ci = {ci}   # Guess for Im(c)
+Ymin = 0.0              # Minimum Y
+Ymax = {ymax}             # Maximum Y
+"""
+
+SPATIAL_DECK = """#
+# spatial deck (values of the reference's sweep.inp)
+#
+nbl = 1000              # number of in profile
+nstep = 1000            # number of integration points
+testalpha = 0.9         # Ortho. constraint (0 - 1)
+Re = 1000.0             # Reynolds number
+beta = 0.0              # Falker-Skan parameter
+fp2 = 0.50              # Guess for profile slope
+alphar = 0.13809592E+00 # Real part of alpha
+alphai = 0.51958399E-02 # Imag part of alpha
+omegar = 0.042          # Guess for Re(omega)
+omegai = 0.00           # Guess for Im(omega)
+Ymin = 0.0              # Minimum Y
+Ymax = 20.0             # Maximum Y
+niter = {niter}              # number of iterations
+domega = 0.002          # step size
+eigfun = {eigfun}              # compute eigenfunctions
+"""
+
+
+def run(prog, stdin, cwd):
+    return subprocess.run([str(DRV), prog], input=stdin, capture_output=True, text=True, cwd=cwd, timeout=600)
+
+
+def test_fortran_edit_descriptors():
+    out = subprocess.run([str(DRV), "--selftest-format"], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert out[0] == "E17.8|   0.36412287E+00|  -0.94619873E-04|   0.00000000E+00|"
+    assert out[1] == "E20.10|    0.5800000000E+03|    0.1790000000E+00|"
+    assert out[2] == "E17.8E3|  0.23752649E+000|"
+    assert out[3] == "ES16.8E3| 1.70000000E+001|-1.50000000E-007| 0.00000000E+000|"
+    assert out[4] == "1PE20.12E3| 5.000000000000E-001|"
+    assert out[5] == "ES17.8|   2.88657986E-15|   1.00000000-101|"  # 3-digit exponent drops the E
+    assert out[6] == "E15.8| 0.10000000E+01| 0.10000000+101|"       # rounding carries into the exponent
+    assert out[7] == "I5|   21|*****|"
+
+
+def test_deck_reader(tmp_path):
+    deck = tmp_path / "t.inp"
+    deck.write_text(TEMPORAL_DECK.format(nbl=400, nstep=4000, Re=580.0, ar=0.179, cr="0.3641312400E+00", ci="0.7952738700E-02", ymax=30.0))
+    out = subprocess.run([str(DRV), "--selftest-deck", str(deck)], capture_output=True, text=True, check=True).stdout.split()
+    assert out[:2] == ["400", "4000"]
+    vals = [float(x) for x in out[2:]]
+    assert vals == [10.0, 580.0, 0.0, 0.5, 0.179, 0.0, 0.36413124, 0.0079527387, 0.0, 30.0]
+    # (G20.10): no decimal point => scaled by 1e-10; only 20 characters are read (oracle D-8)
+    r = subprocess.run([str(DRV), "--selftest-readr", "Re = 580   # no point"], capture_output=True, text=True, check=True)
+    assert abs(float(r.stdout) - 580e-10) < 1e-20
+    r = subprocess.run([str(DRV), "--selftest-readr", "x = 1.5D+01"], capture_output=True, text=True, check=True)
+    assert float(r.stdout) == 15.0
+
+
+def test_driver_refuses_to_run_without_a_gpu(tmp_path):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = run("contebl", "d\n", tmp_path)
+    assert r.returncode == 3 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_contebl_default_transcript(tmp_path, oracle):
+    r = run("contebl", "d\n", tmp_path)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    assert "          Solve Orr-Sommerfeld for Boundary Layer using shooting" in out
+    assert " Read from keyboard, file, default (k,f,d) ==> " in out
+    assert " Re =     0.5800000000E+03" in out and " nbl =  1000" in out
+    assert " c = (    0.3641312400E+00,     0.7952738700E-02)" in out
+    assert " Blasius velocity profile completed..." in out
+    # README.md:24-26
+    assert "Eigenvalue =    0.36412287E+00    0.79597206E-02     21" in out
+    assert "  Eigenvalue iterations =     5" in out
+    lines = [ln for ln in out.splitlines() if ln.startswith("    1   0.36413124E+00   0.79527387E-02")]
+    assert len(lines) == 1
+    # fort.10: y, spline(U), U'' (spline), U, d2U ; fort.11-14: eigenfunction
+    prof, _, _ = oracle.solve_bl()
+    f10 = np.loadtxt(tmp_path / "fort.10")
+    assert f10.shape == (1001, 5)
+    assert np.max(np.abs(f10[:, 3] - prof[1][:1001])) < 1e-8 and abs(f10[1000, 0] - 17.0) < 1e-12
+    ref = oracle.shoot_temporal(ob.FLOW_CONTEBL, ob.INT_CK45, 1000, 10.0, 0.0, 17.0, prof, 0.179 * S2, 580.0 * S2,
+                                complex(0.36413124, 0.79527387e-2), eigfun=True)
+    yr = ref["y"] / ref["vmax"]
+    for i in range(4):
+        f = np.loadtxt(tmp_path / f"fort.{11 + i}")
+        assert f.shape == (1001, 3) and f[0, 0] == 17.0
+        assert np.max(np.abs(f[:, 1] + 1j * f[:, 2] - yr[:, i])) < 2e-8 * max(1.0, np.max(np.abs(yr[:, i])))
+
+
+@pytest.mark.gpu
+def test_contebl_deck_file(tmp_path, oracle):
+    (tmp_path / "t.inp").write_text(TEMPORAL_DECK.format(nbl=1000, nstep=1000, Re=581.1, ar=0.1453, cr=0.35, ci=0.01, ymax=17.0))
+    r = run("contebl", "f\nt.inp\n", tmp_path)
+    assert r.returncode == 0, r.stderr
+    prof, _, _ = oracle.solve_bl()
+    ref = oracle.shoot_temporal(ob.FLOW_CONTEBL, ob.INT_CK45, 1000, 10.0, 0.0, 17.0, prof, 0.1453 * S2, 581.1 * S2, complex(0.35, 0.01))
+    ln = [x for x in r.stdout.splitlines() if x.startswith("Eigenvalue =")][0].split()
+    assert abs(float(ln[2]) - ref["c"].real) < 1e-8 and abs(float(ln[3]) - ref["c"].imag) < 1e-9
+    assert int(ln[4]) == ref["qend"]
+
+
+@pytest.mark.gpu
+def test_conte_default_transcript(tmp_path):
+    r = run("conte", "d\n", tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert "Eigenvalue =   0.23752649E+000  0.37396706E-002    115" in r.stdout
+    assert " Channel velocity profile completed..." in r.stdout
+    f10 = np.loadtxt(tmp_path / "fort.10")
+    assert f10.shape == (4001, 3) and f10[2000, 1] == 1.0
+
+
+@pytest.mark.gpu
+def test_orrsom_deck_on_stdin(tmp_path):
+    deck = TEMPORAL_DECK.format(nbl=400, nstep=4000, Re=580.0, ar=0.179, cr="0.3641312400E+00", ci="0.7952738700E-02", ymax=30.0)
+    r = run("orrsom", deck, tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert "Eigenvalue =    0.36407048E+00    0.80033261E-02     39" in r.stdout
+    assert "Second pass: computing and writing eigenfunction" in r.stdout
+    assert (tmp_path / "fort.15").exists()
+
+
+@pytest.mark.gpu
+def test_orrspace_sweep_fort17(tmp_path, oracle):
+    (tmp_path / "sweep.inp").write_text(SPATIAL_DECK.format(niter=50, eigfun=0))
+    r = run("orrspace", "sweep.inp\n", tmp_path)
+    assert r.returncode == 0, r.stderr
+    f17 = np.loadtxt(tmp_path / "fort.17")
+    assert f17.shape == (50, 3)
+    expect = {0: (0.042, 0.138095915, 0.00519583038), 9: (0.060, 0.183042716, -0.00167594002),
+              28: (0.098, 0.275061388, -0.00738817368), 49: (0.140, 0.372260299, 0.00445007249)}
+    for i, (w, ar, ai) in expect.items():
+        assert abs(f17[i, 0] - w) < 1e-9 and abs(f17[i, 1] - ar) < 2e-8 and abs(f17[i, 2] - ai) < 2e-9
+    assert r.stdout.count("Omega = (") == 50
+    assert "displacement thickness to match Mack" in r.stdout
+
+
+@pytest.mark.gpu
+def test_orrfdchan_fd64_deck(tmp_path):
+    r = run("orrfdchan", "64\n10000\n0.76 1.16 0.02\n0 0 1\neig-64\n0\n", tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert "  nar =    21  nai =     1" in r.stdout
+    dat = np.loadtxt(tmp_path / "eig-64.dat")
+    assert dat.shape == (21, 4)
+    c = ob.chan(ob.DISC_FD, 64)
+    ref = np.array([c.solve_fd(a, 1.0e4)["omega"] for a in dat[:, 0]])
+    c.close()
+    assert np.max(np.abs(dat[:, 2] + 1j * dat[:, 3] - ref)) < 2e-8
+    assert (tmp_path / "eig-64.g").exists() and (tmp_path / "eig-64.q").exists()
+    g = (tmp_path / "eig-64.g").read_text().splitlines()
+    assert g[0] == "   21     1 "
+
+
+@pytest.mark.gpu
+def test_orrncbl_nc_deck(tmp_path):
+    r = run("orrncbl", "64\n10000\n.01\n1\n", tmp_path)
+    assert r.returncode == 0, r.stderr
+    rows = [ln.split() for ln in r.stdout.splitlines() if ln.startswith(" 0.1") and len(ln.split()) == 3]
+    assert 15 <= len(rows) <= 19
+    assert abs(float(rows[-1][0]) - 1.0947279) < 5e-5 and abs(float(rows[-1][2])) < 1e-8
+
+
+@pytest.mark.gpu
+def test_orrcolchan_chan_deck(tmp_path):
+    r = run("orrcolchan", "64\n10000\n1 0\n62\n-1\n", tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert " Eigenvalues for N+1 =   65" in r.stdout
+    row = [ln for ln in r.stdout.splitlines() if ln.startswith("    62 ")][0].split()
+    assert abs(float(row[1]) - 0.2375262367) < 2e-9 and abs(float(row[2]) - 0.0037399251) < 2e-9
+    f11 = np.loadtxt(tmp_path / "fort.11")
+    assert f11.shape == (65, 5)
