@@ -137,7 +137,8 @@ def test_contebl_deck_file(tmp_path, oracle):
 def test_conte_default_transcript(tmp_path):
     r = run("conte", "d\n", tmp_path)
     assert r.returncode == 0, r.stderr
-    assert "Eigenvalue =   0.23752649E+000  0.37396706E-002    115" in r.stdout
+    # format 40 of shoot.f:330-331: 'Eigenvalue = ',e17.8e3,1x,e17.8e3,2x,i5
+    assert "Eigenvalue =   0.23752649E+000   0.37396706E-002    115" in r.stdout
     assert " Channel velocity profile completed..." in r.stdout
     f10 = np.loadtxt(tmp_path / "fort.10")
     assert f10.shape == (4001, 3) and f10[2000, 1] == 1.0
@@ -172,23 +173,26 @@ def test_orrspace_sweep_fort17(tmp_path, oracle):
 def test_orrfdchan_fd64_deck(tmp_path):
     r = run("orrfdchan", "64\n10000\n0.76 1.16 0.02\n0 0 1\neig-64\n0\n", tmp_path)
     assert r.returncode == 0, r.stderr
-    assert "  nar =    21  nai =     1" in r.stdout
+    # nar = aint((maxar-minar)/incar)+1 in fp64 (orrfdchan.f:89): (1.16-0.76)/0.02 = 19.999999999999996 -> 20
+    nar = int((1.16 - 0.76) / 0.02) + 1
+    assert nar == 20
+    assert "  nar =    20  nai =     1" in r.stdout
     dat = np.loadtxt(tmp_path / "eig-64.dat")
-    assert dat.shape == (21, 4)
+    assert dat.shape == (nar, 4)
     c = ob.chan(ob.DISC_FD, 64)
     ref = np.array([c.solve_fd(a, 1.0e4)["omega"] for a in dat[:, 0]])
     c.close()
     assert np.max(np.abs(dat[:, 2] + 1j * dat[:, 3] - ref)) < 2e-8
     assert (tmp_path / "eig-64.g").exists() and (tmp_path / "eig-64.q").exists()
     g = (tmp_path / "eig-64.g").read_text().splitlines()
-    assert g[0] == "   21     1 "
+    assert g[0] == "   20     1 "
 
 
 @pytest.mark.gpu
 def test_orrncbl_nc_deck(tmp_path):
     r = run("orrncbl", "64\n10000\n.01\n1\n", tmp_path)
     assert r.returncode == 0, r.stderr
-    rows = [ln.split() for ln in r.stdout.splitlines() if ln.startswith(" 0.1") and len(ln.split()) == 3]
+    rows = [ln.split() for ln in r.stdout.splitlines() if ln.startswith("  0.1") and len(ln.split()) == 3]
     assert 15 <= len(rows) <= 19
     assert abs(float(rows[-1][0]) - 1.0947279) < 5e-5 and abs(float(rows[-1][2])) < 1e-8
 
