@@ -5,6 +5,7 @@
 // solver here: with no CUDA device every entry point fails with OSB_E_CUDA.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -426,8 +427,14 @@ int osb_shoot_temporal_dev(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_p
   a.history = (double4 *)d_history;
   a.hist_cap = d_history ? hist_cap : 0;
   int nl = 0;
-  OSB_CUDA(ctx, launch_shoot(a, opts->integrator, analytic, st, &nl));
+  unsigned long long *qc = nullptr;
+  if (!getenv("OSB_NO_QUEUE")) {
+    OSB_CUDA(ctx, cudaMallocAsync(&qc, sizeof(unsigned long long), st));
+    OSB_CUDA(ctx, cudaMemsetAsync(qc, 0, sizeof(unsigned long long), st));
+  }
+  OSB_CUDA(ctx, launch_shoot(a, opts->integrator, analytic, st, &nl, qc));
   ctx->launches += nl;
+  if (qc) OSB_CUDA(ctx, cudaFreeAsync(qc, st));
   OSB_CUDA(ctx, cudaFreeAsync(tab, st));
   return OSB_OK;
 }
@@ -479,8 +486,14 @@ int osb_shoot_temporal(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profi
     a.history = (double4 *)b.hist;
     a.hist_cap = history ? hist_cap : 0;
     int nl = 0;
-    OSB_CUDA(ctx, launch_shoot(a, opts->integrator, analytic, st, &nl));
+    unsigned long long *qc = nullptr;
+    if (!getenv("OSB_NO_QUEUE")) {
+      OSB_CUDA(ctx, cudaMallocAsync(&qc, sizeof(unsigned long long), st));
+      OSB_CUDA(ctx, cudaMemsetAsync(qc, 0, sizeof(unsigned long long), st));
+    }
+    OSB_CUDA(ctx, launch_shoot(a, opts->integrator, analytic, st, &nl, qc));
     ctx->launches += nl;
+    if (qc) OSB_CUDA(ctx, cudaFreeAsync(qc, st));
   }
   // phase 2: D2H + free
   for (int d = 0; d < ndev; ++d) {

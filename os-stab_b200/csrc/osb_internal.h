@@ -74,8 +74,10 @@ struct EigfunArgs {
 cudaError_t launch_stage_table(const ProfileDev &p, int flow, int integrator, int nstep,
                                double to, double tf, double2 *tab, cudaStream_t st);
 int stages_per_step(int integrator);
+// queue_counter: zeroed device word enabling the compacting persistent-CTA kernel
+// for temporal sweeps (nullptr: one thread per point for the whole solve)
 cudaError_t launch_shoot(const ShootArgs &a, int integrator, int analytic_inprod,
-                         cudaStream_t st, int *nlaunch);
+                         cudaStream_t st, int *nlaunch, unsigned long long *queue_counter = nullptr);
 cudaError_t launch_eigfun(const EigfunArgs &a, int integrator, int analytic_inprod,
                           int64_t npts, cudaStream_t st);
 cudaError_t launch_blasius(int variant, int integrator, int nbl, double ymin, double ymax,

@@ -24,6 +24,8 @@
 //  * The orthonormality test acos(cc/sqrt(aa*bb)) < ta (shoot.f:593-606) is
 //    evaluated as cc^2 > cos^2(ta)*aa*bb (acos is monotone): no sqrt/div/acos on
 //    the per-step path.
+#include <algorithm>
+
 #include "osb_cplx.cuh"
 #include "osb_internal.h"
 
@@ -555,6 +557,109 @@ __global__ void __launch_bounds__(128) shoot_kernel(const __grid_constant__ Shoo
 }
 
 // ---------------------------------------------------------------------------
+// K2 with divergent convergence compacted through a shared-memory work queue
+// (temporal sweeps).  Pass counts differ from point to point (5..20); with one
+// point per thread for the whole solve a warp runs as long as its slowest lane
+// (ncu round 1: 26.97 of 32 lanes active).  Here CTAs are persistent and the unit
+// of work is one PASS: after every pass the CTA packs the points that need
+// another pass into its lowest slots (order preserving, so neighbours in the
+// sweep stay neighbours and keep normalising at the same steps) and refills the
+// freed slots with fresh points taken from a global counter.  The per-point
+// arithmetic is untouched, so results do not depend on the schedule.
+// ---------------------------------------------------------------------------
+constexpr int QT = 128;  // threads (= slots) per CTA
+
+struct SlotState {  // what a point carries from one pass to the next
+  zd ev, cm1, cm2, errm1, errm2, alpha;
+  double Re;
+  long long line;
+  int icount, cm1_defined;
+};
+
+template <int INTEG, bool ANALYTIC>
+__global__ void __launch_bounds__(QT) shoot_queue_kernel(const __grid_constant__ ShootArgs a,
+                                                         unsigned long long *__restrict__ counter) {
+  __shared__ SlotState slots[QT];
+  __shared__ int warp_keep[QT / 32];
+  __shared__ long long s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  SlotState st;
+  st.line = -1;
+  bool first = true;
+  for (;;) {
+    // ---- compaction + refill
+    bool keep = false;
+    if (!first && st.line >= 0) keep = true;  // st holds a point that needs another pass
+    first = false;
+    const unsigned kmask = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_keep[warp] = __popc(kmask);
+    __syncthreads();
+    int before = 0, nkeep = 0;
+#pragma unroll
+    for (int w = 0; w < QT / 32; ++w) {
+      if (w < warp) before += warp_keep[w];
+      nkeep += warp_keep[w];
+    }
+    if (keep) slots[before + __popc(kmask & ((1u << lane) - 1u))] = st;
+    if (tid == 0) s_base = (long long)atomicAdd(counter, (unsigned long long)(QT - nkeep));
+    __syncthreads();
+    if (tid < nkeep) {
+      st = slots[tid];
+    } else {
+      const long long line = s_base + (tid - nkeep);
+      if (line < a.nlines) {
+        const double2 al = a.alpha[line], c0 = a.ev[line];
+        st.line = line;
+        st.alpha = zd{al.x, al.y};
+        st.Re = a.Re[line];
+        st.ev = zd{c0.x, c0.y};
+        st.icount = 1;
+        st.cm1_defined = a.cm1_defined;
+        st.cm1 = zd{st.ev.x + 1.0, st.ev.y};
+        st.cm2 = zd{0.0, 0.0}; st.errm1 = zd{0.0, 0.0}; st.errm2 = zd{0.0, 0.0};
+      } else {
+        st.line = -1;
+      }
+    }
+    const bool active = st.line >= 0;
+    if (__syncthreads_or(active) == 0) break;  // queue drained and nothing left to continue
+    // ---- one pass
+    const bool real_alpha = __all_sync(0xffffffffu, !active || st.alpha.y == 0.0);
+    if (active) {
+      zd err;
+      int qend = 0;
+      const zd ctemp = st.ev;
+      if (real_alpha) integrate_pass<INTEG, ANALYTIC, true>(a, st.alpha, st.Re, st.ev, err, qend);
+      else integrate_pass<INTEG, ANALYTIC, false>(a, st.alpha, st.Re, st.ev, err, qend);
+      IterState it;
+      it.ev = st.ev; it.cm1 = st.cm1; it.cm2 = st.cm2; it.errm1 = st.errm1; it.errm2 = st.errm2;
+      it.icount = st.icount; it.cm1_defined = st.cm1_defined;
+      update_eigenvalue(it, err, ctemp, a.first_perturb);
+      if (a.history && it.icount <= a.hist_cap) {
+        const zd shown = a.show_updated ? it.ev : ctemp;
+        a.history[st.line * a.hist_cap + (it.icount - 1)] = make_double4(shown.x, shown.y, err.x, err.y);
+      }
+      it.icount += 1;
+      int status = -1;
+      if (!(zfinite(it.ev) && zfinite(err))) status = OSB_ST_NONFINITE;
+      else if (!keep_going(a, it, err)) status = (it.icount <= a.maxcount) ? OSB_ST_CONVERGED : OSB_ST_MAXCOUNT;
+      if (status >= 0) {  // the point is done: report ctemp, the last value integrated
+        a.ev[st.line] = make_double2(ctemp.x, ctemp.y);
+        a.passes[st.line] = it.icount - 1;
+        a.qend[st.line] = qend;
+        a.status[st.line] = status;
+        if (a.resid)
+          a.resid[st.line] = make_double2(zabs(err), it.cm1_defined ? zabs(zsub(it.ev, it.cm1)) : 0.0);
+        st.line = -1;
+      } else {
+        st.ev = it.ev; st.cm1 = it.cm1; st.cm2 = it.cm2; st.errm1 = it.errm1; st.errm2 = it.errm2;
+        st.icount = it.icount; st.cm1_defined = it.cm1_defined;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // K2b: eigenfunction pass (shoot.f:762-810; conte shoot.f:338-385).  One thread
 // per requested point: re-integrates at the converged eigenvalue keeping the
 // (orthonormalised) trajectory, the P matrices and the normalisation abscissae,
@@ -685,9 +790,39 @@ cudaError_t launch_eigfun(const EigfunArgs &e, int integrator, int analytic_inpr
   return cudaGetLastError();
 }
 
+// persistent-CTA launch of the queue kernel; `counter` is a zeroed device word
+static cudaError_t launch_shoot_queue(const ShootArgs &a, int integrator, int analytic_inprod,
+                                      unsigned long long *counter, cudaStream_t st) {
+  int dev = 0, sms = 0, per = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const void *fn = integrator == OSB_INT_CK45
+                       ? (analytic_inprod ? (const void *)shoot_queue_kernel<OSB_INT_CK45, true>
+                                          : (const void *)shoot_queue_kernel<OSB_INT_CK45, false>)
+                       : (analytic_inprod ? (const void *)shoot_queue_kernel<OSB_INT_RK4, true>
+                                          : (const void *)shoot_queue_kernel<OSB_INT_RK4, false>);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, fn, QT, 0);
+  if (e != cudaSuccess) return e;
+  if (per < 1) per = 1;
+  const int64_t want = (a.nlines + QT - 1) / QT;
+  const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * per);
+  if (integrator == OSB_INT_CK45) {
+    if (analytic_inprod) shoot_queue_kernel<OSB_INT_CK45, true><<<grid, QT, 0, st>>>(a, counter);
+    else shoot_queue_kernel<OSB_INT_CK45, false><<<grid, QT, 0, st>>>(a, counter);
+  } else {
+    if (analytic_inprod) shoot_queue_kernel<OSB_INT_RK4, true><<<grid, QT, 0, st>>>(a, counter);
+    else shoot_queue_kernel<OSB_INT_RK4, false><<<grid, QT, 0, st>>>(a, counter);
+  }
+  return cudaGetLastError();
+}
+
 cudaError_t launch_shoot(const ShootArgs &a, int integrator, int analytic_inprod, cudaStream_t st,
-                         int *nlaunch) {
+                         int *nlaunch, unsigned long long *queue_counter) {
   if (a.nlines <= 0) return cudaSuccess;
+  if (queue_counter && !a.spatial && a.niter == 1 && a.nlines >= 4 * QT) {
+    if (nlaunch) *nlaunch += 1;
+    return launch_shoot_queue(a, integrator, analytic_inprod, queue_counter, st);
+  }
   // small batches: narrow CTAs so the points spread over all 148 SMs
   int threads = (a.nlines >= 148 * 4 * 128) ? 128 : (a.nlines >= 148 * 4 * 64 ? 64 : 32);
   int64_t blocks = (a.nlines + threads - 1) / threads;
