@@ -60,7 +60,7 @@ class ShootOpts(C.Structure):
 
 
 def load_library(path: os.PathLike | None = None) -> C.CDLL:
-    p = Path(path) if path else LIB_PATH
+    p = Path(path) if path else Path(os.environ.get("OSB_LIB", LIB_PATH))  # OSB_LIB: experiment builds
     if not p.exists():
         raise ImportError(
             f"{p} not found: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()' "

@@ -537,6 +537,217 @@ __global__ void __launch_bounds__(CH_THREADS) chan_eig_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------------------
+// K4b: the FD operator is banded.  D1hat is tridiagonal (FiniteD1, orrfdchan.f:1183-1215),
+// so D2 = D1hat D1 has half bandwidth 2 and D4 half bandwidth 4: A - sigma B is a 9-diagonal
+// matrix.  Gaussian elimination with partial pivoting on it is the SAME elimination as the
+// dense LU (a pivot can only come from the 4 rows below the diagonal, fill-in stays within
+// 8 super-diagonals) at n*4*8 complex FMAs instead of (8/3) n^3 flops.  One THREAD per
+// instance: a 5-row x 9-column window of the active rows lives in registers, L (4 per
+// column), U (9 per row), the pivots and the two iteration vectors live in global memory
+// interleaved by instance so that a warp's accesses coalesce.
+// ---------------------------------------------------------------------------
+constexpr int BKL = 4, BKU = 4, BW = BKL + BKU + 1;  // 9 stored entries per U row
+
+struct BandArgs {
+  int n;
+  const double *D2, *D4, *u, *d2u;  // dense tables (only the band is read)
+  int64_t ninst;
+  const double2 *alpha;
+  const double *Re;
+  const double2 *sigma;
+  int outer, inner;
+  double tol;
+  double2 *omega;
+  double *delta;
+  int32_t *iters;
+  double2 *evec;   // optional [ninst][n+2]
+  double2 *U;      // [n][BW][ninst]
+  double2 *L;      // [n][BKL][ninst]
+  int8_t *piv;     // [n][ninst]  pivot offset 0..4
+  double2 *x, *y;  // [n][ninst]
+};
+
+__device__ __forceinline__ double2 band_entry(const BandArgs &a, const PencilCoef &p, double2 sb2, double2 sb0,
+                                              int r, int c) {
+  // M(r,c) = D4 + (w2_r - sigma b2) D2 + delta_rc (w0_r - sigma b0); zero outside the matrix / band
+  if (c < 0 || c >= a.n || r >= a.n || c < r - BKL || c > r + BKU) return make_double2(0.0, 0.0);
+  const size_t e = (size_t)c * a.n + r;
+  const double2 w2 = csub2(coef_w2(p, a.u[r]), sb2);
+  const double d2 = a.D2[e], d4 = a.D4[e];
+  double2 v = make_double2(fma(w2.x, d2, d4), w2.y * d2);
+  if (r == c) v = cadd2(v, csub2(coef_w0(p, a.u[r], a.d2u[r]), sb0));
+  return v;
+}
+
+__global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constant__ BandArgs a) {
+  const int64_t inst = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (inst >= a.ninst) return;
+  const int n = a.n;
+  const size_t S = (size_t)a.ninst;  // interleave stride
+  const PencilCoef p = pencil_coef(a.alpha[inst], a.Re[inst]);
+  double2 sigma = a.sigma[inst];
+  double2 *U = a.U + inst, *Lm = a.L + inst, *x = a.x + inst, *y = a.y + inst;
+  int8_t *piv = a.piv + inst;
+  // start vector (same as the dense path)
+  for (int i = 0; i < n; ++i) {
+    const double sv = sin(3.0 * (i + 1.0) / (n + 1.0)) + 0.37 * cos(11.0 * (i + 1.0) / (n + 1.0));
+    x[(size_t)i * S] = make_double2(sv, 0.25 * sv * sv - 0.1);
+  }
+  double2 om = sigma;
+  double dl = 1.0e300;
+  int total = 0;
+  for (int o = 0; o < a.outer; ++o) {
+    // ---- banded LU with partial pivoting (window of rows k..k+4, columns k..k+8)
+    const double2 sb2 = cmul2(sigma, p.b2), sb0 = cmul2(sigma, p.b0);
+    double2 w[BKL + 1][BW];
+#pragma unroll
+    for (int sidx = 0; sidx <= BKL; ++sidx)
+#pragma unroll
+      for (int j = 0; j < BW; ++j) w[sidx][j] = band_entry(a, p, sb2, sb0, sidx, j);
+    for (int k = 0; k < n; ++k) {
+      int pv = 0;
+      double best = fabs(w[0][0].x) + fabs(w[0][0].y);
+#pragma unroll
+      for (int sidx = 1; sidx <= BKL; ++sidx) {
+        const double v = fabs(w[sidx][0].x) + fabs(w[sidx][0].y);
+        if (k + sidx < n && v > best) { best = v; pv = sidx; }
+      }
+      piv[(size_t)k * S] = (int8_t)pv;
+#pragma unroll
+      for (int sidx = 1; sidx <= BKL; ++sidx)
+        if (pv == sidx) {
+#pragma unroll
+          for (int j = 0; j < BW; ++j) { const double2 t = w[0][j]; w[0][j] = w[sidx][j]; w[sidx][j] = t; }
+        }
+      double2 pvt = w[0][0];
+      if (pvt.x == 0.0 && pvt.y == 0.0) pvt = make_double2(1.0e-290, 0.0);
+      const double2 rinv = cdiv2(make_double2(1.0, 0.0), pvt);
+#pragma unroll
+      for (int sidx = 1; sidx <= BKL; ++sidx) {
+        const double2 l = cmul2(w[sidx][0], rinv);
+        Lm[((size_t)k * BKL + (sidx - 1)) * S] = l;
+#pragma unroll
+        for (int j = 1; j < BW; ++j) w[sidx][j] = csub2(w[sidx][j], cmul2(l, w[0][j]));
+      }
+#pragma unroll
+      for (int j = 0; j < BW; ++j) U[((size_t)k * BW + j) * S] = (j == 0) ? pvt : w[0][j];
+      // slide the window: row k leaves, row k+5 enters
+#pragma unroll
+      for (int sidx = 0; sidx < BKL; ++sidx) {
+#pragma unroll
+        for (int j = 0; j < BW - 1; ++j) w[sidx][j] = w[sidx + 1][j + 1];
+        w[sidx][BW - 1] = make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int j = 0; j < BW; ++j) w[BKL][j] = band_entry(a, p, sb2, sb0, k + 1 + BKL, k + 1 + j);
+    }
+    // ---- inverse iteration
+    int it = 0;
+    for (; it < a.inner; ++it) {
+      // y = B x = b2 D2 x + b0 x   (D2 has half bandwidth 2)
+      for (int r = 0; r < n; ++r) {
+        double sr = 0.0, si = 0.0;
+#pragma unroll
+        for (int dc = -2; dc <= 2; ++dc) {
+          const int c = r + dc;
+          if (c >= 0 && c < n) {
+            const double d = a.D2[(size_t)c * n + r];
+            const double2 xc = x[(size_t)c * S];
+            sr = fma(d, xc.x, sr); si = fma(d, xc.y, si);
+          }
+        }
+        y[(size_t)r * S] = cadd2(cmul2(p.b2, make_double2(sr, si)), cmul2(p.b0, x[(size_t)r * S]));
+      }
+      // forward: L y' = P y, window of 5 right-hand-side values
+      double2 bw[BKL + 1];
+#pragma unroll
+      for (int sidx = 0; sidx <= BKL; ++sidx) bw[sidx] = sidx < n ? y[(size_t)sidx * S] : make_double2(0.0, 0.0);
+      for (int k = 0; k < n; ++k) {
+        const int pv = piv[(size_t)k * S];
+#pragma unroll
+        for (int sidx = 1; sidx <= BKL; ++sidx)
+          if (pv == sidx) { const double2 t = bw[0]; bw[0] = bw[sidx]; bw[sidx] = t; }
+#pragma unroll
+        for (int sidx = 1; sidx <= BKL; ++sidx) bw[sidx] = csub2(bw[sidx], cmul2(Lm[((size_t)k * BKL + (sidx - 1)) * S], bw[0]));
+        y[(size_t)k * S] = bw[0];
+#pragma unroll
+        for (int sidx = 0; sidx < BKL; ++sidx) bw[sidx] = bw[sidx + 1];
+        bw[BKL] = (k + 1 + BKL < n) ? y[(size_t)(k + 1 + BKL) * S] : make_double2(0.0, 0.0);
+      }
+      // backward: U y'' = y', window of 8 solved values; accumulate y^H x and y^H y on the way
+      double2 xw[BW - 1];
+#pragma unroll
+      for (int j = 0; j < BW - 1; ++j) xw[j] = make_double2(0.0, 0.0);
+      double2 yx = make_double2(0.0, 0.0);
+      double yy = 0.0;
+      for (int k = n - 1; k >= 0; --k) {
+        double2 acc = y[(size_t)k * S];
+#pragma unroll
+        for (int j = 1; j < BW; ++j) acc = csub2(acc, cmul2(U[((size_t)k * BW + j) * S], xw[j - 1]));
+        const double2 v = cdiv2(acc, U[((size_t)k * BW) * S]);
+        y[(size_t)k * S] = v;
+        const double2 xo = x[(size_t)k * S];
+        yx = cadd2(yx, cmulc2(v, xo));
+        yy += v.x * v.x + v.y * v.y;
+#pragma unroll
+        for (int j = BW - 2; j > 0; --j) xw[j] = xw[j - 1];
+        xw[0] = v;
+      }
+      const double2 om_new = cadd2(sigma, make_double2(yx.x / yy, yx.y / yy));
+      const double rn = rsqrt(yy);
+      for (int i = 0; i < n; ++i) {
+        const double2 v = y[(size_t)i * S];
+        x[(size_t)i * S] = make_double2(v.x * rn, v.y * rn);
+      }
+      dl = hypot(om_new.x - om.x, om_new.y - om.y);
+      om = om_new;
+      if (it > 0 && dl <= a.tol * hypot(om.x, om.y)) { ++it; break; }
+    }
+    total += it;
+    if (dl <= a.tol * hypot(om.x, om.y)) break;
+    sigma = om;
+  }
+  a.omega[inst] = om;
+  a.delta[inst] = dl;
+  a.iters[inst] = total;
+  if (a.evec) {
+    double best = -1.0;
+    int bi = 0;
+    for (int i = 0; i < n; ++i) {
+      const double2 v = x[(size_t)i * S];
+      const double m2 = v.x * v.x + v.y * v.y;
+      if (m2 > best) { best = m2; bi = i; }
+    }
+    const double2 esc = cdiv2(make_double2(1.0, 0.0), x[(size_t)bi * S]);
+    double2 *ev = a.evec + (size_t)inst * (n + 2);
+    ev[0] = make_double2(0.0, 0.0);
+    ev[n + 1] = make_double2(0.0, 0.0);
+    for (int i = 0; i < n; ++i) ev[i + 1] = cmul2(esc, x[(size_t)i * S]);
+  }
+}
+
+size_t chan_band_work_bytes(int n, int64_t ninst) {
+  return (size_t)ninst * (size_t)n * (sizeof(double2) * (BW + BKL + 2) + 1) + 256;
+}
+
+cudaError_t launch_chan_fd_banded(int n, const double *D2, const double *D4, const double *u, const double *d2u,
+                                  void *work, int64_t ninst, const double2 *alpha, const double *Re,
+                                  const double2 *sigma, int outer, int inner, double tol, double2 *omega,
+                                  double *delta, int32_t *iters, double2 *evec, cudaStream_t st) {
+  BandArgs a;
+  a.n = n; a.D2 = D2; a.D4 = D4; a.u = u; a.d2u = d2u; a.ninst = ninst; a.alpha = alpha; a.Re = Re; a.sigma = sigma;
+  a.outer = outer; a.inner = inner; a.tol = tol; a.omega = omega; a.delta = delta; a.iters = iters; a.evec = evec;
+  double2 *w = (double2 *)work;
+  const size_t N1 = (size_t)ninst * n;
+  a.U = w; a.L = w + N1 * BW; a.x = w + N1 * (BW + BKL); a.y = w + N1 * (BW + BKL + 1);
+  a.piv = (int8_t *)(w + N1 * (BW + BKL + 2));
+  const int threads = 32;  // few, long-running threads: spread them over all SMs
+  const unsigned grid = (unsigned)((ninst + threads - 1) / threads);
+  chan_fd_banded_kernel<<<grid, threads, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // Newton on alpha to Im(omega) = 0   (orrncbl.f:109-116, 962-981), one CTA per Re
 // ---------------------------------------------------------------------------
 struct NeutralArgs {

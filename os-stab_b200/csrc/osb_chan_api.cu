@@ -190,21 +190,28 @@ static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::ve
   int grid = 0;
   size_t smem = 0;
   CH_CUDA(ctx, cudaSetDevice(c->device));
-  CH_CUDA(ctx, chan_eig_grid(n, ninst, &grid, &smem));
+  // the FD operator is banded (half bandwidth 4): banded LU, one thread per instance
+  const bool banded = (c->disc == OSB_DISC_FD) && !getenv("OSB_FD_DENSE");
+  if (!banded) CH_CUDA(ctx, chan_eig_grid(n, ninst, &grid, &smem));
   double *d_in = nullptr, *d_out = nullptr;
   double2 *work = nullptr, *d_evec = nullptr;
   int32_t *d_it = nullptr;
   CH_CUDA(ctx, cudaMallocAsync(&d_in, ninst * 5 * sizeof(double), st));   // alpha(2), sigma(2), Re
   CH_CUDA(ctx, cudaMallocAsync(&d_out, ninst * 3 * sizeof(double), st));  // omega(2), delta
   CH_CUDA(ctx, cudaMallocAsync(&d_it, ninst * sizeof(int32_t), st));
-  CH_CUDA(ctx, cudaMallocAsync(&work, (size_t)grid * n * n * sizeof(double2), st));
+  CH_CUDA(ctx, cudaMallocAsync(&work, banded ? chan_band_work_bytes(n, ninst) : (size_t)grid * n * n * sizeof(double2), st));
   if (evec_host) CH_CUDA(ctx, cudaMallocAsync(&d_evec, (size_t)ninst * (n + 2) * sizeof(double2), st));
   CH_CUDA(ctx, cudaMemcpyAsync(d_in, alpha.data(), ninst * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   CH_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * ninst, sigma.data(), ninst * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   CH_CUDA(ctx, cudaMemcpyAsync(d_in + 4 * ninst, Re.data(), ninst * sizeof(double), cudaMemcpyHostToDevice, st));
-  CH_CUDA(ctx, launch_chan_eig(n, c->dD2, c->dD4, c->du, c->dd2u, work, grid, smem, ninst,
-                               (const double2 *)d_in, d_in + 4 * ninst, (const double2 *)(d_in + 2 * ninst), outer,
-                               inner, tol, (double2 *)d_out, d_out + 2 * ninst, d_it, d_evec, st));
+  if (banded)
+    CH_CUDA(ctx, launch_chan_fd_banded(n, c->dD2, c->dD4, c->du, c->dd2u, work, ninst, (const double2 *)d_in,
+                                       d_in + 4 * ninst, (const double2 *)(d_in + 2 * ninst), outer, inner, tol,
+                                       (double2 *)d_out, d_out + 2 * ninst, d_it, d_evec, st));
+  else
+    CH_CUDA(ctx, launch_chan_eig(n, c->dD2, c->dD4, c->du, c->dd2u, work, grid, smem, ninst,
+                                 (const double2 *)d_in, d_in + 4 * ninst, (const double2 *)(d_in + 2 * ninst), outer,
+                                 inner, tol, (double2 *)d_out, d_out + 2 * ninst, d_it, d_evec, st));
   ctx_count_launch(ctx, 1);
   omega.resize(2 * ninst); delta.resize(ninst); iters.resize(ninst);
   CH_CUDA(ctx, cudaMemcpyAsync(omega.data(), d_out, ninst * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -577,7 +577,10 @@ struct SlotState {  // what a point carries from one pass to the next
 };
 
 template <int INTEG, bool ANALYTIC>
-__global__ void __launch_bounds__(QT) shoot_queue_kernel(const __grid_constant__ ShootArgs a,
+#ifndef OSB_QUEUE_MIN_BLOCKS
+#define OSB_QUEUE_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(QT, OSB_QUEUE_MIN_BLOCKS) shoot_queue_kernel(const __grid_constant__ ShootArgs a,
                                                          unsigned long long *__restrict__ counter) {
   __shared__ SlotState slots[QT];
   __shared__ int warp_keep[QT / 32];

@@ -272,3 +272,24 @@ def test_full_size_properties(engine, osb, bl):
     r3 = engine.shoot_temporal(opts, bl, al[sub], Re[sub], r["c"][sub])
     ok = (r["status"][sub] == 0) & (r3["status"] == 0)
     assert rel(r3["c"][ok], r["c"][sub][ok]).max() < 1e-11
+
+
+def test_multi_device_context_matches_single(osb, engine, bl):
+    """osb_create_multi (one host thread driving several GPUs, the deployment of the
+    single-process Fortran hosts): results must be bit-identical to one device."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n = 5000
+    al = (0.179 + 0.000001 * np.arange(n)) * S2
+    Re = np.full(n, 580.0 * S2)
+    guess = np.full(n, complex(0.36412287, 0.0079597206))
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    one = engine.shoot_temporal(opts, bl, al, Re, guess)
+    eng2 = osb.Engine(devices=[0, 1])
+    p2 = eng2.solve_bl()
+    two = eng2.shoot_temporal(opts, p2, al, Re, guess)
+    p2.free()
+    eng2.close()
+    assert np.array_equal(one["c"], two["c"]) and np.array_equal(one["passes"], two["passes"])

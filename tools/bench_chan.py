@@ -45,7 +45,8 @@ def main():
         print(json.dumps({
             "N": N, "npts": args.npts, "seconds": dt, "eig_per_s": args.npts / dt,
             "converged": int((r["status"] == 0).sum()), "mean_inverse_iterations": float(r["iters"].mean()),
-            "lu_tflops_lower_bound": lu_flops / dt / 1e12, "factorisations": float(nfac),
+            "dense_lu_equiv_tflops": lu_flops / dt / 1e12, "factorisations": float(nfac),
+            "path": "banded LU (FD, half bandwidth 4)" if (args.disc == osb.DISC_FD and not __import__("os").environ.get("OSB_FD_DENSE")) else "dense blocked LU + DMMA",
             "tables_s": t_tables, "scan_9pts_s": t_scan}), flush=True)
         ch.free()
     eng.close()
