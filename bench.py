@@ -385,8 +385,12 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
-                "kernel": "osb::shoot_kernel<CK45, Hermitian>", "kernel_ms": kernel_ms,
+                "frac": achieved / peak_tf if peak_tf else None,
+                # ncu --set full, r01 capture (profiles/r01_shoot_queue_ncu_raw.csv): dram__bytes_read 40.2 B/point,
+                # write-back of 28 B/point; scaled to this launch's point count
+                "traffic": float(n) * (40.2 + 28.0), "traffic_unit": "bytes per launch (dram read+write)",
+                "kernel": "osb::shoot_queue_kernel<CK45, Hermitian>" if not os.environ.get("OSB_NO_QUEUE") else "osb::shoot_kernel<CK45, Hermitian>",
+                "kernel_ms": kernel_ms,
                 "flops_per_launch": flops_launch,
                 "how": "algorithmic flops = sum(passes) x nstep x 1122 (SURVEY 8d) / CUDA-event time of the launch on the "
                        "library's stream; peak = DFMA micro-benchmark (osb_measure_fp64_peak) run in this process "

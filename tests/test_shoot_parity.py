@@ -293,3 +293,25 @@ def test_multi_device_context_matches_single(osb, engine, bl):
     p2.free()
     eng2.close()
     assert np.array_equal(one["c"], two["c"]) and np.array_equal(one["passes"], two["passes"])
+
+
+def test_blasius_neutral_curve_critical_reynolds(engine, bl):
+    """SURVEY 8f item 4 (parity unpinned: the reference has no Blasius neutral curve).  Physical
+    check: the critical Reynolds number of the Blasius layer, Re_delta* = 519.4 (R = 301.8)."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import neutral_from_grid as nf
+
+    rows, ci, Re_in, alpha_in = nf.neutral_curve(engine, bl, na=256, nre=96)
+    assert len(rows) > 100
+    unstable = (ci > 0).any(axis=1)
+    Rcrit = Re_in[unstable][0]
+    assert 300.0 <= Rcrit < 310.0, Rcrit          # grid rows are 1.9 % apart in Re
+    # the nose of the curve: alpha ~ 0.176 (alpha delta* = 0.303), c_r ~ 0.397
+    nose = rows[np.argmin(rows[:, 0])]
+    assert abs(nose[1] - 0.176) < 0.01 and abs(nose[2] - 0.397) < 0.01
+    # two branches at higher Re
+    hi = rows[np.abs(rows[:, 0] - 1000.0) < 40.0]
+    assert (hi[:, 3] > 0).any() and (hi[:, 3] < 0).any()
