@@ -294,31 +294,72 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
   }
 }
 
-// x <- M^{-1} x using P M = L U.  x: shared, n complex.
+// x <- M^{-1} x using P M = L U.  x: shared, n complex.  Blocked by 16 columns: the
+// 16x16 diagonal block is staged in shared memory and solved by one warp with shuffles,
+// then all threads apply the 16 solved values to the remaining rows (coalesced column
+// reads): 2 barriers per block instead of one per column.
 __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv, double2 *x) {
-  const int tid = threadIdx.x, nt = blockDim.x;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double2 dblk[16][17];
   if (tid == 0)
     for (int k = 0; k < n; ++k) {
       const int p = ipiv[k];
       if (p != k) { const double2 t = x[k]; x[k] = x[p]; x[p] = t; }
     }
   __syncthreads();
-  for (int j = 0; j < n - 1; ++j) {  // L y = P b (unit lower)
-    const double2 xj = x[j];
-    const double2 *col = M + (size_t)j * n;
-    for (int r = j + 1 + tid; r < n; r += nt) x[r] = csub2(x[r], cmul2(col[r], xj));
-    __syncthreads();
-  }
-  for (int j = n - 1; j >= 0; --j) {  // U x = y
-    const double2 *col = M + (size_t)j * n;
-    if (tid == 0) {
-      double2 d = col[j];
-      if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
-      x[j] = cdiv2(x[j], d);
+  // ---- L y = P b (unit lower)
+  for (int j0 = 0; j0 < n; j0 += 16) {
+    const int nb = min(16, n - j0);
+    if (tid < 256) {
+      const int r = tid & 15, c = tid >> 4;
+      if (r < nb && c < nb) dblk[r][c] = M[(size_t)(j0 + c) * n + j0 + r];
     }
     __syncthreads();
-    const double2 xj = x[j];
-    for (int r = tid; r < j; r += nt) x[r] = csub2(x[r], cmul2(col[r], xj));
+    if (warp == 0) {
+      double2 xi = (lane < nb) ? x[j0 + lane] : make_double2(0.0, 0.0);
+      for (int t = 0; t < nb; ++t) {
+        const double xr = __shfl_sync(0xffffffffu, xi.x, t), xim = __shfl_sync(0xffffffffu, xi.y, t);
+        if (lane > t && lane < nb) xi = csub2(xi, cmul2(dblk[lane][t], make_double2(xr, xim)));
+      }
+      if (lane < nb) x[j0 + lane] = xi;
+    }
+    __syncthreads();
+    for (int r = j0 + nb + tid; r < n; r += nt) {
+      double2 acc = x[r];
+#pragma unroll 4
+      for (int t = 0; t < nb; ++t) acc = csub2(acc, cmul2(M[(size_t)(j0 + t) * n + r], x[j0 + t]));
+      x[r] = acc;
+    }
+    __syncthreads();
+  }
+  // ---- U x = y
+  for (int j0 = ((n - 1) / 16) * 16; j0 >= 0; j0 -= 16) {
+    const int nb = min(16, n - j0);
+    if (tid < 256) {
+      const int r = tid & 15, c = tid >> 4;
+      if (r < nb && c < nb) dblk[r][c] = M[(size_t)(j0 + c) * n + j0 + r];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      double2 xi = (lane < nb) ? x[j0 + lane] : make_double2(0.0, 0.0);
+      for (int t = nb - 1; t >= 0; --t) {
+        if (lane == t) {
+          double2 d = dblk[t][t];
+          if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
+          xi = cdiv2(xi, d);
+        }
+        const double xr = __shfl_sync(0xffffffffu, xi.x, t), xim = __shfl_sync(0xffffffffu, xi.y, t);
+        if (lane < t) xi = csub2(xi, cmul2(dblk[lane][t], make_double2(xr, xim)));
+      }
+      if (lane < nb) x[j0 + lane] = xi;
+    }
+    __syncthreads();
+    for (int r = tid; r < j0; r += nt) {
+      double2 acc = x[r];
+#pragma unroll 4
+      for (int t = 0; t < nb; ++t) acc = csub2(acc, cmul2(M[(size_t)(j0 + t) * n + r], x[j0 + t]));
+      x[r] = acc;
+    }
     __syncthreads();
   }
 }
