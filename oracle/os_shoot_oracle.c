@@ -703,3 +703,23 @@ int osr_shoot_spatial_line(int integrator, int nstep, double testalpha, double y
   }
   return 0;
 }
+
+/* One spatial point with the eigenfunction pass (orrspace with niter = 1, eigfun = 1,
+ * e.g. space.inp).  out: [alpha_re, alpha_im]; iout: [passes, qend, status]. */
+int osr_shoot_spatial_point(int integrator, int nstep, double testalpha, double ymin, double ymax,
+                            int nbl, const double *prof, double Re, double omega_re, double omega_im,
+                            double alpha_re, double alpha_im, double *out, int *iout,
+                            double *eigfun_y, double *eigfun_vmax) {
+  osr_state s;
+  memset(&s, 0, sizeof(s));
+  s.flow = OSR_FLOW_ORRSPACE; s.integrator = integrator; s.nstep = nstep;
+  s.testalpha = testalpha; s.to = ymin; s.tf = ymax; s.nbl = nbl;
+  size_t n = (size_t)nbl + 2;
+  s.ydat = prof; s.U = prof + n; s.Uspl = prof + 2 * n; s.d2U = prof + 3 * n; s.d2Uspl = prof + 4 * n;
+  s.Re = Re; s.alpha = CMPLX(alpha_re, alpha_im); s.omega = CMPLX(omega_re, omega_im);
+  osr_result r;
+  int st = osr_shoot(&s, &r, NULL, 0, eigfun_y, eigfun_vmax);
+  out[0] = r.eig[0]; out[1] = r.eig[1];
+  iout[0] = r.passes; iout[1] = r.qend; iout[2] = r.status;
+  return st;
+}

@@ -33,6 +33,8 @@ class Oracle:
         lib.osr_shoot_temporal_batch.argtypes = [i, i, i, d, d, d, i, _dp, i64, _dp, _dp, _dp, _ip, _ip, _ip]
         lib.osr_shoot_spatial_line.restype = i
         lib.osr_shoot_spatial_line.argtypes = [i, i, d, d, d, i, _dp, d, d, d, d, d, d, i, _dp, _ip, _ip, _ip]
+        lib.osr_shoot_spatial_point.restype = i
+        lib.osr_shoot_spatial_point.argtypes = [i, i, d, d, d, i, _dp, d, d, d, d, d, _dp, _ip, _dp, _dp]
 
     def solve_bl(self, variant=FLOW_CONTEBL, integrator=INT_CK45, nbl=1000, ymin=0.0, ymax=17.0, f2p=0.5, beta=0.0):
         """Returns (prof[5, nbl+2] = ydat,U,Uspl,d2U,d2Uspl zero padded, npass, f2p_last)."""
@@ -95,6 +97,25 @@ class Oracle:
         rows = rows.reshape(niter, 4)
         return dict(omega=rows[:, 0] + 1j * rows[:, 1], alpha=rows[:, 2] + 1j * rows[:, 3],
                     passes=ipass, qend=iq, status=ist)
+
+
+def _spatial_point(self, integrator, nstep, testalpha, ymin, ymax, prof, Re, omega, alpha):
+    """orrspace with niter = 1 and eigfun = 1 (space.inp)."""
+    out = np.zeros(2)
+    iout = np.zeros(3, dtype=np.int32)
+    y = np.zeros((nstep + 1) * 8)
+    vmax = np.zeros(2)
+    omega = complex(omega)
+    alpha = complex(alpha)
+    self.lib.osr_shoot_spatial_point(integrator, nstep, testalpha, ymin, ymax, prof.shape[1] - 2,
+                                     prof.ctypes.data_as(_dp), Re, omega.real, omega.imag, alpha.real, alpha.imag,
+                                     out.ctypes.data_as(_dp), iout.ctypes.data_as(_ip), y.ctypes.data_as(_dp),
+                                     vmax.ctypes.data_as(_dp))
+    return dict(alpha=complex(out[0], out[1]), passes=int(iout[0]), qend=int(iout[1]), status=int(iout[2]),
+                y=y.view(np.complex128).reshape(nstep + 1, 4), vmax=complex(vmax[0], vmax[1]))
+
+
+Oracle.shoot_spatial_point = _spatial_point
 
 
 def load(rebuild=True):

@@ -315,3 +315,44 @@ def test_blasius_neutral_curve_critical_reynolds(engine, bl):
     # two branches at higher Re
     hi = rows[np.abs(rows[:, 0] - 1000.0) < 40.0]
     assert (hi[:, 3] > 0).any() and (hi[:, 3] < 0).any()
+
+
+@pytest.mark.parametrize("n", [500, 2000, 4000, 16000])
+def test_resolution_ladder_decks(engine, osb, oracle, n):
+    """tiny / normal / big / biggest.inp of the reference: nbl = nstep = n, Ymax = 30 -- the
+    largest sizes the reference ships (stage table 16000 x 6 rows)."""
+    p = engine.solve_bl(osb.FLOW_CONTEBL, osb.INT_CK45, n, 0.0, 30.0, 0.5, 0.0)
+    t = p.tables()
+    prof, npass, _ = oracle.solve_bl(ob.FLOW_CONTEBL, ob.INT_CK45, n, 0.0, 30.0, 0.5, 0.0)
+    assert t["npass"] == npass and np.array_equal(t["U"], prof[1][: n + 1]) and np.array_equal(t["Uspl"], prof[2][: n + 1])
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    opts.nstep, opts.ymax = n, 30.0
+    r = engine.shoot_temporal(opts, p, [0.179 * S2], [580.0 * S2], [complex(0.36413124, 0.0079527387)])
+    p.free()
+    ref = oracle.shoot_temporal(ob.FLOW_CONTEBL, ob.INT_CK45, n, 10.0, 0.0, 30.0, prof, 0.179 * S2, 580.0 * S2,
+                                complex(0.36413124, 0.0079527387))
+    assert r["status"][0] == 0 and ref["status"] == 0
+    assert rel(r["c"][0], ref["c"]) < EIG_RTOL
+    assert abs(r["qend"][0] - ref["qend"]) <= 1 and abs(r["passes"][0] - ref["passes"]) <= 1
+
+
+def test_orrspace_space_deck_eigenfunction(engine, osb, oracle):
+    """space.inp: one spatial point (omega = 0.08, testalpha = 0.2) with the eigenfunction pass."""
+    fact = math.sqrt(2.0) / 1.7207876
+    ymin, ymax = 0.0, 20.0 * fact
+    p = engine.solve_bl(osb.FLOW_ORRSPACE, osb.INT_RK4, 1000, ymin, ymax, 0.5, 0.0)
+    opts = osb.shoot_defaults(osb.FLOW_ORRSPACE)
+    opts.nstep, opts.ymin, opts.ymax, opts.testalpha = 1000, ymin, ymax, 0.2
+    Re, om, a0 = 1000.0 * fact, complex(0.08, 0.0) * fact, complex(0.228047, -0.00651) * fact
+    r = engine.shoot_spatial_lines(opts, p, [Re], [om], [0.0], [a0], 1)
+    e = engine.eigfun(opts, p, [Re], r["alpha"][0], omega=[om])
+    p.free()
+    prof, _, _ = oracle.solve_bl(ob.FLOW_ORRSPACE, ob.INT_RK4, 1000, ymin, ymax, 0.5, 0.0)
+    ref = oracle.shoot_spatial_point(ob.INT_RK4, 1000, 0.2, ymin, ymax, prof, Re, om, a0)
+    assert r["status"][0, 0] == 0 and ref["status"] == 0
+    assert rel(r["alpha"][0, 0], ref["alpha"]) < 1e-9      # errtol of orrspace is 1e-8 (orrspace.f:277)
+    assert abs(r["alpha"][0, 0] / fact - complex(0.2318124, -0.0064175)) < 1e-6
+    assert e["qend"][0] == ref["qend"]
+    y, yr = e["y"][0] / e["vmax"][0], ref["y"] / ref["vmax"]
+    for i in range(4):
+        assert np.max(np.abs(y[:, i] - yr[:, i])) / np.max(np.abs(yr[:, i])) < 1e-7
