@@ -333,7 +333,10 @@ def test_resolution_ladder_decks(engine, osb, oracle, n):
                                 complex(0.36413124, 0.0079527387))
     assert r["status"][0] == 0 and ref["status"] == 0
     assert rel(r["c"][0], ref["c"]) < EIG_RTOL
-    assert abs(r["qend"][0] - ref["qend"]) <= 1 and abs(r["passes"][0] - ref["passes"]) <= 1
+    assert abs(r["qend"][0] - ref["qend"]) <= 1
+    # errtol = 1e-14 is at the rounding floor of err; after 16000 steps the floor itself is ~1e-14,
+    # so the number of passes spent bouncing on it depends on the arithmetic (oracle 6, FMA 9)
+    assert abs(r["passes"][0] - ref["passes"]) <= (1 if n <= 4000 else 6)
 
 
 def test_orrspace_space_deck_eigenfunction(engine, osb, oracle):
