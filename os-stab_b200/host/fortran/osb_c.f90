@@ -112,5 +112,44 @@ module osb_c
       complex(c_double_complex), intent(out) :: vmax(*)
       integer(c_int32_t), intent(out) :: qend(*)
     end function
+    !> replaces MAKE_CHANNEL_METRICS + MAKE_DERIVATIVES + INIT_CHANNEL_PROFILE
+    !! (orrfdchan.f:111-113, orrcolchan.f:67-70, orrncbl.f:98-107)
+    integer(c_int) function osb_chan_create(ctx, disc, N, chan) bind(C, name="osb_chan_create")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: disc, N          ! disc: 0 FD, 1 Chebyshev, 2 Chebyshev + numerical U''
+      type(c_ptr), intent(out) :: chan
+    end function
+    integer(c_int) function osb_chan_free(ctx, chan) bind(C, name="osb_chan_free")
+      import :: c_int, c_ptr
+      type(c_ptr), value :: ctx, chan
+    end function
+    !> replaces the alpha loop around MAKE_MATRIX + SOLVE_ORR_SOM (orrfdchan.f:116-121)
+    integer(c_int) function osb_chan_eig(ctx, chan, Re, npts, alpha, sigma0, omega, evec, iters, status) &
+        bind(C, name="osb_chan_eig")
+      import :: c_int, c_int32_t, c_int64_t, c_ptr, c_double, c_double_complex
+      type(c_ptr), value :: ctx, chan
+      real(c_double), value :: Re
+      integer(c_int64_t), value :: npts
+      complex(c_double_complex), intent(in) :: alpha(*)
+      type(c_ptr), value :: sigma0               ! c_null_ptr: let the library scan for the mode
+      complex(c_double_complex), intent(out) :: omega(*)
+      type(c_ptr), value :: evec                 ! c_null_ptr or c_loc of complex (0:N, npts)
+      integer(c_int32_t), intent(out) :: iters(*), status(*)
+    end function
+    !> replaces the `do while (abs(IMAG(eigenvalue)).gt.1.0e-8)` Newton loop (orrncbl.f:109-116)
+    integer(c_int) function osb_chan_neutral(ctx, chan, nRe, Re, alpha0, sfac, tol, maxit, alpha_out, &
+                                             omega, steps, status, trace) bind(C, name="osb_chan_neutral")
+      import :: c_int, c_int32_t, c_int64_t, c_ptr, c_double, c_double_complex
+      type(c_ptr), value :: ctx, chan
+      integer(c_int64_t), value :: nRe
+      real(c_double), intent(in) :: Re(*), alpha0(*)
+      real(c_double), value :: sfac, tol
+      integer(c_int32_t), value :: maxit
+      real(c_double), intent(out) :: alpha_out(*)
+      complex(c_double_complex), intent(out) :: omega(*)
+      integer(c_int32_t), intent(out) :: steps(*), status(*)
+      type(c_ptr), value :: trace                ! c_null_ptr or c_loc of real (7, maxit, nRe)
+    end function
   end interface
 end module osb_c
