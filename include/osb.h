@@ -152,13 +152,15 @@ int osb_shoot_temporal_dev(osb_ctx *ctx, const osb_shoot_opts *opts,
  *   omega0 [2*nlines], domega [nlines]   omega_i = omega0 + i*domega (real part)
  *   alpha0 [2*nlines]  guess for the first point
  *   alpha_out [nlines*niter*2], passes/qend/status [nlines*niter]
+ *   history [nlines*niter*hist_cap*4] optional: per pass alpha (ctemp), err -- the rows of
+ *   the per-pass table orrspace prints (orrspace.f:485-488)
  */
 int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts,
                             const osb_profile *prof, int64_t nlines, int32_t niter,
                             const double *Re, const double *omega0,
                             const double *domega, const double *alpha0,
                             double *alpha_out, int32_t *passes, int32_t *qend,
-                            int32_t *status);
+                            int32_t *status, double *history, int32_t hist_cap);
 
 /*
  * Eigenfunction pass (the "second pass" shoot.f:762-810 / 338-385): for each

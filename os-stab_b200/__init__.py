@@ -88,7 +88,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "osb_shoot_defaults": (C.c_int, [C.c_int, C.POINTER(ShootOpts)]),
         "osb_shoot_temporal": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, _dp, _dp, _dp, _ip, _ip, _ip, _dp, _dp, i32]),
         "osb_shoot_temporal_dev": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
-        "osb_shoot_spatial_lines": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, i32, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _ip]),
+        "osb_shoot_spatial_lines": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, i32, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _ip, _dp, i32]),
         "osb_eigfun": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, _dp, _dp, _dp, _dp, _dp, _dp, _ip]),
         "osb_measure_fp64_peak": (C.c_int, [vp, dbl, _dp, _dp]),
         "osb_chan_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
@@ -281,7 +281,7 @@ class Engine:
             self.ctx, C.byref(opts), prof.handle, int(npts), d_alpha, d_Re, d_c, d_passes, d_qend, d_status,
             d_resid or None, d_history or None, hist_cap))
 
-    def shoot_spatial_lines(self, opts: ShootOpts, prof: Profile, Re, omega0, domega, alpha0, niter):
+    def shoot_spatial_lines(self, opts: ShootOpts, prof: Profile, Re, omega0, domega, alpha0, niter, hist_cap=0):
         Re = _f64(Re)
         n = Re.size
         om = _cplx_pairs(omega0, n)
@@ -291,12 +291,16 @@ class Engine:
         passes = np.zeros(n * niter, dtype=np.int32)
         qend = np.zeros(n * niter, dtype=np.int32)
         status = np.zeros(n * niter, dtype=np.int32)
+        hist = np.zeros(n * niter * hist_cap * 4) if hist_cap else None
         self._check(self.lib.osb_shoot_spatial_lines(
             self.ctx, C.byref(opts), prof.handle, n, niter, Re.ctypes.data_as(_dp), om.ctypes.data_as(_dp),
             dom.ctypes.data_as(_dp), a0.ctypes.data_as(_dp), out.ctypes.data_as(_dp), passes.ctypes.data_as(_ip),
-            qend.ctypes.data_as(_ip), status.ctypes.data_as(_ip)))
-        return dict(alpha=out.view(np.complex128).reshape(n, niter), passes=passes.reshape(n, niter),
-                    qend=qend.reshape(n, niter), status=status.reshape(n, niter))
+            qend.ctypes.data_as(_ip), status.ctypes.data_as(_ip), hist.ctypes.data_as(_dp) if hist_cap else None, hist_cap))
+        r = dict(alpha=out.view(np.complex128).reshape(n, niter), passes=passes.reshape(n, niter),
+                 qend=qend.reshape(n, niter), status=status.reshape(n, niter))
+        if hist_cap:
+            r["history"] = hist.reshape(n, niter, hist_cap, 4)
+        return r
 
     def eigfun(self, opts: ShootOpts, prof: Profile, Re, eig, alpha=None, omega=None):
         Re = _f64(Re)

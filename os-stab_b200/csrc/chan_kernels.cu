@@ -121,13 +121,17 @@ __device__ void assemble_shifted(double2 *__restrict__ M, int n, const double *_
                                  const double *__restrict__ D4, const double *__restrict__ u,
                                  const double *__restrict__ d2u, const PencilCoef &p, double2 sigma) {
   const double2 sb2 = cmul2(sigma, p.b2), sb0 = cmul2(sigma, p.b0);
-  for (size_t e = threadIdx.x; e < (size_t)n * n; e += blockDim.x) {
-    const int i = (int)(e % n), j = (int)(e / n);
+  // a thread keeps its row(s) i and walks the columns: the row coefficient is computed once
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double2 w2 = csub2(coef_w2(p, u[i]), sb2);
-    const double d2 = D2[e], d4 = D4[e];
-    double2 v = make_double2(fma(w2.x, d2, d4), w2.y * d2);
-    if (i == j) v = cadd2(v, csub2(coef_w0(p, u[i], d2u[i]), sb0));
-    M[e] = v;
+    const double2 w0 = csub2(coef_w0(p, u[i], d2u[i]), sb0);
+    for (int j = 0; j < n; ++j) {
+      const size_t e = (size_t)j * n + i;
+      const double d2 = D2[e], d4 = D4[e];
+      double2 v = make_double2(fma(w2.x, d2, d4), w2.y * d2);
+      if (i == j) v = cadd2(v, w0);
+      M[e] = v;
+    }
   }
   __syncthreads();
 }
@@ -456,8 +460,16 @@ __device__ ChanShared carve(unsigned char *smem, int n) {
   return s;
 }
 
+// Small operators (n <= 96: chan.inp, nc.inp, fd-64.inp) keep the whole matrix in shared
+// memory next to the panel, so every phase runs at shared-memory latency.
+constexpr int CH_NSMEM = 96;
+__host__ __device__ inline bool chan_matrix_in_smem(int n) { return n <= CH_NSMEM; }
+__host__ __device__ inline size_t chan_fixed_smem(int n) {
+  size_t b = sizeof(double2) * ((size_t)(n + 16) * CH_NB + 3 * (size_t)n) + sizeof(double) * 64 + sizeof(int) * (size_t)(n + 8);
+  return (b + 15) & ~(size_t)15;
+}
 size_t chan_smem_bytes(int n) {
-  return sizeof(double2) * ((size_t)(n + 16) * CH_NB + 3 * (size_t)n) + sizeof(double) * 64 + sizeof(int) * (size_t)(n + 8);
+  return chan_fixed_smem(n) + (chan_matrix_in_smem(n) ? sizeof(double2) * (size_t)n * n : 0);
 }
 
 // Right inverse iteration with the current LU: x (unit 2-norm, shared) in/out.
@@ -527,7 +539,7 @@ __global__ void __launch_bounds__(CH_THREADS) chan_eig_kernel(const __grid_const
   extern __shared__ __align__(16) unsigned char smem[];
   const int n = a.n;
   ChanShared s = carve(smem, n);
-  double2 *M = a.work + (size_t)blockIdx.x * n * n;
+  double2 *M = chan_matrix_in_smem(n) ? (double2 *)(smem + chan_fixed_smem(n)) : a.work + (size_t)blockIdx.x * n * n;
   for (int64_t inst = blockIdx.x; inst < a.ninst; inst += gridDim.x) {
     const PencilCoef p = pencil_coef(a.alpha[inst], a.Re[inst]);
     double2 sigma = a.sigma[inst];
@@ -812,7 +824,7 @@ __global__ void __launch_bounds__(CH_THREADS) chan_neutral_kernel(const __grid_c
   extern __shared__ __align__(16) unsigned char smem[];
   const int n = a.n;
   ChanShared s = carve(smem, n);
-  double2 *M = a.work + (size_t)blockIdx.x * n * n;
+  double2 *M = chan_matrix_in_smem(n) ? (double2 *)(smem + chan_fixed_smem(n)) : a.work + (size_t)blockIdx.x * n * n;
   for (int64_t inst = blockIdx.x; inst < a.ninst; inst += gridDim.x) {
     const double Re = a.Re[inst];
     double nalpha = a.alpha0[inst];

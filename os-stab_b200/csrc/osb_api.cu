@@ -526,7 +526,8 @@ int osb_shoot_temporal(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profi
 int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof,
                             int64_t nlines, int32_t niter, const double *Re, const double *omega0,
                             const double *domega, const double *alpha0, double *alpha_out,
-                            int32_t *passes, int32_t *qend, int32_t *status) {
+                            int32_t *passes, int32_t *qend, int32_t *status, double *history,
+                            int32_t hist_cap) {
   if (!ctx || nlines < 0 || niter < 1 || !Re || !omega0 || !domega || !alpha0 || !alpha_out ||
       !passes || !qend || !status)
     return fail(ctx, OSB_E_ARG, "null argument");
@@ -539,7 +540,8 @@ int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_
   if (rc) return rc;
   if (nlines == 0) return OSB_OK;
   const int ndev = (int)ctx->devices.size();
-  struct Buf { double *in = 0, *out = 0; int32_t *ip = 0; double2 *tab = 0; int64_t lo = 0, hi = 0; };
+  if (history && hist_cap < 1) return fail(ctx, OSB_E_ARG, "hist_cap < 1");
+  struct Buf { double *in = 0, *out = 0, *hist = 0; int32_t *ip = 0; double2 *tab = 0; int64_t lo = 0, hi = 0; };
   std::vector<Buf> bufs(ndev);
   for (int d = 0; d < ndev; ++d) {
     Buf &b = bufs[d];
@@ -552,6 +554,10 @@ int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_
     OSB_CUDA(ctx, cudaMallocAsync(&b.in, n * 6 * sizeof(double), st));
     OSB_CUDA(ctx, cudaMallocAsync(&b.out, n * niter * 2 * sizeof(double), st));
     OSB_CUDA(ctx, cudaMallocAsync(&b.ip, n * niter * 3 * sizeof(int32_t), st));
+    if (history) {
+      OSB_CUDA(ctx, cudaMallocAsync(&b.hist, (size_t)n * niter * hist_cap * 4 * sizeof(double), st));
+      OSB_CUDA(ctx, cudaMemsetAsync(b.hist, 0, (size_t)n * niter * hist_cap * 4 * sizeof(double), st));
+    }
     OSB_CUDA(ctx, cudaMemcpyAsync(b.in, Re + b.lo, n * sizeof(double), cudaMemcpyHostToDevice, st));
     OSB_CUDA(ctx, cudaMemcpyAsync(b.in + n, domega + b.lo, n * sizeof(double), cudaMemcpyHostToDevice, st));
     OSB_CUDA(ctx, cudaMemcpyAsync(b.in + 2 * n, omega0 + 2 * b.lo, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -567,6 +573,8 @@ int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_
     a.alpha = (const double2 *)(b.in + 4 * n);
     a.ev = (double2 *)b.out;
     a.passes = b.ip; a.qend = b.ip + n * niter; a.status = b.ip + 2 * n * niter;
+    a.history = (double4 *)b.hist;
+    a.hist_cap = history ? hist_cap : 0;
     int nl = 0;
     OSB_CUDA(ctx, launch_shoot(a, opts->integrator, analytic, st, &nl));
     ctx->launches += nl;
@@ -582,6 +590,11 @@ int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_
     OSB_CUDA(ctx, cudaMemcpyAsync(passes + b.lo * niter, b.ip, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     OSB_CUDA(ctx, cudaMemcpyAsync(qend + b.lo * niter, b.ip + m, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     OSB_CUDA(ctx, cudaMemcpyAsync(status + b.lo * niter, b.ip + 2 * m, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (history) {
+      OSB_CUDA(ctx, cudaMemcpyAsync(history + (size_t)b.lo * niter * hist_cap * 4, b.hist,
+                                    (size_t)m * hist_cap * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      OSB_CUDA(ctx, cudaFreeAsync(b.hist, st));
+    }
     OSB_CUDA(ctx, cudaFreeAsync(b.in, st));
     OSB_CUDA(ctx, cudaFreeAsync(b.out, st));
     OSB_CUDA(ctx, cudaFreeAsync(b.ip, st));

@@ -87,7 +87,8 @@ module osb_c
     end function
     !> replaces the omega loop around `call CONTE` (orrspace.f:186-195)
     integer(c_int) function osb_shoot_spatial_lines(ctx, opts, prof, nlines, niter, Re, omega0, &
-                                                    domega, alpha0, alpha_out, passes, qend, status) &
+                                                    domega, alpha0, alpha_out, passes, qend, status, &
+                                                    history, hist_cap) &
         bind(C, name="osb_shoot_spatial_lines")
       import :: c_int, c_int32_t, c_int64_t, c_ptr, c_double, c_double_complex, osb_shoot_opts
       type(c_ptr), value :: ctx, prof
@@ -98,6 +99,8 @@ module osb_c
       complex(c_double_complex), intent(in) :: omega0(*), alpha0(*)
       complex(c_double_complex), intent(out) :: alpha_out(niter, *)
       integer(c_int32_t), intent(out) :: passes(niter, *), qend(niter, *), status(niter, *)
+      real(c_double), intent(out) :: history(4, hist_cap, niter, *)   ! ctemp, err per pass (orrspace.f:485-488)
+      integer(c_int32_t), value :: hist_cap
     end function
     !> replaces the "second pass" (shoot.f:762-810): y(i,k) un-normalised + vmax
     integer(c_int) function osb_eigfun(ctx, opts, prof, npts, alpha, Re, eig, omega, y, vmax, qend) &

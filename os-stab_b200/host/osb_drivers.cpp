@@ -427,13 +427,20 @@ static int run_orrspace(osb_ctx *ctx) {
   std::vector<double> aout((size_t)niter * 2);
   std::vector<int32_t> passes(niter), qend(niter), status(niter);
   double om0[2] = {omega.real(), omega.imag()}, a0[2] = {alpha.real(), alpha.imag()};
+  const int hcap = 50;  // orrspace's pass limit (orrspace.f:277)
+  std::vector<double> hist((size_t)niter * hcap * 4);
   CK(ctx, osb_shoot_spatial_lines(ctx, &o, prof, 1, niter, &Re, om0, &domega, a0, aout.data(), passes.data(), qend.data(),
-                                  status.data()));
+                                  status.data(), hist.data(), hcap));
   FILE *f17 = fopen("fort.17", "w");
   const double pfac = 1.7207877 / std::sqrt(2.);  // orrspace.f:485-486,495-498 (note the ...77)
   int bad = 0;
   for (int i = 0; i < niter; ++i) {
     const cd om(omega.real() + i * domega, omega.imag()), al(aout[2 * i], aout[2 * i + 1]);
+    for (int k = 0; k < passes[i] && k < hcap; ++k) {  // per-pass table, orrspace.f:485-488 (format 30)
+      const double *hr = &hist[((size_t)i * hcap + k) * 4];
+      printf(" %s    %s %s    %s %s    %s\n", I(k + 1, 2).c_str(), E(hr[0] * pfac, 15, 8).c_str(), E(hr[1] * pfac, 15, 8).c_str(),
+             E(hr[2], 15, 8).c_str(), E(hr[3], 15, 8).c_str(), E(std::hypot(hr[2], hr[3]), 15, 8).c_str());
+    }
     printf("\nOmega = (%s %s)    Alpha = (%s %s)\n\n", E(om.real() * pfac, 15, 8).c_str(), E(om.imag() * pfac, 15, 8).c_str(),
            E(al.real() * pfac, 15, 8).c_str(), E(al.imag() * pfac, 15, 8).c_str());
     fprintf(f17, " %s  %s  %s  \n", E((om * facti).real(), 17, 8).c_str(), E((al * facti).real(), 17, 8).c_str(),

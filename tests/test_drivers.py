@@ -166,6 +166,10 @@ def test_orrspace_sweep_fort17(tmp_path, oracle):
     for i, (w, ar, ai) in expect.items():
         assert abs(f17[i, 0] - w) < 1e-9 and abs(f17[i, 1] - ar) < 2e-8 and abs(f17[i, 2] - ai) < 2e-9
     assert r.stdout.count("Omega = (") == 50
+    # per-pass table (orrspace.f:485-488): 402 rows in total for this deck, first row = the deck's guess
+    rows = [ln for ln in r.stdout.splitlines() if len(ln) > 80 and ln[:3].strip().isdigit() and "Omega" not in ln]
+    assert abs(len(rows) - 402) <= 3
+    assert rows[0].split()[0] == "1" and abs(float(rows[0].split()[1]) - 0.13809592) < 1e-7
     assert "displacement thickness to match Mack" in r.stdout
 
 
