@@ -19,7 +19,10 @@
 //       reference's use of the LEFT eigenvector of inv(B)A (oracle D-7), obtained as
 //       vl = B^H u with u from inverse iteration on (A - sigma B)^H.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
 
 #include "osb_cplx.cuh"
 #include "osb_internal.h"
@@ -50,6 +53,10 @@ __device__ __forceinline__ double2 cmulc2(double2 a, double2 b) {  // conj(a) * 
   return make_double2(a.x * b.x + a.y * b.y, a.x * b.y - a.y * b.x);
 }
 __device__ __forceinline__ double2 csub2(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+// a - l*b with four DFMAs (instead of DMUL + DFMA + DADD per component)
+__device__ __forceinline__ double2 cfnma2(double2 a, double2 l, double2 b) {
+  return make_double2(fma(-l.x, b.x, fma(l.y, b.y, a.x)), fma(-l.x, b.y, fma(-l.y, b.x, a.y)));
+}
 __device__ __forceinline__ double2 cadd2(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ double2 cdiv2(double2 a, double2 b) {
   zd r = zdiv(zd{a.x, a.y}, zd{b.x, b.y});
@@ -194,8 +201,7 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
       for (int r = j + 1 + tid; r < mp; r += nt) {
         const double2 l = cmul2(panel[j * ldp + r], rinv);
         panel[j * ldp + r] = l;
-        for (int c = j + 1; c < nb; ++c)
-          panel[c * ldp + r] = csub2(panel[c * ldp + r], cmul2(l, panel[c * ldp + j]));
+        for (int c = j + 1; c < nb; ++c) panel[c * ldp + r] = cfnma2(panel[c * ldp + r], l, panel[c * ldp + j]);
       }
       __syncthreads();
     }
@@ -228,7 +234,7 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
         if (i < nb) {
           double2 s = a[i];
 #pragma unroll
-          for (int t = 0; t < i; ++t) s = csub2(s, cmul2(panel[t * ldp + i], a[t]));
+          for (int t = 0; t < i; ++t) s = cfnma2(s, panel[t * ldp + i], a[t]);
           a[i] = s;
         }
       }
@@ -323,7 +329,7 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
       double2 xi = (lane < nb) ? x[j0 + lane] : make_double2(0.0, 0.0);
       for (int t = 0; t < nb; ++t) {
         const double xr = __shfl_sync(0xffffffffu, xi.x, t), xim = __shfl_sync(0xffffffffu, xi.y, t);
-        if (lane > t && lane < nb) xi = csub2(xi, cmul2(dblk[lane][t], make_double2(xr, xim)));
+        if (lane > t && lane < nb) xi = cfnma2(xi, dblk[lane][t], make_double2(xr, xim));
       }
       if (lane < nb) x[j0 + lane] = xi;
     }
@@ -331,7 +337,7 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
     for (int r = j0 + nb + tid; r < n; r += nt) {
       double2 acc = x[r];
 #pragma unroll 4
-      for (int t = 0; t < nb; ++t) acc = csub2(acc, cmul2(M[(size_t)(j0 + t) * n + r], x[j0 + t]));
+      for (int t = 0; t < nb; ++t) acc = cfnma2(acc, M[(size_t)(j0 + t) * n + r], x[j0 + t]);
       x[r] = acc;
     }
     __syncthreads();
@@ -353,7 +359,7 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
           xi = cdiv2(xi, d);
         }
         const double xr = __shfl_sync(0xffffffffu, xi.x, t), xim = __shfl_sync(0xffffffffu, xi.y, t);
-        if (lane < t) xi = csub2(xi, cmul2(dblk[lane][t], make_double2(xr, xim)));
+        if (lane < t) xi = cfnma2(xi, dblk[lane][t], make_double2(xr, xim));
       }
       if (lane < nb) x[j0 + lane] = xi;
     }
@@ -361,7 +367,7 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
     for (int r = tid; r < j0; r += nt) {
       double2 acc = x[r];
 #pragma unroll 4
-      for (int t = 0; t < nb; ++t) acc = csub2(acc, cmul2(M[(size_t)(j0 + t) * n + r], x[j0 + t]));
+      for (int t = 0; t < nb; ++t) acc = cfnma2(acc, M[(size_t)(j0 + t) * n + r], x[j0 + t]);
       x[r] = acc;
     }
     __syncthreads();
@@ -535,7 +541,13 @@ __device__ void start_vector(double2 *x, int n) {
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(CH_THREADS) chan_eig_kernel(const __grid_constant__ ChanArgs a) {
+// Two register budgets for the same body: up to n ~ 350 two CTAs fit an SM by shared
+// memory and 128 registers/thread keeps them both resident; beyond that the 135 KB panel
+// allows one CTA only and the body may use the full register file.
+__device__ __forceinline__ void chan_eig_body(const ChanArgs &a);
+__global__ void __launch_bounds__(CH_THREADS, 2) chan_eig_kernel(const __grid_constant__ ChanArgs a) { chan_eig_body(a); }
+__global__ void __launch_bounds__(CH_THREADS, 1) chan_eig_kernel_big(const __grid_constant__ ChanArgs a) { chan_eig_body(a); }
+__device__ __forceinline__ void chan_eig_body(const ChanArgs &a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int n = a.n;
   ChanShared s = carve(smem, n);
@@ -680,7 +692,7 @@ __global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constan
         const double2 l = cmul2(w[sidx][0], rinv);
         Lm[((size_t)k * BKL + (sidx - 1)) * S] = l;
 #pragma unroll
-        for (int j = 1; j < BW; ++j) w[sidx][j] = csub2(w[sidx][j], cmul2(l, w[0][j]));
+        for (int j = 1; j < BW; ++j) w[sidx][j] = cfnma2(w[sidx][j], l, w[0][j]);
       }
 #pragma unroll
       for (int j = 0; j < BW; ++j) U[((size_t)k * BW + j) * S] = (j == 0) ? pvt : w[0][j];
@@ -721,7 +733,7 @@ __global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constan
         for (int sidx = 1; sidx <= BKL; ++sidx)
           if (pv == sidx) { const double2 t = bw[0]; bw[0] = bw[sidx]; bw[sidx] = t; }
 #pragma unroll
-        for (int sidx = 1; sidx <= BKL; ++sidx) bw[sidx] = csub2(bw[sidx], cmul2(Lm[((size_t)k * BKL + (sidx - 1)) * S], bw[0]));
+        for (int sidx = 1; sidx <= BKL; ++sidx) bw[sidx] = cfnma2(bw[sidx], Lm[((size_t)k * BKL + (sidx - 1)) * S], bw[0]);
         y[(size_t)k * S] = bw[0];
 #pragma unroll
         for (int sidx = 0; sidx < BKL; ++sidx) bw[sidx] = bw[sidx + 1];
@@ -736,7 +748,7 @@ __global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constan
       for (int k = n - 1; k >= 0; --k) {
         double2 acc = y[(size_t)k * S];
 #pragma unroll
-        for (int j = 1; j < BW; ++j) acc = csub2(acc, cmul2(U[((size_t)k * BW + j) * S], xw[j - 1]));
+        for (int j = 1; j < BW; ++j) acc = cfnma2(acc, U[((size_t)k * BW + j) * S], xw[j - 1]);
         const double2 v = cdiv2(acc, U[((size_t)k * BW) * S]);
         y[(size_t)k * S] = v;
         const double2 xo = x[(size_t)k * S];
@@ -902,6 +914,328 @@ __global__ void __launch_bounds__(CH_THREADS) chan_neutral_kernel(const __grid_c
 }
 
 // ---------------------------------------------------------------------------
+// K4s: small operators (n <= 64: chan.inp, nc.inp), ONE WARP per instance.  The CTA-wide
+// kernels above spend most of their time in barriers when the matrix is only 63 x 63;
+// here a warp keeps its matrix in shared memory (lane l owns rows l and l+32), pivots with
+// shuffles and needs only __syncwarp.  Same algorithm (partial-pivoting LU, shift-invert
+// iteration with re-shift, Newton on alpha), same results to rounding.
+// ---------------------------------------------------------------------------
+constexpr int WN_MAX = 64;
+
+struct WarpShared {
+  double2 *M, *x, *y, *t;
+  int *ipiv;
+};
+__host__ __device__ inline size_t warp_smem_bytes(int n) {
+  return sizeof(double2) * ((size_t)n * n + 3 * (size_t)n) + sizeof(int) * (size_t)(n + 4);
+}
+__device__ WarpShared wcarve(unsigned char *smem, int n) {
+  WarpShared s;
+  s.M = (double2 *)smem;
+  s.x = s.M + (size_t)n * n;
+  s.y = s.x + n;
+  s.t = s.y + n;
+  s.ipiv = (int *)(s.t + n);
+  return s;
+}
+__device__ __forceinline__ double2 wsum(double2 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    v.x += __shfl_xor_sync(0xffffffffu, v.x, o);
+    v.y += __shfl_xor_sync(0xffffffffu, v.y, o);
+  }
+  return v;
+}
+
+__device__ void w_assemble(double2 *M, int n, const double *__restrict__ D2, const double *__restrict__ D4,
+                           const double *__restrict__ u, const double *__restrict__ d2u, const PencilCoef &p,
+                           double2 sigma) {
+  const int lane = threadIdx.x & 31;
+  const double2 sb2 = cmul2(sigma, p.b2), sb0 = cmul2(sigma, p.b0);
+  for (int i = lane; i < n; i += 32) {
+    const double2 w2 = csub2(coef_w2(p, u[i]), sb2);
+    const double2 w0 = csub2(coef_w0(p, u[i], d2u[i]), sb0);
+#pragma unroll 8
+    for (int j = 0; j < n; ++j) {
+      const size_t e = (size_t)j * n + i;
+      const double d2 = __ldg(D2 + e), d4 = __ldg(D4 + e);
+      double2 v = make_double2(fma(w2.x, d2, d4), w2.y * d2);
+      if (i == j) v = cadd2(v, w0);
+      M[e] = v;
+    }
+  }
+  __syncwarp();
+}
+
+__device__ void w_lu(double2 *M, int n, int *ipiv) {
+  const int lane = threadIdx.x & 31;
+  for (int k = 0; k < n; ++k) {
+    double best = -1.0;
+    int bi = k;
+    for (int r = lane; r < n; r += 32)
+      if (r >= k) {
+        const double2 v = M[(size_t)k * n + r];
+        const double a = fabs(v.x) + fabs(v.y);
+        if (a > best) { best = a; bi = r; }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    if (lane == 0) ipiv[k] = bi;
+    if (bi != k)
+      for (int j = lane; j < n; j += 32) {
+        const double2 t = M[(size_t)j * n + k];
+        M[(size_t)j * n + k] = M[(size_t)j * n + bi];
+        M[(size_t)j * n + bi] = t;
+      }
+    __syncwarp();
+    double2 piv = M[(size_t)k * n + k];
+    if (piv.x == 0.0 && piv.y == 0.0) piv = make_double2(1.0e-290, 0.0);
+    const double2 rinv = cdiv2(make_double2(1.0, 0.0), piv);
+    for (int r = lane; r < n; r += 32)
+      if (r > k) {
+        const double2 l = cmul2(M[(size_t)k * n + r], rinv);
+        M[(size_t)k * n + r] = l;
+        int j = k + 1;
+        for (; j + 3 < n; j += 4) {  // loads first, then stores: the compiler cannot prove that the
+                                     // pivot-row elements do not alias the row being written
+          double2 *c0 = M + (size_t)j * n, *c1 = c0 + n, *c2 = c1 + n, *c3 = c2 + n;
+          const double2 u0 = c0[k], u1 = c1[k], u2 = c2[k], u3 = c3[k];
+          const double2 m0 = c0[r], m1 = c1[r], m2 = c2[r], m3 = c3[r];
+          c0[r] = cfnma2(m0, l, u0); c1[r] = cfnma2(m1, l, u1); c2[r] = cfnma2(m2, l, u2); c3[r] = cfnma2(m3, l, u3);
+        }
+        for (; j < n; ++j) M[(size_t)j * n + r] = cfnma2(M[(size_t)j * n + r], l, M[(size_t)j * n + k]);
+      }
+    __syncwarp();
+  }
+}
+
+__device__ void w_solve(const double2 *M, int n, const int *ipiv, double2 *x) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0)
+    for (int k = 0; k < n; ++k) {
+      const int p = ipiv[k];
+      if (p != k) { const double2 t = x[k]; x[k] = x[p]; x[p] = t; }
+    }
+  __syncwarp();
+  for (int k = 0; k < n - 1; ++k) {
+    const double2 xk = x[k];
+    for (int r = lane; r < n; r += 32)
+      if (r > k) x[r] = cfnma2(x[r], M[(size_t)k * n + r], xk);
+    __syncwarp();
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    if (lane == 0) {
+      double2 d = M[(size_t)k * n + k];
+      if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
+      x[k] = cdiv2(x[k], d);
+    }
+    __syncwarp();
+    const double2 xk = x[k];
+    for (int r = lane; r < k; r += 32) x[r] = cfnma2(x[r], M[(size_t)k * n + r], xk);
+    __syncwarp();
+  }
+}
+
+__device__ void w_solve_h(const double2 *M, int n, const int *ipiv, double2 *x) {
+  const int lane = threadIdx.x & 31;
+  for (int j = 0; j < n; ++j) {  // U^H a = r
+    double2 s = make_double2(0.0, 0.0);
+    for (int i = lane; i < j; i += 32) s = cadd2(s, cmulc2(M[(size_t)j * n + i], x[i]));
+    s = wsum(s);
+    if (lane == 0) {
+      const double2 dj = M[(size_t)j * n + j];
+      x[j] = cdiv2(csub2(x[j], s), make_double2(dj.x, -dj.y));
+    }
+    __syncwarp();
+  }
+  for (int j = n - 1; j >= 0; --j) {  // L^H b = a
+    double2 s = make_double2(0.0, 0.0);
+    for (int i = j + 1 + lane; i < n; i += 32) s = cadd2(s, cmulc2(M[(size_t)j * n + i], x[i]));
+    s = wsum(s);
+    if (lane == 0) x[j] = csub2(x[j], s);
+    __syncwarp();
+  }
+  if (lane == 0)
+    for (int k = n - 1; k >= 0; --k) {
+      const int p = ipiv[k];
+      if (p != k) { const double2 t = x[k]; x[k] = x[p]; x[p] = t; }
+    }
+  __syncwarp();
+}
+
+__device__ void w_d2_matvec(const double *__restrict__ D2, int n, const double2 *x, double2 *y, bool transpose) {
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < n; i += 32) {
+    double sr = 0.0, si = 0.0;
+    if (!transpose) {
+#pragma unroll 8
+      for (int j = 0; j < n; ++j) { const double d = __ldg(D2 + (size_t)j * n + i); sr = fma(d, x[j].x, sr); si = fma(d, x[j].y, si); }
+    } else {
+      const double *col = D2 + (size_t)i * n;
+#pragma unroll 8
+      for (int j = 0; j < n; ++j) { const double d = __ldg(col + j); sr = fma(d, x[j].x, sr); si = fma(d, x[j].y, si); }
+    }
+    y[i] = make_double2(sr, si);
+  }
+  __syncwarp();
+}
+
+__device__ void w_start_vector(double2 *x, int n) {
+  for (int i = threadIdx.x & 31; i < n; i += 32) {
+    const double s = sin(3.0 * (i + 1.0) / (n + 1.0)) + 0.37 * cos(11.0 * (i + 1.0) / (n + 1.0));
+    x[i] = make_double2(s, 0.25 * s * s - 0.1);
+  }
+  __syncwarp();
+}
+
+__device__ double2 w_inverse_iterate(const WarpShared &s, int n, const double *D2, const PencilCoef &p, double2 sigma,
+                                     int maxit, double tol, double *delta, int *iters) {
+  const int lane = threadIdx.x & 31;
+  double2 om = sigma;
+  double dl = 1.0e300;
+  int it = 0;
+  for (; it < maxit; ++it) {
+    w_d2_matvec(D2, n, s.x, s.y, false);
+    for (int i = lane; i < n; i += 32) s.y[i] = cadd2(cmul2(p.b2, s.y[i]), cmul2(p.b0, s.x[i]));
+    __syncwarp();
+    w_solve(s.M, n, s.ipiv, s.y);
+    double2 yx = make_double2(0.0, 0.0), yy = make_double2(0.0, 0.0);
+    for (int i = lane; i < n; i += 32) {
+      yx = cadd2(yx, cmulc2(s.y[i], s.x[i]));
+      yy.x += s.y[i].x * s.y[i].x + s.y[i].y * s.y[i].y;
+    }
+    yx = wsum(yx);
+    yy = wsum(yy);
+    const double2 om_new = cadd2(sigma, make_double2(yx.x / yy.x, yx.y / yy.x));
+    const double rn = rsqrt(yy.x);
+    for (int i = lane; i < n; i += 32) s.x[i] = make_double2(s.y[i].x * rn, s.y[i].y * rn);
+    __syncwarp();
+    dl = hypot(om_new.x - om.x, om_new.y - om.y);
+    om = om_new;
+    if (it > 0 && dl <= tol * hypot(om.x, om.y)) { ++it; break; }
+  }
+  *delta = dl;
+  *iters = it;
+  return om;
+}
+
+__global__ void __launch_bounds__(32) chan_eig_warp_kernel(const __grid_constant__ ChanArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int n = a.n, lane = threadIdx.x & 31;
+  WarpShared s = wcarve(smem, n);
+  for (int64_t inst = blockIdx.x; inst < a.ninst; inst += gridDim.x) {
+    const PencilCoef p = pencil_coef(a.alpha[inst], a.Re[inst]);
+    double2 sigma = a.sigma[inst];
+    w_start_vector(s.x, n);
+    double2 om = sigma;
+    double dl = 1.0e300;
+    int total = 0;
+    for (int o = 0; o < a.outer; ++o) {
+      w_assemble(s.M, n, a.D2, a.D4, a.u, a.d2u, p, sigma);
+      w_lu(s.M, n, s.ipiv);
+      int it = 0;
+      om = w_inverse_iterate(s, n, a.D2, p, sigma, a.inner, a.tol, &dl, &it);
+      total += it;
+      if (dl <= a.tol * hypot(om.x, om.y)) break;
+      sigma = om;
+    }
+    if (lane == 0) { a.omega[inst] = om; a.delta[inst] = dl; a.iters[inst] = total; }
+    if (a.evec) {
+      double best = -1.0;
+      int bi = 0;
+      for (int i = lane; i < n; i += 32) {
+        const double m2 = s.x[i].x * s.x[i].x + s.x[i].y * s.x[i].y;
+        if (m2 > best) { best = m2; bi = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      const double2 esc = cdiv2(make_double2(1.0, 0.0), s.x[bi]);
+      double2 *ev = a.evec + (size_t)inst * (n + 2);
+      for (int i = lane; i < n; i += 32) ev[i + 1] = cmul2(esc, s.x[i]);
+      if (lane == 0) { ev[0] = make_double2(0.0, 0.0); ev[n + 1] = make_double2(0.0, 0.0); }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(32) chan_neutral_warp_kernel(const __grid_constant__ NeutralArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int n = a.n, lane = threadIdx.x & 31;
+  WarpShared s = wcarve(smem, n);
+  for (int64_t inst = blockIdx.x; inst < a.ninst; inst += gridDim.x) {
+    const double Re = a.Re[inst];
+    double nalpha = a.alpha0[inst];
+    double2 sigma = a.sigma0[inst];
+    double2 ev = make_double2(1.0, 1.0);
+    int it = 0, st = OSB_ST_MAXCOUNT;
+    while (fabs(ev.y) > a.tol && it < a.maxit) {
+      const PencilCoef p = pencil_coef(make_double2(nalpha, 0.0), Re);
+      w_start_vector(s.x, n);
+      double dl = 1.0e300;
+      for (int o = 0; o < 3; ++o) {
+        w_assemble(s.M, n, a.D2, a.D4, a.u, a.d2u, p, sigma);
+        w_lu(s.M, n, s.ipiv);
+        int k = 0;
+        ev = w_inverse_iterate(s, n, a.D2, p, sigma, 8, 1.0e-14, &dl, &k);
+        if (dl <= 1.0e-14 * hypot(ev.x, ev.y)) break;
+        sigma = ev;
+      }
+      for (int i = lane; i < n; i += 32) s.t[i] = make_double2(s.x[i].x, -s.x[i].y + 0.3);
+      __syncwarp();
+      for (int k = 0; k < 6; ++k) {
+        w_solve_h(s.M, n, s.ipiv, s.t);
+        w_d2_matvec(a.D2, n, s.t, s.y, true);
+        double nn = 0.0;
+        for (int i = lane; i < n; i += 32) {
+          const double2 v = cadd2(cmulc2(p.b2, s.y[i]), cmulc2(p.b0, s.t[i]));
+          s.t[i] = v;
+          nn += v.x * v.x + v.y * v.y;
+        }
+        const double rn = rsqrt(wsum(make_double2(nn, 0.0)).x);
+        for (int i = lane; i < n; i += 32) s.t[i] = make_double2(s.t[i].x * rn, s.t[i].y * rn);
+        __syncwarp();
+      }
+      w_d2_matvec(a.D2, n, s.x, s.y, false);
+      double2 dw = make_double2(0.0, 0.0), dalp = make_double2(0.0, 0.0);
+      for (int i = lane; i < n; i += 32) {
+        const double2 d2x = s.y[i], xi = s.x[i];
+        const double2 tdw = csub2(csub2(cmul2(cmul2(p.db0, ev), xi), cmul2(coef_d2(p, a.u[i]), d2x)),
+                                  cmul2(coef_d0(p, a.u[i], a.d2u[i]), xi));
+        const double2 tbx = cadd2(cmul2(p.b2, d2x), cmul2(p.b0, xi));
+        dw = cadd2(dw, cmulc2(s.t[i], tdw));
+        dalp = cadd2(dalp, cmulc2(s.t[i], tbx));
+      }
+      dw = wsum(dw);
+      dalp = wsum(dalp);
+      const double2 q = cdiv2(dw, dalp);
+      const double2 dwda = make_double2(-q.x, -q.y);
+      const double dalpha = -ev.y / dwda.y;
+      nalpha = nalpha + a.sfac * dalpha;
+      const double nw = ev.x + a.sfac * dalpha * dwda.x;
+      if (a.trace && lane == 0) {
+        double *r = a.trace + ((size_t)inst * a.maxit + it) * 7;
+        r[0] = nalpha; r[1] = ev.x; r[2] = ev.y; r[3] = dwda.x; r[4] = dwda.y; r[5] = dalpha; r[6] = nw;
+      }
+      sigma = make_double2(nw, ev.y);
+      ++it;
+      if (!(isfinite(nalpha) && isfinite(ev.x) && isfinite(ev.y))) { st = OSB_ST_NONFINITE; break; }
+      __syncwarp();
+    }
+    if (fabs(ev.y) <= a.tol) st = OSB_ST_CONVERGED;
+    if (lane == 0) { a.alpha_out[inst] = nalpha; a.omega_out[inst] = ev; a.steps[inst] = it; a.status[inst] = st; }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------
 struct ChanLaunch {
@@ -936,10 +1270,30 @@ void chan_profile_dump(const char *tag) {
   cudaMemcpyToSymbol(g_chan_prof, h, sizeof(h));
 }
 
+static bool use_warp_kernels(int n) { return n <= WN_MAX && !getenv("OSB_CHAN_NO_WARP"); }
+
+static cudaError_t warp_grid(int n, int64_t ninst, int *grid, size_t *smem, const void *func) {
+  *smem = warp_smem_bytes(n);
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 0, per = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, func, 32, *smem);
+  if (e != cudaSuccess) return e;
+  if (per < 1) return cudaErrorInvalidConfiguration;
+  *grid = (int)std::min<int64_t>(ninst, (int64_t)sms * per);
+  return cudaSuccess;
+}
+
+static bool use_big_kernel(int n) { return 2 * chan_smem_bytes(n) > 220 * 1024; }
+
 cudaError_t chan_eig_grid(int n, int64_t ninst, int *grid, size_t *smem) {
-  return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel);
+  if (use_warp_kernels(n)) return warp_grid(n, ninst, grid, smem, (const void *)chan_eig_warp_kernel);
+  return chan_grid(n, ninst, grid, smem, use_big_kernel(n) ? (const void *)chan_eig_kernel_big : (const void *)chan_eig_kernel);
 }
 cudaError_t chan_neutral_grid(int n, int64_t ninst, int *grid, size_t *smem) {
+  if (use_warp_kernels(n)) return warp_grid(n, ninst, grid, smem, (const void *)chan_neutral_warp_kernel);
   return chan_grid(n, ninst, grid, smem, (const void *)chan_neutral_kernel);
 }
 
@@ -951,7 +1305,9 @@ cudaError_t launch_chan_eig(int n, const double *D2, const double *D4, const dou
   a.n = n; a.D2 = D2; a.D4 = D4; a.u = u; a.d2u = d2u; a.work = work; a.ninst = ninst;
   a.alpha = alpha; a.Re = Re; a.sigma = sigma; a.outer = outer; a.inner = inner; a.tol = tol;
   a.omega = omega; a.delta = delta; a.iters = iters; a.evec = evec;
-  chan_eig_kernel<<<grid, CH_THREADS, smem, st>>>(a);
+  if (use_warp_kernels(n)) chan_eig_warp_kernel<<<grid, 32, smem, st>>>(a);
+  else if (use_big_kernel(n)) chan_eig_kernel_big<<<grid, CH_THREADS, smem, st>>>(a);
+  else chan_eig_kernel<<<grid, CH_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -964,7 +1320,8 @@ cudaError_t launch_chan_neutral(int n, const double *D2, const double *D4, const
   a.n = n; a.D2 = D2; a.D4 = D4; a.u = u; a.d2u = d2u; a.work = work; a.ninst = ninst;
   a.Re = Re; a.alpha0 = alpha0; a.sigma0 = sigma0; a.sfac = sfac; a.tol = tol; a.maxit = maxit;
   a.alpha_out = alpha_out; a.omega_out = omega_out; a.steps = steps; a.status = status; a.trace = trace;
-  chan_neutral_kernel<<<grid, CH_THREADS, smem, st>>>(a);
+  if (use_warp_kernels(n)) chan_neutral_warp_kernel<<<grid, 32, smem, st>>>(a);
+  else chan_neutral_kernel<<<grid, CH_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
 
