@@ -196,6 +196,19 @@ class ChanOracle:
             r["evec"] = ev.view(np.complex128)
         return r
 
+    def arbiter(self, alpha, Re, sigma, iters=4):
+        """Quad-precision eigenvalue of the same discrete pencil nearest `sigma` (os_chan_arbiter.c)."""
+        self.lib.osr_chan_arbiter.argtypes = [C.c_int, _dp, _dp, _dp, _dp, C.c_double, C.c_double, C.c_double,
+                                              C.c_double, C.c_double, C.c_int, _dp]
+        D2 = np.ascontiguousarray(self.table(4)); D4 = np.ascontiguousarray(self.table(5))
+        u = self.table(1); d2u = self.table(3)
+        out = np.zeros(4)
+        alpha = complex(alpha); sigma = complex(sigma)
+        self.lib.osr_chan_arbiter(self.n, D2.ctypes.data_as(_dp), D4.ctypes.data_as(_dp), u.ctypes.data_as(_dp),
+                                  d2u.ctypes.data_as(_dp), alpha.real, alpha.imag, Re, sigma.real, sigma.imag, iters,
+                                  out.ctypes.data_as(_dp))
+        return complex(out[0], out[1])
+
     def neutral(self, Re, sfac, alpha_r, tol=1.0e-8, maxit=200):
         tr = np.zeros(7 * maxit)
         it = self.lib.osr_chan_neutral(self.h, Re, sfac, alpha_r, tol, maxit, tr.ctypes.data_as(_dp))

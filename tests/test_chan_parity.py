@@ -112,3 +112,29 @@ def test_orrncbl_neutral_point(engine, oracle):
         assert abs(complex(t0[1], t0[2]) - complex(tr[0, 1], tr[0, 2])) < 1e-8
         assert abs(complex(t0[3], t0[4]) - complex(tr[0, 3], tr[0, 4])) < 1e-6 * abs(complex(tr[0, 3], tr[0, 4])) + 1e-9
     c.close()
+
+
+@pytest.mark.parametrize("N", [64, 128, 256])
+def test_collocation_against_quad_arbiter(engine, oracle, N):
+    """for Chebyshev collocation the reference's LAPACK routes are themselves
+    inaccurate (ill-scaled pencil), so the fp64 oracle cannot arbitrate 1e-10.  The quad-precision
+    arbiter solves the same discrete pencil to ~1e-25; the GPU path must be at least as close to
+    it as the reference's route, and within 1e-10 where fp64 allows (N = 64)."""
+    ch = engine.chan(ob.DISC_CHEB, N)
+    r = ch.solve([1.0], 1.0e4)
+    ch.free()
+    c = ob.chan(ob.DISC_CHEB, N)
+    spec = c.solve_col(1.0, 1.0e4)["spectrum"]
+    w_ref = spec[np.argmin(np.abs(spec - (0.2375 + 0.0037j)))]
+    w_quad = c.arbiter(1.0, 1.0e4, r["omega"][0])
+    c.close()
+    e_gpu = abs(r["omega"][0] - w_quad) / abs(w_quad)
+    e_ref = abs(w_ref - w_quad) / abs(w_quad)
+    print(f"N={N}: gpu err {e_gpu:.2e}, reference-route (ZGEGV) err {e_ref:.2e}")
+    assert r["status"][0] == 0
+    assert e_gpu <= max(e_ref, 1e-12)
+    if N == 64:
+        assert e_gpu < 1e-10
+    # the discrete eigenvalue converges to the shooting value 0.23752648882+0.0037396706230i
+    if N >= 128:
+        assert abs(w_quad - complex(0.23752648882, 0.0037396706230)) < 1e-9
