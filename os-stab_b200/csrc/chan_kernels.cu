@@ -201,18 +201,39 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
       for (int r = j + 1 + tid; r < mp; r += nt) {
         const double2 l = cmul2(panel[j * ldp + r], rinv);
         panel[j * ldp + r] = l;
-        for (int c = j + 1; c < nb; ++c) panel[c * ldp + r] = cfnma2(panel[c * ldp + r], l, panel[c * ldp + j]);
+        // chunks of 4 columns with the loads issued before the stores: the compiler cannot prove
+        // that the pivot-row loads do not alias the row being written and would serialise the loop
+        for (int c0 = j + 1; c0 < nb; c0 += 4) {
+          double2 uu[4], m[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c = min(c0 + q, nb - 1);
+            uu[q] = panel[c * ldp + j];
+            m[q] = panel[c * ldp + r];
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (c0 + q < nb) panel[(c0 + q) * ldp + r] = cfnma2(m[q], l, uu[q]);
+        }
       }
       __syncthreads();
     }
     PROF_ADD(1);
     // ---- row interchanges on the columns outside the panel; write the panel back
-    for (int c = tid; c < n; c += nt) {
-      if (c >= k0 && c < k0 + nb) continue;
-      double2 *col = M + (size_t)c * n;
+    // two columns per thread, interleaved: two independent chains of dependent swaps in flight
+    for (int c = tid; c < n; c += 2 * nt) {
+      const int cb = c + nt;
+      const bool doa = !(c >= k0 && c < k0 + nb), dob = cb < n && !(cb >= k0 && cb < k0 + nb);
+      double2 *cola = M + (size_t)c * n, *colb = M + (size_t)(dob ? cb : c) * n;
       for (int j = 0; j < nb; ++j) {
         const int p = ipiv[k0 + j];
-        if (p != k0 + j) { const double2 t = col[k0 + j]; col[k0 + j] = col[p]; col[p] = t; }
+        if (p != k0 + j) {
+          double2 ta, pa, tb, pb;
+          if (doa) { ta = cola[k0 + j]; pa = cola[p]; }
+          if (dob) { tb = colb[k0 + j]; pb = colb[p]; }
+          if (doa) { cola[k0 + j] = pa; cola[p] = ta; }
+          if (dob) { colb[k0 + j] = pb; colb[p] = tb; }
+        }
       }
     }
     for (int e = tid; e < mp * nb; e += nt) {
