@@ -29,7 +29,9 @@
 
 namespace osb {
 
-constexpr int CH_THREADS = 256;
+constexpr int CH_THREADS = 256;      // CTAs of the 2-per-SM variant and of the Newton kernel
+constexpr int CH_THREADS_BIG = 512;  // the 1-per-SM variant (n > ~350): more warps to hide L2/HBM latency
+constexpr int CH_THREADS_MAX = 512;
 constexpr int CH_NB = 16;
 
 // optional phase timers (cycles of block 0, thread 0); read back when OSB_CHAN_PROFILE is set
@@ -150,7 +152,7 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
   const int tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   const int ldp = n + 16;
-  int *red_i = (int *)(red + 2 * (CH_THREADS / 32));
+  int *red_i = (int *)(red + 2 * (CH_THREADS_MAX / 32));
   for (int k0 = 0; k0 < n; k0 += CH_NB) {
     const int nb = min(CH_NB, n - k0), mp = n - k0;
     PROF_T0();
@@ -408,7 +410,7 @@ __device__ void cta_solve_h(const double2 *__restrict__ M, int n, const int *ipi
       s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
       s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
     }
-    __shared__ double2 part[CH_THREADS / 32];
+    __shared__ double2 part[CH_THREADS_MAX / 32];
     if ((tid & 31) == 0) part[tid >> 5] = s;
     __syncthreads();
     if (tid == 0) {
@@ -428,7 +430,7 @@ __device__ void cta_solve_h(const double2 *__restrict__ M, int n, const int *ipi
       s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
       s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
     }
-    __shared__ double2 part2[CH_THREADS / 32];
+    __shared__ double2 part2[CH_THREADS_MAX / 32];
     if ((tid & 31) == 0) part2[tid >> 5] = s;
     __syncthreads();
     if (tid == 0) {
@@ -567,7 +569,7 @@ __device__ void start_vector(double2 *x, int n) {
 // allows one CTA only and the body may use the full register file.
 __device__ __forceinline__ void chan_eig_body(const ChanArgs &a);
 __global__ void __launch_bounds__(CH_THREADS, 2) chan_eig_kernel(const __grid_constant__ ChanArgs a) { chan_eig_body(a); }
-__global__ void __launch_bounds__(CH_THREADS, 1) chan_eig_kernel_big(const __grid_constant__ ChanArgs a) { chan_eig_body(a); }
+__global__ void __launch_bounds__(CH_THREADS_BIG, 1) chan_eig_kernel_big(const __grid_constant__ ChanArgs a) { chan_eig_body(a); }
 __device__ __forceinline__ void chan_eig_body(const ChanArgs &a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int n = a.n;
@@ -604,8 +606,8 @@ __device__ __forceinline__ void chan_eig_body(const ChanArgs &a) {
         const double m2 = s.x[i].x * s.x[i].x + s.x[i].y * s.x[i].y;
         if (m2 > best) { best = m2; bi = i; }
       }
-      __shared__ double sb[CH_THREADS];
-      __shared__ int si[CH_THREADS];
+      __shared__ double sb[CH_THREADS_MAX];
+      __shared__ int si[CH_THREADS_MAX];
       sb[threadIdx.x] = best; si[threadIdx.x] = bi;
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -1264,14 +1266,14 @@ struct ChanLaunch {
   const double *D2, *D4, *u, *d2u;
 };
 
-static cudaError_t chan_grid(int n, int64_t ninst, int *grid, size_t *smem, const void *func) {
+static cudaError_t chan_grid(int n, int64_t ninst, int *grid, size_t *smem, const void *func, int threads = CH_THREADS) {
   *smem = chan_smem_bytes(n);
   cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 0, per = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, func, CH_THREADS, *smem);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, func, threads, *smem);
   if (e != cudaSuccess) return e;
   if (per < 1) return cudaErrorInvalidConfiguration;
   *grid = (int)std::min<int64_t>(ninst, (int64_t)sms * per);
@@ -1311,7 +1313,8 @@ static bool use_big_kernel(int n) { return 2 * chan_smem_bytes(n) > 220 * 1024; 
 
 cudaError_t chan_eig_grid(int n, int64_t ninst, int *grid, size_t *smem) {
   if (use_warp_kernels(n)) return warp_grid(n, ninst, grid, smem, (const void *)chan_eig_warp_kernel);
-  return chan_grid(n, ninst, grid, smem, use_big_kernel(n) ? (const void *)chan_eig_kernel_big : (const void *)chan_eig_kernel);
+  if (use_big_kernel(n)) return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel_big, CH_THREADS_BIG);
+  return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel);
 }
 cudaError_t chan_neutral_grid(int n, int64_t ninst, int *grid, size_t *smem) {
   if (use_warp_kernels(n)) return warp_grid(n, ninst, grid, smem, (const void *)chan_neutral_warp_kernel);
@@ -1327,7 +1330,7 @@ cudaError_t launch_chan_eig(int n, const double *D2, const double *D4, const dou
   a.alpha = alpha; a.Re = Re; a.sigma = sigma; a.outer = outer; a.inner = inner; a.tol = tol;
   a.omega = omega; a.delta = delta; a.iters = iters; a.evec = evec;
   if (use_warp_kernels(n)) chan_eig_warp_kernel<<<grid, 32, smem, st>>>(a);
-  else if (use_big_kernel(n)) chan_eig_kernel_big<<<grid, CH_THREADS, smem, st>>>(a);
+  else if (use_big_kernel(n)) chan_eig_kernel_big<<<grid, CH_THREADS_BIG, smem, st>>>(a);
   else chan_eig_kernel<<<grid, CH_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
