@@ -94,6 +94,9 @@ int osb_profile_blasius_batch(osb_ctx *ctx, int variant, int integrator, int nbl
 int osb_profile_upload(osb_ctx *ctx, int variant, int nbl, double ymin, double ymax,
                        const double *U, const double *Uspl, const double *d2U,
                        const double *d2Uspl, osb_profile **prof);
+/* A copy of `prof` in the frame moving with u_c, splines rebuilt (replaces SHIFT_BL,
+ * conteucbl.f:924-968): U = U - uc; Uspl = SPLINE(U); d2U := Uspl; d2Uspl = SPLINE(d2U). */
+int osb_profile_shift(osb_ctx *ctx, const osb_profile *prof, double uc, osb_profile **shifted);
 /* The channel profile U = 1 - y^2 (no tables). */
 int osb_profile_channel(osb_ctx *ctx, osb_profile **prof);
 /* Copy the tables back ([nbl+1] each; any pointer may be NULL). */

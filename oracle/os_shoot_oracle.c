@@ -723,3 +723,14 @@ int osr_shoot_spatial_point(int integrator, int nstep, double testalpha, double 
   iout[0] = r.passes; iout[1] = r.qend; iout[2] = r.status;
   return st;
 }
+
+/* SHIFT_BL, conteucbl.f:924-968.  in/out: 5 arrays of nbl+2 doubles as in osr_solve_bl. */
+void osr_profile_shift(int nbl, double uc, const double *in, double *out) {
+  const size_t n2 = (size_t)nbl + 2;
+  double *ydat = out, *U = out + n2, *Uspl = out + 2 * n2, *d2U = out + 3 * n2, *d2Uspl = out + 4 * n2;
+  for (int i = 0; i <= nbl; ++i) { ydat[i] = in[i]; U[i] = in[n2 + i] - uc; }
+  osr_spline(nbl + 1, ydat, U, Uspl);
+  for (int i = 0; i <= nbl; ++i) d2U[i] = Uspl[i];
+  osr_spline(nbl + 1, ydat, d2U, d2Uspl);
+  ydat[nbl + 1] = U[nbl + 1] = Uspl[nbl + 1] = d2U[nbl + 1] = d2Uspl[nbl + 1] = 0.0;
+}

@@ -81,6 +81,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "osb_profile_blasius": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, dbl, dbl, dbl, dbl, C.POINTER(vp)]),
         "osb_profile_blasius_batch": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, dbl, dbl, i64, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _ip]),
         "osb_profile_upload": (C.c_int, [vp, C.c_int, C.c_int, dbl, dbl, _dp, _dp, _dp, _dp, C.POINTER(vp)]),
+        "osb_profile_shift": (C.c_int, [vp, vp, dbl, C.POINTER(vp)]),
         "osb_profile_channel": (C.c_int, [vp, C.POINTER(vp)]),
         "osb_profile_get": (C.c_int, [vp, vp, _dp, _dp, _dp, _dp, _dp, _ip, _dp]),
         "osb_profile_nbl": (C.c_int, [vp]),
@@ -107,7 +108,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
 EXPORTED_SYMBOLS = (
     "osb_version osb_create osb_create_multi osb_destroy osb_device_count osb_last_error osb_stream "
     "osb_launch_count osb_profile_blasius osb_profile_blasius_batch osb_profile_upload "
-    "osb_profile_channel osb_profile_get osb_profile_nbl osb_profile_free osb_shoot_defaults "
+    "osb_profile_shift osb_profile_channel osb_profile_get osb_profile_nbl osb_profile_free osb_shoot_defaults "
     "osb_shoot_temporal osb_shoot_temporal_dev osb_shoot_spatial_lines osb_eigfun osb_measure_fp64_peak "
     "osb_chan_create osb_chan_free osb_chan_tables osb_chan_eig osb_chan_neutral"
 ).split()
@@ -168,6 +169,12 @@ class Profile:
         out["npass"] = npass.value
         out["f2p"] = f2p.value
         return out
+
+    def shifted(self, uc) -> "Profile":
+        """SHIFT_BL (conteucbl.f:924): the profile in the frame moving with u_c."""
+        h = C.c_void_p()
+        self.engine._check(self.engine.lib.osb_profile_shift(self.engine.ctx, self.handle, float(uc), C.byref(h)))
+        return Profile(self.engine, h)
 
     def free(self):
         if self.handle:

@@ -351,6 +351,28 @@ int osb_profile_upload(osb_ctx *ctx, int variant, int nbl, double ymin, double y
   return OSB_OK;
 }
 
+int osb_profile_shift(osb_ctx *ctx, const osb_profile *prof, double uc, osb_profile **out) {
+  if (!ctx || !prof || !out || prof->dev.size() != ctx->devices.size()) return OSB_E_ARG;
+  const ProfileDev &p0 = prof->dev[0];
+  if (!p0.tables) return fail(ctx, OSB_E_ARG, "profile has no tables");
+  osb_profile *q = nullptr;
+  int rc = profile_alloc(ctx, p0.variant, p0.nbl, p0.ymin, p0.ymax, &q);
+  if (rc) return rc;
+  for (size_t i = 0; i < ctx->devices.size(); ++i) {
+    cudaStream_t st = ctx->streams[i];
+    OSB_CUDA(ctx, cudaSetDevice(q->dev[i].device));
+    double *scr = nullptr;
+    OSB_CUDA(ctx, cudaMallocAsync(&scr, 2 * ((size_t)p0.nbl + 2) * sizeof(double), st));
+    OSB_CUDA(ctx, launch_shift_profile(p0.nbl, uc, prof->dev[i].tables, q->dev[i].tables, scr, st));
+    ctx->launches++;
+    OSB_CUDA(ctx, cudaFreeAsync(scr, st));
+    OSB_CUDA(ctx, cudaStreamSynchronize(st));
+    q->dev[i].npass = p0.npass; q->dev[i].f2p_last = p0.f2p_last;
+  }
+  *out = q;
+  return OSB_OK;
+}
+
 int osb_profile_channel(osb_ctx *ctx, osb_profile **out) {
   if (!ctx || !out) return OSB_E_ARG;
   return profile_alloc(ctx, OSB_FLOW_CONTE, 0, -1.0, 1.0, out);

@@ -85,6 +85,8 @@ cudaError_t launch_blasius(int variant, int integrator, int nbl, double ymin, do
                            double *d_tables /*[nprof][5][nbl+2]*/, double *d_scratch,
                            double *d_f2p_out, int32_t *d_npass, cudaStream_t st);
 size_t blasius_scratch_doubles(int nbl, int64_t nprof);
+cudaError_t launch_shift_profile(int nbl, double uc, const double *d_in, double *d_out, double *d_scratch,
+                                 cudaStream_t st);
 // channel matrix path (chan_kernels.cu)
 size_t chan_smem_bytes(int n);
 void chan_profile_dump(const char *tag);

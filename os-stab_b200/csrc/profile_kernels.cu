@@ -179,6 +179,27 @@ __global__ void blasius_kernel(int variant, int integrator, int nbl, double ymin
   ydat[last] = 0.0; U[last] = 0.0; Uspl[last] = 0.0; d2U[last] = 0.0; d2Uspl[last] = 0.0;
 }
 
+// SHIFT_BL of conteucbl.f:924-968: move the profile to a frame travelling with u_c and
+// rebuild both splines:  U = Uorg - uc;  Uspl = SPLINE(U);  d2U := Uspl;  d2Uspl = SPLINE(d2U).
+// in/out tables: [5][nbl+2] (ydat, U, Uspl, d2U, d2Uspl); scratch: 2*(nbl+2).  One thread.
+__global__ void shift_profile_kernel(int nbl, double uc, const double *__restrict__ in,
+                                     double *__restrict__ out, double *__restrict__ scratch) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const size_t n2 = (size_t)nbl + 2;
+  double *ydat = out, *U = out + n2, *Uspl = out + 2 * n2, *d2U = out + 3 * n2, *d2Uspl = out + 4 * n2;
+  for (int i = 0; i <= nbl; ++i) { ydat[i] = in[i]; U[i] = S(in[n2 + i], uc); }
+  spline_strided(nbl + 1, ydat, U, Uspl, scratch, scratch + n2, 1);
+  for (int i = 0; i <= nbl; ++i) d2U[i] = Uspl[i];
+  spline_strided(nbl + 1, ydat, d2U, d2Uspl, scratch, scratch + n2, 1);
+  ydat[nbl + 1] = 0.0; U[nbl + 1] = 0.0; Uspl[nbl + 1] = 0.0; d2U[nbl + 1] = 0.0; d2Uspl[nbl + 1] = 0.0;
+}
+
+cudaError_t launch_shift_profile(int nbl, double uc, const double *d_in, double *d_out, double *d_scratch,
+                                 cudaStream_t st) {
+  shift_profile_kernel<<<1, 32, 0, st>>>(nbl, uc, d_in, d_out, d_scratch);
+  return cudaGetLastError();
+}
+
 size_t blasius_scratch_doubles(int nbl, int64_t nprof) {
   return 2 * ((size_t)nbl + 2) * (size_t)nprof;
 }

@@ -1,6 +1,6 @@
 // osb_drivers.cpp -- C++ twin drivers of the reference's programs over the C ABI.
 //
-//   osb_drivers contebl | conte | orrsom | orrspace | orrfdchan | orrcolchan | orrncbl
+//   osb_drivers contebl | conte | orrsom | orrspace | orrfdchan | orrcolchan | orrncbl | conteucbl
 //
 // Each twin reads the same stdin (prompts, "key = value" decks, list-directed numbers),
 // echoes the same text and writes the same fort.N / <root>.g/.dat/.q files as the
@@ -223,6 +223,131 @@ static int run_contebl(osb_ctx *ctx) {
   }
   osb_profile_free(ctx, prof);
   return status;
+}
+
+// ---------------------------------------------------------------- conteucbl
+// Saddle-point tracking in a frame moving with u_c (conteucbl.f:5-300).  Its private CONTE is
+// CONTE_IC's iteration (tolerances 1e-14, shoot.f:461-479 rules) with CRK4 and the SPDER right-hand
+// side -- i.e. flow CONTEBL with the RK4 integrator -- on the profile shifted by SHIFT_BL.
+static void conteucbl_solve(osb_ctx *ctx, const osb_shoot_opts &o, osb_profile *prof, cd alpha, double Re, cd &c, int &qend) {
+  double al[2] = {alpha.real(), alpha.imag()}, cc[2] = {c.real(), c.imag()}, resid[2], hist[4 * 20];
+  int32_t passes, status;
+  int32_t q = 0;
+  CK(ctx, osb_shoot_temporal(ctx, &o, prof, 1, al, &Re, cc, &passes, &q, &status, resid, hist, 20));
+  for (int i = 0; i < passes && i < 20; ++i)  // conteucbl.f:577-579
+    printf(" %s%s%s   %s%s   \n", I(i + 1, 4).c_str(), E(hist[4 * i], 17, 8).c_str(), E(hist[4 * i + 1], 17, 8).c_str(),
+           E(hist[4 * i + 2], 17, 8).c_str(), E(hist[4 * i + 3], 17, 8).c_str());
+  // eigfun is forced .true. inside the reference's CONTE (conteucbl.f:333): the block always prints
+  printf("\nEigenvalue = %s %s  %s\n\n", E(cc[0], 17, 8).c_str(), E(cc[1], 17, 8).c_str(), I(q, 5).c_str());
+  printf("  Eigenvalue iterations = %s\n  |error| = %s\n  |c-cm1| = %s\n\n", I(passes, 5).c_str(),
+         ES(resid[0], 17, 8).c_str(), ES(resid[1], 17, 8).c_str());
+  c = cd(cc[0], cc[1]);
+  qend = q;
+}
+
+static int run_conteucbl(osb_ctx *ctx) {
+  int nbl = 1000, nstep = 1000, num = 1, omega = 0, saddle = 0;  // conteucbl.f:56-76
+  double testalpha = 10.0, Re = 580., beta = 0.0, alphar1 = 0.179, alphai1 = 0.0;
+  double cr = 0.36413124E+00, ci = 0.79527387E-02, ymin = 0.0, ymax = 17.0, f2p = 0.5, delta = 0.0, deltauc = 0.0, uc = 0.0;
+  printf("\n          Solve Orr-Sommerfeld (Shooting)\n\n");
+  printf("\n Read from keyboard, file, default (k,f,d) ==> ");
+  fflush(stdout);
+  const std::string input = getline80();
+  const char ch = input.empty() ? ' ' : input[0];
+  if (ch == 'k' || ch == 'K') {
+    printf("\n Enter number of profile points ==> "); std::cin >> nbl;
+    printf("\n Enter number of integration steps ==> "); std::cin >> nstep;
+    printf("\n Enter Test Alpha ==> "); std::cin >> testalpha;
+    printf("\n Enter Reynolds number ==> "); std::cin >> Re;
+    printf("\n Enter beta ==> "); std::cin >> beta;
+    printf("\n Enter guess for BL second deriv. at wall ==> "); std::cin >> f2p;
+    printf("\n Enter alpha_r ==> "); std::cin >> alphar1;
+    printf("\n Enter alpha_i ==> "); std::cin >> alphai1;
+    printf("\n Enter guess for (c_r, c_i) ==> "); std::cin >> cr >> ci;
+    printf("\n Enter Ymin and Ymax ==> "); std::cin >> ymin >> ymax;
+    printf("\n Enter reference frame velocity u_c ==> "); std::cin >> uc;
+    printf("\n Enter delta ==> "); std::cin >> delta;
+    printf("\n Enter deltauc ==> "); std::cin >> deltauc;
+  } else if (ch == 'f' || ch == 'F') {
+    printf("\n Enter filename ==> ");
+    fflush(stdout);
+    std::string infile = getline80();
+    while (!infile.empty() && infile.back() == ' ') infile.pop_back();
+    Deck d;
+    if (!d.open(infile)) { printf("\n\n Error in input file...\n\n\n"); return 0; }
+    nbl = (int)d.geti(); nstep = (int)d.geti(); testalpha = d.getr(); Re = d.getr(); beta = d.getr(); f2p = d.getr();
+    alphar1 = d.getr(); alphai1 = d.getr(); cr = d.getr(); ci = d.getr(); ymin = d.getr(); ymax = d.getr();
+    uc = d.getr(); delta = d.getr(); deltauc = d.getr(); num = (int)d.geti(); omega = (int)d.geti(); saddle = (int)d.geti();
+  }
+  if (nbl > 20000) { printf("\n\n N > Idim...Stopping\n\n\n"); return 0; }
+  cd alpha(alphar1, alphai1), c(cr, ci);
+  if (omega == 1) c = c / alpha;  // conteucbl.f:186
+  printf("\n nbl = %s\n", I(nbl, 5).c_str());
+  printf(" nstep = %s\n", I(nstep, 5).c_str());
+  printf(" Test Alpha = %s\n", E(testalpha, 20, 10).c_str());
+  printf(" Re = %s\n", E(Re, 20, 10).c_str());
+  printf(" Beta = %s\n", E(beta, 20, 10).c_str());
+  printf(" f2p = %s\n", E(f2p, 20, 10).c_str());
+  printf(" Ymin = %s  Ymax = %s\n", E(ymin, 20, 10).c_str(), E(ymax, 20, 10).c_str());
+  printf(" alpha = (%s, %s)\n", E(alphar1, 20, 10).c_str(), E(alphai1, 20, 10).c_str());
+  printf(" c = (%s, %s)\n", E(c.real(), 20, 10).c_str(), E(c.imag(), 20, 10).c_str());
+  printf(" Uc = %s\n", E(uc, 20, 10).c_str());
+  printf(" delta = %s\n", E(delta, 20, 10).c_str());
+  printf(" deltauc = %s\n", E(deltauc, 20, 10).c_str());
+  printf(" num = %s\n\n", I(num, 5).c_str());
+  Re = Re * std::sqrt(2.);
+  double ar[3] = {alphar1, alphar1 + delta, alphar1 - delta}, ai[3] = {alphai1, alphai1 - delta, alphai1 - delta};
+  // SOLVE_BL (SRK4) then SHIFT_BL; the un-shifted tables play the role of Uorg
+  osb_profile *porg = nullptr, *prof = nullptr;
+  CK(ctx, osb_profile_blasius(ctx, OSB_FLOW_CONTEBL, OSB_INT_RK4, nbl, ymin, ymax, f2p, beta, &porg));
+  CK(ctx, osb_profile_shift(ctx, porg, uc, &prof));
+  printf(" Velocity Profile completed...\n\n");
+  osb_shoot_opts o;
+  CK(ctx, osb_shoot_defaults(OSB_FLOW_CONTEBL, &o));
+  o.integrator = OSB_INT_RK4; o.nstep = nstep; o.testalpha = testalpha; o.ymin = ymin; o.ymax = ymax;
+  int qend = 0;
+  if (saddle == 1) {
+    cd alphas(10., 10.), eigenvalue[3], alp[3];
+    for (int k = 1; k <= num; ++k) {
+      osb_profile_free(ctx, prof);
+      CK(ctx, osb_profile_shift(ctx, porg, uc, &prof));  // call SHIFT_BL
+      cd resid(10., 0.);
+      int icount = 0;
+      while (std::abs(resid) > 1.E-5) {
+        icount = icount + 1;
+        cd alphasold = alphas;
+        for (int i = 0; i < 3; ++i) {
+          alphasold = alphas;
+          const cd a = cd(ar[i], ai[i]) * std::sqrt(2.);
+          alp[i] = a / std::sqrt(2.);
+          conteucbl_solve(ctx, o, prof, a, Re, c, qend);  // c is carried from call to call (COMMON /eig/)
+          eigenvalue[i] = c * alp[i];
+        }
+        const cd A = cd(0., -1.) * (eigenvalue[1] - eigenvalue[0]), B = cd(0., -1.) * (eigenvalue[2] - eigenvalue[0]);
+        alphas = (A * (alp[2] * alp[2] - alp[0] * alp[0]) - B * (alp[1] * alp[1] - alp[0] * alp[0])) /
+                 (2. * B * (alp[0] - alp[1]) - 2. * A * (alp[0] - alp[2]));
+        resid = alphas - alphasold;
+        if (k == 1 || icount > 4)
+          printf(" ==> %s    %s    %s    \n", E(alphas.real(), 17, 10).c_str(), E(alphas.imag(), 17, 10).c_str(),
+                 E(std::abs(resid), 17, 10).c_str());
+        ar[0] = alphas.real(); ai[0] = alphas.imag();
+        ar[1] = ar[0] + delta; ar[2] = ar[0] - delta;
+        ai[1] = ai[0] - delta; ai[2] = ai[0] - delta;
+        if (icount > 200) { fprintf(stderr, "saddle iteration did not converge\n"); return 1; }
+      }
+      printf(" %s  %s    %s    %s    %s    \n", fortfmt::F(uc, 6, 4).c_str(), E(eigenvalue[0].real(), 17, 10).c_str(),
+             E(eigenvalue[0].imag(), 17, 10).c_str(), E(alphas.real(), 17, 10).c_str(), E(alphas.imag(), 17, 10).c_str());
+      uc = uc - deltauc;
+    }
+  } else {
+    const cd a = cd(ar[0], ai[0]) * std::sqrt(2.);
+    conteucbl_solve(ctx, o, prof, a, Re, c, qend);
+    printf(" %s %s %s %s \n", ES(a.real(), 17, 9, 3).c_str(), ES(a.imag(), 17, 9, 3).c_str(), ES(c.real(), 17, 9, 3).c_str(),
+           ES(c.imag(), 17, 9, 3).c_str());
+  }
+  osb_profile_free(ctx, prof);
+  osb_profile_free(ctx, porg);
+  return 0;
 }
 
 // ---------------------------------------------------------------- conte
@@ -632,7 +757,7 @@ static int selftest_deck(const char *path) {
 
 int main(int argc, char **argv) {
   if (argc < 2) {
-    fprintf(stderr, "usage: osb_drivers contebl|conte|orrsom|orrspace|orrfdchan|orrcolchan|orrncbl  (input on stdin)\n");
+    fprintf(stderr, "usage: osb_drivers contebl|conte|orrsom|orrspace|orrfdchan|orrcolchan|orrncbl|conteucbl  (input on stdin)\n");
     return 64;
   }
   const std::string prog = argv[1];
@@ -653,6 +778,7 @@ int main(int argc, char **argv) {
   }
   int st = 0;
   if (prog == "contebl") st = run_contebl(ctx);
+  else if (prog == "conteucbl") st = run_conteucbl(ctx);
   else if (prog == "conte") st = run_conte(ctx);
   else if (prog == "orrsom") st = run_orrsom(ctx);
   else if (prog == "orrspace") st = run_orrspace(ctx);

@@ -118,6 +118,17 @@ def _spatial_point(self, integrator, nstep, testalpha, ymin, ymax, prof, Re, ome
 Oracle.shoot_spatial_point = _spatial_point
 
 
+def _profile_shift(self, prof, uc):
+    """SHIFT_BL of conteucbl.f:924-968 applied to the tables of solve_bl()."""
+    self.lib.osr_profile_shift.argtypes = [C.c_int, C.c_double, _dp, _dp]
+    out = np.zeros_like(prof)
+    self.lib.osr_profile_shift(prof.shape[1] - 2, float(uc), np.ascontiguousarray(prof).ctypes.data_as(_dp), out.ctypes.data_as(_dp))
+    return out
+
+
+Oracle.profile_shift = _profile_shift
+
+
 def load(rebuild=True):
     if rebuild or not LIB.exists():
         build()

@@ -210,3 +210,70 @@ def test_orrcolchan_chan_deck(tmp_path):
     assert abs(float(row[1]) - 0.2375262367) < 2e-9 and abs(float(row[2]) - 0.0037399251) < 2e-9
     f11 = np.loadtxt(tmp_path / "fort.11")
     assert f11.shape == (65, 5)
+
+
+UC_DECK = TEMPORAL_DECK.rstrip("\n") + """
+Uc = {uc}                # reference frame velocity
+delta = {delta}           # alpha stencil half width
+deltauc = {duc}          # decrement of Uc per step
+num = {num}                 # number of Uc steps
+omega = 0               # guess is omega (1) or c (0)
+saddle = {saddle}              # track the saddle point
+"""
+
+
+def _oracle_saddle(oracle, Re, alpha1, c, uc, delta, duc, num):
+    """The saddle loop of conteucbl.f:232-282 on the CPU oracle (CONTE_IC rules + CRK4 + SHIFT_BL)."""
+    prof0, _, _ = oracle.solve_bl(ob.FLOW_CONTEBL, ob.INT_RK4, 1000, 0.0, 17.0, 0.5, 0.0)
+    ar = [alpha1.real, alpha1.real + delta, alpha1.real - delta]
+    ai = [alpha1.imag, alpha1.imag - delta, alpha1.imag - delta]
+    rows, alphas = [], complex(10.0, 10.0)
+    for k in range(num):
+        prof = oracle.profile_shift(prof0, uc)
+        resid, it = 10.0, 0
+        while abs(resid) > 1e-5 and it < 60:
+            it += 1
+            ev, alp = [], []
+            for i in range(3):
+                old = alphas
+                a = complex(ar[i], ai[i]) * S2
+                alp.append(a / S2)
+                r = oracle.shoot_temporal(ob.FLOW_CONTEBL, ob.INT_RK4, 1000, 10.0, 0.0, 17.0, prof, a, Re * S2, c)
+                c = r["next"]  # COMMON c keeps the last update
+                ev.append(c * alp[i])
+            A = -1j * (ev[1] - ev[0]); B = -1j * (ev[2] - ev[0])
+            alphas = (A * (alp[2] ** 2 - alp[0] ** 2) - B * (alp[1] ** 2 - alp[0] ** 2)) / (2 * B * (alp[0] - alp[1]) - 2 * A * (alp[0] - alp[2]))
+            resid = alphas - old
+            ar = [alphas.real, alphas.real + delta, alphas.real - delta]
+            ai = [alphas.imag, alphas.imag - delta, alphas.imag - delta]
+        rows.append((uc, ev[0], alphas, it))
+        uc -= duc
+    return rows
+
+
+@pytest.mark.gpu
+def test_conteucbl_default_is_contebl_rk4(tmp_path):
+    """conteucbl with its defaults (uc = 0, saddle = 0) is contebl built without USE_RKCK45."""
+    r = run("conteucbl", "d\n", tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert "Eigenvalue =    0.36412271E+00    0.79597135E-02     21" in r.stdout
+    assert " Uc =     0.0000000000E+00" in r.stdout and " Velocity Profile completed..." in r.stdout
+
+
+@pytest.mark.gpu
+def test_conteucbl_saddle_tracking(tmp_path, oracle):
+    """Saddle point (zero group velocity in the frame moving with u_c) tracked for two frame speeds;
+    parity unpinned by the reference (it ships no deck for this), checked against the same loop on the oracle."""
+    uc, delta, duc, num = 0.40, 0.002, 0.01, 2
+    c0 = complex(0.36412271 - uc, 0.0079597135)
+    (tmp_path / "uc.inp").write_text(UC_DECK.format(nbl=1000, nstep=1000, Re=580.0, ar=0.179, cr=c0.real, ci=c0.imag, ymax=17.0,
+                                                    uc=uc, delta=delta, duc=duc, num=num, saddle=1))
+    r = run("conteucbl", "f\nuc.inp\n", tmp_path)
+    assert r.returncode == 0, r.stderr + r.stdout[-2000:]
+    rows = [ln.split() for ln in r.stdout.splitlines() if len(ln.split()) == 5 and ln.startswith(" 0.")]
+    assert len(rows) == num
+    ref = _oracle_saddle(oracle, 580.0, complex(0.179, 0.0), c0, uc, delta, duc, num)
+    for row, (u, ev0, alphas, it) in zip(rows, ref):
+        assert abs(float(row[0]) - u) < 1e-4
+        assert abs(complex(float(row[1]), float(row[2])) - ev0) < 1e-7
+        assert abs(complex(float(row[3]), float(row[4])) - alphas) < 1e-6
