@@ -72,12 +72,6 @@ static const double ck_c[6] = {0.09788359788359788, 0.0, 0.4025764895330113,
 /* zero filled, mirroring the zero-initialised COMMON storage that SPDER    */
 /* touches when XX == X(N)  (Appendix D-1).                                 */
 /* ---------------------------------------------------------------------- */
-typedef struct {
-  int nbl;        /* intervals; N = nbl+1 knots */
-  double ymin, ymax, h;
-  double *ydat, *U, *Uspl, *d2U, *d2Uspl; /* each nbl+2 (last = 0) */
-} osr_profile;
-
 /* SPLINE, shoot.f:906-957.  0-based arrays, N points. */
 static void osr_spline(int N, const double *X, const double *Y, double *FDP) {
   double *A = (double *)calloc((size_t)N + 2, sizeof(double));
