@@ -381,3 +381,34 @@ def test_queue_kernel_equals_plain_kernel_bitwise(engine, osb, bl, n):
         for k in ("c", "passes", "qend", "status", "resid", "history"):
             assert np.array_equal(part[k], whole[k][lo:hi]), (k, lo)
     assert (whole["status"] == 0).mean() > 0.99
+
+
+def test_config5_full_grid(engine, osb, oracle, bl, bl_oracle):
+    """BASELINE config 5 at full size (4096 x 4096 points, the bench workload): every point solved,
+    a spread sample checked against the oracle at 1e-10, and -- for ALL points -- the size-independent
+    property that the converged c is a smooth function of (alpha, Re): neighbouring points of the
+    grid differ by O(grid spacing), so a wrong mode or a garbage value anywhere would stand out."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+    import bench
+
+    idx, nre = bench.workload_indices(1, 0)
+    assert idx.size == 4096 * 4096
+    al, Re, c0 = bench.build_inputs(idx, nre)
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    r = engine.shoot_temporal(opts, bl, al, Re, c0)
+    ok = r["status"] == 0
+    assert ok.mean() > 0.99999
+    assert 5.0 < r["passes"][ok].mean() < 6.5
+    c = r["c"].reshape(4096, 4096)
+    okg = ok.reshape(4096, 4096)
+    da = np.abs(np.diff(c, axis=1))[okg[:, 1:] & okg[:, :-1]]
+    dr = np.abs(np.diff(c, axis=0))[okg[1:, :] & okg[:-1, :]]
+    assert da.max() < 2e-3 and dr.max() < 2e-3, (da.max(), dr.max())  # grid spacing: 6e-5 in alpha, 4e-4 in ln Re
+    pos = np.unique(np.floor(np.arange(400) * ((idx.size - 1) / 399.0)).astype(np.int64))
+    ref = oracle.shoot_temporal_batch(ob.FLOW_CONTEBL, ob.INT_CK45, 1000, 10.0, 0.0, 17.0, bl_oracle[0], al[pos], Re[pos], c0[pos])
+    both = (ref["status"] == 0) & ok[pos]
+    assert both.mean() > 0.99
+    assert rel(r["c"][pos][both], ref["c"][both]).max() < EIG_RTOL
