@@ -412,3 +412,34 @@ def test_config5_full_grid(engine, osb, oracle, bl, bl_oracle):
     both = (ref["status"] == 0) & ok[pos]
     assert both.mean() > 0.99
     assert rel(r["c"][pos][both], ref["c"][both]).max() < EIG_RTOL
+
+
+def test_conte_and_orrsom_small_grids(engine, osb, oracle):
+    """The other two temporal flows on small (alpha, Re) grids against the oracle."""
+    # conte: channel, CK45, n = 2000
+    prof = engine.channel_profile()
+    A, R = np.meshgrid(np.linspace(0.98, 1.02, 5), np.linspace(9800.0, 10200.0, 5))
+    g = np.full(A.size, complex(0.23752649, 0.00373967))
+    opts = osb.shoot_defaults(osb.FLOW_CONTE)
+    r = engine.shoot_temporal(opts, prof, A.ravel(), R.ravel(), g)
+    prof.free()
+    ref = oracle.shoot_temporal_batch(ob.FLOW_CONTE, ob.INT_CK45, 2000, 10.0, -1.0, 1.0, None, A.ravel() + 0j, R.ravel(), g)
+    ok = (ref["status"] == 0) & (r["status"] == 0)
+    assert ok.mean() > 0.9
+    assert rel(r["c"][ok], ref["c"][ok]).max() < EIG_RTOL
+    assert np.abs(r["qend"][ok] - ref["qend"][ok]).max() <= 1
+    # orrsom: Blasius, RK4, spline-of-spline U'', loose tolerances (1e-8 / 1e-12)
+    p = engine.solve_bl(osb.FLOW_ORRSOM, osb.INT_RK4, 1000, 0.0, 17.0, 0.5, 0.0)
+    oprof, _, _ = oracle.solve_bl(ob.FLOW_ORRSOM, ob.INT_RK4, 1000, 0.0, 17.0, 0.5, 0.0)
+    A, R = np.meshgrid(np.linspace(0.176, 0.182, 4), np.linspace(570.0, 590.0, 4))
+    g = np.full(A.size, complex(0.3641, 0.0080))
+    opts = osb.shoot_defaults(osb.FLOW_ORRSOM)
+    opts.nstep, opts.ymax = 1000, 17.0
+    r = engine.shoot_temporal(opts, p, A.ravel() * S2, R.ravel() * S2, g)
+    p.free()
+    ref = oracle.shoot_temporal_batch(ob.FLOW_ORRSOM, ob.INT_RK4, 1000, 10.0, 0.0, 17.0, oprof, A.ravel() * S2 + 0j, R.ravel() * S2, g)
+    ok = (ref["status"] == 0) & (r["status"] == 0)
+    assert ok.all()
+    # orrsom stops at |err| < 1e-8: the converged values agree to that tolerance's consequence, ~1e-9
+    assert rel(r["c"], ref["c"]).max() < 5e-9
+    assert np.array_equal(r["passes"], ref["passes"])
