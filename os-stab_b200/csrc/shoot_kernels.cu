@@ -24,6 +24,8 @@
 //  * The orthonormality test acos(cc/sqrt(aa*bb)) < ta (shoot.f:593-606) is
 //    evaluated as cc^2 > cos^2(ta)*aa*bb (acos is monotone): no sqrt/div/acos on
 //    the per-step path.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "osb_cplx.cuh"
@@ -706,6 +708,190 @@ __global__ void __launch_bounds__(QT, OSB_QUEUE_MIN_BLOCKS) shoot_queue_kernel(c
 }
 
 // ---------------------------------------------------------------------------
+// K2 on a LANE PAIR: the two solution vectors of a point live in two adjacent lanes.
+// For sweeps that cannot fill the GPU with one thread per point -- the spatial continuation
+// lines of orrspace (sequential inside a line), single-point driver runs, small
+// batches -- this doubles the parallelism.  Each lane integrates its own vector; after every
+// step the pair exchanges the vectors with shuffles, so that the orthonormality test, the
+// Gram-Schmidt step and the wall residual are evaluated (redundantly, identically) on both
+// lanes with the very same code as the one-thread kernel: results are bit-identical to it.
+// ---------------------------------------------------------------------------
+template <bool REAL_ALPHA>
+__device__ __forceinline__ void step_ck45_one(double (&y)[8], const double2 *__restrict__ trow,
+                                              const PassConst &pc, const ShootArgs &a) {
+  double f[6][8];
+#pragma unroll
+  for (int m = 0; m < 6; ++m) {
+    const StageCoef sc = stage_coef<REAL_ALPHA>(pc, __ldg(&trow[m]));
+    double yt[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      double acc = y[n];
+#pragma unroll
+      for (int k = 0; k < m; ++k) acc = fma(a.bh[m * (m - 1) / 2 + k], f[k][n], acc);
+      yt[n] = acc;
+    }
+#pragma unroll
+    for (int n = 0; n < 6; ++n) f[m][n] = yt[n + 2];
+    rhs4<REAL_ALPHA>(sc, pc, yt, f[m][6], f[m][7]);
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    double acc = y[n];
+    acc = fma(a.ch[0], f[0][n], acc);
+    acc = fma(a.ch[2], f[2][n], acc);
+    acc = fma(a.ch[3], f[3][n], acc);
+    acc = fma(a.ch[5], f[5][n], acc);
+    y[n] = acc;
+  }
+}
+
+template <bool REAL_ALPHA>
+__device__ __forceinline__ void step_rk4_one(double (&y)[8], const double2 *__restrict__ trow,
+                                             const PassConst &pc, const ShootArgs &a) {
+  const double hs = a.hs, h2 = 0.5 * a.hs, h6 = a.hs / 6.0, h3 = a.hs / 3.0;
+  const StageCoef s0 = stage_coef<REAL_ALPHA>(pc, __ldg(&trow[0]));
+  const StageCoef s1 = stage_coef<REAL_ALPHA>(pc, __ldg(&trow[1]));
+  const StageCoef s2 = stage_coef<REAL_ALPHA>(pc, __ldg(&trow[2]));
+  double f[8], q[8], acc[8];
+#pragma unroll
+  for (int n = 0; n < 6; ++n) f[n] = y[n + 2];
+  rhs4<REAL_ALPHA>(s0, pc, y, f[6], f[7]);
+#pragma unroll
+  for (int n = 0; n < 8; ++n) { acc[n] = fma(h6, f[n], y[n]); q[n] = fma(h2, f[n], y[n]); }
+#pragma unroll
+  for (int n = 0; n < 6; ++n) f[n] = q[n + 2];
+  rhs4<REAL_ALPHA>(s1, pc, q, f[6], f[7]);
+#pragma unroll
+  for (int n = 0; n < 8; ++n) acc[n] = fma(h3, f[n], acc[n]);
+  {
+    double q2[8];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) q2[n] = fma(h2, f[n], y[n]);
+#pragma unroll
+    for (int n = 0; n < 6; ++n) f[n] = q2[n + 2];
+    rhs4<REAL_ALPHA>(s1, pc, q2, f[6], f[7]);
+  }
+#pragma unroll
+  for (int n = 0; n < 8; ++n) { acc[n] = fma(h3, f[n], acc[n]); q[n] = fma(hs, f[n], y[n]); }
+#pragma unroll
+  for (int n = 0; n < 6; ++n) f[n] = q[n + 2];
+  rhs4<REAL_ALPHA>(s2, pc, q, f[6], f[7]);
+#pragma unroll
+  for (int n = 0; n < 8; ++n) y[n] = fma(h6, f[n], acc[n]);
+}
+
+template <int INTEG, bool ANALYTIC, bool REAL_ALPHA>
+__device__ __forceinline__ void integrate_pass_pair(const ShootArgs &a, int v, zd alpha, double Re, zd cw,
+                                                    zd &err, int &qend) {
+  constexpr int NS = (INTEG == OSB_INT_CK45) ? 6 : 3;
+  // pairs of one warp converge after different numbers of passes, so the exchange is
+  // synchronised over the two lanes of the pair only
+  const unsigned pmask = 3u << (threadIdx.x & 30u);
+  const PassConst pc = pass_const(alpha, Re, cw);
+  double u[2][8];
+  initial_vectors(u, a, alpha, Re, cw);
+  int q = 0;
+  const double2 *__restrict__ trow = a.tab;
+  for (int k = a.bl_ic ? 0 : 1; k <= a.nstep; ++k) {
+    bool norm;
+    if (k > 0) {
+      // integrate my vector, then swap in the partner's
+      double y[8];
+#pragma unroll
+      for (int n = 0; n < 8; ++n) y[n] = v ? u[1][n] : u[0][n];
+      if (INTEG == OSB_INT_CK45) step_ck45_one<REAL_ALPHA>(y, trow, pc, a);
+      else step_rk4_one<REAL_ALPHA>(y, trow, pc, a);
+      trow += NS;
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+        const double o = __shfl_xor_sync(pmask, y[n], 1);
+        u[0][n] = v ? o : y[n];
+        u[1][n] = v ? y[n] : o;
+      }
+      norm = need_norm<ANALYTIC>(u, a.thr, a.strict) || (k == a.nstep);
+      q += norm ? 1 : 0;
+    } else {
+      norm = true;
+    }
+    if (norm) {
+      zd w1, w2, p;
+      gram_schmidt<ANALYTIC>(u, w1, w2, p);
+    }
+  }
+  qend = q;
+  zd B1 = zneg(zdiv(zd{u[1][0], u[1][1]}, zd{u[0][0], u[0][1]}));
+  err = zadd(zmul(zd{u[0][2], u[0][3]}, B1), zd{u[1][2], u[1][3]});
+}
+
+template <int INTEG, bool ANALYTIC>
+__global__ void __launch_bounds__(64) shoot_pair_kernel(const __grid_constant__ ShootArgs a) {
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = (int)(gtid & 1);
+  const int64_t gline = gtid >> 1;
+  const bool active = gline < a.nlines;
+  const int64_t line = active ? gline : a.nlines - 1;
+  const double Re = a.Re[line];
+  zd alpha, omega = zd{0.0, 0.0};
+  IterState s;
+  {
+    double2 al = a.alpha[line];
+    alpha = zd{al.x, al.y};
+    if (a.spatial) {
+      double2 om = a.omega0[line];
+      omega = zd{om.x, om.y};
+      s.ev = alpha;
+    } else {
+      double2 c0 = a.ev[line];
+      s.ev = zd{c0.x, c0.y};
+    }
+  }
+  const bool real_alpha = !a.spatial && __all_sync(0xffffffffu, alpha.y == 0.0);
+  for (int it = 0; it < a.niter; ++it) {
+    const int64_t out = line * a.niter + it;
+    s.icount = 1;
+    s.cm1_defined = a.cm1_defined;
+    s.cm1 = zd{s.ev.x + 1.0, s.ev.y};
+    s.cm2 = zd{0.0, 0.0}; s.errm1 = zd{0.0, 0.0}; s.errm2 = zd{0.0, 0.0};
+    zd err = zd{1.0, 0.0}, ctemp = s.ev;
+    int qend = 0, status = OSB_ST_MAXCOUNT;
+    while (true) {
+      // both lanes of a pair hold identical iteration state, so they leave the loop together
+      if (!keep_going(a, s, err)) {
+        if (s.icount <= a.maxcount) status = OSB_ST_CONVERGED;
+        break;
+      }
+      ctemp = s.ev;
+      {
+        const zd al = a.spatial ? s.ev : alpha;
+        const zd cw = a.spatial ? zdiv(omega, s.ev) : s.ev;
+        if (real_alpha) integrate_pass_pair<INTEG, ANALYTIC, true>(a, v, al, Re, cw, err, qend);
+        else integrate_pass_pair<INTEG, ANALYTIC, false>(a, v, al, Re, cw, err, qend);
+      }
+      update_eigenvalue(s, err, ctemp, a.first_perturb);
+      if (active && v == 0 && a.history && s.icount <= a.hist_cap) {
+        zd shown = a.show_updated ? s.ev : ctemp;
+        a.history[out * a.hist_cap + (s.icount - 1)] = make_double4(shown.x, shown.y, err.x, err.y);
+      }
+      s.icount += 1;
+      if (!(zfinite(s.ev) && zfinite(err))) { status = OSB_ST_NONFINITE; break; }
+    }
+    if (active && v == 0) {
+      a.ev[out] = make_double2(ctemp.x, ctemp.y);
+      a.passes[out] = s.icount - 1;
+      a.qend[out] = qend;
+      a.status[out] = status;
+      if (a.resid)
+        a.resid[out] = make_double2(zabs(err), s.cm1_defined ? zabs(zsub(s.ev, s.cm1)) : 0.0);
+    }
+    if (a.spatial) {
+      s.ev = ctemp;
+      omega.x += a.domega[line];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // K2b: eigenfunction pass (shoot.f:762-810; conte shoot.f:338-385).  One thread
 // per requested point: re-integrates at the converged eigenvalue keeping the
 // (orthonormalised) trajectory, the P matrices and the normalisation abscissae,
@@ -868,6 +1054,21 @@ cudaError_t launch_shoot(const ShootArgs &a, int integrator, int analytic_inprod
   if (queue_counter && !a.spatial && a.niter == 1 && a.nlines >= 4 * QT) {
     if (nlaunch) *nlaunch += 1;
     return launch_shoot_queue(a, integrator, analytic_inprod, queue_counter, st);
+  }
+  // too few lines to fill the GPU with one thread each: two lanes per line (measured gain
+  // 1.13-1.18x up to 4096 lines, a loss at 16384: DESIGN.md 5)
+  if (a.nlines <= 148 * 64 && !getenv("OSB_NO_PAIR")) {
+    const int threads = 64;
+    const unsigned blocks = (unsigned)((2 * a.nlines + threads - 1) / threads);
+    if (integrator == OSB_INT_CK45) {
+      if (analytic_inprod) shoot_pair_kernel<OSB_INT_CK45, true><<<blocks, threads, 0, st>>>(a);
+      else shoot_pair_kernel<OSB_INT_CK45, false><<<blocks, threads, 0, st>>>(a);
+    } else {
+      if (analytic_inprod) shoot_pair_kernel<OSB_INT_RK4, true><<<blocks, threads, 0, st>>>(a);
+      else shoot_pair_kernel<OSB_INT_RK4, false><<<blocks, threads, 0, st>>>(a);
+    }
+    if (nlaunch) *nlaunch += 1;
+    return cudaGetLastError();
   }
   // small batches: narrow CTAs so the points spread over all 148 SMs
   int threads = (a.nlines >= 148 * 4 * 128) ? 128 : (a.nlines >= 148 * 4 * 64 ? 64 : 32);

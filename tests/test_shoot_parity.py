@@ -443,3 +443,57 @@ def test_conte_and_orrsom_small_grids(engine, osb, oracle):
     # orrsom stops at |err| < 1e-8: the converged values agree to that tolerance's consequence, ~1e-9
     assert rel(r["c"], ref["c"]).max() < 5e-9
     assert np.array_equal(r["passes"], ref["passes"])
+
+
+def test_pair_kernel_equals_plain_kernel_bitwise(engine, osb, bl, monkeypatch):
+    """Batches too small to fill the GPU run with two lanes per point (one per solution vector,
+    exchanged by shuffles).  The arithmetic per vector is that of the one-thread kernel, so every
+    output must be identical bit for bit, for every flow variant, both integrators, odd batch
+    sizes (the last pair of a warp without a neighbour pair) and lines that converge after
+    different numbers of passes inside one warp."""
+    fact = S2 / 1.7207876
+
+    def both(fn):
+        monkeypatch.delenv("OSB_NO_PAIR", raising=False)
+        a = fn()
+        monkeypatch.setenv("OSB_NO_PAIR", "1")
+        b = fn()
+        monkeypatch.delenv("OSB_NO_PAIR")
+        for k in a:
+            assert np.array_equal(a[k], b[k], equal_nan=True), k
+        return a
+
+    rng = np.random.default_rng(5)
+    for n in (1, 17, 333):
+        al = (0.179 + 0.01 * (rng.random(n) - 0.5)) * S2 + 0j
+        al[::5] += 1j * 0.0003 * S2
+        Re = 580.0 * (1 + 0.05 * (rng.random(n) - 0.5)) * S2
+        guess = np.full(n, complex(0.36412287, 0.0079597206))
+        for integ in (osb.INT_CK45, osb.INT_RK4):
+            opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+            opts.integrator = integ
+            r = both(lambda: engine.shoot_temporal(opts, bl, al, Re, guess, want_resid=True, hist_cap=8))
+            assert (r["status"] == 0).mean() > 0.8, (n, integ, (r["status"] == 0).mean())
+    assert len(set(r["passes"].tolist())) > 1  # divergent pass counts were exercised
+    # conte (channel, e3/e4 start, Hermitian) and orrsom (analytic inner product)
+    ch = engine.channel_profile()
+    opts = osb.shoot_defaults(osb.FLOW_CONTE)
+    al = np.linspace(0.95, 1.05, 9)
+    both(lambda: engine.shoot_temporal(opts, ch, al, np.full(9, 1.0e4), np.full(9, complex(0.23753, 0.00374))))
+    ch.free()
+    p = engine.solve_bl(osb.FLOW_ORRSOM, osb.INT_RK4, 400, 0.0, 30.0, 0.5, 0.0)
+    opts = osb.shoot_defaults(osb.FLOW_ORRSOM)
+    opts.nstep, opts.ymax = 4000, 30.0
+    both(lambda: engine.shoot_temporal(opts, p, np.array([0.179, 0.18, 0.175]) * S2, np.full(3, 580.0 * S2),
+                                       np.full(3, complex(0.36413124, 0.0079527387))))
+    p.free()
+    # orrspace continuation lines
+    p = engine.solve_bl(osb.FLOW_ORRSPACE, osb.INT_RK4, 1000, 0.0, 20.0 * fact, 0.5, 0.0)
+    opts = osb.shoot_defaults(osb.FLOW_ORRSPACE)
+    opts.nstep, opts.ymin, opts.ymax, opts.testalpha = 1000, 0.0, 20.0 * fact, 0.9
+    Re = np.array([1000.0, 990.0, 1010.0, 950.0, 1000.0]) * fact
+    r = both(lambda: engine.shoot_spatial_lines(opts, p, Re, np.full(5, complex(0.042, 0.0)) * fact,
+                                                np.full(5, 0.002) * fact,
+                                                np.full(5, complex(0.13809592, 0.0051958399)) * fact, 12))
+    p.free()
+    assert np.all(r["status"] == 0)
