@@ -24,6 +24,16 @@ struct osb_ctx {
 
 struct osb_profile {
   std::vector<ProfileDev> dev;  // one per context device
+  osb_profile() = default;
+  osb_profile(const osb_profile &) = delete;
+  osb_profile &operator=(const osb_profile &) = delete;
+  ~osb_profile() {
+    for (auto &d : dev)
+      if (d.tables) {
+        cudaSetDevice(d.device);
+        cudaFree(d.tables);
+      }
+  }
 };
 
 namespace {
@@ -36,10 +46,12 @@ int fail(osb_ctx *ctx, int code, const std::string &msg) {
 #define OSB_CUDA(ctx, call)                                                              \
   do {                                                                                   \
     cudaError_t e__ = (call);                                                            \
-    if (e__ != cudaSuccess)                                                              \
+    if (e__ != cudaSuccess) {                                                            \
+      (void)cudaGetLastError(); /* do not let it surface again at the next launch check */ \
       return fail((ctx), OSB_E_CUDA,                                                     \
                   std::string(#call) + ": " + cudaGetErrorString(e__) + " (" __FILE__ ":" + \
                       std::to_string(__LINE__) + ")");                                   \
+    }                                                                                    \
   } while (0)
 
 // Cash-Karp tableau as typed in the reference (shoot.f:1381-1391)
@@ -226,7 +238,7 @@ int osb_shoot_defaults(int flow, osb_shoot_opts *o) {
 
 // ---------------------------------------------------------------- profiles
 static int profile_alloc(osb_ctx *ctx, int variant, int nbl, double ymin, double ymax,
-                         osb_profile **out) {
+                         std::unique_ptr<osb_profile> *out) {
   std::unique_ptr<osb_profile> p(new osb_profile);
   p->dev.resize(ctx->devices.size());
   for (size_t i = 0; i < ctx->devices.size(); ++i) {
@@ -237,7 +249,7 @@ static int profile_alloc(osb_ctx *ctx, int variant, int nbl, double ymin, double
       OSB_CUDA(ctx, cudaMalloc(&d.tables, 5 * ((size_t)nbl + 2) * sizeof(double)));
     }
   }
-  *out = p.release();
+  *out = std::move(p);
   return OSB_OK;
 }
 
@@ -247,34 +259,32 @@ int osb_profile_blasius(osb_ctx *ctx, int variant, int integrator, int nbl, doub
   if (variant != OSB_FLOW_CONTEBL && variant != OSB_FLOW_ORRSOM && variant != OSB_FLOW_ORRSPACE)
     return fail(ctx, OSB_E_ARG, "variant must be CONTEBL, ORRSOM or ORRSPACE");
   if (nbl < 8) return fail(ctx, OSB_E_ARG, "nbl < 8");
-  osb_profile *p = nullptr;
+  std::unique_ptr<osb_profile> p;
   int rc = profile_alloc(ctx, variant, nbl, ymin, ymax, &p);
   if (rc) return rc;
   for (size_t i = 0; i < ctx->devices.size(); ++i) {
     ProfileDev &d = p->dev[i];
     cudaStream_t st = ctx->streams[i];
     OSB_CUDA(ctx, cudaSetDevice(d.device));
-    double *scr = nullptr, *par = nullptr;
+    Scratch scr(d.device, st);
+    double *work = nullptr, *par = nullptr;
     int32_t *np = nullptr;
-    OSB_CUDA(ctx, cudaMallocAsync(&scr, blasius_scratch_doubles(nbl, 1) * sizeof(double), st));
-    OSB_CUDA(ctx, cudaMallocAsync(&par, 3 * sizeof(double), st));
-    OSB_CUDA(ctx, cudaMallocAsync(&np, sizeof(int32_t), st));
+    OSB_CUDA(ctx, scr.alloc(&work, blasius_scratch_doubles(nbl, 1) * sizeof(double)));
+    OSB_CUDA(ctx, scr.alloc(&par, 3 * sizeof(double)));
+    OSB_CUDA(ctx, scr.alloc(&np, sizeof(int32_t)));
     double hp[2] = {f2p, beta};
     OSB_CUDA(ctx, cudaMemcpyAsync(par, hp, sizeof(hp), cudaMemcpyHostToDevice, st));
-    OSB_CUDA(ctx, launch_blasius(variant, integrator, nbl, ymin, ymax, 1, par, par + 1, d.tables, scr,
+    OSB_CUDA(ctx, launch_blasius(variant, integrator, nbl, ymin, ymax, 1, par, par + 1, d.tables, work,
                                  par + 2, np, st));
     ctx->launches++;
     int32_t hnp = 0;
     double hf2 = 0;
     OSB_CUDA(ctx, cudaMemcpyAsync(&hnp, np, sizeof(hnp), cudaMemcpyDeviceToHost, st));
     OSB_CUDA(ctx, cudaMemcpyAsync(&hf2, par + 2, sizeof(hf2), cudaMemcpyDeviceToHost, st));
-    OSB_CUDA(ctx, cudaFreeAsync(scr, st));
-    OSB_CUDA(ctx, cudaFreeAsync(par, st));
-    OSB_CUDA(ctx, cudaFreeAsync(np, st));
     OSB_CUDA(ctx, cudaStreamSynchronize(st));
     d.npass = hnp; d.f2p_last = hf2;
   }
-  *out = p;
+  *out = p.release();
   return OSB_OK;
 }
 
@@ -289,15 +299,16 @@ int osb_profile_blasius_batch(osb_ctx *ctx, int variant, int integrator, int nbl
   cudaStream_t st = ctx->streams[0];
   OSB_CUDA(ctx, cudaSetDevice(ctx->devices[0]));
   const size_t n2 = (size_t)nbl + 2;
-  double *tab = nullptr, *scr = nullptr, *par = nullptr;
+  Scratch scr(ctx->devices[0], st);
+  double *tab = nullptr, *work = nullptr, *par = nullptr;
   int32_t *np = nullptr;
-  OSB_CUDA(ctx, cudaMallocAsync(&tab, 5 * n2 * nprof * sizeof(double), st));
-  OSB_CUDA(ctx, cudaMallocAsync(&scr, blasius_scratch_doubles(nbl, nprof) * sizeof(double), st));
-  OSB_CUDA(ctx, cudaMallocAsync(&par, 3 * nprof * sizeof(double), st));
-  OSB_CUDA(ctx, cudaMallocAsync(&np, nprof * sizeof(int32_t), st));
+  OSB_CUDA(ctx, scr.alloc(&tab, 5 * n2 * nprof * sizeof(double)));
+  OSB_CUDA(ctx, scr.alloc(&work, blasius_scratch_doubles(nbl, nprof) * sizeof(double)));
+  OSB_CUDA(ctx, scr.alloc(&par, 3 * nprof * sizeof(double)));
+  OSB_CUDA(ctx, scr.alloc(&np, nprof * sizeof(int32_t)));
   OSB_CUDA(ctx, cudaMemcpyAsync(par, f2p, nprof * sizeof(double), cudaMemcpyHostToDevice, st));
   OSB_CUDA(ctx, cudaMemcpyAsync(par + nprof, beta, nprof * sizeof(double), cudaMemcpyHostToDevice, st));
-  OSB_CUDA(ctx, launch_blasius(variant, integrator, nbl, ymin, ymax, nprof, par, par + nprof, tab, scr,
+  OSB_CUDA(ctx, launch_blasius(variant, integrator, nbl, ymin, ymax, nprof, par, par + nprof, tab, work,
                                par + 2 * nprof, np, st));
   ctx->launches++;
   // device layout is [array][i][p]; the caller wants [p][i]: strided 2-D copies
@@ -314,10 +325,6 @@ int osb_profile_blasius_batch(osb_ctx *ctx, int variant, int integrator, int nbl
   }
   if (f2p_out) OSB_CUDA(ctx, cudaMemcpyAsync(f2p_out, par + 2 * nprof, nprof * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (npass) OSB_CUDA(ctx, cudaMemcpyAsync(npass, np, nprof * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  OSB_CUDA(ctx, cudaFreeAsync(tab, st));
-  OSB_CUDA(ctx, cudaFreeAsync(scr, st));
-  OSB_CUDA(ctx, cudaFreeAsync(par, st));
-  OSB_CUDA(ctx, cudaFreeAsync(np, st));
   OSB_CUDA(ctx, cudaStreamSynchronize(st));
   return OSB_OK;
 }
@@ -340,14 +347,14 @@ int osb_profile_upload(osb_ctx *ctx, int variant, int nbl, double ymin, double y
     h[3 * n2 + i] = d2U ? d2U[i] : Uspl[i];
     h[4 * n2 + i] = d2Uspl ? d2Uspl[i] : 0.0;
   }
-  osb_profile *p = nullptr;
+  std::unique_ptr<osb_profile> p;
   int rc = profile_alloc(ctx, variant, nbl, ymin, ymax, &p);
   if (rc) return rc;
   for (size_t i = 0; i < ctx->devices.size(); ++i) {
     OSB_CUDA(ctx, cudaSetDevice(p->dev[i].device));
     OSB_CUDA(ctx, cudaMemcpy(p->dev[i].tables, h.data(), h.size() * sizeof(double), cudaMemcpyHostToDevice));
   }
-  *out = p;
+  *out = p.release();
   return OSB_OK;
 }
 
@@ -355,27 +362,31 @@ int osb_profile_shift(osb_ctx *ctx, const osb_profile *prof, double uc, osb_prof
   if (!ctx || !prof || !out || prof->dev.size() != ctx->devices.size()) return OSB_E_ARG;
   const ProfileDev &p0 = prof->dev[0];
   if (!p0.tables) return fail(ctx, OSB_E_ARG, "profile has no tables");
-  osb_profile *q = nullptr;
+  std::unique_ptr<osb_profile> q;
   int rc = profile_alloc(ctx, p0.variant, p0.nbl, p0.ymin, p0.ymax, &q);
   if (rc) return rc;
   for (size_t i = 0; i < ctx->devices.size(); ++i) {
     cudaStream_t st = ctx->streams[i];
     OSB_CUDA(ctx, cudaSetDevice(q->dev[i].device));
-    double *scr = nullptr;
-    OSB_CUDA(ctx, cudaMallocAsync(&scr, 2 * ((size_t)p0.nbl + 2) * sizeof(double), st));
-    OSB_CUDA(ctx, launch_shift_profile(p0.nbl, uc, prof->dev[i].tables, q->dev[i].tables, scr, st));
+    Scratch scr(q->dev[i].device, st);
+    double *work = nullptr;
+    OSB_CUDA(ctx, scr.alloc(&work, 2 * ((size_t)p0.nbl + 2) * sizeof(double)));
+    OSB_CUDA(ctx, launch_shift_profile(p0.nbl, uc, prof->dev[i].tables, q->dev[i].tables, work, st));
     ctx->launches++;
-    OSB_CUDA(ctx, cudaFreeAsync(scr, st));
     OSB_CUDA(ctx, cudaStreamSynchronize(st));
     q->dev[i].npass = p0.npass; q->dev[i].f2p_last = p0.f2p_last;
   }
-  *out = q;
+  *out = q.release();
   return OSB_OK;
 }
 
 int osb_profile_channel(osb_ctx *ctx, osb_profile **out) {
   if (!ctx || !out) return OSB_E_ARG;
-  return profile_alloc(ctx, OSB_FLOW_CONTE, 0, -1.0, 1.0, out);
+  std::unique_ptr<osb_profile> p;
+  int rc = profile_alloc(ctx, OSB_FLOW_CONTE, 0, -1.0, 1.0, &p);
+  if (rc) return rc;
+  *out = p.release();
+  return OSB_OK;
 }
 
 int osb_profile_get(osb_ctx *ctx, const osb_profile *prof, double *ydat, double *U, double *Uspl,
@@ -398,20 +409,15 @@ int osb_profile_nbl(const osb_profile *prof) { return prof && !prof->dev.empty()
 
 int osb_profile_free(osb_ctx *ctx, osb_profile *prof) {
   if (!prof) return OSB_E_ARG;
-  for (auto &d : prof->dev)
-    if (d.tables) {
-      cudaSetDevice(d.device);
-      cudaFree(d.tables);
-    }
   delete prof;
   (void)ctx;
   return OSB_OK;
 }
 
 // ---------------------------------------------------------------- shooting
-// build the stage table for device slot i; returns a stream-ordered allocation
-static int make_stage_table(osb_ctx *ctx, size_t i, const osb_shoot_opts *o, const osb_profile *prof,
-                            double2 **tab) {
+// build the stage table for device slot i in the call's scratch
+static int make_stage_table(osb_ctx *ctx, size_t i, Scratch &scr, const osb_shoot_opts *o,
+                            const osb_profile *prof, double2 **tab) {
   cudaStream_t st = ctx->streams[i];
   size_t n = (size_t)o->nstep * stages_per_step(o->integrator);
   OSB_CUDA(ctx, cudaMallocAsync(tab, n * sizeof(double2), st));
@@ -436,8 +442,9 @@ int osb_shoot_temporal_dev(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_p
   if (npts == 0) return OSB_OK;
   OSB_CUDA(ctx, cudaSetDevice(ctx->devices[0]));
   cudaStream_t st = ctx->streams[0];
+  Scratch scr(ctx->devices[0], st);
   double2 *tab = nullptr;
-  rc = make_stage_table(ctx, 0, opts, prof, &tab);
+  rc = make_stage_table(ctx, 0, scr, opts, prof, &tab);
   if (rc) return rc;
   a.tab = tab;
   a.nlines = npts;
@@ -451,13 +458,11 @@ int osb_shoot_temporal_dev(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_p
   int nl = 0;
   unsigned long long *qc = nullptr;
   if (!getenv("OSB_NO_QUEUE")) {
-    OSB_CUDA(ctx, cudaMallocAsync(&qc, sizeof(unsigned long long), st));
+    OSB_CUDA(ctx, scr.alloc(&qc, sizeof(unsigned long long)));
     OSB_CUDA(ctx, cudaMemsetAsync(qc, 0, sizeof(unsigned long long), st));
   }
   OSB_CUDA(ctx, launch_shoot(a, opts->integrator, analytic, st, &nl, qc));
   ctx->launches += nl;
-  if (qc) OSB_CUDA(ctx, cudaFreeAsync(qc, st));
-  OSB_CUDA(ctx, cudaFreeAsync(tab, st));
   return OSB_OK;
 }
 
@@ -479,6 +484,7 @@ int osb_shoot_temporal(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profi
   const int ndev = (int)ctx->devices.size();
   struct Buf { double *alpha = 0, *Re = 0, *c = 0, *resid = 0, *hist = 0; int32_t *ip = 0; double2 *tab = 0; int64_t lo = 0, hi = 0; };
   std::vector<Buf> bufs(ndev);
+  std::vector<std::unique_ptr<Scratch>> guards(ndev);
   // phase 1: per device H2D + launch (kernels of different devices overlap)
   for (int d = 0; d < ndev; ++d) {
     Buf &b = bufs[d];
@@ -487,17 +493,19 @@ int osb_shoot_temporal(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profi
     if (n <= 0) continue;
     cudaStream_t st = ctx->streams[d];
     OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
-    OSB_CUDA(ctx, cudaMallocAsync(&b.alpha, n * 2 * sizeof(double), st));
-    OSB_CUDA(ctx, cudaMallocAsync(&b.Re, n * sizeof(double), st));
-    OSB_CUDA(ctx, cudaMallocAsync(&b.c, n * 2 * sizeof(double), st));
-    OSB_CUDA(ctx, cudaMallocAsync(&b.ip, n * 3 * sizeof(int32_t), st));
-    if (resid) OSB_CUDA(ctx, cudaMallocAsync(&b.resid, n * 2 * sizeof(double), st));
-    if (history) OSB_CUDA(ctx, cudaMallocAsync(&b.hist, n * hist_cap * 4 * sizeof(double), st));
+    guards[d].reset(new Scratch(ctx->devices[d], st));
+    Scratch &scr = *guards[d];
+    OSB_CUDA(ctx, scr.alloc(&b.alpha, n * 2 * sizeof(double)));
+    OSB_CUDA(ctx, scr.alloc(&b.Re, n * sizeof(double)));
+    OSB_CUDA(ctx, scr.alloc(&b.c, n * 2 * sizeof(double)));
+    OSB_CUDA(ctx, scr.alloc(&b.ip, n * 3 * sizeof(int32_t)));
+    if (resid) OSB_CUDA(ctx, scr.alloc(&b.resid, n * 2 * sizeof(double)));
+    if (history) OSB_CUDA(ctx, scr.alloc(&b.hist, n * hist_cap * 4 * sizeof(double)));
     OSB_CUDA(ctx, cudaMemcpyAsync(b.alpha, alpha + 2 * b.lo, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
     OSB_CUDA(ctx, cudaMemcpyAsync(b.Re, Re + b.lo, n * sizeof(double), cudaMemcpyHostToDevice, st));
     OSB_CUDA(ctx, cudaMemcpyAsync(b.c, c + 2 * b.lo, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
     if (history) OSB_CUDA(ctx, cudaMemsetAsync(b.hist, 0, n * hist_cap * 4 * sizeof(double), st));
-    rc = make_stage_table(ctx, d, opts, prof, &b.tab);
+    rc = make_stage_table(ctx, d, scr, opts, prof, &b.tab);
     if (rc) return rc;
     ShootArgs a = base;
     a.tab = b.tab;
@@ -510,12 +518,11 @@ int osb_shoot_temporal(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profi
     int nl = 0;
     unsigned long long *qc = nullptr;
     if (!getenv("OSB_NO_QUEUE")) {
-      OSB_CUDA(ctx, cudaMallocAsync(&qc, sizeof(unsigned long long), st));
+      OSB_CUDA(ctx, scr.alloc(&qc, sizeof(unsigned long long)));
       OSB_CUDA(ctx, cudaMemsetAsync(qc, 0, sizeof(unsigned long long), st));
     }
     OSB_CUDA(ctx, launch_shoot(a, opts->integrator, analytic, st, &nl, qc));
     ctx->launches += nl;
-    if (qc) OSB_CUDA(ctx, cudaFreeAsync(qc, st));
   }
   // phase 2: D2H + free
   for (int d = 0; d < ndev; ++d) {
@@ -530,13 +537,6 @@ int osb_shoot_temporal(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profi
     OSB_CUDA(ctx, cudaMemcpyAsync(status + b.lo, b.ip + 2 * n, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (resid) OSB_CUDA(ctx, cudaMemcpyAsync(resid + 2 * b.lo, b.resid, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (history) OSB_CUDA(ctx, cudaMemcpyAsync(history + b.lo * hist_cap * 4, b.hist, n * hist_cap * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    OSB_CUDA(ctx, cudaFreeAsync(b.alpha, st));
-    OSB_CUDA(ctx, cudaFreeAsync(b.Re, st));
-    OSB_CUDA(ctx, cudaFreeAsync(b.c, st));
-    OSB_CUDA(ctx, cudaFreeAsync(b.ip, st));
-    if (b.resid) OSB_CUDA(ctx, cudaFreeAsync(b.resid, st));
-    if (b.hist) OSB_CUDA(ctx, cudaFreeAsync(b.hist, st));
-    OSB_CUDA(ctx, cudaFreeAsync(b.tab, st));
   }
   for (int d = 0; d < ndev; ++d) {
     OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
@@ -565,6 +565,7 @@ int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_
   if (history && hist_cap < 1) return fail(ctx, OSB_E_ARG, "hist_cap < 1");
   struct Buf { double *in = 0, *out = 0, *hist = 0; int32_t *ip = 0; double2 *tab = 0; int64_t lo = 0, hi = 0; };
   std::vector<Buf> bufs(ndev);
+  std::vector<std::unique_ptr<Scratch>> guards(ndev);
   for (int d = 0; d < ndev; ++d) {
     Buf &b = bufs[d];
     chunk(nlines, ndev, d, &b.lo, &b.hi);
@@ -572,19 +573,21 @@ int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_
     if (n <= 0) continue;
     cudaStream_t st = ctx->streams[d];
     OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
+    guards[d].reset(new Scratch(ctx->devices[d], st));
+    Scratch &scr = *guards[d];
     // in: Re[n], domega[n], omega0[2n], alpha0[2n]
-    OSB_CUDA(ctx, cudaMallocAsync(&b.in, n * 6 * sizeof(double), st));
-    OSB_CUDA(ctx, cudaMallocAsync(&b.out, n * niter * 2 * sizeof(double), st));
-    OSB_CUDA(ctx, cudaMallocAsync(&b.ip, n * niter * 3 * sizeof(int32_t), st));
+    OSB_CUDA(ctx, scr.alloc(&b.in, n * 6 * sizeof(double)));
+    OSB_CUDA(ctx, scr.alloc(&b.out, n * niter * 2 * sizeof(double)));
+    OSB_CUDA(ctx, scr.alloc(&b.ip, n * niter * 3 * sizeof(int32_t)));
     if (history) {
-      OSB_CUDA(ctx, cudaMallocAsync(&b.hist, (size_t)n * niter * hist_cap * 4 * sizeof(double), st));
+      OSB_CUDA(ctx, scr.alloc(&b.hist, (size_t)n * niter * hist_cap * 4 * sizeof(double)));
       OSB_CUDA(ctx, cudaMemsetAsync(b.hist, 0, (size_t)n * niter * hist_cap * 4 * sizeof(double), st));
     }
     OSB_CUDA(ctx, cudaMemcpyAsync(b.in, Re + b.lo, n * sizeof(double), cudaMemcpyHostToDevice, st));
     OSB_CUDA(ctx, cudaMemcpyAsync(b.in + n, domega + b.lo, n * sizeof(double), cudaMemcpyHostToDevice, st));
     OSB_CUDA(ctx, cudaMemcpyAsync(b.in + 2 * n, omega0 + 2 * b.lo, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
     OSB_CUDA(ctx, cudaMemcpyAsync(b.in + 4 * n, alpha0 + 2 * b.lo, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-    rc = make_stage_table(ctx, d, opts, prof, &b.tab);
+    rc = make_stage_table(ctx, d, scr, opts, prof, &b.tab);
     if (rc) return rc;
     ShootArgs a = base;
     a.tab = b.tab;
@@ -615,12 +618,7 @@ int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_
     if (history) {
       OSB_CUDA(ctx, cudaMemcpyAsync(history + (size_t)b.lo * niter * hist_cap * 4, b.hist,
                                     (size_t)m * hist_cap * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-      OSB_CUDA(ctx, cudaFreeAsync(b.hist, st));
     }
-    OSB_CUDA(ctx, cudaFreeAsync(b.in, st));
-    OSB_CUDA(ctx, cudaFreeAsync(b.out, st));
-    OSB_CUDA(ctx, cudaFreeAsync(b.ip, st));
-    OSB_CUDA(ctx, cudaFreeAsync(b.tab, st));
   }
   for (int d = 0; d < ndev; ++d) {
     OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
@@ -644,21 +642,22 @@ int osb_eigfun(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof
   OSB_CUDA(ctx, cudaSetDevice(ctx->devices[0]));
   cudaStream_t st = ctx->streams[0];
   const size_t n1 = (size_t)opts->nstep + 1;
+  Scratch scr(ctx->devices[0], st);
   double *d_in = nullptr, *d_tq = nullptr;
   double2 *d_U = nullptr, *d_P = nullptr, *d_y = nullptr, *d_vmax = nullptr, *tab = nullptr;
   int32_t *d_q = nullptr;
-  OSB_CUDA(ctx, cudaMallocAsync(&d_in, npts * 5 * sizeof(double), st));  // Re, eig(2), alpha|omega(2)
-  OSB_CUDA(ctx, cudaMallocAsync(&d_U, npts * n1 * 8 * sizeof(double2), st));
-  OSB_CUDA(ctx, cudaMallocAsync(&d_P, npts * n1 * 4 * sizeof(double2), st));
-  OSB_CUDA(ctx, cudaMallocAsync(&d_tq, npts * n1 * sizeof(double), st));
-  OSB_CUDA(ctx, cudaMallocAsync(&d_y, npts * n1 * 4 * sizeof(double2), st));
-  OSB_CUDA(ctx, cudaMallocAsync(&d_vmax, npts * sizeof(double2), st));
-  OSB_CUDA(ctx, cudaMallocAsync(&d_q, npts * sizeof(int32_t), st));
+  OSB_CUDA(ctx, scr.alloc(&d_in, npts * 5 * sizeof(double)));  // Re, eig(2), alpha|omega(2)
+  OSB_CUDA(ctx, scr.alloc(&d_U, npts * n1 * 8 * sizeof(double2)));
+  OSB_CUDA(ctx, scr.alloc(&d_P, npts * n1 * 4 * sizeof(double2)));
+  OSB_CUDA(ctx, scr.alloc(&d_tq, npts * n1 * sizeof(double)));
+  OSB_CUDA(ctx, scr.alloc(&d_y, npts * n1 * 4 * sizeof(double2)));
+  OSB_CUDA(ctx, scr.alloc(&d_vmax, npts * sizeof(double2)));
+  OSB_CUDA(ctx, scr.alloc(&d_q, npts * sizeof(int32_t)));
   // layout: eig(2n), alpha|omega(2n), Re(n)  -- the double2 arrays first (16-byte alignment)
   OSB_CUDA(ctx, cudaMemcpyAsync(d_in, eig, npts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   OSB_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * npts, a.spatial ? omega : alpha, npts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   OSB_CUDA(ctx, cudaMemcpyAsync(d_in + 4 * npts, Re, npts * sizeof(double), cudaMemcpyHostToDevice, st));
-  rc = make_stage_table(ctx, 0, opts, prof, &tab);
+  rc = make_stage_table(ctx, 0, scr, opts, prof, &tab);
   if (rc) return rc;
   EigfunArgs e;
   memset(&e, 0, sizeof(e));
@@ -676,14 +675,6 @@ int osb_eigfun(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof
   OSB_CUDA(ctx, cudaMemcpyAsync(y, d_y, npts * n1 * 4 * sizeof(double2), cudaMemcpyDeviceToHost, st));
   OSB_CUDA(ctx, cudaMemcpyAsync(vmax, d_vmax, npts * sizeof(double2), cudaMemcpyDeviceToHost, st));
   if (qend) OSB_CUDA(ctx, cudaMemcpyAsync(qend, d_q, npts * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  OSB_CUDA(ctx, cudaFreeAsync(d_in, st));
-  OSB_CUDA(ctx, cudaFreeAsync(d_U, st));
-  OSB_CUDA(ctx, cudaFreeAsync(d_P, st));
-  OSB_CUDA(ctx, cudaFreeAsync(d_tq, st));
-  OSB_CUDA(ctx, cudaFreeAsync(d_y, st));
-  OSB_CUDA(ctx, cudaFreeAsync(d_vmax, st));
-  OSB_CUDA(ctx, cudaFreeAsync(d_q, st));
-  OSB_CUDA(ctx, cudaFreeAsync(tab, st));
   OSB_CUDA(ctx, cudaStreamSynchronize(st));
   return OSB_OK;
 }
@@ -696,11 +687,16 @@ int osb_measure_fp64_peak(osb_ctx *ctx, double ms_target, double *tflops, double
   cudaDeviceProp prop;
   OSB_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->devices[0]));
   const int threads = 256, blocks = prop.multiProcessorCount * 8;
+  Scratch scr(ctx->devices[0], st);
   double *d_out = nullptr;
-  OSB_CUDA(ctx, cudaMallocAsync(&d_out, sizeof(double), st));
-  cudaEvent_t e0, e1;
-  OSB_CUDA(ctx, cudaEventCreate(&e0));
-  OSB_CUDA(ctx, cudaEventCreate(&e1));
+  OSB_CUDA(ctx, scr.alloc(&d_out, sizeof(double)));
+  struct Events {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~Events() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+  } ev;
+  OSB_CUDA(ctx, cudaEventCreate(&ev.e0));
+  OSB_CUDA(ctx, cudaEventCreate(&ev.e1));
+  cudaEvent_t e0 = ev.e0, e1 = ev.e1;
   int iters = 2000;
   double best = 0.0;
   float ms = 0.f;
@@ -719,10 +715,7 @@ int osb_measure_fp64_peak(osb_ctx *ctx, double ms_target, double *tflops, double
   *tflops = best;
   if (sm_clock_mhz_est)  // 64 DFMA / clk / SM on B200
     *sm_clock_mhz_est = best * 1e12 / (2.0 * 64.0 * prop.multiProcessorCount) / 1e6;
-  OSB_CUDA(ctx, cudaFreeAsync(d_out, st));
   OSB_CUDA(ctx, cudaStreamSynchronize(st));
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
   return OSB_OK;
 }
 

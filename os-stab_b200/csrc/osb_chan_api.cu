@@ -34,6 +34,14 @@ struct osb_chan {
   std::vector<double> eta, u, d1u, d2u, D2full, D4full;  // host copies, full (N+1) grid, row-major (i,j)
   double *dD2 = nullptr, *dD4 = nullptr, *du = nullptr, *dd2u = nullptr;  // device, interior, column-major
   int device = 0;
+  osb_chan() = default;
+  osb_chan(const osb_chan &) = delete;
+  osb_chan &operator=(const osb_chan &) = delete;
+  ~osb_chan() {
+    if (!dD2 && !dD4 && !du && !dd2u) return;
+    cudaSetDevice(device);
+    cudaFree(dD2); cudaFree(dD4); cudaFree(du); cudaFree(dd2u);
+  }
 };
 
 namespace {
@@ -41,9 +49,11 @@ namespace {
 #define CH_CUDA(ctx, call)                                                                \
   do {                                                                                    \
     cudaError_t e__ = (call);                                                             \
-    if (e__ != cudaSuccess)                                                               \
+    if (e__ != cudaSuccess) {                                                             \
+      (void)cudaGetLastError();                                                           \
       return ctx_fail((ctx), OSB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + \
                                              " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+    }                                                                                     \
   } while (0)
 
 inline double &at(std::vector<double> &M, int N, int i, int j) { return M[(size_t)i * (N + 1) + j]; }
@@ -161,8 +171,6 @@ int osb_chan_create(osb_ctx *ctx, int disc, int N, osb_chan **out) {
 
 int osb_chan_free(osb_ctx *ctx, osb_chan *c) {
   if (!c) return OSB_E_ARG;
-  cudaSetDevice(c->device);
-  cudaFree(c->dD2); cudaFree(c->dD4); cudaFree(c->du); cudaFree(c->dd2u);
   delete c;
   (void)ctx;
   return OSB_OK;
@@ -193,14 +201,15 @@ static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::ve
   // the FD operator is banded (half bandwidth 4): banded LU, one thread per instance
   const bool banded = (c->disc == OSB_DISC_FD) && !getenv("OSB_FD_DENSE");
   if (!banded) CH_CUDA(ctx, chan_eig_grid(n, ninst, &grid, &smem));
+  Scratch scr(c->device, st);
   double *d_in = nullptr, *d_out = nullptr;
   double2 *work = nullptr, *d_evec = nullptr;
   int32_t *d_it = nullptr;
-  CH_CUDA(ctx, cudaMallocAsync(&d_in, ninst * 5 * sizeof(double), st));   // alpha(2), sigma(2), Re
-  CH_CUDA(ctx, cudaMallocAsync(&d_out, ninst * 3 * sizeof(double), st));  // omega(2), delta
-  CH_CUDA(ctx, cudaMallocAsync(&d_it, ninst * sizeof(int32_t), st));
-  CH_CUDA(ctx, cudaMallocAsync(&work, banded ? chan_band_work_bytes(n, ninst) : (size_t)grid * n * n * sizeof(double2), st));
-  if (evec_host) CH_CUDA(ctx, cudaMallocAsync(&d_evec, (size_t)ninst * (n + 2) * sizeof(double2), st));
+  CH_CUDA(ctx, scr.alloc(&d_in, ninst * 5 * sizeof(double)));   // alpha(2), sigma(2), Re
+  CH_CUDA(ctx, scr.alloc(&d_out, ninst * 3 * sizeof(double)));  // omega(2), delta
+  CH_CUDA(ctx, scr.alloc(&d_it, ninst * sizeof(int32_t)));
+  CH_CUDA(ctx, scr.alloc(&work, banded ? chan_band_work_bytes(n, ninst) : (size_t)grid * n * n * sizeof(double2)));
+  if (evec_host) CH_CUDA(ctx, scr.alloc(&d_evec, (size_t)ninst * (n + 2) * sizeof(double2)));
   CH_CUDA(ctx, cudaMemcpyAsync(d_in, alpha.data(), ninst * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   CH_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * ninst, sigma.data(), ninst * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   CH_CUDA(ctx, cudaMemcpyAsync(d_in + 4 * ninst, Re.data(), ninst * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -219,11 +228,6 @@ static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::ve
   CH_CUDA(ctx, cudaMemcpyAsync(iters.data(), d_it, ninst * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (evec_host)
     CH_CUDA(ctx, cudaMemcpyAsync(evec_host, d_evec, (size_t)ninst * (n + 2) * sizeof(double2), cudaMemcpyDeviceToHost, st));
-  CH_CUDA(ctx, cudaFreeAsync(d_in, st));
-  CH_CUDA(ctx, cudaFreeAsync(d_out, st));
-  CH_CUDA(ctx, cudaFreeAsync(d_it, st));
-  CH_CUDA(ctx, cudaFreeAsync(work, st));
-  if (d_evec) CH_CUDA(ctx, cudaFreeAsync(d_evec, st));
   CH_CUDA(ctx, cudaStreamSynchronize(st));
   if (getenv("OSB_CHAN_PROFILE")) chan_profile_dump("eig");
   return OSB_OK;
@@ -333,15 +337,16 @@ int osb_chan_neutral(osb_ctx *ctx, const osb_chan *c, int64_t nRe, const double 
   size_t smem = 0;
   CH_CUDA(ctx, cudaSetDevice(c->device));
   CH_CUDA(ctx, chan_neutral_grid(n, nRe, &grid, &smem));
+  Scratch scr(c->device, st);
   double *d_in = nullptr, *d_out = nullptr, *d_trace = nullptr;
   double2 *work = nullptr;
   int32_t *d_i = nullptr;
-  CH_CUDA(ctx, cudaMallocAsync(&d_in, nRe * 4 * sizeof(double), st));   // sigma0(2), Re, alpha0
-  CH_CUDA(ctx, cudaMallocAsync(&d_out, nRe * 3 * sizeof(double), st));  // omega(2), alpha
-  CH_CUDA(ctx, cudaMallocAsync(&d_i, nRe * 2 * sizeof(int32_t), st));
-  CH_CUDA(ctx, cudaMallocAsync(&work, (size_t)grid * n * n * sizeof(double2), st));
+  CH_CUDA(ctx, scr.alloc(&d_in, nRe * 4 * sizeof(double)));   // sigma0(2), Re, alpha0
+  CH_CUDA(ctx, scr.alloc(&d_out, nRe * 3 * sizeof(double)));  // omega(2), alpha
+  CH_CUDA(ctx, scr.alloc(&d_i, nRe * 2 * sizeof(int32_t)));
+  CH_CUDA(ctx, scr.alloc(&work, (size_t)grid * n * n * sizeof(double2)));
   if (trace) {
-    CH_CUDA(ctx, cudaMallocAsync(&d_trace, (size_t)nRe * maxit * 7 * sizeof(double), st));
+    CH_CUDA(ctx, scr.alloc(&d_trace, (size_t)nRe * maxit * 7 * sizeof(double)));
     CH_CUDA(ctx, cudaMemsetAsync(d_trace, 0, (size_t)nRe * maxit * 7 * sizeof(double), st));
   }
   CH_CUDA(ctx, cudaMemcpyAsync(d_in, sig.data(), nRe * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -356,11 +361,6 @@ int osb_chan_neutral(osb_ctx *ctx, const osb_chan *c, int64_t nRe, const double 
   CH_CUDA(ctx, cudaMemcpyAsync(steps, d_i, nRe * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   CH_CUDA(ctx, cudaMemcpyAsync(status, d_i + nRe, nRe * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (trace) CH_CUDA(ctx, cudaMemcpyAsync(trace, d_trace, (size_t)nRe * maxit * 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CH_CUDA(ctx, cudaFreeAsync(d_in, st));
-  CH_CUDA(ctx, cudaFreeAsync(d_out, st));
-  CH_CUDA(ctx, cudaFreeAsync(d_i, st));
-  CH_CUDA(ctx, cudaFreeAsync(work, st));
-  if (d_trace) CH_CUDA(ctx, cudaFreeAsync(d_trace, st));
   CH_CUDA(ctx, cudaStreamSynchronize(st));
   for (int64_t p = 0; p < nRe; ++p)
     if (!ok[p] && status[p] == OSB_ST_CONVERGED) status[p] = OSB_ST_MAXCOUNT;

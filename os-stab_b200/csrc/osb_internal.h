@@ -22,6 +22,33 @@ struct ProfileDev {
   int device = 0;
 };
 
+// Stream-ordered scratch allocations of one call on one device; released on every exit
+// path (the error returns of the C ABI included) when the guard leaves scope.
+class Scratch {
+ public:
+  Scratch(int device, cudaStream_t st) : device_(device), st_(st) {}
+  Scratch(const Scratch &) = delete;
+  Scratch &operator=(const Scratch &) = delete;
+  ~Scratch() {
+    if (ptrs_.empty()) return;
+    cudaSetDevice(device_);
+    for (void *q : ptrs_) cudaFreeAsync(q, st_);
+  }
+  template <class T>
+  cudaError_t alloc(T **out, size_t bytes) {
+    void *q = nullptr;
+    cudaError_t e = cudaMallocAsync(&q, bytes ? bytes : 1, st_);
+    if (e == cudaSuccess) ptrs_.push_back(q);
+    *out = static_cast<T *>(q);
+    return e;
+  }
+
+ private:
+  int device_;
+  cudaStream_t st_;
+  std::vector<void *> ptrs_;
+};
+
 // Everything the shooting kernel needs that is uniform over the launch.
 struct ShootArgs {
   // stage table: for step k (1-based) and stage s: tab[(k-1)*NS + s] = (U, U'') at

@@ -497,3 +497,36 @@ def test_pair_kernel_equals_plain_kernel_bitwise(engine, osb, bl, monkeypatch):
                                                 np.full(5, complex(0.13809592, 0.0051958399)) * fact, 12))
     p.free()
     assert np.all(r["status"] == 0)
+
+
+def test_device_allocation_failure_is_reported_and_recoverable(engine, osb, bl):
+    """A request whose scratch cannot be allocated must come back as an error code with the CUDA
+    message (no crash, no CPU path), release what it had allocated, and leave the context usable."""
+    import ctypes as C
+
+    n = 4096
+    al = np.full(2 * n, 0.0); al[0::2] = 0.179 * S2
+    Re = np.full(n, 580.0 * S2)
+    cc = np.tile([0.36412287, 0.0079597206], n)
+    ip = np.zeros(3 * n, dtype=np.int32)
+    bogus_history = np.zeros(4)  # never written: the device buffer for it cannot be allocated
+    dp, ipp = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    free0 = _free_bytes()
+    for _ in range(3):
+        rc = engine.lib.osb_shoot_temporal(
+            engine.ctx, C.byref(opts), bl.handle, n, al.ctypes.data_as(dp), Re.ctypes.data_as(dp), cc.ctypes.data_as(dp),
+            ip[:n].ctypes.data_as(ipp), ip[n:2 * n].ctypes.data_as(ipp), ip[2 * n:].ctypes.data_as(ipp), None,
+            bogus_history.ctypes.data_as(dp), 2 ** 31 - 1)
+        assert rc < 0
+        assert b"memory" in engine.lib.osb_last_error(engine.ctx).lower()
+    r = engine.shoot_temporal(opts, bl, [0.179 * S2], [580.0 * S2], [complex(0.36413124, 0.79527387e-2)])
+    assert r["status"][0] == 0 and abs(r["c"][0] - complex(0.36412287, 0.0079597206)) < 1e-8
+    # nothing of the failed calls stays allocated beyond the pool's cache of the small buffers
+    assert free0 - _free_bytes() < 64 << 20
+
+
+def _free_bytes():
+    import torch
+
+    return torch.cuda.mem_get_info(0)[0]
