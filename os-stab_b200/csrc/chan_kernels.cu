@@ -639,6 +639,7 @@ constexpr int BKL = 4, BKU = 4, BW = BKL + BKU + 1;  // 9 stored entries per U r
 struct BandArgs {
   int n;
   const double *D2, *D4, *u, *d2u;  // dense tables (only the band is read)
+  const double2 *band24;            // [n][BW]: (D2, D4)(r, r-4+j), zero outside the matrix (warp kernel)
   int64_t ninst;
   const double2 *alpha;
   const double *Re;
@@ -814,21 +815,389 @@ __global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constan
   }
 }
 
+// ---------------------------------------------------------------------------
+// K4b-w: the same banded elimination on NINE LANES per instance, three instances per warp,
+// for sweeps that cannot fill the GPU with a thread per instance (the reference's decks hold
+// 21 / 41 alpha values; the throughput variant of config 4 holds 4096).  What counts there is
+// the latency of one instance, and at this occupancy that is the number of instructions on
+// its serial path:
+//   * LU: lane l of a group owns window column j = l (mod 9) -- columns never move between
+//     lanes.  The 5 candidates of column k are broadcast, every lane derives pivot and
+//     multipliers redundantly and updates its own 4 entries (4 complex FMAs per step instead
+//     of 36 in the one-thread kernel); row interchange and window shift are one select.
+//     The entering rows are evaluated 32 rows at a time, one diagonal per lane, from the
+//     compact band tables into shared memory.
+//   * U is stored by COLUMNS (Uc[k][j] = U(k-j, k)) with the reciprocal of the pivot in
+//     Uc[k][0], so that the back substitution is column-oriented: its chain per row is one
+//     complex multiply + one complex FMA instead of 8 dependent FMAs and a division.
+//   * the substitutions are sequential: the leader lanes of the three groups run them side
+//     by side out of shared memory, 32 rows per staged chunk; B x, the inner products and
+//     the normalisation use all 32 lanes.
+// Same algorithm as the one-thread kernel (same pivoting rule, same iteration); the pivots'
+// reciprocals and the order of the substitution sums differ in rounding.
+// ---------------------------------------------------------------------------
+constexpr int BWW = 4;    // warps per CTA
+constexpr int BG = 3;     // instances per warp
+constexpr int64_t BAND_WARP_MAX_INST = 16384;  // beyond: the one-thread kernel fills the GPU better
+
+template <int BCH>           // rows per staged chunk
+struct BandStage {           // per instance, shared memory
+  double2 ub[BCH * BW];      // LU: entering band rows; back substitution: chunk of Uc
+  double2 lb[BCH * BKL];     // forward substitution: chunk of L
+  double2 yi[BCH], yo[BCH];  // substitution: entering right-hand sides, solved rows
+  int pv[BCH];
+};
+
+__device__ __forceinline__ double2 shfl2(double2 v, int src) {
+  return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double2 sel2(bool c, double2 a, double2 b) { return c ? a : b; }
+
+// entry (r, r-4+j) of A - sigma B from the compact band table (x: D2, y: D4); same arithmetic as band_entry
+__device__ __forceinline__ double2 band_entry_c(const BandArgs &a, const PencilCoef &p, double2 sb2, double2 sb0, int r, int j) {
+  if (r >= a.n || j < 0 || j >= BW) return make_double2(0.0, 0.0);
+  const int c = r - BKL + j;
+  if (c < 0 || c >= a.n) return make_double2(0.0, 0.0);
+  const double2 b = a.band24[(size_t)r * BW + j];
+  const double2 w2 = csub2(coef_w2(p, a.u[r]), sb2);
+  double2 v = make_double2(fma(w2.x, b.x, b.y), w2.y * b.x);
+  if (j == BKL) v = cadd2(v, csub2(coef_w0(p, a.u[r], a.d2u[r]), sb0));
+  return v;
+}
+
+// Two builds: <32 rows per chunk, 2 CTAs/SM> has the shortest latency per instance (no spills);
+// <16, 3> trades 20 % of it for 12 resident warps per SM, which pays when the sweep needs
+// more than two CTAs per SM to fit in one wave.
+template <int BCH, int MINB>
+__global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(const __grid_constant__ BandArgs a) {
+  typedef BandStage<BCH> Stage;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t inst0 = ((int64_t)blockIdx.x * BWW + warp) * BG;
+  if (inst0 >= a.ninst) return;  // whole warps leave; no block-wide barrier is used below
+  const int n = a.n;
+  const int g = min(lane / BW, BG - 1);   // lanes 27..31 shadow group 2 and never store
+  const int gl = lane - g * BW;
+  const int lead = g * BW;
+  const bool lane_ok = gl < BW;
+  const bool alive = lane_ok && inst0 + g < a.ninst;
+  const int64_t inst = min(inst0 + g, a.ninst - 1);
+  Stage *stg = (Stage *)smem_raw + (warp * BG + g);
+  Stage *stg0 = (Stage *)smem_raw + warp * BG;
+  const size_t nU = (size_t)n * BW, nL = (size_t)n * BKL;
+  double2 *Uc = a.U + (size_t)inst * nU, *Lm = a.L + (size_t)inst * nL;
+  int8_t *piv = a.piv + (size_t)inst * n;
+  const PencilCoef p = pencil_coef(a.alpha[inst], a.Re[inst]);
+  double2 sigma = a.sigma[inst];
+  const int ngrp = (int)min((int64_t)BG, a.ninst - inst0);
+  // start vector (same as the dense path); entries of Uc above the first row are never produced
+  for (int gp = 0; gp < ngrp; ++gp) {
+    double2 *xg = a.x + (size_t)(inst0 + gp) * n;
+    for (int i = lane; i < n; i += 32) {
+      const double sv = sin(3.0 * (i + 1.0) / (n + 1.0)) + 0.37 * cos(11.0 * (i + 1.0) / (n + 1.0));
+      xg[i] = make_double2(sv, 0.25 * sv * sv - 0.1);
+    }
+  }
+  if (alive)
+    for (int e = gl; e < 8 * BW; e += BW) {
+      const int k = e / BW, j = e % BW;
+      if (k < n && j > k) Uc[(size_t)k * BW + j] = make_double2(0.0, 0.0);
+    }
+  double2 om = sigma;
+  double dl = 1.0e300;
+  int total = 0;
+  bool done = !alive;
+  for (int o = 0; o < a.outer; ++o) {
+    if (!__any_sync(0xffffffffu, !done)) break;
+    const bool act = !done;  // group-uniform
+    PROF_T0();
+    // ================= banded LU =================
+    {
+      const double2 sb2 = cmul2(sigma, p.b2), sb0 = cmul2(sigma, p.b0);
+      double2 w[BKL + 1];
+#pragma unroll
+      for (int sidx = 0; sidx <= BKL; ++sidx) w[sidx] = band_entry_c(a, p, sb2, sb0, sidx, lane_ok ? gl - sidx + BKL : -1);
+      int src = 0;      // group lane that holds column k
+      int mycol = gl;   // the column this lane holds
+      for (int c0 = 0; c0 < n; c0 += BCH) {
+        // entering rows c0+5 .. c0+36, diagonal gl on lane gl
+        __syncwarp();
+        if (lane_ok)
+          for (int q = 0; q < BCH; ++q) stg->ub[q * BW + gl] = band_entry_c(a, p, sb2, sb0, c0 + q + 1 + BKL, gl);
+        __syncwarp();
+        const int hi = min(BCH, n - c0);
+        for (int kk = 0; kk < hi; ++kk) {
+          const int k = c0 + kk;
+          double2 cc[BKL + 1];
+#pragma unroll
+          for (int sidx = 0; sidx <= BKL; ++sidx) cc[sidx] = shfl2(w[sidx], lead + src);
+          int pv = 0;
+          double best = fabs(cc[0].x) + fabs(cc[0].y);
+#pragma unroll
+          for (int sidx = 1; sidx <= BKL; ++sidx) {
+            const double v = fabs(cc[sidx].x) + fabs(cc[sidx].y);
+            if (k + sidx < n && v > best) { best = v; pv = sidx; }
+          }
+          double2 prow = w[0], pc = cc[0];
+#pragma unroll
+          for (int sidx = 1; sidx <= BKL; ++sidx) {
+            prow = sel2(pv == sidx, w[sidx], prow);
+            pc = sel2(pv == sidx, cc[sidx], pc);
+          }
+          // 1 / pivot = conj(p) / |p|^2 ; an exactly singular pivot only happens when sigma hits an
+          // eigenvalue to the last bit: inverse iteration wants the huge solve, not a NaN
+          double d = fma(pc.x, pc.x, pc.y * pc.y);
+          double2 rinv;
+          if (d > 1.0e-280 && d < 1.0e280) {
+            const double rd = 1.0 / d;
+            rinv = make_double2(pc.x * rd, -pc.y * rd);
+          } else {
+            if (pc.x == 0.0 && pc.y == 0.0) pc = make_double2(1.0e-290, 0.0);
+            rinv = cdiv2(make_double2(1.0, 0.0), pc);
+          }
+          const bool is_src = (gl == src);
+          double2 l[BKL + 1];
+          const double2 w0 = w[0];
+#pragma unroll
+          for (int sidx = 1; sidx <= BKL; ++sidx) {
+            const double2 tc = sel2(pv == sidx, cc[0], cc[sidx]);   // interchange rows 0 and pv ...
+            const double2 t = sel2(pv == sidx, w0, w[sidx]);
+            l[sidx] = cmul2(tc, rinv);
+            const double2 upd = cfnma2(t, l[sidx], prow);
+            w[sidx - 1] = is_src ? make_double2(0.0, 0.0) : upd;      // ... and shift the window up
+          }
+          if (act && lane_ok) {
+            if (is_src) {
+              Uc[(size_t)k * BW] = rinv;
+              piv[k] = (int8_t)pv;
+#pragma unroll
+              for (int sidx = 1; sidx <= BKL; ++sidx) Lm[(size_t)k * BKL + (sidx - 1)] = l[sidx];
+            } else if (mycol < n) {
+              Uc[(size_t)mycol * BW + (mycol - k)] = prow;   // U(k, mycol), stored by column
+            }
+          }
+          int idx = is_src ? BW - 1 : mycol - k - 1;
+          idx = max(0, min(idx, BW - 1));
+          w[BKL] = stg->ub[kk * BW + idx];
+          if (is_src) mycol = k + BW;
+          src = (src + 1 == BW) ? 0 : src + 1;
+        }
+      }
+    }
+    __syncwarp();
+    PROF_ADD(1);
+    // ================= inverse iteration =================
+    bool inner_on = act;
+    int it = 0;
+    for (int step = 0; step < a.inner; ++step) {
+      if (!__any_sync(0xffffffffu, inner_on)) break;
+      // ---- y = B x = b2 D2 x + b0 x (D2: half bandwidth 2), all lanes, one group after the other
+      for (int gp = 0; gp < ngrp; ++gp) {
+        const bool on = __shfl_sync(0xffffffffu, (int)inner_on, gp * BW) != 0;
+        const double2 b2 = shfl2(p.b2, gp * BW), b0 = shfl2(p.b0, gp * BW);
+        if (!on) continue;
+        const double2 *xg = a.x + (size_t)(inst0 + gp) * n;
+        double2 *yg = a.y + (size_t)(inst0 + gp) * n;
+        for (int r = lane; r < n; r += 32) {
+          double sr = 0.0, si = 0.0;
+#pragma unroll
+          for (int dc = -2; dc <= 2; ++dc) {
+            const int c = r + dc;
+            if (c >= 0 && c < n) {
+              const double dd = a.band24[(size_t)r * BW + BKL + dc].x;
+              const double2 xc = xg[c];
+              sr = fma(dd, xc.x, sr); si = fma(dd, xc.y, si);
+            }
+          }
+          yg[r] = cadd2(cmul2(b2, make_double2(sr, si)), cmul2(b0, xg[r]));
+        }
+      }
+      __syncwarp();
+      PROF_ADD(5);
+      const bool leader = lane_ok && gl == 0 && inner_on;
+      const double2 *yme = a.y + (size_t)inst * n;
+      // ---- forward: L y' = P y.  Lane s of a group holds the right-hand side of row k+s (s = 0..4)
+      {
+        double2 bw = (lane_ok && gl <= BKL && gl < n) ? yme[gl] : make_double2(0.0, 0.0);
+        for (int c0 = 0; c0 < n; c0 += BCH) {
+          for (int gp = 0; gp < ngrp; ++gp) {
+            const size_t ib = (size_t)(inst0 + gp);
+            Stage *sg = stg0 + gp;
+#pragma unroll
+            for (int q = 0; q < (BCH * BKL + 31) / 32; ++q) {
+              const int el = q * 32 + lane, e = c0 * BKL + el;
+              if (el < BCH * BKL) sg->lb[el] = (e < n * BKL) ? a.L[ib * nL + e] : make_double2(0.0, 0.0);
+            }
+            if (lane < BCH) {
+              sg->pv[lane] = (c0 + lane < n) ? (int)a.piv[ib * n + c0 + lane] : 0;
+              const int r = c0 + lane + 1 + BKL;
+              sg->yi[lane] = (r < n) ? a.y[ib * n + r] : make_double2(0.0, 0.0);
+            }
+          }
+          __syncwarp();
+          const int hi = min(BCH, n - c0);
+          const int lrow = min(max(gl - 1, 0), BKL - 1);
+          for (int kk = 0; kk < hi; ++kk) {
+            const int pv = stg->pv[kk];
+            const double2 pvv = shfl2(bw, lead + pv), b0 = shfl2(bw, lead);
+            const double2 t = sel2(gl == pv, b0, bw);                      // row pv receives the old row 0
+            const double2 upd = cfnma2(t, stg->lb[kk * BKL + lrow], pvv);  // rows k+1..k+4 (lanes 1..4)
+            if (leader) stg->yo[kk] = pvv;
+            // shift: lane s takes the updated row s+1; lane 4 takes the entering row k+5
+            const double2 nxt = make_double2(__shfl_down_sync(0xffffffffu, upd.x, 1), __shfl_down_sync(0xffffffffu, upd.y, 1));
+            bw = sel2(gl == BKL, stg->yi[kk], nxt);
+          }
+          __syncwarp();
+          for (int gp = 0; gp < ngrp; ++gp)
+            if (lane < BCH && c0 + lane < n) a.y[(size_t)(inst0 + gp) * n + c0 + lane] = stg0[gp].yo[lane];
+          __syncwarp();
+        }
+      }
+      PROF_ADD(2);
+      // ---- backward, column-oriented: x_k = acc_k / U(k,k); acc_{k-j} -= U(k-j,k) x_k.
+      // Lane j of a group holds the accumulator of row k-j (j = 0..8)
+      {
+        double2 acc = (lane_ok && n - 1 - gl >= 0) ? yme[n - 1 - gl] : make_double2(0.0, 0.0);
+        const int ucol = min(gl, BW - 1);
+        for (int c0 = ((n - 1) / BCH) * BCH; c0 >= 0; c0 -= BCH) {
+          for (int gp = 0; gp < ngrp; ++gp) {
+            const size_t ib = (size_t)(inst0 + gp);
+            Stage *sg = stg0 + gp;
+#pragma unroll
+            for (int q = 0; q < (BCH * BW + 31) / 32; ++q) {
+              const int el = q * 32 + lane, e = c0 * BW + el;
+              if (el < BCH * BW) sg->ub[el] = (e < n * BW) ? a.U[ib * nU + e] : make_double2(0.0, 0.0);
+            }
+            if (lane < BCH) {
+              const int r = c0 + lane - BW;
+              sg->yi[lane] = (r >= 0) ? a.y[ib * n + r] : make_double2(0.0, 0.0);
+            }
+          }
+          __syncwarp();
+          const int hi = min(BCH, n - c0);
+          for (int kk = hi - 1; kk >= 0; --kk) {
+            const double2 um = stg->ub[kk * BW + ucol];          // lane 0: 1/U(k,k); lane j: U(k-j, k)
+            const double2 v = shfl2(cmul2(acc, um), lead);       // x_k
+            if (leader) stg->yo[kk] = v;
+            const double2 upd = cfnma2(acc, um, v);
+            const double2 nxt = make_double2(__shfl_down_sync(0xffffffffu, upd.x, 1), __shfl_down_sync(0xffffffffu, upd.y, 1));
+            acc = sel2(gl == BW - 1, stg->yi[kk], nxt);          // lane 8 takes the entering row k-9
+          }
+          __syncwarp();
+          for (int gp = 0; gp < ngrp; ++gp)
+            if (lane < BCH && c0 + lane < n) a.y[(size_t)(inst0 + gp) * n + c0 + lane] = stg0[gp].yo[lane];
+          __syncwarp();
+        }
+      }
+      PROF_ADD(6);
+      // ---- omega = sigma + y^H x / y^H y ; x = y / |y|
+      double myyx = 0.0, myyxi = 0.0, myyy = 1.0;
+      for (int gp = 0; gp < ngrp; ++gp) {
+        const bool on = __shfl_sync(0xffffffffu, (int)inner_on, gp * BW) != 0;
+        if (!on) continue;
+        double2 *xg = a.x + (size_t)(inst0 + gp) * n;
+        const double2 *yg = a.y + (size_t)(inst0 + gp) * n;
+        double yxr = 0.0, yxi = 0.0, yy = 0.0;
+        for (int i = lane; i < n; i += 32) {
+          const double2 v = yg[i], xo = xg[i];
+          const double2 t = cmulc2(v, xo);
+          yxr += t.x; yxi += t.y;
+          yy += v.x * v.x + v.y * v.y;
+        }
+        yxr = warp_sum(yxr); yxi = warp_sum(yxi); yy = warp_sum(yy);
+        const double rn = rsqrt(yy);
+        for (int i = lane; i < n; i += 32) xg[i] = make_double2(yg[i].x * rn, yg[i].y * rn);
+        if (g == gp) { myyx = yxr; myyxi = yxi; myyy = yy; }
+      }
+      __syncwarp();
+      if (inner_on) {
+        const double2 om_new = cadd2(sigma, make_double2(myyx / myyy, myyxi / myyy));
+        dl = hypot(om_new.x - om.x, om_new.y - om.y);
+        om = om_new;
+        it = step + 1;
+        if (step > 0 && dl <= a.tol * hypot(om.x, om.y)) inner_on = false;
+      }
+      PROF_ADD(0);
+    }
+    if (act) {
+      total += it;
+      if (dl <= a.tol * hypot(om.x, om.y)) done = true;
+      else sigma = om;  // re-shift (Rayleigh-quotient style) and refactorise
+    }
+  }
+  if (alive && gl == 0) {
+    a.omega[inst] = om;
+    a.delta[inst] = dl;
+    a.iters[inst] = total;
+  }
+  if (a.evec) {
+    // normalise by the component of largest modulus, lowest index on ties (orrfdchan.f:849-857)
+    for (int gp = 0; gp < ngrp; ++gp) {
+      const double2 *xg = a.x + (size_t)(inst0 + gp) * n;
+      double best = -1.0;
+      int bi = 0;
+      for (int i = lane; i < n; i += 32) {
+        const double2 v = xg[i];
+        const double m2 = v.x * v.x + v.y * v.y;
+        if (m2 > best) { best = m2; bi = i; }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+      }
+      const double2 esc = cdiv2(make_double2(1.0, 0.0), xg[bi]);
+      double2 *ev = a.evec + (size_t)(inst0 + gp) * (n + 2);
+      if (lane == 0) { ev[0] = make_double2(0.0, 0.0); ev[n + 1] = make_double2(0.0, 0.0); }
+      for (int i = lane; i < n; i += 32) ev[i + 1] = cmul2(esc, xg[i]);
+    }
+  }
+}
+
 size_t chan_band_work_bytes(int n, int64_t ninst) {
   return (size_t)ninst * (size_t)n * (sizeof(double2) * (BW + BKL + 2) + 1) + 256;
 }
 
 cudaError_t launch_chan_fd_banded(int n, const double *D2, const double *D4, const double *u, const double *d2u,
-                                  void *work, int64_t ninst, const double2 *alpha, const double *Re,
-                                  const double2 *sigma, int outer, int inner, double tol, double2 *omega,
-                                  double *delta, int32_t *iters, double2 *evec, cudaStream_t st) {
+                                  const double2 *band24, void *work, int64_t ninst, const double2 *alpha,
+                                  const double *Re, const double2 *sigma, int outer, int inner, double tol,
+                                  double2 *omega, double *delta, int32_t *iters, double2 *evec, cudaStream_t st) {
   BandArgs a;
-  a.n = n; a.D2 = D2; a.D4 = D4; a.u = u; a.d2u = d2u; a.ninst = ninst; a.alpha = alpha; a.Re = Re; a.sigma = sigma;
-  a.outer = outer; a.inner = inner; a.tol = tol; a.omega = omega; a.delta = delta; a.iters = iters; a.evec = evec;
+  a.n = n; a.D2 = D2; a.D4 = D4; a.u = u; a.d2u = d2u; a.band24 = band24; a.ninst = ninst; a.alpha = alpha; a.Re = Re;
+  a.sigma = sigma; a.outer = outer; a.inner = inner; a.tol = tol; a.omega = omega; a.delta = delta; a.iters = iters;
+  a.evec = evec;
   double2 *w = (double2 *)work;
   const size_t N1 = (size_t)ninst * n;
   a.U = w; a.L = w + N1 * BW; a.x = w + N1 * (BW + BKL); a.y = w + N1 * (BW + BKL + 1);
   a.piv = (int8_t *)(w + N1 * (BW + BKL + 2));
+  // nine lanes per instance while that still leaves the GPU room (the one-thread kernel needs
+  // ~10^5 instances to fill it); OSB_FD_THREAD=1 forces the one-thread kernel
+  if (band24 && ninst <= BAND_WARP_MAX_INST && !getenv("OSB_FD_THREAD")) {
+    const int64_t per_cta = (int64_t)BG * BWW;
+    const unsigned grid = (unsigned)((ninst + per_cta - 1) / per_cta);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e;
+    if ((int64_t)grid <= 2 * (int64_t)sms) {
+      const size_t smem = sizeof(BandStage<32>) * BG * BWW;
+      e = cudaFuncSetAttribute(chan_fd_banded_warp_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      chan_fd_banded_warp_kernel<32, 2><<<grid, BWW * 32, smem, st>>>(a);
+    } else {
+      const size_t smem = sizeof(BandStage<16>) * BG * BWW;
+      e = cudaFuncSetAttribute(chan_fd_banded_warp_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      chan_fd_banded_warp_kernel<16, 3><<<grid, BWW * 32, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+  }
   const int threads = 32;  // few, long-running threads: spread them over all SMs
   const unsigned grid = (unsigned)((ninst + threads - 1) / threads);
   chan_fd_banded_kernel<<<grid, threads, 0, st>>>(a);

@@ -33,14 +33,15 @@ struct osb_chan {
   int disc = 0, N = 0, n = 0;
   std::vector<double> eta, u, d1u, d2u, D2full, D4full;  // host copies, full (N+1) grid, row-major (i,j)
   double *dD2 = nullptr, *dD4 = nullptr, *du = nullptr, *dd2u = nullptr;  // device, interior, column-major
+  double2 *dBand = nullptr;  // FD only: [n][9] (D2, D4)(r, r-4+j), the band of the 9-diagonal operator
   int device = 0;
   osb_chan() = default;
   osb_chan(const osb_chan &) = delete;
   osb_chan &operator=(const osb_chan &) = delete;
   ~osb_chan() {
-    if (!dD2 && !dD4 && !du && !dd2u) return;
+    if (!dD2 && !dD4 && !du && !dd2u && !dBand) return;
     cudaSetDevice(device);
-    cudaFree(dD2); cudaFree(dD4); cudaFree(du); cudaFree(dd2u);
+    cudaFree(dD2); cudaFree(dD4); cudaFree(du); cudaFree(dd2u); cudaFree(dBand);
   }
 };
 
@@ -165,6 +166,18 @@ int osb_chan_create(osb_ctx *ctx, int disc, int N, osb_chan **out) {
   CH_CUDA(ctx, cudaMemcpy(c->dD4, h4.data(), h4.size() * sizeof(double), cudaMemcpyHostToDevice));
   CH_CUDA(ctx, cudaMemcpy(c->du, hu.data(), n * sizeof(double), cudaMemcpyHostToDevice));
   CH_CUDA(ctx, cudaMemcpy(c->dd2u, hd.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  if (disc == OSB_DISC_FD) {
+    std::vector<double> hb((size_t)n * 9 * 2, 0.0);
+    for (int r = 0; r < n; ++r)
+      for (int j = 0; j < 9; ++j) {
+        const int cc = r - 4 + j;
+        if (cc < 0 || cc >= n) continue;
+        hb[((size_t)r * 9 + j) * 2] = at(c->D2full, N, r + 1, cc + 1);
+        hb[((size_t)r * 9 + j) * 2 + 1] = at(c->D4full, N, r + 1, cc + 1);
+      }
+    CH_CUDA(ctx, cudaMalloc(&c->dBand, hb.size() * sizeof(double)));
+    CH_CUDA(ctx, cudaMemcpy(c->dBand, hb.data(), hb.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
   *out = c.release();
   return OSB_OK;
 }
@@ -214,7 +227,7 @@ static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::ve
   CH_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * ninst, sigma.data(), ninst * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   CH_CUDA(ctx, cudaMemcpyAsync(d_in + 4 * ninst, Re.data(), ninst * sizeof(double), cudaMemcpyHostToDevice, st));
   if (banded)
-    CH_CUDA(ctx, launch_chan_fd_banded(n, c->dD2, c->dD4, c->du, c->dd2u, work, ninst, (const double2 *)d_in,
+    CH_CUDA(ctx, launch_chan_fd_banded(n, c->dD2, c->dD4, c->du, c->dd2u, c->dBand, work, ninst, (const double2 *)d_in,
                                        d_in + 4 * ninst, (const double2 *)(d_in + 2 * ninst), outer, inner, tol,
                                        (double2 *)d_out, d_out + 2 * ninst, d_it, d_evec, st));
   else

@@ -125,7 +125,7 @@ cudaError_t launch_chan_eig(int n, const double *D2, const double *D4, const dou
                             double2 *omega, double *delta, int32_t *iters, double2 *evec, cudaStream_t st);
 size_t chan_band_work_bytes(int n, int64_t ninst);
 cudaError_t launch_chan_fd_banded(int n, const double *D2, const double *D4, const double *u, const double *d2u,
-                                  void *work, int64_t ninst, const double2 *alpha, const double *Re,
+                                  const double2 *band24, void *work, int64_t ninst, const double2 *alpha, const double *Re,
                                   const double2 *sigma, int outer, int inner, double tol, double2 *omega,
                                   double *delta, int32_t *iters, double2 *evec, cudaStream_t st);
 cudaError_t launch_chan_neutral(int n, const double *D2, const double *D4, const double *u, const double *d2u,

@@ -138,3 +138,30 @@ def test_collocation_against_quad_arbiter(engine, oracle, N):
     # the discrete eigenvalue converges to the shooting value 0.23752648882+0.0037396706230i
     if N >= 128:
         assert abs(w_quad - complex(0.23752648882, 0.0037396706230)) < 1e-9
+
+
+@pytest.mark.parametrize("N", [64, 100, 512])
+def test_banded_warp_kernel_matches_thread_kernel(engine, N, monkeypatch):
+    """The FD operator has two banded-LU kernels: a warp per instance (small sweeps) and a thread
+    per instance (GPU-filling sweeps).  Same elimination (same pivots, L, U); the substitutions
+    differ in rounding only, so eigenvalues agree to ~1e-13 and eigenvectors to 1e-9."""
+    alpha = np.concatenate([np.linspace(0.76, 1.16, 37), [1.0 + 0.01j, 0.9 - 0.02j]])
+    ch = engine.chan(ob.DISC_FD, N)
+    monkeypatch.delenv("OSB_FD_THREAD", raising=False)
+    first = ch.solve(alpha, 1.0e4)  # scan included
+    sig = first["omega"]
+    a = ch.solve(alpha, 1.0e4, sigma0=sig, want_evec=True)
+    monkeypatch.setenv("OSB_FD_THREAD", "1")
+    b = ch.solve(alpha, 1.0e4, sigma0=sig, want_evec=True)
+    second = ch.solve(alpha, 1.0e4)
+    monkeypatch.delenv("OSB_FD_THREAD")
+    ch.free()
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    phys = a["omega"].real > 0
+    # rounding of the two substitution orders is amplified by the conditioning of the FD operator (~N^4)
+    assert rel(a["omega"], b["omega"])[phys].max() < (1e-12 if N <= 128 else 2e-11)
+    # spurious FD modes (w_r < 0) are ill-conditioned: determined to ~1e-10 at N=64, ~1e-8 at N=512
+    assert rel(a["omega"], b["omega"]).max() < (1e-10 if N <= 128 else 1e-6)
+    assert np.max(np.abs(a["evec"] - b["evec"])[phys]) < 1e-8
+    # the scan picks the same mode through either kernel (spurious FD modes: ill-conditioned, 1e-9)
+    assert rel(first["omega"], second["omega"]).max() < (1e-9 if N <= 128 else 1e-6)
