@@ -148,6 +148,25 @@ int osb_shoot_temporal_dev(osb_ctx *ctx, const osb_shoot_opts *opts,
                            double *d_resid, double *d_history, int32_t hist_cap);
 
 /*
+ * Neutral curve by shooting (the reference has no program for it -- orrncbl's
+ * boundary-layer branch is dead code -- so there is no parity target, only physics checks):
+ * for every Re_i the real alpha_i with Im c(alpha_i, Re_i) = 0, by a secant iteration on alpha
+ * whose every step is ONE batched temporal solve (osb_shoot_temporal's kernels) over the points
+ * still iterating.  The eigenvalue guess of a step is continued linearly from the two previous ones.
+ *   Re [npts], alpha0 [npts] (real, solver units), c0 [2*npts] eigenvalue guess at alpha0
+ *   dalpha_rel   the second secant point is alpha0 (1 + dalpha_rel)
+ *   tol          stop when |Im c| <= tol ;  maxit secant steps at most
+ *   alpha_out [npts], c_out [2*npts], steps [npts],
+ *   status [npts]: OSB_ST_CONVERGED, OSB_ST_MAXCOUNT (maxit reached or an inner solve did not
+ *   converge), OSB_ST_NONFINITE
+ * Temporal flows only (CONTEBL, CONTE, ORRSOM).
+ */
+int osb_shoot_neutral(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof,
+                      int64_t npts, const double *Re, const double *alpha0, const double *c0,
+                      double dalpha_rel, double tol, int32_t maxit,
+                      double *alpha_out, double *c_out, int32_t *steps, int32_t *status);
+
+/*
  * Batched spatial continuation lines (the omega sweep of orrspace.f:186-195):
  * nlines independent lines, each niter points; point i of a line starts from
  * the converged alpha of point i-1 (sequential inside a line, parallel across).

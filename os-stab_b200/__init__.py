@@ -90,6 +90,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "osb_shoot_temporal": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, _dp, _dp, _dp, _ip, _ip, _ip, _dp, _dp, i32]),
         "osb_shoot_temporal_dev": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
         "osb_shoot_spatial_lines": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, i32, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _ip, _dp, i32]),
+        "osb_shoot_neutral": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, _dp, _dp, _dp, dbl, dbl, i32, _dp, _dp, _ip, _ip]),
         "osb_eigfun": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, _dp, _dp, _dp, _dp, _dp, _dp, _ip]),
         "osb_measure_fp64_peak": (C.c_int, [vp, dbl, _dp, _dp]),
         "osb_chan_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
@@ -109,7 +110,7 @@ EXPORTED_SYMBOLS = (
     "osb_version osb_create osb_create_multi osb_destroy osb_device_count osb_last_error osb_stream "
     "osb_launch_count osb_profile_blasius osb_profile_blasius_batch osb_profile_upload "
     "osb_profile_shift osb_profile_channel osb_profile_get osb_profile_nbl osb_profile_free osb_shoot_defaults "
-    "osb_shoot_temporal osb_shoot_temporal_dev osb_shoot_spatial_lines osb_eigfun osb_measure_fp64_peak "
+    "osb_shoot_temporal osb_shoot_temporal_dev osb_shoot_spatial_lines osb_shoot_neutral osb_eigfun osb_measure_fp64_peak "
     "osb_chan_create osb_chan_free osb_chan_tables osb_chan_eig osb_chan_neutral"
 ).split()
 
@@ -308,6 +309,23 @@ class Engine:
         if hist_cap:
             r["history"] = hist.reshape(n, niter, hist_cap, 4)
         return r
+
+    def shoot_neutral(self, opts: ShootOpts, prof: Profile, Re, alpha0, c0, dalpha_rel=1.0e-3, tol=1.0e-10, maxit=20):
+        """Neutral points Im c(alpha, Re) = 0 by a batched secant iteration on alpha.
+        Returns dict(alpha, c, steps, status)."""
+        Re = _f64(Re)
+        n = Re.size
+        a0 = _f64(alpha0, n)
+        cc = _cplx_pairs(c0, n)
+        alpha = np.zeros(n)
+        cout = np.zeros(2 * n)
+        steps = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.osb_shoot_neutral(
+            self.ctx, C.byref(opts), prof.handle, n, Re.ctypes.data_as(_dp), a0.ctypes.data_as(_dp), cc.ctypes.data_as(_dp),
+            float(dalpha_rel), float(tol), int(maxit), alpha.ctypes.data_as(_dp), cout.ctypes.data_as(_dp),
+            steps.ctypes.data_as(_ip), status.ctypes.data_as(_ip)))
+        return dict(alpha=alpha, c=cout.view(np.complex128), steps=steps, status=status)
 
     def eigfun(self, opts: ShootOpts, prof: Profile, Re, eig, alpha=None, omega=None):
         Re = _f64(Re)

@@ -627,6 +627,93 @@ int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_
   return OSB_OK;
 }
 
+int osb_shoot_neutral(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof,
+                      int64_t npts, const double *Re, const double *alpha0, const double *c0,
+                      double dalpha_rel, double tol, int32_t maxit,
+                      double *alpha_out, double *c_out, int32_t *steps, int32_t *status) {
+  if (!ctx || npts < 0 || !Re || !alpha0 || !c0 || !alpha_out || !c_out || !steps || !status)
+    return fail(ctx, OSB_E_ARG, "null argument");
+  if (!opts || opts->flow == OSB_FLOW_ORRSPACE) return fail(ctx, OSB_E_ARG, "neutral search needs a temporal flow");
+  if (maxit < 1 || !(tol > 0.0) || dalpha_rel == 0.0) return fail(ctx, OSB_E_ARG, "maxit < 1, tol <= 0 or dalpha_rel == 0");
+  if (npts == 0) return OSB_OK;
+  // secant state per point: (a0, c at a0) and (a1, c at a1)
+  std::vector<double> a_prev(alpha0, alpha0 + npts), a_cur(npts), c_prev(2 * npts), c_cur(2 * npts);
+  std::vector<int64_t> active(npts);
+  for (int64_t i = 0; i < npts; ++i) {
+    active[i] = i;
+    steps[i] = 0;
+    status[i] = OSB_ST_MAXCOUNT;
+    alpha_out[i] = alpha0[i];
+    c_out[2 * i] = c0[2 * i]; c_out[2 * i + 1] = c0[2 * i + 1];
+  }
+  std::vector<double> al, rr, cc, res;
+  std::vector<int32_t> ps, qe, st;
+  auto solve = [&](const std::vector<int64_t> &idx, const std::vector<double> &alpha, std::vector<double> &cio) -> int {
+    const int64_t m = (int64_t)idx.size();
+    al.resize(2 * m); rr.resize(m); cc.resize(2 * m); ps.resize(m); qe.resize(m); st.resize(m);
+    for (int64_t k = 0; k < m; ++k) {
+      const int64_t i = idx[k];
+      al[2 * k] = alpha[i]; al[2 * k + 1] = 0.0;
+      rr[k] = Re[i];
+      cc[2 * k] = cio[2 * i]; cc[2 * k + 1] = cio[2 * i + 1];
+    }
+    int rc = osb_shoot_temporal(ctx, opts, prof, m, al.data(), rr.data(), cc.data(), ps.data(), qe.data(), st.data(),
+                                nullptr, nullptr, 0);
+    if (rc) return rc;
+    for (int64_t k = 0; k < m; ++k) {
+      const int64_t i = idx[k];
+      cio[2 * i] = cc[2 * k]; cio[2 * i + 1] = cc[2 * k + 1];
+    }
+    return OSB_OK;
+  };
+  // first point of the secant: c at alpha0
+  for (int64_t i = 0; i < npts; ++i) { c_prev[2 * i] = c0[2 * i]; c_prev[2 * i + 1] = c0[2 * i + 1]; }
+  int rc = solve(active, a_prev, c_prev);
+  if (rc) return rc;
+  {
+    std::vector<int64_t> keep;
+    for (int64_t k = 0; k < (int64_t)active.size(); ++k) {
+      const int64_t i = active[k];
+      const bool fin = std::isfinite(c_prev[2 * i]) && std::isfinite(c_prev[2 * i + 1]);
+      alpha_out[i] = a_prev[i]; c_out[2 * i] = c_prev[2 * i]; c_out[2 * i + 1] = c_prev[2 * i + 1];
+      if (!fin) { status[i] = OSB_ST_NONFINITE; continue; }
+      if (st[k] != OSB_ST_CONVERGED) continue;                      // inner solve failed: stays MAXCOUNT
+      if (fabs(c_prev[2 * i + 1]) <= tol) { status[i] = OSB_ST_CONVERGED; continue; }
+      a_cur[i] = a_prev[i] * (1.0 + dalpha_rel);
+      c_cur[2 * i] = c_prev[2 * i]; c_cur[2 * i + 1] = c_prev[2 * i + 1];
+      keep.push_back(i);
+    }
+    active.swap(keep);
+  }
+  for (int it = 1; it <= maxit && !active.empty(); ++it) {
+    rc = solve(active, a_cur, c_cur);
+    if (rc) return rc;
+    std::vector<int64_t> keep;
+    for (int64_t k = 0; k < (int64_t)active.size(); ++k) {
+      const int64_t i = active[k];
+      steps[i] = it;
+      const double cr = c_cur[2 * i], ci = c_cur[2 * i + 1];
+      if (!(std::isfinite(cr) && std::isfinite(ci))) { status[i] = OSB_ST_NONFINITE; continue; }
+      if (st[k] != OSB_ST_CONVERGED) continue;
+      alpha_out[i] = a_cur[i]; c_out[2 * i] = cr; c_out[2 * i + 1] = ci;
+      if (fabs(ci) <= tol) { status[i] = OSB_ST_CONVERGED; continue; }
+      const double da = a_cur[i] - a_prev[i], dci = ci - c_prev[2 * i + 1];
+      if (da == 0.0 || dci == 0.0) continue;                        // stalled
+      const double step = -ci * da / dci;                            // secant on g(alpha) = Im c
+      const double a_new = a_cur[i] + step;
+      if (!(a_new > 0.0) || !std::isfinite(a_new)) continue;
+      // continue the eigenvalue guess along the secant
+      const double dcr = (cr - c_prev[2 * i]) / da, dcim = dci / da;
+      a_prev[i] = a_cur[i]; c_prev[2 * i] = cr; c_prev[2 * i + 1] = ci;
+      a_cur[i] = a_new;
+      c_cur[2 * i] = cr + dcr * step; c_cur[2 * i + 1] = ci + dcim * step;
+      keep.push_back(i);
+    }
+    active.swap(keep);
+  }
+  return OSB_OK;
+}
+
 int osb_eigfun(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof, int64_t npts,
                const double *alpha, const double *Re, const double *eig, const double *omega,
                double *y, double *vmax, int32_t *qend) {

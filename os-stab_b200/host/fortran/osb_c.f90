@@ -102,6 +102,22 @@ module osb_c
       real(c_double), intent(out) :: history(4, hist_cap, niter, *)   ! ctemp, err per pass (orrspace.f:485-488)
       integer(c_int32_t), value :: hist_cap
     end function
+    !> (new) neutral points Im c(alpha, Re) = 0 by a batched secant iteration on alpha
+    integer(c_int) function osb_shoot_neutral(ctx, opts, prof, npts, Re, alpha0, c0, dalpha_rel, tol, maxit, &
+                                              alpha_out, c_out, steps, status) &
+        bind(C, name="osb_shoot_neutral")
+      import :: c_int, c_int32_t, c_int64_t, c_ptr, c_double, c_double_complex, osb_shoot_opts
+      type(c_ptr), value :: ctx, prof
+      type(osb_shoot_opts), intent(in) :: opts
+      integer(c_int64_t), value :: npts
+      real(c_double), intent(in) :: Re(*), alpha0(*)
+      complex(c_double_complex), intent(in) :: c0(*)
+      real(c_double), value :: dalpha_rel, tol
+      integer(c_int32_t), value :: maxit
+      real(c_double), intent(out) :: alpha_out(*)
+      complex(c_double_complex), intent(out) :: c_out(*)
+      integer(c_int32_t), intent(out) :: steps(*), status(*)
+    end function
     !> replaces the "second pass" (shoot.f:762-810): y(i,k) un-normalised + vmax
     integer(c_int) function osb_eigfun(ctx, opts, prof, npts, alpha, Re, eig, omega, y, vmax, qend) &
         bind(C, name="osb_eigfun")

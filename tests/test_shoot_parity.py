@@ -530,3 +530,39 @@ def _free_bytes():
     import torch
 
     return torch.cuda.mem_get_info(0)[0]
+
+
+def test_neutral_curve_by_secant_on_alpha(engine, osb, oracle, bl, bl_oracle):
+    """osb_shoot_neutral (no reference counterpart): both branches of the Blasius neutral
+    curve for 48 Reynolds numbers, started from the sign changes of a coarse grid.  Checks: Im c = 0
+    to 1e-10 at the returned alpha, agreement with the grid contour, the CPU oracle sees the same
+    neutral points, and the nose of the curve is where the literature puts it."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import neutral_from_grid as nf
+
+    rows, ci, Re_in, alpha_in = nf.neutral_curve(engine, bl, na=128, nre=48)
+    rows = rows[rows[:, 0] > 330.0]                       # away from the nose, where the branches merge
+    assert len(rows) >= 60
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    Re = rows[:, 0] * S2
+    a0 = rows[:, 1] * S2
+    c0 = rows[:, 2] + 0j
+    r = engine.shoot_neutral(opts, bl, Re, a0, c0, dalpha_rel=2e-3, tol=1e-10, maxit=20)
+    assert (r["status"] == 0).all(), np.nonzero(r["status"])[0]
+    assert np.abs(r["c"].imag).max() <= 1e-10
+    assert r["steps"].max() <= 8
+    assert np.abs(r["alpha"] / S2 - rows[:, 1]).max() < 2e-3   # the contour was linear interpolation on a coarse grid
+    assert np.abs(r["c"].real - rows[:, 2]).max() < 5e-3
+    # the oracle at the returned alpha: neutral to its own rounding
+    prof = bl_oracle[0]
+    for i in (0, len(rows) // 2, len(rows) - 1):
+        ref = oracle.shoot_temporal(ob.FLOW_CONTEBL, ob.INT_CK45, 1000, 10.0, 0.0, 17.0, prof, r["alpha"][i], Re[i], r["c"][i])
+        assert abs(ref["c"].imag) < 1e-9 and abs(ref["c"] - r["c"][i]) < 1e-9
+    # a second call from perturbed starts lands on the same points
+    r2 = engine.shoot_neutral(opts, bl, Re, r["alpha"] * 1.004, r["c"], dalpha_rel=-1e-3, tol=1e-10, maxit=20)
+    assert (r2["status"] == 0).all()
+    # |d Im c / d alpha| ~ 0.05..0.3 on the curve, so Im c to 1e-10 pins alpha to ~1e-8
+    assert np.abs(r2["alpha"] - r["alpha"]).max() < 1e-7

@@ -6,7 +6,9 @@ interpolation in alpha along every Re row.  The reference has no result for this
 the physical check is the critical Reynolds number Re_delta* = 519.4 (R = 301.8 in
 contebl's units).
 
-  python tools/neutral_from_grid.py [--na 512] [--nre 256] [--out neutral.dat]
+  python tools/neutral_from_grid.py [--na 512] [--nre 256] [--out neutral.dat] [--refine]
+
+--refine polishes every contour point with osb_shoot_neutral (secant on alpha to |Im c| <= 1e-10).
 """
 import argparse
 import sys
@@ -50,10 +52,23 @@ def main():
     ap.add_argument("--na", type=int, default=512)
     ap.add_argument("--nre", type=int, default=256)
     ap.add_argument("--out", default="neutral.dat")
+    ap.add_argument("--refine", action="store_true")
     args = ap.parse_args()
     eng = osb.Engine(0)
     prof = eng.solve_bl()
     rows, ci, Re_in, alpha_in = neutral_curve(eng, prof, args.na, args.nre)
+    if args.refine:
+        import time
+
+        opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+        t0 = time.perf_counter()
+        r = eng.shoot_neutral(opts, prof, rows[:, 0] * bench.S2, rows[:, 1] * bench.S2, rows[:, 2] + 0j, dalpha_rel=2e-3)
+        dt = time.perf_counter() - t0
+        ok = r["status"] == 0
+        print(f"refined {int(ok.sum())} of {len(rows)} points to |Im c| <= 1e-10 in {dt * 1e3:.1f} ms "
+              f"({len(rows) / dt:.0f} neutral points/s, {r['steps'].mean():.2f} secant steps each)")
+        rows[ok, 1] = r["alpha"][ok] / bench.S2
+        rows[ok, 2] = r["c"].real[ok]
     np.savetxt(args.out, rows, header="Re alpha c_r branch(+1 lower, -1 upper)")
     unstable = (ci > 0).any(axis=1)
     print(f"{len(rows)} neutral points; first unstable row Re = {Re_in[unstable][0]:.2f} (Re_delta* = {Re_in[unstable][0] * 1.7207876:.1f})")
