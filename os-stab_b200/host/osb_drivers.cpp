@@ -31,6 +31,7 @@
 using fortfmt::E;
 using fortfmt::ES;
 using fortfmt::I;
+using fortfmt::F;
 typedef std::complex<double> cd;
 
 static void die(osb_ctx *ctx, const char *what, int rc) {
@@ -635,10 +636,43 @@ static int run_orrfdchan(osb_ctx *ctx) {
   std::vector<double> al(2 * npts), om(2 * npts);
   std::vector<int32_t> it(npts), st(npts);
   for (int j = 0; j < nai; ++j) for (int i = 0; i < nar; ++i) { al[2 * (j * nar + i)] = alphar[i]; al[2 * (j * nar + i) + 1] = alphai[j]; }
-  CK(ctx, osb_chan_eig(ctx, chan, Re, npts, al.data(), nullptr, om.data(), nullptr, it.data(), st.data()));
+  const bool print = (ians == 1);
+  std::vector<double> ev;
+  if (print) ev.resize((size_t)npts * (n + 1) * 2);
+  CK(ctx, osb_chan_eig(ctx, chan, Re, npts, al.data(), nullptr, om.data(), print ? ev.data() : nullptr, it.data(), st.data()));
+  std::vector<double> eta;
+  if (print) {
+    eta.resize(n + 1);
+    CK(ctx, osb_chan_tables(ctx, chan, eta.data(), nullptr, nullptr, nullptr, nullptr));
+  }
   FILE *dat = fopen((filename + ".dat").c_str(), "w");
+  FILE *f20 = print ? fopen("fort.20", "w") : nullptr;
   int bad = 0;
   for (int64_t p = 0; p < npts; ++p) {
+    if (print) {
+      // the `if (print)` block of SOLVE_ORR_SOM (orrfdchan.f:832-873).  The reference lists the
+      // whole ZGEEV spectrum here; this engine isolates the one mode the sweep keeps,
+      // so the table has that single row.  Whatever index is typed, the reference writes the
+      // eigenvector of the KEPT mode (iloc), normalised by its largest component, to fort.11.
+      const cd alpha(al[2 * p], al[2 * p + 1]), w(om[2 * p], om[2 * p + 1]);
+      printf("\n Residual = %s\n", F(0.0, 17, 10).c_str());
+      printf("\n %s    %s    %s    \n", E(Re, 17, 10).c_str(), E(alpha.real(), 17, 10).c_str(), E(alpha.imag(), 17, 10).c_str());
+      printf("\n        w_r                w_i              count\n\n");
+      printf(" %s    %s    %s\n", E(w.real(), 17, 10).c_str(), E(w.imag(), 17, 10).c_str(), I(1, 5).c_str());
+      const cd cph = w / alpha;
+      fprintf(f20, " %s    %s    \n", E(cph.real(), 17, 10).c_str(), E(cph.imag(), 17, 10).c_str());
+      int which = 0;
+      printf("\n Eigenvector for which eigenvalue (0 quits) ==> ");
+      while (std::cin >> which && which != 0) {
+        const double *v = ev.data() + (size_t)p * (n + 1) * 2;
+        FILE *f = fopen("fort.11", "w");  // format 60; the two adjoint columns are not computed (zeros)
+        for (int j = 0; j <= n; ++j)
+          fprintf(f, " %s %s %s %s %s \n", ES(eta[j], 16, 8, 3).c_str(), ES(v[2 * j], 16, 8, 3).c_str(),
+                  ES(v[2 * j + 1], 16, 8, 3).c_str(), ES(0.0, 16, 8, 3).c_str(), ES(0.0, 16, 8, 3).c_str());
+        fclose(f);
+        printf("\n Eigenvector for which eigenvalue (0 quits) ==> ");
+      }
+    }
     const std::string row = " " + ES(al[2 * p], 16, 8, 3) + " " + ES(al[2 * p + 1], 16, 8, 3) + " " + ES(om[2 * p], 16, 8, 3) + " " +
                             ES(om[2 * p + 1], 16, 8, 3) + " ";
     fprintf(dat, "%s\n", row.c_str());
@@ -646,6 +680,7 @@ static int run_orrfdchan(osb_ctx *ctx) {
     bad |= st[p];
   }
   fclose(dat);
+  if (f20) fclose(f20);
   {
     FILE *q = fopen((filename + ".q").c_str(), "w");  // orrfdchan.f:130-138
     fprintf(q, "%s %s \n", I(nar, 5).c_str(), I(nai, 5).c_str());
@@ -658,7 +693,6 @@ static int run_orrfdchan(osb_ctx *ctx) {
     write5(q, v);
     fclose(q);
   }
-  (void)ians;
   osb_chan_free(ctx, chan);
   return bad;
 }

@@ -277,3 +277,27 @@ def test_conteucbl_saddle_tracking(tmp_path, oracle):
         assert abs(float(row[0]) - u) < 1e-4
         assert abs(complex(float(row[1]), float(row[2])) - ev0) < 1e-7
         assert abs(complex(float(row[3]), float(row[4])) - alphas) < 1e-6
+
+
+@pytest.mark.gpu
+def test_orrfdchan_fdchan_deck_prints_eigenvector(tmp_path):
+    """fdchan.inp (README.md:126): N=128, alpha=1, 'Print eigenvectors' = 1, then which = 1, 0.
+    The reference writes the eigenvector of the mode it keeps (normalised by its largest
+    component) to fort.11 whatever index is typed (orrfdchan.f:843-871)."""
+    r = run("orrfdchan", "128\n10000\n1 1 1\n0 0 1\neig\n1\n1\n0\n", tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert "  nar =     1  nai =     1" in r.stdout
+    assert "w_r                w_i              count" in r.stdout
+    assert r.stdout.count("Eigenvector for which eigenvalue (0 quits) ==>") == 2
+    dat = np.loadtxt(tmp_path / "eig.dat").reshape(-1, 4)
+    c = ob.chan(ob.DISC_FD, 128)
+    ref = c.solve_fd(1.0, 1.0e4, want_evec=True)
+    c.close()
+    assert abs(dat[0, 2] + 1j * dat[0, 3] - ref["omega"]) < 2e-8   # 8 printed digits
+    f11 = np.loadtxt(tmp_path / "fort.11")
+    assert f11.shape == (129, 5)
+    v = f11[:, 1] + 1j * f11[:, 2]
+    assert abs(np.abs(v).max() - 1.0) < 1e-8 and v[0] == 0 and v[-1] == 0
+    assert np.max(np.abs(v - ref["evec"])) < 1e-7
+    f20 = np.loadtxt(tmp_path / "fort.20").reshape(-1, 2)
+    assert abs(f20[0, 0] + 1j * f20[0, 1] - ref["omega"] / 1.0) < 1e-9

@@ -317,10 +317,10 @@ def test_blasius_neutral_curve_critical_reynolds(engine, bl):
     assert (hi[:, 3] > 0).any() and (hi[:, 3] < 0).any()
 
 
-@pytest.mark.parametrize("n", [500, 2000, 4000, 16000])
+@pytest.mark.parametrize("n", [500, 1000, 2000, 4000, 8000, 16000])
 def test_resolution_ladder_decks(engine, osb, oracle, n):
-    """tiny / normal / big / biggest.inp of the reference: nbl = nstep = n, Ymax = 30 -- the
-    largest sizes the reference ships (stage table 16000 x 6 rows)."""
+    """tiny / small / normal / big / bigger / biggest.inp of the reference: nbl = nstep = n,
+    Ymax = 30 -- the largest sizes the reference ships (stage table 16000 x 6 rows)."""
     p = engine.solve_bl(osb.FLOW_CONTEBL, osb.INT_CK45, n, 0.0, 30.0, 0.5, 0.0)
     t = p.tables()
     prof, npass, _ = oracle.solve_bl(ob.FLOW_CONTEBL, ob.INT_CK45, n, 0.0, 30.0, 0.5, 0.0)
@@ -337,6 +337,18 @@ def test_resolution_ladder_decks(engine, osb, oracle, n):
     # errtol = 1e-14 is at the rounding floor of err; after 16000 steps the floor itself is ~1e-14,
     # so the number of passes spent bouncing on it depends on the arithmetic (oracle 6, FMA 9)
     assert abs(r["passes"][0] - ref["passes"]) <= (1 if n <= 4000 else 6)
+
+
+def test_contebl_inp_deck(engine, osb, oracle, bl, bl_oracle):
+    """contebl.inp: alpha = 0.1453, Re = 581.1, guess 0.35 + 0.01i (a far guess: 7 passes)."""
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    r = engine.shoot_temporal(opts, bl, [0.1453 * S2], [581.1 * S2], [complex(0.35, 0.01)], hist_cap=20)
+    ref = oracle.shoot_temporal(ob.FLOW_CONTEBL, ob.INT_CK45, 1000, 10.0, 0.0, 17.0, bl_oracle[0], 0.1453 * S2, 581.1 * S2,
+                                complex(0.35, 0.01))
+    assert r["status"][0] == 0 and ref["status"] == 0
+    assert rel(r["c"][0], ref["c"]) < EIG_RTOL
+    assert (r["passes"][0], r["qend"][0]) == (ref["passes"], ref["qend"])
+    assert abs(r["c"][0] - complex(0.34978737, 0.01208610)) < 1e-5  # the mode orrsom (RK4, linear-search splines) finds for this deck
 
 
 def test_orrspace_space_deck_eigenfunction(engine, osb, oracle):
