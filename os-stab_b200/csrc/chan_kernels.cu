@@ -507,9 +507,12 @@ __device__ double2 inverse_iterate(const double2 *M, int n, const double *D2, co
                                    double2 sigma, ChanShared &s, int maxit, double tol, double *delta,
                                    int *iters) {
   double2 om = sigma;
-  double dl = 1.0e300;
+  double dl = 1.0e300, dl_prev = 1.0e300;
   int it = 0;
-  for (; it < maxit; ++it) {
+  // maxit is the nominal budget of one shift.  A dense refactorisation costs 6-9 solves, so when
+  // the budget is used up the iteration goes on (up to 3 budgets) as long as the observed
+  // contraction says that at most 6 more solves reach the tolerance.
+  for (; it < 3 * maxit; ++it) {
     PROF_T0();
     // y = B x = b2 D2 x + b0 x
     cta_d2_matvec(D2, n, s.x, s.y, false);
@@ -530,9 +533,15 @@ __device__ double2 inverse_iterate(const double2 *M, int n, const double *D2, co
     const double rn = rsqrt(yy.x);
     for (int i = threadIdx.x; i < n; i += blockDim.x) s.x[i] = make_double2(s.y[i].x * rn, s.y[i].y * rn);
     __syncthreads();
+    dl_prev = dl;
     dl = hypot(om_new.x - om.x, om_new.y - om.y);
     om = om_new;
-    if (it > 0 && dl <= tol * hypot(om.x, om.y)) { ++it; break; }
+    const double goal = tol * hypot(om.x, om.y);
+    if (it > 0 && dl <= goal) { ++it; break; }
+    if (it + 1 >= maxit) {
+      const double rho = dl / dl_prev;
+      if (!(rho < 0.5) || !(dl > 0.0) || log(goal / dl) / log(rho) > 6.0) { ++it; break; }
+    }
   }
   *delta = dl;
   *iters = it;
