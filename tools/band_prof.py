@@ -1,3 +1,6 @@
+#!/usr/bin/env python
+"""Phase split of the banded FD kernel (run with OSB_CHAN_PROFILE=1): 41 alpha at N = 128 and 512,
+scan + final solve, then a solve with the converged shifts given."""
 import sys, numpy as np
 sys.path.insert(0, '/root/repo')
 import os_stab_b200 as osb
