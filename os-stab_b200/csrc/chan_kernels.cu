@@ -32,6 +32,7 @@ namespace osb {
 constexpr int CH_THREADS = 256;      // CTAs of the 2-per-SM variant and of the Newton kernel
 constexpr int CH_THREADS_BIG = 512;  // the 1-per-SM variant (n > ~350): more warps to hide L2/HBM latency
 constexpr int CH_THREADS_MAX = 512;
+constexpr int CH_THREADS_SMALL = 128;
 constexpr int CH_NB = 16;
 
 // optional phase timers (cycles of block 0, thread 0); read back when OSB_CHAN_PROFILE is set
@@ -343,8 +344,8 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
   // ---- L y = P b (unit lower)
   for (int j0 = 0; j0 < n; j0 += 16) {
     const int nb = min(16, n - j0);
-    if (tid < 256) {
-      const int r = tid & 15, c = tid >> 4;
+    for (int e = tid; e < 256; e += nt) {
+      const int r = e & 15, c = e >> 4;
       if (r < nb && c < nb) dblk[r][c] = M[(size_t)(j0 + c) * n + j0 + r];
     }
     __syncthreads();
@@ -368,8 +369,8 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
   // ---- U x = y
   for (int j0 = ((n - 1) / 16) * 16; j0 >= 0; j0 -= 16) {
     const int nb = min(16, n - j0);
-    if (tid < 256) {
-      const int r = tid & 15, c = tid >> 4;
+    for (int e = tid; e < 256; e += nt) {
+      const int r = e & 15, c = e >> 4;
       if (r < nb && c < nb) dblk[r][c] = M[(size_t)(j0 + c) * n + j0 + r];
     }
     __syncthreads();
@@ -491,7 +492,7 @@ __device__ ChanShared carve(unsigned char *smem, int n) {
 
 // Small operators (n <= 96: chan.inp, nc.inp, fd-64.inp) keep the whole matrix in shared
 // memory next to the panel, so every phase runs at shared-memory latency.
-constexpr int CH_NSMEM = 96;
+constexpr int CH_NSMEM = 64;
 __host__ __device__ inline bool chan_matrix_in_smem(int n) { return n <= CH_NSMEM; }
 __host__ __device__ inline size_t chan_fixed_smem(int n) {
   size_t b = sizeof(double2) * ((size_t)(n + 16) * CH_NB + 3 * (size_t)n) + sizeof(double) * 64 + sizeof(int) * (size_t)(n + 8);
@@ -579,6 +580,9 @@ __device__ void start_vector(double2 *x, int n) {
 __device__ __forceinline__ void chan_eig_body(const ChanArgs &a);
 __global__ void __launch_bounds__(CH_THREADS, 2) chan_eig_kernel(const __grid_constant__ ChanArgs a) { chan_eig_body(a); }
 __global__ void __launch_bounds__(CH_THREADS_BIG, 1) chan_eig_kernel_big(const __grid_constant__ ChanArgs a) { chan_eig_body(a); }
+// 64 < n <= 200: the serial phases (panel, triangular solves) dominate and a row per thread is all the
+// panel can use; four small CTAs per SM overlap each other's barriers
+__global__ void __launch_bounds__(CH_THREADS_SMALL, 4) chan_eig_kernel_small(const __grid_constant__ ChanArgs a) { chan_eig_body(a); }
 __device__ __forceinline__ void chan_eig_body(const ChanArgs &a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int n = a.n;
@@ -1688,10 +1692,16 @@ static cudaError_t warp_grid(int n, int64_t ninst, int *grid, size_t *smem, cons
 }
 
 static bool use_big_kernel(int n) { return 2 * chan_smem_bytes(n) > 220 * 1024; }
+static bool use_small_kernel(int n) {
+  const char *e = getenv("OSB_CHAN_SMALL_MAX");  // tuning knob; default from measurements on B200
+  const int nmax = e ? atoi(e) : 200;
+  return n <= nmax && !chan_matrix_in_smem(n) && !getenv("OSB_CHAN_NO_SMALL");
+}
 
 cudaError_t chan_eig_grid(int n, int64_t ninst, int *grid, size_t *smem) {
   if (use_warp_kernels(n)) return warp_grid(n, ninst, grid, smem, (const void *)chan_eig_warp_kernel);
   if (use_big_kernel(n)) return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel_big, CH_THREADS_BIG);
+  if (use_small_kernel(n)) return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel_small, CH_THREADS_SMALL);
   return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel);
 }
 cudaError_t chan_neutral_grid(int n, int64_t ninst, int *grid, size_t *smem) {
@@ -1709,6 +1719,7 @@ cudaError_t launch_chan_eig(int n, const double *D2, const double *D4, const dou
   a.omega = omega; a.delta = delta; a.iters = iters; a.evec = evec;
   if (use_warp_kernels(n)) chan_eig_warp_kernel<<<grid, 32, smem, st>>>(a);
   else if (use_big_kernel(n)) chan_eig_kernel_big<<<grid, CH_THREADS_BIG, smem, st>>>(a);
+  else if (use_small_kernel(n)) chan_eig_kernel_small<<<grid, CH_THREADS_SMALL, smem, st>>>(a);
   else chan_eig_kernel<<<grid, CH_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
