@@ -209,6 +209,28 @@ typedef struct osb_chan osb_chan;
  * cosine grid, D1hat, D1 with rows 0,N zeroed, D2 = D1hat D1, D3, D4 formed with the
  * reference's own triple loops on the host (once per N), interior blocks uploaded. */
 int osb_chan_create(osb_ctx *ctx, int disc, int N, osb_chan **chan);
+/*
+ * Mapped boundary-layer operator (orrcolbl.f / orrfdbl.f): the semi-infinite domain
+ * y = Lmap (1+eta)/(1-eta), metrics m1..m4 of MAKE_BL_METRICS (orrcolbl.f:245-311), derivative matrices of
+ * MAKE_DERIVATIVES (orrcolbl.f:161-242: CHEBYD on the cosine grid; orrfdbl.f:145-222: FiniteD1 on the uniform
+ * grid eta_i = 1 - 2i/N), operator of MAKE_MATRIX (orrcolbl.f:470-600).  The reference reads the mean profile
+ * from an external file that it does not ship; here the caller passes U at the N+1 grid points
+ * (osb_chan_bl_points gives y_i; U[0..merge] is the free stream, set to 1 exactly) -- e.g. the Blasius
+ * profile of osb_profile_blasius.  d1u = D1hat u, d2u = D1hat^2 u, zeroed for j <= merge-2 (orrcolbl.f:404-427).
+ * The metrics are folded into row-scaled real tables on the host,
+ *     A = D4' - (2 alpha^2 + i alpha Re U) D2' + w0 I,   B = -i Re D2' + i alpha^2 Re I,
+ *     D2' = m1^2 D2 + m2 D1,   D4' = m1^4 D4 + 6 m1^2 m2 D3 + (3 m2^2 + 4 m1 m3) D2 + m4 D1,
+ * which is the channel operator's form: every osb_chan_* entry point (and every kernel) works on the
+ * handle unchanged.  osb_chan_eig without shifts keeps the most unstable mode found by the scan of
+ * 0 < c_r < 1 (orrcolbl.f:771-779 keeps the largest Im w of the full spectrum).
+ * Parity of this operator is unpinned (the reference programs need IMSL and the missing profile file);
+ * tests check it against the oracle's restatement and against the shooting eigenvalue of the same flow.
+ */
+int osb_chan_create_bl(osb_ctx *ctx, int disc /* OSB_DISC_CHEB | OSB_DISC_FD */, int N, double lmap,
+                       const double *U /* [N+1] */, int merge, osb_chan **out);
+/* y_i = Lmap (1+eta_i)/(1-eta_i) of the grid osb_chan_create_bl uses (y_0 = +inf); host-only helper */
+int osb_chan_bl_points(int disc, int N, double lmap, double *y /* [N+1] */);
+
 int osb_chan_free(osb_ctx *ctx, osb_chan *chan);
 /* eta, u, d2u: [N+1]; D2, D4: [(N+1)*(N+1)] row-major (i,j); any may be NULL */
 int osb_chan_tables(osb_ctx *ctx, const osb_chan *chan, double *eta, double *u, double *d2u,

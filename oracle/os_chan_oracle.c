@@ -76,6 +76,7 @@ typedef struct {
   int disc;
   double *eta, *u, *d1u, *d2u;          /* N+1                                  */
   double *D1hat, *D1, *D2, *D3, *D4;    /* (N+1)^2, element (i,j) at [i*(N+1)+j] */
+  double *m1, *m2, *m3, *m4;            /* N+1: mapping metrics (channel: 1,0,0,0) */
 } osr_chan;
 
 #define AT(M, i, j) (M)[(size_t)(i) * (size_t)(n + 1) + (size_t)(j)]
@@ -134,6 +135,9 @@ osr_chan *osr_chan_create(int disc, int n) {
   c->D1hat = (double *)calloc(nn, sizeof(double)); c->D1 = (double *)calloc(nn, sizeof(double));
   c->D2 = (double *)calloc(nn, sizeof(double)); c->D3 = (double *)calloc(nn, sizeof(double));
   c->D4 = (double *)calloc(nn, sizeof(double));
+  c->m1 = (double *)calloc(n1, sizeof(double)); c->m2 = (double *)calloc(n1, sizeof(double));
+  c->m3 = (double *)calloc(n1, sizeof(double)); c->m4 = (double *)calloc(n1, sizeof(double));
+  for (int i = 0; i <= n; ++i) c->m1[i] = 1.0;   /* orrfdchan.f:185-190: m1 = 1, m2 = m3 = m4 = 0 */
   /* MAKE_CHANNEL_METRICS orrfdchan.f:177-183 */
   const double pi = acos(-1.0);
   const double dth = pi / (double)n;
@@ -168,7 +172,51 @@ void osr_chan_destroy(osr_chan *c) {
   if (!c) return;
   free(c->eta); free(c->u); free(c->d1u); free(c->d2u);
   free(c->D1hat); free(c->D1); free(c->D2); free(c->D3); free(c->D4);
+  free(c->m1); free(c->m2); free(c->m3); free(c->m4);
   free(c);
+}
+
+/*
+ * Mapped boundary layer (orrcolbl.f / orrfdbl.f): y = Lmap (1+eta)/(1-eta).
+ *   MAKE_DERIVATIVES   orrcolbl.f:161-242 (CHEBYD on the cosine grid), orrfdbl.f:145-222 (FiniteD1 on the
+ *                      UNIFORM grid eta_i = 1 - 2 i/N, orrfdbl.f:258-265)
+ *   MAKE_BL_METRICS    orrcolbl.f:245-311 (m1..m4)
+ *   INIT_BL_PROFILE    orrcolbl.f:334-441: the reference interpolates an external profile file onto the grid;
+ *                      here the caller supplies U at the grid points (u[0..merge] = 1 exactly, the free
+ *                      stream).  d1u = D1hat u, d2u = D1hat D1hat u; both zeroed for j <= merge-2 (:419-427).
+ * disc: OSR_DISC_CHEB or OSR_DISC_FD.  The reference cannot be run (IMSL, missing profile file): parity of
+ * this operator is unpinned; the physics check is the shooting eigenvalue of the same flow.
+ */
+osr_chan *osr_chan_create_bl(int disc, int n, double lmap, const double *U, int merge) {
+  osr_chan *c = osr_chan_create(disc, n);
+  const size_t n1 = (size_t)n + 1, nn = n1 * n1;
+  if (disc == OSR_DISC_FD) {
+    const double deta = 2. / (double)n;
+    for (int i = 0; i <= n; ++i) c->eta[i] = 1. - (double)i * deta;
+    finite_d1(c->D1hat, n, c->eta); finite_d1(c->D1, n, c->eta);
+    for (int i = 0; i <= n; ++i) { AT(c->D1, 0, i) = 0.0; AT(c->D1, n, i) = 0.0; }
+    matmul_ref(c->D2, c->D1hat, c->D1, n);
+    matmul_ref(c->D3, c->D1hat, c->D2, n);
+    matmul_ref(c->D4, c->D1hat, c->D3, n);
+  }
+  for (int i = 0; i <= n; ++i) {
+    const double e1 = c->eta[i] - 1.;
+    c->m1[i] = (e1 * e1) / (2. * lmap);
+    c->m2[i] = (e1 * e1 * e1) / (2. * (lmap * lmap));
+    c->m3[i] = 3. * (e1 * e1 * e1 * e1) / (4. * (lmap * lmap * lmap));
+    c->m4[i] = 3. * (e1 * e1 * e1 * e1 * e1) / (2. * (lmap * lmap * lmap * lmap));
+    c->u[i] = (i <= merge) ? 1.0 : U[i];
+  }
+  double *D2hat = (double *)calloc(nn, sizeof(double));
+  matmul_ref(D2hat, c->D1hat, c->D1hat, n);
+  for (int i = 0; i <= n; ++i) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k <= n; ++k) { a = a + AT(c->D1hat, i, k) * c->u[k]; b = b + AT(D2hat, i, k) * c->u[k]; }
+    c->d1u[i] = a; c->d2u[i] = b;
+  }
+  for (int j = merge - 2; j >= 0; --j) { c->d1u[j] = 0.0; c->d2u[j] = 0.0; }
+  free(D2hat);
+  return c;
 }
 
 /* copy tables out for the tests: which = 0 eta, 1 u, 2 d1u, 3 d2u (N+1); 4 D2, 5 D4 ((N+1)^2) */
@@ -191,7 +239,7 @@ static void assemble(const osr_chan *c, zc alpha, double Re, int full, zc *A, zc
   const zc a2 = alpha * alpha, a3 = a2 * alpha, a4 = a2 * a2;
   for (int i = 0; i < m; ++i) {
     const int gi = i + off;
-    const double m1 = 1.0, m2 = 0., m3 = 0., m4 = 0.;
+    const double m1 = c->m1[gi], m2 = c->m2[gi], m3 = c->m3[gi], m4 = c->m4[gi];
     const zc w4 = m1 * m1 * m1 * m1;
     const zc w3 = 6. * (m1 * m1) * m2;
     const zc w2 = 3. * (m2 * m2) + 4. * m1 * m3 - 2. * a2 * (m1 * m1) - iu * alpha * Re * c->u[gi] * (m1 * m1);

@@ -94,6 +94,8 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "osb_eigfun": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, _dp, _dp, _dp, _dp, _dp, _dp, _ip]),
         "osb_measure_fp64_peak": (C.c_int, [vp, dbl, _dp, _dp]),
         "osb_chan_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
+        "osb_chan_create_bl": (C.c_int, [vp, C.c_int, C.c_int, dbl, _dp, C.c_int, C.POINTER(vp)]),
+        "osb_chan_bl_points": (C.c_int, [C.c_int, C.c_int, dbl, _dp]),
         "osb_chan_free": (C.c_int, [vp, vp]),
         "osb_chan_tables": (C.c_int, [vp, vp, _dp, _dp, _dp, _dp, _dp]),
         "osb_chan_eig": (C.c_int, [vp, vp, dbl, i64, _dp, _dp, _dp, _dp, _ip, _ip]),
@@ -111,7 +113,7 @@ EXPORTED_SYMBOLS = (
     "osb_launch_count osb_profile_blasius osb_profile_blasius_batch osb_profile_upload "
     "osb_profile_shift osb_profile_channel osb_profile_get osb_profile_nbl osb_profile_free osb_shoot_defaults "
     "osb_shoot_temporal osb_shoot_temporal_dev osb_shoot_spatial_lines osb_shoot_neutral osb_eigfun osb_measure_fp64_peak "
-    "osb_chan_create osb_chan_free osb_chan_tables osb_chan_eig osb_chan_neutral"
+    "osb_chan_create osb_chan_create_bl osb_chan_bl_points osb_chan_free osb_chan_tables osb_chan_eig osb_chan_neutral"
 ).split()
 
 DISC_FD, DISC_CHEB, DISC_CHEB_NUM = 0, 1, 2
@@ -347,6 +349,37 @@ class Engine:
         h = C.c_void_p()
         self._check(self.lib.osb_chan_create(self.ctx, disc, N, C.byref(h)))
         return Chan(self, h, N)
+
+    def chan_bl(self, disc, N, lmap, prof: Profile = None, U=None, merge=None) -> "Chan":
+        """Mapped boundary-layer operator (orrcolbl.f / orrfdbl.f) on y = lmap (1+eta)/(1-eta).
+        The mean flow is either a Blasius/Falkner-Skan `prof` of this engine (evaluated at the grid points
+        with the cubic spline of its tables, free stream beyond its ymax) or explicit values U[N+1]
+        with `merge` = the last index of the free stream (U[0..merge] = 1)."""
+        y = np.zeros(N + 1)
+        if self.lib.osb_chan_bl_points(disc, N, float(lmap), y.ctypes.data_as(_dp)):
+            raise ValueError("bad (disc, N, lmap)")
+        if U is None:
+            if prof is None:
+                raise ValueError("chan_bl needs a profile or U values")
+            t = prof.tables()
+            yd, Ut, Us = t["ydat"], t["U"], t["Uspl"]
+            h = yd[1] - yd[0]
+            inside = np.isfinite(y) & (y <= yd[-1])
+            merge = int(np.nonzero(~inside)[0].max()) if (~inside).any() else 0
+            yy = np.where(inside, y, yd[-1])
+            i = np.clip(((yy - yd[0]) / h).astype(np.int64), 0, yd.size - 2)
+            A = (yd[i + 1] - yy) / h
+            B = (yy - yd[i]) / h
+            U = A * Ut[i] + B * Ut[i + 1] + ((A ** 3 - A) * Us[i] + (B ** 3 - B) * Us[i + 1]) * h * h / 6.0
+            U = np.where(inside, U, 1.0)
+        U = _f64(U, N + 1)
+        if merge is None:
+            raise ValueError("merge is required with explicit U")
+        hnd = C.c_void_p()
+        self._check(self.lib.osb_chan_create_bl(self.ctx, disc, N, float(lmap), U.ctypes.data_as(_dp), int(merge), C.byref(hnd)))
+        ch = Chan(self, hnd, N)
+        ch.y, ch.U, ch.merge = y, U, int(merge)
+        return ch
 
     def measure_fp64_peak(self, ms_target=200.0):
         tf = C.c_double()

@@ -31,6 +31,7 @@ void ctx_count_launch(osb_ctx *ctx, int n);
 
 struct osb_chan {
   int disc = 0, N = 0, n = 0;
+  int bl = 0;  // mapped boundary-layer operator (osb_chan_create_bl): tables are the metric-folded D2', D4'
   std::vector<double> eta, u, d1u, d2u, D2full, D4full;  // host copies, full (N+1) grid, row-major (i,j)
   double *dD2 = nullptr, *dD4 = nullptr, *du = nullptr, *dd2u = nullptr;  // device, interior, column-major
   double2 *dBand = nullptr;  // FD only: [n][9] (D2, D4)(r, r-4+j), the band of the 9-diagonal operator
@@ -112,6 +113,42 @@ void matmul_ref(std::vector<double> &Cm, const std::vector<double> &A, const std
 
 }  // namespace
 
+// interior blocks of D2, D4 (column-major n x n), profile rows and -- for the banded FD path -- the
+// compact band table go to the device
+static int upload_tables(osb_ctx *ctx, osb_chan *c) {
+  const int N = c->N, disc = c->disc;
+  const int n = c->n;
+  std::vector<double> h2((size_t)n * n), h4((size_t)n * n), hu(n), hd(n);
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) {
+      h2[(size_t)j * n + i] = at(c->D2full, N, i + 1, j + 1);
+      h4[(size_t)j * n + i] = at(c->D4full, N, i + 1, j + 1);
+    }
+  for (int i = 0; i < n; ++i) { hu[i] = c->u[i + 1]; hd[i] = c->d2u[i + 1]; }
+  CH_CUDA(ctx, cudaSetDevice(c->device));
+  CH_CUDA(ctx, cudaMalloc(&c->dD2, h2.size() * sizeof(double)));
+  CH_CUDA(ctx, cudaMalloc(&c->dD4, h4.size() * sizeof(double)));
+  CH_CUDA(ctx, cudaMalloc(&c->du, n * sizeof(double)));
+  CH_CUDA(ctx, cudaMalloc(&c->dd2u, n * sizeof(double)));
+  CH_CUDA(ctx, cudaMemcpy(c->dD2, h2.data(), h2.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CH_CUDA(ctx, cudaMemcpy(c->dD4, h4.data(), h4.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CH_CUDA(ctx, cudaMemcpy(c->du, hu.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  CH_CUDA(ctx, cudaMemcpy(c->dd2u, hd.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  if (disc == OSB_DISC_FD) {
+    std::vector<double> hb((size_t)n * 9 * 2, 0.0);
+    for (int r = 0; r < n; ++r)
+      for (int j = 0; j < 9; ++j) {
+        const int cc = r - 4 + j;
+        if (cc < 0 || cc >= n) continue;
+        hb[((size_t)r * 9 + j) * 2] = at(c->D2full, N, r + 1, cc + 1);
+        hb[((size_t)r * 9 + j) * 2 + 1] = at(c->D4full, N, r + 1, cc + 1);
+      }
+    CH_CUDA(ctx, cudaMalloc(&c->dBand, hb.size() * sizeof(double)));
+    CH_CUDA(ctx, cudaMemcpy(c->dBand, hb.data(), hb.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return OSB_OK;
+}
+
 extern "C" {
 
 int osb_chan_create(osb_ctx *ctx, int disc, int N, osb_chan **out) {
@@ -148,36 +185,79 @@ int osb_chan_create(osb_ctx *ctx, int disc, int N, osb_chan **out) {
       c->d1u[i] = a; c->d2u[i] = b;
     }
   }
-  // interior blocks, column-major n x n
-  const int n = c->n;
-  std::vector<double> h2((size_t)n * n), h4((size_t)n * n), hu(n), hd(n);
-  for (int j = 0; j < n; ++j)
-    for (int i = 0; i < n; ++i) {
-      h2[(size_t)j * n + i] = at(c->D2full, N, i + 1, j + 1);
-      h4[(size_t)j * n + i] = at(c->D4full, N, i + 1, j + 1);
-    }
-  for (int i = 0; i < n; ++i) { hu[i] = c->u[i + 1]; hd[i] = c->d2u[i + 1]; }
-  CH_CUDA(ctx, cudaSetDevice(c->device));
-  CH_CUDA(ctx, cudaMalloc(&c->dD2, h2.size() * sizeof(double)));
-  CH_CUDA(ctx, cudaMalloc(&c->dD4, h4.size() * sizeof(double)));
-  CH_CUDA(ctx, cudaMalloc(&c->du, n * sizeof(double)));
-  CH_CUDA(ctx, cudaMalloc(&c->dd2u, n * sizeof(double)));
-  CH_CUDA(ctx, cudaMemcpy(c->dD2, h2.data(), h2.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CH_CUDA(ctx, cudaMemcpy(c->dD4, h4.data(), h4.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CH_CUDA(ctx, cudaMemcpy(c->du, hu.data(), n * sizeof(double), cudaMemcpyHostToDevice));
-  CH_CUDA(ctx, cudaMemcpy(c->dd2u, hd.data(), n * sizeof(double), cudaMemcpyHostToDevice));
-  if (disc == OSB_DISC_FD) {
-    std::vector<double> hb((size_t)n * 9 * 2, 0.0);
-    for (int r = 0; r < n; ++r)
-      for (int j = 0; j < 9; ++j) {
-        const int cc = r - 4 + j;
-        if (cc < 0 || cc >= n) continue;
-        hb[((size_t)r * 9 + j) * 2] = at(c->D2full, N, r + 1, cc + 1);
-        hb[((size_t)r * 9 + j) * 2 + 1] = at(c->D4full, N, r + 1, cc + 1);
-      }
-    CH_CUDA(ctx, cudaMalloc(&c->dBand, hb.size() * sizeof(double)));
-    CH_CUDA(ctx, cudaMemcpy(c->dBand, hb.data(), hb.size() * sizeof(double), cudaMemcpyHostToDevice));
+  int rc = upload_tables(ctx, c.get());
+  if (rc) return rc;
+  *out = c.release();
+  return OSB_OK;
+}
+
+static void bl_grid(int disc, int N, std::vector<double> &eta) {
+  eta.resize((size_t)N + 1);
+  if (disc == OSB_DISC_FD) {  // orrfdbl.f:258-265
+    const double deta = 2. / (double)N;
+    for (int i = 0; i <= N; ++i) eta[i] = 1. - (double)i * deta;
+  } else {  // orrcolbl.f:290-296
+    const double pi = acos(-1.0), dth = pi / (double)N;
+    for (int i = 0; i <= N; ++i) eta[i] = cos((double)i * dth);
   }
+}
+
+int osb_chan_bl_points(int disc, int N, double lmap, double *y) {
+  if ((disc != OSB_DISC_FD && disc != OSB_DISC_CHEB) || N < 8 || !y || !(lmap > 0.0)) return OSB_E_ARG;
+  std::vector<double> eta;
+  bl_grid(disc, N, eta);
+  y[0] = INFINITY;
+  for (int i = 1; i <= N; ++i) y[i] = lmap * (1. + eta[i]) / (1. - eta[i]);  // orrcolbl.f:391
+  return OSB_OK;
+}
+
+int osb_chan_create_bl(osb_ctx *ctx, int disc, int N, double lmap, const double *U, int merge, osb_chan **out) {
+  if (!ctx || !out || !U) return OSB_E_ARG;
+  if (disc != OSB_DISC_FD && disc != OSB_DISC_CHEB) return ctx_fail(ctx, OSB_E_ARG, "disc must be OSB_DISC_FD or OSB_DISC_CHEB");
+  if (N < 8 || N > 1024) return ctx_fail(ctx, OSB_E_ARG, "N out of range [8,1024]");
+  if (!(lmap > 0.0)) return ctx_fail(ctx, OSB_E_ARG, "lmap <= 0");
+  if (merge < 0 || merge >= N) return ctx_fail(ctx, OSB_E_ARG, "merge out of range [0,N)");
+  if (osb_device_count(ctx) != 1) return ctx_fail(ctx, OSB_E_ARG, "the matrix path takes a single-device context");
+  std::unique_ptr<osb_chan> c(new osb_chan);
+  c->disc = disc; c->N = N; c->n = N - 1; c->device = ctx_device(ctx, 0); c->bl = 1;
+  const size_t n1 = (size_t)N + 1, nn = n1 * n1;
+  bl_grid(disc, N, c->eta);
+  c->u.resize(n1); c->d1u.resize(n1); c->d2u.resize(n1);
+  std::vector<double> D1hat(nn), D1(nn), D2(nn), D3(nn), D4(nn), D2hat(nn);
+  if (disc == OSB_DISC_FD) { finite_d1(D1hat, N, c->eta); finite_d1(D1, N, c->eta); }
+  else { chebyd(D1hat, N); chebyd(D1, N); }
+  for (int i = 0; i <= N; ++i) { at(D1, N, 0, i) = 0.0; at(D1, N, N, i) = 0.0; }  // v' = 0 at both ends
+  matmul_ref(D2, D1hat, D1, N);
+  matmul_ref(D3, D1hat, D2, N);
+  matmul_ref(D4, D1hat, D3, N);
+  matmul_ref(D2hat, D1hat, D1hat, N);
+  // INIT_BL_PROFILE with the caller's profile values (orrcolbl.f:398-427)
+  for (int i = 0; i <= N; ++i) c->u[i] = (i <= merge) ? 1.0 : U[i];
+  std::vector<double> d1u(n1), d2u(n1);
+  for (int i = 0; i <= N; ++i) {
+    double a = 0.0, b = 0.0;
+    for (int k = 0; k <= N; ++k) { a = a + at(D1hat, N, i, k) * c->u[k]; b = b + at(D2hat, N, i, k) * c->u[k]; }
+    d1u[i] = a; d2u[i] = b;
+  }
+  for (int j = merge - 2; j >= 0; --j) { d1u[j] = 0.0; d2u[j] = 0.0; }
+  // MAKE_BL_METRICS (orrcolbl.f:300-306) folded into the tables: the rows of the derivative matrices are
+  // scaled once here instead of once per alpha in MAKE_MATRIX (orrcolbl.f:495-560)
+  c->D2full.assign(nn, 0.0); c->D4full.assign(nn, 0.0);
+  for (int i = 0; i <= N; ++i) {
+    const double e1 = c->eta[i] - 1.;
+    const double m1 = (e1 * e1) / (2. * lmap), m2 = (e1 * e1 * e1) / (2. * (lmap * lmap));
+    const double m3 = 3. * (e1 * e1 * e1 * e1) / (4. * (lmap * lmap * lmap));
+    const double m4 = 3. * (e1 * e1 * e1 * e1 * e1) / (2. * (lmap * lmap * lmap * lmap));
+    const double g4 = m1 * m1 * m1 * m1, g3 = 6. * (m1 * m1) * m2, g2 = 3. * (m2 * m2) + 4. * m1 * m3, m1s = m1 * m1;
+    for (int j = 0; j <= N; ++j) {
+      at(c->D2full, N, i, j) = m1s * at(D2, N, i, j) + m2 * at(D1, N, i, j);
+      at(c->D4full, N, i, j) = g4 * at(D4, N, i, j) + g3 * at(D3, N, i, j) + g2 * at(D2, N, i, j) + m4 * at(D1, N, i, j);
+    }
+    c->d1u[i] = d1u[i];
+    c->d2u[i] = d2u[i] * m1s + d1u[i] * m2;  // the U'' of the mapped operator (orrcolbl.f:529-530)
+  }
+  int rc = upload_tables(ctx, c.get());
+  if (rc) return rc;
   *out = c.release();
   return OSB_OK;
 }
@@ -257,9 +337,10 @@ static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::ve
 // inverse iteration to its nearest eigenvalue; the settled candidate that the
 // reference's rule would keep is the result.  16 shifts cover 0 < c_r < 1; the FD rule
 // adds 32 shifts over -4 < w_r < 0, the |w_r| < 1 rule adds 8 over -1 < w_r < 0.
-static std::vector<double> scan_list(int disc, double alpha_r) {
+static std::vector<double> scan_list(int disc, double alpha_r, int bl = 0) {
   std::vector<double> s;
   for (int k = 0; k < 16; ++k) s.push_back(alpha_r * ((k + 0.5) / 16.0));
+  if (bl) return s;  // boundary layer: discrete modes and the continuous branch all have 0 < c_r <= 1
   if (disc == OSB_DISC_FD) for (int k = 0; k < 32; ++k) s.push_back(-(k + 0.5) * 0.125);
   else for (int k = 0; k < 8; ++k) s.push_back(-(k + 0.5) * 0.125);
   return s;
@@ -267,12 +348,12 @@ static std::vector<double> scan_list(int disc, double alpha_r) {
 
 static int scan_shifts(osb_ctx *ctx, const osb_chan *c, int64_t npts, const double *alpha, const double *Re,
                        std::vector<double> &sigma_out, std::vector<int32_t> &ok) {
-  const int ns = (int)scan_list(c->disc, 1.0).size();
+  const int ns = (int)scan_list(c->disc, 1.0, c->bl).size();
   const int64_t ninst = npts * ns;
   std::vector<double> a(2 * ninst), r(ninst), s(2 * ninst), om, dl;
   std::vector<int32_t> it;
   for (int64_t p = 0; p < npts; ++p) {
-    const std::vector<double> sh = scan_list(c->disc, alpha[2 * p]);
+    const std::vector<double> sh = scan_list(c->disc, alpha[2 * p], c->bl);
     for (int k = 0; k < ns; ++k) {
       const int64_t e = p * ns + k;
       a[2 * e] = alpha[2 * p]; a[2 * e + 1] = alpha[2 * p + 1];
@@ -292,8 +373,8 @@ static int scan_shifts(osb_ctx *ctx, const osb_chan *c, int64_t npts, const doub
       const double wr = om[2 * e], wi = om[2 * e + 1];
       if (!(std::isfinite(wr) && std::isfinite(wi))) continue;
       if (!(dl[e] <= 1.0e-8 * hypot(wr, wi))) continue;  // not settled on one mode
-      if (c->disc == OSB_DISC_FD) {
-        if (!(fabs(wi) < 10.0) || (int)wr == 999) continue;  // orrfdchan.f:818-819
+      if (c->disc == OSB_DISC_FD || c->bl) {
+        if (!(fabs(wi) < 10.0) || (int)wr == 999) continue;  // orrfdchan.f:818-819 (orrcolbl.f:771-779: no filter)
       } else {
         if (!(fabs(wr) < 1.0)) continue;                      // orrncbl.f:898
       }

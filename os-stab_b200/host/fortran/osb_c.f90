@@ -139,6 +139,22 @@ module osb_c
       integer(c_int), value :: disc, N          ! disc: 0 FD, 1 Chebyshev, 2 Chebyshev + numerical U''
       type(c_ptr), intent(out) :: chan
     end function
+    !> mapped boundary-layer operator of orrcolbl.f / orrfdbl.f (MAKE_DERIVATIVES, MAKE_BL_METRICS, MAKE_MATRIX);
+    !> U(0:N) at the grid points replaces the external profile file of INIT_BL_PROFILE
+    integer(c_int) function osb_chan_create_bl(ctx, disc, N, lmap, U, merge, chan) bind(C, name="osb_chan_create_bl")
+      import :: c_int, c_ptr, c_double
+      type(c_ptr), value :: ctx
+      integer(c_int), value :: disc, N, merge
+      real(c_double), value :: lmap
+      real(c_double), intent(in) :: U(0:*)
+      type(c_ptr), intent(out) :: chan
+    end function
+    integer(c_int) function osb_chan_bl_points(disc, N, lmap, y) bind(C, name="osb_chan_bl_points")
+      import :: c_int, c_double
+      integer(c_int), value :: disc, N
+      real(c_double), value :: lmap
+      real(c_double), intent(out) :: y(0:*)
+    end function
     integer(c_int) function osb_chan_free(ctx, chan) bind(C, name="osb_chan_free")
       import :: c_int, c_ptr
       type(c_ptr), value :: ctx, chan

@@ -153,7 +153,7 @@ def _find_openblas():
 class ChanOracle:
     """orrfdchan / orrcolchan / orrncbl restatement (oracle/os_chan_oracle.c)."""
 
-    def __init__(self, lib, disc, n):
+    def __init__(self, lib, disc, n, bl=None):
         self.lib = lib
         self.n = n
         i, d = C.c_int, C.c_double
@@ -168,7 +168,13 @@ class ChanOracle:
         lib.osr_chan_neutral.argtypes = [C.c_void_p, d, d, d, d, i, _dp]
         if lib.osr_lapack_open(_find_openblas().encode()) != 0:
             raise RuntimeError("cannot open LAPACK")
-        self.h = lib.osr_chan_create(disc, n)
+        if bl is None:
+            self.h = lib.osr_chan_create(disc, n)
+        else:  # mapped boundary layer: bl = (lmap, U[N+1], merge)
+            lib.osr_chan_create_bl.restype = C.c_void_p
+            lib.osr_chan_create_bl.argtypes = [i, i, d, _dp, i]
+            U = np.ascontiguousarray(bl[1], dtype=np.float64)
+            self.h = lib.osr_chan_create_bl(disc, n, float(bl[0]), U.ctypes.data_as(_dp), int(bl[2]))
 
     def close(self):
         if self.h:
@@ -226,7 +232,7 @@ class ChanOracle:
         return tr.reshape(maxit, 7)[:it]
 
 
-def chan(disc, n, rebuild=False):
+def chan(disc, n, rebuild=False, bl=None):
     if rebuild or not LIB.exists():
         build()
-    return ChanOracle(C.CDLL(str(LIB)), disc, n)
+    return ChanOracle(C.CDLL(str(LIB)), disc, n, bl=bl)

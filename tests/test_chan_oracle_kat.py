@@ -51,3 +51,37 @@ def test_neutral_point_nc_inp(oracle):
     assert abs(tr[-1, 1] - 0.2698801) < 2e-6 and abs(tr[-1, 2]) < 1e-8
     # the coded dw/da (left vector of inv(B)A, oracle D-7) is ~250x smaller than the true one
     assert abs(complex(tr[0, 3], tr[0, 4])) < 0.01
+
+
+def test_mapped_bl_operator_reproduces_the_shooting_eigenvalue():
+    """orrcolbl.f restated (mapped semi-infinite domain, metrics m1..m4) with the Blasius profile of the
+    shooting oracle as the mean flow: the most unstable mode of the Chebyshev operator is the
+    Tollmien-Schlichting mode of README.md:24-26, c = 0.36412287 + 0.0079597206i."""
+    import math
+
+    S2 = math.sqrt(2.0)
+    o = ob.load()
+    prof, _, _ = o.solve_bl(ob.FLOW_CONTEBL, ob.INT_CK45, 2000, 0.0, 20.0, 0.5, 0.0)
+    yd, U, Us = prof[0][:2001], prof[1][:2001], prof[2][:2001]
+    N, lmap = 64, 8.0
+    eta = np.cos(np.arange(N + 1) * math.pi / N)
+    with np.errstate(divide="ignore"):
+        y = lmap * (1 + eta) / (1 - eta)
+    inside = np.isfinite(y) & (y <= yd[-1])
+    merge = int(np.nonzero(~inside)[0].max())
+    yy = np.where(inside, y, yd[-1])
+    h = yd[1] - yd[0]
+    i = np.clip((yy / h).astype(int), 0, yd.size - 2)
+    A, B = (yd[i + 1] - yy) / h, (yy - yd[i]) / h
+    Ug = np.where(inside, A * U[i] + B * U[i + 1] + ((A ** 3 - A) * Us[i] + (B ** 3 - B) * Us[i + 1]) * h * h / 6, 1.0)
+    c = ob.chan(ob.DISC_CHEB, N, bl=(lmap, Ug, merge))
+    al, Re = 0.179 * S2, 580.0 * S2
+    r = c.solve_fd(al, Re, want_spectrum=True)
+    c.close()
+    cph = r["omega"] / al
+    assert abs(cph - complex(0.36412287, 0.0079597206)) < 5e-8
+    # the rest of the spectrum is stable; the continuous branch sits at c -> 1 - 0.000309i
+    spec = r["spectrum"] / al
+    assert (spec.imag < cph.imag + 1e-12).all()
+    branch = spec[np.abs(spec.real - 1.0) < 1e-3]
+    assert branch.size > 5 and np.abs(branch.imag + 0.000309).min() < 2e-6

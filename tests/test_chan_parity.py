@@ -165,3 +165,41 @@ def test_banded_warp_kernel_matches_thread_kernel(engine, N, monkeypatch):
     assert np.max(np.abs(a["evec"] - b["evec"])[phys]) < 1e-8
     # the scan picks the same mode through either kernel (spurious FD modes: ill-conditioned, 1e-9)
     assert rel(first["omega"], second["omega"]).max() < (1e-9 if N <= 128 else 1e-6)
+
+
+@pytest.mark.parametrize("disc,N,lmap", [(ob.DISC_CHEB, 64, 8.0), (ob.DISC_CHEB, 96, 4.0), (ob.DISC_FD, 128, 2.0)])
+def test_mapped_boundary_layer_operator(engine, osb, oracle, disc, N, lmap):
+    """orrcolbl / orrfdbl operator with this engine's Blasius profile as the mean flow,
+    against the oracle's restatement (same grid, metrics, MAKE_MATRIX; ZGEEV on inv(B)A, most unstable mode)
+    -- and, for collocation, against the shooting eigenvalue of the same flow (the two paths tie together)."""
+    import math
+
+    S2 = math.sqrt(2.0)
+    prof = engine.solve_bl(osb.FLOW_CONTEBL, osb.INT_CK45, 2000, 0.0, 20.0, 0.5, 0.0)
+    ch = engine.chan_bl(disc, N, lmap, prof=prof)
+    alpha = np.array([0.16, 0.179, 0.2, 0.179 + 0.002j]) * S2
+    Re = 580.0 * S2
+    r = ch.solve(alpha, Re, want_evec=True)
+    oc = ob.chan(disc, N, bl=(lmap, ch.U, ch.merge))
+    ref = [oc.solve_fd(a, Re, want_evec=True) for a in alpha]
+    # the host tables fold the metrics into D2', D4': compare them with the oracle's unfolded ones
+    t = ch.tables()
+    oD2 = oc.table(4)
+    assert np.array_equal(t["eta"], oc.table(0)) and np.array_equal(t["u"], oc.table(1))
+    oc.close()
+    ch.free()
+    assert (r["status"] == 0).all()
+    w_ref = np.array([x["omega"] for x in ref])
+    # parity with the LAPACK route on this ill-scaled mapped operator: 1e-9 (collocation), 1e-10 (FD)
+    e = rel(r["omega"], w_ref)
+    assert e.max() < (2e-9 if disc == ob.DISC_CHEB else 1e-10), e
+    v = r["evec"][1]
+    assert np.max(np.abs(v - ref[1]["evec"])) < 1e-6
+    if disc == ob.DISC_CHEB:
+        sh = engine.shoot_temporal(osb.shoot_defaults(osb.FLOW_CONTEBL),
+                                   engine.solve_bl(osb.FLOW_CONTEBL, osb.INT_CK45, 1000, 0.0, 17.0, 0.5, 0.0),
+                                   alpha[:3].real, np.full(3, Re), r["omega"][:3] / alpha[:3])
+        assert (sh["status"] == 0).all()
+        assert np.abs(r["omega"][:3] / alpha[:3] - sh["c"]).max() < 2e-7
+    prof.free()
+    assert oD2.shape == (N + 1, N + 1)
