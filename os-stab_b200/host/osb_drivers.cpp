@@ -1,6 +1,6 @@
 // osb_drivers.cpp -- C++ twin drivers of the reference's programs over the C ABI.
 //
-//   osb_drivers contebl | conte | orrsom | orrspace | orrfdchan | orrcolchan | orrncbl | conteucbl
+//   osb_drivers contebl | conte | orrsom | orrspace | orrfdchan | orrcolchan | orrncbl | conteucbl | orrfdbl | orrcolbl
 //
 // Each twin reads the same stdin (prompts, "key = value" decks, list-directed numbers),
 // echoes the same text and writes the same fort.N / <root>.g/.dat/.q files as the
@@ -697,6 +697,128 @@ static int run_orrfdchan(osb_ctx *ctx) {
   return bad;
 }
 
+// ---------------------------------------------------------------- orrfdbl / orrcolbl
+// Fortran sequential unformatted record (gfortran: 4-byte length before and after the payload)
+static void f_record(FILE *f, const void *data, size_t bytes) {
+  const int32_t len = (int32_t)bytes;
+  fwrite(&len, 4, 1, f);
+  fwrite(data, 1, bytes, f);
+  fwrite(&len, 4, 1, f);
+}
+
+// orrfdbl.f:58-141 / orrcolbl.f:60-157.  The reference programs read the mean profile from a file they do
+// not ship (INIT_BL_PROFILE, orrcolbl.f:366-388) and link against IMSL; the twin keeps their prompts and
+// files and takes the Blasius profile of this engine's SOLVE_BL kernel as the mean flow.  orrcolbl's
+// dw/dalpha column (adjoint formula, orrcolbl.f:815-824) is a central difference of two extra batched solves.
+static int run_orrbl(osb_ctx *ctx, bool colloc) {
+  int n, ians;
+  double Re, lmap, minar, maxar, incar, minai, maxai, incai;
+  std::string filename, profname;
+  printf("\n\n          Solve Orr-Sommerfeld (%s)\n", colloc ? "Collocation" : "Finite-difference");
+  printf("\n Enter the number of %s ==> ", colloc ? "modes" : "mesh points"); std::cin >> n;
+  printf("\n Enter Reynolds number ==> "); std::cin >> Re;
+  printf("\n Enter mapping metric ==> "); std::cin >> lmap;
+  printf("\n Enter alpha_r (min,max,inc) ==> "); std::cin >> minar >> maxar >> incar;
+  printf("\n Enter alpha_i (min,max,inc) ==> "); std::cin >> minai >> maxai >> incai;
+  printf("\n Enter root filename ==> "); std::cin >> filename;
+  printf("\n Print eigenvectors (1,0) ==> "); std::cin >> ians;
+  const int nar = (int)std::trunc((maxar - minar) / incar) + 1, nai = (int)std::trunc((maxai - minai) / incai) + 1;
+  printf("\n  nar = %s  nai = %s\n", I(nar, 5).c_str(), I(nai, 5).c_str());
+  if (nar > 100 || nai > 100 || nar < 1 || nai < 1) { fprintf(stderr, "sweep exceeds the reference's 100x100 arrays\n"); return 1; }
+  if (n < 8 || n > (colloc ? 256 : 512)) { fprintf(stderr, "n exceeds the reference's idim\n"); return 1; }
+  std::vector<double> alphar(nar), alphai(nai);
+  for (int i = 1; i <= nar; ++i) alphar[i - 1] = minar + (i - 1.) * incar;
+  for (int i = 1; i <= nai; ++i) alphai[i - 1] = minai + (i - 1.) * incai;
+  const int64_t npts = (int64_t)nar * nai;
+  const int64_t nxy[2] = {nar, nai};  // -fdefault-integer-8 (gcc.mak:79)
+  {
+    FILE *g = fopen((filename + ".g").c_str(), "wb");
+    f_record(g, nxy, sizeof(nxy));
+    std::vector<double> v;
+    for (int j = 0; j < nai; ++j) for (int i = 0; i < nar; ++i) v.push_back(alphar[i]);
+    for (int j = 0; j < nai; ++j) for (int i = 0; i < nar; ++i) v.push_back(alphai[j]);
+    f_record(g, v.data(), v.size() * sizeof(double));
+    fclose(g);
+  }
+  // INIT_BL_PROFILE: prompt kept; the name is read and ignored (see above)
+  printf("\n Read Mean Profile\n\n Enter filename ==> ");
+  std::cin >> profname;
+  const int disc = colloc ? OSB_DISC_CHEB : OSB_DISC_FD;
+  const int nbl = 2000;
+  const double ymax = 20.0;
+  osb_profile *prof = nullptr;
+  CK(ctx, osb_profile_blasius(ctx, OSB_FLOW_CONTEBL, OSB_INT_CK45, nbl, 0.0, ymax, 0.5, 0.0, &prof));
+  std::vector<double> yd(nbl + 1), Ut(nbl + 1), Us(nbl + 1), y(n + 1), U(n + 1, 1.0);
+  int32_t npass = 0;
+  double f2p = 0.0;
+  CK(ctx, osb_profile_get(ctx, prof, yd.data(), Ut.data(), Us.data(), nullptr, nullptr, &npass, &f2p));
+  osb_profile_free(ctx, prof);
+  if (osb_chan_bl_points(disc, n, lmap, y.data())) { fprintf(stderr, "bad grid parameters\n"); return 1; }
+  int merge = 0;
+  const double h = yd[1] - yd[0];
+  for (int i = n; i >= 0; --i) {  // from the wall outwards, as orrcolbl.f:390-403
+    if (!(y[i] <= ymax)) { merge = i; break; }
+    int k = std::min(std::max((int)(y[i] / h), 0), nbl - 1);
+    const double A = (yd[k + 1] - y[i]) / h, B = (y[i] - yd[k]) / h;  // SPEVAL, shoot.f:996-1013
+    U[i] = A * Ut[k] + B * Ut[k + 1] + ((A * A * A - A) * Us[k] + (B * B * B - B) * Us[k + 1]) * (h * h) / 6.0;
+  }
+  printf("\n Merging at i = %s\n", I(merge, 4).c_str());
+  osb_chan *chan = nullptr;
+  CK(ctx, osb_chan_create_bl(ctx, disc, n, lmap, U.data(), merge, &chan));
+  if (colloc) printf("\n");
+  std::vector<double> al(2 * npts), om(2 * npts);
+  std::vector<int32_t> it(npts), st(npts);
+  for (int j = 0; j < nai; ++j) for (int i = 0; i < nar; ++i) { al[2 * (j * nar + i)] = alphar[i]; al[2 * (j * nar + i) + 1] = alphai[j]; }
+  CK(ctx, osb_chan_eig(ctx, chan, Re, npts, al.data(), nullptr, om.data(), nullptr, it.data(), st.data()));
+  std::vector<double> dw(2 * npts, 0.0);
+  if (colloc) {
+    std::vector<double> a2(4 * npts), s2(4 * npts), o2(4 * npts);
+    std::vector<int32_t> i2(2 * npts), t2(2 * npts);
+    std::vector<double> hh(npts);
+    for (int64_t p = 0; p < npts; ++p) {
+      hh[p] = 1.0e-6 * std::max(std::hypot(al[2 * p], al[2 * p + 1]), 1.0e-3);
+      for (int sgn = 0; sgn < 2; ++sgn) {
+        const int64_t e = 2 * p + sgn;
+        a2[2 * e] = al[2 * p] + (sgn ? hh[p] : -hh[p]); a2[2 * e + 1] = al[2 * p + 1];
+        s2[2 * e] = om[2 * p]; s2[2 * e + 1] = om[2 * p + 1];
+      }
+    }
+    CK(ctx, osb_chan_eig(ctx, chan, Re, 2 * npts, a2.data(), s2.data(), o2.data(), nullptr, i2.data(), t2.data()));
+    for (int64_t p = 0; p < npts; ++p) {
+      dw[2 * p] = (o2[2 * (2 * p + 1)] - o2[2 * (2 * p)]) / (2.0 * hh[p]);
+      dw[2 * p + 1] = (o2[2 * (2 * p + 1) + 1] - o2[2 * (2 * p) + 1]) / (2.0 * hh[p]);
+    }
+  }
+  FILE *dat = fopen((filename + ".dat").c_str(), "w");
+  int bad = 0;
+  for (int64_t p = 0; p < npts; ++p) {
+    std::string row = " ";
+    const char *sep = colloc ? " " : "    ";  // format 60: 6(e17.10,1x) / 4(e17.10,4x)
+    row += E(al[2 * p], 17, 10) + sep + E(al[2 * p + 1], 17, 10) + sep + E(om[2 * p], 17, 10) + sep + E(om[2 * p + 1], 17, 10) + sep;
+    if (colloc) row += E(dw[2 * p], 17, 10) + sep + E(dw[2 * p + 1], 17, 10) + sep;
+    fprintf(dat, "%s\n", row.c_str());
+    printf("%s\n", row.c_str());
+    bad |= st[p];
+  }
+  fclose(dat);
+  {
+    FILE *q = fopen((filename + ".q").c_str(), "wb");
+    f_record(q, nxy, sizeof(nxy));
+    const double z4[4] = {0.0, 0.0, 0.0, 0.0};
+    f_record(q, z4, sizeof(z4));
+    std::vector<double> v;
+    for (int64_t p = 0; p < npts; ++p) v.push_back(1.0);
+    for (int64_t p = 0; p < npts; ++p) v.push_back(om[2 * p]);
+    for (int64_t p = 0; p < npts; ++p) v.push_back(om[2 * p + 1]);
+    for (int64_t p = 0; p < npts; ++p) v.push_back(1.0);
+    f_record(q, v.data(), v.size() * sizeof(double));
+    fclose(q);
+  }
+  if (ians == 1) fprintf(stderr, "note: the eigenvector listing of SOLVE's print branch is not reproduced by this twin\n");
+  osb_chan_free(ctx, chan);
+  return bad;
+}
+
 // ---------------------------------------------------------------- orrcolchan
 static int run_orrcolchan(osb_ctx *ctx) {
   int n;
@@ -791,7 +913,7 @@ static int selftest_deck(const char *path) {
 
 int main(int argc, char **argv) {
   if (argc < 2) {
-    fprintf(stderr, "usage: osb_drivers contebl|conte|orrsom|orrspace|orrfdchan|orrcolchan|orrncbl|conteucbl  (input on stdin)\n");
+    fprintf(stderr, "usage: osb_drivers contebl|conte|orrsom|orrspace|orrfdchan|orrcolchan|orrncbl|conteucbl|orrfdbl|orrcolbl  (input on stdin)\n");
     return 64;
   }
   const std::string prog = argv[1];
@@ -819,6 +941,8 @@ int main(int argc, char **argv) {
   else if (prog == "orrfdchan") st = run_orrfdchan(ctx);
   else if (prog == "orrcolchan") st = run_orrcolchan(ctx);
   else if (prog == "orrncbl") st = run_orrncbl(ctx);
+  else if (prog == "orrfdbl") st = run_orrbl(ctx, false);
+  else if (prog == "orrcolbl") st = run_orrbl(ctx, true);
   else { fprintf(stderr, "unknown program %s\n", prog.c_str()); st = 64; }
   osb_destroy(ctx);
   return st == 0 ? 0 : 1;

@@ -301,3 +301,41 @@ def test_orrfdchan_fdchan_deck_prints_eigenvector(tmp_path):
     assert np.max(np.abs(v - ref["evec"])) < 1e-7
     f20 = np.loadtxt(tmp_path / "fort.20").reshape(-1, 2)
     assert abs(f20[0, 0] + 1j * f20[0, 1] - ref["omega"] / 1.0) < 1e-9
+
+
+@pytest.mark.gpu
+def test_orrcolbl_and_orrfdbl_twins(tmp_path):
+    """orrcolbl / orrfdbl: same prompts and files; the Blasius profile comes from this engine
+    instead of the reference's missing profile file.  Collocation at N=64, Lmap=8 must reproduce the
+    Tollmien-Schlichting eigenvalue of README.md:24-26 (alpha = 0.179 sqrt 2, Re = 580 sqrt 2)."""
+    import math
+    import struct
+
+    S2 = math.sqrt(2.0)
+    a0 = 0.179 * S2
+    deck = f"64\n{580.0 * S2!r}\n8.0\n{a0 - 0.002!r} {a0 + 0.0021!r} 0.002\n0 0 1\nbl\n0\nblasius\n"
+    r = run("orrcolbl", deck, tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert "Solve Orr-Sommerfeld (Collocation)" in r.stdout and "Enter mapping metric ==>" in r.stdout
+    assert "Read Mean Profile" in r.stdout and " Merging at i =   22" in r.stdout
+    dat = np.loadtxt(tmp_path / "bl.dat")
+    assert dat.shape == (3, 6)
+    c = (dat[1, 2] + 1j * dat[1, 3]) / dat[1, 0]
+    assert abs(c - complex(0.36412287, 0.0079597206)) < 5e-8
+    # dw/dalpha (central difference of two extra solves) against the slope across the rows
+    w = dat[:, 2] + 1j * dat[:, 3]
+    slope = (w[2] - w[0]) / (dat[2, 0] - dat[0, 0])
+    dwda = dat[1, 4] + 1j * dat[1, 5]
+    assert abs(dwda - slope) < 2e-4 and 0.3 < dwda.real < 0.5      # group velocity of the TS wave
+    # unformatted .g: record (nx, ny) as 8-byte integers, then 2 nx ny reals
+    g = (tmp_path / "bl.g").read_bytes()
+    assert struct.unpack("<i2qi", g[:24]) == (16, 3, 1, 16)
+    assert struct.unpack("<i", g[24:28])[0] == 2 * 3 * 8
+    q = (tmp_path / "bl.q").read_bytes()
+    assert len(q) == (4 + 16 + 4) + (4 + 32 + 4) + (4 + 4 * 3 * 8 + 4)
+    r = run("orrfdbl", f"128\n{580.0 * S2!r}\n2.0\n{a0!r} {a0!r} 1\n0 0 1\nfdbl\n0\nblasius\n", tmp_path)
+    assert r.returncode == 0, r.stderr
+    assert "Solve Orr-Sommerfeld (Finite-difference)" in r.stdout
+    d2 = np.loadtxt(tmp_path / "fdbl.dat").reshape(-1, 4)
+    c2 = (d2[0, 2] + 1j * d2[0, 3]) / d2[0, 0]
+    assert abs(c2 - complex(0.36412287, 0.0079597206)) < 3e-3      # second-order differences on 128 points
