@@ -714,26 +714,17 @@ int osb_shoot_neutral(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profil
   return OSB_OK;
 }
 
-int osb_eigfun(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof, int64_t npts,
-               const double *alpha, const double *Re, const double *eig, const double *omega,
-               double *y, double *vmax, int32_t *qend) {
-  if (!ctx || npts < 0 || !Re || !eig || !y || !vmax) return fail(ctx, OSB_E_ARG, "null argument");
-  ShootArgs a;
-  int analytic = 0;
-  int rc = fill_args(ctx, opts, &a, &analytic);
-  if (rc) return rc;
-  rc = check_profile(ctx, opts, prof);
-  if (rc) return rc;
-  if (a.spatial ? !omega : !alpha) return fail(ctx, OSB_E_ARG, "alpha (temporal) / omega (spatial) required");
-  if (npts == 0) return OSB_OK;
-  OSB_CUDA(ctx, cudaSetDevice(ctx->devices[0]));
+// one chunk of osb_eigfun: all scratch of the chunk lives in `scr`
+static int eigfun_chunk(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof, const ShootArgs &base,
+                        int analytic, int64_t npts, const double *alpha_or_omega, const double *Re,
+                        const double *eig, double *y, double *vmax, int32_t *qend) {
   cudaStream_t st = ctx->streams[0];
   const size_t n1 = (size_t)opts->nstep + 1;
   Scratch scr(ctx->devices[0], st);
   double *d_in = nullptr, *d_tq = nullptr;
   double2 *d_U = nullptr, *d_P = nullptr, *d_y = nullptr, *d_vmax = nullptr, *tab = nullptr;
   int32_t *d_q = nullptr;
-  OSB_CUDA(ctx, scr.alloc(&d_in, npts * 5 * sizeof(double)));  // Re, eig(2), alpha|omega(2)
+  OSB_CUDA(ctx, scr.alloc(&d_in, npts * 5 * sizeof(double)));  // eig(2), alpha|omega(2), Re
   OSB_CUDA(ctx, scr.alloc(&d_U, npts * n1 * 8 * sizeof(double2)));
   OSB_CUDA(ctx, scr.alloc(&d_P, npts * n1 * 4 * sizeof(double2)));
   OSB_CUDA(ctx, scr.alloc(&d_tq, npts * n1 * sizeof(double)));
@@ -742,10 +733,11 @@ int osb_eigfun(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof
   OSB_CUDA(ctx, scr.alloc(&d_q, npts * sizeof(int32_t)));
   // layout: eig(2n), alpha|omega(2n), Re(n)  -- the double2 arrays first (16-byte alignment)
   OSB_CUDA(ctx, cudaMemcpyAsync(d_in, eig, npts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-  OSB_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * npts, a.spatial ? omega : alpha, npts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * npts, alpha_or_omega, npts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   OSB_CUDA(ctx, cudaMemcpyAsync(d_in + 4 * npts, Re, npts * sizeof(double), cudaMemcpyHostToDevice, st));
-  rc = make_stage_table(ctx, 0, scr, opts, prof, &tab);
+  int rc = make_stage_table(ctx, 0, scr, opts, prof, &tab);
   if (rc) return rc;
+  ShootArgs a = base;
   EigfunArgs e;
   memset(&e, 0, sizeof(e));
   a.tab = tab;
@@ -763,6 +755,35 @@ int osb_eigfun(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof
   OSB_CUDA(ctx, cudaMemcpyAsync(vmax, d_vmax, npts * sizeof(double2), cudaMemcpyDeviceToHost, st));
   if (qend) OSB_CUDA(ctx, cudaMemcpyAsync(qend, d_q, npts * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   OSB_CUDA(ctx, cudaStreamSynchronize(st));
+  return OSB_OK;
+}
+
+int osb_eigfun(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof, int64_t npts,
+               const double *alpha, const double *Re, const double *eig, const double *omega,
+               double *y, double *vmax, int32_t *qend) {
+  if (!ctx || npts < 0 || !Re || !eig || !y || !vmax) return fail(ctx, OSB_E_ARG, "null argument");
+  ShootArgs a;
+  int analytic = 0;
+  int rc = fill_args(ctx, opts, &a, &analytic);
+  if (rc) return rc;
+  rc = check_profile(ctx, opts, prof);
+  if (rc) return rc;
+  if (a.spatial ? !omega : !alpha) return fail(ctx, OSB_E_ARG, "alpha (temporal) / omega (spatial) required");
+  if (npts == 0) return OSB_OK;
+  OSB_CUDA(ctx, cudaSetDevice(ctx->devices[0]));
+  // the second pass keeps the whole orthonormalised trajectory (shoot.f:762-810): 272 bytes per step per
+  // point of device scratch.  Bound it to ~8 GB per chunk so that any npts fits the GPU.
+  const size_t n1 = (size_t)opts->nstep + 1;
+  const size_t per_point = n1 * (8 + 4 + 4) * sizeof(double2) + n1 * sizeof(double) + 64;
+  int64_t chunk = std::max<int64_t>(1, (int64_t)((8ull << 30) / per_point));
+  if (const char *e = getenv("OSB_EIGFUN_CHUNK")) chunk = std::max<int64_t>(1, atoll(e));  // test hook
+  const double *ao = a.spatial ? omega : alpha;
+  for (int64_t lo = 0; lo < npts; lo += chunk) {
+    const int64_t m = std::min(chunk, npts - lo);
+    rc = eigfun_chunk(ctx, opts, prof, a, analytic, m, ao + 2 * lo, Re + lo, eig + 2 * lo, y + (size_t)lo * n1 * 8,
+                      vmax + 2 * lo, qend ? qend + lo : nullptr);
+    if (rc) return rc;
+  }
   return OSB_OK;
 }
 

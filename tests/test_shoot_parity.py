@@ -236,6 +236,24 @@ def test_eigenfunction_contebl(engine, osb, oracle, bl, bl_oracle):
         assert np.max(np.abs(y[:, i] - yr[:, i])) / scale < EIGFUN_TOL
 
 
+def test_eigenfunction_batches_are_chunked(engine, osb, bl, monkeypatch):
+    """The second pass keeps 272 B per step per point of scratch; osb_eigfun walks large batches in
+    chunks (8 GB by default).  Chunked and unchunked results must be identical."""
+    n = 10
+    alpha = (0.179 + 0.001 * np.arange(n)) * S2
+    Re = np.full(n, 580.0 * S2)
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    r = engine.shoot_temporal(opts, bl, alpha, Re, np.full(n, complex(0.36412287, 0.0079597206)))
+    assert (r["status"] == 0).all()
+    whole = engine.eigfun(opts, bl, Re, r["c"], alpha=alpha)
+    monkeypatch.setenv("OSB_EIGFUN_CHUNK", "3")
+    parts = engine.eigfun(opts, bl, Re, r["c"], alpha=alpha)
+    monkeypatch.delenv("OSB_EIGFUN_CHUNK")
+    for k in ("y", "vmax", "qend"):
+        assert np.array_equal(whole[k], parts[k]), k
+    assert np.abs(whole["y"]).max() > 0
+
+
 def test_eigenfunction_conte(engine, osb, oracle):
     prof = engine.channel_profile()
     opts = osb.shoot_defaults(osb.FLOW_CONTE)
