@@ -133,6 +133,14 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------- CPU arm
+def host_cores():
+    """Host threads this process may run on (affinity-aware; falls back to the CPU count)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return os.cpu_count() or 1
+
+
 def _cpu_worker(args):
     sys.path.insert(0, str(ROOT / "tests"))
     import oracle_binding as ob
@@ -175,7 +183,7 @@ def run_reference(args, rank, world):
     the Fortran cannot be compiled in this image) on all host cores."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = host_cores()
     sample = args.points or 256 * cores
     vals, ms = [], []
     conv = passes = n = 0
@@ -354,7 +362,7 @@ def main():
     # ---- CPU baseline (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cores = os.cpu_count() or 1
+        cores = host_cores()
         v, conv, cpasses, dt, ns = cpu_run(256 * cores, cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{ns} points spread evenly over the same 4096x4096 batch, same seeds, one process per core; "
