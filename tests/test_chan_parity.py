@@ -203,3 +203,24 @@ def test_mapped_boundary_layer_operator(engine, osb, oracle, disc, N, lmap):
         assert np.abs(r["omega"][:3] / alpha[:3] - sh["c"]).max() < 2e-7
     prof.free()
     assert oD2.shape == (N + 1, N + 1)
+
+
+def test_banded_kernels_large_batch(engine, monkeypatch):
+    """More than 3552 instances select the <16-row chunk, 3 CTAs/SM> build of the nine-lane kernel; it must
+    agree with the one-thread kernel exactly like the low-latency build does (ragged tail included)."""
+    n = 4001
+    alpha = np.linspace(0.76, 1.16, n)
+    ch = engine.chan(ob.DISC_FD, 64)
+    coarse = ch.solve(np.linspace(0.76, 1.16, 9), 1.0e4)
+    good = coarse["omega"].real > 0
+    xs = np.linspace(0.76, 1.16, 9)[good]
+    sig = np.interp(alpha, xs, coarse["omega"].real[good]) + 1j * np.interp(alpha, xs, coarse["omega"].imag[good])
+    monkeypatch.delenv("OSB_FD_THREAD", raising=False)
+    a = ch.solve(alpha, 1.0e4, sigma0=sig)
+    monkeypatch.setenv("OSB_FD_THREAD", "1")
+    b = ch.solve(alpha, 1.0e4, sigma0=sig)
+    monkeypatch.delenv("OSB_FD_THREAD")
+    ch.free()
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    assert rel(a["omega"], b["omega"]).max() < 1e-12
+    assert np.abs(a["iters"].astype(int) - b["iters"].astype(int)).max() <= 1
