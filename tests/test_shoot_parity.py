@@ -596,3 +596,43 @@ def test_neutral_curve_by_secant_on_alpha(engine, osb, oracle, bl, bl_oracle):
     assert (r2["status"] == 0).all()
     # |d Im c / d alpha| ~ 0.05..0.3 on the curve, so Im c to 1e-10 pins alpha to ~1e-8
     assert np.abs(r2["alpha"] - r["alpha"]).max() < 1e-7
+
+
+def test_private_conte_copies_with_cash_karp(engine, osb, oracle):
+    """orrsom / orrspace call the shared steppers of shoot.f, so a USE_RKCK45 build (gcc.mak:46-48) runs
+    their private CONTE copies with CRKCK45 as well: the non-default kernel instantiations
+    (analytic inner product + Cash-Karp, orrsom's loop rule + Cash-Karp) against the oracle."""
+    fact = S2 / 1.7207876
+    ymin, ymax = 0.0, 20.0 * fact
+    p = engine.solve_bl(osb.FLOW_ORRSPACE, osb.INT_RK4, 1000, ymin, ymax, 0.5, 0.0)
+    prof, _, _ = oracle.solve_bl(ob.FLOW_ORRSPACE, ob.INT_RK4, 1000, ymin, ymax, 0.5, 0.0)
+    opts = osb.shoot_defaults(osb.FLOW_ORRSPACE)
+    opts.integrator = osb.INT_CK45
+    opts.nstep, opts.ymin, opts.ymax, opts.testalpha = 1000, ymin, ymax, 0.9
+    Re = np.array([1000.0, 900.0]) * fact
+    om = np.full(2, complex(0.06, 0.0)) * fact
+    dom = np.full(2, 0.004) * fact
+    a0 = np.array([complex(0.18304, -0.00168), complex(0.1845, 0.0005)]) * fact
+    r = engine.shoot_spatial_lines(opts, p, Re, om, dom, a0, 6)
+    p.free()
+    for line in range(2):
+        ref = oracle.shoot_spatial_line(ob.INT_CK45, 1000, 0.9, ymin, ymax, prof, Re[line], om[line], dom[line], a0[line], 6)
+        assert np.all(r["status"][line] == 0) and np.all(ref["status"] == 0)
+        e = rel(r["alpha"][line], ref["alpha"])
+        assert e.max() < 5e-9, e
+        assert e[ref["passes"] <= 10].max() < EIG_RTOL
+    p = engine.solve_bl(osb.FLOW_ORRSOM, osb.INT_RK4, 1000, 0.0, 17.0, 0.5, 0.0)
+    prof, _, _ = oracle.solve_bl(ob.FLOW_ORRSOM, ob.INT_RK4, 1000, 0.0, 17.0, 0.5, 0.0)
+    opts = osb.shoot_defaults(osb.FLOW_ORRSOM)
+    opts.integrator = osb.INT_CK45
+    opts.nstep, opts.ymax = 1000, 17.0
+    al = np.array([0.1453, 0.16, 0.179]) * S2
+    ReT = np.array([581.1, 581.1, 580.0]) * S2
+    g = np.array([complex(0.35, 0.01), complex(0.355, 0.012), complex(0.3641, 0.008)])
+    r = engine.shoot_temporal(opts, p, al, ReT, g)
+    p.free()
+    for i in range(3):
+        ref = oracle.shoot_temporal(ob.FLOW_ORRSOM, ob.INT_CK45, 1000, 10.0, 0.0, 17.0, prof, al[i], ReT[i], g[i])
+        assert r["status"][i] == 0 and ref["status"] == 0
+        assert rel(r["c"][i], ref["c"]) < 5e-9          # orrsom stops at |err| < 1e-8
+        assert r["passes"][i] == ref["passes"] and r["qend"][i] == ref["qend"]
