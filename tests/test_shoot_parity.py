@@ -636,3 +636,23 @@ def test_private_conte_copies_with_cash_karp(engine, osb, oracle):
         assert r["status"][i] == 0 and ref["status"] == 0
         assert rel(r["c"][i], ref["c"]) < 5e-9          # orrsom stops at |err| < 1e-8
         assert r["passes"][i] == ref["passes"] and r["qend"][i] == ref["qend"]
+
+
+def test_eigenfunction_orrsom(engine, osb, oracle):
+    """orrsom's second pass (orrsom.f:455-503) for test.inp-like settings, against the oracle."""
+    p = engine.solve_bl(osb.FLOW_ORRSOM, osb.INT_RK4, 1000, 0.0, 17.0, 0.5, 0.0)
+    prof, _, _ = oracle.solve_bl(ob.FLOW_ORRSOM, ob.INT_RK4, 1000, 0.0, 17.0, 0.5, 0.0)
+    opts = osb.shoot_defaults(osb.FLOW_ORRSOM)
+    opts.nstep, opts.ymax = 1000, 17.0
+    al, Re, g = 0.179 * S2, 580.0 * S2, complex(0.36413124, 0.0079527387)
+    r = engine.shoot_temporal(opts, p, [al], [Re], [g])
+    e = engine.eigfun(opts, p, [Re], r["c"], alpha=[al])
+    p.free()
+    ref = oracle.shoot_temporal(ob.FLOW_ORRSOM, ob.INT_RK4, 1000, 10.0, 0.0, 17.0, prof, al, Re, g, eigfun=True)
+    assert r["status"][0] == 0 and rel(r["c"][0], ref["c"]) < 5e-9
+    assert e["qend"][0] == ref["qend"]
+    y = e["y"][0] / e["vmax"][0]
+    yr = ref["y"] / ref["vmax"]
+    for i in range(4):
+        scale = np.max(np.abs(yr[:, i]))
+        assert np.max(np.abs(y[:, i] - yr[:, i])) / scale < 1e-7   # the eigenvalues themselves differ by ~1e-9 (errtol 1e-8)
