@@ -224,3 +224,18 @@ def test_banded_kernels_large_batch(engine, monkeypatch):
     assert (a["status"] == 0).all() and (b["status"] == 0).all()
     assert rel(a["omega"], b["omega"]).max() < 1e-12
     assert np.abs(a["iters"].astype(int) - b["iters"].astype(int)).max() <= 1
+
+
+def test_orrfdchan_maximum_size(engine, oracle):
+    """N = 1024, the largest grid the C ABI accepts (orrcolchan.f:22 idim = 1024; orrfdchan itself stops at
+    512): banded path against the oracle's ZGEEV on the 1023 x 1023 operator."""
+    N = 1024
+    alpha = np.array([0.9, 1.0])
+    ch = engine.chan(ob.DISC_FD, N)
+    r = ch.solve(alpha, 1.0e4)
+    ch.free()
+    c = ob.chan(ob.DISC_FD, N)
+    ref = np.array([c.solve_fd(a, 1.0e4)["omega"] for a in alpha])
+    c.close()
+    assert (r["status"] == 0).all()
+    assert rel(r["omega"], ref).max() < 1e-9, rel(r["omega"], ref)
