@@ -482,14 +482,31 @@ int osb_shoot_temporal(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profi
   if (npts == 0) return OSB_OK;
   if (history && hist_cap < 1) return fail(ctx, OSB_E_ARG, "hist_cap < 1");
   const int ndev = (int)ctx->devices.size();
-  struct Buf { double *alpha = 0, *Re = 0, *c = 0, *resid = 0, *hist = 0; int32_t *ip = 0; double2 *tab = 0; int64_t lo = 0, hi = 0; };
+  // pass counts vary by region of a sweep, so contiguous blocks would imbalance the devices:
+  // tiles of the flattened point index are dealt cyclically (tile t -> device t mod ndev) and packed
+  // contiguously in each device's buffers.  Per-point results do not depend on the partition.
+  struct Seg { int64_t host_lo, n, dev_off; };
+  struct Buf { double *alpha = 0, *Re = 0, *c = 0, *resid = 0, *hist = 0; int32_t *ip = 0; double2 *tab = 0; int64_t n = 0; std::vector<Seg> segs; };
   std::vector<Buf> bufs(ndev);
+  {
+    int64_t tile = npts;
+    if (ndev > 1) {
+      tile = ((npts / ((int64_t)ndev * 32) + 4095) / 4096) * 4096;
+      tile = std::min<int64_t>(std::max<int64_t>(tile, 4096), (int64_t)1 << 20);
+    }
+    int64_t t = 0;
+    for (int64_t lo = 0; lo < npts; lo += tile, ++t) {
+      Buf &b = bufs[(int)(t % ndev)];
+      const int64_t n = std::min(tile, npts - lo);
+      b.segs.push_back(Seg{lo, n, b.n});
+      b.n += n;
+    }
+  }
   std::vector<std::unique_ptr<Scratch>> guards(ndev);
   // phase 1: per device H2D + launch (kernels of different devices overlap)
   for (int d = 0; d < ndev; ++d) {
     Buf &b = bufs[d];
-    chunk(npts, ndev, d, &b.lo, &b.hi);
-    const int64_t n = b.hi - b.lo;
+    const int64_t n = b.n;
     if (n <= 0) continue;
     cudaStream_t st = ctx->streams[d];
     OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
@@ -501,9 +518,11 @@ int osb_shoot_temporal(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profi
     OSB_CUDA(ctx, scr.alloc(&b.ip, n * 3 * sizeof(int32_t)));
     if (resid) OSB_CUDA(ctx, scr.alloc(&b.resid, n * 2 * sizeof(double)));
     if (history) OSB_CUDA(ctx, scr.alloc(&b.hist, n * hist_cap * 4 * sizeof(double)));
-    OSB_CUDA(ctx, cudaMemcpyAsync(b.alpha, alpha + 2 * b.lo, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-    OSB_CUDA(ctx, cudaMemcpyAsync(b.Re, Re + b.lo, n * sizeof(double), cudaMemcpyHostToDevice, st));
-    OSB_CUDA(ctx, cudaMemcpyAsync(b.c, c + 2 * b.lo, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (const Seg &g : b.segs) {
+      OSB_CUDA(ctx, cudaMemcpyAsync(b.alpha + 2 * g.dev_off, alpha + 2 * g.host_lo, g.n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+      OSB_CUDA(ctx, cudaMemcpyAsync(b.Re + g.dev_off, Re + g.host_lo, g.n * sizeof(double), cudaMemcpyHostToDevice, st));
+      OSB_CUDA(ctx, cudaMemcpyAsync(b.c + 2 * g.dev_off, c + 2 * g.host_lo, g.n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     if (history) OSB_CUDA(ctx, cudaMemsetAsync(b.hist, 0, n * hist_cap * 4 * sizeof(double), st));
     rc = make_stage_table(ctx, d, scr, opts, prof, &b.tab);
     if (rc) return rc;
@@ -524,19 +543,23 @@ int osb_shoot_temporal(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profi
     OSB_CUDA(ctx, launch_shoot(a, opts->integrator, analytic, st, &nl, qc));
     ctx->launches += nl;
   }
-  // phase 2: D2H + free
+  // phase 2: D2H
   for (int d = 0; d < ndev; ++d) {
     Buf &b = bufs[d];
-    const int64_t n = b.hi - b.lo;
+    const int64_t n = b.n;
     if (n <= 0) continue;
     cudaStream_t st = ctx->streams[d];
     OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
-    OSB_CUDA(ctx, cudaMemcpyAsync(c + 2 * b.lo, b.c, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    OSB_CUDA(ctx, cudaMemcpyAsync(passes + b.lo, b.ip, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    OSB_CUDA(ctx, cudaMemcpyAsync(qend + b.lo, b.ip + n, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    OSB_CUDA(ctx, cudaMemcpyAsync(status + b.lo, b.ip + 2 * n, n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (resid) OSB_CUDA(ctx, cudaMemcpyAsync(resid + 2 * b.lo, b.resid, n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    if (history) OSB_CUDA(ctx, cudaMemcpyAsync(history + b.lo * hist_cap * 4, b.hist, n * hist_cap * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    for (const Seg &g : b.segs) {
+      OSB_CUDA(ctx, cudaMemcpyAsync(c + 2 * g.host_lo, b.c + 2 * g.dev_off, g.n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      OSB_CUDA(ctx, cudaMemcpyAsync(passes + g.host_lo, b.ip + g.dev_off, g.n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      OSB_CUDA(ctx, cudaMemcpyAsync(qend + g.host_lo, b.ip + n + g.dev_off, g.n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      OSB_CUDA(ctx, cudaMemcpyAsync(status + g.host_lo, b.ip + 2 * n + g.dev_off, g.n * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      if (resid) OSB_CUDA(ctx, cudaMemcpyAsync(resid + 2 * g.host_lo, b.resid + 2 * g.dev_off, g.n * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      if (history)
+        OSB_CUDA(ctx, cudaMemcpyAsync(history + g.host_lo * hist_cap * 4, b.hist + g.dev_off * hist_cap * 4,
+                                      g.n * hist_cap * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
   }
   for (int d = 0; d < ndev; ++d) {
     OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
