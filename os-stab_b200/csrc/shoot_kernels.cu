@@ -1051,12 +1051,17 @@ static cudaError_t launch_shoot_queue(const ShootArgs &a, int integrator, int an
 cudaError_t launch_shoot(const ShootArgs &a, int integrator, int analytic_inprod, cudaStream_t st,
                          int *nlaunch, unsigned long long *queue_counter) {
   if (a.nlines <= 0) return cudaSuccess;
-  if (queue_counter && !a.spatial && a.niter == 1 && a.nlines >= 4 * QT) {
+  // Which kernel (measured on B200, tools/bench_small_batches.py, config-5 points):
+  //   <= 9472 lines      two lanes per line: 1.2-1.25x over one thread per line
+  //   up to ~65k points  one thread per point: the GPU is not yet oversubscribed, compaction only costs
+  //   beyond             the compacting persistent-CTA kernel: +9 % at 131k points, +11 % at 524k, more at 16.7M
+  // OSB_QUEUE_MIN overrides the last threshold (tests run the queue kernel on small batches with it).
+  int64_t queue_min = 65536;
+  if (const char *e = getenv("OSB_QUEUE_MIN")) queue_min = std::max<int64_t>(4 * QT, atoll(e));
+  if (queue_counter && !a.spatial && a.niter == 1 && a.nlines >= queue_min) {
     if (nlaunch) *nlaunch += 1;
     return launch_shoot_queue(a, integrator, analytic_inprod, queue_counter, st);
   }
-  // too few lines to fill the GPU with one thread each: two lanes per line (measured gain
-  // 1.13-1.18x up to 4096 lines, a loss at 16384: DESIGN.md 5)
   if (a.nlines <= 148 * 64 && !getenv("OSB_NO_PAIR")) {
     const int threads = 64;
     const unsigned blocks = (unsigned)((2 * a.nlines + threads - 1) / threads);

@@ -393,9 +393,9 @@ def test_orrspace_space_deck_eigenfunction(engine, osb, oracle):
 
 
 @pytest.mark.parametrize("n", [512, 513, 1300, 37888 + 7])
-def test_queue_kernel_equals_plain_kernel_bitwise(engine, osb, bl, n):
-    """Batches >= 512 points go through the compacting persistent-CTA kernel, smaller ones through the
-    one-thread-per-point kernel: same per-point arithmetic, so chunked and unchunked results must be
+def test_queue_kernel_equals_plain_kernel_bitwise(engine, osb, bl, n, monkeypatch):
+    """Large batches go through the compacting persistent-CTA kernel, smaller ones through the lane-pair or
+    the one-thread-per-point kernel: same per-point arithmetic, so chunked and unchunked results must be
     identical bit for bit (c, passes, qend, status, |err|, pass history), whatever the schedule --
     including complex alpha mixed in (per-warp real-alpha fast path) and ragged tails."""
     rng = np.random.default_rng(n)
@@ -404,7 +404,9 @@ def test_queue_kernel_equals_plain_kernel_bitwise(engine, osb, bl, n):
     Re = 580.0 * (1 + 0.02 * (rng.random(n) - 0.5)) * S2
     guess = np.full(n, complex(0.36412287, 0.0079597206))
     opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    monkeypatch.setenv("OSB_QUEUE_MIN", "512")  # the queue kernel normally starts at 65536 points
     whole = engine.shoot_temporal(opts, bl, al, Re, guess, want_resid=True, hist_cap=6)
+    monkeypatch.delenv("OSB_QUEUE_MIN")
     m = min(n, 1300)  # the chunked (plain-kernel) pass over the first m points
     for lo in range(0, m, 100):
         hi = min(lo + 100, m)
