@@ -665,7 +665,8 @@ struct BandArgs {
   double2 *evec;   // optional [ninst][n+2]
   double2 *U;      // [n][BW][ninst]
   double2 *L;      // [n][BKL][ninst]
-  int8_t *piv;     // [n][ninst]  pivot offset 0..4
+  int8_t *piv;     // [n][ninst]  pivot offset 0..4 (one-thread kernel)
+  int32_t *piv32;  // [ninst][n]  the same for the nine-lane kernel (4-byte cp.async granularity)
   double2 *x, *y;  // [n][ninst]
 };
 
@@ -853,13 +854,28 @@ constexpr int BWW = 4;    // warps per CTA
 constexpr int BG = 3;     // instances per warp
 constexpr int64_t BAND_WARP_MAX_INST = 16384;  // beyond: the one-thread kernel fills the GPU better
 
-template <int BCH>           // rows per staged chunk
-struct BandStage {           // per instance, shared memory
-  double2 ub[BCH * BW];      // LU: entering band rows; back substitution: chunk of Uc
-  double2 lb[BCH * BKL];     // forward substitution: chunk of L
-  double2 yi[BCH], yo[BCH];  // substitution: entering right-hand sides, solved rows
-  int pv[BCH];
+template <int BCH>             // rows per staged chunk
+struct BandStage {             // per instance, shared memory; [2]: the next chunk arrives (cp.async) while this one is used
+  double2 ub[2][BCH * BW];     // LU: entering band rows ([0]); back substitution: chunk of Uc
+  double2 lb[2][BCH * BKL];    // forward substitution: chunk of L
+  double2 yi[2][BCH], yo[BCH]; // substitution: entering right-hand sides, solved rows
+  int pv[2][BCH];
 };
+
+// 16-byte / 4-byte asynchronous global -> shared copies; !valid zero-fills the destination
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ double2 shfl2(double2 v, int src) {
   return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
@@ -883,9 +899,9 @@ __device__ __forceinline__ double2 band_entry_c(const BandArgs &a, const PencilC
   return v;
 }
 
-// Two builds: <32 rows per chunk, 2 CTAs/SM> has the shortest latency per instance (no spills);
-// <16, 3> trades 20 % of it for 12 resident warps per SM, which pays when the sweep needs
-// more than two CTAs per SM to fit in one wave.
+// Three builds by sweep size: <32 rows per chunk, 1 CTA/SM> has the shortest latency per instance (fewest
+// chunk turn-arounds; deck-sized sweeps), <16, 2> and <8, 3> trade some of it for 8 / 12 resident warps per
+// SM, which pays when the sweep needs that many CTAs per SM to fit in one wave.
 template <int BCH, int MINB>
 __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(const __grid_constant__ BandArgs a) {
   typedef BandStage<BCH> Stage;
@@ -904,7 +920,7 @@ __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(con
   Stage *stg0 = (Stage *)smem_raw + warp * BG;
   const size_t nU = (size_t)n * BW, nL = (size_t)n * BKL;
   double2 *Uc = a.U + (size_t)inst * nU, *Lm = a.L + (size_t)inst * nL;
-  int8_t *piv = a.piv + (size_t)inst * n;
+  int32_t *piv = a.piv32 + (size_t)inst * n;
   const PencilCoef p = pencil_coef(a.alpha[inst], a.Re[inst]);
   double2 sigma = a.sigma[inst];
   const int ngrp = (int)min((int64_t)BG, a.ninst - inst0);
@@ -941,7 +957,7 @@ __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(con
         // entering rows c0+5 .. c0+36, diagonal gl on lane gl
         __syncwarp();
         if (lane_ok)
-          for (int q = 0; q < BCH; ++q) stg->ub[q * BW + gl] = band_entry_c(a, p, sb2, sb0, c0 + q + 1 + BKL, gl);
+          for (int q = 0; q < BCH; ++q) stg->ub[0][q * BW + gl] = band_entry_c(a, p, sb2, sb0, c0 + q + 1 + BKL, gl);
         __syncwarp();
         const int hi = min(BCH, n - c0);
         for (int kk = 0; kk < hi; ++kk) {
@@ -987,7 +1003,7 @@ __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(con
           if (act && lane_ok) {
             if (is_src) {
               Uc[(size_t)k * BW] = rinv;
-              piv[k] = (int8_t)pv;
+              piv[k] = pv;
 #pragma unroll
               for (int sidx = 1; sidx <= BKL; ++sidx) Lm[(size_t)k * BKL + (sidx - 1)] = l[sidx];
             } else if (mycol < n) {
@@ -996,7 +1012,7 @@ __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(con
           }
           int idx = is_src ? BW - 1 : mycol - k - 1;
           idx = max(0, min(idx, BW - 1));
-          w[BKL] = stg->ub[kk * BW + idx];
+          w[BKL] = stg->ub[0][kk * BW + idx];
           if (is_src) mycol = k + BW;
           src = (src + 1 == BW) ? 0 : src + 1;
         }
@@ -1034,36 +1050,44 @@ __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(con
       PROF_ADD(5);
       const bool leader = lane_ok && gl == 0 && inner_on;
       const double2 *yme = a.y + (size_t)inst * n;
-      // ---- forward: L y' = P y.  Lane s of a group holds the right-hand side of row k+s (s = 0..4)
+      // ---- forward: L y' = P y.  Lane s of a group holds the right-hand side of row k+s (s = 0..4).
+      // Chunk i+1 of L / pivots / entering rows travels by cp.async while chunk i is eliminated.
       {
         double2 bw = (lane_ok && gl <= BKL && gl < n) ? yme[gl] : make_double2(0.0, 0.0);
-        for (int c0 = 0; c0 < n; c0 += BCH) {
+        auto stage = [&](int c0, int buf) {
           for (int gp = 0; gp < ngrp; ++gp) {
             const size_t ib = (size_t)(inst0 + gp);
             Stage *sg = stg0 + gp;
 #pragma unroll
             for (int q = 0; q < (BCH * BKL + 31) / 32; ++q) {
               const int el = q * 32 + lane, e = c0 * BKL + el;
-              if (el < BCH * BKL) sg->lb[el] = (e < n * BKL) ? a.L[ib * nL + e] : make_double2(0.0, 0.0);
+              if (el < BCH * BKL) cp_async16(&sg->lb[buf][el], a.L + ib * nL + min(e, n * BKL - 1), e < n * BKL);
             }
             if (lane < BCH) {
-              sg->pv[lane] = (c0 + lane < n) ? (int)a.piv[ib * n + c0 + lane] : 0;
-              const int r = c0 + lane + 1 + BKL;
-              sg->yi[lane] = (r < n) ? a.y[ib * n + r] : make_double2(0.0, 0.0);
+              const int k = c0 + lane, r = k + 1 + BKL;
+              cp_async4(&sg->pv[buf][lane], a.piv32 + ib * n + min(k, n - 1), k < n);
+              cp_async16(&sg->yi[buf][lane], a.y + ib * n + min(r, n - 1), r < n);
             }
           }
+          cp_async_commit();
+        };
+        stage(0, 0);
+        int buf = 0;
+        for (int c0 = 0; c0 < n; c0 += BCH, buf ^= 1) {
+          if (c0 + BCH < n) { stage(c0 + BCH, buf ^ 1); cp_async_wait<1>(); }
+          else cp_async_wait<0>();
           __syncwarp();
           const int hi = min(BCH, n - c0);
           const int lrow = min(max(gl - 1, 0), BKL - 1);
           for (int kk = 0; kk < hi; ++kk) {
-            const int pv = stg->pv[kk];
+            const int pv = stg->pv[buf][kk];
             const double2 pvv = shfl2(bw, lead + pv), b0 = shfl2(bw, lead);
-            const double2 t = sel2(gl == pv, b0, bw);                      // row pv receives the old row 0
-            const double2 upd = cfnma2(t, stg->lb[kk * BKL + lrow], pvv);  // rows k+1..k+4 (lanes 1..4)
+            const double2 t = sel2(gl == pv, b0, bw);                           // row pv receives the old row 0
+            const double2 upd = cfnma2(t, stg->lb[buf][kk * BKL + lrow], pvv);  // rows k+1..k+4 (lanes 1..4)
             if (leader) stg->yo[kk] = pvv;
             // shift: lane s takes the updated row s+1; lane 4 takes the entering row k+5
             const double2 nxt = make_double2(__shfl_down_sync(0xffffffffu, upd.x, 1), __shfl_down_sync(0xffffffffu, upd.y, 1));
-            bw = sel2(gl == BKL, stg->yi[kk], nxt);
+            bw = sel2(gl == BKL, stg->yi[buf][kk], nxt);
           }
           __syncwarp();
           for (int gp = 0; gp < ngrp; ++gp)
@@ -1077,29 +1101,37 @@ __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(con
       {
         double2 acc = (lane_ok && n - 1 - gl >= 0) ? yme[n - 1 - gl] : make_double2(0.0, 0.0);
         const int ucol = min(gl, BW - 1);
-        for (int c0 = ((n - 1) / BCH) * BCH; c0 >= 0; c0 -= BCH) {
+        auto stage = [&](int c0, int buf) {
           for (int gp = 0; gp < ngrp; ++gp) {
             const size_t ib = (size_t)(inst0 + gp);
             Stage *sg = stg0 + gp;
 #pragma unroll
             for (int q = 0; q < (BCH * BW + 31) / 32; ++q) {
               const int el = q * 32 + lane, e = c0 * BW + el;
-              if (el < BCH * BW) sg->ub[el] = (e < n * BW) ? a.U[ib * nU + e] : make_double2(0.0, 0.0);
+              if (el < BCH * BW) cp_async16(&sg->ub[buf][el], a.U + ib * nU + min(e, n * BW - 1), e < n * BW);
             }
             if (lane < BCH) {
               const int r = c0 + lane - BW;
-              sg->yi[lane] = (r >= 0) ? a.y[ib * n + r] : make_double2(0.0, 0.0);
+              cp_async16(&sg->yi[buf][lane], a.y + ib * n + max(r, 0), r >= 0);
             }
           }
+          cp_async_commit();
+        };
+        const int ctop = ((n - 1) / BCH) * BCH;
+        stage(ctop, 0);
+        int buf = 0;
+        for (int c0 = ctop; c0 >= 0; c0 -= BCH, buf ^= 1) {
+          if (c0 - BCH >= 0) { stage(c0 - BCH, buf ^ 1); cp_async_wait<1>(); }
+          else cp_async_wait<0>();
           __syncwarp();
           const int hi = min(BCH, n - c0);
           for (int kk = hi - 1; kk >= 0; --kk) {
-            const double2 um = stg->ub[kk * BW + ucol];          // lane 0: 1/U(k,k); lane j: U(k-j, k)
+            const double2 um = stg->ub[buf][kk * BW + ucol];     // lane 0: 1/U(k,k); lane j: U(k-j, k)
             const double2 v = shfl2(cmul2(acc, um), lead);       // x_k
             if (leader) stg->yo[kk] = v;
             const double2 upd = cfnma2(acc, um, v);
             const double2 nxt = make_double2(__shfl_down_sync(0xffffffffu, upd.x, 1), __shfl_down_sync(0xffffffffu, upd.y, 1));
-            acc = sel2(gl == BW - 1, stg->yi[kk], nxt);          // lane 8 takes the entering row k-9
+            acc = sel2(gl == BW - 1, stg->yi[buf][kk], nxt);     // lane 8 takes the entering row k-9
           }
           __syncwarp();
           for (int gp = 0; gp < ngrp; ++gp)
@@ -1174,7 +1206,7 @@ __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(con
 }
 
 size_t chan_band_work_bytes(int n, int64_t ninst) {
-  return (size_t)ninst * (size_t)n * (sizeof(double2) * (BW + BKL + 2) + 1) + 256;
+  return (size_t)ninst * (size_t)n * (sizeof(double2) * (BW + BKL + 2) + 1 + 4) + 512;
 }
 
 cudaError_t launch_chan_fd_banded(int n, const double *D2, const double *D4, const double *u, const double *d2u,
@@ -1189,6 +1221,7 @@ cudaError_t launch_chan_fd_banded(int n, const double *D2, const double *D4, con
   const size_t N1 = (size_t)ninst * n;
   a.U = w; a.L = w + N1 * BW; a.x = w + N1 * (BW + BKL); a.y = w + N1 * (BW + BKL + 1);
   a.piv = (int8_t *)(w + N1 * (BW + BKL + 2));
+  a.piv32 = (int32_t *)(((uintptr_t)(a.piv + N1) + 255) & ~(uintptr_t)255);
   // nine lanes per instance while that still leaves the GPU room (the one-thread kernel needs
   // ~10^5 instances to fill it); OSB_FD_THREAD=1 forces the one-thread kernel
   if (band24 && ninst <= BAND_WARP_MAX_INST && !getenv("OSB_FD_THREAD")) {
@@ -1198,16 +1231,21 @@ cudaError_t launch_chan_fd_banded(int n, const double *D2, const double *D4, con
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e;
-    if ((int64_t)grid <= 2 * (int64_t)sms) {
+    if ((int64_t)grid <= (int64_t)sms) {
       const size_t smem = sizeof(BandStage<32>) * BG * BWW;
-      e = cudaFuncSetAttribute(chan_fd_banded_warp_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(chan_fd_banded_warp_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      chan_fd_banded_warp_kernel<32, 2><<<grid, BWW * 32, smem, st>>>(a);
-    } else {
+      chan_fd_banded_warp_kernel<32, 1><<<grid, BWW * 32, smem, st>>>(a);
+    } else if ((int64_t)grid <= 2 * (int64_t)sms) {
       const size_t smem = sizeof(BandStage<16>) * BG * BWW;
-      e = cudaFuncSetAttribute(chan_fd_banded_warp_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(chan_fd_banded_warp_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      chan_fd_banded_warp_kernel<16, 3><<<grid, BWW * 32, smem, st>>>(a);
+      chan_fd_banded_warp_kernel<16, 2><<<grid, BWW * 32, smem, st>>>(a);
+    } else {
+      const size_t smem = sizeof(BandStage<8>) * BG * BWW;
+      e = cudaFuncSetAttribute(chan_fd_banded_warp_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      chan_fd_banded_warp_kernel<8, 3><<<grid, BWW * 32, smem, st>>>(a);
     }
     return cudaGetLastError();
   }
