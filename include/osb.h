@@ -250,6 +250,22 @@ int osb_chan_eig(osb_ctx *ctx, const osb_chan *chan, double Re, int64_t npts, co
                  const double *sigma0, double *omega, double *evec, int32_t *iters, int32_t *status);
 
 /*
+ * The FULL spectrum of the interior pencil at each alpha: what SOLVE_ORR_SOM computes before it keeps one
+ * mode (orrfdchan.f:792-797 inv(B)A + ZGEEV; the table orrcolchan.f:505-513 / orrfdchan.f:834-838 prints).
+ * C = inv(B) A, Hessenberg reduction and single-shift complex QR run on the device, one CTA per alpha;
+ * each value is then polished by one shift-invert iteration on the pencil itself (kept when it settles
+ * next to its seed), which removes the conditioning of inv(B)A from the well-separated modes.
+ * Not a sweep path: osb_chan_eig isolates its mode without the spectrum and is orders of magnitude faster;
+ * this entry point serves the interactive listings and lets a caller apply the reference's selection rule
+ * to the whole spectrum.
+ *   spectrum [npts * (N-1) * 2]  eigenvalues omega of each alpha, ascending in Im(omega) like the
+ *                                reference's SORT / PIKSR2 pass (orrfdchan.f:803-811)
+ *   status   [npts]              OSB_ST_CONVERGED, or OSB_ST_MAXCOUNT if a QR iteration limit was hit
+ */
+int osb_chan_spectrum(osb_ctx *ctx, const osb_chan *chan, double Re, int64_t npts, const double *alpha,
+                      double *spectrum, int32_t *status);
+
+/*
  * Batched neutral-point search, the Newton iteration on alpha of orrncbl.f:109-116
  * (bug-compatible step: the adjoint is the left eigenvector of inv(B)A, D-7), one
  * independent search per Re:  while |Im w| > tol: alpha += sfac * (-Im w / Im dw/da).

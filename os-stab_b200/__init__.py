@@ -99,6 +99,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "osb_chan_free": (C.c_int, [vp, vp]),
         "osb_chan_tables": (C.c_int, [vp, vp, _dp, _dp, _dp, _dp, _dp]),
         "osb_chan_eig": (C.c_int, [vp, vp, dbl, i64, _dp, _dp, _dp, _dp, _ip, _ip]),
+        "osb_chan_spectrum": (C.c_int, [vp, vp, dbl, i64, _dp, _dp, _ip]),
         "osb_chan_neutral": (C.c_int, [vp, vp, i64, _dp, _dp, dbl, dbl, i32, _dp, _dp, _ip, _ip, _dp]),
     }
     for name, (res, args) in sig.items():
@@ -113,7 +114,7 @@ EXPORTED_SYMBOLS = (
     "osb_launch_count osb_profile_blasius osb_profile_blasius_batch osb_profile_upload "
     "osb_profile_shift osb_profile_channel osb_profile_get osb_profile_nbl osb_profile_free osb_shoot_defaults "
     "osb_shoot_temporal osb_shoot_temporal_dev osb_shoot_spatial_lines osb_shoot_neutral osb_eigfun osb_measure_fp64_peak "
-    "osb_chan_create osb_chan_create_bl osb_chan_bl_points osb_chan_free osb_chan_tables osb_chan_eig osb_chan_neutral"
+    "osb_chan_create osb_chan_create_bl osb_chan_bl_points osb_chan_free osb_chan_tables osb_chan_eig osb_chan_spectrum osb_chan_neutral"
 ).split()
 
 DISC_FD, DISC_CHEB, DISC_CHEB_NUM = 0, 1, 2
@@ -420,6 +421,19 @@ class Chan:
         if want_evec:
             r["evec"] = ev.view(np.complex128).reshape(n, self.N + 1)
         return r
+
+    def spectrum(self, alpha, Re):
+        """All N-1 eigenvalues of the interior pencil at each alpha, ascending in Im(omega)
+        (what SOLVE_ORR_SOM sorts before it keeps one mode).  Returns dict(spectrum[npts, N-1], status)."""
+        alpha = np.atleast_1d(np.asarray(alpha, dtype=np.complex128))
+        n = alpha.size
+        al = _cplx_pairs(alpha, n)
+        out = np.zeros(2 * n * (self.N - 1))
+        status = np.zeros(n, dtype=np.int32)
+        self.engine._check(self.engine.lib.osb_chan_spectrum(
+            self.engine.ctx, self.handle, float(Re), n, al.ctypes.data_as(_dp), out.ctypes.data_as(_dp),
+            status.ctypes.data_as(_ip)))
+        return dict(spectrum=out.view(np.complex128).reshape(n, self.N - 1), status=status)
 
     def neutral(self, Re, alpha0, sfac=0.01, tol=1.0e-8, maxit=200, want_trace=False):
         """The Newton iteration on alpha of orrncbl.f:109-116, one search per Re."""

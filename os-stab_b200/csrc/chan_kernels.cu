@@ -638,6 +638,283 @@ __device__ __forceinline__ void chan_eig_body(const ChanArgs &a) {
 }
 
 // ---------------------------------------------------------------------------
+// K4c: the FULL spectrum of one pencil -- what SOLVE_ORR_SOM computes before it keeps one mode
+// (orrfdchan.f:792-797: C = inv(B) A by ZGETRF/ZGETRI/ZGEMM, then ZGEEV; orrcolchan.f:505-513 lists it).
+// Not on the sweep path (the sweep isolates its mode by shift-invert); it serves the interactive
+// listings of the single-alpha programs and lets the tests apply the reference's selection rule to a
+// spectrum computed on the device.  One CTA per pencil:
+//   C = inv(B) A        with the blocked LU above (n triangular solves),
+//   H = Q^H C Q         Householder reduction to Hessenberg form, CTA-parallel rank-1 updates,
+//   eigenvalues of H    single-shift complex QR with Wilkinson shifts and LAPACK's (ZLAHQR) deflation
+//                       test; rotations are applied to the active block only (eigenvalues only).
+// ---------------------------------------------------------------------------
+struct SpectrumArgs {
+  int n;
+  const double *D2, *D4, *u, *d2u;
+  double2 *work;          // gridDim.x * 2 * n*n
+  int64_t ninst;
+  const double2 *alpha;   // [ninst]
+  const double *Re;       // [ninst]
+  double2 *eig;           // [ninst][n]  unsorted
+  int32_t *status;        // [ninst]  0 ok, 1 QR iteration limit hit
+};
+
+__device__ __forceinline__ double cabs1d(double2 z) { return fabs(z.x) + fabs(z.y); }
+__device__ __forceinline__ double2 csqrt2(double2 z) {
+  const zd r = zsqrt(zd{z.x, z.y});
+  return make_double2(r.x, r.y);
+}
+
+// B = b2 D2 + b0 I, column-major n x n
+__device__ void assemble_B(double2 *__restrict__ M, int n, const double *__restrict__ D2, const PencilCoef &p) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    for (int j = 0; j < n; ++j) {
+      const size_t e = (size_t)j * n + i;
+      double2 v = make_double2(p.b2.x * D2[e], p.b2.y * D2[e]);
+      if (i == j) v = cadd2(v, p.b0);
+      M[e] = v;
+    }
+  __syncthreads();
+}
+
+// H <- Q^H H Q (upper Hessenberg), column-major, ld = n.  v: shared, n complex
+__device__ void cta_hessenberg(double2 *H, int n, double2 *v, double *red) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  for (int k = 0; k < n - 2; ++k) {
+    const int m = n - k - 1;                 // length of the column below the diagonal
+    double2 *col = H + (size_t)k * n + k + 1;
+    double2 part = make_double2(0.0, 0.0);
+    for (int i = tid; i < m; i += nt) { const double2 x = col[i]; part.x += x.x * x.x + x.y * x.y; v[i] = x; }
+    const double xn = sqrt(block_sum(part, red).x);
+    __syncthreads();
+    if (xn == 0.0) continue;
+    const double2 a0 = v[0];
+    const double a0n = hypot(a0.x, a0.y);
+    const double2 ph = a0n > 0.0 ? make_double2(a0.x / a0n, a0.y / a0n) : make_double2(1.0, 0.0);
+    const double2 beta = make_double2(-ph.x * xn, -ph.y * xn);
+    __syncthreads();
+    if (tid == 0) v[0] = csub2(a0, beta);
+    __syncthreads();
+    // |v|^2 = |x|^2 - |a0|^2 + |a0 - beta|^2
+    const double2 v0 = v[0];
+    const double vn2 = xn * xn - a0n * a0n + (v0.x * v0.x + v0.y * v0.y);
+    if (!(vn2 > 0.0)) continue;
+    const double tau = 2.0 / vn2;
+    // left: H[k+1:, j] -= tau v (v^H H[k+1:, j]) for j = k..n-1, a warp per column
+    for (int j = k + warp; j < n; j += nwarp) {
+      double2 *cj = H + (size_t)j * n + k + 1;
+      double2 w = make_double2(0.0, 0.0);
+      for (int i = lane; i < m; i += 32) w = cadd2(w, cmulc2(v[i], cj[i]));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        w.x += __shfl_xor_sync(0xffffffffu, w.x, o);
+        w.y += __shfl_xor_sync(0xffffffffu, w.y, o);
+      }
+      w = make_double2(tau * w.x, tau * w.y);
+      for (int i = lane; i < m; i += 32) cj[i] = csub2(cj[i], cmul2(v[i], w));
+    }
+    __syncthreads();
+    // right: H[i, k+1:] -= tau (H[i, k+1:] v) v^H, a thread per row
+    for (int i = tid; i < n; i += nt) {
+      double2 r = make_double2(0.0, 0.0);
+      for (int j = 0; j < m; ++j) r = cadd2(r, cmul2(H[(size_t)(k + 1 + j) * n + i], v[j]));
+      r = make_double2(tau * r.x, tau * r.y);
+      for (int j = 0; j < m; ++j) {
+        const double2 vc = make_double2(v[j].x, -v[j].y);
+        double2 *e = H + (size_t)(k + 1 + j) * n + i;
+        *e = csub2(*e, cmul2(r, vc));
+      }
+    }
+    __syncthreads();
+    for (int i = tid; i < m; i += nt) col[i] = (i == 0) ? beta : make_double2(0.0, 0.0);
+    __syncthreads();
+  }
+}
+
+// eigenvalues of the upper Hessenberg H (destroyed); returns 0 or 1 (iteration limit)
+__device__ int cta_hqr(double2 *H, int n, double2 *w_out, double *red) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ int sh_l, sh_fail;
+  __shared__ double sh_c;
+  __shared__ double2 sh_s, sh_t;
+  const double eps = 2.220446049250313e-16, safmin = 2.2250738585072014e-308;
+  const double smlnum = safmin * ((double)n / eps);
+  int *red_i = (int *)red;
+#define HQ(i, j) H[(size_t)(j) * n + (i)]
+  if (tid == 0) sh_fail = 0;
+  __syncthreads();
+  for (int hi = n - 1; hi >= 0; --hi) {
+    int its = 0;
+    while (true) {
+      // ---- largest l in (0, hi] with a negligible subdiagonal H(l, l-1)   (ZLAHQR's test)
+      int best = 0;
+      for (int l = hi - tid; l > 0; l -= nt) {
+        const double2 sub = HQ(l, l - 1);
+        bool small = cabs1d(sub) <= smlnum;
+        if (!small) {
+          double tst = cabs1d(HQ(l - 1, l - 1)) + cabs1d(HQ(l, l));
+          if (tst == 0.0) {
+            if (l - 2 >= 0) tst += fabs(HQ(l - 1, l - 2).x);
+            if (l + 1 <= n - 1) tst += fabs(HQ(l + 1, l).x);
+          }
+          if (fabs(sub.x) <= eps * tst) {
+            const double h12 = cabs1d(HQ(l - 1, l)), h21 = cabs1d(sub);
+            const double ab = fmax(h21, h12), ba = fmin(h21, h12);
+            const double d11 = cabs1d(HQ(l, l)), d = cabs1d(csub2(HQ(l - 1, l - 1), HQ(l, l)));
+            const double aa = fmax(d11, d), bb = fmin(d11, d);
+            const double sc = aa + ab;
+            small = ba * (ab / sc) <= fmax(smlnum, eps * (bb * (aa / sc)));
+          }
+        }
+        if (small) { best = l; break; }   // this thread's candidates are visited in descending order
+      }
+      // block-wide maximum
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+      __syncthreads();
+      if ((tid & 31) == 0) red_i[tid >> 5] = best;
+      __syncthreads();
+      if (tid == 0) {
+        int b = 0;
+        for (int wv = 0; wv < (nt >> 5); ++wv) b = max(b, red_i[wv]);
+        sh_l = b;
+        if (b > 0) HQ(b, b - 1) = make_double2(0.0, 0.0);
+      }
+      __syncthreads();
+      const int l = sh_l;
+      if (l >= hi) break;          // H(hi,hi) has converged
+      ++its;
+      if (its > 300) { if (tid == 0) sh_fail = 1; break; }
+      // ---- shift (thread 0)
+      if (tid == 0) {
+        double2 t;
+        if (its % 10 == 0 && its % 20 != 0) {
+          t = HQ(l, l); t.x += 0.75 * fabs(HQ(l + 1, l).x);
+        } else if (its % 20 == 0) {
+          t = HQ(hi, hi); t.x += 0.75 * fabs(HQ(hi, hi - 1).x);
+        } else {
+          t = HQ(hi, hi);
+          const double2 uu = cmul2(csqrt2(HQ(hi - 1, hi)), csqrt2(HQ(hi, hi - 1)));
+          double sc = cabs1d(uu);
+          if (sc != 0.0) {
+            const double2 x = make_double2(0.5 * (HQ(hi - 1, hi - 1).x - t.x), 0.5 * (HQ(hi - 1, hi - 1).y - t.y));
+            const double sx = cabs1d(x);
+            sc = fmax(sc, sx);
+            const double2 xs = make_double2(x.x / sc, x.y / sc), us = make_double2(uu.x / sc, uu.y / sc);
+            double2 y = csqrt2(cadd2(cmul2(xs, xs), cmul2(us, us)));
+            y = make_double2(sc * y.x, sc * y.y);
+            if (sx > 0.0 && (x.x / sx) * y.x + (x.y / sx) * y.y < 0.0) y = make_double2(-y.x, -y.y);
+            t = csub2(t, cmul2(uu, cdiv2(uu, cadd2(x, y))));
+          }
+        }
+        sh_t = t;
+      }
+      __syncthreads();
+      // ---- one implicit single-shift QR sweep over the active block [l, hi]
+      for (int k = l; k < hi; ++k) {
+        if (tid == 0) {
+          double2 a, b;
+          if (k == l) { a = csub2(HQ(k, k), sh_t); b = HQ(k + 1, k); }
+          else { a = HQ(k, k - 1); b = HQ(k + 1, k - 1); }
+          double c;
+          double2 sn, r;
+          const double nb = hypot(b.x, b.y), na = hypot(a.x, a.y);
+          if (nb == 0.0) { c = 1.0; sn = make_double2(0.0, 0.0); r = a; }
+          else if (na == 0.0) { c = 0.0; sn = make_double2(b.x / nb, -b.y / nb); r = make_double2(nb, 0.0); }
+          else {
+            const double nrm = hypot(na, nb);
+            const double2 ph = make_double2(a.x / na, a.y / na);
+            c = na / nrm;
+            const double2 cb = make_double2(b.x / nrm, -b.y / nrm);
+            sn = cmul2(ph, cb);
+            r = make_double2(ph.x * nrm, ph.y * nrm);
+          }
+          if (k > l) { HQ(k, k - 1) = r; HQ(k + 1, k - 1) = make_double2(0.0, 0.0); }
+          sh_c = c; sh_s = sn;
+        }
+        __syncthreads();
+        const double c = sh_c;
+        const double2 sn = sh_s, snc = make_double2(sn.x, -sn.y);
+        // rows k, k+1 over the columns k..hi
+        for (int j = k + tid; j <= hi; j += nt) {
+          const double2 x = HQ(k, j), y = HQ(k + 1, j);
+          HQ(k, j) = cadd2(make_double2(c * x.x, c * x.y), cmul2(sn, y));
+          HQ(k + 1, j) = csub2(make_double2(c * y.x, c * y.y), cmul2(snc, x));
+        }
+        __syncthreads();
+        // columns k, k+1 over the rows l..min(k+2, hi)
+        const int top = min(k + 2, hi);
+        for (int i = l + tid; i <= top; i += nt) {
+          const double2 x = HQ(i, k), y = HQ(i, k + 1);
+          HQ(i, k) = cadd2(make_double2(c * x.x, c * x.y), cmul2(snc, y));
+          HQ(i, k + 1) = csub2(make_double2(c * y.x, c * y.y), cmul2(sn, x));
+        }
+        __syncthreads();
+      }
+    }
+    if (tid == 0) w_out[hi] = HQ(hi, hi);
+    __syncthreads();
+    if (sh_fail) {
+      // give the remaining diagonal as it stands so that the caller sees finite numbers
+      for (int i = tid; i < hi; i += nt) w_out[i] = HQ(i, i);
+      __syncthreads();
+      return 1;
+    }
+  }
+#undef HQ
+  return 0;
+}
+
+__global__ void __launch_bounds__(CH_THREADS) chan_spectrum_kernel(const __grid_constant__ SpectrumArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int n = a.n;
+  ChanShared s = carve(smem, n);
+  double2 *M1 = a.work + (size_t)blockIdx.x * 2 * n * n, *M2 = M1 + (size_t)n * n;
+  for (int64_t inst = blockIdx.x; inst < a.ninst; inst += gridDim.x) {
+    const PencilCoef p = pencil_coef(a.alpha[inst], a.Re[inst]);
+    assemble_B(M1, n, a.D2, p);
+    cta_lu(M1, n, s.ipiv, s.panel, s.red);
+    assemble_shifted(M2, n, a.D2, a.D4, a.u, a.d2u, p, make_double2(0.0, 0.0));   // A
+    for (int j = 0; j < n; ++j) {   // C(:, j) = inv(B) A(:, j)
+      double2 *cj = M2 + (size_t)j * n;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) s.x[i] = cj[i];
+      __syncthreads();
+      cta_solve(M1, n, s.ipiv, s.x);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) cj[i] = s.x[i];
+      __syncthreads();
+    }
+    cta_hessenberg(M2, n, s.x, s.red);
+    const int st = cta_hqr(M2, n, a.eig + (size_t)inst * n, s.red);
+    if (threadIdx.x == 0) a.status[inst] = st;
+    __syncthreads();
+  }
+}
+
+cudaError_t launch_chan_spectrum(int n, const double *D2, const double *D4, const double *u, const double *d2u,
+                                 double2 *work, int grid, size_t smem, int64_t ninst, const double2 *alpha,
+                                 const double *Re, double2 *eig, int32_t *status, cudaStream_t st) {
+  SpectrumArgs a;
+  a.n = n; a.D2 = D2; a.D4 = D4; a.u = u; a.d2u = d2u; a.work = work; a.ninst = ninst; a.alpha = alpha; a.Re = Re;
+  a.eig = eig; a.status = status;
+  chan_spectrum_kernel<<<grid, CH_THREADS, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+cudaError_t chan_spectrum_grid(int n, int64_t ninst, int *grid, size_t *smem) {
+  *smem = chan_fixed_smem(n);
+  cudaError_t e = cudaFuncSetAttribute(chan_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
+  if (e != cudaSuccess) return e;
+  int dev = 0, sms = 0, per = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, chan_spectrum_kernel, CH_THREADS, *smem);
+  if (e != cudaSuccess) return e;
+  if (per < 1) return cudaErrorInvalidConfiguration;
+  *grid = (int)std::min<int64_t>(ninst, (int64_t)sms * per);
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------
 // K4b: the FD operator is banded.  D1hat is tridiagonal (FiniteD1, orrfdchan.f:1183-1215),
 // so D2 = D1hat D1 has half bandwidth 2 and D4 half bandwidth 4: A - sigma B is a 9-diagonal
 // matrix.  Gaussian elimination with partial pivoting on it is the SAME elimination as the

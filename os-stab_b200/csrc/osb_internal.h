@@ -123,6 +123,10 @@ cudaError_t launch_chan_eig(int n, const double *D2, const double *D4, const dou
                             double2 *work, int grid, size_t smem, int64_t ninst, const double2 *alpha,
                             const double *Re, const double2 *sigma, int outer, int inner, double tol,
                             double2 *omega, double *delta, int32_t *iters, double2 *evec, cudaStream_t st);
+cudaError_t chan_spectrum_grid(int n, int64_t ninst, int *grid, size_t *smem);
+cudaError_t launch_chan_spectrum(int n, const double *D2, const double *D4, const double *u, const double *d2u,
+                                 double2 *work, int grid, size_t smem, int64_t ninst, const double2 *alpha,
+                                 const double *Re, double2 *eig, int32_t *status, cudaStream_t st);
 size_t chan_band_work_bytes(int n, int64_t ninst);
 cudaError_t launch_chan_fd_banded(int n, const double *D2, const double *D4, const double *u, const double *d2u,
                                   const double2 *band24, void *work, int64_t ninst, const double2 *alpha, const double *Re,

@@ -173,6 +173,17 @@ module osb_c
       integer(c_int32_t), intent(out) :: iters(*), status(*)
     end function
     !> replaces the `do while (abs(IMAG(eigenvalue)).gt.1.0e-8)` Newton loop (orrncbl.f:109-116)
+    !> the whole spectrum SOLVE_ORR_SOM sorts before keeping one mode (orrfdchan.f:792-811), ascending in Im(w)
+    integer(c_int) function osb_chan_spectrum(ctx, chan, Re, npts, alpha, spectrum, status) &
+        bind(C, name="osb_chan_spectrum")
+      import :: c_int, c_int32_t, c_int64_t, c_ptr, c_double, c_double_complex
+      type(c_ptr), value :: ctx, chan
+      real(c_double), value :: Re
+      integer(c_int64_t), value :: npts
+      complex(c_double_complex), intent(in) :: alpha(*)
+      complex(c_double_complex), intent(out) :: spectrum(*)
+      integer(c_int32_t), intent(out) :: status(*)
+    end function
     integer(c_int) function osb_chan_neutral(ctx, chan, nRe, Re, alpha0, sfac, tol, maxit, alpha_out, &
                                              omega, steps, status, trace) bind(C, name="osb_chan_neutral")
       import :: c_int, c_int32_t, c_int64_t, c_ptr, c_double, c_double_complex

@@ -16,6 +16,7 @@
 //     sorted index 62 of chan.inp) instead of the whole QZ spectrum;
 //   * gfortran's list-directed `write(*,*)` spacing (orrncbl.f:902, orrcolchan.f:539,546)
 //     is not reproduced.
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstdio>
@@ -650,17 +651,26 @@ static int run_orrfdchan(osb_ctx *ctx) {
   int bad = 0;
   for (int64_t p = 0; p < npts; ++p) {
     if (print) {
-      // the `if (print)` block of SOLVE_ORR_SOM (orrfdchan.f:832-873).  The reference lists the
-      // whole ZGEEV spectrum here; this engine isolates the one mode the sweep keeps,
-      // so the table has that single row.  Whatever index is typed, the reference writes the
-      // eigenvector of the KEPT mode (iloc), normalised by its largest component, to fort.11.
+      // the `if (print)` block of SOLVE_ORR_SOM (orrfdchan.f:832-873): the spectrum listing, then -- whatever
+      // index is typed -- the eigenvector of the KEPT mode (iloc), normalised by its largest component, in fort.11.
       const cd alpha(al[2 * p], al[2 * p + 1]), w(om[2 * p], om[2 * p + 1]);
       printf("\n Residual = %s\n", F(0.0, 17, 10).c_str());
       printf("\n %s    %s    %s    \n", E(Re, 17, 10).c_str(), E(alpha.real(), 17, 10).c_str(), E(alpha.imag(), 17, 10).c_str());
       printf("\n        w_r                w_i              count\n\n");
-      printf(" %s    %s    %s\n", E(w.real(), 17, 10).c_str(), E(w.imag(), 17, 10).c_str(), I(1, 5).c_str());
-      const cd cph = w / alpha;
-      fprintf(f20, " %s    %s    \n", E(cph.real(), 17, 10).c_str(), E(cph.imag(), 17, 10).c_str());
+      {
+        // the reference lists ZGEEV's raw output order (and one entry past it, orrfdchan.f:834-838); here
+        // the device spectrum in the sorted order of its SORT pass
+        std::vector<double> sp((size_t)(n - 1) * 2);
+        int32_t sst = 0;
+        CK(ctx, osb_chan_spectrum(ctx, chan, Re, 1, al.data() + 2 * p, sp.data(), &sst));
+        for (int i = 0; i < n - 1; ++i) {
+          printf(" %s    %s    %s\n", E(sp[2 * i], 17, 10).c_str(), E(sp[2 * i + 1], 17, 10).c_str(), I(i + 1, 5).c_str());
+          const cd cph = cd(sp[2 * i], sp[2 * i + 1]) / alpha;
+          fprintf(f20, " %s    %s    \n", E(cph.real(), 17, 10).c_str(), E(cph.imag(), 17, 10).c_str());
+        }
+        bad |= sst;
+        (void)w;
+      }
       int which = 0;
       printf("\n Eigenvector for which eigenvalue (0 quits) ==> ");
       while (std::cin >> which && which != 0) {
@@ -838,19 +848,35 @@ static int run_orrcolchan(osb_ctx *ctx) {
               ES(d2u[i], 16, 8, 3).c_str());
     fclose(f);
   }
-  double al[2] = {alphar, alphai}, om[2];
-  std::vector<double> ev((size_t)(n + 1) * 2);
-  int32_t it, st;
-  CK(ctx, osb_chan_eig(ctx, chan, Re, 1, al, nullptr, om, ev.data(), &it, &st));
+  double al[2] = {alphar, alphai};
+  const cd alpha(alphar, alphai);
+  // the whole spectrum on the device (inv(B)A, Hessenberg, shifted QR).  The reference's (N+1) x (N+1) pencil
+  // carries two more eigenvalues from its boundary rows -- infinite, which it maps to 0 (orrcolchan.f:466-472) --
+  // and sorts everything by Im(w) with PIKSR2 (straight insertion: stable)
+  std::vector<double> sp((size_t)(n - 1) * 2);
+  int32_t sst = 0;
+  CK(ctx, osb_chan_spectrum(ctx, chan, Re, 1, al, sp.data(), &sst));
+  std::vector<cd> omega;
+  omega.push_back(cd(0.0, 0.0));
+  omega.push_back(cd(0.0, 0.0));
+  for (int k = 0; k < n - 1; ++k) omega.push_back(cd(sp[2 * k], sp[2 * k + 1]));
+  std::stable_sort(omega.begin(), omega.end(), [](const cd &x, const cd &y) { return x.imag() < y.imag(); });
   printf("\n Eigenvalues for N+1 = %s\n\n", I(n + 1, 4).c_str());
-  const cd w(om[0], om[1]), c = w / cd(alphar, alphai);
-  // the reference lists all N+1 QZ eigenvalues; the GPU path isolates the least stable
-  // physical mode (sorted index N-2 when the two spurious Im~3 modes sit above it)
-  printf(" %s  %s %s %s %s \n", I(n - 2, 5).c_str(), ES(w.real(), 17, 10).c_str(), ES(w.imag(), 17, 10).c_str(),
-         ES(c.real(), 17, 10).c_str(), ES(c.imag(), 17, 10).c_str());
-  int which = -1;
+  for (int i = 0; i <= n; ++i) {
+    const cd c = omega[i] / alpha;
+    printf(" %s  %s %s %s %s \n", I(i, 5).c_str(), ES(omega[i].real(), 17, 10).c_str(), ES(omega[i].imag(), 17, 10).c_str(),
+           ES(c.real(), 17, 10).c_str(), ES(c.imag(), 17, 10).c_str());
+  }
+  int which = -1, bad = sst;
   printf("\n Eigenvector for which eigenvalue (-1 quits) ==> ");
   while (std::cin >> which && which != -1) {
+    if (which < 0 || which > n) { fprintf(stderr, "index out of range\n"); bad = 1; break; }
+    // the eigenvector of the chosen mode: shift-invert with its eigenvalue as the shift
+    double sg[2] = {omega[which].real(), omega[which].imag()}, om[2];
+    std::vector<double> ev((size_t)(n + 1) * 2);
+    int32_t it, st;
+    CK(ctx, osb_chan_eig(ctx, chan, Re, 1, al, sg, om, ev.data(), &it, &st));
+    bad |= st;
     FILE *f = fopen("fort.11", "w");  // orrcolchan.f:551-555 (adjoint columns: not computed, zeros)
     for (int i = 0; i <= n; ++i)
       fprintf(f, " %s %s %s %s %s \n", ES(eta[i], 16, 8, 3).c_str(), ES(ev[2 * i], 16, 8, 3).c_str(), ES(ev[2 * i + 1], 16, 8, 3).c_str(),
@@ -859,7 +885,7 @@ static int run_orrcolchan(osb_ctx *ctx) {
     printf("\n Eigenvector for which eigenvalue (-1 quits) ==> ");
   }
   osb_chan_free(ctx, chan);
-  return st;
+  return bad;
 }
 
 // ---------------------------------------------------------------- orrncbl

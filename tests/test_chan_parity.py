@@ -239,3 +239,49 @@ def test_orrfdchan_maximum_size(engine, oracle):
     c.close()
     assert (r["status"] == 0).all()
     assert rel(r["omega"], ref).max() < 1e-9, rel(r["omega"], ref)
+
+
+def _match(a, b):
+    """Greedy nearest-neighbour matching of two spectra; returns relative distances (per entry of a)."""
+    b = np.array(b)
+    used = np.zeros(b.size, bool)
+    out = np.zeros(a.size)
+    for i, z in enumerate(a):
+        d = np.where(used, np.inf, np.abs(b - z))
+        j = int(np.argmin(d))
+        used[j] = True
+        out[i] = d[j] / max(abs(b[j]), 1e-300)
+    return out
+
+
+@pytest.mark.parametrize("disc,N", [(ob.DISC_FD, 64), (ob.DISC_CHEB, 64), (ob.DISC_FD, 128), (ob.DISC_FD, 300)])
+def test_full_spectrum_on_device(engine, oracle, disc, N):
+    """osb_chan_spectrum: inv(B)A + Hessenberg + shifted QR on the GPU against the oracle's ZGEEV spectrum
+    (orrfdchan.f:792-811), and the reference's selection rule applied to the device spectrum against the
+    mode osb_chan_eig isolates without it."""
+    alpha = np.array([0.76, 1.0, 1.16, 1.0 + 0.02j]) if N <= 128 else np.array([1.0])
+    ch = engine.chan(disc, N)
+    sp = ch.spectrum(alpha, 1.0e4)
+    kept = ch.solve(alpha, 1.0e4)
+    ch.free()
+    assert (sp["status"] == 0).all()
+    c = ob.chan(disc, N)
+    for k, a in enumerate(alpha):
+        ref = c.solve_fd(a, 1.0e4, want_spectrum=True)
+        w = sp["spectrum"][k]
+        assert w.shape == (N - 1,) and np.isfinite(w).all()
+        assert (np.diff(w.imag) >= 0).all()                       # sorted like the reference's listing
+        e = _match(w, ref["spectrum"])
+        # The spectrum of this non-normal operator is sensitive: a 1e-16 relative perturbation of inv(B)A
+        # moves ZGEEV's own eigenvalues by up to 4e-6 (FD, N=200) / 4e-4 (N=300), median 1e-8.  Two QR
+        # implementations can only agree to that level; the kept (least stable) mode is well conditioned.
+        loose = disc != ob.DISC_FD or N > 128
+        assert np.median(e) < (1e-5 if loose else 1e-9), np.median(e)
+        assert e.max() < (5e-3 if loose else 1e-5), e.max()
+        # the reference's rule on the device spectrum (orrfdchan.f:815-823) picks the mode osb_chan_eig returns
+        ok = (np.abs(w.imag) < 10.0) & (w.real.astype(int) != 999)
+        pick = w[ok][np.argmax(w[ok].imag)]
+        if disc == ob.DISC_FD:
+            assert abs(pick - kept["omega"][k]) < 1e-6 * abs(pick), (a, pick, kept["omega"][k])
+            assert abs(pick - ref["omega"]) < 1e-6 * abs(pick)
+    c.close()
