@@ -180,6 +180,7 @@ def test_mapped_boundary_layer_operator(engine, osb, oracle, disc, N, lmap):
     alpha = np.array([0.16, 0.179, 0.2, 0.179 + 0.002j]) * S2
     Re = 580.0 * S2
     r = ch.solve(alpha, Re, want_evec=True)
+    sp = ch.spectrum(alpha[1:2], Re)
     oc = ob.chan(disc, N, bl=(lmap, ch.U, ch.merge))
     ref = [oc.solve_fd(a, Re, want_evec=True) for a in alpha]
     # the host tables fold the metrics into D2', D4': compare them with the oracle's unfolded ones
@@ -190,6 +191,9 @@ def test_mapped_boundary_layer_operator(engine, osb, oracle, disc, N, lmap):
     ch.free()
     assert (r["status"] == 0).all()
     w_ref = np.array([x["omega"] for x in ref])
+    # orrcolbl.f:771-779 keeps the largest Im w of the FULL spectrum: the device spectrum agrees with the scan
+    w_all = sp["spectrum"][0]
+    assert sp["status"][0] == 0 and abs(w_all[np.argmax(w_all.imag)] - r["omega"][1]) < 1e-8 * abs(r["omega"][1])
     # parity with the LAPACK route on this ill-scaled mapped operator: 1e-9 (collocation), 1e-10 (FD)
     e = rel(r["omega"], w_ref)
     assert e.max() < (2e-9 if disc == ob.DISC_CHEB else 1e-10), e
