@@ -2013,6 +2013,24 @@ static bool use_small_kernel(int n) {
   return n <= nmax && !chan_matrix_in_smem(n) && !getenv("OSB_CHAN_NO_SMALL");
 }
 
+// largest interior size n the dense CTA kernels can take: the 16-column panel, three vectors and the pivots
+// must fit the opt-in shared memory next to the kernels' static arrays
+int chan_dense_max_n() {
+  static int cached = -1;
+  if (cached >= 0) return cached;
+  int dev = 0, optin = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaFuncAttributes fa;
+  size_t stat = 0;
+  if (cudaFuncGetAttributes(&fa, (const void *)chan_eig_kernel_big) == cudaSuccess) stat = fa.sharedSizeBytes;
+  if (cudaFuncGetAttributes(&fa, (const void *)chan_spectrum_kernel) == cudaSuccess) stat = std::max(stat, fa.sharedSizeBytes);
+  int n = 64;
+  while (n < 4096 && chan_fixed_smem(n + 1) + stat <= (size_t)optin) ++n;
+  cached = n;
+  return n;
+}
+
 cudaError_t chan_eig_grid(int n, int64_t ninst, int *grid, size_t *smem) {
   if (use_warp_kernels(n)) return warp_grid(n, ninst, grid, smem, (const void *)chan_eig_warp_kernel);
   if (use_big_kernel(n)) return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel_big, CH_THREADS_BIG);

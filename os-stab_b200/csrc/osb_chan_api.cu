@@ -294,6 +294,13 @@ static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::ve
   CH_CUDA(ctx, cudaSetDevice(c->device));
   // the FD operator is banded (half bandwidth 4): banded LU, one thread per instance
   const bool banded = (c->disc == OSB_DISC_FD) && !getenv("OSB_FD_DENSE");
+  if (!banded) {
+    CH_CUDA(ctx, cudaSetDevice(c->device));
+    if (n > chan_dense_max_n())
+      return ctx_fail(ctx, OSB_E_ARG, "N too large for the dense kernels (their 16-column LU panel lives in shared memory): "
+                                      "limit N = " + std::to_string(chan_dense_max_n() + 1) +
+                                      "; the FD operator has no such limit (banded kernels)");
+  }
   if (!banded) CH_CUDA(ctx, chan_eig_grid(n, ninst, &grid, &smem));
   Scratch scr(c->device, st);
   double *d_in = nullptr, *d_out = nullptr;
@@ -422,6 +429,9 @@ int osb_chan_spectrum(osb_ctx *ctx, const osb_chan *c, double Re, int64_t npts, 
   int grid = 0;
   size_t smem = 0;
   CH_CUDA(ctx, cudaSetDevice(c->device));
+  if (n > chan_dense_max_n())
+    return ctx_fail(ctx, OSB_E_ARG, "N too large for the dense kernels (their 16-column LU panel lives in shared memory): "
+                                    "limit N = " + std::to_string(chan_dense_max_n() + 1));
   CH_CUDA(ctx, chan_spectrum_grid(n, npts, &grid, &smem));
   Scratch scr(c->device, st);
   double *d_in = nullptr;

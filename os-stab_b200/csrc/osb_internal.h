@@ -116,6 +116,7 @@ cudaError_t launch_shift_profile(int nbl, double uc, const double *d_in, double 
                                  cudaStream_t st);
 // channel matrix path (chan_kernels.cu)
 size_t chan_smem_bytes(int n);
+int chan_dense_max_n();
 void chan_profile_dump(const char *tag);
 cudaError_t chan_eig_grid(int n, int64_t ninst, int *grid, size_t *smem);
 cudaError_t chan_neutral_grid(int n, int64_t ninst, int *grid, size_t *smem);

@@ -289,3 +289,18 @@ def test_full_spectrum_on_device(engine, oracle, disc, N):
             assert abs(pick - kept["omega"][k]) < 1e-6 * abs(pick), (a, pick, kept["omega"][k])
             assert abs(pick - ref["omega"]) < 1e-6 * abs(pick)
     c.close()
+
+
+def test_dense_path_size_limit_is_reported(engine, osb):
+    """Chebyshev at N = 800 does not fit the dense kernels' shared-memory panel: a clear error, no crash
+    (collocation at such N is numerically meaningless in fp64 anyway); N = 640 still runs."""
+    ch = engine.chan(ob.DISC_CHEB, 800)
+    with pytest.raises(osb.OsbError, match="limit N = "):
+        ch.solve([1.0], 1.0e4, sigma0=[0.2375 + 0.0037j])
+    with pytest.raises(osb.OsbError, match="limit N = "):
+        ch.spectrum([1.0], 1.0e4)
+    ch.free()
+    ch = engine.chan(ob.DISC_CHEB, 640)
+    r = ch.solve([1.0], 1.0e4, sigma0=[0.2375 + 0.0037j])
+    ch.free()
+    assert np.isfinite(r["omega"][0])
