@@ -402,6 +402,29 @@ int osb_chan_eig(osb_ctx *ctx, const osb_chan *c, double Re, int64_t npts, const
   else {
     int rc = scan_shifts(ctx, c, npts, alpha, Rev.data(), sig, ok);
     if (rc) return rc;
+    if (getenv("OSB_CHAN_SCAN_MISS")) std::fill(ok.begin(), ok.end(), 0);  // test hook: pretend the scan found nothing
+    // Points where no scanned shift settled on a mode the rule accepts: take the shift from the full spectrum
+    // computed on the device (K4c) under the same rule.  Rare; the scan covers the reference's decks.
+    std::vector<int64_t> miss;
+    for (int64_t p = 0; p < npts; ++p) if (!ok[p]) miss.push_back(p);
+    if (!miss.empty() && c->n <= chan_dense_max_n()) {
+      const int n = c->n;
+      std::vector<double> am(2 * miss.size()), sp((size_t)miss.size() * n * 2);
+      std::vector<int32_t> sst(miss.size());
+      for (size_t k = 0; k < miss.size(); ++k) { am[2 * k] = alpha[2 * miss[k]]; am[2 * k + 1] = alpha[2 * miss[k] + 1]; }
+      rc = osb_chan_spectrum(ctx, c, Re, (int64_t)miss.size(), am.data(), sp.data(), sst.data());
+      if (rc) return rc;
+      for (size_t k = 0; k < miss.size(); ++k) {
+        double best = -1.0e300;
+        for (int e = 0; e < n; ++e) {
+          const double wr = sp[(k * n + e) * 2], wi = sp[(k * n + e) * 2 + 1];
+          if (!(std::isfinite(wr) && std::isfinite(wi))) continue;
+          if (c->disc == OSB_DISC_FD || c->bl) { if (!(fabs(wi) < 10.0) || (int)wr == 999) continue; }
+          else if (!(fabs(wr) < 1.0)) continue;
+          if (wi > best) { best = wi; sig[2 * miss[k]] = wr; sig[2 * miss[k] + 1] = wi; ok[miss[k]] = 1; }
+        }
+      }
+    }
   }
   std::vector<double> a(alpha, alpha + 2 * npts), om, dl;
   std::vector<int32_t> it;

@@ -304,3 +304,19 @@ def test_dense_path_size_limit_is_reported(engine, osb):
     r = ch.solve([1.0], 1.0e4, sigma0=[0.2375 + 0.0037j])
     ch.free()
     assert np.isfinite(r["omega"][0])
+
+
+@pytest.mark.parametrize("disc", [ob.DISC_FD, ob.DISC_CHEB])
+def test_spectrum_fallback_when_the_scan_misses(engine, disc, monkeypatch):
+    """If no scanned shift settles on an acceptable mode, osb_chan_eig takes its shift from the device
+    spectrum under the same selection rule: same answers as the scan on the reference's deck points."""
+    alpha = np.array([0.76, 0.9, 1.0, 1.16])
+    ch = engine.chan(disc, 64)
+    monkeypatch.delenv("OSB_CHAN_SCAN_MISS", raising=False)
+    a = ch.solve(alpha, 1.0e4)
+    monkeypatch.setenv("OSB_CHAN_SCAN_MISS", "1")
+    b = ch.solve(alpha, 1.0e4)
+    monkeypatch.delenv("OSB_CHAN_SCAN_MISS")
+    ch.free()
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    assert rel(a["omega"], b["omega"]).max() < 1e-10
