@@ -320,3 +320,22 @@ def test_spectrum_fallback_when_the_scan_misses(engine, disc, monkeypatch):
     ch.free()
     assert (a["status"] == 0).all() and (b["status"] == 0).all()
     assert rel(a["omega"], b["omega"]).max() < 1e-10
+
+
+@pytest.mark.parametrize("npts", [1, 2, 4, 5, 13, 25])
+def test_banded_nine_lane_kernel_ragged_groups(engine, npts, monkeypatch):
+    """Three instances share a warp and twelve a CTA in the nine-lane kernel: sweeps that leave groups or
+    warps partly empty must give every instance the result it gets alone."""
+    alpha = np.linspace(0.8, 1.1, npts) + 0.003j * (np.arange(npts) % 3)
+    ch = engine.chan(ob.DISC_FD, 96)
+    monkeypatch.delenv("OSB_FD_THREAD", raising=False)
+    batch = ch.solve(alpha, 1.0e4, want_evec=True)
+    singles = [ch.solve(alpha[k:k + 1], 1.0e4, sigma0=batch["omega"][k:k + 1], want_evec=True) for k in range(npts)]
+    again = ch.solve(alpha, 1.0e4, sigma0=batch["omega"], want_evec=True)
+    ch.free()
+    assert (batch["status"] == 0).all() and (again["status"] == 0).all()
+    for k in range(npts):
+        # same kernel, same arithmetic per instance: bit-identical whatever the neighbours in the warp are
+        assert singles[k]["omega"][0] == again["omega"][k], k
+        assert np.array_equal(singles[k]["evec"][0], again["evec"][k]), k
+    assert rel(again["omega"], batch["omega"]).max() < 1e-11
