@@ -339,3 +339,24 @@ def test_banded_nine_lane_kernel_ragged_groups(engine, npts, monkeypatch):
         assert singles[k]["omega"][0] == again["omega"][k], k
         assert np.array_equal(singles[k]["evec"][0], again["evec"][k]), k
     assert rel(again["omega"], batch["omega"]).max() < 1e-11
+
+
+@pytest.mark.parametrize("N", [8, 9, 12, 17])
+def test_smallest_grids(engine, oracle, N):
+    """The smallest grids the C ABI accepts (interior size 7..16 < one window / one chunk of the banded
+    kernels, < one panel of the dense ones): given the oracle's eigenvalue as the shift, every path must
+    converge onto it."""
+    alpha = np.array([0.9, 1.0])
+    for disc in (ob.DISC_FD, ob.DISC_CHEB):
+        c = ob.chan(disc, N)
+        ref = np.array([c.solve_fd(a, 1.0e3)["omega"] for a in alpha])
+        c.close()
+        ch = engine.chan(disc, N)
+        r = ch.solve(alpha, 1.0e3, sigma0=ref * (1 + 1e-4))
+        sp = ch.spectrum(alpha, 1.0e3)
+        ch.free()
+        assert (r["status"] == 0).all(), (disc, N, r["status"])
+        assert rel(r["omega"], ref).max() < 1e-10, (disc, N, rel(r["omega"], ref))
+        assert (sp["status"] == 0).all() and sp["spectrum"].shape == (2, N - 1)
+        for k in range(2):
+            assert np.abs(sp["spectrum"][k] - ref[k]).min() < 1e-8 * abs(ref[k])
