@@ -683,3 +683,26 @@ def test_coarsest_resolutions(engine, osb, oracle, n, ymax):
         else:
             # a non-converging iteration wanders chaotically (rounding-seeded): only the outcome class is compared
             assert (ref["status"] != 0) == (r["status"][i] != 0) or abs(r["passes"][i] - ref["passes"]) <= 20
+
+
+@pytest.mark.parametrize("beta,f2p", [(0.1, 0.6), (-0.05, 0.4)])
+def test_falkner_skan_profiles_through_the_shooter(engine, osb, oracle, beta, f2p):
+    """beta != 0 (contebl.f:66, the Falkner-Skan family): profile and eigenvalues against the oracle."""
+    p = engine.solve_bl(osb.FLOW_CONTEBL, osb.INT_CK45, 1000, 0.0, 17.0, f2p, beta)
+    t = p.tables()
+    prof, npass, f2 = oracle.solve_bl(ob.FLOW_CONTEBL, ob.INT_CK45, 1000, 0.0, 17.0, f2p, beta)
+    assert t["npass"] == npass and t["f2p"] == f2 and np.array_equal(t["U"], prof[1][:1001])
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    al = np.array([0.17, 0.2]) * S2
+    Re = np.array([700.0, 900.0]) * S2
+    # continuation from the Blasius eigenvalue in a few oracle steps would be the driver's job; here both
+    # sides start from the same rough guess and must end on the same root
+    g = np.full(2, complex(0.36, 0.005))
+    r = engine.shoot_temporal(opts, p, al, Re, g)
+    p.free()
+    for i in range(2):
+        ref = oracle.shoot_temporal(ob.FLOW_CONTEBL, ob.INT_CK45, 1000, 10.0, 0.0, 17.0, prof, al[i], Re[i], g[i])
+        assert (ref["status"] == 0) == (r["status"][i] == 0)
+        if ref["status"] == 0:
+            assert rel(r["c"][i], ref["c"]) < EIG_RTOL
+            assert r["qend"][i] == ref["qend"]
