@@ -283,10 +283,10 @@ int osb_chan_tables(osb_ctx *ctx, const osb_chan *c, double *eta, double *u, dou
 }
 
 // run one batch of instances (alpha, Re, sigma) -> (omega, delta, iters[, evec])
-static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::vector<double> &alpha,
-                   const std::vector<double> &Re, const std::vector<double> &sigma, int outer, int inner,
-                   double tol, std::vector<double> &omega, std::vector<double> &delta,
-                   std::vector<int32_t> &iters, double *evec_host) {
+static int run_eig_chunk(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::vector<double> &alpha,
+                         const std::vector<double> &Re, const std::vector<double> &sigma, int outer, int inner,
+                         double tol, std::vector<double> &omega, std::vector<double> &delta,
+                         std::vector<int32_t> &iters, double *evec_host) {
   cudaStream_t st = (cudaStream_t)osb_stream(ctx);
   const int n = c->n;
   int grid = 0;
@@ -331,6 +331,38 @@ static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::ve
     CH_CUDA(ctx, cudaMemcpyAsync(evec_host, d_evec, (size_t)ninst * (n + 2) * sizeof(double2), cudaMemcpyDeviceToHost, st));
   CH_CUDA(ctx, cudaStreamSynchronize(st));
   if (getenv("OSB_CHAN_PROFILE")) chan_profile_dump("eig");
+  return OSB_OK;
+}
+
+// The banded path keeps 13 n complex factors per instance in HBM (123 KB at N = 512): batches are walked in
+// chunks of at most ~8 GB of device scratch so that any batch size fits.
+static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::vector<double> &alpha,
+                   const std::vector<double> &Re, const std::vector<double> &sigma, int outer, int inner,
+                   double tol, std::vector<double> &omega, std::vector<double> &delta,
+                   std::vector<int32_t> &iters, double *evec_host) {
+  const bool banded = (c->disc == OSB_DISC_FD) && !getenv("OSB_FD_DENSE");
+  int64_t chunk = ninst;
+  if (banded) {
+    const size_t per = chan_band_work_bytes(c->n, 1) + (evec_host ? (size_t)(c->n + 2) * 16 : 0) + 64;
+    chunk = std::max<int64_t>(1, (int64_t)((8ull << 30) / per));
+    if (const char *e = getenv("OSB_CHAN_CHUNK")) chunk = std::max<int64_t>(1, atoll(e));  // test hook
+  }
+  if (ninst <= chunk) return run_eig_chunk(ctx, c, ninst, alpha, Re, sigma, outer, inner, tol, omega, delta, iters, evec_host);
+  omega.resize(2 * ninst); delta.resize(ninst); iters.resize(ninst);
+  std::vector<double> a, r, sg, om, dl;
+  std::vector<int32_t> it;
+  for (int64_t lo = 0; lo < ninst; lo += chunk) {
+    const int64_t m = std::min(chunk, ninst - lo);
+    a.assign(alpha.begin() + 2 * lo, alpha.begin() + 2 * (lo + m));
+    r.assign(Re.begin() + lo, Re.begin() + lo + m);
+    sg.assign(sigma.begin() + 2 * lo, sigma.begin() + 2 * (lo + m));
+    int rc = run_eig_chunk(ctx, c, m, a, r, sg, outer, inner, tol, om, dl, it,
+                           evec_host ? evec_host + (size_t)lo * (c->n + 2) * 2 : nullptr);
+    if (rc) return rc;
+    std::copy(om.begin(), om.end(), omega.begin() + 2 * lo);
+    std::copy(dl.begin(), dl.end(), delta.begin() + lo);
+    std::copy(it.begin(), it.end(), iters.begin() + lo);
+  }
   return OSB_OK;
 }
 

@@ -360,3 +360,17 @@ def test_smallest_grids(engine, oracle, N):
         assert (sp["status"] == 0).all() and sp["spectrum"].shape == (2, N - 1)
         for k in range(2):
             assert np.abs(sp["spectrum"][k] - ref[k]).min() < 1e-8 * abs(ref[k])
+
+
+def test_banded_batches_are_chunked(engine, monkeypatch):
+    """The banded path walks large batches in chunks of bounded device scratch: same bits as one batch."""
+    alpha = np.linspace(0.8, 1.1, 50)
+    ch = engine.chan(ob.DISC_FD, 64)
+    first = ch.solve(alpha, 1.0e4)
+    whole = ch.solve(alpha, 1.0e4, sigma0=first["omega"], want_evec=True)
+    monkeypatch.setenv("OSB_CHAN_CHUNK", "12")
+    parts = ch.solve(alpha, 1.0e4, sigma0=first["omega"], want_evec=True)
+    monkeypatch.delenv("OSB_CHAN_CHUNK")
+    ch.free()
+    for k in ("omega", "evec", "iters", "status"):
+        assert np.array_equal(whole[k], parts[k]), k
