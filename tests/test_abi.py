@@ -67,3 +67,36 @@ def test_shard_bounds_partition(osb):
         parts = [osb.shard_bounds(npts, world, r, tile) for r in range(world)]
         allidx = np.sort(np.concatenate(parts))
         assert np.array_equal(allidx, np.arange(npts))
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/osb.h is the drop-in boundary for a C / Fortran host: it must compile as C99 with no C++ or
+    CUDA types in the signatures, and a C program must link against libosb.so.  Running it without a GPU
+    must fail with OSB_E_CUDA, not crash (there is no CPU fallback)."""
+    import subprocess
+
+    src = tmp_path / "host.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include "osb.h"
+int main(void) {
+  osb_ctx *ctx = 0;
+  osb_shoot_opts o;
+  int rc = osb_shoot_defaults(OSB_FLOW_CONTEBL, &o);
+  if (rc != 0 || o.nstep != 1000 || o.integrator != OSB_INT_CK45) return 10;
+  double y[65];
+  if (osb_chan_bl_points(OSB_DISC_CHEB, 64, 8.0, y) != 0 || !(y[64] == 0.0)) return 11;
+  rc = osb_create(&ctx, 0);
+  printf("osb_version %d create %d\n", osb_version(), rc);
+  if (rc == 0) osb_destroy(ctx);
+  return 0;
+}
+''')
+    exe = tmp_path / "host"
+    libdir = ROOT / "os-stab_b200"
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", str(ROOT / "include"), str(src), "-o", str(exe),
+                         "-L", str(libdir), "-losb", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "osb_version 1" in r.stdout
