@@ -1129,7 +1129,7 @@ __global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constan
 // ---------------------------------------------------------------------------
 constexpr int BWW = 4;    // warps per CTA
 constexpr int BG = 3;     // instances per warp
-constexpr int64_t BAND_WARP_MAX_INST = 16384;  // beyond: the one-thread kernel fills the GPU better
+constexpr int64_t BAND_WARP_MAX_INST = 131072;  // beyond: the one-thread kernel fills the GPU better
 
 template <int BCH>             // rows per staged chunk
 struct BandStage {             // per instance, shared memory; [2]: the next chunk arrives (cp.async) while this one is used
@@ -1518,11 +1518,19 @@ cudaError_t launch_chan_fd_banded(int n, const double *D2, const double *D4, con
       e = cudaFuncSetAttribute(chan_fd_banded_warp_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       chan_fd_banded_warp_kernel<16, 2><<<grid, BWW * 32, smem, st>>>(a);
-    } else {
+    } else if ((int64_t)grid <= 3 * (int64_t)sms || getenv("OSB_FD_NO4") ||
+               // beyond one wave of the 3-per-SM build: the 4-per-SM build (128 registers, a few spills, ~12 % slower
+               // per warp) wins when it saves a wave
+               ((grid + 3 * sms - 1) / (3 * sms)) * 100 <= ((grid + 4 * sms - 1) / (4 * sms)) * 112) {
       const size_t smem = sizeof(BandStage<8>) * BG * BWW;
       e = cudaFuncSetAttribute(chan_fd_banded_warp_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       chan_fd_banded_warp_kernel<8, 3><<<grid, BWW * 32, smem, st>>>(a);
+    } else {
+      const size_t smem = sizeof(BandStage<8>) * BG * BWW;
+      e = cudaFuncSetAttribute(chan_fd_banded_warp_kernel<8, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      chan_fd_banded_warp_kernel<8, 4><<<grid, BWW * 32, smem, st>>>(a);
     }
     return cudaGetLastError();
   }

@@ -209,10 +209,11 @@ def test_mapped_boundary_layer_operator(engine, osb, oracle, disc, N, lmap):
     assert oD2.shape == (N + 1, N + 1)
 
 
-def test_banded_kernels_large_batch(engine, monkeypatch):
-    """More than 3552 instances select the <16-row chunk, 3 CTAs/SM> build of the nine-lane kernel; it must
-    agree with the one-thread kernel exactly like the low-latency build does (ragged tail included)."""
-    n = 4001
+@pytest.mark.parametrize("n", [4001, 6001])
+def test_banded_kernels_large_batch(engine, monkeypatch, n):
+    """More than 3552 instances select the <8-row chunk, 3 CTAs/SM> build of the nine-lane kernel, more than
+    5328 the <8, 4> build (128 registers); both must agree with the one-thread kernel exactly like the
+    low-latency builds do (ragged tail included)."""
     alpha = np.linspace(0.76, 1.16, n)
     ch = engine.chan(ob.DISC_FD, 64)
     coarse = ch.solve(np.linspace(0.76, 1.16, 9), 1.0e4)
