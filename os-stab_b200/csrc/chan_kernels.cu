@@ -502,6 +502,20 @@ size_t chan_smem_bytes(int n) {
   return chan_fixed_smem(n) + (chan_matrix_in_smem(n) ? sizeof(double2) * (size_t)n * n : 0);
 }
 
+// Convergence of the (linear) inverse iteration at a fixed shift: successive changes of omega contract by
+// rho = dl / dl_prev, so after a change dl the next one is ~ rho dl and the current estimate is off by
+// ~ rho dl / (1 - rho).  Stop when the change is below the goal or -- one solve earlier -- when the
+// predicted next change is (with a factor 2 of margin, fast contraction only); the reported delta is then
+// the prediction.
+__device__ __forceinline__ bool inv_iter_converged(int it, double &dl, double dl_prev, double goal) {
+  if (it > 0 && dl <= goal) return true;
+  if (it >= 2 && dl_prev < 1.0e299) {
+    const double rho = dl / dl_prev;
+    if (rho < 0.05 && dl * rho <= 0.5 * goal) { dl *= rho; return true; }
+  }
+  return false;
+}
+
 // Right inverse iteration with the current LU: x (unit 2-norm, shared) in/out.
 // Returns the eigenvalue estimate after up to maxit iterations; *delta = last change.
 __device__ double2 inverse_iterate(const double2 *M, int n, const double *D2, const PencilCoef &p,
@@ -538,7 +552,7 @@ __device__ double2 inverse_iterate(const double2 *M, int n, const double *D2, co
     dl = hypot(om_new.x - om.x, om_new.y - om.y);
     om = om_new;
     const double goal = tol * hypot(om.x, om.y);
-    if (it > 0 && dl <= goal) { ++it; break; }
+    if (inv_iter_converged(it, dl, dl_prev, goal)) { ++it; break; }
     if (it + 1 >= maxit) {
       const double rho = dl / dl_prev;
       if (!(rho < 0.5) || !(dl > 0.0) || log(goal / dl) / log(rho) > 6.0) { ++it; break; }
@@ -1079,9 +1093,10 @@ __global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constan
         const double2 v = y[(size_t)i * S];
         x[(size_t)i * S] = make_double2(v.x * rn, v.y * rn);
       }
+      const double dl_prev = dl;
       dl = hypot(om_new.x - om.x, om_new.y - om.y);
       om = om_new;
-      if (it > 0 && dl <= a.tol * hypot(om.x, om.y)) { ++it; break; }
+      if (inv_iter_converged(it, dl, dl_prev, a.tol * hypot(om.x, om.y))) { ++it; break; }
     }
     total += it;
     if (dl <= a.tol * hypot(om.x, om.y)) break;
@@ -1439,10 +1454,11 @@ __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(con
       __syncwarp();
       if (inner_on) {
         const double2 om_new = cadd2(sigma, make_double2(myyx / myyy, myyxi / myyy));
+        const double dl_prev = dl;
         dl = hypot(om_new.x - om.x, om_new.y - om.y);
         om = om_new;
         it = step + 1;
-        if (step > 0 && dl <= a.tol * hypot(om.x, om.y)) inner_on = false;
+        if (inv_iter_converged(step, dl, dl_prev, a.tol * hypot(om.x, om.y))) inner_on = false;
       }
       PROF_ADD(0);
     }
@@ -1842,9 +1858,10 @@ __device__ double2 w_inverse_iterate(const WarpShared &s, int n, const double *D
     const double rn = rsqrt(yy.x);
     for (int i = lane; i < n; i += 32) s.x[i] = make_double2(s.y[i].x * rn, s.y[i].y * rn);
     __syncwarp();
+    const double dl_prev = dl;
     dl = hypot(om_new.x - om.x, om_new.y - om.y);
     om = om_new;
-    if (it > 0 && dl <= tol * hypot(om.x, om.y)) { ++it; break; }
+    if (inv_iter_converged(it, dl, dl_prev, tol * hypot(om.x, om.y))) { ++it; break; }
   }
   *delta = dl;
   *iters = it;
