@@ -53,6 +53,75 @@ typedef double _Complex zc;
 #define OSR_INT_CK45 1
 
 /* ---------------------------------------------------------------------- */
+/* Elementary functions.  By default the restatement calls libm's complex   */
+/* cabs / csqrt / cexp and real acos exactly like the gfortran build of the */
+/* reference (mode 0).  For the strict-parity tests (tests/                 */
+/* test_strict_parity.py) the REAL functions underneath can be replaced:    */
+/* mode 1 evaluates the complex functions with glibc's own formulas         */
+/* (s_csqrt_template.c, s_cexp_template.c, cabs = hypot) over the four real */
+/* functions in g_math.  Handing it libm's exp/sincos/hypot/acos must       */
+/* reproduce mode 0 bit for bit (that pins the formulas); handing it the    */
+/* portable functions the CUDA strict build uses makes the two sides        */
+/* comparable bit for bit.                                                  */
+/* ---------------------------------------------------------------------- */
+typedef struct {
+  double (*exp)(double);
+  void (*sincos)(double, double *, double *);
+  double (*hypot)(double, double);
+  double (*acos)(double);
+} osr_math;
+static osr_math g_math;
+static int g_math_mode = 0;
+
+void osr_set_math(const osr_math *m) {
+  if (m) { g_math = *m; g_math_mode = 1; }
+  else g_math_mode = 0;
+}
+static void osr_libm_sincos(double x, double *s, double *c) { *s = sin(x); *c = cos(x); }
+/* mode 1 over libm's own real functions (the self-check of the formulas below) */
+void osr_set_math_libm(void) {
+  g_math.exp = exp; g_math.sincos = osr_libm_sincos; g_math.hypot = hypot; g_math.acos = acos;
+  g_math_mode = 1;
+}
+
+static double m_cabs(double _Complex z) {
+  return g_math_mode ? g_math.hypot(creal(z), cimag(z)) : cabs(z);
+}
+static double m_acos(double x) { return g_math_mode ? g_math.acos(x) : acos(x); }
+/* glibc s_cexp_template.c, finite arguments below the overflow threshold */
+static double _Complex m_cexp(double _Complex z) {
+  if (!g_math_mode) return cexp(z);
+  double sn, cs;
+  if (fabs(cimag(z)) > 2.2250738585072014e-308) g_math.sincos(cimag(z), &sn, &cs);
+  else { sn = cimag(z); cs = 1.0; }
+  const double e = g_math.exp(creal(z));
+  return CMPLX(e * cs, e * sn);
+}
+/* glibc s_csqrt_template.c, finite arguments away from the overflow / underflow scaling branches */
+static double _Complex m_csqrt(double _Complex z) {
+  if (!g_math_mode) return csqrt(z);
+  const double re = creal(z), im = cimag(z);
+  if (im == 0.0) {
+    if (re < 0.0) return CMPLX(0.0, copysign(sqrt(-re), im));
+    return CMPLX(fabs(sqrt(re)), copysign(0.0, im));
+  }
+  if (re == 0.0) {
+    const double r = sqrt(0.5 * fabs(im));
+    return CMPLX(r, copysign(r, im));
+  }
+  const double d = g_math.hypot(re, im);
+  double r, s2;
+  if (re > 0.0) {
+    r = sqrt(0.5 * (d + re));
+    s2 = 0.5 * (im / r);
+  } else {
+    s2 = sqrt(0.5 * (d - re));
+    r = fabs(0.5 * (im / s2));
+  }
+  return CMPLX(r, copysign(s2, im));
+}
+
+/* ---------------------------------------------------------------------- */
 /* Cash-Karp tableau exactly as typed in shoot.f:1306-1319 / 1381-1394      */
 /* (column-major DATA fill: b(m,k) below is b[k-1][m-1]).                   */
 /* ---------------------------------------------------------------------- */
@@ -372,11 +441,11 @@ static zc osr_inprod(const osr_state *s, const zc *v1, const zc *v2) {
  * matrix (shoot.f:645-657).  z overwrites Uk.  P is [2][2] as P(j,i). */
 static void osr_gs(const osr_state *s, zc Uk[2][4], zc P[2][2]) {
   zc z[2][4], eta[4], w[2];
-  w[0] = csqrt(osr_inprod(s, Uk[0], Uk[0]));
+  w[0] = m_csqrt(osr_inprod(s, Uk[0], Uk[0]));
   for (int i = 0; i < 4; ++i) z[0][i] = Uk[0][i] / w[0];
   for (int i = 0; i < 4; ++i) eta[i] = Uk[1][i];
   for (int i = 0; i < 4; ++i) eta[i] = eta[i] - osr_inprod(s, Uk[1], z[0]) * z[0][i];
-  w[1] = csqrt(osr_inprod(s, eta, eta));
+  w[1] = m_csqrt(osr_inprod(s, eta, eta));
   for (int i = 0; i < 4; ++i) z[1][i] = eta[i] / w[1];
   if (P) {
     P[0][0] = 1.0 / w[0];
@@ -437,12 +506,12 @@ int osr_shoot(osr_state *s, osr_result *res, double *history, int history_cap,
   int status = 1;
 
   for (;;) {
-    double dc = cm1_defined ? cabs(*ev - cm1) : 1.0;
+    double dc = cm1_defined ? m_cabs(*ev - cm1) : 1.0;
     int go;
     if (flow == OSR_FLOW_CONTEBL)
-      go = ((cabs(err) >= errtol) || (dc >= eigtol)) && (icount <= maxcount);
+      go = ((m_cabs(err) >= errtol) || (dc >= eigtol)) && (icount <= maxcount);
     else
-      go = (cabs(err) >= errtol) && (icount <= maxcount) && (dc >= eigtol);
+      go = (m_cabs(err) >= errtol) && (icount <= maxcount) && (dc >= eigtol);
     if (!go) {
       if (icount <= maxcount) status = 0;
       break;
@@ -453,13 +522,13 @@ int osr_shoot(osr_state *s, osr_result *res, double *history, int history_cap,
       /* BL_IC contebl.f:269-279; orrsom.f:211-221; orrspace.f:285-295 */
       zc alpha = s->alpha;
       zc cc = (flow == OSR_FLOW_ORRSPACE) ? s->omega / alpha : s->c;
-      zc ea = cexp(-alpha * tf);
+      zc ea = m_cexp(-alpha * tf);
       U[0][0][0] = ea;
       U[0][0][1] = (-alpha) * ea;
       U[0][0][2] = (alpha * alpha) * ea;
       U[0][0][3] = (-(alpha * alpha * alpha)) * ea;
-      zc g = csqrt(alpha * alpha + CMPLX(0.0, 1.0) * alpha * s->Re * (1.0 - cc));
-      zc eg = cexp(-g * tf);
+      zc g = m_csqrt(alpha * alpha + CMPLX(0.0, 1.0) * alpha * s->Re * (1.0 - cc));
+      zc eg = m_cexp(-g * tf);
       U[0][1][0] = eg;
       U[0][1][1] = (-g) * eg;
       U[0][1][2] = (g * g) * eg;
@@ -482,31 +551,31 @@ int osr_shoot(osr_state *s, osr_result *res, double *history, int history_cap,
       }
       /* orthonormality test.  (mi,mj) = (1,2) and (2,1) give the same three
        * numbers with aa/bb swapped; aa*bb commutes, so one evaluation. */
-      double aa = cabs(osr_inprod(s, U[k][0], U[k][0]));
-      double bb = cabs(osr_inprod(s, U[k][1], U[k][1]));
-      double cc12 = cabs(osr_inprod(s, U[k][0], U[k][1]));
-      double cc21 = cabs(osr_inprod(s, U[k][1], U[k][0]));
+      double aa = m_cabs(osr_inprod(s, U[k][0], U[k][0]));
+      double bb = m_cabs(osr_inprod(s, U[k][1], U[k][1]));
+      double cc12 = m_cabs(osr_inprod(s, U[k][0], U[k][1]));
+      double cc21 = m_cabs(osr_inprod(s, U[k][1], U[k][0]));
       int norm = 0;
       if (flow == OSR_FLOW_CONTEBL) { /* shoot.f:593-606 */
         double ta = pi * s->testalpha / 180.0;
         double x1 = cc12 / sqrt(aa * bb), x2 = cc21 / sqrt(bb * aa);
         if (x1 > 1.0) x1 = 1.0; /* D-5 */
         if (x2 > 1.0) x2 = 1.0;
-        if (acos(x1) < ta) norm = 1;
-        if (acos(x2) < ta) norm = 1;
+        if (m_acos(x1) < ta) norm = 1;
+        if (m_acos(x2) < ta) norm = 1;
       } else if (flow == OSR_FLOW_CONTE) { /* shoot.f:64-65, 132-151 */
         double ta = 10.0 * pi / 180.0;
         double x1 = cc12 / sqrt(aa * bb), x2 = cc21 / sqrt(bb * aa);
         if (x1 > 1.0) x1 = 1.0;
         if (x2 > 1.0) x2 = 1.0;
-        if (acos(x1) <= ta) norm = 1;
-        if (acos(x2) <= ta) norm = 1;
+        if (m_acos(x1) <= ta) norm = 1;
+        if (m_acos(x2) <= ta) norm = 1;
       } else if (flow == OSR_FLOW_ORRSOM) { /* orrsom.f:292-302 */
         double x1 = cc12 / sqrt(aa * bb), x2 = cc21 / sqrt(bb * aa);
         if (x1 > 1.0) x1 = 1.0;
         if (x2 > 1.0) x2 = 1.0;
-        if (180.0 * acos(x1) / pi <= s->testalpha) norm = 1;
-        if (180.0 * acos(x2) / pi <= s->testalpha) norm = 1;
+        if (180.0 * m_acos(x1) / pi <= s->testalpha) norm = 1;
+        if (180.0 * m_acos(x2) / pi <= s->testalpha) norm = 1;
       } else { /* orrspace.f:350-358 */
         if (cc12 / sqrt(aa * bb) > s->testalpha) norm = 1;
         if (cc21 / sqrt(bb * aa) > s->testalpha) norm = 1;
@@ -542,8 +611,8 @@ int osr_shoot(osr_state *s, osr_result *res, double *history, int history_cap,
       zc At = qt * err - qt * (1. + qt) * errm1 + qt * qt * errm2;
       zc Bt = (2. * qt + 1.) * err - (1. + qt) * (1. + qt) * errm1 + qt * qt * errm2;
       zc Ct = (1. + qt) * err;
-      zc D = csqrt(Bt * Bt - 4. * At * Ct);
-      if (cabs(Bt + D) > cabs(Bt - D))
+      zc D = m_csqrt(Bt * Bt - 4. * At * Ct);
+      if (m_cabs(Bt + D) > m_cabs(Bt - D))
         *ev = ctemp - (ctemp - cm1) * 2. * Ct / (Bt + D);
       else
         *ev = ctemp - (ctemp - cm1) * 2. * Ct / (Bt - D);
@@ -571,8 +640,8 @@ int osr_shoot(osr_state *s, osr_result *res, double *history, int history_cap,
   res->status = status;
   res->eig[0] = creal(ctemp); res->eig[1] = cimag(ctemp);
   res->next[0] = creal(*ev); res->next[1] = cimag(*ev);
-  res->abserr = cabs(err);
-  res->absdc = cm1_defined ? cabs(*ev - cm1) : 0.0;
+  res->abserr = m_cabs(err);
+  res->absdc = cm1_defined ? m_cabs(*ev - cm1) : 0.0;
   if (flow == OSR_FLOW_ORRSPACE) s->alpha = ctemp; /* orrspace.f:494 */
 
   /* ---- second pass: eigenfunction (shoot.f:762-810; conte shoot.f:338-385) */
@@ -604,7 +673,7 @@ int osr_shoot(osr_state *s, osr_result *res, double *history, int history_cap,
         for (int m = 0; m < 2; ++m) y[k][i] = y[k][i] + U[k][m][i] * B[q - 1][m];
       }
       /* D-2: the DO index is left at n+1, so the scan reads y(n+1,k) == y(1,k+1) */
-      if (cabs(y[k + 1][0]) > cabs(vmax)) vmax = y[k + 1][0];
+      if (m_cabs(y[k + 1][0]) > m_cabs(vmax)) vmax = y[k + 1][0];
     }
     for (k = 0; k <= nstep; ++k)
       for (int i = 0; i < 4; ++i) {

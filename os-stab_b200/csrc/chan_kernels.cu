@@ -502,16 +502,29 @@ size_t chan_smem_bytes(int n) {
   return chan_fixed_smem(n) + (chan_matrix_in_smem(n) ? sizeof(double2) * (size_t)n * n : 0);
 }
 
-// Convergence of the (linear) inverse iteration at a fixed shift: successive changes of omega contract by
-// rho = dl / dl_prev, so after a change dl the next one is ~ rho dl and the current estimate is off by
-// ~ rho dl / (1 - rho).  Stop when the change is below the goal or -- one solve earlier -- when the
-// predicted next change is (with a factor 2 of margin, fast contraction only); the reported delta is then
-// the prediction.
-__device__ __forceinline__ bool inv_iter_converged(int it, double &dl, double dl_prev, double goal) {
-  if (it > 0 && dl <= goal) return true;
-  if (it >= 2 && dl_prev < 1.0e299) {
-    const double rho = dl / dl_prev;
-    if (rho < 0.05 && dl * rho <= 0.5 * goal) { dl *= rho; return true; }
+// Convergence of the (linear) inverse iteration at a fixed shift.  Successive changes of omega contract by
+// rho = d0 / d1, so after a change d0 the remaining error of the current estimate is ~ d0 rho / (1 - rho).
+// The iteration stops when the measured change is below the goal, or -- one solve earlier -- when that
+// geometric-series estimate is (with a factor 2 of margin).  The extrapolation is only trusted in the
+// asymptotic regime: three measured changes between successive estimates (the first "change", measured
+// against the shift, does not count), two contraction ratios that are both fast (< 0.05) and do not
+// deteriorate (rho <= 2 rho_prev).  `est` is what the kernels report as delta: the last MEASURED change, or,
+// after an early stop, the remaining-error estimate.  OSB_NO_EARLY_STOP=1 (a.early = 0) disables the
+// extrapolation (tests compare the two).
+struct ConvTrack {
+  double d0, d1, d2;  // the last three measured changes of omega, d0 newest
+};
+__device__ __forceinline__ void conv_reset(ConvTrack &t) { t.d0 = t.d1 = t.d2 = 1.0e300; }
+__device__ __forceinline__ bool conv_push(ConvTrack &t, int it, double change, double goal, int early, double *est) {
+  t.d2 = t.d1; t.d1 = t.d0; t.d0 = change;
+  *est = change;
+  if (it > 0 && change <= goal) return true;
+  if (early && it >= 3 && t.d2 < 1.0e299) {
+    const double rho = t.d0 / t.d1, rho1 = t.d1 / t.d2;
+    if (rho < 0.05 && rho1 < 0.05 && rho <= 2.0 * rho1) {
+      const double rem = t.d0 * rho / (1.0 - rho);
+      if (rem <= 0.5 * goal) { *est = rem; return true; }
+    }
   }
   return false;
 }
@@ -519,10 +532,12 @@ __device__ __forceinline__ bool inv_iter_converged(int it, double &dl, double dl
 // Right inverse iteration with the current LU: x (unit 2-norm, shared) in/out.
 // Returns the eigenvalue estimate after up to maxit iterations; *delta = last change.
 __device__ double2 inverse_iterate(const double2 *M, int n, const double *D2, const PencilCoef &p,
-                                   double2 sigma, ChanShared &s, int maxit, double tol, double *delta,
+                                   double2 sigma, ChanShared &s, int maxit, double tol, int early, double *delta,
                                    int *iters) {
   double2 om = sigma;
-  double dl = 1.0e300, dl_prev = 1.0e300;
+  ConvTrack ct;
+  conv_reset(ct);
+  double est = 1.0e300;
   int it = 0;
   // maxit is the nominal budget of one shift.  A dense refactorisation costs 6-9 solves, so when
   // the budget is used up the iteration goes on (up to 3 budgets) as long as the observed
@@ -548,17 +563,16 @@ __device__ double2 inverse_iterate(const double2 *M, int n, const double *D2, co
     const double rn = rsqrt(yy.x);
     for (int i = threadIdx.x; i < n; i += blockDim.x) s.x[i] = make_double2(s.y[i].x * rn, s.y[i].y * rn);
     __syncthreads();
-    dl_prev = dl;
-    dl = hypot(om_new.x - om.x, om_new.y - om.y);
+    const double change = hypot(om_new.x - om.x, om_new.y - om.y);
     om = om_new;
     const double goal = tol * hypot(om.x, om.y);
-    if (inv_iter_converged(it, dl, dl_prev, goal)) { ++it; break; }
+    if (conv_push(ct, it, change, goal, early, &est)) { ++it; break; }
     if (it + 1 >= maxit) {
-      const double rho = dl / dl_prev;
-      if (!(rho < 0.5) || !(dl > 0.0) || log(goal / dl) / log(rho) > 6.0) { ++it; break; }
+      const double rho = ct.d0 / ct.d1;
+      if (!(rho < 0.5) || !(ct.d0 > 0.0) || log(goal / ct.d0) / log(rho) > 6.0) { ++it; break; }
     }
   }
-  *delta = dl;
+  *delta = est;
   *iters = it;
   return om;
 }
@@ -573,9 +587,10 @@ struct ChanArgs {
   const double *Re;      // [ninst]
   const double2 *sigma;  // [ninst] shifts
   int outer, inner;      // re-shift rounds, iterations per round
+  int early;             // allow the one-solve-early stop of conv_push
   double tol;
   double2 *omega;        // [ninst]
-  double *delta;         // [ninst] last |d omega|
+  double *delta;         // [ninst] error estimate of omega: last measured change, or conv_push's remaining-error estimate
   int32_t *iters;        // [ninst] total inverse iterations
   double2 *evec;         // optional [ninst][n+2] (grid 0..N, zeros at the walls), max-modulus normalised
 };
@@ -615,7 +630,7 @@ __device__ __forceinline__ void chan_eig_body(const ChanArgs &a) {
       PROF_ADD(0);
       cta_lu(M, n, s.ipiv, s.panel, s.red);
       int it = 0;
-      om = inverse_iterate(M, n, a.D2, p, sigma, s, a.inner, a.tol, &dl, &it);
+      om = inverse_iterate(M, n, a.D2, p, sigma, s, a.inner, a.tol, a.early, &dl, &it);
       total += it;
       if (dl <= a.tol * hypot(om.x, om.y)) break;
       sigma = om;  // re-shift (Rayleigh-quotient style) and refactorise
@@ -949,6 +964,7 @@ struct BandArgs {
   const double *Re;
   const double2 *sigma;
   int outer, inner;
+  int early;       // allow the one-solve-early stop of conv_push
   double tol;
   double2 *omega;
   double *delta;
@@ -1037,6 +1053,8 @@ __global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constan
     }
     // ---- inverse iteration
     int it = 0;
+    ConvTrack ct;
+    conv_reset(ct);
     for (; it < a.inner; ++it) {
       // y = B x = b2 D2 x + b0 x   (D2 has half bandwidth 2)
       for (int r = 0; r < n; ++r) {
@@ -1093,10 +1111,9 @@ __global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constan
         const double2 v = y[(size_t)i * S];
         x[(size_t)i * S] = make_double2(v.x * rn, v.y * rn);
       }
-      const double dl_prev = dl;
-      dl = hypot(om_new.x - om.x, om_new.y - om.y);
+      const double change = hypot(om_new.x - om.x, om_new.y - om.y);
       om = om_new;
-      if (inv_iter_converged(it, dl, dl_prev, a.tol * hypot(om.x, om.y))) { ++it; break; }
+      if (conv_push(ct, it, change, a.tol * hypot(om.x, om.y), a.early, &dl)) { ++it; break; }
     }
     total += it;
     if (dl <= a.tol * hypot(om.x, om.y)) break;
@@ -1315,6 +1332,8 @@ __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(con
     // ================= inverse iteration =================
     bool inner_on = act;
     int it = 0;
+    ConvTrack ct;
+    conv_reset(ct);
     for (int step = 0; step < a.inner; ++step) {
       if (!__any_sync(0xffffffffu, inner_on)) break;
       // ---- y = B x = b2 D2 x + b0 x (D2: half bandwidth 2), all lanes, one group after the other
@@ -1454,11 +1473,10 @@ __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(con
       __syncwarp();
       if (inner_on) {
         const double2 om_new = cadd2(sigma, make_double2(myyx / myyy, myyxi / myyy));
-        const double dl_prev = dl;
-        dl = hypot(om_new.x - om.x, om_new.y - om.y);
+        const double change = hypot(om_new.x - om.x, om_new.y - om.y);
         om = om_new;
         it = step + 1;
-        if (inv_iter_converged(step, dl, dl_prev, a.tol * hypot(om.x, om.y))) inner_on = false;
+        if (conv_push(ct, step, change, a.tol * hypot(om.x, om.y), a.early, &dl)) inner_on = false;
       }
       PROF_ADD(0);
     }
@@ -1510,6 +1528,7 @@ cudaError_t launch_chan_fd_banded(int n, const double *D2, const double *D4, con
   a.n = n; a.D2 = D2; a.D4 = D4; a.u = u; a.d2u = d2u; a.band24 = band24; a.ninst = ninst; a.alpha = alpha; a.Re = Re;
   a.sigma = sigma; a.outer = outer; a.inner = inner; a.tol = tol; a.omega = omega; a.delta = delta; a.iters = iters;
   a.evec = evec;
+  a.early = getenv("OSB_NO_EARLY_STOP") ? 0 : 1;
   double2 *w = (double2 *)work;
   const size_t N1 = (size_t)ninst * n;
   a.U = w; a.L = w + N1 * BW; a.x = w + N1 * (BW + BKL); a.y = w + N1 * (BW + BKL + 1);
@@ -1569,6 +1588,7 @@ struct NeutralArgs {
   const double2 *sigma0;  // [ninst] eigenvalue at alpha0 (from the scan)
   double sfac, tol;
   int maxit;
+  int early;              // allow the one-solve-early stop of conv_push
   double *alpha_out;      // [ninst] nalpha after the last step
   double2 *omega_out;     // [ninst]
   int32_t *steps;         // [ninst]
@@ -1596,7 +1616,7 @@ __global__ void __launch_bounds__(CH_THREADS) chan_neutral_kernel(const __grid_c
         assemble_shifted(M, n, a.D2, a.D4, a.u, a.d2u, p, sigma);
         cta_lu(M, n, s.ipiv, s.panel, s.red);
         int k = 0;
-        ev = inverse_iterate(M, n, a.D2, p, sigma, s, 8, 1.0e-14, &dl, &k);
+        ev = inverse_iterate(M, n, a.D2, p, sigma, s, 8, 1.0e-14, a.early, &dl, &k);
         if (dl <= 1.0e-14 * hypot(ev.x, ev.y)) break;
         sigma = ev;
       }
@@ -1837,10 +1857,12 @@ __device__ void w_start_vector(double2 *x, int n) {
 }
 
 __device__ double2 w_inverse_iterate(const WarpShared &s, int n, const double *D2, const PencilCoef &p, double2 sigma,
-                                     int maxit, double tol, double *delta, int *iters) {
+                                     int maxit, double tol, int early, double *delta, int *iters) {
   const int lane = threadIdx.x & 31;
   double2 om = sigma;
   double dl = 1.0e300;
+  ConvTrack ct;
+  conv_reset(ct);
   int it = 0;
   for (; it < maxit; ++it) {
     w_d2_matvec(D2, n, s.x, s.y, false);
@@ -1858,10 +1880,9 @@ __device__ double2 w_inverse_iterate(const WarpShared &s, int n, const double *D
     const double rn = rsqrt(yy.x);
     for (int i = lane; i < n; i += 32) s.x[i] = make_double2(s.y[i].x * rn, s.y[i].y * rn);
     __syncwarp();
-    const double dl_prev = dl;
-    dl = hypot(om_new.x - om.x, om_new.y - om.y);
+    const double change = hypot(om_new.x - om.x, om_new.y - om.y);
     om = om_new;
-    if (inv_iter_converged(it, dl, dl_prev, tol * hypot(om.x, om.y))) { ++it; break; }
+    if (conv_push(ct, it, change, tol * hypot(om.x, om.y), early, &dl)) { ++it; break; }
   }
   *delta = dl;
   *iters = it;
@@ -1883,7 +1904,7 @@ __global__ void __launch_bounds__(32) chan_eig_warp_kernel(const __grid_constant
       w_assemble(s.M, n, a.D2, a.D4, a.u, a.d2u, p, sigma);
       w_lu(s.M, n, s.ipiv);
       int it = 0;
-      om = w_inverse_iterate(s, n, a.D2, p, sigma, a.inner, a.tol, &dl, &it);
+      om = w_inverse_iterate(s, n, a.D2, p, sigma, a.inner, a.tol, a.early, &dl, &it);
       total += it;
       if (dl <= a.tol * hypot(om.x, om.y)) break;
       sigma = om;
@@ -1929,7 +1950,7 @@ __global__ void __launch_bounds__(32) chan_neutral_warp_kernel(const __grid_cons
         w_assemble(s.M, n, a.D2, a.D4, a.u, a.d2u, p, sigma);
         w_lu(s.M, n, s.ipiv);
         int k = 0;
-        ev = w_inverse_iterate(s, n, a.D2, p, sigma, 8, 1.0e-14, &dl, &k);
+        ev = w_inverse_iterate(s, n, a.D2, p, sigma, 8, 1.0e-14, a.early, &dl, &k);
         if (dl <= 1.0e-14 * hypot(ev.x, ev.y)) break;
         sigma = ev;
       }
@@ -2075,6 +2096,7 @@ cudaError_t launch_chan_eig(int n, const double *D2, const double *D4, const dou
   a.n = n; a.D2 = D2; a.D4 = D4; a.u = u; a.d2u = d2u; a.work = work; a.ninst = ninst;
   a.alpha = alpha; a.Re = Re; a.sigma = sigma; a.outer = outer; a.inner = inner; a.tol = tol;
   a.omega = omega; a.delta = delta; a.iters = iters; a.evec = evec;
+  a.early = getenv("OSB_NO_EARLY_STOP") ? 0 : 1;
   if (use_warp_kernels(n)) chan_eig_warp_kernel<<<grid, 32, smem, st>>>(a);
   else if (use_big_kernel(n)) chan_eig_kernel_big<<<grid, CH_THREADS_BIG, smem, st>>>(a);
   else if (use_small_kernel(n)) chan_eig_kernel_small<<<grid, CH_THREADS_SMALL, smem, st>>>(a);
@@ -2091,6 +2113,7 @@ cudaError_t launch_chan_neutral(int n, const double *D2, const double *D4, const
   a.n = n; a.D2 = D2; a.D4 = D4; a.u = u; a.d2u = d2u; a.work = work; a.ninst = ninst;
   a.Re = Re; a.alpha0 = alpha0; a.sigma0 = sigma0; a.sfac = sfac; a.tol = tol; a.maxit = maxit;
   a.alpha_out = alpha_out; a.omega_out = omega_out; a.steps = steps; a.status = status; a.trace = trace;
+  a.early = getenv("OSB_NO_EARLY_STOP") ? 0 : 1;
   if (use_warp_kernels(n)) chan_neutral_warp_kernel<<<grid, 32, smem, st>>>(a);
   else chan_neutral_kernel<<<grid, CH_THREADS, smem, st>>>(a);
   return cudaGetLastError();

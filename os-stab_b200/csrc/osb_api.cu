@@ -18,6 +18,7 @@ using namespace osb;
 struct osb_ctx {
   std::vector<int> devices;
   std::vector<cudaStream_t> streams;
+  std::vector<cudaMemPool_t> pools;  // private stream-ordered pools, one per device (Scratch)
   std::string err;
   int64_t launches = 0;
 };
@@ -119,6 +120,8 @@ int fill_args(osb_ctx *ctx, const osb_shoot_opts *o, ShootArgs *a, int *analytic
   a->strict = r.strict;
   a->first_perturb = r.first_perturb;
   a->show_updated = r.show_updated;
+  a->flow = o->flow;
+  a->testalpha = o->testalpha;
   a->thr = norm_threshold(o->flow, o->testalpha);
   const double h = (o->ymax - o->ymin) / (double)o->nstep;  // shoot.f:471
   a->hs = (o->flow == OSB_FLOW_CONTE) ? h : -h;
@@ -155,6 +158,7 @@ namespace osb {
 int ctx_fail(osb_ctx *ctx, int code, const std::string &msg) { return fail(ctx, code, msg); }
 int ctx_device(const osb_ctx *ctx, int slot) { return ctx->devices[slot]; }
 void ctx_count_launch(osb_ctx *ctx, int n) { ctx->launches += n; }
+cudaMemPool_t ctx_pool(const osb_ctx *ctx, int slot) { return ctx->pools[slot]; }
 }  // namespace osb
 
 extern "C" {
@@ -181,13 +185,27 @@ int osb_create_multi(osb_ctx **out, int ndev, const int *devices) {
     cudaStream_t s;
     if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) return OSB_E_CUDA;
     c->streams.push_back(s);
-    // keep stream-ordered allocations cached between calls (the default pool hands
-    // memory back to the driver at every synchronisation)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) {
-      uint64_t keep = ~0ull;
-      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    // A private pool per context and device keeps stream-ordered scratch cached between calls (a pool
+    // hands memory back to the driver at every synchronisation unless its release threshold says
+    // otherwise) without changing the device's DEFAULT pool, which other allocators of the process share.
+    cudaMemPoolProps props;
+    memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = d;
+    cudaMemPool_t pool = nullptr;
+    if (cudaMemPoolCreate(&pool, &props) != cudaSuccess) {
+      for (size_t i = 0; i < c->streams.size(); ++i) {
+        cudaSetDevice(c->devices[i]);
+        cudaStreamDestroy(c->streams[i]);
+        if (i < c->pools.size()) cudaMemPoolDestroy(c->pools[i]);
+      }
+      return OSB_E_CUDA;
     }
+    uint64_t keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    c->pools.push_back(pool);
   }
   *out = c.release();
   return OSB_OK;
@@ -201,6 +219,8 @@ int osb_destroy(osb_ctx *ctx) {
     cudaSetDevice(ctx->devices[i]);
     cudaStreamSynchronize(ctx->streams[i]);
     cudaStreamDestroy(ctx->streams[i]);
+    cudaMemPoolTrimTo(ctx->pools[i], 0);
+    cudaMemPoolDestroy(ctx->pools[i]);
   }
   delete ctx;
   return OSB_OK;
@@ -266,7 +286,7 @@ int osb_profile_blasius(osb_ctx *ctx, int variant, int integrator, int nbl, doub
     ProfileDev &d = p->dev[i];
     cudaStream_t st = ctx->streams[i];
     OSB_CUDA(ctx, cudaSetDevice(d.device));
-    Scratch scr(d.device, st);
+    Scratch scr(d.device, st, ctx->pools[i]);
     double *work = nullptr, *par = nullptr;
     int32_t *np = nullptr;
     OSB_CUDA(ctx, scr.alloc(&work, blasius_scratch_doubles(nbl, 1) * sizeof(double)));
@@ -299,7 +319,7 @@ int osb_profile_blasius_batch(osb_ctx *ctx, int variant, int integrator, int nbl
   cudaStream_t st = ctx->streams[0];
   OSB_CUDA(ctx, cudaSetDevice(ctx->devices[0]));
   const size_t n2 = (size_t)nbl + 2;
-  Scratch scr(ctx->devices[0], st);
+  Scratch scr(ctx->devices[0], st, ctx->pools[0]);
   double *tab = nullptr, *work = nullptr, *par = nullptr;
   int32_t *np = nullptr;
   OSB_CUDA(ctx, scr.alloc(&tab, 5 * n2 * nprof * sizeof(double)));
@@ -368,7 +388,7 @@ int osb_profile_shift(osb_ctx *ctx, const osb_profile *prof, double uc, osb_prof
   for (size_t i = 0; i < ctx->devices.size(); ++i) {
     cudaStream_t st = ctx->streams[i];
     OSB_CUDA(ctx, cudaSetDevice(q->dev[i].device));
-    Scratch scr(q->dev[i].device, st);
+    Scratch scr(q->dev[i].device, st, ctx->pools[i]);
     double *work = nullptr;
     OSB_CUDA(ctx, scr.alloc(&work, 2 * ((size_t)p0.nbl + 2) * sizeof(double)));
     OSB_CUDA(ctx, launch_shift_profile(p0.nbl, uc, prof->dev[i].tables, q->dev[i].tables, work, st));
@@ -420,7 +440,7 @@ static int make_stage_table(osb_ctx *ctx, size_t i, Scratch &scr, const osb_shoo
                             const osb_profile *prof, double2 **tab) {
   cudaStream_t st = ctx->streams[i];
   size_t n = (size_t)o->nstep * stages_per_step(o->integrator);
-  OSB_CUDA(ctx, cudaMallocAsync(tab, n * sizeof(double2), st));
+  OSB_CUDA(ctx, scr.alloc(tab, n * sizeof(double2)));  // released with the call's other scratch
   OSB_CUDA(ctx, launch_stage_table(prof->dev[i], o->flow, o->integrator, o->nstep, o->ymin, o->ymax, *tab, st));
   ctx->launches++;
   return OSB_OK;
@@ -442,7 +462,7 @@ int osb_shoot_temporal_dev(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_p
   if (npts == 0) return OSB_OK;
   OSB_CUDA(ctx, cudaSetDevice(ctx->devices[0]));
   cudaStream_t st = ctx->streams[0];
-  Scratch scr(ctx->devices[0], st);
+  Scratch scr(ctx->devices[0], st, ctx->pools[0]);
   double2 *tab = nullptr;
   rc = make_stage_table(ctx, 0, scr, opts, prof, &tab);
   if (rc) return rc;
@@ -510,7 +530,7 @@ int osb_shoot_temporal(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profi
     if (n <= 0) continue;
     cudaStream_t st = ctx->streams[d];
     OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
-    guards[d].reset(new Scratch(ctx->devices[d], st));
+    guards[d].reset(new Scratch(ctx->devices[d], st, ctx->pools[d]));
     Scratch &scr = *guards[d];
     OSB_CUDA(ctx, scr.alloc(&b.alpha, n * 2 * sizeof(double)));
     OSB_CUDA(ctx, scr.alloc(&b.Re, n * sizeof(double)));
@@ -596,7 +616,7 @@ int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_
     if (n <= 0) continue;
     cudaStream_t st = ctx->streams[d];
     OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
-    guards[d].reset(new Scratch(ctx->devices[d], st));
+    guards[d].reset(new Scratch(ctx->devices[d], st, ctx->pools[d]));
     Scratch &scr = *guards[d];
     // in: Re[n], domega[n], omega0[2n], alpha0[2n]
     OSB_CUDA(ctx, scr.alloc(&b.in, n * 6 * sizeof(double)));
@@ -743,7 +763,7 @@ static int eigfun_chunk(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_prof
                         const double *eig, double *y, double *vmax, int32_t *qend) {
   cudaStream_t st = ctx->streams[0];
   const size_t n1 = (size_t)opts->nstep + 1;
-  Scratch scr(ctx->devices[0], st);
+  Scratch scr(ctx->devices[0], st, ctx->pools[0]);
   double *d_in = nullptr, *d_tq = nullptr;
   double2 *d_U = nullptr, *d_P = nullptr, *d_y = nullptr, *d_vmax = nullptr, *tab = nullptr;
   int32_t *d_q = nullptr;
@@ -818,7 +838,7 @@ int osb_measure_fp64_peak(osb_ctx *ctx, double ms_target, double *tflops, double
   cudaDeviceProp prop;
   OSB_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->devices[0]));
   const int threads = 256, blocks = prop.multiProcessorCount * 8;
-  Scratch scr(ctx->devices[0], st);
+  Scratch scr(ctx->devices[0], st, ctx->pools[0]);
   double *d_out = nullptr;
   OSB_CUDA(ctx, scr.alloc(&d_out, sizeof(double)));
   struct Events {

@@ -28,6 +28,7 @@ namespace osb {
 int ctx_fail(osb_ctx *ctx, int code, const std::string &msg);
 int ctx_device(const osb_ctx *ctx, int slot);
 void ctx_count_launch(osb_ctx *ctx, int n);
+cudaMemPool_t ctx_pool(const osb_ctx *ctx, int slot);
 }  // namespace osb
 
 struct osb_chan {
@@ -302,7 +303,7 @@ static int run_eig_chunk(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const s
                                       "; the FD operator has no such limit (banded kernels)");
   }
   if (!banded) CH_CUDA(ctx, chan_eig_grid(n, ninst, &grid, &smem));
-  Scratch scr(c->device, st);
+  Scratch scr(c->device, st, ctx_pool(ctx, 0));
   double *d_in = nullptr, *d_out = nullptr;
   double2 *work = nullptr, *d_evec = nullptr;
   int32_t *d_it = nullptr;
@@ -488,7 +489,7 @@ int osb_chan_spectrum(osb_ctx *ctx, const osb_chan *c, double Re, int64_t npts, 
     return ctx_fail(ctx, OSB_E_ARG, "N too large for the dense kernels (their 16-column LU panel lives in shared memory): "
                                     "limit N = " + std::to_string(chan_dense_max_n() + 1));
   CH_CUDA(ctx, chan_spectrum_grid(n, npts, &grid, &smem));
-  Scratch scr(c->device, st);
+  Scratch scr(c->device, st, ctx_pool(ctx, 0));
   double *d_in = nullptr;
   double2 *work = nullptr, *d_eig = nullptr;
   int32_t *d_st = nullptr;
@@ -557,7 +558,7 @@ int osb_chan_neutral(osb_ctx *ctx, const osb_chan *c, int64_t nRe, const double 
   size_t smem = 0;
   CH_CUDA(ctx, cudaSetDevice(c->device));
   CH_CUDA(ctx, chan_neutral_grid(n, nRe, &grid, &smem));
-  Scratch scr(c->device, st);
+  Scratch scr(c->device, st, ctx_pool(ctx, 0));
   double *d_in = nullptr, *d_out = nullptr, *d_trace = nullptr;
   double2 *work = nullptr;
   int32_t *d_i = nullptr;

@@ -23,10 +23,13 @@ struct ProfileDev {
 };
 
 // Stream-ordered scratch allocations of one call on one device; released on every exit
-// path (the error returns of the C ABI included) when the guard leaves scope.
+// path (the error returns of the C ABI included) when the guard leaves scope.  The memory
+// comes from the CONTEXT's private pool (osb_create_multi), not the device's default pool:
+// what the library caches between calls is returned to the driver by osb_destroy and no
+// process-wide pool attribute is touched.
 class Scratch {
  public:
-  Scratch(int device, cudaStream_t st) : device_(device), st_(st) {}
+  Scratch(int device, cudaStream_t st, cudaMemPool_t pool) : device_(device), st_(st), pool_(pool) {}
   Scratch(const Scratch &) = delete;
   Scratch &operator=(const Scratch &) = delete;
   ~Scratch() {
@@ -37,7 +40,7 @@ class Scratch {
   template <class T>
   cudaError_t alloc(T **out, size_t bytes) {
     void *q = nullptr;
-    cudaError_t e = cudaMallocAsync(&q, bytes ? bytes : 1, st_);
+    cudaError_t e = cudaMallocFromPoolAsync(&q, bytes ? bytes : 1, pool_, st_);
     if (e == cudaSuccess) ptrs_.push_back(q);
     *out = static_cast<T *>(q);
     return e;
@@ -46,6 +49,7 @@ class Scratch {
  private:
   int device_;
   cudaStream_t st_;
+  cudaMemPool_t pool_;
   std::vector<void *> ptrs_;
 };
 
@@ -65,6 +69,8 @@ struct ShootArgs {
   int strict;        // normalise when lhs > thr*rhs (1) or >= (0)
   int first_perturb; // 0: (Re c * .9999, Im c)   1: alpha*1.01 (both parts)
   int show_updated;  // history shows the updated c (conte) instead of ctemp
+  int flow;          // OSB_FLOW_* (the strict build evaluates RHS and orthonormality test as typed per driver)
+  double testalpha;  // as given (degrees / cosine bound); the fast kernels use thr
   double thr;        // Hermitian: cos^2(testalpha); analytic: testalpha^4
   double hs;         // signed step (-h for the BL flows, +h for the channel)
   double tf;         // where the initial condition is evaluated (ymax)
@@ -105,6 +111,8 @@ int stages_per_step(int integrator);
 // for temporal sweeps (nullptr: one thread per point for the whole solve)
 cudaError_t launch_shoot(const ShootArgs &a, int integrator, int analytic_inprod,
                          cudaStream_t st, int *nlaunch, unsigned long long *queue_counter = nullptr);
+// strict-parity build of K2 (shoot_strict.cu, -fmad=false); chosen by launch_shoot when OSB_STRICT is set
+cudaError_t launch_shoot_strict(const ShootArgs &a, int integrator, int analytic_inprod, cudaStream_t st);
 cudaError_t launch_eigfun(const EigfunArgs &a, int integrator, int analytic_inprod,
                           int64_t npts, cudaStream_t st);
 cudaError_t launch_blasius(int variant, int integrator, int nbl, double ymin, double ymax,

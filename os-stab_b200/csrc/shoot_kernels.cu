@@ -1051,6 +1051,12 @@ static cudaError_t launch_shoot_queue(const ShootArgs &a, int integrator, int an
 cudaError_t launch_shoot(const ShootArgs &a, int integrator, int analytic_inprod, cudaStream_t st,
                          int *nlaunch, unsigned long long *queue_counter) {
   if (a.nlines <= 0) return cudaSuccess;
+  // OSB_STRICT=1: the strict-parity build (reference operation order, no FMA; shoot_strict.cu) -- bit-identical
+  // to the CPU restatement of the reference, ~3x slower; a verification switch, never a default
+  if (getenv("OSB_STRICT")) {
+    if (nlaunch) *nlaunch += 1;
+    return launch_shoot_strict(a, integrator, analytic_inprod, st);
+  }
   // Which kernel (measured on B200, tools/bench_small_batches.py, config-5 points):
   //   <= 9472 lines      two lanes per line: 1.2-1.25x over one thread per line
   //   up to ~65k points  one thread per point: the GPU is not yet oversubscribed, compaction only costs

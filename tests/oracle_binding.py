@@ -17,8 +17,26 @@ FLOW_CONTEBL, FLOW_CONTE, FLOW_ORRSOM, FLOW_ORRSPACE = 0, 1, 2, 3
 INT_RK4, INT_CK45 = 0, 1
 
 
+PMATH_LIB = ROOT / "tests" / "_build" / "libpmath_host.so"
+
+
 def build():
     subprocess.run(["make", "-s", "-C", str(ROOT / "oracle")], check=True)
+
+
+def build_pmath():
+    """Host build (no FMA contraction) of the product's portable elementary functions, for osr_set_math."""
+    src = ROOT / "tests" / "pmath_host.c"
+    hdr = ROOT / "os-stab_b200" / "csrc" / "osb_pmath.h"
+    if (not PMATH_LIB.exists() or PMATH_LIB.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime)):
+        PMATH_LIB.parent.mkdir(exist_ok=True)
+        subprocess.run(["gcc", "-O2", "-std=gnu11", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+                        "-o", str(PMATH_LIB), str(src), "-lm"], check=True)
+    return C.CDLL(str(PMATH_LIB))
+
+
+class _OsrMath(C.Structure):
+    _fields_ = [("exp", C.c_void_p), ("sincos", C.c_void_p), ("hypot", C.c_void_p), ("acos", C.c_void_p)]
 
 
 class Oracle:
@@ -35,6 +53,24 @@ class Oracle:
         lib.osr_shoot_spatial_line.argtypes = [i, i, d, d, d, i, _dp, d, d, d, d, d, d, i, _dp, _ip, _ip, _ip]
         lib.osr_shoot_spatial_point.restype = i
         lib.osr_shoot_spatial_point.argtypes = [i, i, d, d, d, i, _dp, d, d, d, d, d, _dp, _ip, _dp, _dp]
+
+    def set_math(self, kind=None):
+        """Which elementary functions the shooting restatement uses: None = libm's complex cabs/csqrt/cexp
+        and acos, as the reference's build; "libm" = glibc's complex formulas restated over libm's real
+        exp/sincos/hypot/acos (must equal None bit for bit); "portable" = the same formulas over the
+        IEEE-only functions of osb_pmath.h that the CUDA strict build uses."""
+        if kind is None:
+            self.lib.osr_set_math(None)
+        elif kind == "libm":
+            self.lib.osr_set_math_libm()
+        elif kind == "portable":
+            pm = build_pmath()
+            self._pm = pm  # keep the library alive
+            m = _OsrMath(*[C.cast(getattr(pm, n), C.c_void_p).value for n in ("pmh_exp", "pmh_sincos", "pmh_hypot", "pmh_acos")])
+            self.lib.osr_set_math.argtypes = [C.POINTER(_OsrMath)]
+            self.lib.osr_set_math(C.byref(m))
+        else:
+            raise ValueError(kind)
 
     def solve_bl(self, variant=FLOW_CONTEBL, integrator=INT_CK45, nbl=1000, ymin=0.0, ymax=17.0, f2p=0.5, beta=0.0):
         """Returns (prof[5, nbl+2] = ydat,U,Uspl,d2U,d2Uspl zero padded, npass, f2p_last)."""

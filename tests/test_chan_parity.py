@@ -66,6 +66,31 @@ def test_orrfdchan_large_N(engine, oracle):
         assert rel(r["omega"], ref).max() < 1e-10, (N, rel(r["omega"], ref).max())
 
 
+@pytest.mark.parametrize("N", [256, 512])
+def test_fd_operator_on_the_dense_kernels(engine, oracle, N, monkeypatch):
+    """OSB_FD_DENSE=1 sends the FD operator through the dense complex LU (DMMA trailing update) instead of
+    the banded kernels: N=256 is the 256-thread two-per-SM kernel, N=512 the one-per-SM kernel (n > ~350,
+    config 4's largest size).  Against the oracle's inv(B)A + ZGEEV (orrfdchan.f:792-797) and against the
+    banded path, 1e-10 relative."""
+    alpha = np.array([0.76, 0.9, 1.0, 1.16])
+    ch = engine.chan(ob.DISC_FD, N)
+    banded = ch.solve(alpha, 1.0e4)
+    monkeypatch.setenv("OSB_FD_DENSE", "1")
+    dense = ch.solve(alpha, 1.0e4, want_evec=True)
+    dense_given = ch.solve(alpha, 1.0e4, sigma0=banded["omega"] * (1 + 1e-4))
+    monkeypatch.delenv("OSB_FD_DENSE")
+    bv = ch.solve(alpha, 1.0e4, want_evec=True)
+    ch.free()
+    c = ob.chan(ob.DISC_FD, N)
+    ref = np.array([c.solve_fd(a, 1.0e4)["omega"] for a in alpha])
+    c.close()
+    assert (dense["status"] == 0).all() and (dense_given["status"] == 0).all()
+    assert rel(dense["omega"], ref).max() < 1e-10, (N, rel(dense["omega"], ref).max())
+    assert rel(dense_given["omega"], ref).max() < 1e-10
+    assert rel(dense["omega"], banded["omega"]).max() < 1e-10
+    assert np.max(np.abs(dense["evec"] - bv["evec"])) < 1e-8
+
+
 def test_complex_alpha_and_given_shift(engine, oracle):
     """alpha_i != 0 (orrfdchan sweeps alpha_i too, orrfdchan.f:116-118) with a user shift."""
     ch = engine.chan(ob.DISC_FD, 64)
@@ -114,12 +139,13 @@ def test_orrncbl_neutral_point(engine, oracle):
     c.close()
 
 
-@pytest.mark.parametrize("N", [64, 128, 256])
+@pytest.mark.parametrize("N", [64, 128, 256, 512])
 def test_collocation_against_quad_arbiter(engine, oracle, N):
     """for Chebyshev collocation the reference's LAPACK routes are themselves
     inaccurate (ill-scaled pencil), so the fp64 oracle cannot arbitrate 1e-10.  The quad-precision
     arbiter solves the same discrete pencil to ~1e-25; the GPU path must be at least as close to
-    it as the reference's route, and within 1e-10 where fp64 allows (N = 64)."""
+    it as the reference's route, and within 1e-10 where fp64 allows (N = 64).  N = 512 (config 4's
+    largest size) runs the one-CTA-per-SM dense kernel (n > ~350)."""
     ch = engine.chan(ob.DISC_CHEB, N)
     r = ch.solve([1.0], 1.0e4)
     ch.free()
@@ -375,3 +401,29 @@ def test_banded_batches_are_chunked(engine, monkeypatch):
     ch.free()
     for k in ("omega", "evec", "iters", "status"):
         assert np.array_equal(whole[k], parts[k]), k
+
+
+@pytest.mark.parametrize("disc,N,route", [(ob.DISC_FD, 128, "banded"), (ob.DISC_FD, 128, "thread"), (ob.DISC_FD, 96, "dense"),
+                                          (ob.DISC_CHEB, 64, "warp"), (ob.DISC_CHEB, 200, "dense")])
+def test_early_stop_of_the_inverse_iteration(engine, disc, N, route, monkeypatch):
+    """The inverse iteration may stop one solve early when two agreeing contraction ratios predict a remaining
+    error below the tolerance (conv_push).  With the extrapolation switched off (OSB_NO_EARLY_STOP=1) every
+    point iterates until the MEASURED change is below 1e-14 |omega|; the early-stopped results must agree with
+    those to the tolerance the status word certifies (1e-12), and must not take more solves."""
+    if route == "thread":
+        monkeypatch.setenv("OSB_FD_THREAD", "1")
+    if route == "dense" and disc == ob.DISC_FD:
+        monkeypatch.setenv("OSB_FD_DENSE", "1")
+    alpha = np.linspace(0.76, 1.16, 64)
+    ch = engine.chan(disc, N)
+    seed = ch.solve(alpha[::9], 1.0e4)["omega"]
+    sig = np.interp(alpha, alpha[::9], seed.real) + 1j * np.interp(alpha, alpha[::9], seed.imag)
+    fast = ch.solve(alpha, 1.0e4, sigma0=sig)
+    monkeypatch.setenv("OSB_NO_EARLY_STOP", "1")
+    full = ch.solve(alpha, 1.0e4, sigma0=sig)
+    ch.free()
+    assert (fast["status"] == 0).all() and (full["status"] == 0).all()
+    d = rel(fast["omega"], full["omega"])
+    print(f"{route} N={N}: early-stop vs full max rel diff {d.max():.2e}; solves {fast['iters'].mean():.2f} vs {full['iters'].mean():.2f}")
+    assert d.max() <= 1e-12, d.max()
+    assert fast["iters"].sum() <= full["iters"].sum()

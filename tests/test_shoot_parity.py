@@ -565,6 +565,31 @@ def _free_bytes():
     return torch.cuda.mem_get_info(0)[0]
 
 
+def test_repeated_calls_do_not_leak_device_memory(osb):
+    """Every entry point that builds a stage table (temporal, spatial, eigenfunction, neutral search) releases
+    it with the call's other scratch: device memory stays flat over 1000 calls, and a destroyed context gives
+    its private pool back to the driver."""
+    eng = osb.Engine(0)
+    p = eng.solve_bl(osb.FLOW_CONTEBL, osb.INT_CK45, 1000, 0.0, 17.0, 0.5, 0.0)
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    opts.nstep = 4000  # 384 KB of stage table per call
+    opts.maxcount = 2
+    a, R, c = [0.179 * S2], [580.0 * S2], [complex(0.36413124, 0.79527387e-2)]
+    for _ in range(20):
+        eng.shoot_temporal(opts, p, a, R, c)
+    free0 = _free_bytes()
+    for k in range(1000):
+        eng.shoot_temporal(opts, p, a, R, c)
+        if k % 100 == 0:
+            eng.eigfun(opts, p, R, c, alpha=a)
+            eng.shoot_neutral(opts, p, R, [0.179 * S2], c, maxit=2)
+    assert free0 - _free_bytes() < 8 << 20, free0 - _free_bytes()
+    before = _free_bytes()
+    p.free()
+    eng.close()
+    assert _free_bytes() >= before
+
+
 def test_neutral_curve_by_secant_on_alpha(engine, osb, oracle, bl, bl_oracle):
     """osb_shoot_neutral (no reference counterpart): both branches of the Blasius neutral
     curve for 48 Reynolds numbers, started from the sign changes of a coarse grid.  Checks: Im c = 0
