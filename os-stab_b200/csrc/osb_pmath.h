@@ -10,7 +10,7 @@
  * either.  The strict build therefore evaluates them with the functions below: plain C, only IEEE
  * operations in a fixed order, accurate to ~1 ulp, compiled WITHOUT contraction on both sides
  * (nvcc -fmad=false for shoot_strict.cu; gcc -ffp-contract=off for the test-side copy that is handed
- * to the CPU oracle through osr_set_math).  With the same four functions on both sides the GPU
+ * to the CPU checker by the tests).  With the same four functions on both sides the GPU
  * eigenvalue iteration is bit-identical to the oracle's (tests/test_strict_parity.py); how little the
  * choice of libm matters is measured separately by swapping them in the oracle alone.
  *
