@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define OSB_VERSION 1
+#define OSB_VERSION 2
 
 /* error codes */
 #define OSB_OK 0
@@ -245,9 +245,19 @@ int osb_chan_tables(osb_ctx *ctx, const osb_chan *chan, double *eta, double *u, 
  *   alpha  [2*npts]; sigma0 [2*npts] optional shift guesses (NULL: a 16-shift scan
  *   over 0 < c_r < 1 per point picks the mode); omega [2*npts] out;
  *   evec   [npts*(N+1)*2] optional; iters [npts] inverse iterations; status [npts].
+ *   evec_adj [npts*(N+1)*2] optional: the LEFT (adjoint) eigenvector of the same mode -- the reference solves
+ *   with JOBVL = 'V' (orrfdchan.f:796, orrcolchan.f:461) and writes it as columns 4-5 of fort.11.  By inverse
+ *   iteration on the adjoint pencil, u <- (A - s B)^{-H} B^H u, zeros at the walls, in the form adj_form:
+ *     OSB_ADJ_PENCIL  u with u^H (A - w B) = 0 scaled so that u^H evec = 1: ZGEGV's left vector after the
+ *                     bi-orthonormalisation of orrcolchan.f:537-545
+ *     OSB_ADJ_INVBA   B^H u, the left eigenvector of inv(B) A with ZGEEV's normalisation (unit 2-norm, largest
+ *                     component real and positive): what orrfdchan.f:796 returns in `avec`
  */
+#define OSB_ADJ_PENCIL 0
+#define OSB_ADJ_INVBA 1
 int osb_chan_eig(osb_ctx *ctx, const osb_chan *chan, double Re, int64_t npts, const double *alpha,
-                 const double *sigma0, double *omega, double *evec, int32_t *iters, int32_t *status);
+                 const double *sigma0, double *omega, double *evec, double *evec_adj, int adj_form,
+                 int32_t *iters, int32_t *status);
 
 /*
  * The FULL spectrum of the interior pencil at each alpha: what SOLVE_ORR_SOM computes before it keeps one

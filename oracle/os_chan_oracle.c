@@ -311,9 +311,13 @@ static int eig_invBA(int m, zc *A, zc *B, zc *eval, zc *vl, zc *vr, int use_getr
  * spectrum (optional, 2*(N-1) doubles): all eigenvalues sorted by Im ascending.
  * evec (optional, 2*(N+1)): the eigenvector of the selected mode on the full
  * grid (zeros at 0 and N), normalised by its max-modulus component (orrfdchan.f:849-857).
+ * avec (optional, 2*(N+1)): columns 4-5 of fort.11 as orrfdchan.f:865-871 writes them: row j holds
+ * avec(j, ind(iloc)), ZGEEV's LEFT eigenvector of inv(B)A (unit 2-norm, largest component real) --
+ * NOT shifted onto the grid like the right vector (the reference pairs eta(j) with interior entry j)
+ * and read two entries past the N-1 that ZGEEV wrote, which are zeros of the static array.
  */
 int osr_chan_solve_fdstyle(const osr_chan *c, double alpha_re, double alpha_im, double Re,
-                           double *omega, double *spectrum, double *evec) {
+                           double *omega, double *spectrum, double *evec, double *avec) {
   const int n = c->n, m = n - 1;
   zc *A = (zc *)malloc(sizeof(zc) * (size_t)m * m), *B = (zc *)malloc(sizeof(zc) * (size_t)m * m);
   zc *eval = (zc *)malloc(sizeof(zc) * m), *vl = (zc *)malloc(sizeof(zc) * (size_t)m * m),
@@ -340,6 +344,13 @@ int osr_chan_solve_fdstyle(const osr_chan *c, double alpha_re, double alpha_im, 
     evec[0] = evec[1] = 0.0; evec[2 * n] = evec[2 * n + 1] = 0.0;
     for (int i = 0; i < m; ++i) { zc s = escale * v[i]; evec[2 * (i + 1)] = creal(s); evec[2 * (i + 1) + 1] = cimag(s); }
   }
+  if (avec && iloc >= 0) {
+    const zc *v = vl + (size_t)ind[iloc] * m;
+    for (int j = 0; j <= n; ++j) {
+      avec[2 * j] = j < m ? creal(v[j]) : 0.0;
+      avec[2 * j + 1] = j < m ? cimag(v[j]) : 0.0;
+    }
+  }
   free(A); free(B); free(eval); free(vl); free(vr); free(t1); free(t2); free(ind);
   return info;
 }
@@ -349,9 +360,12 @@ int osr_chan_solve_fdstyle(const osr_chan *c, double alpha_re, double alpha_im, 
  * alp/beta (0 when beta = 0), PIKSR2 by Im; spectrum: 2*(N+1) doubles sorted
  * ascending (index 0..N as the reference prints them, orrcolchan.f:505-513).
  * evec (optional): eigenvector `which` normalised by its max-modulus component.
+ * avec (optional, 2*(N+1)): ZGEGV's left eigenvector of the same mode scaled by 1/conj(zdotc(avec, evec))
+ * (orrcolchan.f:537-545), i.e. columns 4-5 of fort.11; dots (optional, 4 doubles): the two zdotc values the
+ * reference prints (orrcolchan.f:539,546) -- the first depends on LAPACK's normalisation of avec, the second is 1.
  */
 int osr_chan_solve_col(const osr_chan *c, double alpha_re, double alpha_im, double Re,
-                       double *spectrum, int which, double *evec) {
+                       double *spectrum, int which, double *evec, double *avec, double *dots) {
   const int n = c->n;
   int m = n + 1, info = 0, lwork = 64 * m;
   zc *A = (zc *)malloc(sizeof(zc) * (size_t)m * m), *B = (zc *)malloc(sizeof(zc) * (size_t)m * m);
@@ -376,6 +390,18 @@ int osr_chan_solve_col(const osr_chan *c, double alpha_re, double alpha_im, doub
     for (int i = 0; i < m; ++i) if (cabs(v[i]) > cabs(escale)) escale = v[i];
     escale = 1.0 / escale;
     for (int i = 0; i < m; ++i) { zc s = escale * v[i]; evec[2 * i] = creal(s); evec[2 * i + 1] = cimag(s); }
+    if (avec) {
+      const zc *a = vl + (size_t)ind[which] * m;
+      zc d1 = 0.0, d2 = 0.0;
+      for (int i = 0; i < m; ++i) d1 += conj(a[i]) * (escale * v[i]);  /* zdotc(avec, evec) */
+      const zc sc = 1.0 / conj(d1);
+      for (int i = 0; i < m; ++i) {
+        const zc t = sc * a[i];
+        avec[2 * i] = creal(t); avec[2 * i + 1] = cimag(t);
+        d2 += conj(t) * (escale * v[i]);
+      }
+      if (dots) { dots[0] = creal(d1); dots[1] = cimag(d1); dots[2] = creal(d2); dots[3] = cimag(d2); }
+    }
   }
   free(A); free(B); free(alp); free(beta); free(vl); free(vr); free(work); free(rwork); free(t2); free(ind); free(eval);
   return info;

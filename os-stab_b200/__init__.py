@@ -98,7 +98,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "osb_chan_bl_points": (C.c_int, [C.c_int, C.c_int, dbl, _dp]),
         "osb_chan_free": (C.c_int, [vp, vp]),
         "osb_chan_tables": (C.c_int, [vp, vp, _dp, _dp, _dp, _dp, _dp]),
-        "osb_chan_eig": (C.c_int, [vp, vp, dbl, i64, _dp, _dp, _dp, _dp, _ip, _ip]),
+        "osb_chan_eig": (C.c_int, [vp, vp, dbl, i64, _dp, _dp, _dp, _dp, _dp, C.c_int, _ip, _ip]),
         "osb_chan_spectrum": (C.c_int, [vp, vp, dbl, i64, _dp, _dp, _ip]),
         "osb_chan_neutral": (C.c_int, [vp, vp, i64, _dp, _dp, dbl, dbl, i32, _dp, _dp, _ip, _ip, _dp]),
     }
@@ -118,6 +118,7 @@ EXPORTED_SYMBOLS = (
 ).split()
 
 DISC_FD, DISC_CHEB, DISC_CHEB_NUM = 0, 1, 2
+ADJ_PENCIL, ADJ_INVBA = 0, 1
 
 
 def contebl_units(alpha, Re):
@@ -403,21 +404,26 @@ class Chan:
             self.engine.ctx, self.handle, *[out[k].ctypes.data_as(_dp) for k in ("eta", "u", "d2u", "D2", "D4")]))
         return out
 
-    def solve(self, alpha, Re, sigma0=None, want_evec=False):
-        """SOLVE_ORR_SOM for a batch of alpha (orrfdchan.f:116-121 hoisted into one call)."""
+    def solve(self, alpha, Re, sigma0=None, want_evec=False, want_adj=None):
+        """SOLVE_ORR_SOM for a batch of alpha (orrfdchan.f:116-121 hoisted into one call).
+        want_adj = ADJ_PENCIL | ADJ_INVBA also returns the left eigenvector in that form (include/osb.h)."""
         alpha = np.atleast_1d(np.asarray(alpha, dtype=np.complex128))
         n = alpha.size
         al = _cplx_pairs(alpha, n)
         sg = _cplx_pairs(np.atleast_1d(sigma0), n) if sigma0 is not None else None
         om = np.zeros(2 * n)
         ev = np.zeros(2 * n * (self.N + 1)) if want_evec else None
+        av = np.zeros(2 * n * (self.N + 1)) if want_adj is not None else None
         iters = np.zeros(n, dtype=np.int32)
         status = np.zeros(n, dtype=np.int32)
         self.engine._check(self.engine.lib.osb_chan_eig(
             self.engine.ctx, self.handle, float(Re), n, al.ctypes.data_as(_dp),
             sg.ctypes.data_as(_dp) if sg is not None else None, om.ctypes.data_as(_dp),
-            ev.ctypes.data_as(_dp) if want_evec else None, iters.ctypes.data_as(_ip), status.ctypes.data_as(_ip)))
+            ev.ctypes.data_as(_dp) if want_evec else None, av.ctypes.data_as(_dp) if av is not None else None,
+            int(want_adj or 0), iters.ctypes.data_as(_ip), status.ctypes.data_as(_ip)))
         r = dict(omega=om.view(np.complex128), iters=iters, status=status)
+        if av is not None:
+            r["avec"] = av.view(np.complex128).reshape(n, self.N + 1)
         if want_evec:
             r["evec"] = ev.view(np.complex128).reshape(n, self.N + 1)
         return r

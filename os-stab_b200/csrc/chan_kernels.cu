@@ -593,7 +593,32 @@ struct ChanArgs {
   double *delta;         // [ninst] error estimate of omega: last measured change, or conv_push's remaining-error estimate
   int32_t *iters;        // [ninst] total inverse iterations
   double2 *evec;         // optional [ninst][n+2] (grid 0..N, zeros at the walls), max-modulus normalised
+  double2 *adj;          // optional [ninst][n+2] left (adjoint) eigenvector, see adj_form
+  int adj_form;          // OSB_ADJ_PENCIL: u with u^H (A - w B) = 0 scaled to u^H evec = 1 (orrcolchan.f:537-545);
+                         // OSB_ADJ_INVBA: B^H u = ZGEEV's left vector of inv(B)A, unit 2-norm, largest component
+                         // real positive (orrfdchan.f:796)
 };
+
+// index of the component of largest modulus, lowest index on ties (the scan of orrfdchan.f:849-857)
+__device__ int block_argmax_abs(const double2 *v, int n) {
+  __shared__ double sb[CH_THREADS_MAX];
+  __shared__ int si[CH_THREADS_MAX];
+  double best = -1.0;
+  int bi = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double m2 = v[i].x * v[i].x + v[i].y * v[i].y;
+    if (m2 > best) { best = m2; bi = i; }
+  }
+  __syncthreads();
+  sb[threadIdx.x] = best; si[threadIdx.x] = bi;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int t = 1; t < blockDim.x; ++t)
+      if (sb[t] > sb[0] || (sb[t] == sb[0] && si[t] < si[0])) { sb[0] = sb[t]; si[0] = si[t]; }
+  }
+  __syncthreads();
+  return si[0];
+}
 
 __device__ void start_vector(double2 *x, int n) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -602,6 +627,58 @@ __device__ void start_vector(double2 *x, int n) {
   }
   __syncthreads();
 }
+
+// Left (adjoint) eigenvector of the converged mode; kept out of line so that its second LU call site does not
+// weigh on the register allocation of the sweep path.
+__device__ __noinline__ void cta_adjoint(const ChanArgs &a, ChanShared &s, double2 *M, const PencilCoef &p, double2 om,
+                                         double2 esc, int64_t inst) {
+  const int n = a.n;
+    // Left eigenvector u, u^H (A - w B) = 0, by inverse iteration on the adjoint pencil
+    //     u <- (A - s B)^{-H} B^H u
+    // with a fresh factorisation at s = w (1 + 1e-8): every solve then contracts the other modes by ~1e-8 |w| / gap.
+    const double2 sg = make_double2(om.x + 1.0e-8 * hypot(om.x, om.y), om.y);
+    assemble_shifted(M, n, a.D2, a.D4, a.u, a.d2u, p, sg);
+    cta_lu(M, n, s.ipiv, s.panel, s.red);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s.t[i] = make_double2(s.x[i].x, 0.3 - s.x[i].y);
+    __syncthreads();
+    for (int k = 0; k < 4; ++k) {
+      cta_d2_matvec(a.D2, n, s.t, s.y, true);  // D2^T u
+      for (int i = threadIdx.x; i < n; i += blockDim.x)
+        s.y[i] = cadd2(cmulc2(p.b2, s.y[i]), cmulc2(p.b0, s.t[i]));  // B^H u
+      __syncthreads();
+      cta_solve_h(M, n, s.ipiv, s.y);
+      double nn = 0.0;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) nn += s.y[i].x * s.y[i].x + s.y[i].y * s.y[i].y;
+      const double rn = rsqrt(block_sum(make_double2(nn, 0.0), s.red).x);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) s.t[i] = make_double2(s.y[i].x * rn, s.y[i].y * rn);
+      __syncthreads();
+    }
+    double2 *av = a.adj + (size_t)inst * (n + 2);
+    if (a.adj_form == OSB_ADJ_PENCIL) {
+      // escale = zdotc(avec, evec); avec <- avec / conj(escale)   (orrcolchan.f:537-545)
+      double2 d = make_double2(0.0, 0.0);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) d = cadd2(d, cmulc2(s.t[i], cmul2(esc, s.x[i])));
+      d = block_sum(d, s.red);
+      const double2 sc = cdiv2(make_double2(1.0, 0.0), make_double2(d.x, -d.y));
+      for (int i = threadIdx.x; i < n; i += blockDim.x) av[i + 1] = cmul2(sc, s.t[i]);
+    } else {
+      // vl = B^H u, then ZGEEV's normalisation: unit 2-norm, largest component real (positive)
+      cta_d2_matvec(a.D2, n, s.t, s.y, true);
+      double nn = 0.0;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double2 v = cadd2(cmulc2(p.b2, s.y[i]), cmulc2(p.b0, s.t[i]));
+        s.y[i] = v;
+        nn += v.x * v.x + v.y * v.y;
+      }
+      const double rn = rsqrt(block_sum(make_double2(nn, 0.0), s.red).x);
+      const int k = block_argmax_abs(s.y, n);
+      const double2 vk = s.y[k];
+      const double ak = hypot(vk.x, vk.y);
+      const double2 ph = make_double2(rn * vk.x / ak, -rn * vk.y / ak);  // rn * conj(v_k) / |v_k|
+      for (int i = threadIdx.x; i < n; i += blockDim.x) av[i + 1] = cmul2(ph, s.y[i]);
+    }
+    if (threadIdx.x == 0) { av[0] = make_double2(0.0, 0.0); av[n + 1] = make_double2(0.0, 0.0); }
+  }
 
 // Two register budgets for the same body: up to n ~ 350 two CTAs fit an SM by shared
 // memory and 128 registers/thread keeps them both resident; beyond that the 135 KB panel
@@ -640,27 +717,16 @@ __device__ __forceinline__ void chan_eig_body(const ChanArgs &a) {
       a.delta[inst] = dl;
       a.iters[inst] = total;
     }
-    if (a.evec) {
+    if (a.evec || a.adj) {
       // normalise by the component of largest modulus (orrfdchan.f:849-857)
-      double best = -1.0;
-      int bi = 0;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double m2 = s.x[i].x * s.x[i].x + s.x[i].y * s.x[i].y;
-        if (m2 > best) { best = m2; bi = i; }
+      const int imax = block_argmax_abs(s.x, n);
+      const double2 esc = cdiv2(make_double2(1.0, 0.0), s.x[imax]);
+      if (a.evec) {
+        double2 *ev = a.evec + (size_t)inst * (n + 2);
+        for (int i = threadIdx.x; i < n; i += blockDim.x) ev[i + 1] = cmul2(esc, s.x[i]);
+        if (threadIdx.x == 0) { ev[0] = make_double2(0.0, 0.0); ev[n + 1] = make_double2(0.0, 0.0); }
       }
-      __shared__ double sb[CH_THREADS_MAX];
-      __shared__ int si[CH_THREADS_MAX];
-      sb[threadIdx.x] = best; si[threadIdx.x] = bi;
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        for (int t = 1; t < blockDim.x; ++t)
-          if (sb[t] > sb[0] || (sb[t] == sb[0] && si[t] < si[0])) { sb[0] = sb[t]; si[0] = si[t]; }
-      }
-      __syncthreads();
-      const double2 esc = cdiv2(make_double2(1.0, 0.0), s.x[si[0]]);
-      double2 *ev = a.evec + (size_t)inst * (n + 2);
-      for (int i = threadIdx.x; i < n; i += blockDim.x) ev[i + 1] = cmul2(esc, s.x[i]);
-      if (threadIdx.x == 0) { ev[0] = make_double2(0.0, 0.0); ev[n + 1] = make_double2(0.0, 0.0); }
+      if (a.adj) cta_adjoint(a, s, M, p, om, esc, inst);
     }
     __syncthreads();
   }
@@ -970,6 +1036,8 @@ struct BandArgs {
   double *delta;
   int32_t *iters;
   double2 *evec;   // optional [ninst][n+2]
+  double2 *adj;    // optional [ninst][n+2] left eigenvector (one-thread kernel only), see ChanArgs
+  int adj_form;
   double2 *U;      // [n][BW][ninst]
   double2 *L;      // [n][BKL][ninst]
   int8_t *piv;     // [n][ninst]  pivot offset 0..4 (one-thread kernel)
@@ -987,6 +1055,55 @@ __device__ __forceinline__ double2 band_entry(const BandArgs &a, const PencilCoe
   double2 v = make_double2(fma(w2.x, d2, d4), w2.y * d2);
   if (r == c) v = cadd2(v, csub2(coef_w0(p, a.u[r], a.d2u[r]), sb0));
   return v;
+}
+
+// banded LU with partial pivoting of A - sigma B, one thread per instance (window of rows k..k+4, columns k..k+8)
+__device__ __noinline__ void band_lu_thread(const BandArgs &a, const PencilCoef &p, double2 sigma, double2 *U,
+                                               double2 *Lm, int8_t *piv, size_t S) {
+  const int n = a.n;
+  const double2 sb2 = cmul2(sigma, p.b2), sb0 = cmul2(sigma, p.b0);
+  double2 w[BKL + 1][BW];
+#pragma unroll
+  for (int sidx = 0; sidx <= BKL; ++sidx)
+#pragma unroll
+    for (int j = 0; j < BW; ++j) w[sidx][j] = band_entry(a, p, sb2, sb0, sidx, j);
+  for (int k = 0; k < n; ++k) {
+    int pv = 0;
+    double best = fabs(w[0][0].x) + fabs(w[0][0].y);
+#pragma unroll
+    for (int sidx = 1; sidx <= BKL; ++sidx) {
+      const double v = fabs(w[sidx][0].x) + fabs(w[sidx][0].y);
+      if (k + sidx < n && v > best) { best = v; pv = sidx; }
+    }
+    piv[(size_t)k * S] = (int8_t)pv;
+#pragma unroll
+    for (int sidx = 1; sidx <= BKL; ++sidx)
+      if (pv == sidx) {
+#pragma unroll
+        for (int j = 0; j < BW; ++j) { const double2 t = w[0][j]; w[0][j] = w[sidx][j]; w[sidx][j] = t; }
+      }
+    double2 pvt = w[0][0];
+    if (pvt.x == 0.0 && pvt.y == 0.0) pvt = make_double2(1.0e-290, 0.0);
+    const double2 rinv = cdiv2(make_double2(1.0, 0.0), pvt);
+#pragma unroll
+    for (int sidx = 1; sidx <= BKL; ++sidx) {
+      const double2 l = cmul2(w[sidx][0], rinv);
+      Lm[((size_t)k * BKL + (sidx - 1)) * S] = l;
+#pragma unroll
+      for (int j = 1; j < BW; ++j) w[sidx][j] = cfnma2(w[sidx][j], l, w[0][j]);
+    }
+#pragma unroll
+    for (int j = 0; j < BW; ++j) U[((size_t)k * BW + j) * S] = (j == 0) ? pvt : w[0][j];
+    // slide the window: row k leaves, row k+5 enters
+#pragma unroll
+    for (int sidx = 0; sidx < BKL; ++sidx) {
+#pragma unroll
+      for (int j = 0; j < BW - 1; ++j) w[sidx][j] = w[sidx + 1][j + 1];
+      w[sidx][BW - 1] = make_double2(0.0, 0.0);
+    }
+#pragma unroll
+    for (int j = 0; j < BW; ++j) w[BKL][j] = band_entry(a, p, sb2, sb0, k + 1 + BKL, k + 1 + j);
+  }
 }
 
 __global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constant__ BandArgs a) {
@@ -1007,50 +1124,7 @@ __global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constan
   double dl = 1.0e300;
   int total = 0;
   for (int o = 0; o < a.outer; ++o) {
-    // ---- banded LU with partial pivoting (window of rows k..k+4, columns k..k+8)
-    const double2 sb2 = cmul2(sigma, p.b2), sb0 = cmul2(sigma, p.b0);
-    double2 w[BKL + 1][BW];
-#pragma unroll
-    for (int sidx = 0; sidx <= BKL; ++sidx)
-#pragma unroll
-      for (int j = 0; j < BW; ++j) w[sidx][j] = band_entry(a, p, sb2, sb0, sidx, j);
-    for (int k = 0; k < n; ++k) {
-      int pv = 0;
-      double best = fabs(w[0][0].x) + fabs(w[0][0].y);
-#pragma unroll
-      for (int sidx = 1; sidx <= BKL; ++sidx) {
-        const double v = fabs(w[sidx][0].x) + fabs(w[sidx][0].y);
-        if (k + sidx < n && v > best) { best = v; pv = sidx; }
-      }
-      piv[(size_t)k * S] = (int8_t)pv;
-#pragma unroll
-      for (int sidx = 1; sidx <= BKL; ++sidx)
-        if (pv == sidx) {
-#pragma unroll
-          for (int j = 0; j < BW; ++j) { const double2 t = w[0][j]; w[0][j] = w[sidx][j]; w[sidx][j] = t; }
-        }
-      double2 pvt = w[0][0];
-      if (pvt.x == 0.0 && pvt.y == 0.0) pvt = make_double2(1.0e-290, 0.0);
-      const double2 rinv = cdiv2(make_double2(1.0, 0.0), pvt);
-#pragma unroll
-      for (int sidx = 1; sidx <= BKL; ++sidx) {
-        const double2 l = cmul2(w[sidx][0], rinv);
-        Lm[((size_t)k * BKL + (sidx - 1)) * S] = l;
-#pragma unroll
-        for (int j = 1; j < BW; ++j) w[sidx][j] = cfnma2(w[sidx][j], l, w[0][j]);
-      }
-#pragma unroll
-      for (int j = 0; j < BW; ++j) U[((size_t)k * BW + j) * S] = (j == 0) ? pvt : w[0][j];
-      // slide the window: row k leaves, row k+5 enters
-#pragma unroll
-      for (int sidx = 0; sidx < BKL; ++sidx) {
-#pragma unroll
-        for (int j = 0; j < BW - 1; ++j) w[sidx][j] = w[sidx + 1][j + 1];
-        w[sidx][BW - 1] = make_double2(0.0, 0.0);
-      }
-#pragma unroll
-      for (int j = 0; j < BW; ++j) w[BKL][j] = band_entry(a, p, sb2, sb0, k + 1 + BKL, k + 1 + j);
-    }
+    band_lu_thread(a, p, sigma, U, Lm, piv, S);
     // ---- inverse iteration
     int it = 0;
     ConvTrack ct;
@@ -1122,7 +1196,7 @@ __global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constan
   a.omega[inst] = om;
   a.delta[inst] = dl;
   a.iters[inst] = total;
-  if (a.evec) {
+  if (a.evec || a.adj) {
     double best = -1.0;
     int bi = 0;
     for (int i = 0; i < n; ++i) {
@@ -1131,10 +1205,98 @@ __global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constan
       if (m2 > best) { best = m2; bi = i; }
     }
     const double2 esc = cdiv2(make_double2(1.0, 0.0), x[(size_t)bi * S]);
-    double2 *ev = a.evec + (size_t)inst * (n + 2);
-    ev[0] = make_double2(0.0, 0.0);
-    ev[n + 1] = make_double2(0.0, 0.0);
-    for (int i = 0; i < n; ++i) ev[i + 1] = cmul2(esc, x[(size_t)i * S]);
+    if (a.evec) {
+      double2 *ev = a.evec + (size_t)inst * (n + 2);
+      ev[0] = make_double2(0.0, 0.0);
+      ev[n + 1] = make_double2(0.0, 0.0);
+      for (int i = 0; i < n; ++i) ev[i + 1] = cmul2(esc, x[(size_t)i * S]);
+    }
+    if (a.adj) {
+      // Left eigenvector by inverse iteration on the adjoint pencil, u <- (A - s B)^{-H} B^H u, after a fresh
+      // banded factorisation at s = w (1 + 1e-8) (see chan_eig_body).  With E_k = L_k P_k the elimination steps,
+      // M = E_0^{-1} ... E_{n-1}^{-1} U, so M^{-H} r = E_0^H ... E_{n-1}^H U^{-H} r.  The iterate lives in y and
+      // is written to the output array (used as the second vector) between the phases.
+      double2 *av = a.adj + (size_t)inst * (n + 2);
+      const double2 sg = make_double2(om.x + 1.0e-8 * hypot(om.x, om.y), om.y);
+      band_lu_thread(a, p, sg, U, Lm, piv, S);
+      for (int i = 0; i < n; ++i) { const double2 v = x[(size_t)i * S]; av[i + 1] = make_double2(v.x, 0.3 - v.y); }
+      for (int it2 = 0; it2 < 4; ++it2) {
+        // y = B^H u = conj(b2) D2^T u + conj(b0) u
+        for (int r = 0; r < n; ++r) {
+          double sr = 0.0, si = 0.0;
+#pragma unroll
+          for (int dc = -2; dc <= 2; ++dc) {
+            const int c = r + dc;
+            if (c >= 0 && c < n) {
+              const double d = a.D2[(size_t)r * n + c];  // D2(c, r)
+              const double2 uc = av[c + 1];
+              sr = fma(d, uc.x, sr); si = fma(d, uc.y, si);
+            }
+          }
+          y[(size_t)r * S] = cadd2(cmulc2(p.b2, make_double2(sr, si)), cmulc2(p.b0, av[r + 1]));
+        }
+        // U^H a = y: a_k = (y_k - sum_j conj(U(k-j, k)) a_{k-j}) / conj(U(k,k))
+        for (int k = 0; k < n; ++k) {
+          double2 acc = y[(size_t)k * S];
+#pragma unroll
+          for (int j = 1; j < BW; ++j)
+            if (k - j >= 0) acc = csub2(acc, cmulc2(U[((size_t)(k - j) * BW + j) * S], y[(size_t)(k - j) * S]));
+          const double2 d = U[((size_t)k * BW) * S];
+          y[(size_t)k * S] = cdiv2(acc, make_double2(d.x, -d.y));
+        }
+        // z = E_0^H ... E_{n-1}^H a: for k = n-1 .. 0: a_k -= sum_s conj(l_{k,s}) a_{k+s}; swap(a_k, a_{k+piv_k})
+        for (int k = n - 1; k >= 0; --k) {
+          double2 acc = y[(size_t)k * S];
+#pragma unroll
+          for (int sidx = 1; sidx <= BKL; ++sidx)
+            if (k + sidx < n) acc = csub2(acc, cmulc2(Lm[((size_t)k * BKL + (sidx - 1)) * S], y[(size_t)(k + sidx) * S]));
+          const int pv = piv[(size_t)k * S];
+          if (pv) {
+            y[(size_t)k * S] = y[(size_t)(k + pv) * S];
+            y[(size_t)(k + pv) * S] = acc;
+          } else {
+            y[(size_t)k * S] = acc;
+          }
+        }
+        double nn = 0.0;
+        for (int i = 0; i < n; ++i) { const double2 v = y[(size_t)i * S]; nn += v.x * v.x + v.y * v.y; }
+        const double rn = rsqrt(nn);
+        for (int i = 0; i < n; ++i) { const double2 v = y[(size_t)i * S]; av[i + 1] = make_double2(v.x * rn, v.y * rn); }
+      }
+      if (a.adj_form == OSB_ADJ_PENCIL) {
+        double2 d = make_double2(0.0, 0.0);
+        for (int i = 0; i < n; ++i) d = cadd2(d, cmulc2(av[i + 1], cmul2(esc, x[(size_t)i * S])));
+        const double2 sc = cdiv2(make_double2(1.0, 0.0), make_double2(d.x, -d.y));
+        for (int i = 0; i < n; ++i) av[i + 1] = cmul2(sc, av[i + 1]);
+      } else {
+        double nn = 0.0, vb = -1.0;
+        int vi = 0;
+        for (int r = 0; r < n; ++r) {
+          double sr = 0.0, si = 0.0;
+#pragma unroll
+          for (int dc = -2; dc <= 2; ++dc) {
+            const int c = r + dc;
+            if (c >= 0 && c < n) {
+              const double d = a.D2[(size_t)r * n + c];
+              const double2 uc = av[c + 1];
+              sr = fma(d, uc.x, sr); si = fma(d, uc.y, si);
+            }
+          }
+          const double2 v = cadd2(cmulc2(p.b2, make_double2(sr, si)), cmulc2(p.b0, av[r + 1]));
+          y[(size_t)r * S] = v;
+          const double m2 = v.x * v.x + v.y * v.y;
+          nn += m2;
+          if (m2 > vb) { vb = m2; vi = r; }
+        }
+        const double rn = rsqrt(nn);
+        const double2 vk = y[(size_t)vi * S];
+        const double ak = hypot(vk.x, vk.y);
+        const double2 ph = make_double2(rn * vk.x / ak, -rn * vk.y / ak);
+        for (int i = 0; i < n; ++i) av[i + 1] = cmul2(ph, y[(size_t)i * S]);
+      }
+      av[0] = make_double2(0.0, 0.0);
+      av[n + 1] = make_double2(0.0, 0.0);
+    }
   }
 }
 
@@ -1523,11 +1685,12 @@ size_t chan_band_work_bytes(int n, int64_t ninst) {
 cudaError_t launch_chan_fd_banded(int n, const double *D2, const double *D4, const double *u, const double *d2u,
                                   const double2 *band24, void *work, int64_t ninst, const double2 *alpha,
                                   const double *Re, const double2 *sigma, int outer, int inner, double tol,
-                                  double2 *omega, double *delta, int32_t *iters, double2 *evec, cudaStream_t st) {
+                                  double2 *omega, double *delta, int32_t *iters, double2 *evec, double2 *adj, int adj_form,
+                                  cudaStream_t st) {
   BandArgs a;
   a.n = n; a.D2 = D2; a.D4 = D4; a.u = u; a.d2u = d2u; a.band24 = band24; a.ninst = ninst; a.alpha = alpha; a.Re = Re;
   a.sigma = sigma; a.outer = outer; a.inner = inner; a.tol = tol; a.omega = omega; a.delta = delta; a.iters = iters;
-  a.evec = evec;
+  a.evec = evec; a.adj = adj; a.adj_form = adj_form;
   a.early = getenv("OSB_NO_EARLY_STOP") ? 0 : 1;
   double2 *w = (double2 *)work;
   const size_t N1 = (size_t)ninst * n;
@@ -1536,7 +1699,9 @@ cudaError_t launch_chan_fd_banded(int n, const double *D2, const double *D4, con
   a.piv32 = (int32_t *)(((uintptr_t)(a.piv + N1) + 255) & ~(uintptr_t)255);
   // nine lanes per instance while that still leaves the GPU room (the one-thread kernel needs
   // ~10^5 instances to fill it); OSB_FD_THREAD=1 forces the one-thread kernel
-  if (band24 && ninst <= BAND_WARP_MAX_INST && !getenv("OSB_FD_THREAD")) {
+  // (the adjoint eigenvector is implemented in the one-thread kernel only: it is asked for by the single-alpha
+  // listings, never by sweeps)
+  if (band24 && ninst <= BAND_WARP_MAX_INST && !adj && !getenv("OSB_FD_THREAD")) {
     const int64_t per_cta = (int64_t)BG * BWW;
     const unsigned grid = (unsigned)((ninst + per_cta - 1) / per_cta);
     int dev = 0, sms = 148;
@@ -1910,7 +2075,7 @@ __global__ void __launch_bounds__(32) chan_eig_warp_kernel(const __grid_constant
       sigma = om;
     }
     if (lane == 0) { a.omega[inst] = om; a.delta[inst] = dl; a.iters[inst] = total; }
-    if (a.evec) {
+    if (a.evec || a.adj) {
       double best = -1.0;
       int bi = 0;
       for (int i = lane; i < n; i += 32) {
@@ -1924,9 +2089,61 @@ __global__ void __launch_bounds__(32) chan_eig_warp_kernel(const __grid_constant
         if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
       }
       const double2 esc = cdiv2(make_double2(1.0, 0.0), s.x[bi]);
-      double2 *ev = a.evec + (size_t)inst * (n + 2);
-      for (int i = lane; i < n; i += 32) ev[i + 1] = cmul2(esc, s.x[i]);
-      if (lane == 0) { ev[0] = make_double2(0.0, 0.0); ev[n + 1] = make_double2(0.0, 0.0); }
+      if (a.evec) {
+        double2 *ev = a.evec + (size_t)inst * (n + 2);
+        for (int i = lane; i < n; i += 32) ev[i + 1] = cmul2(esc, s.x[i]);
+        if (lane == 0) { ev[0] = make_double2(0.0, 0.0); ev[n + 1] = make_double2(0.0, 0.0); }
+      }
+      if (a.adj) {  // see chan_eig_body
+        const double2 sg = make_double2(om.x + 1.0e-8 * hypot(om.x, om.y), om.y);
+        w_assemble(s.M, n, a.D2, a.D4, a.u, a.d2u, p, sg);
+        w_lu(s.M, n, s.ipiv);
+        for (int i = lane; i < n; i += 32) s.t[i] = make_double2(s.x[i].x, 0.3 - s.x[i].y);
+        __syncwarp();
+        for (int k = 0; k < 4; ++k) {
+          w_d2_matvec(a.D2, n, s.t, s.y, true);
+          for (int i = lane; i < n; i += 32) s.y[i] = cadd2(cmulc2(p.b2, s.y[i]), cmulc2(p.b0, s.t[i]));
+          __syncwarp();
+          w_solve_h(s.M, n, s.ipiv, s.y);
+          double nn = 0.0;
+          for (int i = lane; i < n; i += 32) nn += s.y[i].x * s.y[i].x + s.y[i].y * s.y[i].y;
+          const double rn = rsqrt(wsum(make_double2(nn, 0.0)).x);
+          for (int i = lane; i < n; i += 32) s.t[i] = make_double2(s.y[i].x * rn, s.y[i].y * rn);
+          __syncwarp();
+        }
+        double2 *av = a.adj + (size_t)inst * (n + 2);
+        if (a.adj_form == OSB_ADJ_PENCIL) {
+          double2 d = make_double2(0.0, 0.0);
+          for (int i = lane; i < n; i += 32) d = cadd2(d, cmulc2(s.t[i], cmul2(esc, s.x[i])));
+          d = wsum(d);
+          const double2 sc = cdiv2(make_double2(1.0, 0.0), make_double2(d.x, -d.y));
+          for (int i = lane; i < n; i += 32) av[i + 1] = cmul2(sc, s.t[i]);
+        } else {
+          w_d2_matvec(a.D2, n, s.t, s.y, true);
+          double nn = 0.0, vb = -1.0;
+          int vi = 0;
+          for (int i = lane; i < n; i += 32) {
+            const double2 v = cadd2(cmulc2(p.b2, s.y[i]), cmulc2(p.b0, s.t[i]));
+            s.y[i] = v;
+            const double m2 = v.x * v.x + v.y * v.y;
+            nn += m2;
+            if (m2 > vb) { vb = m2; vi = i; }
+          }
+          const double rn = rsqrt(wsum(make_double2(nn, 0.0)).x);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, vb, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, vi, o);
+            if (ob > vb || (ob == vb && oi < vi)) { vb = ob; vi = oi; }
+          }
+          __syncwarp();
+          const double2 vk = s.y[vi];
+          const double ak = hypot(vk.x, vk.y);
+          const double2 ph = make_double2(rn * vk.x / ak, -rn * vk.y / ak);
+          for (int i = lane; i < n; i += 32) av[i + 1] = cmul2(ph, s.y[i]);
+        }
+        if (lane == 0) { av[0] = make_double2(0.0, 0.0); av[n + 1] = make_double2(0.0, 0.0); }
+      }
     }
     __syncwarp();
   }
@@ -2091,11 +2308,12 @@ cudaError_t chan_neutral_grid(int n, int64_t ninst, int *grid, size_t *smem) {
 cudaError_t launch_chan_eig(int n, const double *D2, const double *D4, const double *u, const double *d2u,
                             double2 *work, int grid, size_t smem, int64_t ninst, const double2 *alpha,
                             const double *Re, const double2 *sigma, int outer, int inner, double tol,
-                            double2 *omega, double *delta, int32_t *iters, double2 *evec, cudaStream_t st) {
+                            double2 *omega, double *delta, int32_t *iters, double2 *evec, double2 *adj, int adj_form,
+                            cudaStream_t st) {
   ChanArgs a;
   a.n = n; a.D2 = D2; a.D4 = D4; a.u = u; a.d2u = d2u; a.work = work; a.ninst = ninst;
   a.alpha = alpha; a.Re = Re; a.sigma = sigma; a.outer = outer; a.inner = inner; a.tol = tol;
-  a.omega = omega; a.delta = delta; a.iters = iters; a.evec = evec;
+  a.omega = omega; a.delta = delta; a.iters = iters; a.evec = evec; a.adj = adj; a.adj_form = adj_form;
   a.early = getenv("OSB_NO_EARLY_STOP") ? 0 : 1;
   if (use_warp_kernels(n)) chan_eig_warp_kernel<<<grid, 32, smem, st>>>(a);
   else if (use_big_kernel(n)) chan_eig_kernel_big<<<grid, CH_THREADS_BIG, smem, st>>>(a);

@@ -287,7 +287,7 @@ int osb_chan_tables(osb_ctx *ctx, const osb_chan *c, double *eta, double *u, dou
 static int run_eig_chunk(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::vector<double> &alpha,
                          const std::vector<double> &Re, const std::vector<double> &sigma, int outer, int inner,
                          double tol, std::vector<double> &omega, std::vector<double> &delta,
-                         std::vector<int32_t> &iters, double *evec_host) {
+                         std::vector<int32_t> &iters, double *evec_host, double *adj_host = nullptr, int adj_form = 0) {
   cudaStream_t st = (cudaStream_t)osb_stream(ctx);
   const int n = c->n;
   int grid = 0;
@@ -305,24 +305,25 @@ static int run_eig_chunk(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const s
   if (!banded) CH_CUDA(ctx, chan_eig_grid(n, ninst, &grid, &smem));
   Scratch scr(c->device, st, ctx_pool(ctx, 0));
   double *d_in = nullptr, *d_out = nullptr;
-  double2 *work = nullptr, *d_evec = nullptr;
+  double2 *work = nullptr, *d_evec = nullptr, *d_adj = nullptr;
   int32_t *d_it = nullptr;
   CH_CUDA(ctx, scr.alloc(&d_in, ninst * 5 * sizeof(double)));   // alpha(2), sigma(2), Re
   CH_CUDA(ctx, scr.alloc(&d_out, ninst * 3 * sizeof(double)));  // omega(2), delta
   CH_CUDA(ctx, scr.alloc(&d_it, ninst * sizeof(int32_t)));
   CH_CUDA(ctx, scr.alloc(&work, banded ? chan_band_work_bytes(n, ninst) : (size_t)grid * n * n * sizeof(double2)));
   if (evec_host) CH_CUDA(ctx, scr.alloc(&d_evec, (size_t)ninst * (n + 2) * sizeof(double2)));
+  if (adj_host) CH_CUDA(ctx, scr.alloc(&d_adj, (size_t)ninst * (n + 2) * sizeof(double2)));
   CH_CUDA(ctx, cudaMemcpyAsync(d_in, alpha.data(), ninst * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   CH_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * ninst, sigma.data(), ninst * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   CH_CUDA(ctx, cudaMemcpyAsync(d_in + 4 * ninst, Re.data(), ninst * sizeof(double), cudaMemcpyHostToDevice, st));
   if (banded)
     CH_CUDA(ctx, launch_chan_fd_banded(n, c->dD2, c->dD4, c->du, c->dd2u, c->dBand, work, ninst, (const double2 *)d_in,
                                        d_in + 4 * ninst, (const double2 *)(d_in + 2 * ninst), outer, inner, tol,
-                                       (double2 *)d_out, d_out + 2 * ninst, d_it, d_evec, st));
+                                       (double2 *)d_out, d_out + 2 * ninst, d_it, d_evec, d_adj, adj_form, st));
   else
     CH_CUDA(ctx, launch_chan_eig(n, c->dD2, c->dD4, c->du, c->dd2u, work, grid, smem, ninst,
                                  (const double2 *)d_in, d_in + 4 * ninst, (const double2 *)(d_in + 2 * ninst), outer,
-                                 inner, tol, (double2 *)d_out, d_out + 2 * ninst, d_it, d_evec, st));
+                                 inner, tol, (double2 *)d_out, d_out + 2 * ninst, d_it, d_evec, d_adj, adj_form, st));
   ctx_count_launch(ctx, 1);
   omega.resize(2 * ninst); delta.resize(ninst); iters.resize(ninst);
   CH_CUDA(ctx, cudaMemcpyAsync(omega.data(), d_out, ninst * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -330,6 +331,8 @@ static int run_eig_chunk(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const s
   CH_CUDA(ctx, cudaMemcpyAsync(iters.data(), d_it, ninst * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   if (evec_host)
     CH_CUDA(ctx, cudaMemcpyAsync(evec_host, d_evec, (size_t)ninst * (n + 2) * sizeof(double2), cudaMemcpyDeviceToHost, st));
+  if (adj_host)
+    CH_CUDA(ctx, cudaMemcpyAsync(adj_host, d_adj, (size_t)ninst * (n + 2) * sizeof(double2), cudaMemcpyDeviceToHost, st));
   CH_CUDA(ctx, cudaStreamSynchronize(st));
   if (getenv("OSB_CHAN_PROFILE")) chan_profile_dump("eig");
   return OSB_OK;
@@ -340,15 +343,16 @@ static int run_eig_chunk(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const s
 static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::vector<double> &alpha,
                    const std::vector<double> &Re, const std::vector<double> &sigma, int outer, int inner,
                    double tol, std::vector<double> &omega, std::vector<double> &delta,
-                   std::vector<int32_t> &iters, double *evec_host) {
+                   std::vector<int32_t> &iters, double *evec_host, double *adj_host = nullptr, int adj_form = 0) {
   const bool banded = (c->disc == OSB_DISC_FD) && !getenv("OSB_FD_DENSE");
   int64_t chunk = ninst;
   if (banded) {
-    const size_t per = chan_band_work_bytes(c->n, 1) + (evec_host ? (size_t)(c->n + 2) * 16 : 0) + 64;
+    const size_t per = chan_band_work_bytes(c->n, 1) + ((evec_host ? 1 : 0) + (adj_host ? 1 : 0)) * (size_t)(c->n + 2) * 16 + 64;
     chunk = std::max<int64_t>(1, (int64_t)((8ull << 30) / per));
     if (const char *e = getenv("OSB_CHAN_CHUNK")) chunk = std::max<int64_t>(1, atoll(e));  // test hook
   }
-  if (ninst <= chunk) return run_eig_chunk(ctx, c, ninst, alpha, Re, sigma, outer, inner, tol, omega, delta, iters, evec_host);
+  if (ninst <= chunk)
+    return run_eig_chunk(ctx, c, ninst, alpha, Re, sigma, outer, inner, tol, omega, delta, iters, evec_host, adj_host, adj_form);
   omega.resize(2 * ninst); delta.resize(ninst); iters.resize(ninst);
   std::vector<double> a, r, sg, om, dl;
   std::vector<int32_t> it;
@@ -358,7 +362,8 @@ static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::ve
     r.assign(Re.begin() + lo, Re.begin() + lo + m);
     sg.assign(sigma.begin() + 2 * lo, sigma.begin() + 2 * (lo + m));
     int rc = run_eig_chunk(ctx, c, m, a, r, sg, outer, inner, tol, om, dl, it,
-                           evec_host ? evec_host + (size_t)lo * (c->n + 2) * 2 : nullptr);
+                           evec_host ? evec_host + (size_t)lo * (c->n + 2) * 2 : nullptr,
+                           adj_host ? adj_host + (size_t)lo * (c->n + 2) * 2 : nullptr, adj_form);
     if (rc) return rc;
     std::copy(om.begin(), om.end(), omega.begin() + 2 * lo);
     std::copy(dl.begin(), dl.end(), delta.begin() + lo);
@@ -426,8 +431,10 @@ static int scan_shifts(osb_ctx *ctx, const osb_chan *c, int64_t npts, const doub
 }
 
 int osb_chan_eig(osb_ctx *ctx, const osb_chan *c, double Re, int64_t npts, const double *alpha,
-                 const double *sigma0, double *omega, double *evec, int32_t *iters, int32_t *status) {
+                 const double *sigma0, double *omega, double *evec, double *evec_adj, int adj_form,
+                 int32_t *iters, int32_t *status) {
   if (!ctx || !c || npts < 0 || !alpha || !omega || !status) return ctx_fail(ctx, OSB_E_ARG, "null argument");
+  if (evec_adj && adj_form != OSB_ADJ_PENCIL && adj_form != OSB_ADJ_INVBA) return ctx_fail(ctx, OSB_E_ARG, "unknown adj_form");
   if (npts == 0) return OSB_OK;
   std::vector<double> Rev(npts, Re), sig(2 * npts);
   std::vector<int32_t> ok(npts, 1);
@@ -461,9 +468,11 @@ int osb_chan_eig(osb_ctx *ctx, const osb_chan *c, double Re, int64_t npts, const
   }
   std::vector<double> a(alpha, alpha + 2 * npts), om, dl;
   std::vector<int32_t> it;
-  std::vector<double> ev;
+  std::vector<double> ev, av;
   if (evec) ev.resize((size_t)npts * (c->n + 2) * 2);
-  int rc = run_eig(ctx, c, npts, a, Rev, sig, 4, 8, 1.0e-14, om, dl, it, evec ? ev.data() : nullptr);
+  if (evec_adj) av.resize((size_t)npts * (c->n + 2) * 2);
+  int rc = run_eig(ctx, c, npts, a, Rev, sig, 4, 8, 1.0e-14, om, dl, it, evec ? ev.data() : nullptr,
+                   evec_adj ? av.data() : nullptr, adj_form);
   if (rc) return rc;
   for (int64_t p = 0; p < npts; ++p) {
     omega[2 * p] = om[2 * p]; omega[2 * p + 1] = om[2 * p + 1];
@@ -473,6 +482,7 @@ int osb_chan_eig(osb_ctx *ctx, const osb_chan *c, double Re, int64_t npts, const
     status[p] = !fin ? OSB_ST_NONFINITE : ((conv && ok[p]) ? OSB_ST_CONVERGED : OSB_ST_MAXCOUNT);
   }
   if (evec) memcpy(evec, ev.data(), ev.size() * sizeof(double));
+  if (evec_adj) memcpy(evec_adj, av.data(), av.size() * sizeof(double));
   return OSB_OK;
 }
 

@@ -131,7 +131,8 @@ cudaError_t chan_neutral_grid(int n, int64_t ninst, int *grid, size_t *smem);
 cudaError_t launch_chan_eig(int n, const double *D2, const double *D4, const double *u, const double *d2u,
                             double2 *work, int grid, size_t smem, int64_t ninst, const double2 *alpha,
                             const double *Re, const double2 *sigma, int outer, int inner, double tol,
-                            double2 *omega, double *delta, int32_t *iters, double2 *evec, cudaStream_t st);
+                            double2 *omega, double *delta, int32_t *iters, double2 *evec, double2 *adj, int adj_form,
+                            cudaStream_t st);
 cudaError_t chan_spectrum_grid(int n, int64_t ninst, int *grid, size_t *smem);
 cudaError_t launch_chan_spectrum(int n, const double *D2, const double *D4, const double *u, const double *d2u,
                                  double2 *work, int grid, size_t smem, int64_t ninst, const double2 *alpha,
@@ -140,7 +141,8 @@ size_t chan_band_work_bytes(int n, int64_t ninst);
 cudaError_t launch_chan_fd_banded(int n, const double *D2, const double *D4, const double *u, const double *d2u,
                                   const double2 *band24, void *work, int64_t ninst, const double2 *alpha, const double *Re,
                                   const double2 *sigma, int outer, int inner, double tol, double2 *omega,
-                                  double *delta, int32_t *iters, double2 *evec, cudaStream_t st);
+                                  double *delta, int32_t *iters, double2 *evec, double2 *adj, int adj_form,
+                                  cudaStream_t st);
 cudaError_t launch_chan_neutral(int n, const double *D2, const double *D4, const double *u, const double *d2u,
                                 double2 *work, int grid, size_t smem, int64_t ninst, const double *Re,
                                 const double *alpha0, const double2 *sigma0, double sfac, double tol, int maxit,

@@ -583,6 +583,38 @@ static int run_orrspace(osb_ctx *ctx) {
     int32_t q2;
     CK(ctx, osb_eigfun(ctx, &o, prof, 1, nullptr, &Re, ev, omr, y.data(), vmax, &q2));
     write_eigfun(y, cd(vmax[0], vmax[1]), nstep, ymax, ymin, (ymax - ymin) / nstep, true, 16, false, std::sqrt(2.) / 1.7207876);
+    // u and v disturbance velocities (orrspace.f:547-578): fort.15 / fort.16 hold u = phi' and v = -i alpha phi
+    // at x = 0 and nine phases of one half period, fort.18 both normalised by the u of largest modulus
+    {
+      const double pi = 3.14159265358979323846, h = (ymax - ymin) / nstep, ts = std::sqrt(2.) / 1.7207876;  // orrspace.f:267
+      const cd alpha(ev[0], ev[1]), mx(vmax[0], vmax[1]), iu(0.0, 1.0);
+      const int ntime = 8;
+      const double x = 0.0, dtime = pi / om.real() / ntime;
+      auto Y = [&](int comp, int k) { return cd(y[2 * (4 * k + comp)], y[2 * (4 * k + comp) + 1]); };
+      FILE *f15 = fopen("fort.15", "w"), *f16 = fopen("fort.16", "w"), *f18 = fopen("fort.18", "w");
+      for (int k = 0; k <= nstep; ++k) {
+        const double t = (ymax - h * k) * ts;
+        fprintf(f15, "%s ", ES(t, 16, 8, 3).c_str());
+        fprintf(f16, "%s ", ES(t, 16, 8, 3).c_str());
+        for (int i = 0; i <= ntime; ++i) {
+          const cd ph = std::exp(iu * (alpha * x - om * (double)i * dtime));
+          fprintf(f15, "%s ", ES((Y(1, k) / mx * ph).real(), 16, 8, 3).c_str());
+          fprintf(f16, "%s ", ES((cd(0.0, -1.0) * alpha * Y(0, k) / mx * ph).real(), 16, 8, 3).c_str());
+        }
+        fprintf(f15, "\n");
+        fprintf(f16, "\n");
+      }
+      cd umax(0.0, 0.0);
+      for (int k = 0; k <= nstep; ++k)
+        if (std::abs(Y(1, k)) > std::abs(umax)) umax = Y(1, k);
+      for (int k = 0; k <= nstep; ++k) {
+        const double t = (ymax - h * k) * ts;
+        const cd uu = Y(1, k) / umax, vv = cd(0.0, -1.0) * alpha * Y(0, k) / umax;
+        fprintf(f18, "%s %s %s %s %s \n", ES(t, 16, 8, 3).c_str(), ES(uu.real(), 16, 8, 3).c_str(), ES(uu.imag(), 16, 8, 3).c_str(),
+                ES(vv.real(), 16, 8, 3).c_str(), ES(vv.imag(), 16, 8, 3).c_str());
+      }
+      fclose(f15); fclose(f16); fclose(f18);
+    }
   }
   osb_profile_free(ctx, prof);
   return bad;
@@ -638,9 +670,10 @@ static int run_orrfdchan(osb_ctx *ctx) {
   std::vector<int32_t> it(npts), st(npts);
   for (int j = 0; j < nai; ++j) for (int i = 0; i < nar; ++i) { al[2 * (j * nar + i)] = alphar[i]; al[2 * (j * nar + i) + 1] = alphai[j]; }
   const bool print = (ians == 1);
-  std::vector<double> ev;
-  if (print) ev.resize((size_t)npts * (n + 1) * 2);
-  CK(ctx, osb_chan_eig(ctx, chan, Re, npts, al.data(), nullptr, om.data(), print ? ev.data() : nullptr, it.data(), st.data()));
+  std::vector<double> ev, av;
+  if (print) { ev.resize((size_t)npts * (n + 1) * 2); av.resize((size_t)npts * (n + 1) * 2); }
+  CK(ctx, osb_chan_eig(ctx, chan, Re, npts, al.data(), nullptr, om.data(), print ? ev.data() : nullptr,
+                       print ? av.data() : nullptr, OSB_ADJ_INVBA, it.data(), st.data()));
   std::vector<double> eta;
   if (print) {
     eta.resize(n + 1);
@@ -674,11 +707,20 @@ static int run_orrfdchan(osb_ctx *ctx) {
       int which = 0;
       printf("\n Eigenvector for which eigenvalue (0 quits) ==> ");
       while (std::cin >> which && which != 0) {
-        const double *v = ev.data() + (size_t)p * (n + 1) * 2;
-        FILE *f = fopen("fort.11", "w");  // format 60; the two adjoint columns are not computed (zeros)
-        for (int j = 0; j <= n; ++j)
+        const double *v = ev.data() + (size_t)p * (n + 1) * 2, *a = av.data() + (size_t)p * (n + 1) * 2;
+        // escale (orrfdchan.f:849-856): the largest component of ZGEEV's unit-norm right vector, which ZGEEV makes
+        // real and positive: 1 / |v|_2 of the max-normalised vector
+        double nrm = 0.0;
+        for (int j = 0; j <= n; ++j) nrm += v[2 * j] * v[2 * j] + v[2 * j + 1] * v[2 * j + 1];
+        printf(" escale =  (%.16g,%.16g)\n", 1.0 / std::sqrt(nrm), 0.0);
+        FILE *f = fopen("fort.11", "w");  // format 60
+        for (int j = 0; j <= n; ++j) {
+          // columns 4-5: avec(j, ind(iloc)), j = 0..N (orrfdchan.f:865-871): ZGEEV's left vector of inv(B)A, NOT shifted
+          // onto the grid like the right vector, and two entries past the N-1 that ZGEEV wrote (zeros of the static array)
+          const double ar = j < n - 1 ? a[2 * (j + 1)] : 0.0, ai = j < n - 1 ? a[2 * (j + 1) + 1] : 0.0;
           fprintf(f, " %s %s %s %s %s \n", ES(eta[j], 16, 8, 3).c_str(), ES(v[2 * j], 16, 8, 3).c_str(),
-                  ES(v[2 * j + 1], 16, 8, 3).c_str(), ES(0.0, 16, 8, 3).c_str(), ES(0.0, 16, 8, 3).c_str());
+                  ES(v[2 * j + 1], 16, 8, 3).c_str(), ES(ar, 16, 8, 3).c_str(), ES(ai, 16, 8, 3).c_str());
+        }
         fclose(f);
         printf("\n Eigenvector for which eigenvalue (0 quits) ==> ");
       }
@@ -779,7 +821,7 @@ static int run_orrbl(osb_ctx *ctx, bool colloc) {
   std::vector<double> al(2 * npts), om(2 * npts);
   std::vector<int32_t> it(npts), st(npts);
   for (int j = 0; j < nai; ++j) for (int i = 0; i < nar; ++i) { al[2 * (j * nar + i)] = alphar[i]; al[2 * (j * nar + i) + 1] = alphai[j]; }
-  CK(ctx, osb_chan_eig(ctx, chan, Re, npts, al.data(), nullptr, om.data(), nullptr, it.data(), st.data()));
+  CK(ctx, osb_chan_eig(ctx, chan, Re, npts, al.data(), nullptr, om.data(), nullptr, nullptr, 0, it.data(), st.data()));
   std::vector<double> dw(2 * npts, 0.0);
   if (colloc) {
     std::vector<double> a2(4 * npts), s2(4 * npts), o2(4 * npts);
@@ -793,7 +835,7 @@ static int run_orrbl(osb_ctx *ctx, bool colloc) {
         s2[2 * e] = om[2 * p]; s2[2 * e + 1] = om[2 * p + 1];
       }
     }
-    CK(ctx, osb_chan_eig(ctx, chan, Re, 2 * npts, a2.data(), s2.data(), o2.data(), nullptr, i2.data(), t2.data()));
+    CK(ctx, osb_chan_eig(ctx, chan, Re, 2 * npts, a2.data(), s2.data(), o2.data(), nullptr, nullptr, 0, i2.data(), t2.data()));
     for (int64_t p = 0; p < npts; ++p) {
       dw[2 * p] = (o2[2 * (2 * p + 1)] - o2[2 * (2 * p)]) / (2.0 * hh[p]);
       dw[2 * p + 1] = (o2[2 * (2 * p + 1) + 1] - o2[2 * (2 * p) + 1]) / (2.0 * hh[p]);
@@ -873,14 +915,29 @@ static int run_orrcolchan(osb_ctx *ctx) {
     if (which < 0 || which > n) { fprintf(stderr, "index out of range\n"); bad = 1; break; }
     // the eigenvector of the chosen mode: shift-invert with its eigenvalue as the shift
     double sg[2] = {omega[which].real(), omega[which].imag()}, om[2];
-    std::vector<double> ev((size_t)(n + 1) * 2);
+    std::vector<double> ev((size_t)(n + 1) * 2), av((size_t)(n + 1) * 2);
     int32_t it, st;
-    CK(ctx, osb_chan_eig(ctx, chan, Re, 1, al, sg, om, ev.data(), &it, &st));
+    CK(ctx, osb_chan_eig(ctx, chan, Re, 1, al, sg, om, ev.data(), av.data(), OSB_ADJ_PENCIL, &it, &st));
     bad |= st;
-    FILE *f = fopen("fort.11", "w");  // orrcolchan.f:551-555 (adjoint columns: not computed, zeros)
+    {
+      // the two zdotc(avec, evec) checks (orrcolchan.f:537-546).  The first is taken with avec as LAPACK leaves it
+      // (largest |re|+|im| component scaled to modulus 1, phase arbitrary -- here: that component = 1); the second,
+      // after the scaling by 1/conj(escale), is 1.
+      int k = 0;
+      double best = -1.0;
+      for (int i = 0; i <= n; ++i) {
+        const double m = std::fabs(av[2 * i]) + std::fabs(av[2 * i + 1]);
+        if (m > best) { best = m; k = i; }
+      }
+      const cd e1 = std::conj(cd(1.0, 0.0) / cd(av[2 * k], av[2 * k + 1]));
+      cd e2(0.0, 0.0);
+      for (int i = 0; i <= n; ++i) e2 += std::conj(cd(av[2 * i], av[2 * i + 1])) * cd(ev[2 * i], ev[2 * i + 1]);
+      printf(" (%.16g,%.16g)\n (%.16g,%.16g)\n", e1.real(), e1.imag(), e2.real(), e2.imag());
+    }
+    FILE *f = fopen("fort.11", "w");  // orrcolchan.f:551-555
     for (int i = 0; i <= n; ++i)
       fprintf(f, " %s %s %s %s %s \n", ES(eta[i], 16, 8, 3).c_str(), ES(ev[2 * i], 16, 8, 3).c_str(), ES(ev[2 * i + 1], 16, 8, 3).c_str(),
-              ES(0.0, 16, 8, 3).c_str(), ES(0.0, 16, 8, 3).c_str());
+              ES(av[2 * i], 16, 8, 3).c_str(), ES(av[2 * i + 1], 16, 8, 3).c_str());
     fclose(f);
     printf("\n Eigenvector for which eigenvalue (-1 quits) ==> ");
   }

@@ -198,8 +198,8 @@ class ChanOracle:
         lib.osr_chan_create.argtypes = [i, i]
         lib.osr_chan_destroy.argtypes = [C.c_void_p]
         lib.osr_chan_get.argtypes = [C.c_void_p, i, _dp]
-        lib.osr_chan_solve_fdstyle.argtypes = [C.c_void_p, d, d, d, _dp, _dp, _dp]
-        lib.osr_chan_solve_col.argtypes = [C.c_void_p, d, d, d, _dp, i, _dp]
+        lib.osr_chan_solve_fdstyle.argtypes = [C.c_void_p, d, d, d, _dp, _dp, _dp, _dp]
+        lib.osr_chan_solve_col.argtypes = [C.c_void_p, d, d, d, _dp, i, _dp, _dp, _dp]
         lib.osr_chan_neutral.restype = i
         lib.osr_chan_neutral.argtypes = [C.c_void_p, d, d, d, d, i, _dp]
         if lib.osr_lapack_open(_find_openblas().encode()) != 0:
@@ -223,15 +223,19 @@ class ChanOracle:
         self.lib.osr_chan_get(self.h, which, out.ctypes.data_as(_dp))
         return out if which < 4 else out.reshape(n1, n1)
 
-    def solve_fd(self, alpha, Re, want_spectrum=False, want_evec=False):
+    def solve_fd(self, alpha, Re, want_spectrum=False, want_evec=False, want_adj=False):
         alpha = complex(alpha)
         om = np.zeros(2)
         spec = np.zeros(2 * (self.n - 1)) if want_spectrum else None
         ev = np.zeros(2 * (self.n + 1)) if want_evec else None
+        av = np.zeros(2 * (self.n + 1)) if want_adj else None
         self.lib.osr_chan_solve_fdstyle(self.h, alpha.real, alpha.imag, Re, om.ctypes.data_as(_dp),
                                         spec.ctypes.data_as(_dp) if want_spectrum else None,
-                                        ev.ctypes.data_as(_dp) if want_evec else None)
+                                        ev.ctypes.data_as(_dp) if want_evec else None,
+                                        av.ctypes.data_as(_dp) if want_adj else None)
         r = dict(omega=complex(om[0], om[1]))
+        if want_adj:
+            r["avec"] = av.view(np.complex128)
         if want_spectrum:
             r["spectrum"] = spec.view(np.complex128)
         if want_evec:
@@ -242,11 +246,16 @@ class ChanOracle:
         alpha = complex(alpha)
         spec = np.zeros(2 * (self.n + 1))
         ev = np.zeros(2 * (self.n + 1)) if which >= 0 else None
+        av = np.zeros(2 * (self.n + 1)) if which >= 0 else None
+        dots = np.zeros(4)
         self.lib.osr_chan_solve_col(self.h, alpha.real, alpha.imag, Re, spec.ctypes.data_as(_dp), which,
-                                    ev.ctypes.data_as(_dp) if which >= 0 else None)
+                                    ev.ctypes.data_as(_dp) if which >= 0 else None,
+                                    av.ctypes.data_as(_dp) if which >= 0 else None, dots.ctypes.data_as(_dp))
         r = dict(spectrum=spec.view(np.complex128))
         if which >= 0:
             r["evec"] = ev.view(np.complex128)
+            r["avec"] = av.view(np.complex128)
+            r["dots"] = dots.view(np.complex128)
         return r
 
     def arbiter(self, alpha, Re, sigma, iters=4):

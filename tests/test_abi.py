@@ -27,7 +27,7 @@ def test_header_symbols_are_exported(osb):
 
 def test_version_and_defaults(osb):
     lib = osb.load_library()
-    assert lib.osb_version() == 1
+    assert lib.osb_version() == 2
     o = osb.shoot_defaults(osb.FLOW_CONTEBL, lib)
     # contebl.f:64-83 and shoot.f:461-463
     assert (o.nstep, o.maxcount, o.testalpha, o.ymin, o.ymax) == (1000, 20, 10.0, 0.0, 17.0)
@@ -99,4 +99,4 @@ int main(void) {
     assert cc.returncode == 0, cc.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
-    assert "osb_version 1" in r.stdout
+    assert "osb_version 2" in r.stdout

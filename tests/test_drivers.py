@@ -174,6 +174,45 @@ def test_orrspace_sweep_fort17(tmp_path, oracle):
 
 
 @pytest.mark.gpu
+def test_orrspace_space_deck_writes_u_and_v(tmp_path, oracle):
+    """space.inp (niter = 1, eigfun = 1): fort.11-14 and the u, v disturbance velocities of orrspace.f:547-578 --
+    fort.15 / fort.16 at nine phases of a half period (format 21), fort.18 normalised by the largest |u| --
+    against the same formulas applied to the oracle's eigenfunction.  orrspace stops at |err| < 1e-8
+    (orrspace.f:277), so alpha itself is only converged to ~1e-9 and the normalised eigenfunctions of two
+    arithmetics agree to ~1e-8: asserted at 1e-7 like test_orrspace_space_deck_eigenfunction."""
+    deck = SPATIAL_DECK.format(niter=1, eigfun=1).replace("testalpha = 0.9 ", "testalpha = 0.2 ")
+    deck = deck.replace("alphar = 0.13809592E+00", "alphar = 0.228047").replace("alphai = 0.51958399E-02", "alphai = -0.00651")
+    deck = deck.replace("omegar = 0.042 ", "omegar = 0.08 ").replace("domega = 0.002", "domega = 0.0")
+    (tmp_path / "space.inp").write_text(deck)
+    r = run("orrspace", "space.inp\n", tmp_path)
+    assert r.returncode == 0, r.stderr
+    fact = math.sqrt(2.0) / 1.7207876
+    ymin, ymax, nstep = 0.0, 20.0 * fact, 1000
+    prof, _, _ = oracle.solve_bl(ob.FLOW_ORRSPACE, ob.INT_RK4, 1000, ymin, ymax, 0.5, 0.0)
+    Re, om, a0 = 1000.0 * fact, complex(0.08, 0.0) * fact, complex(0.228047, -0.00651) * fact
+    ref = oracle.shoot_spatial_point(ob.INT_RK4, nstep, 0.2, ymin, ymax, prof, Re, om, a0)
+    y, alpha = ref["y"], ref["alpha"]
+    t = (ymax - (ymax - ymin) / nstep * np.arange(nstep + 1)) * fact
+    f11 = np.loadtxt(tmp_path / "fort.11")
+    assert np.max(np.abs(f11[:, 0] - t)) < 1e-7
+    phases = np.exp(1j * (-om * np.arange(9) * (3.14159265358979323846 / om.real / 8)))
+    u15 = (y[:, 1] / ref["vmax"])[:, None] * phases[None, :]
+    v16 = (-1j * alpha * y[:, 0] / ref["vmax"])[:, None] * phases[None, :]
+    f15, f16, f18 = (np.loadtxt(tmp_path / f"fort.{k}") for k in (15, 16, 18))
+    assert f15.shape == (nstep + 1, 10) and f16.shape == (nstep + 1, 10) and f18.shape == (nstep + 1, 5)
+    assert np.max(np.abs(f15[:, 1:] - u15.real)) < 1e-7 * np.abs(u15).max()
+    assert np.max(np.abs(f16[:, 1:] - v16.real)) < 1e-7 * np.abs(v16).max()
+    uu, vv = y[:, 1], -1j * alpha * y[:, 0]
+    umax = uu[np.argmax(np.abs(uu))]
+    assert np.max(np.abs(f18[:, 1] + 1j * f18[:, 2] - uu / umax)) < 1e-7
+    assert np.max(np.abs(f18[:, 3] + 1j * f18[:, 4] - vv / umax)) < 1e-7
+    assert abs(np.abs(f18[:, 1] + 1j * f18[:, 2]).max() - 1.0) < 1e-8
+    # every line of fort.15 is format 21: one ES16.8E3 field, 1x, then nine fields each followed by a blank
+    line = (tmp_path / "fort.15").read_text().splitlines()[3]
+    assert len(line) == 16 + 1 + 9 * 17
+
+
+@pytest.mark.gpu
 def test_orrfdchan_fd64_deck(tmp_path):
     r = run("orrfdchan", "64\n10000\n0.76 1.16 0.02\n0 0 1\neig-64\n0\n", tmp_path)
     assert r.returncode == 0, r.stderr
@@ -225,6 +264,19 @@ def test_orrcolchan_chan_deck(tmp_path):
     assert f11.shape == (65, 5)
     v = f11[:, 1] + 1j * f11[:, 2]
     assert abs(np.abs(v).max() - 1.0) < 1e-8
+    # columns 4-5: the adjoint eigenvector after the bi-orthonormalisation of orrcolchan.f:537-545, and the two
+    # zdotc checks the reference prints before / after it (the second is 1)
+    c = ob.chan(ob.DISC_CHEB, 64)
+    refv = c.solve_col(1.0, 1.0e4, which=62)
+    c.close()
+    a = f11[:, 3] + 1j * f11[:, 4]
+    assert a[0] == 0 and a[-1] == 0
+    assert np.max(np.abs(a - refv["avec"])) < 2e-6 * np.abs(refv["avec"]).max()
+    assert abs(np.vdot(a, v) - 1.0) < 1e-6   # 8 printed digits
+    dots = [ln for ln in r.stdout.splitlines() if ln.startswith(" (") and ln.rstrip().endswith(")")]
+    assert len(dots) == 2
+    d2 = complex(*[float(x) for x in dots[1].strip(" ()").split(",")])
+    assert abs(d2 - 1.0) < 1e-12
 
 
 UC_DECK = TEMPORAL_DECK.rstrip("\n") + """
@@ -316,6 +368,14 @@ def test_orrfdchan_fdchan_deck_prints_eigenvector(tmp_path):
     v = f11[:, 1] + 1j * f11[:, 2]
     assert abs(np.abs(v).max() - 1.0) < 1e-8 and v[0] == 0 and v[-1] == 0
     assert np.max(np.abs(v - ref["evec"])) < 1e-7
+    # columns 4-5: ZGEEV's left eigenvector of inv(B)A as orrfdchan.f:865-871 lays it out (unshifted, two zero rows)
+    c = ob.chan(ob.DISC_FD, 128)
+    refa = c.solve_fd(1.0, 1.0e4, want_adj=True)["avec"]
+    c.close()
+    a = f11[:, 3] + 1j * f11[:, 4]
+    assert a[-1] == 0 and a[-2] == 0 and abs(np.linalg.norm(a) - 1.0) < 1e-7
+    assert np.max(np.abs(a - refa)) < 2e-8
+    assert " escale = " in r.stdout
     f20 = np.loadtxt(tmp_path / "fort.20").reshape(-1, 2)
     assert f20.shape == (127, 2)
     c20 = f20[:, 0] + 1j * f20[:, 1]

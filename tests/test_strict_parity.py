@@ -289,7 +289,7 @@ def test_sensitivity_classed_tolerances(engine, osb, oracle):
     # orrsom decks around the default point
     p = engine.solve_bl(osb.FLOW_ORRSOM, osb.INT_RK4, 1000, 0.0, 17.0, 0.5, 0.0)
     prof, _, _ = oracle.solve_bl(ob.FLOW_ORRSOM, ob.INT_RK4, 1000, 0.0, 17.0, 0.5, 0.0)
-    al = (0.179 + 0.004 * np.arange(-8, 9)) * S2
+    al = (0.179 + 0.002 * np.arange(-16, 9)) * S2   # far guesses on the low side: up to 13 passes
     Re = np.full(al.size, 580.0 * S2)
     g = np.full(al.size, GUESS)
     opts = osb.shoot_defaults(osb.FLOW_ORRSOM)
@@ -297,6 +297,7 @@ def test_sensitivity_classed_tolerances(engine, osb, oracle):
     r = engine.shoot_temporal(opts, p, al, Re, g)
     p.free()
     base = oracle.shoot_temporal_batch(ob.FLOW_ORRSOM, ob.INT_RK4, 1000, 10.0, 0.0, 17.0, prof, al, Re, g)
+    assert (base["status"] == 0).all() and (r["status"] == 0).all()
     sens = np.zeros(al.size)
     for dg in (np.nextafter(g.real, 1.0) + 1j * g.imag, np.nextafter(g.real, 0.0) + 1j * g.imag,
                g.real + 1j * np.nextafter(g.imag, 1.0)):
@@ -312,6 +313,7 @@ def test_sensitivity_classed_tolerances(engine, osb, oracle):
     a0 = complex(0.13809592, 0.0051958399) * FACT
     rr = engine.shoot_spatial_lines(opts, p, [1000.0 * FACT], [0.042 * FACT], [0.002 * FACT], [a0], 50)
     p.free()
+    assert (rr["status"] == 0).all()
     line = lambda a: oracle.shoot_spatial_line(ob.INT_RK4, 1000, 0.9, ymin, ymax, prof, 1000.0 * FACT, 0.042 * FACT,
                                                0.002 * FACT, a, 50)["alpha"]
     base = line(a0)
