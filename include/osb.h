@@ -292,6 +292,9 @@ int osb_chan_neutral(osb_ctx *ctx, const osb_chan *chan, int64_t nRe, const doub
  * per DFMA).  Used as the roofline denominator of the shooting kernel. */
 int osb_measure_fp64_peak(osb_ctx *ctx, double ms_target, double *tflops,
                           double *sm_clock_mhz_est);
+/* The same for the FP64 tensor path (mma.sync.m8n8k4.f64 = DMMA, 512 flops per warp instruction): the
+ * roofline denominator of the dense LU's trailing update (BASELINE.md section 3 asks for both). */
+int osb_measure_dmma_peak(osb_ctx *ctx, double ms_target, double *tflops);
 
 #ifdef __cplusplus
 }

@@ -722,7 +722,7 @@ int osr_shoot_temporal(int flow, int integrator, int nstep, double testalpha,
 int osr_shoot_temporal_batch(int flow, int integrator, int nstep, double testalpha,
                              double ymin, double ymax, int nbl, const double *prof,
                              int64_t npts, const double *alpha, const double *Re,
-                             double *c, int *passes, int *qend, int *status) {
+                             double *c, int *passes, int *qend, int *status, double *absdc) {
   for (int64_t p = 0; p < npts; ++p) {
     double out[6];
     int iout[3];
@@ -733,6 +733,7 @@ int osr_shoot_temporal_batch(int flow, int integrator, int nstep, double testalp
     if (passes) passes[p] = iout[0];
     if (qend) qend[p] = iout[1];
     if (status) status[p] = iout[2];
+    if (absdc) absdc[p] = out[5]; /* |c_next - ctemp|: the update the loop computed but did not integrate */
   }
   return 0;
 }
@@ -745,7 +746,7 @@ int osr_shoot_spatial_line(int integrator, int nstep, double testalpha, double y
                            double ymax, int nbl, const double *prof, double Re,
                            double omega_re, double omega_im, double domega,
                            double alpha_re, double alpha_im, int niter, double *rows,
-                           int *ipass, int *iqend, int *istat) {
+                           int *ipass, int *iqend, int *istat, double *absdc) {
   osr_state s;
   memset(&s, 0, sizeof(s));
   s.flow = OSR_FLOW_ORRSPACE; s.integrator = integrator; s.nstep = nstep;
@@ -761,6 +762,7 @@ int osr_shoot_spatial_line(int integrator, int nstep, double testalpha, double y
     if (ipass) ipass[i] = r.passes;
     if (iqend) iqend[i] = r.qend;
     if (istat) istat[i] = r.status;
+    if (absdc) absdc[i] = r.absdc;
     double omegar = creal(s.omega) + domega; /* orrspace.f:192-194 */
     s.omega = CMPLX(omegar, cimag(s.omega));
   }

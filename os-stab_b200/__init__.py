@@ -93,6 +93,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "osb_shoot_neutral": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, _dp, _dp, _dp, dbl, dbl, i32, _dp, _dp, _ip, _ip]),
         "osb_eigfun": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, _dp, _dp, _dp, _dp, _dp, _dp, _ip]),
         "osb_measure_fp64_peak": (C.c_int, [vp, dbl, _dp, _dp]),
+        "osb_measure_dmma_peak": (C.c_int, [vp, dbl, _dp]),
         "osb_chan_create": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(vp)]),
         "osb_chan_create_bl": (C.c_int, [vp, C.c_int, C.c_int, dbl, _dp, C.c_int, C.POINTER(vp)]),
         "osb_chan_bl_points": (C.c_int, [C.c_int, C.c_int, dbl, _dp]),
@@ -113,7 +114,7 @@ EXPORTED_SYMBOLS = (
     "osb_version osb_create osb_create_multi osb_destroy osb_device_count osb_last_error osb_stream "
     "osb_launch_count osb_profile_blasius osb_profile_blasius_batch osb_profile_upload "
     "osb_profile_shift osb_profile_channel osb_profile_get osb_profile_nbl osb_profile_free osb_shoot_defaults "
-    "osb_shoot_temporal osb_shoot_temporal_dev osb_shoot_spatial_lines osb_shoot_neutral osb_eigfun osb_measure_fp64_peak "
+    "osb_shoot_temporal osb_shoot_temporal_dev osb_shoot_spatial_lines osb_shoot_neutral osb_eigfun osb_measure_fp64_peak osb_measure_dmma_peak "
     "osb_chan_create osb_chan_create_bl osb_chan_bl_points osb_chan_free osb_chan_tables osb_chan_eig osb_chan_spectrum osb_chan_neutral"
 ).split()
 
@@ -388,6 +389,11 @@ class Engine:
         mhz = C.c_double()
         self._check(self.lib.osb_measure_fp64_peak(self.ctx, ms_target, C.byref(tf), C.byref(mhz)))
         return tf.value, mhz.value
+
+    def measure_dmma_peak(self, ms_target=200.0):
+        tf = C.c_double()
+        self._check(self.lib.osb_measure_dmma_peak(self.ctx, ms_target, C.byref(tf)))
+        return tf.value
 
 
 class Chan:

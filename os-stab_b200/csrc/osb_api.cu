@@ -831,8 +831,8 @@ int osb_eigfun(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof
 }
 
 // ---------------------------------------------------------------- measurement
-int osb_measure_fp64_peak(osb_ctx *ctx, double ms_target, double *tflops, double *sm_clock_mhz_est) {
-  if (!ctx || !tflops) return OSB_E_ARG;
+// shared body of the two peak micro-benchmarks: `flops_per_thread_iter` = flops one thread performs per loop trip
+static int measure_peak(osb_ctx *ctx, double ms_target, bool dmma, double *tflops) {
   OSB_CUDA(ctx, cudaSetDevice(ctx->devices[0]));
   cudaStream_t st = ctx->streams[0];
   cudaDeviceProp prop;
@@ -848,26 +848,44 @@ int osb_measure_fp64_peak(osb_ctx *ctx, double ms_target, double *tflops, double
   OSB_CUDA(ctx, cudaEventCreate(&ev.e0));
   OSB_CUDA(ctx, cudaEventCreate(&ev.e1));
   cudaEvent_t e0 = ev.e0, e1 = ev.e1;
+  // DFMA kernel: 8 chains x 16 unrolled FMAs x 2 flops per thread and trip;
+  // DMMA kernel: 4 x 8 instructions of 512 flops per WARP and trip = 512 flops per thread and trip
+  const double per_thread_trip = dmma ? 4.0 * 8.0 * 512.0 / 32.0 : 2.0 * 8.0 * 16.0;
   int iters = 2000;
   double best = 0.0;
   float ms = 0.f;
   for (int rep = 0; rep < 6; ++rep) {
     OSB_CUDA(ctx, cudaEventRecord(e0, st));
-    OSB_CUDA(ctx, launch_fp64_peak(d_out, iters, blocks, threads, st));
+    OSB_CUDA(ctx, dmma ? launch_dmma_peak(d_out, iters, blocks, threads, st) : launch_fp64_peak(d_out, iters, blocks, threads, st));
     ctx->launches++;
     OSB_CUDA(ctx, cudaEventRecord(e1, st));
     OSB_CUDA(ctx, cudaEventSynchronize(e1));
     OSB_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
-    double flops = 2.0 * 8.0 * 16.0 * (double)iters * threads * (double)blocks;
-    double tf = flops / (ms * 1e-3) / 1e12;
+    const double flops = per_thread_trip * (double)iters * threads * (double)blocks;
+    const double tf = flops / (ms * 1e-3) / 1e12;
     if (rep > 0) best = std::max(best, tf);
     if (ms < ms_target && iters < (1 << 24)) iters = (int)std::min<double>(1 << 24, iters * std::max(1.5, ms_target / std::max(ms, 1e-3f)));
   }
   *tflops = best;
-  if (sm_clock_mhz_est)  // 64 DFMA / clk / SM on B200
-    *sm_clock_mhz_est = best * 1e12 / (2.0 * 64.0 * prop.multiProcessorCount) / 1e6;
   OSB_CUDA(ctx, cudaStreamSynchronize(st));
   return OSB_OK;
+}
+
+int osb_measure_fp64_peak(osb_ctx *ctx, double ms_target, double *tflops, double *sm_clock_mhz_est) {
+  if (!ctx || !tflops) return OSB_E_ARG;
+  int rc = measure_peak(ctx, ms_target, false, tflops);
+  if (rc) return rc;
+  if (sm_clock_mhz_est) {  // 64 DFMA / clk / SM on B200
+    cudaDeviceProp prop;
+    OSB_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->devices[0]));
+    *sm_clock_mhz_est = *tflops * 1e12 / (2.0 * 64.0 * prop.multiProcessorCount) / 1e6;
+  }
+  return OSB_OK;
+}
+
+int osb_measure_dmma_peak(osb_ctx *ctx, double ms_target, double *tflops) {
+  if (!ctx || !tflops) return OSB_E_ARG;
+  return measure_peak(ctx, ms_target, true, tflops);
 }
 
 }  // extern "C"

@@ -149,5 +149,6 @@ cudaError_t launch_chan_neutral(int n, const double *D2, const double *D4, const
                                 double *alpha_out, double2 *omega_out, int32_t *steps, int32_t *status,
                                 double *trace, cudaStream_t st);
 cudaError_t launch_fp64_peak(double *d_out, int iters, int blocks, int threads, cudaStream_t st);
+cudaError_t launch_dmma_peak(double *d_out, int iters, int blocks, int threads, cudaStream_t st);
 
 }  // namespace osb

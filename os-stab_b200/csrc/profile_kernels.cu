@@ -239,4 +239,35 @@ cudaError_t launch_fp64_peak(double *d_out, int iters, int blocks, int threads, 
   return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------
+// FP64 TENSOR peak: 8 independent chains of mma.sync.m8n8k4.f64 (DMMA) per warp, no memory traffic.
+// One instruction = 8 x 8 x 4 multiply-adds = 512 flops per warp.  This is the roofline of the dense LU's
+// trailing update (chan_kernels.cu); tcgen05 has no fp64 kind.
+// ---------------------------------------------------------------------------
+__global__ void dmma_peak_kernel(double *out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { c[j][0] = threadIdx.x * 1e-9 + j; c[j][1] = 0.5 * j; }
+  const double a = 0.999999999 + 1e-12 * threadIdx.x, b = 1e-3;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c[j][0]), "+d"(c[j][1])
+                     : "d"(a), "d"(b));
+    }
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += c[j][0] + c[j][1];
+  if (s == 123.456) out[0] = s;
+}
+
+cudaError_t launch_dmma_peak(double *d_out, int iters, int blocks, int threads, cudaStream_t st) {
+  dmma_peak_kernel<<<blocks, threads, 0, st>>>(d_out, iters);
+  return cudaGetLastError();
+}
+
 }  // namespace osb

@@ -48,9 +48,9 @@ class Oracle:
         lib.osr_shoot_temporal.restype = i
         lib.osr_shoot_temporal.argtypes = [i, i, i, d, d, d, i, _dp, d, d, d, d, d, _dp, _ip, _dp, i, _dp, _dp]
         lib.osr_shoot_temporal_batch.restype = i
-        lib.osr_shoot_temporal_batch.argtypes = [i, i, i, d, d, d, i, _dp, i64, _dp, _dp, _dp, _ip, _ip, _ip]
+        lib.osr_shoot_temporal_batch.argtypes = [i, i, i, d, d, d, i, _dp, i64, _dp, _dp, _dp, _ip, _ip, _ip, _dp]
         lib.osr_shoot_spatial_line.restype = i
-        lib.osr_shoot_spatial_line.argtypes = [i, i, d, d, d, i, _dp, d, d, d, d, d, d, i, _dp, _ip, _ip, _ip]
+        lib.osr_shoot_spatial_line.argtypes = [i, i, d, d, d, i, _dp, d, d, d, d, d, d, i, _dp, _ip, _ip, _ip, _dp]
         lib.osr_shoot_spatial_point.restype = i
         lib.osr_shoot_spatial_point.argtypes = [i, i, d, d, d, i, _dp, d, d, d, d, d, _dp, _ip, _dp, _dp]
 
@@ -112,27 +112,29 @@ class Oracle:
         qend = np.zeros(n, dtype=np.int32)
         status = np.zeros(n, dtype=np.int32)
         nbl = prof.shape[1] - 2 if prof is not None else 0
+        absdc = np.zeros(n)
         self.lib.osr_shoot_temporal_batch(
             flow, integrator, nstep, testalpha, ymin, ymax, nbl,
             prof.ctypes.data_as(_dp) if prof is not None else None, n, al.ctypes.data_as(_dp),
             Re.ctypes.data_as(_dp), cc.ctypes.data_as(_dp), passes.ctypes.data_as(_ip), qend.ctypes.data_as(_ip),
-            status.ctypes.data_as(_ip))
-        return dict(c=cc.view(np.complex128), passes=passes, qend=qend, status=status)
+            status.ctypes.data_as(_ip), absdc.ctypes.data_as(_dp))
+        return dict(c=cc.view(np.complex128), passes=passes, qend=qend, status=status, absdc=absdc)
 
     def shoot_spatial_line(self, integrator, nstep, testalpha, ymin, ymax, prof, Re, omega, domega, alpha, niter):
         rows = np.zeros(4 * niter)
         ipass = np.zeros(niter, dtype=np.int32)
         iq = np.zeros(niter, dtype=np.int32)
         ist = np.zeros(niter, dtype=np.int32)
+        absdc = np.zeros(niter)
         omega = complex(omega)
         alpha = complex(alpha)
         self.lib.osr_shoot_spatial_line(
             integrator, nstep, testalpha, ymin, ymax, prof.shape[1] - 2, prof.ctypes.data_as(_dp), Re,
             omega.real, omega.imag, domega, alpha.real, alpha.imag, niter, rows.ctypes.data_as(_dp),
-            ipass.ctypes.data_as(_ip), iq.ctypes.data_as(_ip), ist.ctypes.data_as(_ip))
+            ipass.ctypes.data_as(_ip), iq.ctypes.data_as(_ip), ist.ctypes.data_as(_ip), absdc.ctypes.data_as(_dp))
         rows = rows.reshape(niter, 4)
         return dict(omega=rows[:, 0] + 1j * rows[:, 1], alpha=rows[:, 2] + 1j * rows[:, 3],
-                    passes=ipass, qend=iq, status=ist)
+                    passes=ipass, qend=iq, status=ist, absdc=absdc)
 
 
 def _spatial_point(self, integrator, nstep, testalpha, ymin, ymax, prof, Re, omega, alpha):

@@ -471,7 +471,8 @@ def test_adjoint_eigenvector(engine, osb, oracle, disc, N, route, monkeypatch):
         kmax = np.argmax(np.abs(vl))
         assert abs(vl[kmax].imag) < 1e-14 and vl[kmax].real > 0            # ... largest component real
         bu = B.conj().T @ u
-        assert np.linalg.norm(bu / np.linalg.norm(bu) * np.exp(-1j * np.angle(bu[kmax])) - vl) < 1e-8
+        # (numpy's own B^H u carries cond(B) eps: the FD operator's entries grow like N^4)
+        assert np.linalg.norm(bu / np.linalg.norm(bu) * np.exp(-1j * np.angle(bu[kmax])) - vl) < (1e-8 if N <= 128 else 1e-6)
     c = ob.chan(disc, N)
     if disc == ob.DISC_FD and N <= 128:
         for k, al in enumerate(alpha):

@@ -273,10 +273,10 @@ def test_orrcolchan_chan_deck(tmp_path):
     assert a[0] == 0 and a[-1] == 0
     assert np.max(np.abs(a - refv["avec"])) < 2e-6 * np.abs(refv["avec"]).max()
     assert abs(np.vdot(a, v) - 1.0) < 1e-6   # 8 printed digits
-    dots = [ln for ln in r.stdout.splitlines() if ln.startswith(" (") and ln.rstrip().endswith(")")]
+    import re
+    dots = re.findall(r"\(([-+0-9.eE]+),([-+0-9.eE]+)\)", r.stdout)   # the first follows the prompt on its line
     assert len(dots) == 2
-    d2 = complex(*[float(x) for x in dots[1].strip(" ()").split(",")])
-    assert abs(d2 - 1.0) < 1e-12
+    assert abs(complex(float(dots[1][0]), float(dots[1][1])) - 1.0) < 1e-12
 
 
 UC_DECK = TEMPORAL_DECK.rstrip("\n") + """

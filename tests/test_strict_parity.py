@@ -280,21 +280,25 @@ def test_fast_build_agrees_with_strict_build(engine, osb, monkeypatch):
 
 @pytest.mark.gpu
 def test_sensitivity_classed_tolerances(engine, osb, oracle):
-    """(6) SURVEY 7.3 P2(i): the answer of the REFERENCE algorithm itself moves when its input moves by one
-    ulp (the iteration amplifies rounding where Muller wanders).  Per point, sens = the largest movement of
-    the oracle's eigenvalue under +-1 ulp perturbations of the guess; the fast GPU result must be within
-    max(1e-10, 10 x sens) of the oracle.  Classes are reported.  orrsom (errtol 1e-8) and the orrspace
-    continuation line are the flows whose looser bounds in test_shoot_parity.py this replaces."""
+    """(6) SURVEY 7.3 P2(i).  orrsom and orrspace stop as soon as |err| < 1e-8 (orrsom.f:203, orrspace.f:277):
+    the value they REPORT (ctemp, the last value integrated) is still a distance delta = |c_next - ctemp| away
+    from the root their own last Muller step points at -- 1e-13 ... 1e-9 depending on how the iteration arrived
+    -- and which iterate the loop stops at depends on the phase of err, which is fixed by rounding residues
+    (DESIGN.md section 4).  Two arithmetics therefore agree on such a point to delta, not to 1e-10.  Per point:
+        sens  = largest movement of the oracle's own answer under +-1 ulp perturbations of the guess
+        delta = the oracle's and the GPU's unapplied last update (resid / last two history rows)
+        tol   = max(1e-10, 10 sens, 2 (delta_oracle + delta_gpu))
+    and the classes are reported.  (The strict build reproduces the oracle bit for bit on the same flows.)"""
     rows = []
-    # orrsom decks around the default point
+    # orrsom decks around the default point, far guesses on the low side (up to 13 passes)
     p = engine.solve_bl(osb.FLOW_ORRSOM, osb.INT_RK4, 1000, 0.0, 17.0, 0.5, 0.0)
     prof, _, _ = oracle.solve_bl(ob.FLOW_ORRSOM, ob.INT_RK4, 1000, 0.0, 17.0, 0.5, 0.0)
-    al = (0.179 + 0.002 * np.arange(-16, 9)) * S2   # far guesses on the low side: up to 13 passes
+    al = (0.179 + 0.002 * np.arange(-16, 9)) * S2
     Re = np.full(al.size, 580.0 * S2)
     g = np.full(al.size, GUESS)
     opts = osb.shoot_defaults(osb.FLOW_ORRSOM)
     opts.nstep = 1000
-    r = engine.shoot_temporal(opts, p, al, Re, g)
+    r = engine.shoot_temporal(opts, p, al, Re, g, want_resid=True)
     p.free()
     base = oracle.shoot_temporal_batch(ob.FLOW_ORRSOM, ob.INT_RK4, 1000, 10.0, 0.0, 17.0, prof, al, Re, g)
     assert (base["status"] == 0).all() and (r["status"] == 0).all()
@@ -303,7 +307,8 @@ def test_sensitivity_classed_tolerances(engine, osb, oracle):
                g.real + 1j * np.nextafter(g.imag, 1.0)):
         pert = oracle.shoot_temporal_batch(ob.FLOW_ORRSOM, ob.INT_RK4, 1000, 10.0, 0.0, 17.0, prof, al, Re, dg)
         sens = np.maximum(sens, rel(pert["c"], base["c"]))
-    rows.append(("orrsom", rel(r["c"], base["c"]), sens))
+    delta = (base["absdc"] + r["resid"][:, 1]) / np.abs(base["c"])
+    rows.append(("orrsom", rel(r["c"], base["c"]), sens, delta))
     # orrspace sweep.inp line: the perturbation is applied to the first alpha guess and propagates by continuation
     ymin, ymax = 0.0, 20.0 * FACT
     p = engine.solve_bl(osb.FLOW_ORRSPACE, osb.INT_RK4, 1000, ymin, ymax, 0.5, 0.0)
@@ -311,21 +316,31 @@ def test_sensitivity_classed_tolerances(engine, osb, oracle):
     opts = osb.shoot_defaults(osb.FLOW_ORRSPACE)
     opts.nstep, opts.ymin, opts.ymax, opts.testalpha = 1000, ymin, ymax, 0.9
     a0 = complex(0.13809592, 0.0051958399) * FACT
-    rr = engine.shoot_spatial_lines(opts, p, [1000.0 * FACT], [0.042 * FACT], [0.002 * FACT], [a0], 50)
+    rr = engine.shoot_spatial_lines(opts, p, [1000.0 * FACT], [0.042 * FACT], [0.002 * FACT], [a0], 50, hist_cap=50)
     p.free()
     assert (rr["status"] == 0).all()
     line = lambda a: oracle.shoot_spatial_line(ob.INT_RK4, 1000, 0.9, ymin, ymax, prof, 1000.0 * FACT, 0.042 * FACT,
-                                               0.002 * FACT, a, 50)["alpha"]
+                                               0.002 * FACT, a, 50)
     base = line(a0)
     sens = np.zeros(50)
     for a in (complex(np.nextafter(a0.real, 1.0), a0.imag), complex(np.nextafter(a0.real, 0.0), a0.imag),
               complex(a0.real, np.nextafter(a0.imag, 1.0))):
-        sens = np.maximum(sens, rel(line(a), base))
-    rows.append(("orrspace sweep.inp", rel(rr["alpha"][0], base), sens))
-    for name, err, sens in rows:
-        tol = np.maximum(1e-10, 10.0 * sens)
-        cls = {"sens<=1e-11 (tol 1e-10)": np.mean(sens <= 1e-11), "1e-11<sens<=1e-9": np.mean((sens > 1e-11) & (sens <= 1e-9)),
-               "sens>1e-9": np.mean(sens > 1e-9)}
-        print(f"{name}: max err {err.max():.2e}, max sens {sens.max():.2e}, classes {cls}, "
-              f"err/tol max {np.max(err / tol):.2f}")
+        sens = np.maximum(sens, rel(line(a)["alpha"], base["alpha"]))
+    # the GPU's unapplied update from the last two rows of its per-pass table: |err| / |d err / d alpha|
+    dg = np.zeros(50)
+    for i in range(50):
+        n = rr["passes"][0, i]
+        h = rr["history"][0, i]
+        a_n, a_m = complex(h[n - 1, 0], h[n - 1, 1]), complex(h[n - 2, 0], h[n - 2, 1])
+        e_n, e_m = complex(h[n - 1, 2], h[n - 1, 3]), complex(h[n - 2, 2], h[n - 2, 3])
+        dg[i] = abs(e_n) / abs((e_n - e_m) / (a_n - a_m))
+    delta = (base["absdc"] + dg) / np.abs(base["alpha"])
+    rows.append(("orrspace sweep.inp", rel(rr["alpha"][0], base["alpha"]), sens, delta))
+    for name, err, sens, delta in rows:
+        tol = np.maximum(1e-10, np.maximum(10.0 * sens, 2.0 * delta))
+        cls = {"tol = 1e-10": float(np.mean(tol <= 1e-10)),
+               "tol = 10 x 1-ulp sensitivity": float(np.mean((tol > 1e-10) & (10.0 * sens >= 2.0 * delta))),
+               "tol = 2 x unapplied last update (errtol 1e-8)": float(np.mean((tol > 1e-10) & (10.0 * sens < 2.0 * delta)))}
+        print(f"{name}: max err {err.max():.2e}, max sens {sens.max():.2e}, max delta {delta.max():.2e}, classes {cls}, "
+              f"err/tol max {np.max(err / tol):.2f}; points beyond 1e-10: {int(np.sum(err > 1e-10))} of {err.size}")
         assert (err <= tol).all(), (name, np.max(err / tol))
