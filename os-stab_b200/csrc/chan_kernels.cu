@@ -328,13 +328,403 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
   }
 }
 
+// 16-byte / 4-byte asynchronous global -> shared copies; !valid zero-fills the destination
+__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src, bool valid) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+
+// ---------------------------------------------------------------------------
+// K4 for large n (the one-CTA-per-SM kernel, n > ~350): TWO-LEVEL blocked LU.
+// With a single 16-column blocking the right-looking update sweeps the whole trailing matrix n/16 times; at
+// n = 511 that is 253 MB of DRAM traffic for a 4.2 MB matrix (148 concurrent matrices do not fit the L2) and
+// the kernel is bound by it (ncu round 1: long_scoreboard 49 %, DMMA pipe 15 %).  Here the matrix is processed
+// in OUTER panels of 64 columns:
+//   * inside an outer panel the 16-column panels are factorised as before (shared-memory panel, pivot search,
+//     rank-1 updates), but their row interchanges, U12 solves and DMMA updates touch only the other columns
+//     of the outer panel (<= 48 columns, L2-resident);
+//   * once per outer panel: the 64 interchanges are applied to the rest of the matrix, U12 = L11^{-1} A12 is
+//     solved with the 64 x 64 unit-lower L11 staged in shared memory, and the trailing matrix is updated with
+//     k = 64: A22 -= L21 U12 in 64 x 64 super-tiles whose operands are staged in shared memory once per CTA
+//     (the 64 x 64 L21 block and the 64 x 64 U12 strip, reused by all warps) and read from there by the
+//     mma.sync.m8n8k4.f64 (DMMA) tiles.  The trailing matrix is read and written n/64 times: 4x less traffic.
+// Same pivoting rule and the same elimination order inside a column as cta_lu: identical pivots; the updates
+// of a trailing entry are accumulated in the same order k = 0, 1, ... (results agree to rounding).
+// ---------------------------------------------------------------------------
+// Two shapes: <16, 64> for the 512-thread one-CTA-per-SM kernel, and <8, 32> whose panel (8 columns) and
+// staging area (32-deep) leave room for TWO 256-thread CTAs per SM, so that one CTA's latency-bound phases
+// (pivot search, substitutions) overlap the other's DMMA update.
+constexpr int CH_ST = 64;  // columns of a super-tile of the big update
+// Super-tile rows SR and staging of the L21 blocks, per shape:
+//   <16, 64> (512 threads): SR = 64, 16 warp tiles, one L buffer (a second one does not fit next to the U strip)
+//   <8, 32>  (256 threads): SR = 32,  8 warp tiles, TWO L buffers: the next block arrives by cp.async while this one is used
+__host__ __device__ constexpr int ch_sr(int nbo) { return nbo == 64 ? 64 : 32; }
+__host__ __device__ constexpr bool ch_db(int nbo) { return nbo != 64; }
+__host__ __device__ constexpr int ch_ldl(int nbo) { return ch_sr(nbo) + 2; }  // staged L21 block: [k][row], padded against bank conflicts
+__host__ __device__ constexpr int ch_ldu(int nbo) { return nbo + 4; }         // staged U12 strip: [col][k]
+__host__ __device__ constexpr size_t chan_stage_elems(int nbo) {
+  return (size_t)(ch_db(nbo) ? 2 : 1) * nbo * ch_ldl(nbo) + (size_t)CH_ST * ch_ldu(nbo);
+}
+
+// A22 -= L21 U12 with k = nbo (<= NBO): SR x 64 super-tiles, operands staged in shared memory, a warp per 16 x 16 tile
+template <int NBO>
+__device__ __forceinline__ void lu2_big_update(double2 *__restrict__ M, int n, int K0, int KE, int nbo, int MT, double2 *stage) {
+  constexpr int SR = ch_sr(NBO), LDL = ch_ldl(NBO), LDU = ch_ldu(NBO), LBUF = NBO * LDL;
+  constexpr bool DB = ch_db(NBO);
+  constexpr int TR = SR / 16;  // tile rows per super-tile; 4 tile columns
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t4 = lane & 3;
+  double2 *sU = stage + (DB ? 2 : 1) * LBUF;
+  const int ncs = (MT + CH_ST - 1) / CH_ST, nrs = (MT + SR - 1) / SR;
+  auto stage_L = [&](int I, double2 *dst) {
+    for (int e = tid; e < NBO * SR; e += nt) {
+      const int r = e % SR, k = e / SR;
+      const bool ok = k < nbo && I * SR + r < MT;
+      const double2 *src = M + (size_t)(K0 + (ok ? k : 0)) * n + KE + (ok ? I * SR + r : 0);
+      if (DB) cp_async16(dst + k * LDL + r, src, ok);
+      else dst[k * LDL + r] = ok ? *src : make_double2(0.0, 0.0);
+    }
+  };
+  for (int J = 0; J < ncs; ++J) {
+    const int C0 = J * CH_ST;
+    __syncthreads();  // every warp is done with the previous strip's buffers
+    for (int e = tid; e < NBO * CH_ST; e += nt) {  // U12 strip: sU[col][k]
+      const int k = e % NBO, c = e / NBO;
+      double2 v = make_double2(0.0, 0.0);
+      if (k < nbo && C0 + c < MT) v = M[(size_t)(KE + C0 + c) * n + K0 + k];
+      sU[c * LDU + k] = v;
+    }
+    if (DB) { stage_L(0, stage); cp_async_commit(); }
+    for (int I = 0; I < nrs; ++I) {
+      const int R0 = I * SR;
+      double2 *sL = stage + (DB ? (I & 1) * LBUF : 0);
+      // this warp's first tile: its C block is requested before the barrier so that its latency overlaps the wait
+      const int tile0 = warp;
+      const int tr0 = (tile0 % TR) << 4, tc0 = (tile0 / TR) << 4;
+      const bool have0 = tile0 < TR * 4 && R0 + tr0 < MT && C0 + tc0 < MT;
+      double cr[2][2][2], ci[2][2][2];
+      if (have0) {
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+          for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = R0 + tr0 + 8 * rt + g, j = C0 + tc0 + 8 * ct + 2 * t4 + e;
+              double2 v = make_double2(0.0, 0.0);
+              if (i < MT && j < MT) v = M[(size_t)(KE + j) * n + KE + i];
+              cr[rt][ct][e] = v.x; ci[rt][ct][e] = v.y;
+            }
+      }
+      if (DB) {
+        cp_async_wait<0>();
+        __syncthreads();  // block I has landed for everybody; everybody is done with block I-1
+        if (I + 1 < nrs) { stage_L(I + 1, stage + ((I + 1) & 1) * LBUF); cp_async_commit(); }
+      } else {
+        __syncthreads();
+        stage_L(I, sL);
+        __syncthreads();
+      }
+      if (have0) {  // one tile per warp: TR * 4 == warps per CTA for both shapes
+        const int tr = tr0, tc = tc0;
+#pragma unroll 4
+        for (int ks = 0; ks < NBO / 4; ++ks) {
+          const int k = 4 * ks + t4;
+          double lr[2], li[2], ur[2], ui[2];
+#pragma unroll
+          for (int rt = 0; rt < 2; ++rt) {
+            const double2 l = sL[k * LDL + tr + 8 * rt + g];
+            lr[rt] = l.x; li[rt] = l.y;
+          }
+#pragma unroll
+          for (int ct = 0; ct < 2; ++ct) {
+            const double2 uu = sU[(tc + 8 * ct + g) * LDU + k];
+            ur[ct] = uu.x; ui[ct] = uu.y;
+          }
+#pragma unroll
+          for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) {
+              dmma884(cr[rt][ct][0], cr[rt][ct][1], -lr[rt], ur[ct]);
+              dmma884(cr[rt][ct][0], cr[rt][ct][1], li[rt], ui[ct]);
+              dmma884(ci[rt][ct][0], ci[rt][ct][1], -lr[rt], ui[ct]);
+              dmma884(ci[rt][ct][0], ci[rt][ct][1], -li[rt], ur[ct]);
+            }
+        }
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+          for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = R0 + tr + 8 * rt + g, j = C0 + tc + 8 * ct + 2 * t4 + e;
+              if (i < MT && j < MT) M[(size_t)(KE + j) * n + KE + i] = make_double2(cr[rt][ct][e], ci[rt][ct][e]);
+            }
+      }
+    }
+  }
+}
+
+template <int NBI, int NBO>
+__device__ __noinline__ void cta_lu2(double2 *__restrict__ M, int n, int *ipiv, double2 *panel, double *red) {
+  constexpr int CH_NBO = NBO;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  const int ldp = n + 16;
+  const int g = lane >> 2, t4 = lane & 3;
+  int *red_i = (int *)(red + 2 * (CH_THREADS_MAX / 32));
+  for (int K0 = 0; K0 < n; K0 += CH_NBO) {
+    const int nbo = min(CH_NBO, n - K0);
+    const int KE = K0 + nbo;  // end of the outer panel
+    // ================= factorise the outer panel, 16 columns at a time =================
+    for (int k0 = K0; k0 < KE; k0 += NBI) {
+      const int nb = min(NBI, KE - k0), mp = n - k0;
+      PROF_T0();
+      for (int e = tid; e < mp * nb; e += nt) {
+        const int r = e % mp, c = e / mp;
+        panel[c * ldp + r] = M[(size_t)(k0 + c) * n + k0 + r];
+      }
+      __syncthreads();
+      for (int j = 0; j < nb; ++j) {
+        double best = -1.0;
+        int bi = j;
+        for (int r = j + tid; r < mp; r += nt) {
+          const double2 v = panel[j * ldp + r];
+          const double a = fabs(v.x) + fabs(v.y);
+          if (a > best) { best = a; bi = r; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) { red[warp] = best; red_i[warp] = bi; }
+        __syncthreads();
+        if (tid == 0) {
+          double b = red[0];
+          int p = red_i[0];
+          for (int w = 1; w < nwarp; ++w)
+            if (red[w] > b || (red[w] == b && red_i[w] < p)) { b = red[w]; p = red_i[w]; }
+          ipiv[k0 + j] = k0 + p;
+          red_i[nwarp] = p;
+        }
+        __syncthreads();
+        const int p = red_i[nwarp];
+        if (p != j && tid < nb) {
+          const double2 t = panel[tid * ldp + j];
+          panel[tid * ldp + j] = panel[tid * ldp + p];
+          panel[tid * ldp + p] = t;
+        }
+        __syncthreads();
+        double2 piv = panel[j * ldp + j];
+        if (piv.x == 0.0 && piv.y == 0.0) piv = make_double2(1.0e-290, 0.0);
+        const double2 rinv = cdiv2(make_double2(1.0, 0.0), piv);
+        for (int r = j + 1 + tid; r < mp; r += nt) {
+          const double2 l = cmul2(panel[j * ldp + r], rinv);
+          panel[j * ldp + r] = l;
+          for (int c0 = j + 1; c0 < nb; c0 += 4) {
+            double2 uu[4], m[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int c = min(c0 + q, nb - 1);
+              uu[q] = panel[c * ldp + j];
+              m[q] = panel[c * ldp + r];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (c0 + q < nb) panel[(c0 + q) * ldp + r] = cfnma2(m[q], l, uu[q]);
+          }
+        }
+        __syncthreads();
+      }
+      PROF_ADD(1);
+      // ---- interchanges on the OTHER columns of the outer panel; write the panel back
+      for (int c = K0 + tid; c < KE; c += nt) {
+        if (c >= k0 && c < k0 + nb) continue;
+        double2 *col = M + (size_t)c * n;
+        for (int j = 0; j < nb; ++j) {
+          const int p = ipiv[k0 + j];
+          if (p != k0 + j) { const double2 t = col[k0 + j]; col[k0 + j] = col[p]; col[p] = t; }
+        }
+      }
+      for (int e = tid; e < mp * nb; e += nt) {
+        const int r = e % mp, c = e / mp;
+        M[(size_t)(k0 + c) * n + k0 + r] = panel[c * ldp + r];
+      }
+      __syncthreads();
+      PROF_ADD(2);
+      const int nc = KE - k0 - nb;     // columns of the outer panel to the right of this panel
+      const int mt = n - k0 - nb;      // rows below it
+      if (nc <= 0) break;
+      // ---- U12 = L11^{-1} A12 for those columns, one thread per column
+      for (int c = tid; c < nc; c += nt) {
+        double2 *col = M + (size_t)(k0 + nb + c) * n + k0;
+        double2 a[NBI];
+#pragma unroll
+        for (int i = 0; i < NBI; ++i) a[i] = (i < nb) ? col[i] : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int i = 1; i < NBI; ++i) {
+          if (i < nb) {
+            double2 sacc = a[i];
+#pragma unroll
+            for (int t = 0; t < i; ++t) sacc = cfnma2(sacc, panel[t * ldp + i], a[t]);
+            a[i] = sacc;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NBI; ++i) if (i < nb) col[i] = a[i];
+      }
+      __syncthreads();
+      PROF_ADD(3);
+      // ---- update of the outer panel's remaining columns (k = 16, DMMA); a warp owns 16x16 blocks
+      if (nb == NBI && mt > 0) {
+        const int nbr = (mt + 15) >> 4, nbc = (nc + 15) >> 4;
+        for (int blk = warp; blk < nbr * nbc; blk += nwarp) {
+          const int R0 = (blk % nbr) << 4, C0 = (blk / nbr) << 4;
+          double cr[2][2][2], ci[2][2][2];
+#pragma unroll
+          for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int i = R0 + 8 * rt + g, j = C0 + 8 * ct + 2 * t4 + e;
+                double2 v = make_double2(0.0, 0.0);
+                if (i < mt && j < nc) v = M[(size_t)(k0 + nb + j) * n + k0 + nb + i];
+                cr[rt][ct][e] = v.x; ci[rt][ct][e] = v.y;
+              }
+#pragma unroll
+          for (int ks = 0; ks < NBI / 4; ++ks) {
+            const int k = 4 * ks + t4;
+            double lr[2], li[2], ur[2], ui[2];
+#pragma unroll
+            for (int rt = 0; rt < 2; ++rt) {
+              const double2 l = panel[k * ldp + nb + R0 + 8 * rt + g];
+              lr[rt] = l.x; li[rt] = l.y;
+            }
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) {
+              const int j = min(C0 + 8 * ct + g, nc - 1);
+              const double2 uu = M[(size_t)(k0 + nb + j) * n + k0 + k];
+              ur[ct] = uu.x; ui[ct] = uu.y;
+            }
+#pragma unroll
+            for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+              for (int ct = 0; ct < 2; ++ct) {
+                dmma884(cr[rt][ct][0], cr[rt][ct][1], -lr[rt], ur[ct]);
+                dmma884(cr[rt][ct][0], cr[rt][ct][1], li[rt], ui[ct]);
+                dmma884(ci[rt][ct][0], ci[rt][ct][1], -lr[rt], ui[ct]);
+                dmma884(ci[rt][ct][0], ci[rt][ct][1], -li[rt], ur[ct]);
+              }
+          }
+#pragma unroll
+          for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) {
+                const int i = R0 + 8 * rt + g, j = C0 + 8 * ct + 2 * t4 + e;
+                if (i < mt && j < nc)
+                  M[(size_t)(k0 + nb + j) * n + k0 + nb + i] = make_double2(cr[rt][ct][e], ci[rt][ct][e]);
+              }
+        }
+      }
+      __syncthreads();
+      PROF_ADD(4);
+    }
+    // ================= the rest of the matrix, once per outer panel =================
+    PROF_T0();
+    // ---- the nbo interchanges on the columns outside the outer panel (two interleaved columns per thread)
+    {
+      const int nout = n - nbo;  // columns 0..K0-1 and KE..n-1
+      for (int e = tid; e < nout; e += 2 * nt) {
+        const int eb = e + nt;
+        const bool dob = eb < nout;
+        const int ca = e < K0 ? e : e + nbo, cb = dob ? (eb < K0 ? eb : eb + nbo) : ca;
+        double2 *cola = M + (size_t)ca * n, *colb = M + (size_t)cb * n;
+        for (int j = 0; j < nbo; ++j) {
+          const int p = ipiv[K0 + j];
+          if (p != K0 + j) {
+            const double2 ta = cola[K0 + j], pa = cola[p];
+            double2 tb, pb;
+            if (dob) { tb = colb[K0 + j]; pb = colb[p]; }
+            cola[K0 + j] = pa; cola[p] = ta;
+            if (dob) { colb[K0 + j] = pb; colb[p] = tb; }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    PROF_ADD(2);
+    const int MT = n - KE;  // trailing size
+    if (MT <= 0) break;
+    // ---- U12 = L11^{-1} A12 (nbo x MT): L11 (unit lower, nbo x nbo) staged in shared memory [col][row]
+    double2 *l11 = panel;  // the panel buffer is free between outer-panel factorisations
+    for (int e = tid; e < nbo * nbo; e += nt) {
+      const int r = e % nbo, c = e / nbo;
+      l11[c * CH_NBO + r] = M[(size_t)(K0 + c) * n + K0 + r];
+    }
+    __syncthreads();
+    for (int c = tid; c < MT; c += nt) {
+      double2 *col = M + (size_t)(KE + c) * n + K0;
+      for (int i0 = 0; i0 < nbo; i0 += CH_NB) {   // 16 rows at a time: registers hold one chunk
+        const int ni = min(CH_NB, nbo - i0);
+        double2 a[CH_NB];
+#pragma unroll
+        for (int i = 0; i < CH_NB; ++i) a[i] = (i < ni) ? col[i0 + i] : make_double2(0.0, 0.0);
+        for (int t = 0; t < i0; ++t) {            // rows solved in earlier chunks
+          const double2 ut = col[t];
+#pragma unroll
+          for (int i = 0; i < CH_NB; ++i)
+            if (i < ni) a[i] = cfnma2(a[i], l11[t * CH_NBO + i0 + i], ut);
+        }
+#pragma unroll
+        for (int i = 1; i < CH_NB; ++i) {
+          if (i < ni) {
+            double2 sacc = a[i];
+#pragma unroll
+            for (int t = 0; t < i; ++t) sacc = cfnma2(sacc, l11[(i0 + t) * CH_NBO + i0 + i], a[t]);
+            a[i] = sacc;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < CH_NB; ++i) if (i < ni) col[i0 + i] = a[i];
+      }
+    }
+    __syncthreads();
+    PROF_ADD(3);
+    // ---- A22 -= L21 U12 with k = nbo, operands staged in shared memory (the panel buffer is free here)
+    lu2_big_update<NBO>(M, n, K0, KE, nbo, MT, panel);
+    __syncthreads();
+    PROF_ADD(4);
+  }
+}
+
 // x <- M^{-1} x using P M = L U.  x: shared, n complex.  Blocked by 16 columns: the
 // 16x16 diagonal block is staged in shared memory and solved by one warp with shuffles,
 // then all threads apply the 16 solved values to the remaining rows (coalesced column
 // reads): 2 barriers per block instead of one per column.
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv, double2 *x) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   __shared__ double2 dblk[16][17];
+  // Large matrices are streamed from DRAM by every solve (hundreds of concurrent 4 MB factorisations do not fit the
+  // L2) and each block step waits for its 16 columns: the NEXT step's columns are requested into the L2 one step
+  // ahead (one prefetch per 128-byte line).
+  const bool pf = n > 128;
   if (tid == 0)
     for (int k = 0; k < n; ++k) {
       const int p = ipiv[k];
@@ -349,6 +739,11 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
       if (r < nb && c < nb) dblk[r][c] = M[(size_t)(j0 + c) * n + j0 + r];
     }
     __syncthreads();
+    if (pf && j0 + 16 < n)
+      for (int r = j0 + 16 + 8 * tid; r < n; r += 8 * nt)
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          if (j0 + 16 + t < n) prefetch_l2(M + (size_t)(j0 + 16 + t) * n + r);
     if (warp == 0) {
       double2 xi = (lane < nb) ? x[j0 + lane] : make_double2(0.0, 0.0);
       for (int t = 0; t < nb; ++t) {
@@ -374,6 +769,10 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
       if (r < nb && c < nb) dblk[r][c] = M[(size_t)(j0 + c) * n + j0 + r];
     }
     __syncthreads();
+    if (pf && j0 >= 16)
+      for (int r = 8 * tid; r < j0; r += 8 * nt)
+#pragma unroll
+        for (int t = 0; t < 16; ++t) prefetch_l2(M + (size_t)(j0 - 16 + t) * n + r);
     if (warp == 0) {
       double2 xi = (lane < nb) ? x[j0 + lane] : make_double2(0.0, 0.0);
       for (int t = nb - 1; t >= 0; --t) {
@@ -478,10 +877,19 @@ struct ChanShared {
   double *red;
 };
 
-__device__ ChanShared carve(unsigned char *smem, int n) {
+// n >= CH_BIG_MIN_N: two CTAs of the 256-thread kernel no longer fit an SM by shared memory (308 n + 4640 bytes
+// each); those sizes run the one-CTA-per-SM kernel with the two-level LU, whose staging area shares the panel buffer
+constexpr int CH_BIG_MIN_N = 351;
+// LU variants: 0 = single-level, 16-column panel (cta_lu); 1 = two-level <16, 64>; 2 = two-level <8, 32>
+__host__ __device__ inline size_t chan_panel_elems(int n, int variant) {
+  if (variant == 0) return (size_t)(n + 16) * CH_NB;
+  const size_t p = (size_t)(n + 16) * (variant == 1 ? 16 : 8), st = chan_stage_elems(variant == 1 ? 64 : 32);  // (NBO)
+  return p > st ? p : st;
+}
+__device__ ChanShared carve(unsigned char *smem, int n, int variant = 0) {
   ChanShared s;
   size_t off = 0;
-  s.panel = (double2 *)(smem + off); off += sizeof(double2) * (size_t)(n + 16) * CH_NB;
+  s.panel = (double2 *)(smem + off); off += sizeof(double2) * chan_panel_elems(n, variant);
   s.x = (double2 *)(smem + off); off += sizeof(double2) * (size_t)n;
   s.y = (double2 *)(smem + off); off += sizeof(double2) * (size_t)n;
   s.t = (double2 *)(smem + off); off += sizeof(double2) * (size_t)n;
@@ -494,8 +902,8 @@ __device__ ChanShared carve(unsigned char *smem, int n) {
 // memory next to the panel, so every phase runs at shared-memory latency.
 constexpr int CH_NSMEM = 64;
 __host__ __device__ inline bool chan_matrix_in_smem(int n) { return n <= CH_NSMEM; }
-__host__ __device__ inline size_t chan_fixed_smem(int n) {
-  size_t b = sizeof(double2) * ((size_t)(n + 16) * CH_NB + 3 * (size_t)n) + sizeof(double) * 64 + sizeof(int) * (size_t)(n + 8);
+__host__ __device__ inline size_t chan_fixed_smem(int n, int variant = 0) {
+  size_t b = sizeof(double2) * (chan_panel_elems(n, variant) + 3 * (size_t)n) + sizeof(double) * 64 + sizeof(int) * (size_t)(n + 8);
   return (b + 15) & ~(size_t)15;
 }
 size_t chan_smem_bytes(int n) {
@@ -513,27 +921,35 @@ size_t chan_smem_bytes(int n) {
 // extrapolation (tests compare the two).
 struct ConvTrack {
   double d0, d1, d2;  // the last three measured changes of omega, d0 newest
+  double dmax;        // the largest change between successive estimates seen so far
 };
-__device__ __forceinline__ void conv_reset(ConvTrack &t) { t.d0 = t.d1 = t.d2 = 1.0e300; }
-__device__ __forceinline__ bool conv_push(ConvTrack &t, int it, double change, double goal, int early, double *est) {
+__device__ __forceinline__ void conv_reset(ConvTrack &t) { t.d0 = t.d1 = t.d2 = 1.0e300; t.dmax = 0.0; }
+// returns 0: keep iterating; 1: converged (measured change below the goal, or the early stop above);
+// 2: stalled at the rounding floor -- the changes have dropped by 1e6 from their maximum and stopped
+// contracting although the goal is not met (ill-conditioned pencils: Chebyshev collocation at N >= 256, SURVEY
+// H7).  More solves, or a re-shift with a new factorisation, cannot improve such a point; *est stays the
+// measured change and the host reports the point as not converged if that is above its 1e-12 criterion.
+__device__ __forceinline__ int conv_push(ConvTrack &t, int it, double change, double goal, int early, double *est) {
   t.d2 = t.d1; t.d1 = t.d0; t.d0 = change;
   *est = change;
-  if (it > 0 && change <= goal) return true;
+  if (it > 0 && change <= goal) return 1;
+  if (it >= 1) t.dmax = fmax(t.dmax, change);
   if (early && it >= 3 && t.d2 < 1.0e299) {
     const double rho = t.d0 / t.d1, rho1 = t.d1 / t.d2;
     if (rho < 0.05 && rho1 < 0.05 && rho <= 2.0 * rho1) {
       const double rem = t.d0 * rho / (1.0 - rho);
-      if (rem <= 0.5 * goal) { *est = rem; return true; }
+      if (rem <= 0.5 * goal) { *est = rem; return 1; }
     }
   }
-  return false;
+  if (it >= 3 && t.d0 >= 0.5 * t.d1 && t.d0 <= 1.0e-6 * t.dmax) return 2;
+  return 0;
 }
 
 // Right inverse iteration with the current LU: x (unit 2-norm, shared) in/out.
 // Returns the eigenvalue estimate after up to maxit iterations; *delta = last change.
 __device__ double2 inverse_iterate(const double2 *M, int n, const double *D2, const PencilCoef &p,
                                    double2 sigma, ChanShared &s, int maxit, double tol, int early, double *delta,
-                                   int *iters) {
+                                   int *iters, int *stalled = nullptr) {
   double2 om = sigma;
   ConvTrack ct;
   conv_reset(ct);
@@ -566,7 +982,8 @@ __device__ double2 inverse_iterate(const double2 *M, int n, const double *D2, co
     const double change = hypot(om_new.x - om.x, om_new.y - om.y);
     om = om_new;
     const double goal = tol * hypot(om.x, om.y);
-    if (conv_push(ct, it, change, goal, early, &est)) { ++it; break; }
+    const int cv = conv_push(ct, it, change, goal, early, &est);
+    if (cv) { ++it; if (stalled) *stalled = (cv == 2); break; }
     if (it + 1 >= maxit) {
       const double rho = ct.d0 / ct.d1;
       if (!(rho < 0.5) || !(ct.d0 > 0.0) || log(goal / ct.d0) / log(rho) > 6.0) { ++it; break; }
@@ -630,69 +1047,80 @@ __device__ void start_vector(double2 *x, int n) {
 
 // Left (adjoint) eigenvector of the converged mode; kept out of line so that its second LU call site does not
 // weigh on the register allocation of the sweep path.
+template <int LUV>
 __device__ __noinline__ void cta_adjoint(const ChanArgs &a, ChanShared &s, double2 *M, const PencilCoef &p, double2 om,
                                          double2 esc, int64_t inst) {
   const int n = a.n;
-    // Left eigenvector u, u^H (A - w B) = 0, by inverse iteration on the adjoint pencil
-    //     u <- (A - s B)^{-H} B^H u
-    // with a fresh factorisation at s = w (1 + 1e-8): every solve then contracts the other modes by ~1e-8 |w| / gap.
-    const double2 sg = make_double2(om.x + 1.0e-8 * hypot(om.x, om.y), om.y);
-    assemble_shifted(M, n, a.D2, a.D4, a.u, a.d2u, p, sg);
-    cta_lu(M, n, s.ipiv, s.panel, s.red);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) s.t[i] = make_double2(s.x[i].x, 0.3 - s.x[i].y);
+  // Left eigenvector u, u^H (A - w B) = 0, by inverse iteration on the adjoint pencil
+  //     u <- (A - s B)^{-H} B^H u
+  // with a fresh factorisation at s = w (1 + 1e-8): every solve then contracts the other modes by ~1e-8 |w| / gap.
+  const double2 sg = make_double2(om.x + 1.0e-8 * hypot(om.x, om.y), om.y);
+  assemble_shifted(M, n, a.D2, a.D4, a.u, a.d2u, p, sg);
+  if (LUV == 1) cta_lu2<16, 64>(M, n, s.ipiv, s.panel, s.red);
+  else if (LUV == 2) cta_lu2<8, 32>(M, n, s.ipiv, s.panel, s.red);
+  else cta_lu(M, n, s.ipiv, s.panel, s.red);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s.t[i] = make_double2(s.x[i].x, 0.3 - s.x[i].y);
+  __syncthreads();
+  for (int k = 0; k < 4; ++k) {
+    cta_d2_matvec(a.D2, n, s.t, s.y, true);  // D2^T u
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      s.y[i] = cadd2(cmulc2(p.b2, s.y[i]), cmulc2(p.b0, s.t[i]));  // B^H u
     __syncthreads();
-    for (int k = 0; k < 4; ++k) {
-      cta_d2_matvec(a.D2, n, s.t, s.y, true);  // D2^T u
-      for (int i = threadIdx.x; i < n; i += blockDim.x)
-        s.y[i] = cadd2(cmulc2(p.b2, s.y[i]), cmulc2(p.b0, s.t[i]));  // B^H u
-      __syncthreads();
-      cta_solve_h(M, n, s.ipiv, s.y);
-      double nn = 0.0;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) nn += s.y[i].x * s.y[i].x + s.y[i].y * s.y[i].y;
-      const double rn = rsqrt(block_sum(make_double2(nn, 0.0), s.red).x);
-      for (int i = threadIdx.x; i < n; i += blockDim.x) s.t[i] = make_double2(s.y[i].x * rn, s.y[i].y * rn);
-      __syncthreads();
-    }
-    double2 *av = a.adj + (size_t)inst * (n + 2);
-    if (a.adj_form == OSB_ADJ_PENCIL) {
-      // escale = zdotc(avec, evec); avec <- avec / conj(escale)   (orrcolchan.f:537-545)
-      double2 d = make_double2(0.0, 0.0);
-      for (int i = threadIdx.x; i < n; i += blockDim.x) d = cadd2(d, cmulc2(s.t[i], cmul2(esc, s.x[i])));
-      d = block_sum(d, s.red);
-      const double2 sc = cdiv2(make_double2(1.0, 0.0), make_double2(d.x, -d.y));
-      for (int i = threadIdx.x; i < n; i += blockDim.x) av[i + 1] = cmul2(sc, s.t[i]);
-    } else {
-      // vl = B^H u, then ZGEEV's normalisation: unit 2-norm, largest component real (positive)
-      cta_d2_matvec(a.D2, n, s.t, s.y, true);
-      double nn = 0.0;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double2 v = cadd2(cmulc2(p.b2, s.y[i]), cmulc2(p.b0, s.t[i]));
-        s.y[i] = v;
-        nn += v.x * v.x + v.y * v.y;
-      }
-      const double rn = rsqrt(block_sum(make_double2(nn, 0.0), s.red).x);
-      const int k = block_argmax_abs(s.y, n);
-      const double2 vk = s.y[k];
-      const double ak = hypot(vk.x, vk.y);
-      const double2 ph = make_double2(rn * vk.x / ak, -rn * vk.y / ak);  // rn * conj(v_k) / |v_k|
-      for (int i = threadIdx.x; i < n; i += blockDim.x) av[i + 1] = cmul2(ph, s.y[i]);
-    }
-    if (threadIdx.x == 0) { av[0] = make_double2(0.0, 0.0); av[n + 1] = make_double2(0.0, 0.0); }
+    cta_solve_h(M, n, s.ipiv, s.y);
+    double nn = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) nn += s.y[i].x * s.y[i].x + s.y[i].y * s.y[i].y;
+    const double rn = rsqrt(block_sum(make_double2(nn, 0.0), s.red).x);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s.t[i] = make_double2(s.y[i].x * rn, s.y[i].y * rn);
+    __syncthreads();
   }
+  double2 *av = a.adj + (size_t)inst * (n + 2);
+  if (a.adj_form == OSB_ADJ_PENCIL) {
+    // escale = zdotc(avec, evec); avec <- avec / conj(escale)   (orrcolchan.f:537-545)
+    double2 d = make_double2(0.0, 0.0);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) d = cadd2(d, cmulc2(s.t[i], cmul2(esc, s.x[i])));
+    d = block_sum(d, s.red);
+    const double2 sc = cdiv2(make_double2(1.0, 0.0), make_double2(d.x, -d.y));
+    for (int i = threadIdx.x; i < n; i += blockDim.x) av[i + 1] = cmul2(sc, s.t[i]);
+  } else {
+    // vl = B^H u, then ZGEEV's normalisation: unit 2-norm, largest component real (positive)
+    cta_d2_matvec(a.D2, n, s.t, s.y, true);
+    double nn = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const double2 v = cadd2(cmulc2(p.b2, s.y[i]), cmulc2(p.b0, s.t[i]));
+      s.y[i] = v;
+      nn += v.x * v.x + v.y * v.y;
+    }
+    const double rn = rsqrt(block_sum(make_double2(nn, 0.0), s.red).x);
+    const int k = block_argmax_abs(s.y, n);
+    const double2 vk = s.y[k];
+    const double ak = hypot(vk.x, vk.y);
+    const double2 ph = make_double2(rn * vk.x / ak, -rn * vk.y / ak);  // rn * conj(v_k) / |v_k|
+    for (int i = threadIdx.x; i < n; i += blockDim.x) av[i + 1] = cmul2(ph, s.y[i]);
+  }
+  if (threadIdx.x == 0) { av[0] = make_double2(0.0, 0.0); av[n + 1] = make_double2(0.0, 0.0); }
+}
 
 // Two register budgets for the same body: up to n ~ 350 two CTAs fit an SM by shared
 // memory and 128 registers/thread keeps them both resident; beyond that the 135 KB panel
 // allows one CTA only and the body may use the full register file.
+template <int LUV>
 __device__ __forceinline__ void chan_eig_body(const ChanArgs &a);
-__global__ void __launch_bounds__(CH_THREADS, 2) chan_eig_kernel(const __grid_constant__ ChanArgs a) { chan_eig_body(a); }
-__global__ void __launch_bounds__(CH_THREADS_BIG, 1) chan_eig_kernel_big(const __grid_constant__ ChanArgs a) { chan_eig_body(a); }
+__global__ void __launch_bounds__(CH_THREADS, 2) chan_eig_kernel(const __grid_constant__ ChanArgs a) { chan_eig_body<0>(a); }
+// n >= CH_BIG_MIN_N, three builds (OSB_CHAN_BIG = 2 | 1 | 0 selects; default 2 while two CTAs fit an SM):
+//   _big2    256 threads, two CTAs per SM, two-level LU <8, 32>
+//   _big     512 threads, one CTA per SM, two-level LU <16, 64>
+//   _big_lu1 512 threads, one CTA per SM, the single-level LU (the round-1 kernel, kept for A/B measurements)
+__global__ void __launch_bounds__(CH_THREADS, 2) chan_eig_kernel_big2(const __grid_constant__ ChanArgs a) { chan_eig_body<2>(a); }
+__global__ void __launch_bounds__(CH_THREADS_BIG, 1) chan_eig_kernel_big(const __grid_constant__ ChanArgs a) { chan_eig_body<1>(a); }
+__global__ void __launch_bounds__(CH_THREADS_BIG, 1) chan_eig_kernel_big_lu1(const __grid_constant__ ChanArgs a) { chan_eig_body<0>(a); }
 // 64 < n <= 200: the serial phases (panel, triangular solves) dominate and a row per thread is all the
 // panel can use; four small CTAs per SM overlap each other's barriers
-__global__ void __launch_bounds__(CH_THREADS_SMALL, 4) chan_eig_kernel_small(const __grid_constant__ ChanArgs a) { chan_eig_body(a); }
+__global__ void __launch_bounds__(CH_THREADS_SMALL, 4) chan_eig_kernel_small(const __grid_constant__ ChanArgs a) { chan_eig_body<0>(a); }
+template <int LUV>
 __device__ __forceinline__ void chan_eig_body(const ChanArgs &a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int n = a.n;
-  ChanShared s = carve(smem, n);
+  ChanShared s = carve(smem, n, LUV);
   double2 *M = chan_matrix_in_smem(n) ? (double2 *)(smem + chan_fixed_smem(n)) : a.work + (size_t)blockIdx.x * n * n;
   for (int64_t inst = blockIdx.x; inst < a.ninst; inst += gridDim.x) {
     const PencilCoef p = pencil_coef(a.alpha[inst], a.Re[inst]);
@@ -705,11 +1133,13 @@ __device__ __forceinline__ void chan_eig_body(const ChanArgs &a) {
       PROF_T0();
       assemble_shifted(M, n, a.D2, a.D4, a.u, a.d2u, p, sigma);
       PROF_ADD(0);
-      cta_lu(M, n, s.ipiv, s.panel, s.red);
-      int it = 0;
-      om = inverse_iterate(M, n, a.D2, p, sigma, s, a.inner, a.tol, a.early, &dl, &it);
+      if (LUV == 1) cta_lu2<16, 64>(M, n, s.ipiv, s.panel, s.red);
+      else if (LUV == 2) cta_lu2<8, 32>(M, n, s.ipiv, s.panel, s.red);
+      else cta_lu(M, n, s.ipiv, s.panel, s.red);
+      int it = 0, stalled = 0;
+      om = inverse_iterate(M, n, a.D2, p, sigma, s, a.inner, a.tol, a.early, &dl, &it, &stalled);
       total += it;
-      if (dl <= a.tol * hypot(om.x, om.y)) break;
+      if (dl <= a.tol * hypot(om.x, om.y) || stalled) break;
       sigma = om;  // re-shift (Rayleigh-quotient style) and refactorise
     }
     if (threadIdx.x == 0) {
@@ -726,7 +1156,7 @@ __device__ __forceinline__ void chan_eig_body(const ChanArgs &a) {
         for (int i = threadIdx.x; i < n; i += blockDim.x) ev[i + 1] = cmul2(esc, s.x[i]);
         if (threadIdx.x == 0) { ev[0] = make_double2(0.0, 0.0); ev[n + 1] = make_double2(0.0, 0.0); }
       }
-      if (a.adj) cta_adjoint(a, s, M, p, om, esc, inst);
+      if (a.adj) cta_adjoint<LUV>(a, s, M, p, om, esc, inst);
     }
     __syncthreads();
   }
@@ -1126,7 +1556,7 @@ __global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constan
   for (int o = 0; o < a.outer; ++o) {
     band_lu_thread(a, p, sigma, U, Lm, piv, S);
     // ---- inverse iteration
-    int it = 0;
+    int it = 0, stalled = 0;
     ConvTrack ct;
     conv_reset(ct);
     for (; it < a.inner; ++it) {
@@ -1187,10 +1617,11 @@ __global__ void __launch_bounds__(64) chan_fd_banded_kernel(const __grid_constan
       }
       const double change = hypot(om_new.x - om.x, om_new.y - om.y);
       om = om_new;
-      if (conv_push(ct, it, change, a.tol * hypot(om.x, om.y), a.early, &dl)) { ++it; break; }
+      const int cv = conv_push(ct, it, change, a.tol * hypot(om.x, om.y), a.early, &dl);
+      if (cv) { ++it; stalled = (cv == 2); break; }
     }
     total += it;
-    if (dl <= a.tol * hypot(om.x, om.y)) break;
+    if (dl <= a.tol * hypot(om.x, om.y) || stalled) break;
     sigma = om;
   }
   a.omega[inst] = om;
@@ -1332,21 +1763,6 @@ struct BandStage {             // per instance, shared memory; [2]: the next chu
   double2 yi[2][BCH], yo[BCH]; // substitution: entering right-hand sides, solved rows
   int pv[2][BCH];
 };
-
-// 16-byte / 4-byte asynchronous global -> shared copies; !valid zero-fills the destination
-__device__ __forceinline__ void cp_async16(void *dst, const void *src, bool valid) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *dst, const void *src, bool valid) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-  const int sz = valid ? 4 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ double2 shfl2(double2 v, int src) {
   return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
@@ -1492,7 +1908,7 @@ __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(con
     __syncwarp();
     PROF_ADD(1);
     // ================= inverse iteration =================
-    bool inner_on = act;
+    bool inner_on = act, stalled = false;
     int it = 0;
     ConvTrack ct;
     conv_reset(ct);
@@ -1638,13 +2054,15 @@ __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(con
         const double change = hypot(om_new.x - om.x, om_new.y - om.y);
         om = om_new;
         it = step + 1;
-        if (conv_push(ct, step, change, a.tol * hypot(om.x, om.y), a.early, &dl)) inner_on = false;
+        const int cv = conv_push(ct, step, change, a.tol * hypot(om.x, om.y), a.early, &dl);
+        if (cv) inner_on = false;
+        if (cv == 2) stalled = true;
       }
       PROF_ADD(0);
     }
     if (act) {
       total += it;
-      if (dl <= a.tol * hypot(om.x, om.y)) done = true;
+      if (dl <= a.tol * hypot(om.x, om.y) || stalled) done = true;
       else sigma = om;  // re-shift (Rayleigh-quotient style) and refactorise
     }
   }
@@ -2022,7 +2440,7 @@ __device__ void w_start_vector(double2 *x, int n) {
 }
 
 __device__ double2 w_inverse_iterate(const WarpShared &s, int n, const double *D2, const PencilCoef &p, double2 sigma,
-                                     int maxit, double tol, int early, double *delta, int *iters) {
+                                     int maxit, double tol, int early, double *delta, int *iters, int *stalled = nullptr) {
   const int lane = threadIdx.x & 31;
   double2 om = sigma;
   double dl = 1.0e300;
@@ -2047,7 +2465,8 @@ __device__ double2 w_inverse_iterate(const WarpShared &s, int n, const double *D
     __syncwarp();
     const double change = hypot(om_new.x - om.x, om_new.y - om.y);
     om = om_new;
-    if (conv_push(ct, it, change, tol * hypot(om.x, om.y), early, &dl)) { ++it; break; }
+    const int cv = conv_push(ct, it, change, tol * hypot(om.x, om.y), early, &dl);
+    if (cv) { ++it; if (stalled) *stalled = (cv == 2); break; }
   }
   *delta = dl;
   *iters = it;
@@ -2068,10 +2487,10 @@ __global__ void __launch_bounds__(32) chan_eig_warp_kernel(const __grid_constant
     for (int o = 0; o < a.outer; ++o) {
       w_assemble(s.M, n, a.D2, a.D4, a.u, a.d2u, p, sigma);
       w_lu(s.M, n, s.ipiv);
-      int it = 0;
-      om = w_inverse_iterate(s, n, a.D2, p, sigma, a.inner, a.tol, a.early, &dl, &it);
+      int it = 0, stalled = 0;
+      om = w_inverse_iterate(s, n, a.D2, p, sigma, a.inner, a.tol, a.early, &dl, &it, &stalled);
       total += it;
-      if (dl <= a.tol * hypot(om.x, om.y)) break;
+      if (dl <= a.tol * hypot(om.x, om.y) || stalled) break;
       sigma = om;
     }
     if (lane == 0) { a.omega[inst] = om; a.delta[inst] = dl; a.iters[inst] = total; }
@@ -2226,8 +2645,9 @@ struct ChanLaunch {
   const double *D2, *D4, *u, *d2u;
 };
 
-static cudaError_t chan_grid(int n, int64_t ninst, int *grid, size_t *smem, const void *func, int threads = CH_THREADS) {
-  *smem = chan_smem_bytes(n);
+static cudaError_t chan_grid(int n, int64_t ninst, int *grid, size_t *smem, const void *func, int threads = CH_THREADS,
+                             int variant = 0) {
+  *smem = variant ? chan_fixed_smem(n, variant) : chan_smem_bytes(n);
   cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem);
   if (e != cudaSuccess) return e;
   int dev = 0, sms = 0, per = 0;
@@ -2269,7 +2689,20 @@ static cudaError_t warp_grid(int n, int64_t ninst, int *grid, size_t *smem, cons
   return cudaSuccess;
 }
 
-static bool use_big_kernel(int n) { return 2 * chan_smem_bytes(n) > 220 * 1024; }
+static bool use_big_kernel(int n) { return n >= CH_BIG_MIN_N; }
+// which build of the big kernel: 2 = two CTAs per SM (while 2 x its shared memory fits), 1 = one CTA per SM two-level
+// LU, 0 = the single-level LU; OSB_CHAN_BIG overrides (A/B measurements)
+static int big_variant(int n) {
+  // two CTAs: 2 x (dynamic + ~11 KB static + 1 KB reserved) must fit the 228 KB of an SM
+  const bool two_fit = 2 * (chan_fixed_smem(n, 2) + 12 * 1024) <= 228 * 1024;
+  // measured on B200 (tools/bench_chan.py, 4096 alpha): N = 384: 37.7 k eig/s (build 2) / 27.2 k (1) / 21.7 k (0);
+  // N = 512: 22.8 k / 17.6 k / 19.5 k; N = 600 (two CTAs no longer fit): 11.1 k (1) / 10.8 k (0)
+  int v = two_fit ? 2 : 0;
+  if (const char *e = getenv("OSB_CHAN_BIG")) v = atoi(e);
+  if (getenv("OSB_CHAN_LU1")) v = 0;
+  if (v == 2 && !two_fit) v = 1;
+  return v;
+}
 static bool use_small_kernel(int n) {
   const char *e = getenv("OSB_CHAN_SMALL_MAX");  // tuning knob; default from measurements on B200
   const int nmax = e ? atoi(e) : 200;
@@ -2296,7 +2729,12 @@ int chan_dense_max_n() {
 
 cudaError_t chan_eig_grid(int n, int64_t ninst, int *grid, size_t *smem) {
   if (use_warp_kernels(n)) return warp_grid(n, ninst, grid, smem, (const void *)chan_eig_warp_kernel);
-  if (use_big_kernel(n)) return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel_big, CH_THREADS_BIG);
+  if (use_big_kernel(n)) {
+    const int v = big_variant(n);
+    if (v == 2) return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel_big2, CH_THREADS, 2);
+    if (v == 1) return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel_big, CH_THREADS_BIG, 1);
+    return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel_big_lu1, CH_THREADS_BIG);
+  }
   if (use_small_kernel(n)) return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel_small, CH_THREADS_SMALL);
   return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel);
 }
@@ -2316,7 +2754,12 @@ cudaError_t launch_chan_eig(int n, const double *D2, const double *D4, const dou
   a.omega = omega; a.delta = delta; a.iters = iters; a.evec = evec; a.adj = adj; a.adj_form = adj_form;
   a.early = getenv("OSB_NO_EARLY_STOP") ? 0 : 1;
   if (use_warp_kernels(n)) chan_eig_warp_kernel<<<grid, 32, smem, st>>>(a);
-  else if (use_big_kernel(n)) chan_eig_kernel_big<<<grid, CH_THREADS_BIG, smem, st>>>(a);
+  else if (use_big_kernel(n)) {
+    const int v = big_variant(n);
+    if (v == 2) chan_eig_kernel_big2<<<grid, CH_THREADS, smem, st>>>(a);
+    else if (v == 1) chan_eig_kernel_big<<<grid, CH_THREADS_BIG, smem, st>>>(a);
+    else chan_eig_kernel_big_lu1<<<grid, CH_THREADS_BIG, smem, st>>>(a);
+  }
   else if (use_small_kernel(n)) chan_eig_kernel_small<<<grid, CH_THREADS_SMALL, smem, st>>>(a);
   else chan_eig_kernel<<<grid, CH_THREADS, smem, st>>>(a);
   return cudaGetLastError();

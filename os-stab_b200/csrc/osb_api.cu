@@ -331,17 +331,19 @@ int osb_profile_blasius_batch(osb_ctx *ctx, int variant, int integrator, int nbl
   OSB_CUDA(ctx, launch_blasius(variant, integrator, nbl, ymin, ymax, nprof, par, par + nprof, tab, work,
                                par + 2 * nprof, np, st));
   ctx->launches++;
-  // device layout is [array][i][p]; the caller wants [p][i]: strided 2-D copies
+  ctx->launches++;  // spline_grid_kernel
+  // device layout is [array][i][p] (profile-fastest, coalesced for the march); the caller wants [p][i]:
+  // transposed on the device, then one contiguous copy per requested table
   double *outs[4] = {U, Uspl, d2U, d2Uspl};
-  for (int a = 0; a < 4; ++a) {
-    if (!outs[a]) continue;
-    // source: rows i (pitch nprof doubles), columns p -> transpose on the host side
-    std::vector<double> tmp((size_t)(nbl + 1) * nprof);
-    OSB_CUDA(ctx, cudaMemcpyAsync(tmp.data(), tab + (size_t)(a + 1) * n2 * nprof,
-                                  tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
-    OSB_CUDA(ctx, cudaStreamSynchronize(st));
-    for (int64_t p = 0; p < nprof; ++p)
-      for (int i = 0; i <= nbl; ++i) outs[a][p * (nbl + 1) + i] = tmp[(size_t)i * nprof + p];
+  if (U || Uspl || d2U || d2Uspl) {
+    double *tr = nullptr;
+    OSB_CUDA(ctx, scr.alloc(&tr, 4 * (size_t)(nbl + 1) * nprof * sizeof(double)));
+    OSB_CUDA(ctx, launch_transpose_tables(tab, tr, nbl, nprof, st));
+    ctx->launches++;
+    for (int a = 0; a < 4; ++a)
+      if (outs[a])
+        OSB_CUDA(ctx, cudaMemcpyAsync(outs[a], tr + (size_t)a * (nbl + 1) * nprof, (size_t)(nbl + 1) * nprof * sizeof(double),
+                                      cudaMemcpyDeviceToHost, st));
   }
   if (f2p_out) OSB_CUDA(ctx, cudaMemcpyAsync(f2p_out, par + 2 * nprof, nprof * sizeof(double), cudaMemcpyDeviceToHost, st));
   if (npass) OSB_CUDA(ctx, cudaMemcpyAsync(npass, np, nprof * sizeof(int32_t), cudaMemcpyDeviceToHost, st));

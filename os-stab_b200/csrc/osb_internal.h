@@ -120,6 +120,8 @@ cudaError_t launch_blasius(int variant, int integrator, int nbl, double ymin, do
                            double *d_tables /*[nprof][5][nbl+2]*/, double *d_scratch,
                            double *d_f2p_out, int32_t *d_npass, cudaStream_t st);
 size_t blasius_scratch_doubles(int nbl, int64_t nprof);
+// d_out[4][nprof][nbl+1] <- U, Uspl, d2U, d2Uspl of the profile-fastest batch tables
+cudaError_t launch_transpose_tables(const double *d_tables, double *d_out, int nbl, int64_t nprof, cudaStream_t st);
 cudaError_t launch_shift_profile(int nbl, double uc, const double *d_in, double *d_out, double *d_scratch,
                                  cudaStream_t st);
 // channel matrix path (chan_kernels.cu)

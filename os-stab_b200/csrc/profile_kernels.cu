@@ -117,11 +117,77 @@ __device__ static void spline_strided(int N, const double *X, const double *Y, d
 #undef C_
 }
 
-// tables: [5][nbl+2][nprof] (ydat, U, Uspl, d2U, d2Uspl); scratch: [2][nbl+2][nprof]
+// ---------------------------------------------------------------------------
+// The spline (SPLINE, shoot.f:906-957) of a batch.  Its tridiagonal system has the SAME matrix for every
+// profile and for both splines of a profile -- it depends on the grid only -- so the part of the Thomas
+// algorithm that does not involve the data is done once per launch by spline_grid_kernel, with the reference's
+// own operations in the reference's order:
+//     Cg[I] = X(I+1) - X(I)                                   I = 1 .. N-1
+//     Bp[I] = the eliminated diagonal B(I) after shoot.f:934-939  (incl. the ALAMDA = 1 end corrections)
+//     Tp[I] = A(I) / B(I-1), the multiplier of row I
+// A profile's spline is then two sweeps over its own data: forward R(I) = 6 (dy/C - dy/C) - Tp(I) R(I-1),
+// stored in the output array itself, and backward FDP(I) = (R(I) - Cg(I) FDP(I+1)) / Bp(I) in place.
+// Bit-identical to the per-profile elimination (same operations on the same numbers); per profile it moves
+// 32 KB per spline instead of ~110 KB.  grid: [3][nbl+2] doubles (Cg, Bp, Tp), 1-based index I at [I].
+// ---------------------------------------------------------------------------
+__global__ void spline_grid_kernel(int nbl, double ymin, double ymax, double *__restrict__ grid) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  const int N = nbl + 1, NM1 = N - 1;
+  const size_t n2 = (size_t)nbl + 2;
+  double *Cg = grid, *Bp = grid + n2, *Tp = grid + 2 * n2;
+  const double h = D(S(ymax, ymin), (double)nbl);
+#define X_(I) A(ymin, M((double)((I)-1), h))  /* ydat(I-1), contebl.f:499 */
+  for (int I = 1; I <= NM1; ++I) Cg[I] = S(X_(I + 1), X_(I));
+#undef X_
+  for (int I = 2; I <= NM1; ++I) Bp[I] = M(2.0, A(Cg[I - 1], Cg[I]));
+  Bp[2] = A(Bp[2], Cg[1]);
+  Bp[NM1] = A(Bp[NM1], Cg[NM1]);
+  Tp[2] = 0.0;
+  for (int I = 3; I <= NM1; ++I) {
+    const double T = D(Cg[I - 1], Bp[I - 1]);
+    Tp[I] = T;
+    Bp[I] = S(Bp[I], M(T, Cg[I - 1]));
+  }
+}
+
+// Y -> FDP for one profile of the batch (element i of an array at [i * st]); FDP may not alias Y.
+// copy (optional): receives FDP as well (contebl.f:505-507: d2U := Uspl).
+__device__ __forceinline__ void spline_batched(int N, const double *__restrict__ grid, size_t n2, const double *Y,
+                                               double *FDP, double *copy, size_t st) {
+  const double *Cg = grid, *Bp = grid + n2, *Tp = grid + 2 * n2;
+  const int NM1 = N - 1, NM2 = N - 2;
+#define Y_(I) Y[(size_t)((I)-1) * st]
+#define F_(I) FDP[(size_t)((I)-1) * st]
+  double ym = Y_(1), y0 = Y_(2), rprev = 0.0;
+  for (int I = 2; I <= NM1; ++I) {
+    const double yp = Y_(I + 1);
+    double r = M(6.0, S(D(S(yp, y0), __ldg(Cg + I)), D(S(y0, ym), __ldg(Cg + I - 1))));
+    if (I >= 3) r = S(r, M(__ldg(Tp + I), rprev));
+    F_(I) = r;
+    rprev = r;
+    ym = y0; y0 = yp;
+  }
+  double f = D(F_(NM1), __ldg(Bp + NM1));
+  F_(NM1) = f;
+  F_(N) = f;
+  if (copy) { copy[(size_t)(NM1 - 1) * st] = f; copy[(size_t)(N - 1) * st] = f; }
+  for (int I = 2; I <= NM2; ++I) {
+    const int NMI = N - I;
+    f = D(S(F_(NMI), M(__ldg(Cg + NMI), f)), __ldg(Bp + NMI));
+    F_(NMI) = f;
+    if (copy) copy[(size_t)(NMI - 1) * st] = f;
+  }
+  F_(1) = f;  // FDP(1) = FDP(2)
+  if (copy) copy[0] = f;
+#undef Y_
+#undef F_
+}
+
+// tables: [5][nbl+2][nprof] (ydat, U, Uspl, d2U, d2Uspl); grid: the tables of spline_grid_kernel
 __global__ void blasius_kernel(int variant, int integrator, int nbl, double ymin, double ymax,
                                int64_t nprof, const double *__restrict__ f2p_in,
                                const double *__restrict__ beta_in, double *__restrict__ tables,
-                               double *__restrict__ scratch, double *__restrict__ f2p_out,
+                               const double *__restrict__ grid, double *__restrict__ f2p_out,
                                int32_t *__restrict__ npass_out) {
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= nprof) return;
@@ -129,21 +195,20 @@ __global__ void blasius_kernel(int variant, int integrator, int nbl, double ymin
   const size_t n2 = (size_t)nbl + 2;
   double *ydat = tables + p, *U = tables + n2 * st + p, *Uspl = tables + 2 * n2 * st + p,
          *d2U = tables + 3 * n2 * st + p, *d2Uspl = tables + 4 * n2 * st + p;
-  double *Bw = scratch + p, *Rw = scratch + n2 * st + p;
   const double beta = beta_in[p];
   const double h = D(S(ymax, ymin), (double)nbl);  // contebl.f:177
   const bool ck45 = (variant == OSB_FLOW_CONTEBL) && (integrator == OSB_INT_CK45);
-  // secant iteration on f''(0), contebl.f:422-478
+  // secant iteration on f''(0), contebl.f:422-478.  The reference stores the profile on every pass and keeps the
+  // last one; here the passes only carry f'(ymax) and the accepted pass is integrated once more with the stores
+  // (same starting value, same operations: same bits) -- the table is written once instead of ~6 times.
   double x30 = f2p_in[p], used = x30, xi3old = 0.0, xi2old = 0.0, err = 1.0;
   int pass = 1;
   while (fabs(err) > 1.e-10) {
     used = x30;
     double xi[3] = {0.0, 0.0, x30}, xn[3];
-    U[0] = xi[1];
     for (int i = 1; i <= nbl; ++i) {
       if (ck45) srkck45(beta, xi, xn, h); else srk4(beta, xi, xn, h);
       xi[0] = xn[0]; xi[1] = xn[1]; xi[2] = xn[2];
-      U[(size_t)i * st] = xi[1];
     }
     const double x2n = xi[1];
     if (pass == 1) {
@@ -161,22 +226,61 @@ __global__ void blasius_kernel(int variant, int integrator, int nbl, double ymin
   }
   if (f2p_out) f2p_out[p] = used;
   if (npass_out) npass_out[p] = pass - 1;
+  {
+    double xi[3] = {0.0, 0.0, used}, xn[3];
+    U[0] = xi[1];
+    ydat[0] = A(ymin, M(0.0, h));
+    for (int i = 1; i <= nbl; ++i) {
+      if (ck45) srkck45(beta, xi, xn, h); else srk4(beta, xi, xn, h);
+      xi[0] = xn[0]; xi[1] = xn[1]; xi[2] = xn[2];
+      U[(size_t)i * st] = xi[1];
+      ydat[(size_t)i * st] = A(ymin, M((double)i, h));
+    }
+  }
+  spline_batched(nbl + 1, grid, n2, U, Uspl, variant != OSB_FLOW_ORRSPACE ? d2U : nullptr, st);
+  if (variant == OSB_FLOW_ORRSPACE) {
 #define U_(i) U[(size_t)(i) * st]
-  // 2nd-order finite-difference U'' (contebl.f:489-493); kept by orrspace only
-  const double hh = M(h, h);
-  for (int i = 1; i <= nbl - 1; ++i)
-    d2U[(size_t)i * st] = D(A(S(U_(i + 1), M(2.0, U_(i))), U_(i - 1)), hh);
-  d2U[0] = D(A(S(A(-U_(4), M(4.0, U_(3))), M(5.0, U_(2))), M(2.0, U_(1))), hh);
-  d2U[(size_t)nbl * st] =
-      D(S(A(S(M(2.0, U_(nbl)), M(5.0, U_(nbl - 1))), M(4.0, U_(nbl - 2))), U_(nbl - 3)), hh);
+    // 2nd-order finite-difference U'' (orrspace.f:784-788); contebl / orrsom overwrite it with Uspl (contebl.f:505-507)
+    const double hh = M(h, h);
+    for (int i = 1; i <= nbl - 1; ++i)
+      d2U[(size_t)i * st] = D(A(S(U_(i + 1), M(2.0, U_(i))), U_(i - 1)), hh);
+    d2U[0] = D(A(S(A(-U_(4), M(4.0, U_(3))), M(5.0, U_(2))), M(2.0, U_(1))), hh);
+    d2U[(size_t)nbl * st] =
+        D(S(A(S(M(2.0, U_(nbl)), M(5.0, U_(nbl - 1))), M(4.0, U_(nbl - 2))), U_(nbl - 3)), hh);
 #undef U_
-  for (int i = 0; i <= nbl; ++i) ydat[(size_t)i * st] = A(ymin, M((double)i, h));
-  spline_strided(nbl + 1, ydat, U, Uspl, Bw, Rw, st);
-  if (variant != OSB_FLOW_ORRSPACE)  // contebl.f:505-507, orrsom.f:781-783
-    for (int i = 0; i <= nbl; ++i) d2U[(size_t)i * st] = Uspl[(size_t)i * st];
-  spline_strided(nbl + 1, ydat, d2U, d2Uspl, Bw, Rw, st);
+  }
+  spline_batched(nbl + 1, grid, n2, d2U, d2Uspl, nullptr, st);
   const size_t last = (size_t)(nbl + 1) * st;  // zero pad (oracle D-1)
   ydat[last] = 0.0; U[last] = 0.0; Uspl[last] = 0.0; d2U[last] = 0.0; d2Uspl[last] = 0.0;
+}
+
+// [nprof-fastest] -> [profile][i]: out[a][p][i] = in[a][i][p] for the four tables the batched ABI returns, so that
+// the host receives each table with ONE contiguous copy.  32 x 32 tiles through shared memory.
+__global__ void transpose_tables_kernel(const double *__restrict__ in, double *__restrict__ out, int n1 /* nbl+1 */,
+                                        size_t n2 /* nbl+2 */, int64_t nprof) {
+  __shared__ double tile[32][33];
+  const int a = blockIdx.z;  // table 0..3 = U, Uspl, d2U, d2Uspl
+  const double *src = in + (size_t)(a + 1) * n2 * nprof;
+  double *dst = out + (size_t)a * n1 * nprof;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int i0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int i = i0 + r;
+    const int64_t pp = p0 + threadIdx.x;
+    if (i < n1 && pp < nprof) tile[r][threadIdx.x] = src[(size_t)i * nprof + pp];
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int64_t pp = p0 + r;
+    const int i = i0 + threadIdx.x;
+    if (i < n1 && pp < nprof) dst[(size_t)pp * n1 + i] = tile[threadIdx.x][r];
+  }
+}
+
+cudaError_t launch_transpose_tables(const double *d_tables, double *d_out, int nbl, int64_t nprof, cudaStream_t st) {
+  const dim3 grid((unsigned)((nprof + 31) / 32), (unsigned)((nbl + 1 + 31) / 32), 4), block(32, 8);
+  transpose_tables_kernel<<<grid, block, 0, st>>>(d_tables, d_out, nbl + 1, (size_t)nbl + 2, nprof);
+  return cudaGetLastError();
 }
 
 // SHIFT_BL of conteucbl.f:924-968: move the profile to a frame travelling with u_c and
@@ -200,8 +304,10 @@ cudaError_t launch_shift_profile(int nbl, double uc, const double *d_in, double 
   return cudaGetLastError();
 }
 
+// the grid tables of spline_grid_kernel (independent of the number of profiles)
 size_t blasius_scratch_doubles(int nbl, int64_t nprof) {
-  return 2 * ((size_t)nbl + 2) * (size_t)nprof;
+  (void)nprof;
+  return 3 * ((size_t)nbl + 2);
 }
 
 cudaError_t launch_blasius(int variant, int integrator, int nbl, double ymin, double ymax,
@@ -210,6 +316,7 @@ cudaError_t launch_blasius(int variant, int integrator, int nbl, double ymin, do
                            int32_t *d_npass, cudaStream_t st) {
   int threads = nprof >= 148 * 64 ? 64 : 32;
   int64_t blocks = (nprof + threads - 1) / threads;
+  spline_grid_kernel<<<1, 32, 0, st>>>(nbl, ymin, ymax, d_scratch);
   blasius_kernel<<<(unsigned)blocks, threads, 0, st>>>(variant, integrator, nbl, ymin, ymax, nprof,
                                                        d_f2p, d_beta, d_tables, d_scratch,
                                                        d_f2p_out, d_npass);
