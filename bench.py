@@ -416,9 +416,13 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    cpu_pg = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        # a host-side barrier for the single-process leg: ranks parked in an NCCL barrier keep a spinning kernel
+        # on their GPU, which would time-slice against the kernels rank 0 launches there from its own context
+        cpu_pg = dist.new_group(backend="gloo")
 
     eng = osb.Engine(local_rank)
     stream = torch.cuda.ExternalStream(eng.stream, device=dev)
@@ -431,6 +435,12 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def host_barrier():
+        stream.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=cpu_pg)
 
     def timed(fn, steps):
         """EXACTLY `steps` calls between barriers; device time by CUDA events on the
@@ -581,7 +591,7 @@ def main():
                 full_c.reshape(-1, 2)[ridx] = gc
                 full_i[:, ridx] = gi
             full = (full_c, full_i)
-        barrier()  # every other rank idles from here: rank 0 drives their GPUs through its own context
+        host_barrier()  # every other rank idles on the HOST from here: rank 0 drives their GPUs through its own context
         if rank == 0:
             try:
                 meng = osb.Engine(devices=list(range(world)))
@@ -623,7 +633,7 @@ def main():
                 meng.close()
             except Exception as e:  # noqa: BLE001
                 single = {"error": repr(e)}
-        barrier()
+        host_barrier()
 
     # ---- the other scaling mode as an extra key (N > 1): weak next to the strong headline
     other = None

@@ -2638,6 +2638,28 @@ __global__ void __launch_bounds__(32) chan_neutral_warp_kernel(const __grid_cons
 }
 
 // ---------------------------------------------------------------------------
+// MAKE_DERIVATIVES' products D2 = D1hat D1, D3 = D1hat D2, D4 = D1hat D3 (orrfdchan.f:318-342: three (N+1)^3 triple
+// loops on one core, ~3 s at N = 1024).  One thread per entry, the k loop ascending with separately rounded
+// multiply and add: the same operations in the same order as the reference's loop nest, so the tables keep
+// the bits of a no-FMA CPU build.  Row-major (i, j) at [i * ld + j].
+// ---------------------------------------------------------------------------
+__global__ void table_matmul_kernel(double *__restrict__ C, const double *__restrict__ A, const double *__restrict__ B,
+                                    int ld) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, i = blockIdx.y;
+  if (j >= ld) return;
+  const double *a = A + (size_t)i * ld;
+  double s = 0.0;
+  for (int k = 0; k < ld; ++k) s = __dadd_rn(s, __dmul_rn(__ldg(a + k), B[(size_t)k * ld + j]));
+  C[(size_t)i * ld + j] = s;
+}
+
+cudaError_t launch_table_matmul(double *C, const double *A, const double *B, int ld, cudaStream_t st) {
+  const dim3 block(128), grid((ld + 127) / 128, ld);
+  table_matmul_kernel<<<grid, block, 0, st>>>(C, A, B, ld);
+  return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------
 struct ChanLaunch {

@@ -63,8 +63,9 @@ namespace {
 inline double &at(std::vector<double> &M, int N, int i, int j) { return M[(size_t)i * (N + 1) + j]; }
 inline double at(const std::vector<double> &M, int N, int i, int j) { return M[(size_t)i * (N + 1) + j]; }
 
-// FiniteD1, orrfdchan.f:1183-1215
-void finite_d1(std::vector<double> &D, int N, const std::vector<double> &eta) {
+// first-derivative matrix of orrfdchan (FiniteD1, orrfdchan.f:1183-1215): central differences on the given grid,
+// one-sided in the first and last row
+void fd_first_derivative(std::vector<double> &D, int N, const std::vector<double> &eta) {
   std::fill(D.begin(), D.end(), 0.0);
   at(D, N, 0, 0) = 1. / (eta[0] - eta[1]);
   at(D, N, 0, 1) = -1. / (eta[0] - eta[1]);
@@ -76,8 +77,8 @@ void finite_d1(std::vector<double> &D, int N, const std::vector<double> &eta) {
   }
 }
 
-// CHEBYD, orrcolchan.f:904-944
-void chebyd(std::vector<double> &D, int N) {
+// Chebyshev collocation first-derivative matrix on eta_j = cos(j pi / N) as CHEBYD forms it (orrcolchan.f:904-944)
+void cheb_first_derivative(std::vector<double> &D, int N) {
   const double PI = acos(-1.0), fn = (double)N;
   std::vector<double> C(N + 1, 1.0);
   C[0] = 2.0; C[N] = 2.0;
@@ -97,21 +98,48 @@ void chebyd(std::vector<double> &D, int N) {
     }
 }
 
-// D(i,j) = sum_k A(i,k) B(k,j), k ascending (orrfdchan.f:318-342)
-void matmul_ref(std::vector<double> &Cm, const std::vector<double> &A, const std::vector<double> &B, int N) {
-  // B is traversed by column; transpose it once so that the k loop is contiguous
-  // (same products, same summation order as the reference's triple loop)
-  std::vector<double> Bt(B.size());
-  for (int k = 0; k <= N; ++k)
-    for (int j = 0; j <= N; ++j) Bt[(size_t)j * (N + 1) + k] = at(B, N, k, j);
-  for (int i = 0; i <= N; ++i)
-    for (int j = 0; j <= N; ++j) {
-      const double *a = &A[(size_t)i * (N + 1)], *b = &Bt[(size_t)j * (N + 1)];
-      double s = 0.0;
-      for (int k = 0; k <= N; ++k) s = s + a[k] * b[k];
-      at(Cm, N, i, j) = s;
+// The products of MAKE_DERIVATIVES on the device (table_matmul_kernel: k ascending, no FMA = the reference's
+// triple loops, orrfdchan.f:318-342).  Operands are uploaded once; results stay on the device for the next product.
+class TableProducts {
+ public:
+  TableProducts(osb_ctx *ctx, int device, int N) : ctx_(ctx), device_(device), ld_(N + 1), st_((cudaStream_t)osb_stream(ctx)) {}
+  ~TableProducts() {
+    cudaSetDevice(device_);
+    for (double *p : bufs_) cudaFree(p);
+  }
+  // device copy of a host table
+  int upload(const std::vector<double> &h, double **d) {
+    CH_CUDA(ctx_, cudaSetDevice(device_));
+    CH_CUDA(ctx_, cudaMalloc(d, bytes()));
+    bufs_.push_back(*d);
+    CH_CUDA(ctx_, cudaMemcpyAsync(*d, h.data(), bytes(), cudaMemcpyHostToDevice, st_));
+    return OSB_OK;
+  }
+  // *dC = dA dB on the device; host copy in hC when given
+  int product(const double *dA, const double *dB, double **dC, std::vector<double> *hC) {
+    CH_CUDA(ctx_, cudaSetDevice(device_));
+    CH_CUDA(ctx_, cudaMalloc(dC, bytes()));
+    bufs_.push_back(*dC);
+    CH_CUDA(ctx_, launch_table_matmul(*dC, dA, dB, ld_, st_));
+    ctx_count_launch(ctx_, 1);
+    if (hC) {
+      hC->resize((size_t)ld_ * ld_);
+      CH_CUDA(ctx_, cudaMemcpyAsync(hC->data(), *dC, bytes(), cudaMemcpyDeviceToHost, st_));
     }
-}
+    return OSB_OK;
+  }
+  int sync() {
+    CH_CUDA(ctx_, cudaStreamSynchronize(st_));
+    return OSB_OK;
+  }
+
+ private:
+  size_t bytes() const { return (size_t)ld_ * ld_ * sizeof(double); }
+  osb_ctx *ctx_;
+  int device_, ld_;
+  cudaStream_t st_;
+  std::vector<double *> bufs_;
+};
 
 }  // namespace
 
@@ -167,27 +195,33 @@ int osb_chan_create(osb_ctx *ctx, int disc, int N, osb_chan **out) {
   c->D2full.resize(nn); c->D4full.resize(nn);
   const double pi = acos(-1.0), dth = pi / (double)N;  // orrfdchan.f:177-183
   for (int i = 0; i <= N; ++i) c->eta[i] = cos((double)i * dth);
-  if (disc == OSB_DISC_FD) { finite_d1(D1hat, N, c->eta); finite_d1(D1, N, c->eta); }
-  else { chebyd(D1hat, N); chebyd(D1, N); }
+  if (disc == OSB_DISC_FD) { fd_first_derivative(D1hat, N, c->eta); fd_first_derivative(D1, N, c->eta); }
+  else { cheb_first_derivative(D1hat, N); cheb_first_derivative(D1, N); }
   for (int i = 0; i <= N; ++i) { at(D1, N, 0, i) = 0.0; at(D1, N, N, i) = 0.0; }  // phi' = 0
-  matmul_ref(c->D2full, D1hat, D1, N);
-  matmul_ref(D3, D1hat, c->D2full, N);
-  matmul_ref(c->D4full, D1hat, D3, N);
+  TableProducts tp(ctx, c->device, N);
+  double *dD1hat = nullptr, *dD1 = nullptr, *dD2 = nullptr, *dD3 = nullptr, *dD4 = nullptr, *dD2hat = nullptr;
+  std::vector<double> D2hat;
+  int rc = tp.upload(D1hat, &dD1hat);
+  if (!rc) rc = tp.upload(D1, &dD1);
+  if (!rc) rc = tp.product(dD1hat, dD1, &dD2, &c->D2full);
+  if (!rc) rc = tp.product(dD1hat, dD2, &dD3, nullptr);
+  if (!rc) rc = tp.product(dD1hat, dD3, &dD4, &c->D4full);
+  if (!rc && disc == OSB_DISC_CHEB_NUM) rc = tp.product(dD1hat, dD1hat, &dD2hat, &D2hat);
+  if (!rc) rc = tp.sync();
+  if (rc) return rc;
   for (int i = 0; i <= N; ++i) {  // INIT_CHANNEL_PROFILE
     c->u[i] = (1. - c->eta[i] * c->eta[i]);
     c->d1u[i] = -2.0 * c->eta[i];
     c->d2u[i] = -2.0;
   }
   if (disc == OSB_DISC_CHEB_NUM) {  // orrncbl.f:520-545
-    std::vector<double> D2hat(nn);
-    matmul_ref(D2hat, D1hat, D1hat, N);
     for (int i = 0; i <= N; ++i) {
       double a = 0.0, b = 0.0;
       for (int k = 0; k <= N; ++k) { a = a + at(D1hat, N, i, k) * c->u[k]; b = b + at(D2hat, N, i, k) * c->u[k]; }
       c->d1u[i] = a; c->d2u[i] = b;
     }
   }
-  int rc = upload_tables(ctx, c.get());
+  rc = upload_tables(ctx, c.get());
   if (rc) return rc;
   *out = c.release();
   return OSB_OK;
@@ -226,13 +260,21 @@ int osb_chan_create_bl(osb_ctx *ctx, int disc, int N, double lmap, const double 
   bl_grid(disc, N, c->eta);
   c->u.resize(n1); c->d1u.resize(n1); c->d2u.resize(n1);
   std::vector<double> D1hat(nn), D1(nn), D2(nn), D3(nn), D4(nn), D2hat(nn);
-  if (disc == OSB_DISC_FD) { finite_d1(D1hat, N, c->eta); finite_d1(D1, N, c->eta); }
-  else { chebyd(D1hat, N); chebyd(D1, N); }
+  if (disc == OSB_DISC_FD) { fd_first_derivative(D1hat, N, c->eta); fd_first_derivative(D1, N, c->eta); }
+  else { cheb_first_derivative(D1hat, N); cheb_first_derivative(D1, N); }
   for (int i = 0; i <= N; ++i) { at(D1, N, 0, i) = 0.0; at(D1, N, N, i) = 0.0; }  // v' = 0 at both ends
-  matmul_ref(D2, D1hat, D1, N);
-  matmul_ref(D3, D1hat, D2, N);
-  matmul_ref(D4, D1hat, D3, N);
-  matmul_ref(D2hat, D1hat, D1hat, N);
+  {
+    TableProducts tp(ctx, c->device, N);
+    double *dD1hat = nullptr, *dD1 = nullptr, *dD2 = nullptr, *dD3 = nullptr, *dD4 = nullptr, *dD2hat = nullptr;
+    int rcp = tp.upload(D1hat, &dD1hat);
+    if (!rcp) rcp = tp.upload(D1, &dD1);
+    if (!rcp) rcp = tp.product(dD1hat, dD1, &dD2, &D2);
+    if (!rcp) rcp = tp.product(dD1hat, dD2, &dD3, &D3);
+    if (!rcp) rcp = tp.product(dD1hat, dD3, &dD4, &D4);
+    if (!rcp) rcp = tp.product(dD1hat, dD1hat, &dD2hat, &D2hat);
+    if (!rcp) rcp = tp.sync();
+    if (rcp) return rcp;
+  }
   // INIT_BL_PROFILE with the caller's profile values (orrcolbl.f:398-427)
   for (int i = 0; i <= N; ++i) c->u[i] = (i <= merge) ? 1.0 : U[i];
   std::vector<double> d1u(n1), d2u(n1);

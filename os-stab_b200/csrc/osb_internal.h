@@ -150,6 +150,8 @@ cudaError_t launch_chan_neutral(int n, const double *D2, const double *D4, const
                                 const double *alpha0, const double2 *sigma0, double sfac, double tol, int maxit,
                                 double *alpha_out, double2 *omega_out, int32_t *steps, int32_t *status,
                                 double *trace, cudaStream_t st);
+// C = A B for the (N+1) x (N+1) derivative tables, k ascending, no FMA (row-major, ld = N+1); device pointers
+cudaError_t launch_table_matmul(double *C, const double *A, const double *B, int ld, cudaStream_t st);
 cudaError_t launch_fp64_peak(double *d_out, int iters, int blocks, int threads, cudaStream_t st);
 cudaError_t launch_dmma_peak(double *d_out, int iters, int blocks, int threads, cudaStream_t st);
 

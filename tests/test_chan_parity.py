@@ -17,6 +17,8 @@ def rel(a, b):
 
 @pytest.mark.parametrize("disc", [ob.DISC_FD, ob.DISC_CHEB, ob.DISC_CHEB_NUM])
 def test_tables_bit_exact(engine, oracle, disc):
+    """Product tables (D1hat on the host, the three O(N^3) products on the device, k ascending, no FMA) against
+    the oracle's triple loops: same bits.  (Independence of the two is test_tables_against_multiprecision's job.)"""
     ch = engine.chan(disc, 64)
     t = ch.tables()
     ch.free()
@@ -27,6 +29,50 @@ def test_tables_bit_exact(engine, oracle, disc):
     assert np.array_equal(t["D2"], c.table(4))
     assert np.array_equal(t["D4"], c.table(5))
     c.close()
+
+
+@pytest.mark.parametrize("disc,N", [(ob.DISC_FD, 48), (ob.DISC_CHEB, 48), (ob.DISC_FD, 96), (ob.DISC_CHEB, 64)])
+def test_tables_against_multiprecision(engine, disc, N):
+    """An independent check of the derivative tables (the product and the oracle restate the same short reference
+    routines, so comparing those two proves little): FiniteD1 / CHEBYD and the products D2 = D1hat D1,
+    D4 = D1hat^3 D1 of MAKE_DERIVATIVES (orrfdchan.f:305-342) evaluated with mpmath at 40 digits from the formulas
+    in the reference; the fp64 tables (host-built D1hat, device-side products) must equal them to rounding."""
+    import mpmath as mp
+
+    mp.mp.dps = 40
+    eta = [mp.cos(mp.mpf(i) * mp.pi / N) for i in range(N + 1)]
+    D = mp.zeros(N + 1, N + 1)
+    if disc == ob.DISC_FD:  # orrfdchan.f:1183-1215
+        D[0, 0] = 1 / (eta[0] - eta[1]); D[0, 1] = -1 / (eta[0] - eta[1])
+        D[N, N - 1] = 1 / (eta[N - 1] - eta[N]); D[N, N] = -1 / (eta[N - 1] - eta[N])
+        for i in range(1, N):
+            D[i, i - 1] = 1 / (eta[i - 1] - eta[i + 1]); D[i, i + 1] = -1 / (eta[i - 1] - eta[i + 1])
+    else:  # orrcolchan.f:904-944
+        c = [mp.mpf(1)] * (N + 1)
+        c[0] = c[N] = mp.mpf(2)
+        for j in range(N + 1):
+            for k in range(N + 1):
+                if j == 0 and k == 0: v = (2 * mp.mpf(N) ** 2 + 1) / 6
+                elif j == N and k == N: v = -(2 * mp.mpf(N) ** 2 + 1) / 6
+                elif j == k: v = -eta[j] / (2 * (1 - eta[j] ** 2))
+                else: v = c[j] * (-1) ** (j + k) / (c[k] * (eta[j] - eta[k]))
+                D[j, k] = v
+    D1 = D.copy()
+    for i in range(N + 1):
+        D1[0, i] = 0; D1[N, i] = 0
+    D2 = D * D1
+    D4 = D * (D * D2)
+    tofloat = lambda Mx: np.array([[float(Mx[i, j]) for j in range(N + 1)] for i in range(N + 1)])
+    ch = engine.chan(disc, N)
+    t = ch.tables()
+    ch.free()
+    assert np.max(np.abs(t["eta"] - np.array([float(e) for e in eta]))) < 2e-16
+    D2f, D4f = tofloat(D2), tofloat(D4)
+    assert np.abs(t["D2"] - D2f).max() / np.abs(D2f).max() < 1e-12
+    assert np.abs(t["D4"] - D4f).max() / np.abs(D4f).max() < 1e-12
+    if disc == ob.DISC_FD:  # the FD operator is banded: exact zeros outside half bandwidths 2 and 4
+        i, j = np.indices(D2f.shape)
+        assert np.all(t["D2"][np.abs(i - j) > 2] == 0) and np.all(t["D4"][np.abs(i - j) > 4] == 0)
 
 
 @pytest.mark.parametrize("N,lo,hi,inc", [(64, 0.76, 1.16, 0.02), (128, 0.76, 1.16, 0.01)])
