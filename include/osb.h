@@ -45,6 +45,8 @@ extern "C" {
 #define OSB_ST_CONVERGED 0 /* eigenvalue loop left by tolerance               */
 #define OSB_ST_MAXCOUNT 1  /* left by the pass limit (shoot.f:478-479)        */
 #define OSB_ST_NONFINITE 2 /* NaN/Inf met (the reference would SIGFPE)        */
+#define OSB_ST_UNVERIFIED 3 /* osb_chan_eig only: converged, but the choice of mode could not be
+                              cross-checked against the full spectrum (see osb_chan_eig)       */
 
 /* flows: which reference driver's iteration is reproduced */
 #define OSB_FLOW_CONTEBL 0  /* CONTE_IC via contebl.f:205   (shoot.f:391-813) */
@@ -242,8 +244,14 @@ int osb_chan_tables(osb_ctx *ctx, const osb_chan *chan, double *eta, double *u, 
  * optionally, its eigenvector on the full grid normalised by the component of largest
  * modulus (orrfdchan.f:849-857).  The interior (N-1)x(N-1) pencil is used (the BC rows
  * of orrcolchan.f:424-435 only add infinite eigenvalues).
- *   alpha  [2*npts]; sigma0 [2*npts] optional shift guesses (NULL: a 16-shift scan
- *   over 0 < c_r < 1 per point picks the mode); omega [2*npts] out;
+ *   alpha  [2*npts]; sigma0 [2*npts] optional shift guesses; omega [2*npts] out.
+ *   sigma0 = NULL: the mode is chosen by the reference's rule.  A scan of real shifts (16 over 0 < c_r < 1,
+ *   plus 32 over -4 < w_r < 0 for the FD rule / 8 over -1 < w_r < 0 for the |w_r| < 1 rule) proposes it; the
+ *   proposal is cross-checked against the device spectrum (osb_chan_spectrum) under the same rule wherever no
+ *   shift settled, at both ends of the sweep and across every jump of the chosen branch, and the whole sweep
+ *   (up to 512 points) is re-checked if any of those disagrees.  Points left unchecked after a disagreement
+ *   come back as OSB_ST_UNVERIFIED.  For N beyond the dense kernels' limit (FD, N > ~700) no spectrum is
+ *   available and the scan's choice stands (a mode with w_r outside the scanned windows is then missed).
  *   evec   [npts*(N+1)*2] optional; iters [npts] inverse iterations; status [npts].
  *   evec_adj [npts*(N+1)*2] optional: the LEFT (adjoint) eigenvector of the same mode -- the reference solves
  *   with JOBVL = 'V' (orrfdchan.f:796, orrcolchan.f:461) and writes it as columns 4-5 of fort.11.  By inverse

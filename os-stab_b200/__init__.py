@@ -30,7 +30,7 @@ LIB_PATH = _HERE / "libosb.so"
 
 FLOW_CONTEBL, FLOW_CONTE, FLOW_ORRSOM, FLOW_ORRSPACE = 0, 1, 2, 3
 INT_RK4, INT_CK45 = 0, 1
-ST_CONVERGED, ST_MAXCOUNT, ST_NONFINITE = 0, 1, 2
+ST_CONVERGED, ST_MAXCOUNT, ST_NONFINITE, ST_UNVERIFIED = 0, 1, 2, 3
 E_ARG, E_CUDA, E_ALLOC, E_STATE = -1, -2, -3, -4
 
 _dp = C.POINTER(C.c_double)

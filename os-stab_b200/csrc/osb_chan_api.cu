@@ -480,30 +480,101 @@ int osb_chan_eig(osb_ctx *ctx, const osb_chan *c, double Re, int64_t npts, const
   if (npts == 0) return OSB_OK;
   std::vector<double> Rev(npts, Re), sig(2 * npts);
   std::vector<int32_t> ok(npts, 1);
+  std::vector<char> verified(npts, 0), unverified(npts, 0);
   if (sigma0) memcpy(sig.data(), sigma0, 2 * npts * sizeof(double));
   else {
     int rc = scan_shifts(ctx, c, npts, alpha, Rev.data(), sig, ok);
     if (rc) return rc;
     if (getenv("OSB_CHAN_SCAN_MISS")) std::fill(ok.begin(), ok.end(), 0);  // test hook: pretend the scan found nothing
-    // Points where no scanned shift settled on a mode the rule accepts: take the shift from the full spectrum
-    // computed on the device (K4c) under the same rule.  Rare; the scan covers the reference's decks.
-    std::vector<int64_t> miss;
-    for (int64_t p = 0; p < npts; ++p) if (!ok[p]) miss.push_back(p);
-    if (!miss.empty() && c->n <= chan_dense_max_n()) {
-      const int n = c->n;
-      std::vector<double> am(2 * miss.size()), sp((size_t)miss.size() * n * 2);
-      std::vector<int32_t> sst(miss.size());
-      for (size_t k = 0; k < miss.size(); ++k) { am[2 * k] = alpha[2 * miss[k]]; am[2 * k + 1] = alpha[2 * miss[k] + 1]; }
-      rc = osb_chan_spectrum(ctx, c, Re, (int64_t)miss.size(), am.data(), sp.data(), sst.data());
+    // The reference's rule runs over the FULL spectrum; the scan only sees the modes nearest to its shifts
+    // (0 < c_r < 1 and -4 < w_r < 0), and e.g. the FD operator's spurious branch sits at w_r ~ -2 / alpha:
+    // outside the windows for alpha < 0.5.  So the scan's choice is cross-checked against the device spectrum
+    // (K4c) under the same rule: at every point where no shift settled, at the first and the last point of the
+    // sweep, and on both sides of every jump of the chosen branch between neighbours.  If a checked point
+    // disagrees, the spectrum's mode is taken there and the check is extended to the whole sweep (up to 512
+    // points; beyond that the unchecked points are reported as OSB_ST_UNVERIFIED).
+    const int n = c->n;
+    const bool can_verify = n <= chan_dense_max_n() && !getenv("OSB_CHAN_NO_VERIFY");
+    auto rule_ok = [&](double wr, double wi) {
+      if (!(std::isfinite(wr) && std::isfinite(wi))) return false;
+      if (c->disc == OSB_DISC_FD || c->bl) return fabs(wi) < 10.0 && (int)wr != 999;  // orrfdchan.f:818-819
+      return fabs(wr) < 1.0;                                                          // orrncbl.f:898
+    };
+    // Cross-check of the points `pts`.  The device spectrum proposes the values the rule would prefer to the
+    // scan's choice (larger Im w); a proposal only counts once a shift-invert solve started from it has settled
+    // next to it -- the QR values of inv(B)A are not trustworthy by themselves for ill-conditioned pencils
+    // (collocation at N >= 256; the spectrum kernel's own polish leaves those unsettled).
+    auto verify = [&](const std::vector<int64_t> &pts, int *nfixed) -> int {
+      *nfixed = 0;
+      if (pts.empty()) return OSB_OK;
+      std::vector<double> am(2 * pts.size()), sp((size_t)pts.size() * n * 2);
+      std::vector<int32_t> sst(pts.size());
+      for (size_t k = 0; k < pts.size(); ++k) { am[2 * k] = alpha[2 * pts[k]]; am[2 * k + 1] = alpha[2 * pts[k] + 1]; }
+      int rcv = osb_chan_spectrum(ctx, c, Re, (int64_t)pts.size(), am.data(), sp.data(), sst.data());
+      if (rcv) return rcv;
+      const int kMaxCand = 6;
+      std::vector<int64_t> cpt;           // candidate -> index into pts
+      std::vector<double> ca, cr, cs;     // alpha, Re, shift of every candidate
+      for (size_t k = 0; k < pts.size(); ++k) {
+        const int64_t p = pts[k];
+        const double *w = sp.data() + k * n * 2;
+        const double floor_i = ok[p] ? sig[2 * p + 1] + 1.0e-7 * std::max(1.0, hypot(sig[2 * p], sig[2 * p + 1])) : -1.0e300;
+        int taken = 0;
+        for (int e = n - 1; e >= 0 && taken < kMaxCand; --e) {  // ascending in Im(w): walk from the top
+          if (!rule_ok(w[2 * e], w[2 * e + 1]) || !(w[2 * e + 1] > floor_i)) continue;
+          cpt.push_back((int64_t)k);
+          ca.push_back(alpha[2 * p]); ca.push_back(alpha[2 * p + 1]);
+          cr.push_back(Re);
+          cs.push_back(w[2 * e]); cs.push_back(w[2 * e + 1]);
+          ++taken;
+        }
+      }
+      std::vector<double> om, dl;
+      std::vector<int32_t> it;
+      if (!cpt.empty()) {
+        rcv = run_eig(ctx, c, (int64_t)cpt.size(), ca, cr, cs, 2, 6, 1.0e-10, om, dl, it, nullptr);
+        if (rcv) return rcv;
+      }
+      std::vector<char> fixed(pts.size(), 0);
+      for (size_t e = 0; e < cpt.size(); ++e) {  // candidates of a point are in descending Im: the first confirmed one wins
+        const size_t k = (size_t)cpt[e];
+        if (fixed[k]) continue;
+        const int64_t p = pts[k];
+        const double wr = om[2 * e], wi = om[2 * e + 1], mag = hypot(wr, wi);
+        if (!rule_ok(wr, wi) || !(dl[e] <= 1.0e-8 * mag)) continue;
+        if (hypot(wr - cs[2 * e], wi - cs[2 * e + 1]) > 1.0e-3 * mag) continue;  // wandered off to another mode
+        if (ok[p] && !(wi > sig[2 * p + 1] + 1.0e-9 * std::max(1.0, mag))) continue;  // the scan's own mode again
+        sig[2 * p] = wr; sig[2 * p + 1] = wi; ok[p] = 1;
+        fixed[k] = 1;
+        *nfixed += 1;
+      }
+      for (int64_t p : pts) verified[p] = 1;
+      return OSB_OK;
+    };
+    if (can_verify) {
+      std::vector<int64_t> pts;
+      std::vector<char> want(npts, 0);
+      for (int64_t p = 0; p < npts; ++p) if (!ok[p]) want[p] = 1;
+      want[0] = 1; want[npts - 1] = 1;
+      int njump = 0;
+      for (int64_t p = 1; p < npts && njump < 8; ++p) {
+        if (!ok[p] || !ok[p - 1]) continue;
+        const double d = hypot(sig[2 * p] - sig[2 * p - 2], sig[2 * p + 1] - sig[2 * p - 1]);
+        const double m = 0.5 * (hypot(sig[2 * p], sig[2 * p + 1]) + hypot(sig[2 * p - 2], sig[2 * p - 1]));
+        if (d > 0.25 * m) { want[p] = 1; want[p - 1] = 1; ++njump; }
+      }
+      for (int64_t p = 0; p < npts; ++p) if (want[p]) pts.push_back(p);
+      int nfixed = 0;
+      rc = verify(pts, &nfixed);
       if (rc) return rc;
-      for (size_t k = 0; k < miss.size(); ++k) {
-        double best = -1.0e300;
-        for (int e = 0; e < n; ++e) {
-          const double wr = sp[(k * n + e) * 2], wi = sp[(k * n + e) * 2 + 1];
-          if (!(std::isfinite(wr) && std::isfinite(wi))) continue;
-          if (c->disc == OSB_DISC_FD || c->bl) { if (!(fabs(wi) < 10.0) || (int)wr == 999) continue; }
-          else if (!(fabs(wr) < 1.0)) continue;
-          if (wi > best) { best = wi; sig[2 * miss[k]] = wr; sig[2 * miss[k] + 1] = wi; ok[miss[k]] = 1; }
+      if (nfixed > 0) {  // the scan missed the reference's mode somewhere: trust it nowhere
+        std::vector<int64_t> rest;
+        for (int64_t p = 0; p < npts; ++p) if (!verified[p]) rest.push_back(p);
+        if (rest.size() <= 512) {
+          rc = verify(rest, &nfixed);
+          if (rc) return rc;
+        } else {
+          for (int64_t p : rest) unverified[p] = 1;
         }
       }
     }
@@ -521,7 +592,7 @@ int osb_chan_eig(osb_ctx *ctx, const osb_chan *c, double Re, int64_t npts, const
     if (iters) iters[p] = it[p];
     const bool fin = std::isfinite(om[2 * p]) && std::isfinite(om[2 * p + 1]);
     const bool conv = fin && dl[p] <= 1.0e-12 * hypot(om[2 * p], om[2 * p + 1]);
-    status[p] = !fin ? OSB_ST_NONFINITE : ((conv && ok[p]) ? OSB_ST_CONVERGED : OSB_ST_MAXCOUNT);
+    status[p] = !fin ? OSB_ST_NONFINITE : ((conv && ok[p]) ? (unverified[p] ? OSB_ST_UNVERIFIED : OSB_ST_CONVERGED) : OSB_ST_MAXCOUNT);
   }
   if (evec) memcpy(evec, ev.data(), ev.size() * sizeof(double));
   if (evec_adj) memcpy(evec_adj, av.data(), av.size() * sizeof(double));

