@@ -9,7 +9,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <memory>
+#include <mutex>
+#include <thread>
 
 #include "osb_internal.h"
 
@@ -20,7 +23,8 @@ struct osb_ctx {
   std::vector<cudaStream_t> streams;
   std::vector<cudaMemPool_t> pools;  // private stream-ordered pools, one per device (Scratch)
   std::string err;
-  int64_t launches = 0;
+  std::mutex mu;                     // guards err: multi-device calls run one worker thread per device
+  std::atomic<int64_t> launches{0};
 };
 
 struct osb_profile {
@@ -40,7 +44,10 @@ struct osb_profile {
 namespace {
 
 int fail(osb_ctx *ctx, int code, const std::string &msg) {
-  if (ctx) ctx->err = msg;
+  if (ctx) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err = msg;
+  }
   return code;
 }
 
@@ -151,6 +158,26 @@ void chunk(int64_t n, int ndev, int d, int64_t *lo, int64_t *hi) {
   *hi = std::min<int64_t>(n, per * (d + 1));
 }
 
+// pass counts vary by region of a sweep, so contiguous blocks would imbalance the devices: tiles of the
+// flattened unit index (points, continuation lines) are dealt cyclically (tile t -> device t mod ndev) and packed
+// contiguously in each device's buffers.  Per-unit results do not depend on the partition.
+struct Seg { int64_t host_lo, n, dev_off; };
+struct Deal { std::vector<std::vector<Seg>> segs; std::vector<int64_t> count; };
+Deal deal_tiles(int64_t n, int ndev, int64_t tile) {
+  Deal d;
+  d.segs.resize(ndev);
+  d.count.assign(ndev, 0);
+  if (ndev == 1) tile = n;
+  int64_t t = 0;
+  for (int64_t lo = 0; lo < n; lo += tile, ++t) {
+    const int dev = (int)(t % ndev);
+    const int64_t m = std::min(tile, n - lo);
+    d.segs[dev].push_back(Seg{lo, m, d.count[dev]});
+    d.count[dev] += m;
+  }
+  return d;
+}
+
 }  // namespace
 
 // accessors for the other translation units of the library
@@ -159,6 +186,7 @@ int ctx_fail(osb_ctx *ctx, int code, const std::string &msg) { return fail(ctx, 
 int ctx_device(const osb_ctx *ctx, int slot) { return ctx->devices[slot]; }
 void ctx_count_launch(osb_ctx *ctx, int n) { ctx->launches += n; }
 cudaMemPool_t ctx_pool(const osb_ctx *ctx, int slot) { return ctx->pools[slot]; }
+cudaStream_t ctx_stream(const osb_ctx *ctx, int slot) { return ctx->streams[slot]; }
 }  // namespace osb
 
 extern "C" {
@@ -229,7 +257,7 @@ int osb_destroy(osb_ctx *ctx) {
 int osb_device_count(const osb_ctx *ctx) { return ctx ? (int)ctx->devices.size() : 0; }
 const char *osb_last_error(const osb_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 void *osb_stream(osb_ctx *ctx) { return ctx && !ctx->streams.empty() ? (void *)ctx->streams[0] : nullptr; }
-int64_t osb_launch_count(const osb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+int64_t osb_launch_count(const osb_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
 
 int osb_shoot_defaults(int flow, osb_shoot_opts *o) {
   FlowRules r;
@@ -308,6 +336,41 @@ int osb_profile_blasius(osb_ctx *ctx, int variant, int integrator, int nbl, doub
   return OSB_OK;
 }
 
+// one device's share [lo, lo+m) of a profile batch: enqueue everything on that device's stream (no synchronisation)
+static int blasius_batch_slice(osb_ctx *ctx, int slot, Scratch &scr, int variant, int integrator, int nbl, double ymin,
+                               double ymax, int64_t lo, int64_t m, const double *f2p, const double *beta, double *U,
+                               double *Uspl, double *d2U, double *d2Uspl, double *f2p_out, int32_t *npass) {
+  cudaStream_t st = ctx->streams[slot];
+  OSB_CUDA(ctx, cudaSetDevice(ctx->devices[slot]));
+  const size_t n2 = (size_t)nbl + 2, n1 = (size_t)nbl + 1;
+  double *tab = nullptr, *work = nullptr, *par = nullptr;
+  int32_t *np = nullptr;
+  OSB_CUDA(ctx, scr.alloc(&tab, 5 * n2 * m * sizeof(double)));
+  OSB_CUDA(ctx, scr.alloc(&work, blasius_scratch_doubles(nbl, m) * sizeof(double)));
+  OSB_CUDA(ctx, scr.alloc(&par, 3 * m * sizeof(double)));
+  OSB_CUDA(ctx, scr.alloc(&np, m * sizeof(int32_t)));
+  OSB_CUDA(ctx, cudaMemcpyAsync(par, f2p + lo, m * sizeof(double), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(ctx, cudaMemcpyAsync(par + m, beta + lo, m * sizeof(double), cudaMemcpyHostToDevice, st));
+  OSB_CUDA(ctx, launch_blasius(variant, integrator, nbl, ymin, ymax, m, par, par + m, tab, work, par + 2 * m, np, st));
+  ctx->launches += 2;  // spline_grid_kernel + blasius_kernel
+  // device layout is [array][i][p] (profile-fastest, coalesced for the march); the caller wants [p][i]:
+  // transposed on the device, then one contiguous copy per requested table
+  double *outs[4] = {U, Uspl, d2U, d2Uspl};
+  if (U || Uspl || d2U || d2Uspl) {
+    double *tr = nullptr;
+    OSB_CUDA(ctx, scr.alloc(&tr, 4 * n1 * m * sizeof(double)));
+    OSB_CUDA(ctx, launch_transpose_tables(tab, tr, nbl, m, st));
+    ctx->launches++;
+    for (int a = 0; a < 4; ++a)
+      if (outs[a])
+        OSB_CUDA(ctx, cudaMemcpyAsync(outs[a] + (size_t)lo * n1, tr + (size_t)a * n1 * m, n1 * m * sizeof(double),
+                                      cudaMemcpyDeviceToHost, st));
+  }
+  if (f2p_out) OSB_CUDA(ctx, cudaMemcpyAsync(f2p_out + lo, par + 2 * m, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (npass) OSB_CUDA(ctx, cudaMemcpyAsync(npass + lo, np, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  return OSB_OK;
+}
+
 int osb_profile_blasius_batch(osb_ctx *ctx, int variant, int integrator, int nbl, double ymin,
                               double ymax, int64_t nprof, const double *f2p, const double *beta,
                               double *U, double *Uspl, double *d2U, double *d2Uspl,
@@ -316,38 +379,22 @@ int osb_profile_blasius_batch(osb_ctx *ctx, int variant, int integrator, int nbl
   if (variant != OSB_FLOW_CONTEBL && variant != OSB_FLOW_ORRSOM && variant != OSB_FLOW_ORRSPACE)
     return fail(ctx, OSB_E_ARG, "variant must be CONTEBL, ORRSOM or ORRSPACE");
   if (nbl < 8) return fail(ctx, OSB_E_ARG, "nbl < 8");
-  cudaStream_t st = ctx->streams[0];
-  OSB_CUDA(ctx, cudaSetDevice(ctx->devices[0]));
-  const size_t n2 = (size_t)nbl + 2;
-  Scratch scr(ctx->devices[0], st, ctx->pools[0]);
-  double *tab = nullptr, *work = nullptr, *par = nullptr;
-  int32_t *np = nullptr;
-  OSB_CUDA(ctx, scr.alloc(&tab, 5 * n2 * nprof * sizeof(double)));
-  OSB_CUDA(ctx, scr.alloc(&work, blasius_scratch_doubles(nbl, nprof) * sizeof(double)));
-  OSB_CUDA(ctx, scr.alloc(&par, 3 * nprof * sizeof(double)));
-  OSB_CUDA(ctx, scr.alloc(&np, nprof * sizeof(int32_t)));
-  OSB_CUDA(ctx, cudaMemcpyAsync(par, f2p, nprof * sizeof(double), cudaMemcpyHostToDevice, st));
-  OSB_CUDA(ctx, cudaMemcpyAsync(par + nprof, beta, nprof * sizeof(double), cudaMemcpyHostToDevice, st));
-  OSB_CUDA(ctx, launch_blasius(variant, integrator, nbl, ymin, ymax, nprof, par, par + nprof, tab, work,
-                               par + 2 * nprof, np, st));
-  ctx->launches++;
-  ctx->launches++;  // spline_grid_kernel
-  // device layout is [array][i][p] (profile-fastest, coalesced for the march); the caller wants [p][i]:
-  // transposed on the device, then one contiguous copy per requested table
-  double *outs[4] = {U, Uspl, d2U, d2Uspl};
-  if (U || Uspl || d2U || d2Uspl) {
-    double *tr = nullptr;
-    OSB_CUDA(ctx, scr.alloc(&tr, 4 * (size_t)(nbl + 1) * nprof * sizeof(double)));
-    OSB_CUDA(ctx, launch_transpose_tables(tab, tr, nbl, nprof, st));
-    ctx->launches++;
-    for (int a = 0; a < 4; ++a)
-      if (outs[a])
-        OSB_CUDA(ctx, cudaMemcpyAsync(outs[a], tr + (size_t)a * (nbl + 1) * nprof, (size_t)(nbl + 1) * nprof * sizeof(double),
-                                      cudaMemcpyDeviceToHost, st));
+  // profiles cost the same to first order: contiguous shares, one per device, all enqueued before the first wait
+  const int ndev = (int)ctx->devices.size();
+  std::vector<std::unique_ptr<Scratch>> guards(ndev);
+  for (int d = 0; d < ndev; ++d) {
+    int64_t lo, hi;
+    chunk(nprof, ndev, d, &lo, &hi);
+    if (hi <= lo) continue;
+    guards[d].reset(new Scratch(ctx->devices[d], ctx->streams[d], ctx->pools[d]));
+    int rc = blasius_batch_slice(ctx, d, *guards[d], variant, integrator, nbl, ymin, ymax, lo, hi - lo, f2p, beta, U, Uspl, d2U,
+                                 d2Uspl, f2p_out, npass);
+    if (rc) return rc;
   }
-  if (f2p_out) OSB_CUDA(ctx, cudaMemcpyAsync(f2p_out, par + 2 * nprof, nprof * sizeof(double), cudaMemcpyDeviceToHost, st));
-  if (npass) OSB_CUDA(ctx, cudaMemcpyAsync(npass, np, nprof * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  OSB_CUDA(ctx, cudaStreamSynchronize(st));
+  for (int d = 0; d < ndev; ++d) {
+    OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
+    OSB_CUDA(ctx, cudaStreamSynchronize(ctx->streams[d]));
+  }
   return OSB_OK;
 }
 
@@ -504,25 +551,13 @@ int osb_shoot_temporal(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profi
   if (npts == 0) return OSB_OK;
   if (history && hist_cap < 1) return fail(ctx, OSB_E_ARG, "hist_cap < 1");
   const int ndev = (int)ctx->devices.size();
-  // pass counts vary by region of a sweep, so contiguous blocks would imbalance the devices:
-  // tiles of the flattened point index are dealt cyclically (tile t -> device t mod ndev) and packed
-  // contiguously in each device's buffers.  Per-point results do not depend on the partition.
-  struct Seg { int64_t host_lo, n, dev_off; };
   struct Buf { double *alpha = 0, *Re = 0, *c = 0, *resid = 0, *hist = 0; int32_t *ip = 0; double2 *tab = 0; int64_t n = 0; std::vector<Seg> segs; };
   std::vector<Buf> bufs(ndev);
   {
-    int64_t tile = npts;
-    if (ndev > 1) {
-      tile = ((npts / ((int64_t)ndev * 32) + 4095) / 4096) * 4096;
-      tile = std::min<int64_t>(std::max<int64_t>(tile, 4096), (int64_t)1 << 20);
-    }
-    int64_t t = 0;
-    for (int64_t lo = 0; lo < npts; lo += tile, ++t) {
-      Buf &b = bufs[(int)(t % ndev)];
-      const int64_t n = std::min(tile, npts - lo);
-      b.segs.push_back(Seg{lo, n, b.n});
-      b.n += n;
-    }
+    int64_t tile = ((npts / ((int64_t)ndev * 32) + 4095) / 4096) * 4096;
+    tile = std::min<int64_t>(std::max<int64_t>(tile, 4096), (int64_t)1 << 20);
+    Deal dl = deal_tiles(npts, ndev, tile);
+    for (int d = 0; d < ndev; ++d) { bufs[d].segs = dl.segs[d]; bufs[d].n = dl.count[d]; }
   }
   std::vector<std::unique_ptr<Scratch>> guards(ndev);
   // phase 1: per device H2D + launch (kernels of different devices overlap)
@@ -608,13 +643,18 @@ int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_
   if (nlines == 0) return OSB_OK;
   const int ndev = (int)ctx->devices.size();
   if (history && hist_cap < 1) return fail(ctx, OSB_E_ARG, "hist_cap < 1");
-  struct Buf { double *in = 0, *out = 0, *hist = 0; int32_t *ip = 0; double2 *tab = 0; int64_t lo = 0, hi = 0; };
+  // continuation lines are the indivisible unit; tiles of lines are dealt cyclically to the devices
+  struct Buf { double *in = 0, *out = 0, *hist = 0; int32_t *ip = 0; double2 *tab = 0; int64_t n = 0; std::vector<Seg> segs; };
   std::vector<Buf> bufs(ndev);
+  {
+    const int64_t tile = std::max<int64_t>(32, (nlines + (int64_t)ndev * 8 - 1) / ((int64_t)ndev * 8));
+    Deal dl = deal_tiles(nlines, ndev, tile);
+    for (int d = 0; d < ndev; ++d) { bufs[d].segs = dl.segs[d]; bufs[d].n = dl.count[d]; }
+  }
   std::vector<std::unique_ptr<Scratch>> guards(ndev);
   for (int d = 0; d < ndev; ++d) {
     Buf &b = bufs[d];
-    chunk(nlines, ndev, d, &b.lo, &b.hi);
-    const int64_t n = b.hi - b.lo;
+    const int64_t n = b.n;
     if (n <= 0) continue;
     cudaStream_t st = ctx->streams[d];
     OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
@@ -628,10 +668,12 @@ int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_
       OSB_CUDA(ctx, scr.alloc(&b.hist, (size_t)n * niter * hist_cap * 4 * sizeof(double)));
       OSB_CUDA(ctx, cudaMemsetAsync(b.hist, 0, (size_t)n * niter * hist_cap * 4 * sizeof(double), st));
     }
-    OSB_CUDA(ctx, cudaMemcpyAsync(b.in, Re + b.lo, n * sizeof(double), cudaMemcpyHostToDevice, st));
-    OSB_CUDA(ctx, cudaMemcpyAsync(b.in + n, domega + b.lo, n * sizeof(double), cudaMemcpyHostToDevice, st));
-    OSB_CUDA(ctx, cudaMemcpyAsync(b.in + 2 * n, omega0 + 2 * b.lo, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-    OSB_CUDA(ctx, cudaMemcpyAsync(b.in + 4 * n, alpha0 + 2 * b.lo, n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    for (const Seg &g : b.segs) {
+      OSB_CUDA(ctx, cudaMemcpyAsync(b.in + g.dev_off, Re + g.host_lo, g.n * sizeof(double), cudaMemcpyHostToDevice, st));
+      OSB_CUDA(ctx, cudaMemcpyAsync(b.in + n + g.dev_off, domega + g.host_lo, g.n * sizeof(double), cudaMemcpyHostToDevice, st));
+      OSB_CUDA(ctx, cudaMemcpyAsync(b.in + 2 * n + 2 * g.dev_off, omega0 + 2 * g.host_lo, g.n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+      OSB_CUDA(ctx, cudaMemcpyAsync(b.in + 4 * n + 2 * g.dev_off, alpha0 + 2 * g.host_lo, g.n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
     rc = make_stage_table(ctx, d, scr, opts, prof, &b.tab);
     if (rc) return rc;
     ShootArgs a = base;
@@ -651,18 +693,20 @@ int osb_shoot_spatial_lines(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_
   }
   for (int d = 0; d < ndev; ++d) {
     Buf &b = bufs[d];
-    const int64_t n = b.hi - b.lo;
+    const int64_t n = b.n;
     if (n <= 0) continue;
     cudaStream_t st = ctx->streams[d];
     const int64_t m = n * niter;
     OSB_CUDA(ctx, cudaSetDevice(ctx->devices[d]));
-    OSB_CUDA(ctx, cudaMemcpyAsync(alpha_out + 2 * b.lo * niter, b.out, m * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    OSB_CUDA(ctx, cudaMemcpyAsync(passes + b.lo * niter, b.ip, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    OSB_CUDA(ctx, cudaMemcpyAsync(qend + b.lo * niter, b.ip + m, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    OSB_CUDA(ctx, cudaMemcpyAsync(status + b.lo * niter, b.ip + 2 * m, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    if (history) {
-      OSB_CUDA(ctx, cudaMemcpyAsync(history + (size_t)b.lo * niter * hist_cap * 4, b.hist,
-                                    (size_t)m * hist_cap * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    for (const Seg &g : b.segs) {
+      const int64_t ho = g.host_lo * niter, dof = g.dev_off * niter, cnt = g.n * niter;
+      OSB_CUDA(ctx, cudaMemcpyAsync(alpha_out + 2 * ho, b.out + 2 * dof, cnt * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      OSB_CUDA(ctx, cudaMemcpyAsync(passes + ho, b.ip + dof, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      OSB_CUDA(ctx, cudaMemcpyAsync(qend + ho, b.ip + m + dof, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      OSB_CUDA(ctx, cudaMemcpyAsync(status + ho, b.ip + 2 * m + dof, cnt * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      if (history)
+        OSB_CUDA(ctx, cudaMemcpyAsync(history + (size_t)ho * hist_cap * 4, b.hist + (size_t)dof * hist_cap * 4,
+                                      (size_t)cnt * hist_cap * 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
   }
   for (int d = 0; d < ndev; ++d) {
@@ -760,12 +804,13 @@ int osb_shoot_neutral(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profil
 }
 
 // one chunk of osb_eigfun: all scratch of the chunk lives in `scr`
-static int eigfun_chunk(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof, const ShootArgs &base,
+static int eigfun_chunk(osb_ctx *ctx, int slot, const osb_shoot_opts *opts, const osb_profile *prof, const ShootArgs &base,
                         int analytic, int64_t npts, const double *alpha_or_omega, const double *Re,
                         const double *eig, double *y, double *vmax, int32_t *qend) {
-  cudaStream_t st = ctx->streams[0];
+  cudaStream_t st = ctx->streams[slot];
+  OSB_CUDA(ctx, cudaSetDevice(ctx->devices[slot]));
   const size_t n1 = (size_t)opts->nstep + 1;
-  Scratch scr(ctx->devices[0], st, ctx->pools[0]);
+  Scratch scr(ctx->devices[slot], st, ctx->pools[slot]);
   double *d_in = nullptr, *d_tq = nullptr;
   double2 *d_U = nullptr, *d_P = nullptr, *d_y = nullptr, *d_vmax = nullptr, *tab = nullptr;
   int32_t *d_q = nullptr;
@@ -780,7 +825,7 @@ static int eigfun_chunk(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_prof
   OSB_CUDA(ctx, cudaMemcpyAsync(d_in, eig, npts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   OSB_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * npts, alpha_or_omega, npts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   OSB_CUDA(ctx, cudaMemcpyAsync(d_in + 4 * npts, Re, npts * sizeof(double), cudaMemcpyHostToDevice, st));
-  int rc = make_stage_table(ctx, 0, scr, opts, prof, &tab);
+  int rc = make_stage_table(ctx, slot, scr, opts, prof, &tab);
   if (rc) return rc;
   ShootArgs a = base;
   EigfunArgs e;
@@ -815,7 +860,6 @@ int osb_eigfun(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof
   if (rc) return rc;
   if (a.spatial ? !omega : !alpha) return fail(ctx, OSB_E_ARG, "alpha (temporal) / omega (spatial) required");
   if (npts == 0) return OSB_OK;
-  OSB_CUDA(ctx, cudaSetDevice(ctx->devices[0]));
   // the second pass keeps the whole orthonormalised trajectory (shoot.f:762-810): 272 bytes per step per
   // point of device scratch.  Bound it to ~8 GB per chunk so that any npts fits the GPU.
   const size_t n1 = (size_t)opts->nstep + 1;
@@ -823,12 +867,25 @@ int osb_eigfun(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof
   int64_t chunk = std::max<int64_t>(1, (int64_t)((8ull << 30) / per_point));
   if (const char *e = getenv("OSB_EIGFUN_CHUNK")) chunk = std::max<int64_t>(1, atoll(e));  // test hook
   const double *ao = a.spatial ? omega : alpha;
-  for (int64_t lo = 0; lo < npts; lo += chunk) {
-    const int64_t m = std::min(chunk, npts - lo);
-    rc = eigfun_chunk(ctx, opts, prof, a, analytic, m, ao + 2 * lo, Re + lo, eig + 2 * lo, y + (size_t)lo * n1 * 8,
-                      vmax + 2 * lo, qend ? qend + lo : nullptr);
-    if (rc) return rc;
-  }
+  const int ndev = (int)ctx->devices.size();
+  if (ndev > 1) chunk = std::min<int64_t>(chunk, std::max<int64_t>(1, (npts + ndev - 1) / ndev));
+  const int64_t nchunk = (npts + chunk - 1) / chunk;
+  // chunk k runs on device k mod ndev; one worker thread per device walks its chunks (points are independent)
+  auto worker = [&](int slot) -> int {
+    for (int64_t k = slot; k < nchunk; k += ndev) {
+      const int64_t lo = k * chunk, m = std::min(chunk, npts - lo);
+      int rcw = eigfun_chunk(ctx, slot, opts, prof, a, analytic, m, ao + 2 * lo, Re + lo, eig + 2 * lo, y + (size_t)lo * n1 * 8,
+                             vmax + 2 * lo, qend ? qend + lo : nullptr);
+      if (rcw) return rcw;
+    }
+    return OSB_OK;
+  };
+  if (ndev == 1 || nchunk == 1) return worker(0);
+  std::vector<int> rcs(ndev, OSB_OK);
+  std::vector<std::thread> th;
+  for (int d = 0; d < ndev; ++d) th.emplace_back([&, d] { rcs[d] = worker(d); });
+  for (auto &t : th) t.join();
+  for (int d = 0; d < ndev; ++d) if (rcs[d]) return rcs[d];
   return OSB_OK;
 }
 

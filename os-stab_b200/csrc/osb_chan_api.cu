@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <memory>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -29,22 +30,28 @@ int ctx_fail(osb_ctx *ctx, int code, const std::string &msg);
 int ctx_device(const osb_ctx *ctx, int slot);
 void ctx_count_launch(osb_ctx *ctx, int n);
 cudaMemPool_t ctx_pool(const osb_ctx *ctx, int slot);
+cudaStream_t ctx_stream(const osb_ctx *ctx, int slot);
 }  // namespace osb
 
 struct osb_chan {
   int disc = 0, N = 0, n = 0;
   int bl = 0;  // mapped boundary-layer operator (osb_chan_create_bl): tables are the metric-folded D2', D4'
   std::vector<double> eta, u, d1u, d2u, D2full, D4full;  // host copies, full (N+1) grid, row-major (i,j)
-  double *dD2 = nullptr, *dD4 = nullptr, *du = nullptr, *dd2u = nullptr;  // device, interior, column-major
-  double2 *dBand = nullptr;  // FD only: [n][9] (D2, D4)(r, r-4+j), the band of the 9-diagonal operator
-  int device = 0;
+  struct Dev {              // the tables on one device of the context (every device holds its own copy)
+    int device = 0;
+    double *dD2 = nullptr, *dD4 = nullptr, *du = nullptr, *dd2u = nullptr;  // interior, column-major
+    double2 *dBand = nullptr;  // FD only: [n][9] (D2, D4)(r, r-4+j), the band of the 9-diagonal operator
+  };
+  std::vector<Dev> dev;
   osb_chan() = default;
   osb_chan(const osb_chan &) = delete;
   osb_chan &operator=(const osb_chan &) = delete;
   ~osb_chan() {
-    if (!dD2 && !dD4 && !du && !dd2u && !dBand) return;
-    cudaSetDevice(device);
-    cudaFree(dD2); cudaFree(dD4); cudaFree(du); cudaFree(dd2u); cudaFree(dBand);
+    for (Dev &d : dev) {
+      if (!d.dD2 && !d.dD4 && !d.du && !d.dd2u && !d.dBand) continue;
+      cudaSetDevice(d.device);
+      cudaFree(d.dD2); cudaFree(d.dD4); cudaFree(d.du); cudaFree(d.dd2u); cudaFree(d.dBand);
+    }
   }
 };
 
@@ -102,7 +109,7 @@ void cheb_first_derivative(std::vector<double> &D, int N) {
 // triple loops, orrfdchan.f:318-342).  Operands are uploaded once; results stay on the device for the next product.
 class TableProducts {
  public:
-  TableProducts(osb_ctx *ctx, int device, int N) : ctx_(ctx), device_(device), ld_(N + 1), st_((cudaStream_t)osb_stream(ctx)) {}
+  TableProducts(osb_ctx *ctx, int device, int N) : ctx_(ctx), device_(device), ld_(N + 1), st_(ctx_stream(ctx, 0)) {}
   ~TableProducts() {
     cudaSetDevice(device_);
     for (double *p : bufs_) cudaFree(p);
@@ -141,6 +148,25 @@ class TableProducts {
   std::vector<double *> bufs_;
 };
 
+// One worker thread per device of the context, each with its own contiguous share of a batch (the instances of a
+// sweep cost the same to first order; every device holds its own copy of the tables).  fn(slot, lo, m) -> rc.
+template <class F>
+static int for_each_device_share(osb_ctx *ctx, int64_t nitems, F fn) {
+  const int ndev = osb_device_count(ctx);
+  if (ndev == 1 || nitems < 2 * (int64_t)ndev) return fn(0, (int64_t)0, nitems);
+  const int64_t per = (nitems + ndev - 1) / ndev;
+  std::vector<int> rcs(ndev, OSB_OK);
+  std::vector<std::thread> th;
+  for (int d = 0; d < ndev; ++d) {
+    const int64_t lo = std::min<int64_t>(nitems, per * d), m = std::min<int64_t>(nitems, per * (d + 1)) - lo;
+    if (m <= 0) continue;
+    th.emplace_back([&, d, lo, m] { rcs[d] = fn(d, lo, m); });
+  }
+  for (auto &t : th) t.join();
+  for (int d = 0; d < ndev; ++d) if (rcs[d]) return rcs[d];
+  return OSB_OK;
+}
+
 }  // namespace
 
 // interior blocks of D2, D4 (column-major n x n), profile rows and -- for the banded FD path -- the
@@ -155,17 +181,9 @@ static int upload_tables(osb_ctx *ctx, osb_chan *c) {
       h4[(size_t)j * n + i] = at(c->D4full, N, i + 1, j + 1);
     }
   for (int i = 0; i < n; ++i) { hu[i] = c->u[i + 1]; hd[i] = c->d2u[i + 1]; }
-  CH_CUDA(ctx, cudaSetDevice(c->device));
-  CH_CUDA(ctx, cudaMalloc(&c->dD2, h2.size() * sizeof(double)));
-  CH_CUDA(ctx, cudaMalloc(&c->dD4, h4.size() * sizeof(double)));
-  CH_CUDA(ctx, cudaMalloc(&c->du, n * sizeof(double)));
-  CH_CUDA(ctx, cudaMalloc(&c->dd2u, n * sizeof(double)));
-  CH_CUDA(ctx, cudaMemcpy(c->dD2, h2.data(), h2.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CH_CUDA(ctx, cudaMemcpy(c->dD4, h4.data(), h4.size() * sizeof(double), cudaMemcpyHostToDevice));
-  CH_CUDA(ctx, cudaMemcpy(c->du, hu.data(), n * sizeof(double), cudaMemcpyHostToDevice));
-  CH_CUDA(ctx, cudaMemcpy(c->dd2u, hd.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+  std::vector<double> hb;
   if (disc == OSB_DISC_FD) {
-    std::vector<double> hb((size_t)n * 9 * 2, 0.0);
+    hb.assign((size_t)n * 9 * 2, 0.0);
     for (int r = 0; r < n; ++r)
       for (int j = 0; j < 9; ++j) {
         const int cc = r - 4 + j;
@@ -173,8 +191,25 @@ static int upload_tables(osb_ctx *ctx, osb_chan *c) {
         hb[((size_t)r * 9 + j) * 2] = at(c->D2full, N, r + 1, cc + 1);
         hb[((size_t)r * 9 + j) * 2 + 1] = at(c->D4full, N, r + 1, cc + 1);
       }
-    CH_CUDA(ctx, cudaMalloc(&c->dBand, hb.size() * sizeof(double)));
-    CH_CUDA(ctx, cudaMemcpy(c->dBand, hb.data(), hb.size() * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  const int ndev = osb_device_count(ctx);
+  c->dev.resize(ndev);
+  for (int s = 0; s < ndev; ++s) {
+    osb_chan::Dev &d = c->dev[s];
+    d.device = ctx_device(ctx, s);
+    CH_CUDA(ctx, cudaSetDevice(d.device));
+    CH_CUDA(ctx, cudaMalloc(&d.dD2, h2.size() * sizeof(double)));
+    CH_CUDA(ctx, cudaMalloc(&d.dD4, h4.size() * sizeof(double)));
+    CH_CUDA(ctx, cudaMalloc(&d.du, n * sizeof(double)));
+    CH_CUDA(ctx, cudaMalloc(&d.dd2u, n * sizeof(double)));
+    CH_CUDA(ctx, cudaMemcpy(d.dD2, h2.data(), h2.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CH_CUDA(ctx, cudaMemcpy(d.dD4, h4.data(), h4.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CH_CUDA(ctx, cudaMemcpy(d.du, hu.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    CH_CUDA(ctx, cudaMemcpy(d.dd2u, hd.data(), n * sizeof(double), cudaMemcpyHostToDevice));
+    if (disc == OSB_DISC_FD) {
+      CH_CUDA(ctx, cudaMalloc(&d.dBand, hb.size() * sizeof(double)));
+      CH_CUDA(ctx, cudaMemcpy(d.dBand, hb.data(), hb.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
   }
   return OSB_OK;
 }
@@ -186,9 +221,8 @@ int osb_chan_create(osb_ctx *ctx, int disc, int N, osb_chan **out) {
   if (disc != OSB_DISC_FD && disc != OSB_DISC_CHEB && disc != OSB_DISC_CHEB_NUM)
     return ctx_fail(ctx, OSB_E_ARG, "unknown discretisation");
   if (N < 8 || N > 1024) return ctx_fail(ctx, OSB_E_ARG, "N out of range [8,1024]");
-  if (osb_device_count(ctx) != 1) return ctx_fail(ctx, OSB_E_ARG, "the matrix path takes a single-device context");
   std::unique_ptr<osb_chan> c(new osb_chan);
-  c->disc = disc; c->N = N; c->n = N - 1; c->device = ctx_device(ctx, 0);
+  c->disc = disc; c->N = N; c->n = N - 1;
   const size_t n1 = (size_t)N + 1, nn = n1 * n1;
   c->eta.resize(n1); c->u.resize(n1); c->d1u.resize(n1); c->d2u.resize(n1);
   std::vector<double> D1hat(nn), D1(nn), D3(nn);
@@ -198,7 +232,7 @@ int osb_chan_create(osb_ctx *ctx, int disc, int N, osb_chan **out) {
   if (disc == OSB_DISC_FD) { fd_first_derivative(D1hat, N, c->eta); fd_first_derivative(D1, N, c->eta); }
   else { cheb_first_derivative(D1hat, N); cheb_first_derivative(D1, N); }
   for (int i = 0; i <= N; ++i) { at(D1, N, 0, i) = 0.0; at(D1, N, N, i) = 0.0; }  // phi' = 0
-  TableProducts tp(ctx, c->device, N);
+  TableProducts tp(ctx, ctx_device(ctx, 0), N);
   double *dD1hat = nullptr, *dD1 = nullptr, *dD2 = nullptr, *dD3 = nullptr, *dD4 = nullptr, *dD2hat = nullptr;
   std::vector<double> D2hat;
   int rc = tp.upload(D1hat, &dD1hat);
@@ -253,9 +287,8 @@ int osb_chan_create_bl(osb_ctx *ctx, int disc, int N, double lmap, const double 
   if (N < 8 || N > 1024) return ctx_fail(ctx, OSB_E_ARG, "N out of range [8,1024]");
   if (!(lmap > 0.0)) return ctx_fail(ctx, OSB_E_ARG, "lmap <= 0");
   if (merge < 0 || merge >= N) return ctx_fail(ctx, OSB_E_ARG, "merge out of range [0,N)");
-  if (osb_device_count(ctx) != 1) return ctx_fail(ctx, OSB_E_ARG, "the matrix path takes a single-device context");
   std::unique_ptr<osb_chan> c(new osb_chan);
-  c->disc = disc; c->N = N; c->n = N - 1; c->device = ctx_device(ctx, 0); c->bl = 1;
+  c->disc = disc; c->N = N; c->n = N - 1; c->bl = 1;
   const size_t n1 = (size_t)N + 1, nn = n1 * n1;
   bl_grid(disc, N, c->eta);
   c->u.resize(n1); c->d1u.resize(n1); c->d2u.resize(n1);
@@ -264,7 +297,7 @@ int osb_chan_create_bl(osb_ctx *ctx, int disc, int N, double lmap, const double 
   else { cheb_first_derivative(D1hat, N); cheb_first_derivative(D1, N); }
   for (int i = 0; i <= N; ++i) { at(D1, N, 0, i) = 0.0; at(D1, N, N, i) = 0.0; }  // v' = 0 at both ends
   {
-    TableProducts tp(ctx, c->device, N);
+    TableProducts tp(ctx, ctx_device(ctx, 0), N);
     double *dD1hat = nullptr, *dD1 = nullptr, *dD2 = nullptr, *dD3 = nullptr, *dD4 = nullptr, *dD2hat = nullptr;
     int rcp = tp.upload(D1hat, &dD1hat);
     if (!rcp) rcp = tp.upload(D1, &dD1);
@@ -326,26 +359,26 @@ int osb_chan_tables(osb_ctx *ctx, const osb_chan *c, double *eta, double *u, dou
 }
 
 // run one batch of instances (alpha, Re, sigma) -> (omega, delta, iters[, evec])
-static int run_eig_chunk(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::vector<double> &alpha,
+static int run_eig_chunk(osb_ctx *ctx, const osb_chan *c, int slot, int64_t ninst, const std::vector<double> &alpha,
                          const std::vector<double> &Re, const std::vector<double> &sigma, int outer, int inner,
                          double tol, std::vector<double> &omega, std::vector<double> &delta,
                          std::vector<int32_t> &iters, double *evec_host, double *adj_host = nullptr, int adj_form = 0) {
-  cudaStream_t st = (cudaStream_t)osb_stream(ctx);
+  cudaStream_t st = ctx_stream(ctx, slot);
+  const osb_chan::Dev &cd = c->dev[slot];
   const int n = c->n;
   int grid = 0;
   size_t smem = 0;
-  CH_CUDA(ctx, cudaSetDevice(c->device));
+  CH_CUDA(ctx, cudaSetDevice(cd.device));
   // the FD operator is banded (half bandwidth 4): banded LU, one thread per instance
   const bool banded = (c->disc == OSB_DISC_FD) && !getenv("OSB_FD_DENSE");
   if (!banded) {
-    CH_CUDA(ctx, cudaSetDevice(c->device));
     if (n > chan_dense_max_n())
       return ctx_fail(ctx, OSB_E_ARG, "N too large for the dense kernels (their 16-column LU panel lives in shared memory): "
                                       "limit N = " + std::to_string(chan_dense_max_n() + 1) +
                                       "; the FD operator has no such limit (banded kernels)");
   }
   if (!banded) CH_CUDA(ctx, chan_eig_grid(n, ninst, &grid, &smem));
-  Scratch scr(c->device, st, ctx_pool(ctx, 0));
+  Scratch scr(cd.device, st, ctx_pool(ctx, slot));
   double *d_in = nullptr, *d_out = nullptr;
   double2 *work = nullptr, *d_evec = nullptr, *d_adj = nullptr;
   int32_t *d_it = nullptr;
@@ -359,11 +392,11 @@ static int run_eig_chunk(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const s
   CH_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * ninst, sigma.data(), ninst * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
   CH_CUDA(ctx, cudaMemcpyAsync(d_in + 4 * ninst, Re.data(), ninst * sizeof(double), cudaMemcpyHostToDevice, st));
   if (banded)
-    CH_CUDA(ctx, launch_chan_fd_banded(n, c->dD2, c->dD4, c->du, c->dd2u, c->dBand, work, ninst, (const double2 *)d_in,
+    CH_CUDA(ctx, launch_chan_fd_banded(n, cd.dD2, cd.dD4, cd.du, cd.dd2u, cd.dBand, work, ninst, (const double2 *)d_in,
                                        d_in + 4 * ninst, (const double2 *)(d_in + 2 * ninst), outer, inner, tol,
                                        (double2 *)d_out, d_out + 2 * ninst, d_it, d_evec, d_adj, adj_form, st));
   else
-    CH_CUDA(ctx, launch_chan_eig(n, c->dD2, c->dD4, c->du, c->dd2u, work, grid, smem, ninst,
+    CH_CUDA(ctx, launch_chan_eig(n, cd.dD2, cd.dD4, cd.du, cd.dd2u, work, grid, smem, ninst,
                                  (const double2 *)d_in, d_in + 4 * ninst, (const double2 *)(d_in + 2 * ninst), outer,
                                  inner, tol, (double2 *)d_out, d_out + 2 * ninst, d_it, d_evec, d_adj, adj_form, st));
   ctx_count_launch(ctx, 1);
@@ -382,10 +415,10 @@ static int run_eig_chunk(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const s
 
 // The banded path keeps 13 n complex factors per instance in HBM (123 KB at N = 512): batches are walked in
 // chunks of at most ~8 GB of device scratch so that any batch size fits.
-static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::vector<double> &alpha,
-                   const std::vector<double> &Re, const std::vector<double> &sigma, int outer, int inner,
-                   double tol, std::vector<double> &omega, std::vector<double> &delta,
-                   std::vector<int32_t> &iters, double *evec_host, double *adj_host = nullptr, int adj_form = 0) {
+static int run_eig_slot(osb_ctx *ctx, const osb_chan *c, int slot, int64_t ninst, const std::vector<double> &alpha,
+                        const std::vector<double> &Re, const std::vector<double> &sigma, int outer, int inner,
+                        double tol, std::vector<double> &omega, std::vector<double> &delta,
+                        std::vector<int32_t> &iters, double *evec_host, double *adj_host = nullptr, int adj_form = 0) {
   const bool banded = (c->disc == OSB_DISC_FD) && !getenv("OSB_FD_DENSE");
   int64_t chunk = ninst;
   if (banded) {
@@ -394,7 +427,7 @@ static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::ve
     if (const char *e = getenv("OSB_CHAN_CHUNK")) chunk = std::max<int64_t>(1, atoll(e));  // test hook
   }
   if (ninst <= chunk)
-    return run_eig_chunk(ctx, c, ninst, alpha, Re, sigma, outer, inner, tol, omega, delta, iters, evec_host, adj_host, adj_form);
+    return run_eig_chunk(ctx, c, slot, ninst, alpha, Re, sigma, outer, inner, tol, omega, delta, iters, evec_host, adj_host, adj_form);
   omega.resize(2 * ninst); delta.resize(ninst); iters.resize(ninst);
   std::vector<double> a, r, sg, om, dl;
   std::vector<int32_t> it;
@@ -403,7 +436,7 @@ static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::ve
     a.assign(alpha.begin() + 2 * lo, alpha.begin() + 2 * (lo + m));
     r.assign(Re.begin() + lo, Re.begin() + lo + m);
     sg.assign(sigma.begin() + 2 * lo, sigma.begin() + 2 * (lo + m));
-    int rc = run_eig_chunk(ctx, c, m, a, r, sg, outer, inner, tol, om, dl, it,
+    int rc = run_eig_chunk(ctx, c, slot, m, a, r, sg, outer, inner, tol, om, dl, it,
                            evec_host ? evec_host + (size_t)lo * (c->n + 2) * 2 : nullptr,
                            adj_host ? adj_host + (size_t)lo * (c->n + 2) * 2 : nullptr, adj_form);
     if (rc) return rc;
@@ -412,6 +445,29 @@ static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::ve
     std::copy(it.begin(), it.end(), iters.begin() + lo);
   }
   return OSB_OK;
+}
+
+// a batch of instances over all devices of the context
+static int run_eig(osb_ctx *ctx, const osb_chan *c, int64_t ninst, const std::vector<double> &alpha,
+                   const std::vector<double> &Re, const std::vector<double> &sigma, int outer, int inner,
+                   double tol, std::vector<double> &omega, std::vector<double> &delta,
+                   std::vector<int32_t> &iters, double *evec_host, double *adj_host = nullptr, int adj_form = 0) {
+  if (osb_device_count(ctx) == 1)
+    return run_eig_slot(ctx, c, 0, ninst, alpha, Re, sigma, outer, inner, tol, omega, delta, iters, evec_host, adj_host, adj_form);
+  omega.resize(2 * ninst); delta.resize(ninst); iters.resize(ninst);
+  const size_t ev_stride = (size_t)(c->n + 2) * 2;
+  return for_each_device_share(ctx, ninst, [&](int slot, int64_t lo, int64_t m) -> int {
+    std::vector<double> a(alpha.begin() + 2 * lo, alpha.begin() + 2 * (lo + m)), r(Re.begin() + lo, Re.begin() + lo + m),
+        sg(sigma.begin() + 2 * lo, sigma.begin() + 2 * (lo + m)), om, dl;
+    std::vector<int32_t> it;
+    int rc = run_eig_slot(ctx, c, slot, m, a, r, sg, outer, inner, tol, om, dl, it, evec_host ? evec_host + (size_t)lo * ev_stride : nullptr,
+                          adj_host ? adj_host + (size_t)lo * ev_stride : nullptr, adj_form);
+    if (rc) return rc;
+    std::copy(om.begin(), om.end(), omega.begin() + 2 * lo);
+    std::copy(dl.begin(), dl.end(), delta.begin() + lo);
+    std::copy(it.begin(), it.end(), iters.begin() + lo);
+    return OSB_OK;
+  });
 }
 
 // The reference keeps ONE eigenvalue out of the full spectrum:
@@ -603,32 +659,41 @@ int osb_chan_spectrum(osb_ctx *ctx, const osb_chan *c, double Re, int64_t npts, 
                       double *spectrum, int32_t *status) {
   if (!ctx || !c || npts < 0 || !alpha || !spectrum || !status) return ctx_fail(ctx, OSB_E_ARG, "null argument");
   if (npts == 0) return OSB_OK;
-  cudaStream_t st = (cudaStream_t)osb_stream(ctx);
   const int n = c->n;
-  int grid = 0;
-  size_t smem = 0;
-  CH_CUDA(ctx, cudaSetDevice(c->device));
+  CH_CUDA(ctx, cudaSetDevice(c->dev[0].device));
   if (n > chan_dense_max_n())
     return ctx_fail(ctx, OSB_E_ARG, "N too large for the dense kernels (their 16-column LU panel lives in shared memory): "
                                     "limit N = " + std::to_string(chan_dense_max_n() + 1));
-  CH_CUDA(ctx, chan_spectrum_grid(n, npts, &grid, &smem));
-  Scratch scr(c->device, st, ctx_pool(ctx, 0));
-  double *d_in = nullptr;
-  double2 *work = nullptr, *d_eig = nullptr;
-  int32_t *d_st = nullptr;
-  std::vector<double> Rev(npts, Re);
-  CH_CUDA(ctx, scr.alloc(&d_in, npts * 3 * sizeof(double)));  // alpha(2), Re
-  CH_CUDA(ctx, scr.alloc(&work, (size_t)grid * 2 * n * n * sizeof(double2)));
-  CH_CUDA(ctx, scr.alloc(&d_eig, (size_t)npts * n * sizeof(double2)));
-  CH_CUDA(ctx, scr.alloc(&d_st, npts * sizeof(int32_t)));
-  CH_CUDA(ctx, cudaMemcpyAsync(d_in, alpha, npts * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-  CH_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * npts, Rev.data(), npts * sizeof(double), cudaMemcpyHostToDevice, st));
-  CH_CUDA(ctx, launch_chan_spectrum(n, c->dD2, c->dD4, c->du, c->dd2u, work, grid, smem, npts, (const double2 *)d_in,
-                                    d_in + 2 * npts, d_eig, d_st, st));
-  ctx_count_launch(ctx, 1);
-  CH_CUDA(ctx, cudaMemcpyAsync(spectrum, d_eig, (size_t)npts * n * sizeof(double2), cudaMemcpyDeviceToHost, st));
-  CH_CUDA(ctx, cudaMemcpyAsync(status, d_st, npts * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CH_CUDA(ctx, cudaStreamSynchronize(st));
+  // inv(B)A, Hessenberg, QR: every device of the context takes a contiguous share of the alphas
+  {
+    int rc = for_each_device_share(ctx, npts, [&](int slot, int64_t lo, int64_t m) -> int {
+      cudaStream_t st = ctx_stream(ctx, slot);
+      const osb_chan::Dev &cd = c->dev[slot];
+      int grid = 0;
+      size_t smem = 0;
+      CH_CUDA(ctx, cudaSetDevice(cd.device));
+      CH_CUDA(ctx, chan_spectrum_grid(n, m, &grid, &smem));
+      Scratch scr(cd.device, st, ctx_pool(ctx, slot));
+      double *d_in = nullptr;
+      double2 *work = nullptr, *d_eig = nullptr;
+      int32_t *d_st = nullptr;
+      std::vector<double> Rev(m, Re);
+      CH_CUDA(ctx, scr.alloc(&d_in, m * 3 * sizeof(double)));  // alpha(2), Re
+      CH_CUDA(ctx, scr.alloc(&work, (size_t)grid * 2 * n * n * sizeof(double2)));
+      CH_CUDA(ctx, scr.alloc(&d_eig, (size_t)m * n * sizeof(double2)));
+      CH_CUDA(ctx, scr.alloc(&d_st, m * sizeof(int32_t)));
+      CH_CUDA(ctx, cudaMemcpyAsync(d_in, alpha + 2 * lo, m * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+      CH_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * m, Rev.data(), m * sizeof(double), cudaMemcpyHostToDevice, st));
+      CH_CUDA(ctx, launch_chan_spectrum(n, cd.dD2, cd.dD4, cd.du, cd.dd2u, work, grid, smem, m, (const double2 *)d_in,
+                                        d_in + 2 * m, d_eig, d_st, st));
+      ctx_count_launch(ctx, 1);
+      CH_CUDA(ctx, cudaMemcpyAsync(spectrum + (size_t)lo * n * 2, d_eig, (size_t)m * n * sizeof(double2), cudaMemcpyDeviceToHost, st));
+      CH_CUDA(ctx, cudaMemcpyAsync(status + lo, d_st, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      CH_CUDA(ctx, cudaStreamSynchronize(st));
+      return OSB_OK;
+    });
+    if (rc) return rc;
+  }
   // Polish: eigenvalues of inv(B)A inherit its conditioning (the collocation pencil: ~1e-7 on the least stable
   // mode), shift-invert on the pencil itself does not.  Every QR value seeds one inverse iteration; the refined
   // value replaces it when the iteration settled next to its seed.
@@ -675,37 +740,44 @@ int osb_chan_neutral(osb_ctx *ctx, const osb_chan *c, int64_t nRe, const double 
   for (int64_t p = 0; p < nRe; ++p) { a[2 * p] = alpha0[p]; a[2 * p + 1] = 0.0; }
   int rc = scan_shifts(ctx, c, nRe, a.data(), Re, sig, ok);
   if (rc) return rc;
-  cudaStream_t st = (cudaStream_t)osb_stream(ctx);
   const int n = c->n;
-  int grid = 0;
-  size_t smem = 0;
-  CH_CUDA(ctx, cudaSetDevice(c->device));
-  CH_CUDA(ctx, chan_neutral_grid(n, nRe, &grid, &smem));
-  Scratch scr(c->device, st, ctx_pool(ctx, 0));
-  double *d_in = nullptr, *d_out = nullptr, *d_trace = nullptr;
-  double2 *work = nullptr;
-  int32_t *d_i = nullptr;
-  CH_CUDA(ctx, scr.alloc(&d_in, nRe * 4 * sizeof(double)));   // sigma0(2), Re, alpha0
-  CH_CUDA(ctx, scr.alloc(&d_out, nRe * 3 * sizeof(double)));  // omega(2), alpha
-  CH_CUDA(ctx, scr.alloc(&d_i, nRe * 2 * sizeof(int32_t)));
-  CH_CUDA(ctx, scr.alloc(&work, (size_t)grid * n * n * sizeof(double2)));
-  if (trace) {
-    CH_CUDA(ctx, scr.alloc(&d_trace, (size_t)nRe * maxit * 7 * sizeof(double)));
-    CH_CUDA(ctx, cudaMemsetAsync(d_trace, 0, (size_t)nRe * maxit * 7 * sizeof(double), st));
-  }
-  CH_CUDA(ctx, cudaMemcpyAsync(d_in, sig.data(), nRe * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
-  CH_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * nRe, Re, nRe * sizeof(double), cudaMemcpyHostToDevice, st));
-  CH_CUDA(ctx, cudaMemcpyAsync(d_in + 3 * nRe, alpha0, nRe * sizeof(double), cudaMemcpyHostToDevice, st));
-  CH_CUDA(ctx, launch_chan_neutral(n, c->dD2, c->dD4, c->du, c->dd2u, work, grid, smem, nRe, d_in + 2 * nRe,
-                                   d_in + 3 * nRe, (const double2 *)d_in, sfac, tol, maxit, d_out + 2 * nRe,
-                                   (double2 *)d_out, d_i, d_i + nRe, d_trace, st));
-  ctx_count_launch(ctx, 1);
-  CH_CUDA(ctx, cudaMemcpyAsync(omega, d_out, nRe * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CH_CUDA(ctx, cudaMemcpyAsync(alpha_out, d_out + 2 * nRe, nRe * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CH_CUDA(ctx, cudaMemcpyAsync(steps, d_i, nRe * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  CH_CUDA(ctx, cudaMemcpyAsync(status, d_i + nRe, nRe * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  if (trace) CH_CUDA(ctx, cudaMemcpyAsync(trace, d_trace, (size_t)nRe * maxit * 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
-  CH_CUDA(ctx, cudaStreamSynchronize(st));
+  // the Newton searches are independent: every device of the context takes a contiguous share of the Reynolds numbers
+  rc = for_each_device_share(ctx, nRe, [&](int slot, int64_t lo, int64_t m) -> int {
+    cudaStream_t st = ctx_stream(ctx, slot);
+    const osb_chan::Dev &cd = c->dev[slot];
+    int grid = 0;
+    size_t smem = 0;
+    CH_CUDA(ctx, cudaSetDevice(cd.device));
+    CH_CUDA(ctx, chan_neutral_grid(n, m, &grid, &smem));
+    Scratch scr(cd.device, st, ctx_pool(ctx, slot));
+    double *d_in = nullptr, *d_out = nullptr, *d_trace = nullptr;
+    double2 *work = nullptr;
+    int32_t *d_i = nullptr;
+    CH_CUDA(ctx, scr.alloc(&d_in, m * 4 * sizeof(double)));   // sigma0(2), Re, alpha0
+    CH_CUDA(ctx, scr.alloc(&d_out, m * 3 * sizeof(double)));  // omega(2), alpha
+    CH_CUDA(ctx, scr.alloc(&d_i, m * 2 * sizeof(int32_t)));
+    CH_CUDA(ctx, scr.alloc(&work, (size_t)grid * n * n * sizeof(double2)));
+    if (trace) {
+      CH_CUDA(ctx, scr.alloc(&d_trace, (size_t)m * maxit * 7 * sizeof(double)));
+      CH_CUDA(ctx, cudaMemsetAsync(d_trace, 0, (size_t)m * maxit * 7 * sizeof(double), st));
+    }
+    CH_CUDA(ctx, cudaMemcpyAsync(d_in, sig.data() + 2 * lo, m * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+    CH_CUDA(ctx, cudaMemcpyAsync(d_in + 2 * m, Re + lo, m * sizeof(double), cudaMemcpyHostToDevice, st));
+    CH_CUDA(ctx, cudaMemcpyAsync(d_in + 3 * m, alpha0 + lo, m * sizeof(double), cudaMemcpyHostToDevice, st));
+    CH_CUDA(ctx, launch_chan_neutral(n, cd.dD2, cd.dD4, cd.du, cd.dd2u, work, grid, smem, m, d_in + 2 * m,
+                                     d_in + 3 * m, (const double2 *)d_in, sfac, tol, maxit, d_out + 2 * m,
+                                     (double2 *)d_out, d_i, d_i + m, d_trace, st));
+    ctx_count_launch(ctx, 1);
+    CH_CUDA(ctx, cudaMemcpyAsync(omega + 2 * lo, d_out, m * 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CH_CUDA(ctx, cudaMemcpyAsync(alpha_out + lo, d_out + 2 * m, m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CH_CUDA(ctx, cudaMemcpyAsync(steps + lo, d_i, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CH_CUDA(ctx, cudaMemcpyAsync(status + lo, d_i + m, m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (trace)
+      CH_CUDA(ctx, cudaMemcpyAsync(trace + (size_t)lo * maxit * 7, d_trace, (size_t)m * maxit * 7 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CH_CUDA(ctx, cudaStreamSynchronize(st));
+    return OSB_OK;
+  });
+  if (rc) return rc;
   for (int64_t p = 0; p < nRe; ++p)
     if (!ok[p] && status[p] == OSB_ST_CONVERGED) status[p] = OSB_ST_MAXCOUNT;
   return OSB_OK;

@@ -314,6 +314,64 @@ def test_multi_device_context_matches_single(osb, engine, bl):
         assert np.array_equal(one[k], two[k]), k
 
 
+def test_multi_device_context_shards_every_entry_point(osb, engine, bl):
+    """every batched entry point shards by point / line / profile / Reynolds number over the devices of
+    a multi-device context (cyclic tiles for the shooting sweeps and continuation lines, contiguous shares with one
+    worker thread per device elsewhere; every device holds its own copy of the tables) -- and returns what one
+    device returns, bit for bit."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    eng2 = osb.Engine(devices=[0, 1])
+    same = lambda a, b, keys: [np.testing.assert_array_equal(a[k], b[k], err_msg=k) for k in keys]
+    # spatial continuation lines (orrspace), cyclic tiles of lines
+    fact = math.sqrt(2.0) / 1.7207876
+    ymax = 20.0 * fact
+    so = osb.shoot_defaults(osb.FLOW_ORRSPACE)
+    so.nstep, so.ymin, so.ymax, so.testalpha = 1000, 0.0, ymax, 0.9
+    nl = 301
+    Re = (900.0 + 0.5 * np.arange(nl)) * fact
+    args = (Re, np.full(nl, complex(0.042, 0.0)) * fact, np.full(nl, 0.002) * fact, np.full(nl, complex(0.13809592, 0.0051958399)) * fact, 3)
+    p1 = engine.solve_bl(osb.FLOW_ORRSPACE, osb.INT_RK4, 1000, 0.0, ymax, 0.5, 0.0)
+    p2 = eng2.solve_bl(osb.FLOW_ORRSPACE, osb.INT_RK4, 1000, 0.0, ymax, 0.5, 0.0)
+    same(engine.shoot_spatial_lines(so, p1, *args, hist_cap=3), eng2.shoot_spatial_lines(so, p2, *args, hist_cap=3),
+         ("alpha", "passes", "qend", "status", "history"))
+    p1.free(); p2.free()
+    # eigenfunction pass, chunked over the devices
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    n = 11
+    al = (0.179 + 0.001 * np.arange(n)) * S2
+    Rt = np.full(n, 580.0 * S2)
+    c = engine.shoot_temporal(opts, bl, al, Rt, np.full(n, complex(0.36412287, 0.0079597206)))["c"]
+    q2 = eng2.solve_bl()
+    same(engine.eigfun(opts, bl, Rt, c, alpha=al), eng2.eigfun(opts, q2, Rt, c, alpha=al), ("y", "vmax", "qend"))
+    q2.free()
+    # batched profiles
+    beta = np.linspace(-0.05, 0.3, 37)
+    f2p = 0.47 + 0.9 * beta
+    same(engine.solve_bl_batch(f2p, beta, nbl=400, ymax=12.0), eng2.solve_bl_batch(f2p, beta, nbl=400, ymax=12.0),
+         ("U", "Uspl", "d2U", "d2Uspl", "f2p", "npass"))
+    # matrix path: dense (Chebyshev) and banded (FD) sweeps with and without shifts, adjoints, spectrum, Newton search
+    alpha = np.linspace(0.8, 1.1, 23)
+    for disc, N in ((osb.DISC_CHEB, 64), (osb.DISC_CHEB, 96), (osb.DISC_FD, 128)):
+        c1, c2 = engine.chan(disc, N), eng2.chan(disc, N)
+        r1 = c1.solve(alpha, 1.0e4, want_evec=True, want_adj=osb.ADJ_PENCIL)
+        r2 = c2.solve(alpha, 1.0e4, want_evec=True, want_adj=osb.ADJ_PENCIL)
+        same(r1, r2, ("omega", "iters", "status", "evec", "avec"))
+        g1, g2 = c1.solve(alpha, 1.0e4, sigma0=r1["omega"] * (1 + 1e-4)), c2.solve(alpha, 1.0e4, sigma0=r1["omega"] * (1 + 1e-4))
+        same(g1, g2, ("omega", "iters", "status"))
+        if N <= 96:
+            same(c1.spectrum(alpha[:5], 1.0e4), c2.spectrum(alpha[:5], 1.0e4), ("spectrum", "status"))
+        c1.free(); c2.free()
+    n1, n2 = engine.chan(osb.DISC_CHEB_NUM, 64), eng2.chan(osb.DISC_CHEB_NUM, 64)
+    Rn = 6000.0 * (1.0 + np.arange(9) / 8.0)
+    same(n1.neutral(Rn, 1.0, sfac=0.05, want_trace=True), n2.neutral(Rn, 1.0, sfac=0.05, want_trace=True),
+         ("alpha", "omega", "steps", "status", "trace"))
+    n1.free(); n2.free()
+    eng2.close()
+
+
 def test_blasius_neutral_curve_critical_reynolds(engine, bl):
     """SURVEY 8f item 4 (parity unpinned: the reference has no Blasius neutral curve).  Physical
     check: the critical Reynolds number of the Blasius layer, Re_delta* = 519.4 (R = 301.8)."""
