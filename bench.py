@@ -371,6 +371,29 @@ def secondary_configs(eng, osb, peak_dfma, peak_dmma, hbm_gbs, traffic):
     except Exception as e:  # noqa: BLE001
         out["config5b_orrncbl_neutral"] = {"error": repr(e)}
 
+    # ---- self-seeding sweep driver: config-5 plane from ONE anchor guess (no oracle-made table)
+    try:
+        ng = 1024
+        al = (0.05 + 0.25 * np.arange(ng) / (ng - 1)) * S2
+        Rg = 300.0 * 6.0 ** (np.arange(ng) / (ng - 1)) * S2
+        prof = eng.solve_bl(osb.FLOW_CONTEBL, osb.INT_CK45, 1000, 0.0, 17.0, 0.5, 0.0)
+        opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+        t0 = time.perf_counter()
+        r = eng.shoot_grid_temporal(opts, prof, al, Rg, 0.179 * S2, 580.0 * S2, complex(0.36413124, 0.79527387e-2), want_seed=True)
+        dt = time.perf_counter() - t0
+        prof.free()
+        ok = r["status"] == 0
+        d = np.abs(r["seed"] - r["c"])[ok]
+        out["self_seeding_1024x1024"] = {
+            "workload": "osb_shoot_grid_temporal: 1024 x 1024 points of the config-5 plane from the contebl default guess alone "
+                        "(device-side continuation on a 65 x 65 coarse grid + bilinear seeds + one batched solve), host arrays out",
+            "value": float(ok.sum()) / dt, "unit": UNIT, "seconds": dt, "converged": int(ok.sum()), "points": int(ok.size),
+            "passes_per_point": float(r["passes"][ok].mean()), "coarse_phase": r["info"],
+            "seed_error_fraction_below": {f"{t:g}": float(np.mean(d < t)) for t in (1e-6, 1e-5, 1e-4, 1e-3, 3e-3)},
+            "seed_error_max": float(d.max())}
+    except Exception as e:  # noqa: BLE001
+        out["self_seeding_1024x1024"] = {"error": repr(e)}
+
     # ---- K1 batched: Falkner-Skan profile family
     try:
         nprof, nbl = 16384, 1000

@@ -169,6 +169,25 @@ int osb_shoot_neutral(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profil
                       double *alpha_out, double *c_out, int32_t *steps, int32_t *status);
 
 /*
+ * Self-seeding temporal sweep over a tensor grid (alpha_j, Re_i), j < na, i < nre (both ascending, solver units).
+ * The reference's only seeding scheme is continuation from a guess typed into a deck (contebl.f:75-76; the omega
+ * loop orrspace.f:186-195 hands each converged alpha to the next point), and CONTE_IC only converges from within
+ * ~3e-3 of the root, so a grid sweep needs a seed per point.  This driver needs ONE: the guess anchor_c at
+ * (anchor_alpha, anchor_Re) (e.g. the contebl defaults).  It solves the anchor, then a coarse grid of at most
+ * `coarse` x `coarse` nodes (0 = 65) by batched continuation on the device (linear extrapolation along each
+ * walker's path; failed steps bisected in (alpha, log Re)), interpolates the coarse solutions bilinearly in
+ * (alpha, log Re) to every grid point and solves the whole grid in one batched call (osb_shoot_temporal's kernels).
+ *   c, passes, qend, status [nre*na]   point (i, j) at i*na + j (c interleaved re, im)
+ *   seed  [2*nre*na] optional          the guess each point was started from
+ *   info  [4] optional                 coarse solves, coarse rounds (batched calls), bisections, coarse nodes given up
+ * Temporal flows only.  Points whose iteration does not converge are reported through `status` as always.
+ */
+int osb_shoot_grid_temporal(osb_ctx *ctx, const osb_shoot_opts *opts, const osb_profile *prof, int32_t na,
+                            const double *alpha, int32_t nre, const double *Re, double anchor_alpha,
+                            double anchor_Re, const double *anchor_c, int32_t coarse, double *c,
+                            int32_t *passes, int32_t *qend, int32_t *status, double *seed, int32_t *info);
+
+/*
  * Batched spatial continuation lines (the omega sweep of orrspace.f:186-195):
  * nlines independent lines, each niter points; point i of a line starts from
  * the converged alpha of point i-1 (sequential inside a line, parallel across).

@@ -91,6 +91,7 @@ def load_library(path: os.PathLike | None = None) -> C.CDLL:
         "osb_shoot_temporal_dev": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, i32]),
         "osb_shoot_spatial_lines": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, i32, _dp, _dp, _dp, _dp, _dp, _ip, _ip, _ip, _dp, i32]),
         "osb_shoot_neutral": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, _dp, _dp, _dp, dbl, dbl, i32, _dp, _dp, _ip, _ip]),
+        "osb_shoot_grid_temporal": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i32, _dp, i32, _dp, dbl, dbl, _dp, i32, _dp, _ip, _ip, _ip, _dp, _ip]),
         "osb_eigfun": (C.c_int, [vp, C.POINTER(ShootOpts), vp, i64, _dp, _dp, _dp, _dp, _dp, _dp, _ip]),
         "osb_measure_fp64_peak": (C.c_int, [vp, dbl, _dp, _dp]),
         "osb_measure_dmma_peak": (C.c_int, [vp, dbl, _dp]),
@@ -114,7 +115,7 @@ EXPORTED_SYMBOLS = (
     "osb_version osb_create osb_create_multi osb_destroy osb_device_count osb_last_error osb_stream "
     "osb_launch_count osb_profile_blasius osb_profile_blasius_batch osb_profile_upload "
     "osb_profile_shift osb_profile_channel osb_profile_get osb_profile_nbl osb_profile_free osb_shoot_defaults "
-    "osb_shoot_temporal osb_shoot_temporal_dev osb_shoot_spatial_lines osb_shoot_neutral osb_eigfun osb_measure_fp64_peak osb_measure_dmma_peak "
+    "osb_shoot_temporal osb_shoot_temporal_dev osb_shoot_spatial_lines osb_shoot_neutral osb_shoot_grid_temporal osb_eigfun osb_measure_fp64_peak osb_measure_dmma_peak "
     "osb_chan_create osb_chan_create_bl osb_chan_bl_points osb_chan_free osb_chan_tables osb_chan_eig osb_chan_spectrum osb_chan_neutral"
 ).split()
 
@@ -331,6 +332,32 @@ class Engine:
             float(dalpha_rel), float(tol), int(maxit), alpha.ctypes.data_as(_dp), cout.ctypes.data_as(_dp),
             steps.ctypes.data_as(_ip), status.ctypes.data_as(_ip)))
         return dict(alpha=alpha, c=cout.view(np.complex128), steps=steps, status=status)
+
+    def shoot_grid_temporal(self, opts: ShootOpts, prof: Profile, alpha, Re, anchor_alpha, anchor_Re, anchor_c, coarse=0,
+                            want_seed=False):
+        """Self-seeding sweep over the tensor grid alpha[na] x Re[nre] from one anchor guess (include/osb.h).
+        Returns dict(c[nre, na], passes, qend, status, info[, seed])."""
+        alpha = _f64(alpha)
+        Re = _f64(Re)
+        na, nre = alpha.size, Re.size
+        n = na * nre
+        ac = _cplx_pairs(np.atleast_1d(anchor_c), 1)
+        c = np.zeros(2 * n)
+        passes = np.zeros(n, dtype=np.int32)
+        qend = np.zeros(n, dtype=np.int32)
+        status = np.zeros(n, dtype=np.int32)
+        seed = np.zeros(2 * n) if want_seed else None
+        info = np.zeros(4, dtype=np.int32)
+        self._check(self.lib.osb_shoot_grid_temporal(
+            self.ctx, C.byref(opts), prof.handle, na, alpha.ctypes.data_as(_dp), nre, Re.ctypes.data_as(_dp),
+            float(anchor_alpha), float(anchor_Re), ac.ctypes.data_as(_dp), int(coarse), c.ctypes.data_as(_dp),
+            passes.ctypes.data_as(_ip), qend.ctypes.data_as(_ip), status.ctypes.data_as(_ip),
+            seed.ctypes.data_as(_dp) if want_seed else None, info.ctypes.data_as(_ip)))
+        out = dict(c=c.view(np.complex128).reshape(nre, na), passes=passes.reshape(nre, na), qend=qend.reshape(nre, na),
+                   status=status.reshape(nre, na), info=dict(zip(("coarse_solves", "rounds", "bisections", "given_up"), info.tolist())))
+        if want_seed:
+            out["seed"] = seed.view(np.complex128).reshape(nre, na)
+        return out
 
     def eigfun(self, opts: ShootOpts, prof: Profile, Re, eig, alpha=None, omega=None):
         Re = _f64(Re)

@@ -789,3 +789,40 @@ def test_falkner_skan_profiles_through_the_shooter(engine, osb, oracle, beta, f2
         if ref["status"] == 0:
             assert rel(r["c"][i], ref["c"]) < EIG_RTOL
             assert r["qend"][i] == ref["qend"]
+
+
+def test_self_seeding_grid_sweep(engine, osb, bl):
+    """osb_shoot_grid_temporal: the config-5 (alpha, Re) plane from ONE anchor guess (the contebl defaults), no
+    oracle-made seed table.  257 x 257 points of the grid; the nodes it shares with the committed 65 x 65 table
+    (converged by the CPU oracle's own continuation, tests/golden/make_cfg5_seeds.py) must carry the same
+    eigenvalues to 1e-10, the device-made seeds must sit inside the iteration's basin and
+    the pass counts must be those of a well-seeded sweep."""
+    from pathlib import Path
+
+    seeds = np.load(Path(__file__).resolve().parent.parent / "bench_data" / "cfg5_seeds_65x65.npy")  # [i_Re, j_alpha]
+    n = 257
+    alpha = (0.05 + 0.25 * np.arange(n) / (n - 1)) * S2
+    Re = 300.0 * 6.0 ** (np.arange(n) / (n - 1)) * S2
+    opts = osb.shoot_defaults(osb.FLOW_CONTEBL)
+    r = engine.shoot_grid_temporal(opts, bl, alpha, Re, 0.179 * S2, 580.0 * S2, complex(0.36413124, 0.79527387e-2), want_seed=True)
+    ok = r["status"] == 0
+    print("coarse phase:", r["info"], " converged", ok.mean(), " passes/point", r["passes"][ok].mean())
+    assert r["info"]["given_up"] == 0
+    assert ok.mean() > 0.9995
+    sub = r["c"][::4, ::4]
+    sok = ok[::4, ::4]
+    assert rel(sub[sok], seeds[sok]).max() < 1e-10
+    d = np.abs(r["seed"] - r["c"])[ok]
+    hist = {f"<{t:g}": float(np.mean(d < t)) for t in (1e-6, 1e-5, 1e-4, 1e-3, 3e-3)}
+    print("seed error histogram:", hist, " max", d.max())
+    assert d.max() < 3e-3 and np.mean(d < 1e-4) > 0.9
+    assert r["passes"][ok].mean() < 6.5
+    # degenerate grids: a single point, a single row / column
+    one = engine.shoot_grid_temporal(opts, bl, [0.2 * S2], [600.0 * S2], 0.179 * S2, 580.0 * S2, complex(0.36413124, 0.79527387e-2))
+    assert one["status"][0, 0] == 0
+    ref = engine.shoot_temporal(opts, bl, [0.2 * S2], [600.0 * S2], one["c"][0])
+    assert rel(one["c"][0, 0], ref["c"][0]) < 1e-12
+    row = engine.shoot_grid_temporal(opts, bl, alpha[100:140], [580.0 * S2], 0.179 * S2, 580.0 * S2, complex(0.36413124, 0.79527387e-2), coarse=5)
+    assert (row["status"] == 0).all() and row["c"].shape == (1, 40)
+    col = engine.shoot_grid_temporal(opts, bl, [0.179 * S2], Re[60:90], 0.179 * S2, 580.0 * S2, complex(0.36413124, 0.79527387e-2), coarse=3)
+    assert (col["status"] == 0).all() and col["c"].shape == (30, 1)
