@@ -278,7 +278,7 @@ def secondary_configs(eng, osb, peak_dfma, peak_dmma, hbm_gbs, traffic):
             "workload": "conte channel, 512x512 (alpha,Re) around (1, 1e4), n=2000, CK45, host buffers in/out",
             "value": conv / dt, "unit": UNIT, "converged": conv, "points": int(A.size), "passes_per_point": float(r["passes"].mean()),
             "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_dfma, "unit": "TFLOP/s", "frac": tf / peak_dfma,
-                         "traffic": tr("shoot_queue_kernel", A.size)}}
+                         "traffic": tr("shoot_queue_kernel_conte", A.size)}}
     except Exception as e:  # noqa: BLE001
         out["config2_conte_512x512"] = {"error": repr(e)}
 
