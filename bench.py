@@ -484,6 +484,22 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1])
 
+    def timed_calls(reset, call, steps):
+        """`steps` synchronous host calls, each preceded by an untimed reset of its in/out buffer; wall time of the
+        calls alone, max over ranks"""
+        barrier()
+        tot = 0.0
+        for _ in range(steps):
+            reset()
+            t0 = time.perf_counter()
+            call()
+            tot += time.perf_counter() - t0
+        t = torch.tensor([tot * 1e3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(t[0])
+
     class Leg:
         """One sharding of the workload resident on this rank's GPU + its step functions."""
 
@@ -523,10 +539,13 @@ def main():
                     dist.gather(self.d_c, self.gather_c, dst=0)
                     dist.gather(self.d_int, self.gather_i, dst=0)
 
+        def reset_e2e(self):
+            """c is in/out (guess -> result): restore the guesses; benchmark scaffolding, outside the timed call"""
+            self.h_c.copy_(self.h_guess)
+
         def step_e2e(self):
             """the reference-facing call: HOST buffers in, HOST buffers out"""
             n = self.n
-            self.h_c.copy_(self.h_guess)
             c_np = self.h_c.numpy()
             i_np = self.h_int.numpy()
             eng._check(eng.lib.osb_shoot_temporal(
@@ -591,8 +610,9 @@ def main():
     e2e = None
     if not args.no_e2e:
         e_steps = min(args.steps, 3)
+        leg.reset_e2e()
         leg.step_e2e()
-        _, e_wall = timed(leg.step_e2e, e_steps)  # the host call is synchronous: wall clock is the honest measure
+        e_wall = timed_calls(leg.reset_e2e, leg.step_e2e, e_steps)  # the host call is synchronous: wall clock of the calls
         e2e = {"value": conv_total * e_steps / (e_wall * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": int(n * 40), "d2h_bytes_per_step": int(n * 28), "steps": e_steps,
                "ms_per_step": e_wall / e_steps,
@@ -629,7 +649,6 @@ def main():
                 hp_int = torch.empty(3 * npts, dtype=torch.int32).pin_memory()
 
                 def call():
-                    hp_c.copy_(hp_guess)
                     meng._check(meng.lib.osb_shoot_temporal(
                         meng.ctx, opts, mprof.handle, npts,
                         osb.C.cast(hp_alpha.data_ptr(), osb._dp), osb.C.cast(hp_Re.data_ptr(), osb._dp),
@@ -637,12 +656,16 @@ def main():
                         osb.C.cast(hp_int.data_ptr() + 4 * npts, osb._ip), osb.C.cast(hp_int.data_ptr() + 8 * npts, osb._ip),
                         None, None, 0))
 
+                hp_c.copy_(hp_guess)
                 call()
                 s_steps = min(args.steps, 2)
-                t0 = time.perf_counter()
+                s_wall = 0.0
                 for _ in range(s_steps):
+                    hp_c.copy_(hp_guess)  # restore the guesses (c is in/out); not part of the timed call
+                    t0 = time.perf_counter()
                     call()
-                s_wall = (time.perf_counter() - t0) / s_steps
+                    s_wall += time.perf_counter() - t0
+                s_wall /= s_steps
                 ci = hp_int.numpy().reshape(3, -1)
                 same = (np.array_equal(hp_c.numpy().view(np.int64), full[0].view(np.int64))
                         and np.array_equal(ci, full[1]))
