@@ -304,10 +304,17 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
           for (int rt = 0; rt < 2; ++rt)
 #pragma unroll
             for (int ct = 0; ct < 2; ++ct) {
-              // C -= L U :  Cr += (-Lr) Ur + Li Ui ;  Ci += (-Lr) Ui + (-Li) Ur
+              // C -= L U :  Cr += (-Lr) Ur + Li Ui ;  Ci += (-Lr) Ui + (-Li) Ur.  The two products of an accumulator are issued
+              // eight instructions apart (first halves of all eight accumulators, then the second halves): a dependent DMMA
+              // back to back would stall the warp for the pipe's latency.  Same order per accumulator, same bits.
               dmma884(cr[rt][ct][0], cr[rt][ct][1], -lr[rt], ur[ct]);
-              dmma884(cr[rt][ct][0], cr[rt][ct][1], li[rt], ui[ct]);
               dmma884(ci[rt][ct][0], ci[rt][ct][1], -lr[rt], ui[ct]);
+            }
+#pragma unroll
+          for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) {
+              dmma884(cr[rt][ct][0], cr[rt][ct][1], li[rt], ui[ct]);
               dmma884(ci[rt][ct][0], ci[rt][ct][1], -li[rt], ur[ct]);
             }
         }
@@ -339,6 +346,7 @@ __device__ __forceinline__ void cp_async4(void *dst, const void *src, bool valid
   const int sz = valid ? 4 : 0;
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -408,24 +416,18 @@ __device__ __forceinline__ void lu2_big_update(double2 *__restrict__ M, int n, i
     for (int I = 0; I < nrs; ++I) {
       const int R0 = I * SR;
       double2 *sL = stage + (DB ? (I & 1) * LBUF : 0);
-      // this warp's first tile: its C block is requested before the barrier so that its latency overlaps the wait
+      // one tile per warp (TR * 4 == warps per CTA for both shapes).  The C block of the NEXT row block is requested
+      // into the L2 now (one 128-byte line per lane: 16 columns x 2 halves), a whole super-tile ahead of its use;
+      // holding it in registers across the barrier instead spills at the 128-register budget (ncu: the spill
+      // stores waiting for the loads were 11 % of all stall samples).
       const int tile0 = warp;
       const int tr0 = (tile0 % TR) << 4, tc0 = (tile0 / TR) << 4;
       const bool have0 = tile0 < TR * 4 && R0 + tr0 < MT && C0 + tc0 < MT;
-      double cr[2][2][2], ci[2][2][2];
-      if (have0) {
-#pragma unroll
-        for (int rt = 0; rt < 2; ++rt)
-#pragma unroll
-          for (int ct = 0; ct < 2; ++ct)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int i = R0 + tr0 + 8 * rt + g, j = C0 + tc0 + 8 * ct + 2 * t4 + e;
-              double2 v = make_double2(0.0, 0.0);
-              if (i < MT && j < MT) v = M[(size_t)(KE + j) * n + KE + i];
-              cr[rt][ct][e] = v.x; ci[rt][ct][e] = v.y;
-            }
+      if (tile0 < TR * 4 && I + 1 < nrs) {
+        const int i = R0 + SR + tr0 + 8 * (lane & 1), j = C0 + tc0 + (lane >> 1);
+        if (i < MT && j < MT) prefetch_l2(M + (size_t)(KE + j) * n + KE + i);
       }
+      double cr[2][2][2], ci[2][2][2];
       if (DB) {
         cp_async_wait<0>();
         __syncthreads();  // block I has landed for everybody; everybody is done with block I-1
@@ -435,8 +437,19 @@ __device__ __forceinline__ void lu2_big_update(double2 *__restrict__ M, int n, i
         stage_L(I, sL);
         __syncthreads();
       }
-      if (have0) {  // one tile per warp: TR * 4 == warps per CTA for both shapes
+      if (have0) {
         const int tr = tr0, tc = tc0;
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+          for (int ct = 0; ct < 2; ++ct)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int i = R0 + tr + 8 * rt + g, j = C0 + tc + 8 * ct + 2 * t4 + e;
+              double2 v = make_double2(0.0, 0.0);
+              if (i < MT && j < MT) v = M[(size_t)(KE + j) * n + KE + i];
+              cr[rt][ct][e] = v.x; ci[rt][ct][e] = v.y;
+            }
 #pragma unroll 4
         for (int ks = 0; ks < NBO / 4; ++ks) {
           const int k = 4 * ks + t4;
@@ -455,9 +468,17 @@ __device__ __forceinline__ void lu2_big_update(double2 *__restrict__ M, int n, i
           for (int rt = 0; rt < 2; ++rt)
 #pragma unroll
             for (int ct = 0; ct < 2; ++ct) {
+              // C -= L U :  Cr += (-Lr) Ur + Li Ui ;  Ci += (-Lr) Ui + (-Li) Ur.  The two products of an accumulator are issued
+              // eight instructions apart (first halves of all eight accumulators, then the second halves): a dependent DMMA
+              // back to back would stall the warp for the pipe's latency.  Same order per accumulator, same bits.
               dmma884(cr[rt][ct][0], cr[rt][ct][1], -lr[rt], ur[ct]);
-              dmma884(cr[rt][ct][0], cr[rt][ct][1], li[rt], ui[ct]);
               dmma884(ci[rt][ct][0], ci[rt][ct][1], -lr[rt], ui[ct]);
+            }
+#pragma unroll
+          for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+            for (int ct = 0; ct < 2; ++ct) {
+              dmma884(cr[rt][ct][0], cr[rt][ct][1], li[rt], ui[ct]);
               dmma884(ci[rt][ct][0], ci[rt][ct][1], -li[rt], ur[ct]);
             }
         }
@@ -623,9 +644,17 @@ __device__ __noinline__ void cta_lu2(double2 *__restrict__ M, int n, int *ipiv, 
             for (int rt = 0; rt < 2; ++rt)
 #pragma unroll
               for (int ct = 0; ct < 2; ++ct) {
+                // C -= L U :  Cr += (-Lr) Ur + Li Ui ;  Ci += (-Lr) Ui + (-Li) Ur.  The two products of an accumulator are issued
+                // eight instructions apart (first halves of all eight accumulators, then the second halves): a dependent DMMA
+                // back to back would stall the warp for the pipe's latency.  Same order per accumulator, same bits.
                 dmma884(cr[rt][ct][0], cr[rt][ct][1], -lr[rt], ur[ct]);
-                dmma884(cr[rt][ct][0], cr[rt][ct][1], li[rt], ui[ct]);
                 dmma884(ci[rt][ct][0], ci[rt][ct][1], -lr[rt], ui[ct]);
+              }
+#pragma unroll
+            for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+              for (int ct = 0; ct < 2; ++ct) {
+                dmma884(cr[rt][ct][0], cr[rt][ct][1], li[rt], ui[ct]);
                 dmma884(ci[rt][ct][0], ci[rt][ct][1], -li[rt], ur[ct]);
               }
           }
@@ -716,8 +745,6 @@ __device__ __noinline__ void cta_lu2(double2 *__restrict__ M, int n, int *ipiv, 
 // 16x16 diagonal block is staged in shared memory and solved by one warp with shuffles,
 // then all threads apply the 16 solved values to the remaining rows (coalesced column
 // reads): 2 barriers per block instead of one per column.
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
 __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv, double2 *x) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   __shared__ double2 dblk[16][17];
@@ -725,6 +752,10 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
   // L2) and each block step waits for its 16 columns: the NEXT step's columns are requested into the L2 one step
   // ahead (one prefetch per 128-byte line).
   const bool pf = n > 128;
+  // n >= 300 (the factorisation streams from DRAM): all 16 column entries of a row are requested before the first
+  // one is used -- one memory latency per row instead of one per unrolled group (+4.5 % at N = 384 / 512; below,
+  // with the matrix L2-resident, the extra registers cost more than the latency: -4 % at N = 128 / 256)
+  const bool deep = n >= 300;
   if (tid == 0)
     for (int k = 0; k < n; ++k) {
       const int p = ipiv[k];
@@ -753,11 +784,23 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
       if (lane < nb) x[j0 + lane] = xi;
     }
     __syncthreads();
-    for (int r = j0 + nb + tid; r < n; r += nt) {
-      double2 acc = x[r];
+    if (deep) {
+      for (int r = j0 + nb + tid; r < n; r += nt) {
+        double2 m[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) m[t] = M[(size_t)(j0 + min(t, nb - 1)) * n + r];
+        double2 acc = x[r];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) if (t < nb) acc = cfnma2(acc, m[t], x[j0 + t]);
+        x[r] = acc;
+      }
+    } else {
+      for (int r = j0 + nb + tid; r < n; r += nt) {
+        double2 acc = x[r];
 #pragma unroll 4
-      for (int t = 0; t < nb; ++t) acc = cfnma2(acc, M[(size_t)(j0 + t) * n + r], x[j0 + t]);
-      x[r] = acc;
+        for (int t = 0; t < nb; ++t) acc = cfnma2(acc, M[(size_t)(j0 + t) * n + r], x[j0 + t]);
+        x[r] = acc;
+      }
     }
     __syncthreads();
   }
@@ -787,11 +830,23 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
       if (lane < nb) x[j0 + lane] = xi;
     }
     __syncthreads();
-    for (int r = tid; r < j0; r += nt) {
-      double2 acc = x[r];
+    if (deep) {
+      for (int r = tid; r < j0; r += nt) {
+        double2 m[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) m[t] = M[(size_t)(j0 + min(t, nb - 1)) * n + r];
+        double2 acc = x[r];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) if (t < nb) acc = cfnma2(acc, m[t], x[j0 + t]);
+        x[r] = acc;
+      }
+    } else {
+      for (int r = tid; r < j0; r += nt) {
+        double2 acc = x[r];
 #pragma unroll 4
-      for (int t = 0; t < nb; ++t) acc = cfnma2(acc, M[(size_t)(j0 + t) * n + r], x[j0 + t]);
-      x[r] = acc;
+        for (int t = 0; t < nb; ++t) acc = cfnma2(acc, M[(size_t)(j0 + t) * n + r], x[j0 + t]);
+        x[r] = acc;
+      }
     }
     __syncthreads();
   }
