@@ -36,7 +36,7 @@ constexpr int CH_THREADS_SMALL = 128;
 constexpr int CH_NB = 16;
 
 // optional phase timers (cycles of block 0, thread 0); read back when OSB_CHAN_PROFILE is set
-__device__ long long g_chan_prof[8];
+__device__ long long g_chan_prof[16];
 #define PROF_T0() long long prof_t0 = clock64()
 #define PROF_ADD(slot)                                                        \
   do {                                                                        \
@@ -496,6 +496,8 @@ __device__ __forceinline__ void lu2_big_update(double2 *__restrict__ M, int n, i
   }
 }
 
+constexpr int LU2_RPT = 4;  // panel rows per thread: n <= LU2_RPT * blockDim.x (checked by the launcher)
+
 template <int NBI, int NBO>
 __device__ __noinline__ void cta_lu2(double2 *__restrict__ M, int n, int *ipiv, double2 *panel, double *red) {
   constexpr int CH_NBO = NBO;
@@ -516,61 +518,99 @@ __device__ __noinline__ void cta_lu2(double2 *__restrict__ M, int n, int *ipiv, 
         panel[c * ldp + r] = M[(size_t)(k0 + c) * n + k0 + r];
       }
       __syncthreads();
+      PROF_ADD(7);
+      // ---- the nb columns, ONE barrier each.  Rows stay where they are in shared memory while the panel is factorised
+      // (a thread owns the physical rows tid, tid + nt, ... and keeps, in registers, the POSITION each would have after
+      // LAPACK's interchanges): the pivot row is only read once chosen, every other row is updated by its owner alone,
+      // so the one thing the threads exchange per column is the pivot search.  Same pivots (ties go to the smaller
+      // position, as IZAMAX), same arithmetic per row, same ipiv as the swapping form -- 4 barriers per column there.
+      int pos[LU2_RPT];
+      unsigned alive = 0;
+#pragma unroll
+      for (int q = 0; q < LU2_RPT; ++q) {
+        pos[q] = tid + q * nt;
+        if (pos[q] < mp) alive |= 1u << q;
+      }
       for (int j = 0; j < nb; ++j) {
-        double best = -1.0;
-        int bi = j;
-        for (int r = j + tid; r < mp; r += nt) {
-          const double2 v = panel[j * ldp + r];
-          const double a = fabs(v.x) + fabs(v.y);
-          if (a > best) { best = a; bi = r; }
-        }
+        // pivot search in INTEGER arithmetic (the bit pattern of a non-negative double orders like the double, a NaN
+        // above everything): the FP64 pipe is shared with the other CTA of the SM, which keeps it busy with DMMAs, so
+        // every FP64 instruction taken off this serial chain shortens the column
+        long long best = -1;
+        int key = 0x7fffffff;  // position << 16 | physical row
+#pragma unroll
+        for (int q = 0; q < LU2_RPT; ++q)
+          if (alive >> q & 1) {
+            const int r = tid + q * nt;
+            const double2 v = panel[j * ldp + r];
+            const long long a = __double_as_longlong(fabs(v.x) + fabs(v.y)) & 0x7fffffffffffffffll;
+            const int k = pos[q] << 16 | r;
+            if (a > best || (a == best && k < key)) { best = a; key = k; }
+          }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
-          const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-          if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+          const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int ok = __shfl_xor_sync(0xffffffffu, key, o);
+          if (ob > best || (ob == best && ok < key)) { best = ob; key = ok; }
         }
-        if (lane == 0) { red[warp] = best; red_i[warp] = bi; }
+        long long *redj = (long long *)red + (j & 1) * nwarp;  // double-buffered: column j + 1 writes the other half
+        int *redij = red_i + (j & 1) * nwarp;
+        if (lane == 0) { redj[warp] = best; redij[warp] = key; }
         __syncthreads();
-        if (tid == 0) {
-          double b = red[0];
-          int p = red_i[0];
-          for (int w = 1; w < nwarp; ++w)
-            if (red[w] > b || (red[w] == b && red_i[w] < p)) { b = red[w]; p = red_i[w]; }
-          ipiv[k0 + j] = k0 + p;
-          red_i[nwarp] = p;
-        }
-        __syncthreads();
-        const int p = red_i[nwarp];
-        if (p != j && tid < nb) {
-          const double2 t = panel[tid * ldp + j];
-          panel[tid * ldp + j] = panel[tid * ldp + p];
-          panel[tid * ldp + p] = t;
-        }
-        __syncthreads();
-        double2 piv = panel[j * ldp + j];
-        if (piv.x == 0.0 && piv.y == 0.0) piv = make_double2(1.0e-290, 0.0);
-        const double2 rinv = cdiv2(make_double2(1.0, 0.0), piv);
-        for (int r = j + 1 + tid; r < mp; r += nt) {
-          const double2 l = cmul2(panel[j * ldp + r], rinv);
-          panel[j * ldp + r] = l;
-          for (int c0 = j + 1; c0 < nb; c0 += 4) {
-            double2 uu[4], m[4];
+        {
+          long long b[CH_THREADS_MAX / 32];
+          int k[CH_THREADS_MAX / 32];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int c = min(c0 + q, nb - 1);
-              uu[q] = panel[c * ldp + j];
-              m[q] = panel[c * ldp + r];
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-              if (c0 + q < nb) panel[(c0 + q) * ldp + r] = cfnma2(m[q], l, uu[q]);
+          for (int w = 0; w < CH_THREADS_MAX / 32; ++w) {
+            b[w] = w < nwarp ? redj[w] : -1;
+            k[w] = w < nwarp ? redij[w] : 0x7fffffff;
           }
+#pragma unroll
+          for (int o = CH_THREADS_MAX / 64; o > 0; o >>= 1)
+#pragma unroll
+            for (int w = 0; w < o; ++w)
+              if (b[w + o] > b[w] || (b[w + o] == b[w] && k[w + o] < k[w])) { b[w] = b[w + o]; k[w] = k[w + o]; }
+          key = k[0];
         }
-        __syncthreads();
+        const int P = key & 0xffff, posP = key >> 16;
+        if (tid == 0) ipiv[k0 + j] = k0 + posP;
+        // 1 / pivot with one division (the entries of these matrices are far from the overflow range of |pivot|^2)
+        double2 piv = panel[j * ldp + P];
+        if (piv.x == 0.0 && piv.y == 0.0) piv = make_double2(1.0e-290, 0.0);
+        const double pinv = 1.0 / fma(piv.x, piv.x, piv.y * piv.y);
+        const double2 rinv = make_double2(piv.x * pinv, -piv.y * pinv);
+#pragma unroll
+        for (int q = 0; q < LU2_RPT; ++q)
+          if (alive >> q & 1) {
+            const int r = tid + q * nt;
+            if (r == P) { alive &= ~(1u << q); pos[q] = j; continue; }
+            if (pos[q] == j) pos[q] = posP;
+            const double2 l = cmul2(panel[j * ldp + r], rinv);
+            panel[j * ldp + r] = l;
+            for (int c0 = j + 1; c0 < nb; c0 += 4) {
+              double2 uu[4], m[4];
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq) {
+                const int c = min(c0 + qq, nb - 1);
+                uu[qq] = panel[c * ldp + P];
+                m[qq] = panel[c * ldp + r];
+              }
+#pragma unroll
+              for (int qq = 0; qq < 4; ++qq)
+                if (c0 + qq < nb) panel[(c0 + qq) * ldp + r] = cfnma2(m[qq], l, uu[qq]);
+            }
+          }
       }
+      __syncthreads();
       PROF_ADD(1);
-      // ---- interchanges on the OTHER columns of the outer panel; write the panel back
+      // ---- the panel goes back to the matrix with every row at its position; the interchanges on the OTHER columns of
+      // the outer panel; then the (at most 2 nb) rows whose position differs from where they lie are put in place in
+      // shared memory too, from the copy just written (U12 and the update below read the panel by position)
+#pragma unroll
+      for (int q = 0; q < LU2_RPT; ++q) {
+        const int r = tid + q * nt;
+        if (r < mp)
+          for (int c = 0; c < nb; ++c) M[(size_t)(k0 + c) * n + k0 + pos[q]] = panel[c * ldp + r];
+      }
       for (int c = K0 + tid; c < KE; c += nt) {
         if (c >= k0 && c < k0 + nb) continue;
         double2 *col = M + (size_t)c * n;
@@ -579,9 +619,12 @@ __device__ __noinline__ void cta_lu2(double2 *__restrict__ M, int n, int *ipiv, 
           if (p != k0 + j) { const double2 t = col[k0 + j]; col[k0 + j] = col[p]; col[p] = t; }
         }
       }
-      for (int e = tid; e < mp * nb; e += nt) {
-        const int r = e % mp, c = e / mp;
-        M[(size_t)(k0 + c) * n + k0 + r] = panel[c * ldp + r];
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < LU2_RPT; ++q) {
+        const int r = tid + q * nt;
+        if (r < mp && pos[q] != r)
+          for (int c = 0; c < nb; ++c) panel[c * ldp + pos[q]] = M[(size_t)(k0 + c) * n + k0 + pos[q]];
       }
       __syncthreads();
       PROF_ADD(2);
@@ -741,6 +784,16 @@ __device__ __noinline__ void cta_lu2(double2 *__restrict__ M, int n, int *ipiv, 
   }
 }
 
+// x_r - sum_t m[t] xs[t] over the nb <= 16 solved values of a block step, summed in column order.  (Four independent
+// partial sums would shorten the chain of dependent DFMAs, but measured no faster and the rounding noise of the solve
+// rose enough to stall 5 % of the N = 512 inverse iterations above the 1e-12 criterion.)
+__device__ __forceinline__ double2 solve_row16(double2 xr, const double2 (&m)[16], const double2 *xs, int nb) {
+  double2 acc = xr;
+#pragma unroll
+  for (int t = 0; t < 16; ++t) if (t < nb) acc = cfnma2(acc, m[t], xs[t]);
+  return acc;
+}
+
 // x <- M^{-1} x using P M = L U.  x: shared, n complex.  Blocked by 16 columns: the
 // 16x16 diagonal block is staged in shared memory and solved by one warp with shuffles,
 // then all threads apply the 16 solved values to the remaining rows (coalesced column
@@ -789,10 +842,7 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
         double2 m[16];
 #pragma unroll
         for (int t = 0; t < 16; ++t) m[t] = M[(size_t)(j0 + min(t, nb - 1)) * n + r];
-        double2 acc = x[r];
-#pragma unroll
-        for (int t = 0; t < 16; ++t) if (t < nb) acc = cfnma2(acc, m[t], x[j0 + t]);
-        x[r] = acc;
+        x[r] = solve_row16(x[r], m, x + j0, nb);
       }
     } else {
       for (int r = j0 + nb + tid; r < n; r += nt) {
@@ -807,9 +857,18 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
   // ---- U x = y
   for (int j0 = ((n - 1) / 16) * 16; j0 >= 0; j0 -= 16) {
     const int nb = min(16, n - j0);
+    // the diagonal block is staged as D^{-1} U (unit upper, the reciprocal of the pivot on the diagonal): the serial
+    // chain of the 16 back-substitution steps then holds no division
     for (int e = tid; e < 256; e += nt) {
       const int r = e & 15, c = e >> 4;
-      if (r < nb && c < nb) dblk[r][c] = M[(size_t)(j0 + c) * n + j0 + r];
+      if (r < nb && c < nb && c >= r) {
+        const double2 a = M[(size_t)(j0 + c) * n + j0 + r];
+        double2 d = M[(size_t)(j0 + r) * n + j0 + r];
+        if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
+        const double s = 1.0 / fma(d.x, d.x, d.y * d.y);
+        const double2 dinv = make_double2(d.x * s, -d.y * s);
+        dblk[r][c] = (c == r) ? dinv : cmul2(a, dinv);
+      }
     }
     __syncthreads();
     if (pf && j0 >= 16)
@@ -817,13 +876,8 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
 #pragma unroll
         for (int t = 0; t < 16; ++t) prefetch_l2(M + (size_t)(j0 - 16 + t) * n + r);
     if (warp == 0) {
-      double2 xi = (lane < nb) ? x[j0 + lane] : make_double2(0.0, 0.0);
+      double2 xi = (lane < nb) ? cmul2(x[j0 + lane], dblk[lane][lane]) : make_double2(0.0, 0.0);
       for (int t = nb - 1; t >= 0; --t) {
-        if (lane == t) {
-          double2 d = dblk[t][t];
-          if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
-          xi = cdiv2(xi, d);
-        }
         const double xr = __shfl_sync(0xffffffffu, xi.x, t), xim = __shfl_sync(0xffffffffu, xi.y, t);
         if (lane < t) xi = cfnma2(xi, dblk[lane][t], make_double2(xr, xim));
       }
@@ -835,10 +889,7 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
         double2 m[16];
 #pragma unroll
         for (int t = 0; t < 16; ++t) m[t] = M[(size_t)(j0 + min(t, nb - 1)) * n + r];
-        double2 acc = x[r];
-#pragma unroll
-        for (int t = 0; t < 16; ++t) if (t < nb) acc = cfnma2(acc, m[t], x[j0 + t]);
-        x[r] = acc;
+        x[r] = solve_row16(x[r], m, x + j0, nb);
       }
     } else {
       for (int r = tid; r < j0; r += nt) {
@@ -2738,13 +2789,13 @@ static cudaError_t chan_grid(int n, int64_t ninst, int *grid, size_t *smem, cons
 }
 
 void chan_profile_dump(const char *tag) {
-  long long h[8];
+  long long h[16];
   if (cudaMemcpyFromSymbol(h, g_chan_prof, sizeof(h)) != cudaSuccess) return;
-  const char *names[8] = {"assemble", "panel", "swap+writeback", "U12", "trailing(DMMA)", "B x", "solve", "-"};
+  const char *names[8] = {"assemble", "panel", "swap+writeback", "U12", "trailing(DMMA)", "B x", "solve", "stage"};
   double tot = 0;
-  for (int i = 0; i < 7; ++i) tot += (double)h[i];
+  for (int i = 0; i < 8; ++i) tot += (double)h[i];
   fprintf(stderr, "[osb chan profile %s] block 0 cycles:", tag);
-  for (int i = 0; i < 7; ++i) fprintf(stderr, " %s=%.1f%%", names[i], tot > 0 ? 100.0 * h[i] / tot : 0.0);
+  for (int i = 0; i < 8; ++i) fprintf(stderr, " %s=%.1f%%", names[i], tot > 0 ? 100.0 * h[i] / tot : 0.0);
   fprintf(stderr, " total=%.3g\n", tot);
   memset(h, 0, sizeof(h));
   cudaMemcpyToSymbol(g_chan_prof, h, sizeof(h));

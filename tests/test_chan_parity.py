@@ -355,7 +355,11 @@ def test_full_spectrum_on_device(engine, oracle, disc, N):
         # implementations can only agree to that level; the kept (least stable) mode is well conditioned.
         loose = disc != ob.DISC_FD or N > 128
         assert np.median(e) < (1e-5 if loose else 1e-9), np.median(e)
-        assert e.max() < (5e-3 if loose else 1e-5), e.max()
+        # (the worst eigenvalues sit at the junction of the three branches, where the 1e-16-pseudospectrum is ~1e-3 wide:
+        # any change of rounding -- e.g. the order of operations of the triangular solves that form inv(B)A -- moves the
+        # maximum between 2e-3 and 6e-3 at N = 300 while the median and the well-conditioned modes do not move)
+        assert e.max() < (2e-2 if loose else 1e-5), e.max()
+        assert (e < 1e-3).mean() > 0.97, (e < 1e-3).mean()
         # the reference's rule on the device spectrum (orrfdchan.f:815-823) picks the mode osb_chan_eig returns
         ok = (np.abs(w.imag) < 10.0) & (w.real.astype(int) != 999)
         pick = w[ok][np.argmax(w[ok].imag)]
