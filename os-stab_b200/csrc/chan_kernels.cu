@@ -146,6 +146,120 @@ __device__ void assemble_shifted(double2 *__restrict__ M, int n, const double *_
   __syncthreads();
 }
 
+constexpr int LU_RPT = 4;  // panel rows per thread: n <= LU_RPT * blockDim.x (every launcher satisfies it)
+
+// The nb columns of a staged panel, ONE barrier each.  Rows stay where they are in shared memory while the panel is factorised
+// (a thread owns the physical rows tid, tid + nt, ... and keeps, in registers, the POSITION each would have after
+// LAPACK's interchanges): the pivot row is only read once chosen, every other row is updated by its owner alone,
+// so the one thing the threads exchange per column is the pivot search.  Same pivots (ties go to the smaller
+// position, as IZAMAX), same arithmetic per row, same ipiv as the swapping form -- 4 barriers per column there.
+__device__ __forceinline__ void lu_panel_columns(double2 *panel, int ldp, int mp, int nb, int k0, int *ipiv, double *red,
+                                                 int (&pos)[LU_RPT]) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
+  int *red_i = (int *)(red + 2 * (CH_THREADS_MAX / 32));
+  unsigned alive = 0;
+#pragma unroll
+  for (int q = 0; q < LU_RPT; ++q) {
+    pos[q] = tid + q * nt;
+    if (pos[q] < mp) alive |= 1u << q;
+  }
+  for (int j = 0; j < nb; ++j) {
+    // pivot search in INTEGER arithmetic (the bit pattern of a non-negative double orders like the double, a NaN
+    // above everything): the FP64 pipe is shared with the other CTA of the SM, which keeps it busy with DMMAs, so
+    // every FP64 instruction taken off this serial chain shortens the column
+    long long best = -1;
+    int key = 0x7fffffff;  // position << 16 | physical row
+#pragma unroll
+    for (int q = 0; q < LU_RPT; ++q)
+      if (alive >> q & 1) {
+        const int r = tid + q * nt;
+        const double2 v = panel[j * ldp + r];
+        const long long a = __double_as_longlong(fabs(v.x) + fabs(v.y)) & 0x7fffffffffffffffll;
+        const int k = pos[q] << 16 | r;
+        if (a > best || (a == best && k < key)) { best = a; key = k; }
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int ok = __shfl_xor_sync(0xffffffffu, key, o);
+      if (ob > best || (ob == best && ok < key)) { best = ob; key = ok; }
+    }
+    long long *redj = (long long *)red + (j & 1) * nwarp;  // double-buffered: column j + 1 writes the other half
+    int *redij = red_i + (j & 1) * nwarp;
+    if (lane == 0) { redj[warp] = best; redij[warp] = key; }
+    __syncthreads();
+    {
+      long long b[CH_THREADS_MAX / 32];
+      int k[CH_THREADS_MAX / 32];
+#pragma unroll
+      for (int w = 0; w < CH_THREADS_MAX / 32; ++w) {
+        b[w] = w < nwarp ? redj[w] : -1;
+        k[w] = w < nwarp ? redij[w] : 0x7fffffff;
+      }
+#pragma unroll
+      for (int o = CH_THREADS_MAX / 64; o > 0; o >>= 1)
+#pragma unroll
+        for (int w = 0; w < o; ++w)
+          if (b[w + o] > b[w] || (b[w + o] == b[w] && k[w + o] < k[w])) { b[w] = b[w + o]; k[w] = k[w + o]; }
+      key = k[0];
+    }
+    const int P = key & 0xffff, posP = key >> 16;
+    if (tid == 0) ipiv[k0 + j] = k0 + posP;
+    // 1 / pivot with one division (the entries of these matrices are far from the overflow range of |pivot|^2)
+    double2 piv = panel[j * ldp + P];
+    if (piv.x == 0.0 && piv.y == 0.0) piv = make_double2(1.0e-290, 0.0);
+    const double pinv = 1.0 / fma(piv.x, piv.x, piv.y * piv.y);
+    const double2 rinv = make_double2(piv.x * pinv, -piv.y * pinv);
+#pragma unroll
+    for (int q = 0; q < LU_RPT; ++q)
+      if (alive >> q & 1) {
+        const int r = tid + q * nt;
+        if (r == P) { alive &= ~(1u << q); pos[q] = j; continue; }
+        if (pos[q] == j) pos[q] = posP;
+        const double2 l = cmul2(panel[j * ldp + r], rinv);
+        panel[j * ldp + r] = l;
+        for (int c0 = j + 1; c0 < nb; c0 += 4) {
+          double2 uu[4], m[4];
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const int c = min(c0 + qq, nb - 1);
+            uu[qq] = panel[c * ldp + P];
+            m[qq] = panel[c * ldp + r];
+          }
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq)
+            if (c0 + qq < nb) panel[(c0 + qq) * ldp + r] = cfnma2(m[qq], l, uu[qq]);
+        }
+      }
+  }
+  __syncthreads();
+}
+
+// The factorised panel goes back to the matrix with every row at its position ...
+__device__ __forceinline__ void lu_panel_store(double2 *__restrict__ M, int n, int k0, int nb, int mp, const double2 *panel,
+                                               int ldp, const int (&pos)[LU_RPT]) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+#pragma unroll
+  for (int q = 0; q < LU_RPT; ++q) {
+    const int r = tid + q * nt;
+    if (r < mp)
+      for (int c = 0; c < nb; ++c) M[(size_t)(k0 + c) * n + k0 + pos[q]] = panel[c * ldp + r];
+  }
+}
+// ... and, after a barrier, the (at most 2 nb) rows whose position differs from where they lie are put in place in
+// shared memory too, from the copy just written (U12 and the trailing update read the panel by position)
+__device__ __forceinline__ void lu_panel_settle(const double2 *__restrict__ M, int n, int k0, int nb, int mp, double2 *panel,
+                                                int ldp, const int (&pos)[LU_RPT]) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+#pragma unroll
+  for (int q = 0; q < LU_RPT; ++q) {
+    const int r = tid + q * nt;
+    if (r < mp && pos[q] != r)
+      for (int c = 0; c < nb; ++c) panel[c * ldp + pos[q]] = M[(size_t)(k0 + c) * n + k0 + pos[q]];
+  }
+  __syncthreads();
+}
+
 // ---------------------------------------------------------------------------
 // K4: blocked LU, P M = L U in place.  panel: shared, (n + 16) x CH_NB complex.
 // ---------------------------------------------------------------------------
@@ -163,64 +277,9 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
       panel[c * ldp + r] = M[(size_t)(k0 + c) * n + k0 + r];
     }
     __syncthreads();
-    // ---- unblocked factorisation inside the panel (ZGETF2)
-    for (int j = 0; j < nb; ++j) {
-      double best = -1.0;
-      int bi = j;
-      for (int r = j + tid; r < mp; r += nt) {
-        const double2 v = panel[j * ldp + r];
-        const double a = fabs(v.x) + fabs(v.y);
-        if (a > best) { best = a; bi = r; }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-      }
-      if (lane == 0) { red[warp] = best; red_i[warp] = bi; }
-      __syncthreads();
-      if (tid == 0) {
-        double b = red[0];
-        int p = red_i[0];
-        for (int w = 1; w < nwarp; ++w)
-          if (red[w] > b || (red[w] == b && red_i[w] < p)) { b = red[w]; p = red_i[w]; }
-        ipiv[k0 + j] = k0 + p;
-        red_i[nwarp] = p;
-      }
-      __syncthreads();
-      const int p = red_i[nwarp];
-      if (p != j && tid < nb) {
-        const double2 t = panel[tid * ldp + j];
-        panel[tid * ldp + j] = panel[tid * ldp + p];
-        panel[tid * ldp + p] = t;
-      }
-      __syncthreads();
-      double2 piv = panel[j * ldp + j];
-      // an exactly singular pivot only happens when sigma hits an eigenvalue to the last
-      // bit; inverse iteration wants the huge solve, not a NaN
-      if (piv.x == 0.0 && piv.y == 0.0) piv = make_double2(1.0e-290, 0.0);
-      const double2 rinv = cdiv2(make_double2(1.0, 0.0), piv);
-      for (int r = j + 1 + tid; r < mp; r += nt) {
-        const double2 l = cmul2(panel[j * ldp + r], rinv);
-        panel[j * ldp + r] = l;
-        // chunks of 4 columns with the loads issued before the stores: the compiler cannot prove
-        // that the pivot-row loads do not alias the row being written and would serialise the loop
-        for (int c0 = j + 1; c0 < nb; c0 += 4) {
-          double2 uu[4], m[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int c = min(c0 + q, nb - 1);
-            uu[q] = panel[c * ldp + j];
-            m[q] = panel[c * ldp + r];
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (c0 + q < nb) panel[(c0 + q) * ldp + r] = cfnma2(m[q], l, uu[q]);
-        }
-      }
-      __syncthreads();
-    }
+    // ---- unblocked factorisation inside the panel (ZGETF2's pivots and arithmetic, rows left in place)
+    int pos[LU_RPT];
+    lu_panel_columns(panel, ldp, mp, nb, k0, ipiv, red, pos);
     PROF_ADD(1);
     // ---- row interchanges on the columns outside the panel; write the panel back
     // two columns per thread, interleaved: two independent chains of dependent swaps in flight
@@ -239,11 +298,9 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
         }
       }
     }
-    for (int e = tid; e < mp * nb; e += nt) {
-      const int r = e % mp, c = e / mp;
-      M[(size_t)(k0 + c) * n + k0 + r] = panel[c * ldp + r];
-    }
+    lu_panel_store(M, n, k0, nb, mp, panel, ldp, pos);
     __syncthreads();
+    lu_panel_settle(M, n, k0, nb, mp, panel, ldp, pos);
     PROF_ADD(2);
     const int mt = n - k0 - nb;  // trailing size
     if (mt <= 0) break;
@@ -496,8 +553,6 @@ __device__ __forceinline__ void lu2_big_update(double2 *__restrict__ M, int n, i
   }
 }
 
-constexpr int LU2_RPT = 4;  // panel rows per thread: n <= LU2_RPT * blockDim.x (checked by the launcher)
-
 template <int NBI, int NBO>
 __device__ __noinline__ void cta_lu2(double2 *__restrict__ M, int n, int *ipiv, double2 *panel, double *red) {
   constexpr int CH_NBO = NBO;
@@ -519,98 +574,11 @@ __device__ __noinline__ void cta_lu2(double2 *__restrict__ M, int n, int *ipiv, 
       }
       __syncthreads();
       PROF_ADD(7);
-      // ---- the nb columns, ONE barrier each.  Rows stay where they are in shared memory while the panel is factorised
-      // (a thread owns the physical rows tid, tid + nt, ... and keeps, in registers, the POSITION each would have after
-      // LAPACK's interchanges): the pivot row is only read once chosen, every other row is updated by its owner alone,
-      // so the one thing the threads exchange per column is the pivot search.  Same pivots (ties go to the smaller
-      // position, as IZAMAX), same arithmetic per row, same ipiv as the swapping form -- 4 barriers per column there.
-      int pos[LU2_RPT];
-      unsigned alive = 0;
-#pragma unroll
-      for (int q = 0; q < LU2_RPT; ++q) {
-        pos[q] = tid + q * nt;
-        if (pos[q] < mp) alive |= 1u << q;
-      }
-      for (int j = 0; j < nb; ++j) {
-        // pivot search in INTEGER arithmetic (the bit pattern of a non-negative double orders like the double, a NaN
-        // above everything): the FP64 pipe is shared with the other CTA of the SM, which keeps it busy with DMMAs, so
-        // every FP64 instruction taken off this serial chain shortens the column
-        long long best = -1;
-        int key = 0x7fffffff;  // position << 16 | physical row
-#pragma unroll
-        for (int q = 0; q < LU2_RPT; ++q)
-          if (alive >> q & 1) {
-            const int r = tid + q * nt;
-            const double2 v = panel[j * ldp + r];
-            const long long a = __double_as_longlong(fabs(v.x) + fabs(v.y)) & 0x7fffffffffffffffll;
-            const int k = pos[q] << 16 | r;
-            if (a > best || (a == best && k < key)) { best = a; key = k; }
-          }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
-          const int ok = __shfl_xor_sync(0xffffffffu, key, o);
-          if (ob > best || (ob == best && ok < key)) { best = ob; key = ok; }
-        }
-        long long *redj = (long long *)red + (j & 1) * nwarp;  // double-buffered: column j + 1 writes the other half
-        int *redij = red_i + (j & 1) * nwarp;
-        if (lane == 0) { redj[warp] = best; redij[warp] = key; }
-        __syncthreads();
-        {
-          long long b[CH_THREADS_MAX / 32];
-          int k[CH_THREADS_MAX / 32];
-#pragma unroll
-          for (int w = 0; w < CH_THREADS_MAX / 32; ++w) {
-            b[w] = w < nwarp ? redj[w] : -1;
-            k[w] = w < nwarp ? redij[w] : 0x7fffffff;
-          }
-#pragma unroll
-          for (int o = CH_THREADS_MAX / 64; o > 0; o >>= 1)
-#pragma unroll
-            for (int w = 0; w < o; ++w)
-              if (b[w + o] > b[w] || (b[w + o] == b[w] && k[w + o] < k[w])) { b[w] = b[w + o]; k[w] = k[w + o]; }
-          key = k[0];
-        }
-        const int P = key & 0xffff, posP = key >> 16;
-        if (tid == 0) ipiv[k0 + j] = k0 + posP;
-        // 1 / pivot with one division (the entries of these matrices are far from the overflow range of |pivot|^2)
-        double2 piv = panel[j * ldp + P];
-        if (piv.x == 0.0 && piv.y == 0.0) piv = make_double2(1.0e-290, 0.0);
-        const double pinv = 1.0 / fma(piv.x, piv.x, piv.y * piv.y);
-        const double2 rinv = make_double2(piv.x * pinv, -piv.y * pinv);
-#pragma unroll
-        for (int q = 0; q < LU2_RPT; ++q)
-          if (alive >> q & 1) {
-            const int r = tid + q * nt;
-            if (r == P) { alive &= ~(1u << q); pos[q] = j; continue; }
-            if (pos[q] == j) pos[q] = posP;
-            const double2 l = cmul2(panel[j * ldp + r], rinv);
-            panel[j * ldp + r] = l;
-            for (int c0 = j + 1; c0 < nb; c0 += 4) {
-              double2 uu[4], m[4];
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq) {
-                const int c = min(c0 + qq, nb - 1);
-                uu[qq] = panel[c * ldp + P];
-                m[qq] = panel[c * ldp + r];
-              }
-#pragma unroll
-              for (int qq = 0; qq < 4; ++qq)
-                if (c0 + qq < nb) panel[(c0 + qq) * ldp + r] = cfnma2(m[qq], l, uu[qq]);
-            }
-          }
-      }
-      __syncthreads();
+      int pos[LU_RPT];
+      lu_panel_columns(panel, ldp, mp, nb, k0, ipiv, red, pos);
       PROF_ADD(1);
-      // ---- the panel goes back to the matrix with every row at its position; the interchanges on the OTHER columns of
-      // the outer panel; then the (at most 2 nb) rows whose position differs from where they lie are put in place in
-      // shared memory too, from the copy just written (U12 and the update below read the panel by position)
-#pragma unroll
-      for (int q = 0; q < LU2_RPT; ++q) {
-        const int r = tid + q * nt;
-        if (r < mp)
-          for (int c = 0; c < nb; ++c) M[(size_t)(k0 + c) * n + k0 + pos[q]] = panel[c * ldp + r];
-      }
+      // ---- write the panel back (rows by position); the interchanges on the OTHER columns of the outer panel
+      lu_panel_store(M, n, k0, nb, mp, panel, ldp, pos);
       for (int c = K0 + tid; c < KE; c += nt) {
         if (c >= k0 && c < k0 + nb) continue;
         double2 *col = M + (size_t)c * n;
@@ -620,13 +588,7 @@ __device__ __noinline__ void cta_lu2(double2 *__restrict__ M, int n, int *ipiv, 
         }
       }
       __syncthreads();
-#pragma unroll
-      for (int q = 0; q < LU2_RPT; ++q) {
-        const int r = tid + q * nt;
-        if (r < mp && pos[q] != r)
-          for (int c = 0; c < nb; ++c) panel[c * ldp + pos[q]] = M[(size_t)(k0 + c) * n + k0 + pos[q]];
-      }
-      __syncthreads();
+      lu_panel_settle(M, n, k0, nb, mp, panel, ldp, pos);
       PROF_ADD(2);
       const int nc = KE - k0 - nb;     // columns of the outer panel to the right of this panel
       const int mt = n - k0 - nb;      // rows below it
