@@ -762,7 +762,8 @@ __device__ __forceinline__ double2 solve_row16(double2 xr, const double2 (&m)[16
 // reads): 2 barriers per block instead of one per column.
 __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv, double2 *x) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  __shared__ double2 dblk[16][17];
+  // two buffers: the diagonal block of the NEXT step is fetched while the rows below are updated with this one
+  __shared__ double2 dblk[2][16][17];
   // Large matrices are streamed from DRAM by every solve (hundreds of concurrent 4 MB factorisations do not fit the
   // L2) and each block step waits for its 16 columns: the NEXT step's columns are requested into the L2 one step
   // ahead (one prefetch per 128-byte line).
@@ -776,35 +777,52 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
       const int p = ipiv[k];
       if (p != k) { const double2 t = x[k]; x[k] = x[p]; x[p] = t; }
     }
-  __syncthreads();
   // ---- L y = P b (unit lower)
-  for (int j0 = 0; j0 < n; j0 += 16) {
+  for (int e = tid; e < 256; e += nt) {
+    const int r = e & 15, c = e >> 4;
+    if (r < n && c < n) dblk[0][r][c] = M[(size_t)c * n + r];
+  }
+  __syncthreads();
+  int buf = 0;
+  for (int j0 = 0; j0 < n; j0 += 16, buf ^= 1) {
     const int nb = min(16, n - j0);
-    for (int e = tid; e < 256; e += nt) {
-      const int r = e & 15, c = e >> 4;
-      if (r < nb && c < nb) dblk[r][c] = M[(size_t)(j0 + c) * n + j0 + r];
-    }
-    __syncthreads();
-    if (pf && j0 + 16 < n)
-      for (int r = j0 + 16 + 8 * tid; r < n; r += 8 * nt)
-#pragma unroll
-        for (int t = 0; t < 16; ++t)
-          if (j0 + 16 + t < n) prefetch_l2(M + (size_t)(j0 + 16 + t) * n + r);
     if (warp == 0) {
       double2 xi = (lane < nb) ? x[j0 + lane] : make_double2(0.0, 0.0);
       for (int t = 0; t < nb; ++t) {
         const double xr = __shfl_sync(0xffffffffu, xi.x, t), xim = __shfl_sync(0xffffffffu, xi.y, t);
-        if (lane > t && lane < nb) xi = cfnma2(xi, dblk[lane][t], make_double2(xr, xim));
+        if (lane > t && lane < nb) xi = cfnma2(xi, dblk[buf][lane][t], make_double2(xr, xim));
       }
       if (lane < nb) x[j0 + lane] = xi;
+    } else if (pf && j0 + 16 < n) {
+      // (the warps that wait for the diagonal block request the columns of the next step into the L2)
+      for (int r = j0 + 16 + 8 * (tid - 32); r < n; r += 8 * (nt - 32))
+#pragma unroll
+        for (int t = 0; t < 16; ++t)
+          if (j0 + 16 + t < n) prefetch_l2(M + (size_t)(j0 + 16 + t) * n + r);
     }
     __syncthreads();
+    // next diagonal block: loads issued here, stored after the update
+    const int jn = j0 + 16, nbn = min(16, n - jn);
+    double2 dn[2];
+    if (!deep) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int e = tid + q * nt, r = e & 15, c = e >> 4;
+        dn[q] = (e < 256 && r < nbn && c < nbn) ? M[(size_t)(jn + c) * n + jn + r] : make_double2(0.0, 0.0);
+      }
+    }
     if (deep) {
       for (int r = j0 + nb + tid; r < n; r += nt) {
         double2 m[16];
 #pragma unroll
         for (int t = 0; t < 16; ++t) m[t] = M[(size_t)(j0 + min(t, nb - 1)) * n + r];
         x[r] = solve_row16(x[r], m, x + j0, nb);
+      }
+      // (16 row entries in registers: the block is fetched afterwards, from the L2 it was prefetched into)
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int e = tid + q * nt, r = e & 15, c = e >> 4;
+        dn[q] = (e < 256 && r < nbn && c < nbn) ? M[(size_t)(jn + c) * n + jn + r] : make_double2(0.0, 0.0);
       }
     } else {
       for (int r = j0 + nb + tid; r < n; r += nt) {
@@ -813,39 +831,57 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
         for (int t = 0; t < nb; ++t) acc = cfnma2(acc, M[(size_t)(j0 + t) * n + r], x[j0 + t]);
         x[r] = acc;
       }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = tid + q * nt, r = e & 15, c = e >> 4;
+      if (e < 256) dblk[buf ^ 1][r][c] = dn[q];
     }
     __syncthreads();
   }
-  // ---- U x = y
-  for (int j0 = ((n - 1) / 16) * 16; j0 >= 0; j0 -= 16) {
+  // ---- U x = y.  The diagonal block is staged as D^{-1} U (unit upper, the reciprocal of the pivot on the diagonal):
+  // the serial chain of the 16 back-substitution steps then holds no division
+  auto load_u = [&](int j0, int e, double2 &a, double2 &d) {
+    const int nb = min(16, n - j0), r = e & 15, c = e >> 4;
+    const bool in = j0 >= 0 && e < 256 && r < nb && c < nb && c >= r;
+    a = in ? M[(size_t)(j0 + c) * n + j0 + r] : make_double2(0.0, 0.0);
+    d = in ? M[(size_t)(j0 + r) * n + j0 + r] : make_double2(1.0, 0.0);
+  };
+  auto scaled_u = [&](int e, double2 a, double2 d) {
+    const int r = e & 15, c = e >> 4;
+    if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
+    const double s = 1.0 / fma(d.x, d.x, d.y * d.y);
+    const double2 dinv = make_double2(d.x * s, -d.y * s);
+    return (c == r) ? dinv : cmul2(a, dinv);
+  };
+  const int jlast = ((n - 1) / 16) * 16;
+  for (int q = 0; q < 2; ++q) {
+    const int e = tid + q * nt;
+    double2 a, d;
+    load_u(jlast, e, a, d);
+    if (e < 256) dblk[buf][e & 15][e >> 4] = scaled_u(e, a, d);
+  }
+  __syncthreads();
+  for (int j0 = jlast; j0 >= 0; j0 -= 16, buf ^= 1) {
     const int nb = min(16, n - j0);
-    // the diagonal block is staged as D^{-1} U (unit upper, the reciprocal of the pivot on the diagonal): the serial
-    // chain of the 16 back-substitution steps then holds no division
-    for (int e = tid; e < 256; e += nt) {
-      const int r = e & 15, c = e >> 4;
-      if (r < nb && c < nb && c >= r) {
-        const double2 a = M[(size_t)(j0 + c) * n + j0 + r];
-        double2 d = M[(size_t)(j0 + r) * n + j0 + r];
-        if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
-        const double s = 1.0 / fma(d.x, d.x, d.y * d.y);
-        const double2 dinv = make_double2(d.x * s, -d.y * s);
-        dblk[r][c] = (c == r) ? dinv : cmul2(a, dinv);
-      }
-    }
-    __syncthreads();
-    if (pf && j0 >= 16)
-      for (int r = 8 * tid; r < j0; r += 8 * nt)
-#pragma unroll
-        for (int t = 0; t < 16; ++t) prefetch_l2(M + (size_t)(j0 - 16 + t) * n + r);
     if (warp == 0) {
-      double2 xi = (lane < nb) ? cmul2(x[j0 + lane], dblk[lane][lane]) : make_double2(0.0, 0.0);
+      double2 xi = (lane < nb) ? cmul2(x[j0 + lane], dblk[buf][lane][lane]) : make_double2(0.0, 0.0);
       for (int t = nb - 1; t >= 0; --t) {
         const double xr = __shfl_sync(0xffffffffu, xi.x, t), xim = __shfl_sync(0xffffffffu, xi.y, t);
-        if (lane < t) xi = cfnma2(xi, dblk[lane][t], make_double2(xr, xim));
+        if (lane < t) xi = cfnma2(xi, dblk[buf][lane][t], make_double2(xr, xim));
       }
       if (lane < nb) x[j0 + lane] = xi;
+    } else if (pf && j0 >= 16) {
+      for (int r = 8 * (tid - 32); r < j0; r += 8 * (nt - 32))
+#pragma unroll
+        for (int t = 0; t < 16; ++t) prefetch_l2(M + (size_t)(j0 - 16 + t) * n + r);
     }
     __syncthreads();
+    double2 an[2], dn[2];
+    if (!deep) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) load_u(j0 - 16, tid + q * nt, an[q], dn[q]);
+    }
     if (deep) {
       for (int r = tid; r < j0; r += nt) {
         double2 m[16];
@@ -853,6 +889,8 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
         for (int t = 0; t < 16; ++t) m[t] = M[(size_t)(j0 + min(t, nb - 1)) * n + r];
         x[r] = solve_row16(x[r], m, x + j0, nb);
       }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) load_u(j0 - 16, tid + q * nt, an[q], dn[q]);
     } else {
       for (int r = tid; r < j0; r += nt) {
         double2 acc = x[r];
@@ -860,6 +898,11 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
         for (int t = 0; t < nb; ++t) acc = cfnma2(acc, M[(size_t)(j0 + t) * n + r], x[j0 + t]);
         x[r] = acc;
       }
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = tid + q * nt;
+      if (e < 256) dblk[buf ^ 1][e & 15][e >> 4] = scaled_u(e, an[q], dn[q]);
     }
     __syncthreads();
   }
@@ -1086,23 +1129,27 @@ struct ChanArgs {
 
 // index of the component of largest modulus, lowest index on ties (the scan of orrfdchan.f:849-857)
 __device__ int block_argmax_abs(const double2 *v, int n) {
-  __shared__ double sb[CH_THREADS_MAX];
-  __shared__ int si[CH_THREADS_MAX];
+  __shared__ double sb[CH_THREADS_MAX / 32];
+  __shared__ int si[CH_THREADS_MAX / 32];
   double best = -1.0;
   int bi = 0;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double m2 = v[i].x * v[i].x + v[i].y * v[i].y;
     if (m2 > best) { best = m2; bi = i; }
   }
-  __syncthreads();
-  sb[threadIdx.x] = best; si[threadIdx.x] = bi;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int t = 1; t < blockDim.x; ++t)
-      if (sb[t] > sb[0] || (sb[t] == sb[0] && si[t] < si[0])) { sb[0] = sb[t]; si[0] = si[t]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
   }
+  __syncthreads();  // a previous call's readers are done with sb / si
+  if ((threadIdx.x & 31) == 0) { sb[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
   __syncthreads();
-  return si[0];
+  best = sb[0]; bi = si[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+    if (sb[w] > best || (sb[w] == best && si[w] < bi)) { best = sb[w]; bi = si[w]; }
+  return bi;
 }
 
 __device__ void start_vector(double2 *x, int n) {
@@ -2783,8 +2830,13 @@ static bool use_big_kernel(int n) { return n >= CH_BIG_MIN_N; }
 // which build of the big kernel: 2 = two CTAs per SM (while 2 x its shared memory fits), 1 = one CTA per SM two-level
 // LU, 0 = the single-level LU; OSB_CHAN_BIG overrides (A/B measurements)
 static int big_variant(int n) {
-  // two CTAs: 2 x (dynamic + ~11 KB static + 1 KB reserved) must fit the 228 KB of an SM
-  const bool two_fit = 2 * (chan_fixed_smem(n, 2) + 12 * 1024) <= 228 * 1024;
+  // two CTAs: 2 x (dynamic + static + 1 KB reserved) must fit the 228 KB of an SM
+  static size_t stat = 0;
+  if (!stat) {
+    cudaFuncAttributes fa;
+    stat = cudaFuncGetAttributes(&fa, (const void *)chan_eig_kernel_big2) == cudaSuccess ? fa.sharedSizeBytes : 12 * 1024;
+  }
+  const bool two_fit = 2 * (chan_fixed_smem(n, 2) + stat + 1024) <= 228 * 1024;
   // measured on B200 (tools/bench_chan.py, 4096 alpha): N = 384: 37.7 k eig/s (build 2) / 27.2 k (1) / 21.7 k (0);
   // N = 512: 22.8 k / 17.6 k / 19.5 k; N = 600 (two CTAs no longer fit): 11.1 k (1) / 10.8 k (0)
   int v = two_fit ? 2 : 0;
@@ -2795,7 +2847,7 @@ static int big_variant(int n) {
 }
 static bool use_small_kernel(int n) {
   const char *e = getenv("OSB_CHAN_SMALL_MAX");  // tuning knob; default from measurements on B200
-  const int nmax = e ? atoi(e) : 200;
+  const int nmax = e ? atoi(e) : 184;  // N = 160: 279 k (small) / 217 k eig/s; N = 200: 140 k / 162 k
   return n <= nmax && !chan_matrix_in_smem(n) && !getenv("OSB_CHAN_NO_SMALL");
 }
 
