@@ -756,17 +756,17 @@ __device__ __forceinline__ double2 solve_row16(double2 xr, const double2 (&m)[16
   return acc;
 }
 
-// x <- M^{-1} x using P M = L U.  x: shared, n complex.  Blocked by 16 columns: the
-// 16x16 diagonal block is staged in shared memory and solved by one warp with shuffles,
-// then all threads apply the 16 solved values to the remaining rows (coalesced column
-// reads): 2 barriers per block instead of one per column.
+// x <- M^{-1} x using P M = L U.  x: shared, n complex.  Blocked by 16 columns with a one-block look-ahead: while
+// warps 1.. apply the 16 values solved last to the rows further down (coalesced column reads), warp 0 applies them
+// to the 16 rows of the NEXT diagonal block and solves that block with shuffles -- the serial chain of the diagonal
+// solve runs beside the row update instead of in front of it, one barrier per block step.  The diagonal blocks are
+// staged in shared memory two steps ahead by the updating warps.
 __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv, double2 *x) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  // two buffers: the diagonal block of the NEXT step is fetched while the rows below are updated with this one
+  const int ut = tid - 32, nut = nt - 32;  // the updating threads (warps 1..)
   __shared__ double2 dblk[2][16][17];
   // Large matrices are streamed from DRAM by every solve (hundreds of concurrent 4 MB factorisations do not fit the
-  // L2) and each block step waits for its 16 columns: the NEXT step's columns are requested into the L2 one step
-  // ahead (one prefetch per 128-byte line).
+  // L2): the NEXT step's columns are requested into the L2 one step ahead (one prefetch per 128-byte line).
   const bool pf = n > 128;
   // n >= 300 (the factorisation streams from DRAM): all 16 column entries of a row are requested before the first
   // one is used -- one memory latency per row instead of one per unrolled group (+4.5 % at N = 384 / 512; below,
@@ -777,132 +777,121 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
       const int p = ipiv[k];
       if (p != k) { const double2 t = x[k]; x[k] = x[p]; x[p] = t; }
     }
-  // ---- L y = P b (unit lower)
-  for (int e = tid; e < 256; e += nt) {
+  // ---------------- L y = P b (unit lower) ----------------
+  auto stage_l = [&](int b, int j0, int e) {  // entry e of the diagonal block at j0 -> dblk[b]
     const int r = e & 15, c = e >> 4;
-    if (r < n && c < n) dblk[0][r][c] = M[(size_t)c * n + r];
-  }
-  __syncthreads();
-  int buf = 0;
-  for (int j0 = 0; j0 < n; j0 += 16, buf ^= 1) {
+    if (e < 256 && j0 + r < n && j0 + c < n) dblk[b][r][c] = M[(size_t)(j0 + c) * n + j0 + r];
+  };
+  auto diag_l = [&](int b, int j0, double2 xi) {  // warp 0: forward substitution inside the block at j0
     const int nb = min(16, n - j0);
+    for (int t = 0; t < nb; ++t) {
+      const double xr = __shfl_sync(0xffffffffu, xi.x, t), xim = __shfl_sync(0xffffffffu, xi.y, t);
+      if (lane > t && lane < nb) xi = cfnma2(xi, dblk[b][lane][t], make_double2(xr, xim));
+    }
+    if (lane < nb) x[j0 + lane] = xi;
+  };
+  for (int e = tid; e < 512; e += nt) stage_l(e >> 8, (e >> 8) * 16, e & 255);
+  __syncthreads();
+  if (warp == 0) diag_l(0, 0, lane < min(16, n) ? x[lane] : make_double2(0.0, 0.0));
+  __syncthreads();
+  int cur = 1;  // dblk[cur] holds the block after the one just solved
+  for (int j0 = 0; j0 + 16 < n; j0 += 16, cur ^= 1) {
+    const int jn = j0 + 16;
     if (warp == 0) {
-      double2 xi = (lane < nb) ? x[j0 + lane] : make_double2(0.0, 0.0);
-      for (int t = 0; t < nb; ++t) {
-        const double xr = __shfl_sync(0xffffffffu, xi.x, t), xim = __shfl_sync(0xffffffffu, xi.y, t);
-        if (lane > t && lane < nb) xi = cfnma2(xi, dblk[buf][lane][t], make_double2(xr, xim));
-      }
-      if (lane < nb) x[j0 + lane] = xi;
-    } else if (pf && j0 + 16 < n) {
-      // (the warps that wait for the diagonal block request the columns of the next step into the L2)
-      for (int r = j0 + 16 + 8 * (tid - 32); r < n; r += 8 * (nt - 32))
-#pragma unroll
-        for (int t = 0; t < 16; ++t)
-          if (j0 + 16 + t < n) prefetch_l2(M + (size_t)(j0 + 16 + t) * n + r);
-    }
-    __syncthreads();
-    // next diagonal block: loads issued here, stored after the update
-    const int jn = j0 + 16, nbn = min(16, n - jn);
-    double2 dn[2];
-    if (!deep) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int e = tid + q * nt, r = e & 15, c = e >> 4;
-        dn[q] = (e < 256 && r < nbn && c < nbn) ? M[(size_t)(jn + c) * n + jn + r] : make_double2(0.0, 0.0);
-      }
-    }
-    if (deep) {
-      for (int r = j0 + nb + tid; r < n; r += nt) {
+      const int nbn = min(16, n - jn);
+      double2 xi = make_double2(0.0, 0.0);
+      if (lane < nbn) {
         double2 m[16];
 #pragma unroll
-        for (int t = 0; t < 16; ++t) m[t] = M[(size_t)(j0 + min(t, nb - 1)) * n + r];
-        x[r] = solve_row16(x[r], m, x + j0, nb);
+        for (int t = 0; t < 16; ++t) m[t] = M[(size_t)(j0 + t) * n + jn + lane];
+        xi = solve_row16(x[jn + lane], m, x + j0, 16);
       }
-      // (16 row entries in registers: the block is fetched afterwards, from the L2 it was prefetched into)
-#pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const int e = tid + q * nt, r = e & 15, c = e >> 4;
-        dn[q] = (e < 256 && r < nbn && c < nbn) ? M[(size_t)(jn + c) * n + jn + r] : make_double2(0.0, 0.0);
-      }
+      diag_l(cur, jn, xi);
     } else {
-      for (int r = j0 + nb + tid; r < n; r += nt) {
-        double2 acc = x[r];
-#pragma unroll 4
-        for (int t = 0; t < nb; ++t) acc = cfnma2(acc, M[(size_t)(j0 + t) * n + r], x[j0 + t]);
-        x[r] = acc;
-      }
-    }
+      if (pf && jn + 16 < n)
+        for (int r = jn + 16 + 8 * ut; r < n; r += 8 * nut)
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int e = tid + q * nt, r = e & 15, c = e >> 4;
-      if (e < 256) dblk[buf ^ 1][r][c] = dn[q];
+          for (int t = 0; t < 16; ++t) prefetch_l2(M + (size_t)(jn + t) * n + r);
+      if (deep) {
+        for (int r = jn + 16 + ut; r < n; r += nut) {
+          double2 m[16];
+#pragma unroll
+          for (int t = 0; t < 16; ++t) m[t] = M[(size_t)(j0 + t) * n + r];
+          x[r] = solve_row16(x[r], m, x + j0, 16);
+        }
+      } else {
+        for (int r = jn + 16 + ut; r < n; r += nut) {
+          double2 acc = x[r];
+#pragma unroll 4
+          for (int t = 0; t < 16; ++t) acc = cfnma2(acc, M[(size_t)(j0 + t) * n + r], x[j0 + t]);
+          x[r] = acc;
+        }
+      }
+      for (int e = ut; e < 256; e += nut) stage_l(cur ^ 1, jn + 16, e);
     }
     __syncthreads();
   }
-  // ---- U x = y.  The diagonal block is staged as D^{-1} U (unit upper, the reciprocal of the pivot on the diagonal):
-  // the serial chain of the 16 back-substitution steps then holds no division
-  auto load_u = [&](int j0, int e, double2 &a, double2 &d) {
-    const int nb = min(16, n - j0), r = e & 15, c = e >> 4;
-    const bool in = j0 >= 0 && e < 256 && r < nb && c < nb && c >= r;
-    a = in ? M[(size_t)(j0 + c) * n + j0 + r] : make_double2(0.0, 0.0);
-    d = in ? M[(size_t)(j0 + r) * n + j0 + r] : make_double2(1.0, 0.0);
-  };
-  auto scaled_u = [&](int e, double2 a, double2 d) {
+  // ---------------- U x = y ----------------
+  // The diagonal blocks are staged as D^{-1} U (unit upper, the reciprocal of the pivot on the diagonal): the serial
+  // chain of the 16 back-substitution steps then holds no division
+  auto stage_u = [&](int b, int j0, int e) {
     const int r = e & 15, c = e >> 4;
-    if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
-    const double s = 1.0 / fma(d.x, d.x, d.y * d.y);
-    const double2 dinv = make_double2(d.x * s, -d.y * s);
-    return (c == r) ? dinv : cmul2(a, dinv);
+    if (e < 256 && j0 >= 0 && j0 + r < n && j0 + c < n && c >= r) {
+      const double2 a = M[(size_t)(j0 + c) * n + j0 + r];
+      double2 d = M[(size_t)(j0 + r) * n + j0 + r];
+      if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
+      const double sc = 1.0 / fma(d.x, d.x, d.y * d.y);
+      const double2 dinv = make_double2(d.x * sc, -d.y * sc);
+      dblk[b][r][c] = (c == r) ? dinv : cmul2(a, dinv);
+    }
+  };
+  auto diag_u = [&](int b, int j0, double2 xi) {  // warp 0: back substitution inside the block at j0
+    const int nb = min(16, n - j0);
+    if (lane < nb) xi = cmul2(xi, dblk[b][lane][lane]);
+    for (int t = nb - 1; t >= 0; --t) {
+      const double xr = __shfl_sync(0xffffffffu, xi.x, t), xim = __shfl_sync(0xffffffffu, xi.y, t);
+      if (lane < t) xi = cfnma2(xi, dblk[b][lane][t], make_double2(xr, xim));
+    }
+    if (lane < nb) x[j0 + lane] = xi;
   };
   const int jlast = ((n - 1) / 16) * 16;
-  for (int q = 0; q < 2; ++q) {
-    const int e = tid + q * nt;
-    double2 a, d;
-    load_u(jlast, e, a, d);
-    if (e < 256) dblk[buf][e & 15][e >> 4] = scaled_u(e, a, d);
-  }
+  for (int e = tid; e < 512; e += nt) stage_u(e >> 8, jlast - (e >> 8) * 16, e & 255);
   __syncthreads();
-  for (int j0 = jlast; j0 >= 0; j0 -= 16, buf ^= 1) {
-    const int nb = min(16, n - j0);
+  if (warp == 0) diag_u(0, jlast, lane < n - jlast ? x[jlast + lane] : make_double2(0.0, 0.0));
+  __syncthreads();
+  cur = 1;
+  for (int j0 = jlast; j0 >= 16; j0 -= 16, cur ^= 1) {
+    const int nb = min(16, n - j0), jp = j0 - 16;  // the block above is always full
     if (warp == 0) {
-      double2 xi = (lane < nb) ? cmul2(x[j0 + lane], dblk[buf][lane][lane]) : make_double2(0.0, 0.0);
-      for (int t = nb - 1; t >= 0; --t) {
-        const double xr = __shfl_sync(0xffffffffu, xi.x, t), xim = __shfl_sync(0xffffffffu, xi.y, t);
-        if (lane < t) xi = cfnma2(xi, dblk[buf][lane][t], make_double2(xr, xim));
-      }
-      if (lane < nb) x[j0 + lane] = xi;
-    } else if (pf && j0 >= 16) {
-      for (int r = 8 * (tid - 32); r < j0; r += 8 * (nt - 32))
-#pragma unroll
-        for (int t = 0; t < 16; ++t) prefetch_l2(M + (size_t)(j0 - 16 + t) * n + r);
-    }
-    __syncthreads();
-    double2 an[2], dn[2];
-    if (!deep) {
-#pragma unroll
-      for (int q = 0; q < 2; ++q) load_u(j0 - 16, tid + q * nt, an[q], dn[q]);
-    }
-    if (deep) {
-      for (int r = tid; r < j0; r += nt) {
+      double2 xi = make_double2(0.0, 0.0);
+      if (lane < 16) {
         double2 m[16];
 #pragma unroll
-        for (int t = 0; t < 16; ++t) m[t] = M[(size_t)(j0 + min(t, nb - 1)) * n + r];
-        x[r] = solve_row16(x[r], m, x + j0, nb);
+        for (int t = 0; t < 16; ++t) m[t] = M[(size_t)(j0 + min(t, nb - 1)) * n + jp + lane];
+        xi = solve_row16(x[jp + lane], m, x + j0, nb);
       }
-#pragma unroll
-      for (int q = 0; q < 2; ++q) load_u(j0 - 16, tid + q * nt, an[q], dn[q]);
+      diag_u(cur, jp, xi);
     } else {
-      for (int r = tid; r < j0; r += nt) {
-        double2 acc = x[r];
-#pragma unroll 4
-        for (int t = 0; t < nb; ++t) acc = cfnma2(acc, M[(size_t)(j0 + t) * n + r], x[j0 + t]);
-        x[r] = acc;
-      }
-    }
+      if (pf && jp >= 16)
+        for (int r = 8 * ut; r < jp; r += 8 * nut)
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int e = tid + q * nt;
-      if (e < 256) dblk[buf ^ 1][e & 15][e >> 4] = scaled_u(e, an[q], dn[q]);
+          for (int t = 0; t < 16; ++t) prefetch_l2(M + (size_t)(jp + t) * n + r);
+      if (deep) {
+        for (int r = ut; r < jp; r += nut) {
+          double2 m[16];
+#pragma unroll
+          for (int t = 0; t < 16; ++t) m[t] = M[(size_t)(j0 + min(t, nb - 1)) * n + r];
+          x[r] = solve_row16(x[r], m, x + j0, nb);
+        }
+      } else {
+        for (int r = ut; r < jp; r += nut) {
+          double2 acc = x[r];
+#pragma unroll 4
+          for (int t = 0; t < nb; ++t) acc = cfnma2(acc, M[(size_t)(j0 + t) * n + r], x[j0 + t]);
+          x[r] = acc;
+        }
+      }
+      for (int e = ut; e < 256; e += nut) stage_u(cur ^ 1, jp - 16, e);
     }
     __syncthreads();
   }
