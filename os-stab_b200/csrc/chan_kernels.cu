@@ -135,12 +135,24 @@ __device__ void assemble_shifted(double2 *__restrict__ M, int n, const double *_
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const double2 w2 = csub2(coef_w2(p, u[i]), sb2);
     const double2 w0 = csub2(coef_w0(p, u[i], d2u[i]), sb0);
-    for (int j = 0; j < n; ++j) {
-      const size_t e = (size_t)j * n + i;
-      const double d2 = D2[e], d4 = D4[e];
-      double2 v = make_double2(fma(w2.x, d2, d4), w2.y * d2);
-      if (i == j) v = cadd2(v, w0);
-      M[e] = v;
+    // eight columns per trip, the sixteen table loads issued before the first store: the loop waits for the L2 once
+    // per trip (the tables are shared by every CTA and stay L2-resident, the matrix is written through to DRAM)
+    for (int j0 = 0; j0 < n; j0 += 8) {
+      double d2[8], d4[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const size_t e = (size_t)min(j0 + q, n - 1) * n + i;
+        d2[q] = D2[e]; d4[q] = D4[e];
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const int j = j0 + q;
+        if (j < n) {
+          double2 v = make_double2(fma(w2.x, d2[q], d4[q]), w2.y * d2[q]);
+          if (i == j) v = cadd2(v, w0);
+          M[(size_t)j * n + i] = v;
+        }
+      }
     }
   }
   __syncthreads();

@@ -51,7 +51,8 @@ def raw_page(rep):
 
 
 def main():
-    out = {}
+    tj = ROOT / "profiles" / "r02_traffic.json"
+    out = json.loads(tj.read_text()) if tj.exists() else {}  # cases not recaptured keep their entry
     for case, (key, unit, nunits) in CASES.items():
         rep = ROOT / "gpurun_out" / f"r02_{case}_rawpage.csv"
         if not rep.exists():
