@@ -221,7 +221,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------- ncu-derived traffic
@@ -413,6 +413,29 @@ def secondary_configs(eng, osb, peak_dfma, peak_dmma, hbm_gbs, traffic):
 
 
 # ----------------------------------------------------------------- GPU arm
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries write there too (NCCL prints its version banner on the
+    first communicator when NCCL_DEBUG is set on the box): file descriptor 1 is pointed at stderr for the whole run and
+    the line goes to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -428,6 +451,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -775,7 +799,7 @@ def main():
             "cpu_baseline": cpu,
             "secondary": secondary,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     barrier()
     # torch frees pinned/device buffers by recording events on the library's stream:
     # release them before the stream goes away with the context
