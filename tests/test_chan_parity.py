@@ -481,6 +481,40 @@ def test_early_stop_of_the_inverse_iteration(engine, disc, N, route, monkeypatch
     assert fast["iters"].sum() <= full["iters"].sum()
 
 
+@pytest.mark.parametrize("N,env", [(20, {"OSB_CHAN_NO_WARP": "1"}), (33, {"OSB_CHAN_NO_WARP": "1"}), (64, {"OSB_CHAN_NO_WARP": "1"}),
+                                   (150, {"OSB_CHAN_NO_SMALL": "1"}), (200, {"OSB_CHAN_SMALL_MAX": "256"}),
+                                   (361, {"OSB_CHAN_BIG": "0"}), (361, {"OSB_CHAN_BIG": "1"})])
+def test_dense_kernel_shapes_agree(engine, N, env, monkeypatch):
+    """The dense path picks a kernel by size (warp per instance for n <= 64, 128- and 256-thread CTAs, two CTAs per SM with
+    the two-level LU from n = 351).  Forcing the neighbouring shape at the same N -- CTA kernels on warp-sized operators
+    (n = 19, 32, 63: fewer rows than one 16-column block step, exactly two, a ragged last block), the 256-thread kernel on a
+    small one and the other way round, the single-level and the one-CTA two-level LU on a large one -- must reproduce the
+    default shape's eigenvalues: they share pivots and row arithmetic and differ in summation grouping at most."""
+    alpha = np.linspace(0.8, 1.12, 25)
+    ch = engine.chan(ob.DISC_CHEB, N)
+    # shifts 1e-5 away from the eigenvalue (a first solve without shifts finds it): both shapes then converge in a few
+    # solves, far from the stall of a slowly contracting iteration at the rounding floor of a large collocation pencil
+    sig = ch.solve(alpha, 1.0e4)["omega"] * (1.0 + 1.0e-5)
+    base = ch.solve(alpha, 1.0e4, sigma0=sig)
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    other = ch.solve(alpha, 1.0e4, sigma0=sig)
+    ch.free()
+    assert (base["status"] == 0).all() and (other["status"] == 0).all()
+    d = rel(base["omega"], other["omega"])
+    print(f"N={N} {env}: max rel diff between kernel shapes {d.max():.2e}")
+    # Same kernel arithmetic, different thread count (n <= 200): identical pivots and row operations, 1e-15.  CTA against
+    # warp kernel, and the LU shapes at n = 360 (k = 16 / 64 / 32 trailing updates group their sums differently): the
+    # difference is rounding amplified by the collocation pencil -- ~1e-12 at N = 64, ~1e-9 at N = 361, where single
+    # points next to a near-degenerate pair reach 1e-6 (SURVEY H7; the reference's own ZGEGV is no better there).
+    if N <= 64:
+        assert d.max() < 5e-12, d.max()
+    elif N <= 200:
+        assert d.max() < 1e-13, d.max()
+    else:
+        assert np.median(d) < 5e-9 and d.max() < 5e-6, (np.median(d), d.max())
+
+
 def _pencil(t, alpha, Re):
     """A and B of the interior pencil from the tables osb_chan_tables returns (channel metrics)."""
     n = t["eta"].size - 2
