@@ -2433,17 +2433,18 @@ __device__ void w_assemble(double2 *M, int n, const double *__restrict__ D2, con
 __device__ void w_lu(double2 *M, int n, int *ipiv) {
   const int lane = threadIdx.x & 31;
   for (int k = 0; k < n; ++k) {
-    double best = -1.0;
+    // pivot search on the bit patterns (non-negative doubles order like their bits; ties to the lower row as IZAMAX)
+    long long best = -1;
     int bi = k;
     for (int r = lane; r < n; r += 32)
       if (r >= k) {
         const double2 v = M[(size_t)k * n + r];
-        const double a = fabs(v.x) + fabs(v.y);
+        const long long a = __double_as_longlong(fabs(v.x) + fabs(v.y)) & 0x7fffffffffffffffll;
         if (a > best) { best = a; bi = r; }
       }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
@@ -2457,7 +2458,8 @@ __device__ void w_lu(double2 *M, int n, int *ipiv) {
     __syncwarp();
     double2 piv = M[(size_t)k * n + k];
     if (piv.x == 0.0 && piv.y == 0.0) piv = make_double2(1.0e-290, 0.0);
-    const double2 rinv = cdiv2(make_double2(1.0, 0.0), piv);
+    const double pinv = 1.0 / fma(piv.x, piv.x, piv.y * piv.y);  // one division in the column's serial chain
+    const double2 rinv = make_double2(piv.x * pinv, -piv.y * pinv);
     for (int r = lane; r < n; r += 32)
       if (r > k) {
         const double2 l = cmul2(M[(size_t)k * n + r], rinv);
@@ -2476,6 +2478,9 @@ __device__ void w_lu(double2 *M, int n, int *ipiv) {
   }
 }
 
+// x <- M^{-1} x, n <= 64: a lane keeps rows lane and lane + 32 of x in registers and the solved value of a column
+// reaches the others by shuffle -- no shared-memory round trip and no warp barrier per column; the reciprocals of the
+// pivots are formed up front, two per lane, so the back substitution's chain holds no division
 __device__ void w_solve(const double2 *M, int n, const int *ipiv, double2 *x) {
   const int lane = threadIdx.x & 31;
   if (lane == 0)
@@ -2484,44 +2489,72 @@ __device__ void w_solve(const double2 *M, int n, const int *ipiv, double2 *x) {
       if (p != k) { const double2 t = x[k]; x[k] = x[p]; x[p] = t; }
     }
   __syncwarp();
-  for (int k = 0; k < n - 1; ++k) {
-    const double2 xk = x[k];
-    for (int r = lane; r < n; r += 32)
-      if (r > k) x[r] = cfnma2(x[r], M[(size_t)k * n + r], xk);
-    __syncwarp();
+  const int r0 = lane, r1 = lane + 32;
+  double2 x0 = r0 < n ? x[r0] : make_double2(0.0, 0.0), x1 = r1 < n ? x[r1] : make_double2(0.0, 0.0);
+  double2 dinv0 = make_double2(0.0, 0.0), dinv1 = dinv0;
+  {
+    double2 d = r0 < n ? M[(size_t)r0 * n + r0] : make_double2(1.0, 0.0);
+    if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
+    double sc = 1.0 / fma(d.x, d.x, d.y * d.y);
+    dinv0 = make_double2(d.x * sc, -d.y * sc);
+    d = r1 < n ? M[(size_t)r1 * n + r1] : make_double2(1.0, 0.0);
+    if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
+    sc = 1.0 / fma(d.x, d.x, d.y * d.y);
+    dinv1 = make_double2(d.x * sc, -d.y * sc);
   }
-  for (int k = n - 1; k >= 0; --k) {
-    if (lane == 0) {
-      double2 d = M[(size_t)k * n + k];
-      if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
-      x[k] = cdiv2(x[k], d);
-    }
-    __syncwarp();
-    const double2 xk = x[k];
-    for (int r = lane; r < k; r += 32) x[r] = cfnma2(x[r], M[(size_t)k * n + r], xk);
-    __syncwarp();
+  for (int k = 0; k < n - 1; ++k) {  // L y = P b
+    const double2 src = k < 32 ? x0 : x1;
+    const double2 xk = make_double2(__shfl_sync(0xffffffffu, src.x, k & 31), __shfl_sync(0xffffffffu, src.y, k & 31));
+    if (r0 > k && r0 < n) x0 = cfnma2(x0, M[(size_t)k * n + r0], xk);
+    if (r1 > k && r1 < n) x1 = cfnma2(x1, M[(size_t)k * n + r1], xk);
   }
+  for (int k = n - 1; k >= 0; --k) {  // U x = y
+    if (k == r0) x0 = cmul2(x0, dinv0);
+    if (k == r1) x1 = cmul2(x1, dinv1);
+    const double2 src = k < 32 ? x0 : x1;
+    const double2 xk = make_double2(__shfl_sync(0xffffffffu, src.x, k & 31), __shfl_sync(0xffffffffu, src.y, k & 31));
+    if (r0 < k) x0 = cfnma2(x0, M[(size_t)k * n + r0], xk);
+    if (r1 < k) x1 = cfnma2(x1, M[(size_t)k * n + r1], xk);
+  }
+  if (r0 < n) x[r0] = x0;
+  if (r1 < n) x[r1] = x1;
+  __syncwarp();
 }
 
 __device__ void w_solve_h(const double2 *M, int n, const int *ipiv, double2 *x) {
+  // x <- M^{-H} x,  M^H = U^H L^H P.  Column-oriented like w_solve: x lives in registers (rows lane, lane + 32), the
+  // solved component is broadcast by shuffle, the pivots' reciprocals are formed up front.
   const int lane = threadIdx.x & 31;
-  for (int j = 0; j < n; ++j) {  // U^H a = r
-    double2 s = make_double2(0.0, 0.0);
-    for (int i = lane; i < j; i += 32) s = cadd2(s, cmulc2(M[(size_t)j * n + i], x[i]));
-    s = wsum(s);
-    if (lane == 0) {
-      const double2 dj = M[(size_t)j * n + j];
-      x[j] = cdiv2(csub2(x[j], s), make_double2(dj.x, -dj.y));
-    }
-    __syncwarp();
+  const int r0 = lane, r1 = lane + 32;
+  double2 x0 = r0 < n ? x[r0] : make_double2(0.0, 0.0), x1 = r1 < n ? x[r1] : make_double2(0.0, 0.0);
+  double2 dinv0, dinv1;  // 1 / conj(U(r, r))
+  {
+    double2 d = r0 < n ? M[(size_t)r0 * n + r0] : make_double2(1.0, 0.0);
+    if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
+    double sc = 1.0 / fma(d.x, d.x, d.y * d.y);
+    dinv0 = make_double2(d.x * sc, d.y * sc);
+    d = r1 < n ? M[(size_t)r1 * n + r1] : make_double2(1.0, 0.0);
+    if (d.x == 0.0 && d.y == 0.0) d = make_double2(1.0e-290, 0.0);
+    sc = 1.0 / fma(d.x, d.x, d.y * d.y);
+    dinv1 = make_double2(d.x * sc, d.y * sc);
   }
-  for (int j = n - 1; j >= 0; --j) {  // L^H b = a
-    double2 s = make_double2(0.0, 0.0);
-    for (int i = j + 1 + lane; i < n; i += 32) s = cadd2(s, cmulc2(M[(size_t)j * n + i], x[i]));
-    s = wsum(s);
-    if (lane == 0) x[j] = csub2(x[j], s);
-    __syncwarp();
+  for (int k = 0; k < n; ++k) {  // U^H a = r : lower triangular, (U^H)(j, k) = conj(U(k, j)) = conj(M[j n + k])
+    if (k == r0) x0 = cmul2(x0, dinv0);
+    if (k == r1) x1 = cmul2(x1, dinv1);
+    const double2 src = k < 32 ? x0 : x1;
+    const double2 ak = make_double2(__shfl_sync(0xffffffffu, src.x, k & 31), __shfl_sync(0xffffffffu, src.y, k & 31));
+    if (r0 > k && r0 < n) { const double2 u = M[(size_t)r0 * n + k]; x0 = cfnma2(x0, make_double2(u.x, -u.y), ak); }
+    if (r1 > k && r1 < n) { const double2 u = M[(size_t)r1 * n + k]; x1 = cfnma2(x1, make_double2(u.x, -u.y), ak); }
   }
+  for (int k = n - 1; k > 0; --k) {  // L^H b = a : unit upper, (L^H)(j, k) = conj(L(k, j)) = conj(M[j n + k])
+    const double2 src = k < 32 ? x0 : x1;
+    const double2 bk = make_double2(__shfl_sync(0xffffffffu, src.x, k & 31), __shfl_sync(0xffffffffu, src.y, k & 31));
+    if (r0 < k) { const double2 l = M[(size_t)r0 * n + k]; x0 = cfnma2(x0, make_double2(l.x, -l.y), bk); }
+    if (r1 < k) { const double2 l = M[(size_t)r1 * n + k]; x1 = cfnma2(x1, make_double2(l.x, -l.y), bk); }
+  }
+  if (r0 < n) x[r0] = x0;
+  if (r1 < n) x[r1] = x1;
+  __syncwarp();
   if (lane == 0)
     for (int k = n - 1; k >= 0; --k) {
       const int p = ipiv[k];
