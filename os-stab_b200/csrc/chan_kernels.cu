@@ -158,15 +158,46 @@ __device__ void assemble_shifted(double2 *__restrict__ M, int n, const double *_
   __syncthreads();
 }
 
+// The composed row permutation of a factorisation lives right behind its pivot list: perm[k] = the original row that
+// ends at position k.  The solves gather / scatter through it in parallel instead of replaying the n interchanges on
+// one thread (n dependent shared-memory round trips per solve).
+__host__ __device__ inline int lu_perm_offset(int n) { return (n + 8 + 3) & ~3; }
+__device__ __forceinline__ int *lu_perm(const int *ipiv, int n) { return const_cast<int *>(ipiv) + lu_perm_offset(n); }
+
 constexpr int LU_RPT = 4;  // panel rows per thread: n <= LU_RPT * blockDim.x (every launcher satisfies it)
+
+// The composed permutation follows the rows of a factorised panel to their positions (all reads before the barrier, all
+// writes after it).  Out of line: its four values held across the barrier would otherwise weigh on the register
+// allocation of the LU around it.
+__device__ __noinline__ void lu_perm_follow(int *perm, int mp, int p0, int p1, int p2, int p3) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int r0 = tid, r1 = tid + nt, r2 = tid + 2 * nt, r3 = tid + 3 * nt;
+  const int v0 = r0 < mp ? perm[r0] : 0, v1 = r1 < mp ? perm[r1] : 0, v2 = r2 < mp ? perm[r2] : 0, v3 = r3 < mp ? perm[r3] : 0;
+  __syncthreads();
+  if (r0 < mp) perm[p0] = v0;
+  if (r1 < mp) perm[p1] = v1;
+  if (r2 < mp) perm[p2] = v2;
+  if (r3 < mp) perm[p3] = v3;
+}
+// x <- P x (forward) or x <- P^T x through the composed permutation; ends with a barrier
+__device__ __noinline__ void cta_permute(double2 *x, const int *perm, int n, bool forward) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  double2 xv[LU_RPT];
+#pragma unroll
+  for (int q = 0; q < LU_RPT; ++q) { const int r = tid + q * nt; if (r < n) xv[q] = forward ? x[perm[r]] : x[r]; }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < LU_RPT; ++q) { const int r = tid + q * nt; if (r < n) x[forward ? r : perm[r]] = xv[q]; }
+  __syncthreads();
+}
 
 // The nb columns of a staged panel, ONE barrier each.  Rows stay where they are in shared memory while the panel is factorised
 // (a thread owns the physical rows tid, tid + nt, ... and keeps, in registers, the POSITION each would have after
 // LAPACK's interchanges): the pivot row is only read once chosen, every other row is updated by its owner alone,
 // so the one thing the threads exchange per column is the pivot search.  Same pivots (ties go to the smaller
 // position, as IZAMAX), same arithmetic per row, same ipiv as the swapping form -- 4 barriers per column there.
-__device__ __forceinline__ void lu_panel_columns(double2 *panel, int ldp, int mp, int nb, int k0, int *ipiv, double *red,
-                                                 int (&pos)[LU_RPT]) {
+__device__ __forceinline__ void lu_panel_columns(double2 *panel, int ldp, int mp, int nb, int k0, int *ipiv, int *perm,
+                                                 double *red, int (&pos)[LU_RPT]) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   int *red_i = (int *)(red + 2 * (CH_THREADS_MAX / 32));
   unsigned alive = 0;
@@ -244,7 +275,7 @@ __device__ __forceinline__ void lu_panel_columns(double2 *panel, int ldp, int mp
         }
       }
   }
-  __syncthreads();
+  lu_perm_follow(perm + k0, mp, pos[0], pos[1], pos[2], pos[3]);  // holds the barrier the callers rely on
 }
 
 // The factorised panel goes back to the matrix with every row at its position ...
@@ -277,6 +308,8 @@ __device__ __forceinline__ void lu_panel_settle(const double2 *__restrict__ M, i
 // ---------------------------------------------------------------------------
 __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel, double *red) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  int *perm = lu_perm(ipiv, n);
+  for (int i = tid; i < n; i += nt) perm[i] = i;  // (visible to thread 0 after the barrier that follows the first staging)
   const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   const int ldp = n + 16;
   int *red_i = (int *)(red + 2 * (CH_THREADS_MAX / 32));
@@ -291,7 +324,7 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
     __syncthreads();
     // ---- unblocked factorisation inside the panel (ZGETF2's pivots and arithmetic, rows left in place)
     int pos[LU_RPT];
-    lu_panel_columns(panel, ldp, mp, nb, k0, ipiv, red, pos);
+    lu_panel_columns(panel, ldp, mp, nb, k0, ipiv, perm, red, pos);
     PROF_ADD(1);
     // ---- row interchanges on the columns outside the panel; write the panel back
     // two columns per thread, interleaved: two independent chains of dependent swaps in flight
@@ -569,6 +602,8 @@ template <int NBI, int NBO>
 __device__ __noinline__ void cta_lu2(double2 *__restrict__ M, int n, int *ipiv, double2 *panel, double *red) {
   constexpr int CH_NBO = NBO;
   const int tid = threadIdx.x, nt = blockDim.x;
+  int *perm = lu_perm(ipiv, n);
+  for (int i = tid; i < n; i += nt) perm[i] = i;
   const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   const int ldp = n + 16;
   const int g = lane >> 2, t4 = lane & 3;
@@ -587,7 +622,7 @@ __device__ __noinline__ void cta_lu2(double2 *__restrict__ M, int n, int *ipiv, 
       __syncthreads();
       PROF_ADD(7);
       int pos[LU_RPT];
-      lu_panel_columns(panel, ldp, mp, nb, k0, ipiv, red, pos);
+      lu_panel_columns(panel, ldp, mp, nb, k0, ipiv, perm, red, pos);
       PROF_ADD(1);
       // ---- write the panel back (rows by position); the interchanges on the OTHER columns of the outer panel
       lu_panel_store(M, n, k0, nb, mp, panel, ldp, pos);
@@ -784,11 +819,7 @@ __device__ void cta_solve(const double2 *__restrict__ M, int n, const int *ipiv,
   // one is used -- one memory latency per row instead of one per unrolled group (+4.5 % at N = 384 / 512; below,
   // with the matrix L2-resident, the extra registers cost more than the latency: -4 % at N = 128 / 256)
   const bool deep = n >= 300;
-  if (tid == 0)
-    for (int k = 0; k < n; ++k) {
-      const int p = ipiv[k];
-      if (p != k) { const double2 t = x[k]; x[k] = x[p]; x[p] = t; }
-    }
+  cta_permute(x, lu_perm(ipiv, n), n, true);  // x <- P x
   // ---------------- L y = P b (unit lower) ----------------
   auto stage_l = [&](int b, int j0, int e) {  // entry e of the diagonal block at j0 -> dblk[b]
     const int r = e & 15, c = e >> 4;
@@ -952,12 +983,7 @@ __device__ void cta_solve_h(const double2 *__restrict__ M, int n, const int *ipi
     }
     __syncthreads();
   }
-  if (tid == 0)  // z = P^T b
-    for (int k = n - 1; k >= 0; --k) {
-      const int p = ipiv[k];
-      if (p != k) { const double2 t = x[k]; x[k] = x[p]; x[p] = t; }
-    }
-  __syncthreads();
+  cta_permute(x, lu_perm(ipiv, n), n, false);  // z = P^T b
 }
 
 // y = D2 x (or D2^T x); D2 real column-major n x n; x, y shared
@@ -1015,7 +1041,7 @@ __device__ ChanShared carve(unsigned char *smem, int n, int variant = 0) {
 constexpr int CH_NSMEM = 64;
 __host__ __device__ inline bool chan_matrix_in_smem(int n) { return n <= CH_NSMEM; }
 __host__ __device__ inline size_t chan_fixed_smem(int n, int variant = 0) {
-  size_t b = sizeof(double2) * (chan_panel_elems(n, variant) + 3 * (size_t)n) + sizeof(double) * 64 + sizeof(int) * (size_t)(n + 8);
+  size_t b = sizeof(double2) * (chan_panel_elems(n, variant) + 3 * (size_t)n) + sizeof(double) * 64 + sizeof(int) * (size_t)(lu_perm_offset(n) + n);
   return (b + 15) & ~(size_t)15;
 }
 size_t chan_smem_bytes(int n) {
@@ -2390,7 +2416,7 @@ struct WarpShared {
   int *ipiv;
 };
 __host__ __device__ inline size_t warp_smem_bytes(int n) {
-  return sizeof(double2) * ((size_t)n * n + 3 * (size_t)n) + sizeof(int) * (size_t)(n + 4);
+  return sizeof(double2) * ((size_t)n * n + 3 * (size_t)n) + sizeof(int) * (size_t)(lu_perm_offset(n) + n);
 }
 __device__ WarpShared wcarve(unsigned char *smem, int n) {
   WarpShared s;
@@ -2432,6 +2458,9 @@ __device__ void w_assemble(double2 *M, int n, const double *__restrict__ D2, con
 
 __device__ void w_lu(double2 *M, int n, int *ipiv) {
   const int lane = threadIdx.x & 31;
+  int *perm = lu_perm(ipiv, n);
+  for (int i = lane; i < n; i += 32) perm[i] = i;
+  __syncwarp();
   for (int k = 0; k < n; ++k) {
     // pivot search on the bit patterns (non-negative doubles order like their bits; ties to the lower row as IZAMAX)
     long long best = -1;
@@ -2448,7 +2477,12 @@ __device__ void w_lu(double2 *M, int n, int *ipiv) {
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
     }
-    if (lane == 0) ipiv[k] = bi;
+    if (lane == 0) {
+      ipiv[k] = bi;
+      const int ta = perm[k];
+      perm[k] = perm[bi];
+      perm[bi] = ta;
+    }
     if (bi != k)
       for (int j = lane; j < n; j += 32) {
         const double2 t = M[(size_t)j * n + k];
@@ -2483,14 +2517,10 @@ __device__ void w_lu(double2 *M, int n, int *ipiv) {
 // pivots are formed up front, two per lane, so the back substitution's chain holds no division
 __device__ void w_solve(const double2 *M, int n, const int *ipiv, double2 *x) {
   const int lane = threadIdx.x & 31;
-  if (lane == 0)
-    for (int k = 0; k < n; ++k) {
-      const int p = ipiv[k];
-      if (p != k) { const double2 t = x[k]; x[k] = x[p]; x[p] = t; }
-    }
-  __syncwarp();
+  const int *perm = lu_perm(ipiv, n);
   const int r0 = lane, r1 = lane + 32;
-  double2 x0 = r0 < n ? x[r0] : make_double2(0.0, 0.0), x1 = r1 < n ? x[r1] : make_double2(0.0, 0.0);
+  double2 x0 = r0 < n ? x[perm[r0]] : make_double2(0.0, 0.0), x1 = r1 < n ? x[perm[r1]] : make_double2(0.0, 0.0);  // P x
+  __syncwarp();
   double2 dinv0 = make_double2(0.0, 0.0), dinv1 = dinv0;
   {
     double2 d = r0 < n ? M[(size_t)r0 * n + r0] : make_double2(1.0, 0.0);
@@ -2552,14 +2582,9 @@ __device__ void w_solve_h(const double2 *M, int n, const int *ipiv, double2 *x) 
     if (r0 < k) { const double2 l = M[(size_t)r0 * n + k]; x0 = cfnma2(x0, make_double2(l.x, -l.y), bk); }
     if (r1 < k) { const double2 l = M[(size_t)r1 * n + k]; x1 = cfnma2(x1, make_double2(l.x, -l.y), bk); }
   }
-  if (r0 < n) x[r0] = x0;
-  if (r1 < n) x[r1] = x1;
-  __syncwarp();
-  if (lane == 0)
-    for (int k = n - 1; k >= 0; --k) {
-      const int p = ipiv[k];
-      if (p != k) { const double2 t = x[k]; x[k] = x[p]; x[p] = t; }
-    }
+  const int *perm = lu_perm(ipiv, n);  // P^T: the value at position r goes back to row perm[r]
+  if (r0 < n) x[perm[r0]] = x0;
+  if (r1 < n) x[perm[r1]] = x1;
   __syncwarp();
 }
 
