@@ -1015,9 +1015,11 @@ struct ChanShared {
   double *red;
 };
 
-// n >= CH_BIG_MIN_N: two CTAs of the 256-thread kernel no longer fit an SM by shared memory (308 n + 4640 bytes
-// each); those sizes run the one-CTA-per-SM kernel with the two-level LU, whose staging area shares the panel buffer
-constexpr int CH_BIG_MIN_N = 351;
+// n >= CH_BIG_MIN_N run the kernels with the two-level LU (two 256-thread CTAs per SM while they fit).  The threshold was
+// 351 (where two CTAs of the single-level kernel stop fitting an SM) until the two-level LU was measured below it
+// (4096 alpha, eig/s, single-level / two-level): N = 184: 227 k / 176 k; 200: 174 k / 183 k; 256: 135.5 k / 136.9 k;
+// 288: 93 k / 108 k; 320: 74 k / 86 k; 350: 36 k / 67 k.  OSB_CHAN_BIG_MIN overrides.
+constexpr int CH_BIG_MIN_N = 185;
 // LU variants: 0 = single-level, 16-column panel (cta_lu); 1 = two-level <16, 64>; 2 = two-level <8, 32>
 __host__ __device__ inline size_t chan_panel_elems(int n, int variant) {
   if (variant == 0) return (size_t)(n + 16) * CH_NB;
@@ -2885,7 +2887,10 @@ static cudaError_t warp_grid(int n, int64_t ninst, int *grid, size_t *smem, cons
   return cudaSuccess;
 }
 
-static bool use_big_kernel(int n) { return n >= CH_BIG_MIN_N; }
+static bool use_big_kernel(int n) {
+  const char *e = getenv("OSB_CHAN_BIG_MIN");  // tuning knob; default from measurements on B200
+  return n >= (e ? atoi(e) : CH_BIG_MIN_N);
+}
 // which build of the big kernel: 2 = two CTAs per SM (while 2 x its shared memory fits), 1 = one CTA per SM two-level
 // LU, 0 = the single-level LU; OSB_CHAN_BIG overrides (A/B measurements)
 static int big_variant(int n) {
