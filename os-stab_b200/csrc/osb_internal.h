@@ -87,6 +87,7 @@ struct ShootArgs {
   double2 *resid;         // optional [nlines*niter]: |err|, |ev-cm1|
   double4 *history;       // optional [nlines*niter*hist_cap]
   int hist_cap;
+  int pair_lpw;           // lane-pair kernel: lines per warp (1..16), set by launch_shoot
 };
 
 // Eigenfunction kernel args (K2b)

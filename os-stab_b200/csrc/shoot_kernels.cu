@@ -781,8 +781,9 @@ __device__ __forceinline__ void step_rk4_one(double (&y)[8], const double2 *__re
   for (int n = 0; n < 8; ++n) y[n] = fma(h6, f[n], acc[n]);
 }
 
+// ---- round-1/2 form of the pair kernel (OSB_PAIR_V1=1), kept for A/B measurements and bit-identity tests
 template <int INTEG, bool ANALYTIC, bool REAL_ALPHA>
-__device__ __forceinline__ void integrate_pass_pair(const ShootArgs &a, int v, zd alpha, double Re, zd cw,
+__device__ __forceinline__ void integrate_pass_pair_v1(const ShootArgs &a, int v, zd alpha, double Re, zd cw,
                                                     zd &err, int &qend) {
   constexpr int NS = (INTEG == OSB_INT_CK45) ? 6 : 3;
   // pairs of one warp converge after different numbers of passes, so the exchange is
@@ -825,7 +826,7 @@ __device__ __forceinline__ void integrate_pass_pair(const ShootArgs &a, int v, z
 }
 
 template <int INTEG, bool ANALYTIC>
-__global__ void __launch_bounds__(64) shoot_pair_kernel(const __grid_constant__ ShootArgs a) {
+__global__ void __launch_bounds__(64) shoot_pair_kernel_v1(const __grid_constant__ ShootArgs a) {
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int v = (int)(gtid & 1);
   const int64_t gline = gtid >> 1;
@@ -865,8 +866,8 @@ __global__ void __launch_bounds__(64) shoot_pair_kernel(const __grid_constant__ 
       {
         const zd al = a.spatial ? s.ev : alpha;
         const zd cw = a.spatial ? zdiv(omega, s.ev) : s.ev;
-        if (real_alpha) integrate_pass_pair<INTEG, ANALYTIC, true>(a, v, al, Re, cw, err, qend);
-        else integrate_pass_pair<INTEG, ANALYTIC, false>(a, v, al, Re, cw, err, qend);
+        if (real_alpha) integrate_pass_pair_v1<INTEG, ANALYTIC, true>(a, v, al, Re, cw, err, qend);
+        else integrate_pass_pair_v1<INTEG, ANALYTIC, false>(a, v, al, Re, cw, err, qend);
       }
       update_eigenvalue(s, err, ctemp, a.first_perturb);
       if (active && v == 0 && a.history && s.icount <= a.hist_cap) {
@@ -888,6 +889,156 @@ __global__ void __launch_bounds__(64) shoot_pair_kernel(const __grid_constant__ 
       s.ev = ctemp;
       omega.x += a.domega[line];
     }
+  }
+}
+
+// The pass as the pair kernel runs it.  A lane's own vector needs nothing from its partner until a Gram-Schmidt
+// step happens, so step k+1 is started from the un-normalised result of step k while the exchange and the
+// orthonormality test of step k are still in flight (one basic block: the scheduler interleaves the two dependent
+// chains); only when the test asks for a normalisation (2-4 % of the steps) is step k+1 redone from the normalised
+// vector.  Same operations on the same values as integrate_pass: bit-identical results, ~40 % less latency per step
+// in the regime this kernel serves (one warp per scheduler, nothing else to overlap with).
+template <int INTEG, bool ANALYTIC, bool REAL_ALPHA>
+__device__ __forceinline__ void integrate_pass_pair(const ShootArgs &a, int v, zd alpha, double Re, zd cw,
+                                                    zd &err, int &qend) {
+  constexpr int NS = (INTEG == OSB_INT_CK45) ? 6 : 3;
+  // pairs of one warp are at different passes of different continuation points, so the exchange is
+  // synchronised over the two lanes of the pair only
+  const unsigned pmask = 3u << (threadIdx.x & 30u);
+  const PassConst pc = pass_const(alpha, Re, cw);
+  double u[2][8];
+  initial_vectors(u, a, alpha, Re, cw);
+  if (a.bl_ic) {  // k = 0: Gram-Schmidt of the initial vectors (shoot.f:490-515)
+    zd w1, w2, p;
+    gram_schmidt<ANALYTIC>(u, w1, w2, p);
+  }
+  int q = 0;
+  const double2 *__restrict__ trow = a.tab;
+  double y[8];  // my vector after step k, not yet tested
+#pragma unroll
+  for (int n = 0; n < 8; ++n) y[n] = v ? u[1][n] : u[0][n];
+  if (INTEG == OSB_INT_CK45) step_ck45_one<REAL_ALPHA>(y, trow, pc, a);
+  else step_rk4_one<REAL_ALPHA>(y, trow, pc, a);
+  trow += NS;
+  for (int k = 1; k < a.nstep; ++k) {
+    double ys[8];  // step k+1, valid unless step k ends in a normalisation
+#pragma unroll
+    for (int n = 0; n < 8; ++n) ys[n] = y[n];
+    if (INTEG == OSB_INT_CK45) step_ck45_one<REAL_ALPHA>(ys, trow, pc, a);
+    else step_rk4_one<REAL_ALPHA>(ys, trow, pc, a);
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const double o = __shfl_xor_sync(pmask, y[n], 1);
+      u[0][n] = v ? o : y[n];
+      u[1][n] = v ? y[n] : o;
+    }
+    if (need_norm<ANALYTIC>(u, a.thr, a.strict)) {
+      q += 1;
+      zd w1, w2, p;
+      gram_schmidt<ANALYTIC>(u, w1, w2, p);
+#pragma unroll
+      for (int n = 0; n < 8; ++n) ys[n] = v ? u[1][n] : u[0][n];
+      if (INTEG == OSB_INT_CK45) step_ck45_one<REAL_ALPHA>(ys, trow, pc, a);
+      else step_rk4_one<REAL_ALPHA>(ys, trow, pc, a);
+    }
+    trow += NS;
+#pragma unroll
+    for (int n = 0; n < 8; ++n) y[n] = ys[n];
+  }
+  // k = nstep always ends in a normalisation (shoot.f:607)
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const double o = __shfl_xor_sync(pmask, y[n], 1);
+    u[0][n] = v ? o : y[n];
+    u[1][n] = v ? y[n] : o;
+  }
+  {
+    zd w1, w2, p;
+    gram_schmidt<ANALYTIC>(u, w1, w2, p);
+  }
+  qend = q + 1;
+  zd B1 = zneg(zdiv(zd{u[1][0], u[1][1]}, zd{u[0][0], u[0][1]}));
+  err = zadd(zmul(zd{u[0][2], u[0][3]}, B1), zd{u[1][2], u[1][3]});
+}
+
+// One pass per trip of ONE loop: a pair that has finished a continuation point writes it out, seeds the next point
+// (orrspace.f:494) and joins the very next pass together with the pairs that are still iterating.  With a loop nest
+// (points outside, passes inside) a warp spent, at every point, as many passes as its slowest line; now a warp runs
+// as long as the largest TOTAL over its lines.  a.pair_lpw lines share a warp (the lanes above them exit): fewer
+// lines per warp shorten that maximum further and spread a small sweep over more schedulers.
+template <int INTEG, bool ANALYTIC>
+__global__ void __launch_bounds__(64) shoot_pair_kernel(const __grid_constant__ ShootArgs a) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gwarp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int v = lane & 1;
+  const int64_t gline = gwarp * a.pair_lpw + (lane >> 1);
+  const bool active = gline < a.nlines && (lane >> 1) < a.pair_lpw;
+  const int64_t line = gline < a.nlines ? gline : a.nlines - 1;
+  const double Re = a.Re[line];
+  zd alpha, omega = zd{0.0, 0.0};
+  IterState s;
+  {
+    double2 al = a.alpha[line];
+    alpha = zd{al.x, al.y};
+    if (a.spatial) {
+      double2 om = a.omega0[line];
+      omega = zd{om.x, om.y};
+      s.ev = alpha;
+    } else {
+      double2 c0 = a.ev[line];
+      s.ev = zd{c0.x, c0.y};
+    }
+  }
+  const bool real_alpha = !a.spatial && __all_sync(0xffffffffu, alpha.y == 0.0);
+  if (!active) return;  // both lanes of a pair together; the exchange is pair-masked
+  int it = 0;
+  bool bad = false;
+  zd err, ctemp;
+  int qend;
+  auto fresh = [&]() {
+    s.icount = 1;
+    s.cm1_defined = a.cm1_defined;
+    s.cm1 = zd{s.ev.x + 1.0, s.ev.y};
+    s.cm2 = zd{0.0, 0.0}; s.errm1 = zd{0.0, 0.0}; s.errm2 = zd{0.0, 0.0};
+    err = zd{1.0, 0.0}; ctemp = s.ev;
+    qend = 0;
+    bad = false;
+  };
+  fresh();
+  while (true) {
+    // both lanes of a pair hold identical iteration state, so they take the same way through here
+    while (bad || !keep_going(a, s, err)) {
+      const int64_t out = line * a.niter + it;
+      if (v == 0) {
+        a.ev[out] = make_double2(ctemp.x, ctemp.y);
+        a.passes[out] = s.icount - 1;
+        a.qend[out] = qend;
+        a.status[out] = bad ? OSB_ST_NONFINITE : (s.icount <= a.maxcount ? OSB_ST_CONVERGED : OSB_ST_MAXCOUNT);
+        if (a.resid)
+          a.resid[out] = make_double2(zabs(err), s.cm1_defined ? zabs(zsub(s.ev, s.cm1)) : 0.0);
+      }
+      if (a.spatial) {
+        s.ev = ctemp;
+        omega.x += a.domega[line];
+      }
+      if (++it >= a.niter) return;
+      fresh();
+    }
+    ctemp = s.ev;
+    {
+      const zd al = a.spatial ? s.ev : alpha;
+      const zd cw = a.spatial ? zdiv(omega, s.ev) : s.ev;
+      if (real_alpha) integrate_pass_pair<INTEG, ANALYTIC, true>(a, v, al, Re, cw, err, qend);
+      else integrate_pass_pair<INTEG, ANALYTIC, false>(a, v, al, Re, cw, err, qend);
+    }
+    update_eigenvalue(s, err, ctemp, a.first_perturb);
+    if (v == 0 && a.history && s.icount <= a.hist_cap) {
+      const int64_t out = line * a.niter + it;
+      zd shown = a.show_updated ? s.ev : ctemp;
+      a.history[out * a.hist_cap + (s.icount - 1)] = make_double4(shown.x, shown.y, err.x, err.y);
+    }
+    s.icount += 1;
+    if (!(zfinite(s.ev) && zfinite(err))) bad = true;
   }
 }
 
@@ -1070,13 +1221,41 @@ cudaError_t launch_shoot(const ShootArgs &a, int integrator, int analytic_inprod
   }
   if (a.nlines <= 148 * 64 && !getenv("OSB_NO_PAIR")) {
     const int threads = 64;
-    const unsigned blocks = (unsigned)((2 * a.nlines + threads - 1) / threads);
+    // Single solves in batches that already give every scheduler a full warp gain nothing from the speculative step
+    // (4096 contebl points: 318 k eig/s in the plain form against 312 k); OSB_PAIR_V1=1 / =0 forces either form.
+    bool v1 = a.niter == 1 && a.nlines >= 4096;
+    if (const char *e = getenv("OSB_PAIR_V1")) v1 = atoi(e) != 0;
+    if (v1) {
+      const unsigned blocks = (unsigned)((2 * a.nlines + threads - 1) / threads);
+      if (integrator == OSB_INT_CK45) {
+        if (analytic_inprod) shoot_pair_kernel_v1<OSB_INT_CK45, true><<<blocks, threads, 0, st>>>(a);
+        else shoot_pair_kernel_v1<OSB_INT_CK45, false><<<blocks, threads, 0, st>>>(a);
+      } else {
+        if (analytic_inprod) shoot_pair_kernel_v1<OSB_INT_RK4, true><<<blocks, threads, 0, st>>>(a);
+        else shoot_pair_kernel_v1<OSB_INT_RK4, false><<<blocks, threads, 0, st>>>(a);
+      }
+      if (nlaunch) *nlaunch += 1;
+      return cudaGetLastError();
+    }
+    // Lines per warp (measured on B200, tools/bench_pair2.py).  A warp instruction costs the FP64 pipe the same 2.25
+    // cycles whether 2 or 32 lanes are active and a lone warp already keeps its scheduler's pipe ~50 % busy, so the
+    // count that matters is warps per scheduler (148 SMs x 4): spread the lines over up to ~512 warps (continuation
+    // lines: fewer lines per warp also means fewer divergent Gram-Schmidt events, 4096 lines x 50 omega: 8 per warp
+    // 367 k points/s, 16: 313 k, 4: 339 k; 1024 lines: 2 per warp 170 k, 4: 147 k, 1: 137 k) or ~296 (single solves with the heavier Cash-Karp step).
+    // OSB_PAIR_LPW overrides.
+    ShootArgs b = a;
+    const int64_t target = a.niter > 1 ? 512 : 296;
+    int lpw = (int)((a.nlines + target - 1) / target);
+    if (const char *e = getenv("OSB_PAIR_LPW")) lpw = atoi(e);
+    b.pair_lpw = std::min(16, std::max(1, lpw));
+    const int64_t warps = (a.nlines + b.pair_lpw - 1) / b.pair_lpw;
+    const unsigned blocks = (unsigned)((warps * 32 + threads - 1) / threads);
     if (integrator == OSB_INT_CK45) {
-      if (analytic_inprod) shoot_pair_kernel<OSB_INT_CK45, true><<<blocks, threads, 0, st>>>(a);
-      else shoot_pair_kernel<OSB_INT_CK45, false><<<blocks, threads, 0, st>>>(a);
+      if (analytic_inprod) shoot_pair_kernel<OSB_INT_CK45, true><<<blocks, threads, 0, st>>>(b);
+      else shoot_pair_kernel<OSB_INT_CK45, false><<<blocks, threads, 0, st>>>(b);
     } else {
-      if (analytic_inprod) shoot_pair_kernel<OSB_INT_RK4, true><<<blocks, threads, 0, st>>>(a);
-      else shoot_pair_kernel<OSB_INT_RK4, false><<<blocks, threads, 0, st>>>(a);
+      if (analytic_inprod) shoot_pair_kernel<OSB_INT_RK4, true><<<blocks, threads, 0, st>>>(b);
+      else shoot_pair_kernel<OSB_INT_RK4, false><<<blocks, threads, 0, st>>>(b);
     }
     if (nlaunch) *nlaunch += 1;
     return cudaGetLastError();

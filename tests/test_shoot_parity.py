@@ -538,20 +538,32 @@ def test_conte_and_orrsom_small_grids(engine, osb, oracle):
 
 def test_pair_kernel_equals_plain_kernel_bitwise(engine, osb, bl, monkeypatch):
     """Batches too small to fill the GPU run with two lanes per point (one per solution vector,
-    exchanged by shuffles).  The arithmetic per vector is that of the one-thread kernel, so every
+    exchanged by shuffles; step k+1 started while step k is still being tested, continuation points
+    of a line taken up pass by pass).  The arithmetic per vector is that of the one-thread kernel, so every
     output must be identical bit for bit, for every flow variant, both integrators, odd batch
     sizes (the last pair of a warp without a neighbour pair) and lines that converge after
     different numbers of passes inside one warp."""
     fact = S2 / 1.7207876
 
     def both(fn):
-        monkeypatch.delenv("OSB_NO_PAIR", raising=False)
-        a = fn()
-        monkeypatch.setenv("OSB_NO_PAIR", "1")
-        b = fn()
-        monkeypatch.delenv("OSB_NO_PAIR")
-        for k in a:
-            assert np.array_equal(a[k], b[k], equal_nan=True), k
+        # every form of the pair kernel: the default choice, the loop-nest form (OSB_PAIR_V1=1), and the single-loop
+        # form with the speculative step at 1, 3 (ragged) and 16 lines per warp -- against one thread per point
+        keys = ("OSB_NO_PAIR", "OSB_PAIR_V1", "OSB_PAIR_LPW")
+        outs = []
+        for env in ({}, {"OSB_PAIR_V1": "1"}, {"OSB_PAIR_V1": "0", "OSB_PAIR_LPW": "1"},
+                    {"OSB_PAIR_V1": "0", "OSB_PAIR_LPW": "3"}, {"OSB_PAIR_V1": "0", "OSB_PAIR_LPW": "16"},
+                    {"OSB_NO_PAIR": "1"}):
+            for k in keys:
+                monkeypatch.delenv(k, raising=False)
+            for k, val in env.items():
+                monkeypatch.setenv(k, val)
+            outs.append(fn())
+        for k in keys:
+            monkeypatch.delenv(k, raising=False)
+        a = outs[0]
+        for b in outs[1:]:
+            for k in a:
+                assert np.array_equal(a[k], b[k], equal_nan=True), k
         return a
 
     rng = np.random.default_rng(5)
