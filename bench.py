@@ -313,7 +313,7 @@ def secondary_configs(eng, osb, peak_dfma, peak_dmma, hbm_gbs, traffic):
             "passes_per_point": float(r["passes"].mean()),
             "roofline": {"bound": "fp64", "achieved": tf, "peak": peak_dfma, "unit": "TFLOP/s", "frac": tf / peak_dfma,
                          "traffic": tr("shoot_pair_kernel_spatial", nl * 50),
-                         "note": "sequential continuation inside a line (SURVEY H6): 4096 lines cannot fill 148 SMs"}}
+                         "note": "bound by the critical path of the slowest continuation line (SURVEY H6: points of a line are sequential); 4096 lines cannot fill 148 SMs"}}
     except Exception as e:  # noqa: BLE001
         out["config3_orrspace_4096_lines"] = {"error": repr(e)}
 

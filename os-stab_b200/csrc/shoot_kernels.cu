@@ -536,8 +536,8 @@ __device__ __forceinline__ bool keep_going(const ShootArgs &a, const IterState &
 template <int INTEG, bool ANALYTIC>
 __global__ void __launch_bounds__(128) shoot_kernel(const __grid_constant__ ShootArgs a) {
   const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  // lanes past the end shadow the last line (same work, no stores) so that every
-  // warp is full for the warp-wide vote below
+  // lanes past the end read the last line's inputs so that every warp is full for the
+  // warp-wide vote below, then leave
   const bool active = gid < a.nlines;
   const int64_t line = active ? gid : a.nlines - 1;
   const double Re = a.Re[line];
@@ -557,47 +557,57 @@ __global__ void __launch_bounds__(128) shoot_kernel(const __grid_constant__ Shoo
   }
   // temporal sweeps normally have real alpha: take the cheaper RHS when the whole warp does
   const bool real_alpha = !a.spatial && __all_sync(0xffffffffu, alpha.y == 0.0);
-  for (int it = 0; it < a.niter; ++it) {
-    const int64_t out = line * a.niter + it;
+  if (!active) return;
+  // ONE loop, one pass per trip: a line that has finished a continuation point writes it out, seeds the next one
+  // (orrspace.f:494) and joins the very next pass with the lines that are still iterating, so a warp runs as long as
+  // the largest TOTAL pass count over its lines instead of the sum over the points of the per-point maxima (a loop
+  // nest would give the latter; sweep.inp as 4096 lines: 1005 against 656 passes for the slowest warp).
+  int it = 0;
+  bool bad = false;
+  zd err, ctemp;
+  int qend;
+  auto fresh = [&]() {
     s.icount = 1;
     s.cm1_defined = a.cm1_defined;
     s.cm1 = zd{s.ev.x + 1.0, s.ev.y};
     s.cm2 = zd{0.0, 0.0}; s.errm1 = zd{0.0, 0.0}; s.errm2 = zd{0.0, 0.0};
-    zd err = zd{1.0, 0.0}, ctemp = s.ev;
-    int qend = 0, status = OSB_ST_MAXCOUNT;
-    while (true) {
-      if (!keep_going(a, s, err)) {
-        if (s.icount <= a.maxcount) status = OSB_ST_CONVERGED;
-        break;
-      }
-      ctemp = s.ev;
-      {
-        // spatial: the unknown is alpha and c = omega/alpha (orrspace.f:290,645)
-        const zd al = a.spatial ? s.ev : alpha;
-        const zd cw = a.spatial ? zdiv(omega, s.ev) : s.ev;
-        if (real_alpha) integrate_pass<INTEG, ANALYTIC, true>(a, al, Re, cw, err, qend);
-        else integrate_pass<INTEG, ANALYTIC, false>(a, al, Re, cw, err, qend);
-      }
-      update_eigenvalue(s, err, ctemp, a.first_perturb);
-      if (active && a.history && s.icount <= a.hist_cap) {
-        zd shown = a.show_updated ? s.ev : ctemp;
-        a.history[out * a.hist_cap + (s.icount - 1)] = make_double4(shown.x, shown.y, err.x, err.y);
-      }
-      s.icount += 1;
-      if (!(zfinite(s.ev) && zfinite(err))) { status = OSB_ST_NONFINITE; break; }
-    }
-    if (active) {
+    err = zd{1.0, 0.0}; ctemp = s.ev;
+    qend = 0;
+    bad = false;
+  };
+  fresh();
+  while (true) {
+    while (bad || !keep_going(a, s, err)) {
+      const int64_t out = line * a.niter + it;
       a.ev[out] = make_double2(ctemp.x, ctemp.y);
       a.passes[out] = s.icount - 1;
       a.qend[out] = qend;
-      a.status[out] = status;
+      a.status[out] = bad ? OSB_ST_NONFINITE : (s.icount <= a.maxcount ? OSB_ST_CONVERGED : OSB_ST_MAXCOUNT);
       if (a.resid)
         a.resid[out] = make_double2(zabs(err), s.cm1_defined ? zabs(zsub(s.ev, s.cm1)) : 0.0);
+      if (a.spatial) {
+        s.ev = ctemp;  // orrspace.f:494: alpha = ctemp seeds the next omega
+        omega.x += a.domega[line];  // orrspace.f:192-194
+      }
+      if (++it >= a.niter) return;
+      fresh();
     }
-    if (a.spatial) {
-      s.ev = ctemp;  // orrspace.f:494: alpha = ctemp seeds the next omega
-      omega.x += a.domega[line];  // orrspace.f:192-194
+    ctemp = s.ev;
+    {
+      // spatial: the unknown is alpha and c = omega/alpha (orrspace.f:290,645)
+      const zd al = a.spatial ? s.ev : alpha;
+      const zd cw = a.spatial ? zdiv(omega, s.ev) : s.ev;
+      if (real_alpha) integrate_pass<INTEG, ANALYTIC, true>(a, al, Re, cw, err, qend);
+      else integrate_pass<INTEG, ANALYTIC, false>(a, al, Re, cw, err, qend);
     }
+    update_eigenvalue(s, err, ctemp, a.first_perturb);
+    if (a.history && s.icount <= a.hist_cap) {
+      const int64_t out = line * a.niter + it;
+      zd shown = a.show_updated ? s.ev : ctemp;
+      a.history[out * a.hist_cap + (s.icount - 1)] = make_double4(shown.x, shown.y, err.x, err.y);
+    }
+    s.icount += 1;
+    if (!(zfinite(s.ev) && zfinite(err))) bad = true;
   }
 }
 
