@@ -2438,41 +2438,62 @@ __device__ __forceinline__ double2 wsum(double2 v) {
   return v;
 }
 
+template <bool TWO>  // TWO: n > 32, a lane owns rows lane and lane + 32; otherwise one row and none of the second row's work
 __device__ void w_assemble(double2 *M, int n, const double *__restrict__ D2, const double *__restrict__ D4,
                            const double *__restrict__ u, const double *__restrict__ d2u, const PencilCoef &p,
                            double2 sigma) {
   const int lane = threadIdx.x & 31;
   const double2 sb2 = cmul2(sigma, p.b2), sb0 = cmul2(sigma, p.b0);
-  for (int i = lane; i < n; i += 32) {
-    const double2 w2 = csub2(coef_w2(p, u[i]), sb2);
-    const double2 w0 = csub2(coef_w0(p, u[i], d2u[i]), sb0);
+  // rows lane and lane + 32 together: twice the table loads in flight per trip (the kernel runs one warp per
+  // scheduler, so nothing else hides their latency)
+  const int i0 = min(lane, n - 1), i1 = min(lane + 32, n - 1);
+  const bool h0 = lane < n, h1 = TWO && lane + 32 < n;
+  const double2 w2a = csub2(coef_w2(p, u[i0]), sb2), w2b = csub2(coef_w2(p, u[i1]), sb2);
+  const double2 w0a = csub2(coef_w0(p, u[i0], d2u[i0]), sb0), w0b = csub2(coef_w0(p, u[i1], d2u[i1]), sb0);
 #pragma unroll 8
-    for (int j = 0; j < n; ++j) {
-      const size_t e = (size_t)j * n + i;
-      const double d2 = __ldg(D2 + e), d4 = __ldg(D4 + e);
-      double2 v = make_double2(fma(w2.x, d2, d4), w2.y * d2);
-      if (i == j) v = cadd2(v, w0);
-      M[e] = v;
+  for (int j = 0; j < n; ++j) {
+    const size_t e0 = (size_t)j * n + i0, e1 = (size_t)j * n + i1;
+    const double d2a = __ldg(D2 + e0), d4a = __ldg(D4 + e0);
+    double2 va = make_double2(fma(w2a.x, d2a, d4a), w2a.y * d2a);
+    if (i0 == j) va = cadd2(va, w0a);
+    if (h0) M[e0] = va;
+    if (TWO) {
+      const double d2b = __ldg(D2 + e1), d4b = __ldg(D4 + e1);
+      double2 vb = make_double2(fma(w2b.x, d2b, d4b), w2b.y * d2b);
+      if (i1 == j) vb = cadd2(vb, w0b);
+      if (h1) M[e1] = vb;
     }
   }
   __syncwarp();
 }
 
+// Partial-pivoting LU of the shared-memory matrix by one warp; lane l owns rows l and l + 32.  The warp is alone on its
+// scheduler, so what counts is the latency of its own instruction stream (SASS-level stall attribution of round 2,
+// tools/capture_source.sh): the trailing update takes eight columns per trip with ALL loads first -- the compiler cannot
+// move the loads of the next columns above the stores of these (it cannot prove that pivot-row entries and the rows
+// being written do not alias), so every trip exposes one shared-memory round trip, and a trip now carries both rows
+// and eight columns instead of one row and four; pivot scan and row interchange are branch-free over the lane's two
+// entries.  Same operations on every entry, same pivots.
+template <bool TWO>
 __device__ void w_lu(double2 *M, int n, int *ipiv) {
   const int lane = threadIdx.x & 31;
   int *perm = lu_perm(ipiv, n);
   for (int i = lane; i < n; i += 32) perm[i] = i;
   __syncwarp();
+  const int r0 = lane, r1 = lane + 32;
   for (int k = 0; k < n; ++k) {
+    double2 *ck = M + (size_t)k * n;
     // pivot search on the bit patterns (non-negative doubles order like their bits; ties to the lower row as IZAMAX)
     long long best = -1;
     int bi = k;
-    for (int r = lane; r < n; r += 32)
-      if (r >= k) {
-        const double2 v = M[(size_t)k * n + r];
-        const long long a = __double_as_longlong(fabs(v.x) + fabs(v.y)) & 0x7fffffffffffffffll;
-        if (a > best) { best = a; bi = r; }
-      }
+    {
+      const bool h0 = r0 >= k && r0 < n, h1 = TWO && r1 >= k && r1 < n;
+      const double2 v0 = ck[h0 ? r0 : k], v1 = TWO ? ck[h1 ? r1 : k] : v0;
+      const long long a0 = h0 ? (__double_as_longlong(fabs(v0.x) + fabs(v0.y)) & 0x7fffffffffffffffll) : -1ll;
+      const long long a1 = h1 ? (__double_as_longlong(fabs(v1.x) + fabs(v1.y)) & 0x7fffffffffffffffll) : -1ll;
+      if (a0 > best) { best = a0; bi = r0; }
+      if (a1 > best) { best = a1; bi = r1; }
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -2485,31 +2506,81 @@ __device__ void w_lu(double2 *M, int n, int *ipiv) {
       perm[k] = perm[bi];
       perm[bi] = ta;
     }
-    if (bi != k)
-      for (int j = lane; j < n; j += 32) {
-        const double2 t = M[(size_t)j * n + k];
-        M[(size_t)j * n + k] = M[(size_t)j * n + bi];
-        M[(size_t)j * n + bi] = t;
-      }
+    if (bi != k) {  // interchange rows k and bi: columns lane and lane + 32
+      const int j0 = min(r0, n - 1), j1 = min(r1, n - 1);
+      double2 *c0 = M + (size_t)j0 * n, *c1 = M + (size_t)j1 * n;
+      const double2 t0 = c0[k], b0 = c0[bi];
+      double2 t1 = t0, b1 = b0;
+      if (TWO) { t1 = c1[k]; b1 = c1[bi]; }
+      if (r0 < n) { c0[k] = b0; c0[bi] = t0; }
+      if (TWO && r1 < n) { c1[k] = b1; c1[bi] = t1; }
+    }
     __syncwarp();
-    double2 piv = M[(size_t)k * n + k];
+    double2 piv = ck[k];
     if (piv.x == 0.0 && piv.y == 0.0) piv = make_double2(1.0e-290, 0.0);
     const double pinv = 1.0 / fma(piv.x, piv.x, piv.y * piv.y);  // one division in the column's serial chain
     const double2 rinv = make_double2(piv.x * pinv, -piv.y * pinv);
-    for (int r = lane; r < n; r += 32)
-      if (r > k) {
-        const double2 l = cmul2(M[(size_t)k * n + r], rinv);
-        M[(size_t)k * n + r] = l;
-        int j = k + 1;
-        for (; j + 3 < n; j += 4) {  // loads first, then stores: the compiler cannot prove that the
-                                     // pivot-row elements do not alias the row being written
-          double2 *c0 = M + (size_t)j * n, *c1 = c0 + n, *c2 = c1 + n, *c3 = c2 + n;
-          const double2 u0 = c0[k], u1 = c1[k], u2 = c2[k], u3 = c3[k];
-          const double2 m0 = c0[r], m1 = c1[r], m2 = c2[r], m3 = c3[r];
-          c0[r] = cfnma2(m0, l, u0); c1[r] = cfnma2(m1, l, u1); c2[r] = cfnma2(m2, l, u2); c3[r] = cfnma2(m3, l, u3);
-        }
-        for (; j < n; ++j) M[(size_t)j * n + r] = cfnma2(M[(size_t)j * n + r], l, M[(size_t)j * n + k]);
+    const bool a0 = r0 > k && r0 < n, a1 = TWO && r1 > k && r1 < n;
+    const int q0 = a0 ? r0 : k, q1 = a1 ? r1 : k;  // rows to read where a lane has nothing to update (never stored)
+    double2 l0 = make_double2(0.0, 0.0), l1 = l0;
+    if (a0) { l0 = cmul2(ck[r0], rinv); ck[r0] = l0; }
+    if (a1) { l1 = cmul2(ck[r1], rinv); ck[r1] = l1; }
+    int j = k + 1;
+    if (!TWO) {    // one row per lane
+      for (; j + 7 < n; j += 8) {
+        double2 *c = M + (size_t)j * n;
+        double2 uu[8], ma[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { uu[t] = c[t * n + k]; ma[t] = c[t * n + q0]; }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) ma[t] = cfnma2(ma[t], l0, uu[t]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          if (a0) c[t * n + r0] = ma[t];
       }
+      for (; j < n; ++j) {
+        double2 *c = M + (size_t)j * n;
+        const double2 uu = c[k], ma = c[q0];
+        if (a0) c[r0] = cfnma2(ma, l0, uu);
+      }
+    } else if (k < 31) {  // some lanes still own two rows below the pivot
+      for (; j + 7 < n; j += 8) {
+        double2 *c = M + (size_t)j * n;
+        double2 uu[8], ma[8], mb[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { uu[t] = c[t * n + k]; ma[t] = c[t * n + q0]; mb[t] = c[t * n + q1]; }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { ma[t] = cfnma2(ma[t], l0, uu[t]); mb[t] = cfnma2(mb[t], l1, uu[t]); }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          if (a0) c[t * n + r0] = ma[t];
+          if (a1) c[t * n + r1] = mb[t];
+        }
+      }
+      for (; j < n; ++j) {
+        double2 *c = M + (size_t)j * n;
+        const double2 uu = c[k], ma = c[q0], mb = c[q1];
+        if (a0) c[r0] = cfnma2(ma, l0, uu);
+        if (a1) c[r1] = cfnma2(mb, l1, uu);
+      }
+    } else {       // only the rows lane + 32 are left
+      for (; j + 7 < n; j += 8) {
+        double2 *c = M + (size_t)j * n;
+        double2 uu[8], mb[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) { uu[t] = c[t * n + k]; mb[t] = c[t * n + q1]; }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) mb[t] = cfnma2(mb[t], l1, uu[t]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t)
+          if (a1) c[t * n + r1] = mb[t];
+      }
+      for (; j < n; ++j) {
+        double2 *c = M + (size_t)j * n;
+        const double2 uu = c[k], mb = c[q1];
+        if (a1) c[r1] = cfnma2(mb, l1, uu);
+      }
+    }
     __syncwarp();
   }
 }
@@ -2517,6 +2588,7 @@ __device__ void w_lu(double2 *M, int n, int *ipiv) {
 // x <- M^{-1} x, n <= 64: a lane keeps rows lane and lane + 32 of x in registers and the solved value of a column
 // reaches the others by shuffle -- no shared-memory round trip and no warp barrier per column; the reciprocals of the
 // pivots are formed up front, two per lane, so the back substitution's chain holds no division
+template <bool TWO>
 __device__ void w_solve(const double2 *M, int n, const int *ipiv, double2 *x) {
   const int lane = threadIdx.x & 31;
   const int *perm = lu_perm(ipiv, n);
@@ -2534,25 +2606,63 @@ __device__ void w_solve(const double2 *M, int n, const int *ipiv, double2 *x) {
     sc = 1.0 / fma(d.x, d.x, d.y * d.y);
     dinv1 = make_double2(d.x * sc, -d.y * sc);
   }
-  for (int k = 0; k < n - 1; ++k) {  // L y = P b
-    const double2 src = k < 32 ? x0 : x1;
-    const double2 xk = make_double2(__shfl_sync(0xffffffffu, src.x, k & 31), __shfl_sync(0xffffffffu, src.y, k & 31));
-    if (r0 > k && r0 < n) x0 = cfnma2(x0, M[(size_t)k * n + r0], xk);
-    if (r1 > k && r1 < n) x1 = cfnma2(x1, M[(size_t)k * n + r1], xk);
+  // The factor entries of four columns are loaded before the four dependent steps that use them (addresses clamped
+  // where a lane has no row): the chain then holds only the shuffle and the complex FMA.
+  const int c0 = min(r0, n - 1), c1 = min(r1, n - 1);
+  {  // L y = P b
+    int k = 0;
+    for (; k + 3 < n - 1; k += 4) {
+      double2 m0[4], m1[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { m0[t] = M[(size_t)(k + t) * n + c0]; m1[t] = TWO ? M[(size_t)(k + t) * n + c1] : m0[t]; }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int kk = k + t;
+        const double2 src = kk < 32 ? x0 : x1;
+        const double2 xk = make_double2(__shfl_sync(0xffffffffu, src.x, kk & 31), __shfl_sync(0xffffffffu, src.y, kk & 31));
+        if (r0 > kk && r0 < n) x0 = cfnma2(x0, m0[t], xk);
+        if (TWO && r1 > kk && r1 < n) x1 = cfnma2(x1, m1[t], xk);
+      }
+    }
+    for (; k < n - 1; ++k) {
+      const double2 src = k < 32 ? x0 : x1;
+      const double2 xk = make_double2(__shfl_sync(0xffffffffu, src.x, k & 31), __shfl_sync(0xffffffffu, src.y, k & 31));
+      if (r0 > k && r0 < n) x0 = cfnma2(x0, M[(size_t)k * n + r0], xk);
+      if (TWO && r1 > k && r1 < n) x1 = cfnma2(x1, M[(size_t)k * n + r1], xk);
+    }
   }
-  for (int k = n - 1; k >= 0; --k) {  // U x = y
-    if (k == r0) x0 = cmul2(x0, dinv0);
-    if (k == r1) x1 = cmul2(x1, dinv1);
-    const double2 src = k < 32 ? x0 : x1;
-    const double2 xk = make_double2(__shfl_sync(0xffffffffu, src.x, k & 31), __shfl_sync(0xffffffffu, src.y, k & 31));
-    if (r0 < k) x0 = cfnma2(x0, M[(size_t)k * n + r0], xk);
-    if (r1 < k) x1 = cfnma2(x1, M[(size_t)k * n + r1], xk);
+  {  // U x = y
+    int k = n - 1;
+    for (; k - 3 >= 0; k -= 4) {
+      double2 m0[4], m1[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { m0[t] = M[(size_t)(k - t) * n + c0]; m1[t] = TWO ? M[(size_t)(k - t) * n + c1] : m0[t]; }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int kk = k - t;
+        if (kk == r0) x0 = cmul2(x0, dinv0);
+        if (TWO && kk == r1) x1 = cmul2(x1, dinv1);
+        const double2 src = kk < 32 ? x0 : x1;
+        const double2 xk = make_double2(__shfl_sync(0xffffffffu, src.x, kk & 31), __shfl_sync(0xffffffffu, src.y, kk & 31));
+        if (r0 < kk) x0 = cfnma2(x0, m0[t], xk);
+        if (TWO && r1 < kk) x1 = cfnma2(x1, m1[t], xk);
+      }
+    }
+    for (; k >= 0; --k) {
+      if (k == r0) x0 = cmul2(x0, dinv0);
+      if (TWO && k == r1) x1 = cmul2(x1, dinv1);
+      const double2 src = k < 32 ? x0 : x1;
+      const double2 xk = make_double2(__shfl_sync(0xffffffffu, src.x, k & 31), __shfl_sync(0xffffffffu, src.y, k & 31));
+      if (r0 < k) x0 = cfnma2(x0, M[(size_t)k * n + r0], xk);
+      if (TWO && r1 < k) x1 = cfnma2(x1, M[(size_t)k * n + r1], xk);
+    }
   }
   if (r0 < n) x[r0] = x0;
   if (r1 < n) x[r1] = x1;
   __syncwarp();
 }
 
+template <bool TWO>
 __device__ void w_solve_h(const double2 *M, int n, const int *ipiv, double2 *x) {
   // x <- M^{-H} x,  M^H = U^H L^H P.  Column-oriented like w_solve: x lives in registers (rows lane, lane + 32), the
   // solved component is broadcast by shuffle, the pivots' reciprocals are formed up front.
@@ -2570,19 +2680,56 @@ __device__ void w_solve_h(const double2 *M, int n, const int *ipiv, double2 *x) 
     sc = 1.0 / fma(d.x, d.x, d.y * d.y);
     dinv1 = make_double2(d.x * sc, d.y * sc);
   }
-  for (int k = 0; k < n; ++k) {  // U^H a = r : lower triangular, (U^H)(j, k) = conj(U(k, j)) = conj(M[j n + k])
-    if (k == r0) x0 = cmul2(x0, dinv0);
-    if (k == r1) x1 = cmul2(x1, dinv1);
-    const double2 src = k < 32 ? x0 : x1;
-    const double2 ak = make_double2(__shfl_sync(0xffffffffu, src.x, k & 31), __shfl_sync(0xffffffffu, src.y, k & 31));
-    if (r0 > k && r0 < n) { const double2 u = M[(size_t)r0 * n + k]; x0 = cfnma2(x0, make_double2(u.x, -u.y), ak); }
-    if (r1 > k && r1 < n) { const double2 u = M[(size_t)r1 * n + k]; x1 = cfnma2(x1, make_double2(u.x, -u.y), ak); }
+  // as in w_solve: the factor entries of four steps are loaded ahead of the dependent chain.  Row r of U / L is read
+  // along the row here (stride n), clamped where a lane has no row.
+  const int c0 = min(r0, n - 1), c1 = min(r1, n - 1);
+  {  // U^H a = r : lower triangular, (U^H)(j, k) = conj(U(k, j)) = conj(M[j n + k])
+    int k = 0;
+    for (; k + 3 < n; k += 4) {
+      double2 m0[4], m1[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { m0[t] = M[(size_t)c0 * n + k + t]; m1[t] = TWO ? M[(size_t)c1 * n + k + t] : m0[t]; }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int kk = k + t;
+        if (kk == r0) x0 = cmul2(x0, dinv0);
+        if (TWO && kk == r1) x1 = cmul2(x1, dinv1);
+        const double2 src = kk < 32 ? x0 : x1;
+        const double2 ak = make_double2(__shfl_sync(0xffffffffu, src.x, kk & 31), __shfl_sync(0xffffffffu, src.y, kk & 31));
+        if (r0 > kk && r0 < n) x0 = cfnma2(x0, make_double2(m0[t].x, -m0[t].y), ak);
+        if (TWO && r1 > kk && r1 < n) x1 = cfnma2(x1, make_double2(m1[t].x, -m1[t].y), ak);
+      }
+    }
+    for (; k < n; ++k) {
+      if (k == r0) x0 = cmul2(x0, dinv0);
+      if (TWO && k == r1) x1 = cmul2(x1, dinv1);
+      const double2 src = k < 32 ? x0 : x1;
+      const double2 ak = make_double2(__shfl_sync(0xffffffffu, src.x, k & 31), __shfl_sync(0xffffffffu, src.y, k & 31));
+      if (r0 > k && r0 < n) { const double2 u = M[(size_t)r0 * n + k]; x0 = cfnma2(x0, make_double2(u.x, -u.y), ak); }
+      if (TWO && r1 > k && r1 < n) { const double2 u = M[(size_t)r1 * n + k]; x1 = cfnma2(x1, make_double2(u.x, -u.y), ak); }
+    }
   }
-  for (int k = n - 1; k > 0; --k) {  // L^H b = a : unit upper, (L^H)(j, k) = conj(L(k, j)) = conj(M[j n + k])
-    const double2 src = k < 32 ? x0 : x1;
-    const double2 bk = make_double2(__shfl_sync(0xffffffffu, src.x, k & 31), __shfl_sync(0xffffffffu, src.y, k & 31));
-    if (r0 < k) { const double2 l = M[(size_t)r0 * n + k]; x0 = cfnma2(x0, make_double2(l.x, -l.y), bk); }
-    if (r1 < k) { const double2 l = M[(size_t)r1 * n + k]; x1 = cfnma2(x1, make_double2(l.x, -l.y), bk); }
+  {  // L^H b = a : unit upper, (L^H)(j, k) = conj(L(k, j)) = conj(M[j n + k])
+    int k = n - 1;
+    for (; k - 3 > 0; k -= 4) {
+      double2 m0[4], m1[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { m0[t] = M[(size_t)c0 * n + k - t]; m1[t] = TWO ? M[(size_t)c1 * n + k - t] : m0[t]; }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int kk = k - t;
+        const double2 src = kk < 32 ? x0 : x1;
+        const double2 bk = make_double2(__shfl_sync(0xffffffffu, src.x, kk & 31), __shfl_sync(0xffffffffu, src.y, kk & 31));
+        if (r0 < kk) x0 = cfnma2(x0, make_double2(m0[t].x, -m0[t].y), bk);
+        if (TWO && r1 < kk) x1 = cfnma2(x1, make_double2(m1[t].x, -m1[t].y), bk);
+      }
+    }
+    for (; k > 0; --k) {
+      const double2 src = k < 32 ? x0 : x1;
+      const double2 bk = make_double2(__shfl_sync(0xffffffffu, src.x, k & 31), __shfl_sync(0xffffffffu, src.y, k & 31));
+      if (r0 < k) { const double2 l = M[(size_t)r0 * n + k]; x0 = cfnma2(x0, make_double2(l.x, -l.y), bk); }
+      if (TWO && r1 < k) { const double2 l = M[(size_t)r1 * n + k]; x1 = cfnma2(x1, make_double2(l.x, -l.y), bk); }
+    }
   }
   const int *perm = lu_perm(ipiv, n);  // P^T: the value at position r goes back to row perm[r]
   if (r0 < n) x[perm[r0]] = x0;
@@ -2590,20 +2737,32 @@ __device__ void w_solve_h(const double2 *M, int n, const int *ipiv, double2 *x) 
   __syncwarp();
 }
 
+template <bool TWO>
 __device__ void w_d2_matvec(const double *__restrict__ D2, int n, const double2 *x, double2 *y, bool transpose) {
+  // rows lane and lane + 32 in one sweep (each row's sum keeps its order j = 0, 1, ...): twice the table loads in flight
   const int lane = threadIdx.x & 31;
-  for (int i = lane; i < n; i += 32) {
-    double sr = 0.0, si = 0.0;
-    if (!transpose) {
-#pragma unroll 8
-      for (int j = 0; j < n; ++j) { const double d = __ldg(D2 + (size_t)j * n + i); sr = fma(d, x[j].x, sr); si = fma(d, x[j].y, si); }
-    } else {
-      const double *col = D2 + (size_t)i * n;
-#pragma unroll 8
-      for (int j = 0; j < n; ++j) { const double d = __ldg(col + j); sr = fma(d, x[j].x, sr); si = fma(d, x[j].y, si); }
+  const int i0 = min(lane, n - 1), i1 = min(lane + 32, n - 1);
+  double sr0 = 0.0, si0 = 0.0, sr1 = 0.0, si1 = 0.0;
+  if (!transpose) {
+#pragma unroll 16
+    for (int j = 0; j < n; ++j) {
+      const double d0 = __ldg(D2 + (size_t)j * n + i0);
+      const double2 xj = x[j];
+      sr0 = fma(d0, xj.x, sr0); si0 = fma(d0, xj.y, si0);
+      if (TWO) { const double d1 = __ldg(D2 + (size_t)j * n + i1); sr1 = fma(d1, xj.x, sr1); si1 = fma(d1, xj.y, si1); }
     }
-    y[i] = make_double2(sr, si);
+  } else {
+    const double *col0 = D2 + (size_t)i0 * n, *col1 = D2 + (size_t)i1 * n;
+#pragma unroll 16
+    for (int j = 0; j < n; ++j) {
+      const double d0 = __ldg(col0 + j);
+      const double2 xj = x[j];
+      sr0 = fma(d0, xj.x, sr0); si0 = fma(d0, xj.y, si0);
+      if (TWO) { const double d1 = __ldg(col1 + j); sr1 = fma(d1, xj.x, sr1); si1 = fma(d1, xj.y, si1); }
+    }
   }
+  if (lane < n) y[lane] = make_double2(sr0, si0);
+  if (TWO && lane + 32 < n) y[lane + 32] = make_double2(sr1, si1);
   __syncwarp();
 }
 
@@ -2615,6 +2774,7 @@ __device__ void w_start_vector(double2 *x, int n) {
   __syncwarp();
 }
 
+template <bool TWO>
 __device__ double2 w_inverse_iterate(const WarpShared &s, int n, const double *D2, const PencilCoef &p, double2 sigma,
                                      int maxit, double tol, int early, double *delta, int *iters, int *stalled = nullptr) {
   const int lane = threadIdx.x & 31;
@@ -2624,10 +2784,10 @@ __device__ double2 w_inverse_iterate(const WarpShared &s, int n, const double *D
   conv_reset(ct);
   int it = 0;
   for (; it < maxit; ++it) {
-    w_d2_matvec(D2, n, s.x, s.y, false);
+    w_d2_matvec<TWO>(D2, n, s.x, s.y, false);
     for (int i = lane; i < n; i += 32) s.y[i] = cadd2(cmul2(p.b2, s.y[i]), cmul2(p.b0, s.x[i]));
     __syncwarp();
-    w_solve(s.M, n, s.ipiv, s.y);
+    w_solve<TWO>(s.M, n, s.ipiv, s.y);
     double2 yx = make_double2(0.0, 0.0), yy = make_double2(0.0, 0.0);
     for (int i = lane; i < n; i += 32) {
       yx = cadd2(yx, cmulc2(s.y[i], s.x[i]));
@@ -2649,6 +2809,7 @@ __device__ double2 w_inverse_iterate(const WarpShared &s, int n, const double *D
   return om;
 }
 
+template <bool TWO>
 __global__ void __launch_bounds__(32) chan_eig_warp_kernel(const __grid_constant__ ChanArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int n = a.n, lane = threadIdx.x & 31;
@@ -2661,10 +2822,10 @@ __global__ void __launch_bounds__(32) chan_eig_warp_kernel(const __grid_constant
     double dl = 1.0e300;
     int total = 0;
     for (int o = 0; o < a.outer; ++o) {
-      w_assemble(s.M, n, a.D2, a.D4, a.u, a.d2u, p, sigma);
-      w_lu(s.M, n, s.ipiv);
+      w_assemble<TWO>(s.M, n, a.D2, a.D4, a.u, a.d2u, p, sigma);
+      w_lu<TWO>(s.M, n, s.ipiv);
       int it = 0, stalled = 0;
-      om = w_inverse_iterate(s, n, a.D2, p, sigma, a.inner, a.tol, a.early, &dl, &it, &stalled);
+      om = w_inverse_iterate<TWO>(s, n, a.D2, p, sigma, a.inner, a.tol, a.early, &dl, &it, &stalled);
       total += it;
       if (dl <= a.tol * hypot(om.x, om.y) || stalled) break;
       sigma = om;
@@ -2691,15 +2852,15 @@ __global__ void __launch_bounds__(32) chan_eig_warp_kernel(const __grid_constant
       }
       if (a.adj) {  // see chan_eig_body
         const double2 sg = make_double2(om.x + 1.0e-8 * hypot(om.x, om.y), om.y);
-        w_assemble(s.M, n, a.D2, a.D4, a.u, a.d2u, p, sg);
-        w_lu(s.M, n, s.ipiv);
+        w_assemble<TWO>(s.M, n, a.D2, a.D4, a.u, a.d2u, p, sg);
+        w_lu<TWO>(s.M, n, s.ipiv);
         for (int i = lane; i < n; i += 32) s.t[i] = make_double2(s.x[i].x, 0.3 - s.x[i].y);
         __syncwarp();
         for (int k = 0; k < 4; ++k) {
-          w_d2_matvec(a.D2, n, s.t, s.y, true);
+          w_d2_matvec<TWO>(a.D2, n, s.t, s.y, true);
           for (int i = lane; i < n; i += 32) s.y[i] = cadd2(cmulc2(p.b2, s.y[i]), cmulc2(p.b0, s.t[i]));
           __syncwarp();
-          w_solve_h(s.M, n, s.ipiv, s.y);
+          w_solve_h<TWO>(s.M, n, s.ipiv, s.y);
           double nn = 0.0;
           for (int i = lane; i < n; i += 32) nn += s.y[i].x * s.y[i].x + s.y[i].y * s.y[i].y;
           const double rn = rsqrt(wsum(make_double2(nn, 0.0)).x);
@@ -2714,7 +2875,7 @@ __global__ void __launch_bounds__(32) chan_eig_warp_kernel(const __grid_constant
           const double2 sc = cdiv2(make_double2(1.0, 0.0), make_double2(d.x, -d.y));
           for (int i = lane; i < n; i += 32) av[i + 1] = cmul2(sc, s.t[i]);
         } else {
-          w_d2_matvec(a.D2, n, s.t, s.y, true);
+          w_d2_matvec<TWO>(a.D2, n, s.t, s.y, true);
           double nn = 0.0, vb = -1.0;
           int vi = 0;
           for (int i = lane; i < n; i += 32) {
@@ -2744,6 +2905,7 @@ __global__ void __launch_bounds__(32) chan_eig_warp_kernel(const __grid_constant
   }
 }
 
+template <bool TWO>
 __global__ void __launch_bounds__(32) chan_neutral_warp_kernel(const __grid_constant__ NeutralArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const int n = a.n, lane = threadIdx.x & 31;
@@ -2759,18 +2921,18 @@ __global__ void __launch_bounds__(32) chan_neutral_warp_kernel(const __grid_cons
       w_start_vector(s.x, n);
       double dl = 1.0e300;
       for (int o = 0; o < 3; ++o) {
-        w_assemble(s.M, n, a.D2, a.D4, a.u, a.d2u, p, sigma);
-        w_lu(s.M, n, s.ipiv);
+        w_assemble<TWO>(s.M, n, a.D2, a.D4, a.u, a.d2u, p, sigma);
+        w_lu<TWO>(s.M, n, s.ipiv);
         int k = 0;
-        ev = w_inverse_iterate(s, n, a.D2, p, sigma, 8, 1.0e-14, a.early, &dl, &k);
+        ev = w_inverse_iterate<TWO>(s, n, a.D2, p, sigma, 8, 1.0e-14, a.early, &dl, &k);
         if (dl <= 1.0e-14 * hypot(ev.x, ev.y)) break;
         sigma = ev;
       }
       for (int i = lane; i < n; i += 32) s.t[i] = make_double2(s.x[i].x, -s.x[i].y + 0.3);
       __syncwarp();
       for (int k = 0; k < 6; ++k) {
-        w_solve_h(s.M, n, s.ipiv, s.t);
-        w_d2_matvec(a.D2, n, s.t, s.y, true);
+        w_solve_h<TWO>(s.M, n, s.ipiv, s.t);
+        w_d2_matvec<TWO>(a.D2, n, s.t, s.y, true);
         double nn = 0.0;
         for (int i = lane; i < n; i += 32) {
           const double2 v = cadd2(cmulc2(p.b2, s.y[i]), cmulc2(p.b0, s.t[i]));
@@ -2781,7 +2943,7 @@ __global__ void __launch_bounds__(32) chan_neutral_warp_kernel(const __grid_cons
         for (int i = lane; i < n; i += 32) s.t[i] = make_double2(s.t[i].x * rn, s.t[i].y * rn);
         __syncwarp();
       }
-      w_d2_matvec(a.D2, n, s.x, s.y, false);
+      w_d2_matvec<TWO>(a.D2, n, s.x, s.y, false);
       double2 dw = make_double2(0.0, 0.0), dalp = make_double2(0.0, 0.0);
       for (int i = lane; i < n; i += 32) {
         const double2 d2x = s.y[i], xi = s.x[i];
@@ -2934,7 +3096,7 @@ int chan_dense_max_n() {
 }
 
 cudaError_t chan_eig_grid(int n, int64_t ninst, int *grid, size_t *smem) {
-  if (use_warp_kernels(n)) return warp_grid(n, ninst, grid, smem, (const void *)chan_eig_warp_kernel);
+  if (use_warp_kernels(n)) return warp_grid(n, ninst, grid, smem, n > 32 ? (const void *)chan_eig_warp_kernel<true> : (const void *)chan_eig_warp_kernel<false>);
   if (use_big_kernel(n)) {
     const int v = big_variant(n);
     if (v == 2) return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel_big2, CH_THREADS, 2);
@@ -2945,7 +3107,7 @@ cudaError_t chan_eig_grid(int n, int64_t ninst, int *grid, size_t *smem) {
   return chan_grid(n, ninst, grid, smem, (const void *)chan_eig_kernel);
 }
 cudaError_t chan_neutral_grid(int n, int64_t ninst, int *grid, size_t *smem) {
-  if (use_warp_kernels(n)) return warp_grid(n, ninst, grid, smem, (const void *)chan_neutral_warp_kernel);
+  if (use_warp_kernels(n)) return warp_grid(n, ninst, grid, smem, n > 32 ? (const void *)chan_neutral_warp_kernel<true> : (const void *)chan_neutral_warp_kernel<false>);
   return chan_grid(n, ninst, grid, smem, (const void *)chan_neutral_kernel);
 }
 
@@ -2959,7 +3121,10 @@ cudaError_t launch_chan_eig(int n, const double *D2, const double *D4, const dou
   a.alpha = alpha; a.Re = Re; a.sigma = sigma; a.outer = outer; a.inner = inner; a.tol = tol;
   a.omega = omega; a.delta = delta; a.iters = iters; a.evec = evec; a.adj = adj; a.adj_form = adj_form;
   a.early = getenv("OSB_NO_EARLY_STOP") ? 0 : 1;
-  if (use_warp_kernels(n)) chan_eig_warp_kernel<<<grid, 32, smem, st>>>(a);
+  if (use_warp_kernels(n)) {
+    if (n > 32) chan_eig_warp_kernel<true><<<grid, 32, smem, st>>>(a);
+    else chan_eig_warp_kernel<false><<<grid, 32, smem, st>>>(a);
+  }
   else if (use_big_kernel(n)) {
     const int v = big_variant(n);
     if (v == 2) chan_eig_kernel_big2<<<grid, CH_THREADS, smem, st>>>(a);
@@ -2981,7 +3146,10 @@ cudaError_t launch_chan_neutral(int n, const double *D2, const double *D4, const
   a.Re = Re; a.alpha0 = alpha0; a.sigma0 = sigma0; a.sfac = sfac; a.tol = tol; a.maxit = maxit;
   a.alpha_out = alpha_out; a.omega_out = omega_out; a.steps = steps; a.status = status; a.trace = trace;
   a.early = getenv("OSB_NO_EARLY_STOP") ? 0 : 1;
-  if (use_warp_kernels(n)) chan_neutral_warp_kernel<<<grid, 32, smem, st>>>(a);
+  if (use_warp_kernels(n)) {
+    if (n > 32) chan_neutral_warp_kernel<true><<<grid, 32, smem, st>>>(a);
+    else chan_neutral_warp_kernel<false><<<grid, 32, smem, st>>>(a);
+  }
   else chan_neutral_kernel<<<grid, CH_THREADS, smem, st>>>(a);
   return cudaGetLastError();
 }
