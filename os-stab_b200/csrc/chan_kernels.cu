@@ -2494,11 +2494,15 @@ __device__ void w_lu(double2 *M, int n, int *ipiv) {
       if (a0 > best) { best = a0; bi = r0; }
       if (a1 > best) { best = a1; bi = r1; }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const long long ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    {
+      // warp maximum of the 64-bit key, lowest row on ties, by three integer reductions (redux.sync) instead of five
+      // rounds of three shuffles: high words, then low words among the lanes that hold the maximal high word, then the
+      // smallest row among the lanes that hold the maximum.  key + 1 maps "no candidate" (-1) to 0.
+      const unsigned long long key = (unsigned long long)(best + 1);
+      const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+      const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+      const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+      bi = (int)__reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? (unsigned)bi : 0xffffffffu);
     }
     if (lane == 0) {
       ipiv[k] = bi;
@@ -2525,60 +2529,43 @@ __device__ void w_lu(double2 *M, int n, int *ipiv) {
     double2 l0 = make_double2(0.0, 0.0), l1 = l0;
     if (a0) { l0 = cmul2(ck[r0], rinv); ck[r0] = l0; }
     if (a1) { l1 = cmul2(ck[r1], rinv); ck[r1] = l1; }
+    // eight columns per trip; the last trip of a column step is masked (column index clamped for the loads, stores
+    // predicated) rather than finished one column at a time -- a single-column trip exposes the same round trip
     int j = k + 1;
     if (!TWO) {    // one row per lane
-      for (; j + 7 < n; j += 8) {
-        double2 *c = M + (size_t)j * n;
+      for (; j < n; j += 8) {
         double2 uu[8], ma[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { uu[t] = c[t * n + k]; ma[t] = c[t * n + q0]; }
+        for (int t = 0; t < 8; ++t) { const double2 *c = M + (size_t)min(j + t, n - 1) * n; uu[t] = c[k]; ma[t] = c[q0]; }
 #pragma unroll
         for (int t = 0; t < 8; ++t) ma[t] = cfnma2(ma[t], l0, uu[t]);
 #pragma unroll
         for (int t = 0; t < 8; ++t)
-          if (a0) c[t * n + r0] = ma[t];
-      }
-      for (; j < n; ++j) {
-        double2 *c = M + (size_t)j * n;
-        const double2 uu = c[k], ma = c[q0];
-        if (a0) c[r0] = cfnma2(ma, l0, uu);
+          if (a0 && j + t < n) M[(size_t)(j + t) * n + r0] = ma[t];
       }
     } else if (k < 31) {  // some lanes still own two rows below the pivot
-      for (; j + 7 < n; j += 8) {
-        double2 *c = M + (size_t)j * n;
+      for (; j < n; j += 8) {
         double2 uu[8], ma[8], mb[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { uu[t] = c[t * n + k]; ma[t] = c[t * n + q0]; mb[t] = c[t * n + q1]; }
+        for (int t = 0; t < 8; ++t) { const double2 *c = M + (size_t)min(j + t, n - 1) * n; uu[t] = c[k]; ma[t] = c[q0]; mb[t] = c[q1]; }
 #pragma unroll
         for (int t = 0; t < 8; ++t) { ma[t] = cfnma2(ma[t], l0, uu[t]); mb[t] = cfnma2(mb[t], l1, uu[t]); }
 #pragma unroll
         for (int t = 0; t < 8; ++t) {
-          if (a0) c[t * n + r0] = ma[t];
-          if (a1) c[t * n + r1] = mb[t];
+          if (a0 && j + t < n) M[(size_t)(j + t) * n + r0] = ma[t];
+          if (a1 && j + t < n) M[(size_t)(j + t) * n + r1] = mb[t];
         }
       }
-      for (; j < n; ++j) {
-        double2 *c = M + (size_t)j * n;
-        const double2 uu = c[k], ma = c[q0], mb = c[q1];
-        if (a0) c[r0] = cfnma2(ma, l0, uu);
-        if (a1) c[r1] = cfnma2(mb, l1, uu);
-      }
     } else {       // only the rows lane + 32 are left
-      for (; j + 7 < n; j += 8) {
-        double2 *c = M + (size_t)j * n;
+      for (; j < n; j += 8) {
         double2 uu[8], mb[8];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { uu[t] = c[t * n + k]; mb[t] = c[t * n + q1]; }
+        for (int t = 0; t < 8; ++t) { const double2 *c = M + (size_t)min(j + t, n - 1) * n; uu[t] = c[k]; mb[t] = c[q1]; }
 #pragma unroll
         for (int t = 0; t < 8; ++t) mb[t] = cfnma2(mb[t], l1, uu[t]);
 #pragma unroll
         for (int t = 0; t < 8; ++t)
-          if (a1) c[t * n + r1] = mb[t];
-      }
-      for (; j < n; ++j) {
-        double2 *c = M + (size_t)j * n;
-        const double2 uu = c[k], mb = c[q1];
-        if (a1) c[r1] = cfnma2(mb, l1, uu);
+          if (a1 && j + t < n) M[(size_t)(j + t) * n + r1] = mb[t];
       }
     }
     __syncwarp();
