@@ -2450,18 +2450,27 @@ __device__ void w_assemble(double2 *M, int n, const double *__restrict__ D2, con
   const bool h0 = lane < n, h1 = TWO && lane + 32 < n;
   const double2 w2a = csub2(coef_w2(p, u[i0]), sb2), w2b = csub2(coef_w2(p, u[i1]), sb2);
   const double2 w0a = csub2(coef_w0(p, u[i0], d2u[i0]), sb0), w0b = csub2(coef_w0(p, u[i1], d2u[i1]), sb0);
-#pragma unroll 8
-  for (int j = 0; j < n; ++j) {
-    const size_t e0 = (size_t)j * n + i0, e1 = (size_t)j * n + i1;
-    const double d2a = __ldg(D2 + e0), d4a = __ldg(D4 + e0);
-    double2 va = make_double2(fma(w2a.x, d2a, d4a), w2a.y * d2a);
-    if (i0 == j) va = cadd2(va, w0a);
-    if (h0) M[e0] = va;
-    if (TWO) {
-      const double d2b = __ldg(D2 + e1), d4b = __ldg(D4 + e1);
-      double2 vb = make_double2(fma(w2b.x, d2b, d4b), w2b.y * d2b);
-      if (i1 == j) vb = cadd2(vb, w0b);
-      if (h1) M[e1] = vb;
+  for (int j = 0; j < n; j += 8) {  // eight columns per trip, table loads first; the last trip is masked
+    double d2a[8], d4a[8], d2b[8], d4b[8];
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const size_t c = (size_t)min(j + t, n - 1) * n;
+      d2a[t] = __ldg(D2 + c + i0); d4a[t] = __ldg(D4 + c + i0);
+      if (TWO) { d2b[t] = __ldg(D2 + c + i1); d4b[t] = __ldg(D4 + c + i1); }
+    }
+#pragma unroll
+    for (int t = 0; t < 8; ++t) {
+      const int jt = j + t;
+      if (jt < n) {
+        double2 va = make_double2(fma(w2a.x, d2a[t], d4a[t]), w2a.y * d2a[t]);
+        if (i0 == jt) va = cadd2(va, w0a);
+        if (h0) M[(size_t)jt * n + i0] = va;
+        if (TWO) {
+          double2 vb = make_double2(fma(w2b.x, d2b[t], d4b[t]), w2b.y * d2b[t]);
+          if (i1 == jt) vb = cadd2(vb, w0b);
+          if (h1) M[(size_t)jt * n + i1] = vb;
+        }
+      }
     }
   }
   __syncwarp();
@@ -2726,27 +2735,29 @@ __device__ void w_solve_h(const double2 *M, int n, const int *ipiv, double2 *x) 
 
 template <bool TWO>
 __device__ void w_d2_matvec(const double *__restrict__ D2, int n, const double2 *x, double2 *y, bool transpose) {
-  // rows lane and lane + 32 in one sweep (each row's sum keeps its order j = 0, 1, ...): twice the table loads in flight
+  // Rows lane and lane + 32 in one sweep; each row's sum keeps its order j = 0, 1, ...  The table comes from the L2 (the
+  // matrices leave the L1 no room), so the loads are issued sixteen columns at a time ahead of the sums, and the last
+  // block is masked (index clamped, sums predicated) instead of left to a one-column-per-round-trip remainder loop.
   const int lane = threadIdx.x & 31;
   const int i0 = min(lane, n - 1), i1 = min(lane + 32, n - 1);
   double sr0 = 0.0, si0 = 0.0, sr1 = 0.0, si1 = 0.0;
-  if (!transpose) {
-#pragma unroll 16
-    for (int j = 0; j < n; ++j) {
-      const double d0 = __ldg(D2 + (size_t)j * n + i0);
-      const double2 xj = x[j];
-      sr0 = fma(d0, xj.x, sr0); si0 = fma(d0, xj.y, si0);
-      if (TWO) { const double d1 = __ldg(D2 + (size_t)j * n + i1); sr1 = fma(d1, xj.x, sr1); si1 = fma(d1, xj.y, si1); }
+  const size_t s0 = transpose ? (size_t)i0 * n : (size_t)i0, s1 = transpose ? (size_t)i1 * n : (size_t)i1;
+  const size_t sj = transpose ? 1 : (size_t)n;   // D2[j n + i] or, transposed, D2[i n + j]
+  for (int j = 0; j < n; j += 16) {
+    double d0[16], d1[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+      const size_t jj = (size_t)min(j + t, n - 1) * sj;
+      d0[t] = __ldg(D2 + s0 + jj);
+      if (TWO) d1[t] = __ldg(D2 + s1 + jj);
     }
-  } else {
-    const double *col0 = D2 + (size_t)i0 * n, *col1 = D2 + (size_t)i1 * n;
-#pragma unroll 16
-    for (int j = 0; j < n; ++j) {
-      const double d0 = __ldg(col0 + j);
-      const double2 xj = x[j];
-      sr0 = fma(d0, xj.x, sr0); si0 = fma(d0, xj.y, si0);
-      if (TWO) { const double d1 = __ldg(col1 + j); sr1 = fma(d1, xj.x, sr1); si1 = fma(d1, xj.y, si1); }
-    }
+#pragma unroll
+    for (int t = 0; t < 16; ++t)
+      if (j + t < n) {
+        const double2 xj = x[j + t];
+        sr0 = fma(d0[t], xj.x, sr0); si0 = fma(d0[t], xj.y, si0);
+        if (TWO) { sr1 = fma(d1[t], xj.x, sr1); si1 = fma(d1[t], xj.y, si1); }
+      }
   }
   if (lane < n) y[lane] = make_double2(sr0, si0);
   if (TWO && lane + 32 < n) y[lane + 32] = make_double2(sr1, si1);
