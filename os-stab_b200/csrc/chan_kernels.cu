@@ -2477,104 +2477,158 @@ __device__ void w_assemble(double2 *M, int n, const double *__restrict__ D2, con
 }
 
 // Partial-pivoting LU of the shared-memory matrix by one warp; lane l owns rows l and l + 32.  The warp is alone on its
-// scheduler, so what counts is the latency of its own instruction stream (SASS-level stall attribution of round 2,
-// tools/capture_source.sh): the trailing update takes eight columns per trip with ALL loads first -- the compiler cannot
-// move the loads of the next columns above the stores of these (it cannot prove that pivot-row entries and the rows
-// being written do not alias), so every trip exposes one shared-memory round trip, and a trip now carries both rows
-// and eight columns instead of one row and four; pivot scan and row interchange are branch-free over the lane's two
-// entries.  Same operations on every entry, same pivots.
+// scheduler and three warps share the SM's shared-memory pipe, so two things count (SASS-level stall attribution of
+// round 2, tools/capture_source.sh): the latency of the warp's own instruction stream, and shared-memory traffic --
+// a rank-1 update reads and writes the trailing matrix once per pivot (16 LDS.128 + 16 STS.128 against 64 DFMAs per
+// trip: the three warps' 384 cycles of shared-memory pipe per trip against 144 cycles of FP64 pipe each).  Hence
+// FOUR pivots per visit of the trailing matrix:
+//   * the four panel columns are factorised column by column as before (pivot search by three redux.sync reductions,
+//     branch-free over the lane's two entries; interchange over ALL columns; multipliers; rank-1 update of the panel's
+//     remaining <= 3 columns only);
+//   * the pivot rows' entries in the trailing columns (U12 = L11^{-1} A12) are finished with a lane per column;
+//   * every row below the panel then receives its four updates in registers: one load and one store per entry and
+//     four pivots, eight complex FMAs per loaded pair, all loads of a trip first (the compiler cannot move loads above
+//     the stores of the previous columns: it cannot prove that pivot-row entries and updated rows do not alias).
+// Every entry receives the same updates with the same operands in the same order k = 0, 1, ... as in the unblocked
+// right-looking elimination: same pivots, same bits.
 template <bool TWO>
 __device__ void w_lu(double2 *M, int n, int *ipiv) {
+  constexpr int NB = 4;
   const int lane = threadIdx.x & 31;
   int *perm = lu_perm(ipiv, n);
   for (int i = lane; i < n; i += 32) perm[i] = i;
   __syncwarp();
   const int r0 = lane, r1 = lane + 32;
-  for (int k = 0; k < n; ++k) {
-    double2 *ck = M + (size_t)k * n;
-    // pivot search on the bit patterns (non-negative doubles order like their bits; ties to the lower row as IZAMAX)
-    long long best = -1;
-    int bi = k;
-    {
-      const bool h0 = r0 >= k && r0 < n, h1 = TWO && r1 >= k && r1 < n;
-      const double2 v0 = ck[h0 ? r0 : k], v1 = TWO ? ck[h1 ? r1 : k] : v0;
-      const long long a0 = h0 ? (__double_as_longlong(fabs(v0.x) + fabs(v0.y)) & 0x7fffffffffffffffll) : -1ll;
-      const long long a1 = h1 ? (__double_as_longlong(fabs(v1.x) + fabs(v1.y)) & 0x7fffffffffffffffll) : -1ll;
-      if (a0 > best) { best = a0; bi = r0; }
-      if (a1 > best) { best = a1; bi = r1; }
+  for (int k0 = 0; k0 < n; k0 += NB) {
+    const int ke = min(k0 + NB, n);  // panel columns k0 .. ke - 1
+    for (int k = k0; k < ke; ++k) {
+      double2 *ck = M + (size_t)k * n;
+      // pivot search on the bit patterns (non-negative doubles order like their bits; ties to the lower row as IZAMAX)
+      long long best = -1;
+      int bi = k;
+      {
+        const bool h0 = r0 >= k && r0 < n, h1 = TWO && r1 >= k && r1 < n;
+        const double2 v0 = ck[h0 ? r0 : k], v1 = TWO ? ck[h1 ? r1 : k] : v0;
+        const long long a0 = h0 ? (__double_as_longlong(fabs(v0.x) + fabs(v0.y)) & 0x7fffffffffffffffll) : -1ll;
+        const long long a1 = h1 ? (__double_as_longlong(fabs(v1.x) + fabs(v1.y)) & 0x7fffffffffffffffll) : -1ll;
+        if (a0 > best) { best = a0; bi = r0; }
+        if (a1 > best) { best = a1; bi = r1; }
+      }
+      {
+        // warp maximum of the 64-bit key, lowest row on ties, by three integer reductions (redux.sync) instead of five
+        // rounds of three shuffles: high words, then low words among the lanes that hold the maximal high word, then
+        // the smallest row among the lanes that hold the maximum.  key + 1 maps "no candidate" (-1) to 0.
+        const unsigned long long key = (unsigned long long)(best + 1);
+        const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        bi = (int)__reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? (unsigned)bi : 0xffffffffu);
+      }
+      if (lane == 0) {
+        ipiv[k] = bi;
+        const int ta = perm[k];
+        perm[k] = perm[bi];
+        perm[bi] = ta;
+      }
+      if (bi != k) {  // interchange rows k and bi: columns lane and lane + 32
+        const int j0 = min(r0, n - 1), j1 = min(r1, n - 1);
+        double2 *c0 = M + (size_t)j0 * n, *c1 = M + (size_t)j1 * n;
+        const double2 t0 = c0[k], b0 = c0[bi];
+        double2 t1 = t0, b1 = b0;
+        if (TWO) { t1 = c1[k]; b1 = c1[bi]; }
+        if (r0 < n) { c0[k] = b0; c0[bi] = t0; }
+        if (TWO && r1 < n) { c1[k] = b1; c1[bi] = t1; }
+      }
+      __syncwarp();
+      double2 piv = ck[k];
+      if (piv.x == 0.0 && piv.y == 0.0) piv = make_double2(1.0e-290, 0.0);
+      const double pinv = 1.0 / fma(piv.x, piv.x, piv.y * piv.y);  // one division in the column's serial chain
+      const double2 rinv = make_double2(piv.x * pinv, -piv.y * pinv);
+      const bool a0 = r0 > k && r0 < n, a1 = TWO && r1 > k && r1 < n;
+      const int q0 = a0 ? r0 : k, q1 = a1 ? r1 : k;  // rows to read where a lane has nothing to update (never stored)
+      double2 l0 = make_double2(0.0, 0.0), l1 = l0;
+      if (a0) { l0 = cmul2(ck[r0], rinv); ck[r0] = l0; }
+      if (a1) { l1 = cmul2(ck[r1], rinv); ck[r1] = l1; }
+      if (k + 1 < ke) {  // the panel's remaining columns (<= 3): loads first
+        double2 uu[NB - 1], ma[NB - 1], mb[NB - 1];
+#pragma unroll
+        for (int t = 0; t < NB - 1; ++t) {
+          const double2 *c = M + (size_t)min(k + 1 + t, ke - 1) * n;
+          uu[t] = c[k]; ma[t] = c[q0]; mb[t] = TWO ? c[q1] : ma[t];
+        }
+#pragma unroll
+        for (int t = 0; t < NB - 1; ++t)
+          if (k + 1 + t < ke) {
+            double2 *c = M + (size_t)(k + 1 + t) * n;
+            if (a0) c[r0] = cfnma2(ma[t], l0, uu[t]);
+            if (a1) c[r1] = cfnma2(mb[t], l1, uu[t]);
+          }
+      }
+      __syncwarp();
     }
-    {
-      // warp maximum of the 64-bit key, lowest row on ties, by three integer reductions (redux.sync) instead of five
-      // rounds of three shuffles: high words, then low words among the lanes that hold the maximal high word, then the
-      // smallest row among the lanes that hold the maximum.  key + 1 maps "no candidate" (-1) to 0.
-      const unsigned long long key = (unsigned long long)(best + 1);
-      const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
-      const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
-      const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
-      bi = (int)__reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? (unsigned)bi : 0xffffffffu);
-    }
-    if (lane == 0) {
-      ipiv[k] = bi;
-      const int ta = perm[k];
-      perm[k] = perm[bi];
-      perm[bi] = ta;
-    }
-    if (bi != k) {  // interchange rows k and bi: columns lane and lane + 32
-      const int j0 = min(r0, n - 1), j1 = min(r1, n - 1);
-      double2 *c0 = M + (size_t)j0 * n, *c1 = M + (size_t)j1 * n;
-      const double2 t0 = c0[k], b0 = c0[bi];
-      double2 t1 = t0, b1 = b0;
-      if (TWO) { t1 = c1[k]; b1 = c1[bi]; }
-      if (r0 < n) { c0[k] = b0; c0[bi] = t0; }
-      if (TWO && r1 < n) { c1[k] = b1; c1[bi] = t1; }
+    if (ke >= n) break;  // (a ragged last panel has no trailing columns)
+    // ---- pivot rows k0+1 .. k0+3 in the trailing columns: U12 = L11^{-1} A12, a lane per column
+    for (int j = ke + lane; j < n; j += 32) {
+      double2 *c = M + (size_t)j * n;
+      double2 u[NB];
+#pragma unroll
+      for (int cc = 0; cc < NB; ++cc) u[cc] = c[k0 + cc];
+#pragma unroll
+      for (int cc = 1; cc < NB; ++cc) {
+#pragma unroll
+        for (int d = 0; d < cc; ++d) u[cc] = cfnma2(u[cc], M[(size_t)(k0 + d) * n + k0 + cc], u[d]);
+        c[k0 + cc] = u[cc];
+      }
     }
     __syncwarp();
-    double2 piv = ck[k];
-    if (piv.x == 0.0 && piv.y == 0.0) piv = make_double2(1.0e-290, 0.0);
-    const double pinv = 1.0 / fma(piv.x, piv.x, piv.y * piv.y);  // one division in the column's serial chain
-    const double2 rinv = make_double2(piv.x * pinv, -piv.y * pinv);
-    const bool a0 = r0 > k && r0 < n, a1 = TWO && r1 > k && r1 < n;
-    const int q0 = a0 ? r0 : k, q1 = a1 ? r1 : k;  // rows to read where a lane has nothing to update (never stored)
-    double2 l0 = make_double2(0.0, 0.0), l1 = l0;
-    if (a0) { l0 = cmul2(ck[r0], rinv); ck[r0] = l0; }
-    if (a1) { l1 = cmul2(ck[r1], rinv); ck[r1] = l1; }
-    // eight columns per trip; the last trip of a column step is masked (column index clamped for the loads, stores
-    // predicated) rather than finished one column at a time -- a single-column trip exposes the same round trip
-    int j = k + 1;
-    if (!TWO) {    // one row per lane
-      for (; j < n; j += 8) {
-        double2 uu[8], ma[8];
+    // ---- rows below the panel: four updates per visit
+    const bool b0 = r0 >= ke && r0 < n, b1 = TWO && r1 >= ke && r1 < n;
+    const int q0 = b0 ? r0 : k0, q1 = b1 ? r1 : k0;
+    double2 l0[NB], l1[NB];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { const double2 *c = M + (size_t)min(j + t, n - 1) * n; uu[t] = c[k]; ma[t] = c[q0]; }
+    for (int cc = 0; cc < NB; ++cc) {
+      l0[cc] = M[(size_t)(k0 + cc) * n + q0];
+      l1[cc] = TWO ? M[(size_t)(k0 + cc) * n + q1] : l0[cc];
+    }
+    if (!TWO || ke > 31) {  // one row per lane left: r0 (n <= 32) or r1
+      const bool bb = TWO ? b1 : b0;
+      const int qq = TWO ? q1 : q0, rr = TWO ? r1 : r0;
+      for (int j = ke; j < n; j += 4) {
+        double2 uu[4][NB], mm[4];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) ma[t] = cfnma2(ma[t], l0, uu[t]);
+        for (int t = 0; t < 4; ++t) {
+          const double2 *c = M + (size_t)min(j + t, n - 1) * n;
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
-          if (a0 && j + t < n) M[(size_t)(j + t) * n + r0] = ma[t];
-      }
-    } else if (k < 31) {  // some lanes still own two rows below the pivot
-      for (; j < n; j += 8) {
-        double2 uu[8], ma[8], mb[8];
-#pragma unroll
-        for (int t = 0; t < 8; ++t) { const double2 *c = M + (size_t)min(j + t, n - 1) * n; uu[t] = c[k]; ma[t] = c[q0]; mb[t] = c[q1]; }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) { ma[t] = cfnma2(ma[t], l0, uu[t]); mb[t] = cfnma2(mb[t], l1, uu[t]); }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          if (a0 && j + t < n) M[(size_t)(j + t) * n + r0] = ma[t];
-          if (a1 && j + t < n) M[(size_t)(j + t) * n + r1] = mb[t];
+          for (int cc = 0; cc < NB; ++cc) uu[t][cc] = c[k0 + cc];
+          mm[t] = c[qq];
         }
+#pragma unroll
+        for (int cc = 0; cc < NB; ++cc)
+#pragma unroll
+          for (int t = 0; t < 4; ++t) mm[t] = cfnma2(mm[t], TWO ? l1[cc] : l0[cc], uu[t][cc]);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (bb && j + t < n) M[(size_t)(j + t) * n + rr] = mm[t];
       }
-    } else {       // only the rows lane + 32 are left
-      for (; j < n; j += 8) {
-        double2 uu[8], mb[8];
+    } else {
+      for (int j = ke; j < n; j += 4) {
+        double2 uu[4][NB], ma[4], mb[4];
 #pragma unroll
-        for (int t = 0; t < 8; ++t) { const double2 *c = M + (size_t)min(j + t, n - 1) * n; uu[t] = c[k]; mb[t] = c[q1]; }
+        for (int t = 0; t < 4; ++t) {
+          const double2 *c = M + (size_t)min(j + t, n - 1) * n;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) mb[t] = cfnma2(mb[t], l1, uu[t]);
+          for (int cc = 0; cc < NB; ++cc) uu[t][cc] = c[k0 + cc];
+          ma[t] = c[q0]; mb[t] = c[q1];
+        }
 #pragma unroll
-        for (int t = 0; t < 8; ++t)
-          if (a1 && j + t < n) M[(size_t)(j + t) * n + r1] = mb[t];
+        for (int cc = 0; cc < NB; ++cc)
+#pragma unroll
+          for (int t = 0; t < 4; ++t) { ma[t] = cfnma2(ma[t], l0[cc], uu[t][cc]); mb[t] = cfnma2(mb[t], l1[cc], uu[t][cc]); }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          if (b0 && j + t < n) M[(size_t)(j + t) * n + r0] = ma[t];
+          if (b1 && j + t < n) M[(size_t)(j + t) * n + r1] = mb[t];
+        }
       }
     }
     __syncwarp();
