@@ -1936,6 +1936,7 @@ __device__ __forceinline__ double2 band_entry_c(const BandArgs &a, const PencilC
 template <int BCH, int MINB>
 __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(const __grid_constant__ BandArgs a) {
   typedef BandStage<BCH> Stage;
+  constexpr int RT = MINB >= 3 ? 2 : 4;  // rows per lane and trip of the vector loops (B x, inner products)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t inst0 = ((int64_t)blockIdx.x * BWW + warp) * BG;
@@ -2065,18 +2066,33 @@ __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(con
         if (!on) continue;
         const double2 *xg = a.x + (size_t)(inst0 + gp) * n;
         double2 *yg = a.y + (size_t)(inst0 + gp) * n;
-        for (int r = lane; r < n; r += 32) {
-          double sr = 0.0, si = 0.0;
+        // RT rows per lane and trip (four, or two in the register-limited builds), all loads first: x, y and the band table come from the L2 / DRAM and a trip
+        // exposes one round trip (the SASS-level stall attribution had 13 % of the deck-sized kernel waiting here)
+        for (int r0 = lane; r0 < n; r0 += 32 * RT) {
+          double dd[RT][5];
+          double2 xc[RT][5];
 #pragma unroll
-          for (int dc = -2; dc <= 2; ++dc) {
-            const int c = r + dc;
-            if (c >= 0 && c < n) {
-              const double dd = a.band24[(size_t)r * BW + BKL + dc].x;
-              const double2 xc = xg[c];
-              sr = fma(dd, xc.x, sr); si = fma(dd, xc.y, si);
+          for (int t = 0; t < RT; ++t) {
+            const int r = min(r0 + 32 * t, n - 1);
+#pragma unroll
+            for (int dc = -2; dc <= 2; ++dc) {
+              dd[t][dc + 2] = a.band24[(size_t)r * BW + BKL + dc].x;
+              xc[t][dc + 2] = xg[min(max(r + dc, 0), n - 1)];
             }
           }
-          yg[r] = cadd2(cmul2(b2, make_double2(sr, si)), cmul2(b0, xg[r]));
+#pragma unroll
+          for (int t = 0; t < RT; ++t) {
+            const int r = r0 + 32 * t;
+            if (r < n) {
+              double sr = 0.0, si = 0.0;
+#pragma unroll
+              for (int dc = -2; dc <= 2; ++dc) {
+                const int c = r + dc;
+                if (c >= 0 && c < n) { sr = fma(dd[t][dc + 2], xc[t][dc + 2].x, sr); si = fma(dd[t][dc + 2], xc[t][dc + 2].y, si); }
+              }
+              yg[r] = cadd2(cmul2(b2, make_double2(sr, si)), cmul2(b0, xc[t][2]));
+            }
+          }
         }
       }
       __syncwarp();
@@ -2181,15 +2197,29 @@ __global__ void __launch_bounds__(BWW * 32, MINB) chan_fd_banded_warp_kernel(con
         double2 *xg = a.x + (size_t)(inst0 + gp) * n;
         const double2 *yg = a.y + (size_t)(inst0 + gp) * n;
         double yxr = 0.0, yxi = 0.0, yy = 0.0;
-        for (int i = lane; i < n; i += 32) {
-          const double2 v = yg[i], xo = xg[i];
-          const double2 t = cmulc2(v, xo);
-          yxr += t.x; yxi += t.y;
-          yy += v.x * v.x + v.y * v.y;
+        // RT rows per lane and trip, loads first; the sums keep their order i = lane, lane + 32, ...
+        for (int i0 = lane; i0 < n; i0 += 32 * RT) {
+          double2 v[RT], xo[RT];
+#pragma unroll
+          for (int t = 0; t < RT; ++t) { const int i = min(i0 + 32 * t, n - 1); v[t] = yg[i]; xo[t] = xg[i]; }
+#pragma unroll
+          for (int t = 0; t < RT; ++t)
+            if (i0 + 32 * t < n) {
+              const double2 tt = cmulc2(v[t], xo[t]);
+              yxr += tt.x; yxi += tt.y;
+              yy += v[t].x * v[t].x + v[t].y * v[t].y;
+            }
         }
         yxr = warp_sum(yxr); yxi = warp_sum(yxi); yy = warp_sum(yy);
         const double rn = rsqrt(yy);
-        for (int i = lane; i < n; i += 32) xg[i] = make_double2(yg[i].x * rn, yg[i].y * rn);
+        for (int i0 = lane; i0 < n; i0 += 32 * RT) {
+          double2 v[RT];
+#pragma unroll
+          for (int t = 0; t < RT; ++t) v[t] = yg[min(i0 + 32 * t, n - 1)];
+#pragma unroll
+          for (int t = 0; t < RT; ++t)
+            if (i0 + 32 * t < n) xg[i0 + 32 * t] = make_double2(v[t].x * rn, v[t].y * rn);
+        }
         if (g == gp) { myyx = yxr; myyxi = yxi; myyy = yy; }
       }
       __syncwarp();
