@@ -598,8 +598,24 @@ def test_pair_kernel_equals_plain_kernel_bitwise(engine, osb, bl, monkeypatch):
     r = both(lambda: engine.shoot_spatial_lines(opts, p, Re, np.full(5, complex(0.042, 0.0)) * fact,
                                                 np.full(5, 0.002) * fact,
                                                 np.full(5, complex(0.13809592, 0.0051958399)) * fact, 12))
-    p.free()
     assert np.all(r["status"] == 0)
+    # points that do NOT converge inside a line: every form must report the same status per (line, omega) and seed the
+    # next omega from the same value -- a pass budget of 3 (every point ends by maxcount) and a line started far from
+    # any mode (non-finite or maxcount along the way)
+    opts.maxcount = 3
+    r = both(lambda: engine.shoot_spatial_lines(opts, p, Re, np.full(5, complex(0.042, 0.0)) * fact,
+                                                np.full(5, 0.002) * fact,
+                                                np.full(5, complex(0.13809592, 0.0051958399)) * fact, 6))
+    assert np.all(r["status"] == osb.ST_MAXCOUNT) and np.all(r["passes"] == 3)
+    opts.maxcount = 12
+    a0 = np.full(5, complex(0.13809592, 0.0051958399)) * fact
+    a0[1] = complex(2.5, -1.5)   # nowhere near a mode
+    a0[3] = complex(1.0e-9, 0.0)  # c = omega / alpha overflows the asymptotes
+    r = both(lambda: engine.shoot_spatial_lines(opts, p, Re, np.full(5, complex(0.042, 0.0)) * fact,
+                                                np.full(5, 0.002) * fact, a0, 6))
+    assert (r["status"][[0, 4]] == 0).all()
+    assert (r["status"][[1, 3]] != 0).any()
+    p.free()
 
 
 def test_device_allocation_failure_is_reported_and_recoverable(engine, osb, bl):
