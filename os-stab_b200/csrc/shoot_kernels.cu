@@ -1229,7 +1229,9 @@ cudaError_t launch_shoot(const ShootArgs &a, int integrator, int analytic_inprod
     if (nlaunch) *nlaunch += 1;
     return launch_shoot_queue(a, integrator, analytic_inprod, queue_counter, st);
   }
-  if (a.nlines <= 148 * 64 && !getenv("OSB_NO_PAIR")) {
+  int64_t pair_max = 148 * 64;
+  if (const char *e = getenv("OSB_PAIR_MAX")) pair_max = atoll(e);  // measurement knob
+  if (a.nlines <= pair_max && !getenv("OSB_NO_PAIR")) {
     const int threads = 64;
     // Single solves in batches that already give every scheduler a full warp gain nothing from the speculative step
     // (4096 contebl points: 318 k eig/s in the plain form against 312 k); OSB_PAIR_V1=1 / =0 forces either form.
