@@ -1233,9 +1233,18 @@ cudaError_t launch_shoot(const ShootArgs &a, int integrator, int analytic_inprod
   if (const char *e = getenv("OSB_PAIR_MAX")) pair_max = atoll(e);  // measurement knob
   if (a.nlines <= pair_max && !getenv("OSB_NO_PAIR")) {
     const int threads = 64;
-    // Single solves in batches that already give every scheduler a full warp gain nothing from the speculative step
-    // (4096 contebl points: 318 k eig/s in the plain form against 312 k); OSB_PAIR_V1=1 / =0 forces either form.
-    bool v1 = a.niter == 1 && a.nlines >= 4096;
+    // Lines per warp (measured on B200, tools/bench_pair2.py, tools/bench_pair_lpw.py).  A warp instruction costs the FP64
+    // pipe the same 2.25 cycles whether 2 or 32 lanes are active and a lone warp keeps its scheduler's pipe ~50 % busy,
+    // so the count that matters is warps per scheduler, and there is a cliff at one: with 148 SMs x 4 schedulers the
+    // lines are spread over at most 592 warps (4096 contebl points: 8 lines per warp = 512 warps 367 k eig/s, 6 = 683
+    // warps 241 k, 16 = 256 warps 312 k; 6144 points: 12 per warp 498 k, 10 per warp 416 k; continuation lines, 4096 x
+    // 50 omega: 8 per warp 367 k points/s, 16: 313 k, 4: 339 k).  Fewer lines per warp also means fewer divergent
+    // Gram-Schmidt events.  Single solves at 16 lines per warp (> 8880 points) gain nothing from the speculative step
+    // (9472 points: 708 k eig/s in the plain form against 681 k).  OSB_PAIR_LPW / OSB_PAIR_V1=1|0 override.
+    int lpw = (int)((a.nlines + 591) / 592);
+    if (const char *e = getenv("OSB_PAIR_LPW")) lpw = atoi(e);
+    lpw = std::min(16, std::max(1, lpw));
+    bool v1 = a.niter == 1 && lpw >= 16;
     if (const char *e = getenv("OSB_PAIR_V1")) v1 = atoi(e) != 0;
     if (v1) {
       const unsigned blocks = (unsigned)((2 * a.nlines + threads - 1) / threads);
@@ -1249,17 +1258,8 @@ cudaError_t launch_shoot(const ShootArgs &a, int integrator, int analytic_inprod
       if (nlaunch) *nlaunch += 1;
       return cudaGetLastError();
     }
-    // Lines per warp (measured on B200, tools/bench_pair2.py).  A warp instruction costs the FP64 pipe the same 2.25
-    // cycles whether 2 or 32 lanes are active and a lone warp already keeps its scheduler's pipe ~50 % busy, so the
-    // count that matters is warps per scheduler (148 SMs x 4): spread the lines over up to ~512 warps (continuation
-    // lines: fewer lines per warp also means fewer divergent Gram-Schmidt events, 4096 lines x 50 omega: 8 per warp
-    // 367 k points/s, 16: 313 k, 4: 339 k; 1024 lines: 2 per warp 170 k, 4: 147 k, 1: 137 k) or ~296 (single solves with the heavier Cash-Karp step).
-    // OSB_PAIR_LPW overrides.
     ShootArgs b = a;
-    const int64_t target = a.niter > 1 ? 512 : 296;
-    int lpw = (int)((a.nlines + target - 1) / target);
-    if (const char *e = getenv("OSB_PAIR_LPW")) lpw = atoi(e);
-    b.pair_lpw = std::min(16, std::max(1, lpw));
+    b.pair_lpw = lpw;
     const int64_t warps = (a.nlines + b.pair_lpw - 1) / b.pair_lpw;
     const unsigned blocks = (unsigned)((warps * 32 + threads - 1) / threads);
     if (integrator == OSB_INT_CK45) {
