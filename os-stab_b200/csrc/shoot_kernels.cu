@@ -398,7 +398,20 @@ __device__ __forceinline__ bool need_norm(const double (&u)[2][8], double thr, i
   if (ANALYTIC) {
     zd a = inprod<true>(u[0], u[0]), b = inprod<true>(u[1], u[1]), c = inprod<true>(u[0], u[1]);
     lhs = fma(c.x, c.x, c.y * c.y);
-    rhs = thr * (sqrt(fma(a.x, a.x, a.y * a.y)) * sqrt(fma(b.x, b.x, b.y * b.y)));
+    const double a2 = fma(a.x, a.x, a.y * a.y), b2 = fma(b.x, b.x, b.y * b.y);
+    // The two square roots below were 17 % of the continuation-line kernel's stall samples (every step, on the path to
+    // the branch).  The squared form of the same test decides all but a 1e-12-wide band around the threshold, where
+    // the rounding of the two forms (a few 1e-16 each) could differ; only there is the original expression evaluated.
+    // The quick form is only trusted while its right-hand side is far inside the normal range (relative rounding
+    // errors); overflow, underflow and NaN take the original expression: identical decisions.
+    {
+      const double l2 = lhs * lhs, r2 = (thr * thr) * (a2 * b2);
+      if (r2 > 1.0e-250 && r2 < 1.0e250) {
+        if (l2 > r2 * 1.000000000001) return true;
+        if (l2 < r2 * 0.999999999999) return false;
+      }
+    }
+    rhs = thr * (sqrt(a2) * sqrt(b2));
   } else {
     double aa = 0.0, bb = 0.0;
 #pragma unroll
