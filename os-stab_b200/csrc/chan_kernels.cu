@@ -312,7 +312,6 @@ __device__ void cta_lu(double2 *__restrict__ M, int n, int *ipiv, double2 *panel
   for (int i = tid; i < n; i += nt) perm[i] = i;  // (visible to thread 0 after the barrier that follows the first staging)
   const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   const int ldp = n + 16;
-  int *red_i = (int *)(red + 2 * (CH_THREADS_MAX / 32));
   for (int k0 = 0; k0 < n; k0 += CH_NB) {
     const int nb = min(CH_NB, n - k0), mp = n - k0;
     PROF_T0();
@@ -607,7 +606,6 @@ __device__ __noinline__ void cta_lu2(double2 *__restrict__ M, int n, int *ipiv, 
   const int lane = tid & 31, warp = tid >> 5, nwarp = nt >> 5;
   const int ldp = n + 16;
   const int g = lane >> 2, t4 = lane & 3;
-  int *red_i = (int *)(red + 2 * (CH_THREADS_MAX / 32));
   for (int K0 = 0; K0 < n; K0 += CH_NBO) {
     const int nbo = min(CH_NBO, n - K0);
     const int KE = K0 + nbo;  // end of the outer panel

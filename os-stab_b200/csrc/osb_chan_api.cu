@@ -68,7 +68,6 @@ namespace {
   } while (0)
 
 inline double &at(std::vector<double> &M, int N, int i, int j) { return M[(size_t)i * (N + 1) + j]; }
-inline double at(const std::vector<double> &M, int N, int i, int j) { return M[(size_t)i * (N + 1) + j]; }
 
 // first-derivative matrix of orrfdchan (FiniteD1, orrfdchan.f:1183-1215): central differences on the given grid,
 // one-sided in the first and last row
